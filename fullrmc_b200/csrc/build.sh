@@ -1,0 +1,22 @@
+#!/bin/bash
+# Builds libfullrmc_b200.so for sm_100a in-tree (fullrmc_b200/lib/).
+# -fmad=false: no FMA contraction anywhere (the distance/bin arithmetic must match the
+# reference's fp32 operation order bit for bit); IEEE sqrt/div are nvcc defaults and are
+# spelled out so that nobody "optimises" them away.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/../lib"
+mkdir -p "$OUT"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+       -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+       -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -fno-fast-math)
+if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
+OBJS=()
+for f in common stateless fullhist store; do
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
+  OBJS+=("$OUT/$f.o")
+done
+wait
+"$NVCC" -shared -o "$OUT/libfullrmc_b200.so" "${OBJS[@]}" -lcudart
+echo "built $OUT/libfullrmc_b200.so"

@@ -1,0 +1,208 @@
+// common.cuh -- shared device/host helpers for the fullrmc_b200 CUDA library (sm_100a).
+//
+// The arithmetic in this file is the parity contract: every operation is an explicit
+// round-to-nearest fp32 intrinsic (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn),
+// which nvcc never contracts into FMA, in the reference's exact evaluation order
+// (Extensions/pairs_distances.pyx:372-386, Extensions/pairs_histograms.pyx:58-63).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+
+#include "../../include/fullrmc_b200.h"
+
+namespace frmc {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char *fmt, ...);
+extern unsigned long long g_launch_count;   // kernels launched by this library
+
+#define FRMC_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            frmc::set_error("%s:%d %s failed: %s", __FILE__, __LINE__, #call,                \
+                            cudaGetErrorString(_e));                                         \
+            return FRMC_ECUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define FRMC_LAUNCH_CHECK()                                                                  \
+    do {                                                                                     \
+        ++frmc::g_launch_count;                                                              \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            frmc::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,            \
+                            cudaGetErrorString(_e));                                         \
+            return FRMC_ECUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define FRMC_REQUIRE(cond, code, ...)                                                        \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            frmc::set_error(__VA_ARGS__);                                                    \
+            return (code);                                                                   \
+        }                                                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- geometry modes
+// MODE selects the minimum-image variant at compile time so the inner loops carry no
+// run-time branches.
+enum : int {
+    MODE_IBC = 0,        // infinite boundaries: plain Cartesian difference (pairs_distances.pyx:443-471)
+    MODE_ORTHO_FAST = 1, // PBC, diagonal basis, all |frac diff| < 1.5  (sign-free wrap, 3 multiplies)
+    MODE_TRI_FAST = 2,   // PBC, general basis,  all |frac diff| < 1.5
+    MODE_ORTHO_GEN = 3,  // PBC, diagonal basis, unbounded fractional coordinates (floor/ceil wrap)
+    MODE_TRI_GEN = 4     // PBC, general basis,  unbounded fractional coordinates
+};
+
+struct Lattice {
+    float b[9];   // row-major basis, rows = lattice vectors (Engine.basisVectors)
+};
+
+// r-grid of one histogram + the d^2 thresholds equivalent to the reference's range test.
+// Because IEEE sqrt is correctly rounded and monotone,
+//   d = fl(sqrt(d2)) >= rmin  <=>  d2 >= t2min      and      d < rmax  <=>  d2 < t2max
+// with t2min/t2max found on the host by exact fp32 search (see sqrt_threshold()).
+struct GridParams {
+    float rmin, rmax, bin;
+    float t2min, t2max;
+    int hs;
+};
+
+// smallest non-negative fp32 t such that fl(sqrtf(t)) >= r
+float sqrt_threshold(float r);
+
+// pick the geometry mode for a coordinate set (host side)
+int choose_mode(const float *basis, int isPBC, const float *coords, int64_t n);
+int choose_mode_from_bounds(const float *basis, int isPBC, const float lo[3], const float hi[3]);
+
+// ---------------------------------------------------------------- exact fp32 device math
+#ifdef __CUDACC__
+
+// d - round(d) with round = half away from zero: floor(d+0.5) if d>0 else ceil(d-0.5)
+// (pairs_distances.pyx:31-32).  Works for any finite d.
+__device__ __forceinline__ float wrap_general(float d)
+{
+    float r = (d > 0.0f) ? floorf(__fadd_rn(d, 0.5f)) : ceilf(__fsub_rn(d, 0.5f));
+    return __fsub_rn(d, r);
+}
+
+// Same value as wrap_general for |d| < 1.5: there fl(|d|+0.5) < 2, so the image is 1 exactly
+// when fl(|d|+0.5) >= 1, i.e. |d| >= 0.5 - 2^-25 (0x3EFFFFFF; 0.5-2^-25+0.5 ties to even = 1.0),
+// and 0 otherwise.  No FRND (quarter-rate conversion pipe) in the hot loop.
+__device__ __forceinline__ float wrap_fast(float d)
+{
+    const float T = __int_as_float(0x3EFFFFFF);
+    float one = __int_as_float((__float_as_int(d) & 0x80000000) | 0x3F800000);   // copysign(1, d)
+    return (fabsf(d) >= T) ? __fsub_rn(d, one) : d;
+}
+
+// |wrap(d)| up to sign: enough for a diagonal basis, where only squares of the
+// components reach the distance.  Saves the copysign.
+__device__ __forceinline__ float wrap_fast_nosign(float d)
+{
+    const float T = __int_as_float(0x3EFFFFFF);
+    float a = fabsf(d);
+    return (a >= T) ? __fsub_rn(a, 1.0f) : a;
+}
+
+// squared real distance between two stored positions, reference operation order:
+//   real_x = (bx*b00 + by*b10) + bz*b20 ... ; d2 = (rx*rx + ry*ry) + rz*rz
+// (pairs_distances.pyx:380-386).  The result is symmetric in (i,j) because the wrap is odd.
+template <int MODE>
+__device__ __forceinline__ float dist2(float xi, float yi, float zi, float xj, float yj, float zj,
+                                       const Lattice &L)
+{
+    float dx = __fsub_rn(xi, xj);
+    float dy = __fsub_rn(yi, yj);
+    float dz = __fsub_rn(zi, zj);
+    float rx, ry, rz;
+    if (MODE == MODE_IBC) {
+        rx = dx; ry = dy; rz = dz;
+    } else if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
+        // diagonal basis: by*b10 and bz*b20 are (signed) zeros, adding them is exact
+        if (MODE == MODE_ORTHO_FAST) {
+            dx = wrap_fast_nosign(dx); dy = wrap_fast_nosign(dy); dz = wrap_fast_nosign(dz);
+        } else {
+            dx = wrap_general(dx); dy = wrap_general(dy); dz = wrap_general(dz);
+        }
+        rx = __fmul_rn(dx, L.b[0]);
+        ry = __fmul_rn(dy, L.b[4]);
+        rz = __fmul_rn(dz, L.b[8]);
+    } else {
+        if (MODE == MODE_TRI_FAST) {
+            dx = wrap_fast(dx); dy = wrap_fast(dy); dz = wrap_fast(dz);
+        } else {
+            dx = wrap_general(dx); dy = wrap_general(dy); dz = wrap_general(dz);
+        }
+        rx = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[0]), __fmul_rn(dy, L.b[3])), __fmul_rn(dz, L.b[6]));
+        ry = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[1]), __fmul_rn(dy, L.b[4])), __fmul_rn(dz, L.b[7]));
+        rz = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[2]), __fmul_rn(dy, L.b[5])), __fmul_rn(dz, L.b[8]));
+    }
+    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+}
+
+// real-space difference vector point - other (PBC) with the reference's operation order
+template <bool PBC>
+__device__ __forceinline__ void diff3(float px, float py, float pz, float cx, float cy, float cz,
+                                      const Lattice &L, float &rx, float &ry, float &rz)
+{
+    float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
+    if (PBC) {
+        dx = wrap_general(dx); dy = wrap_general(dy); dz = wrap_general(dz);
+        rx = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[0]), __fmul_rn(dy, L.b[3])), __fmul_rn(dz, L.b[6]));
+        ry = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[1]), __fmul_rn(dy, L.b[4])), __fmul_rn(dz, L.b[7]));
+        rz = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[2]), __fmul_rn(dy, L.b[5])), __fmul_rn(dz, L.b[8]));
+    } else {
+        rx = dx; ry = dy; rz = dz;
+    }
+}
+
+__device__ __forceinline__ bool in_range(float d2, const GridParams &g)
+{
+    return (d2 >= g.t2min) && (d2 < g.t2max);
+}
+
+// bin index of an in-range pair: (int)((d - rmin) / bin), fp32, truncation
+// (pairs_histograms.pyx:63)
+__device__ __forceinline__ int bin_index(float d2, const GridParams &g)
+{
+    float d = __fsqrt_rn(d2);
+    return (int)__fdiv_rn(__fsub_rn(d, g.rmin), g.bin);
+}
+
+// bin rule applied to an already computed distance (the *_dists entry points)
+__device__ __forceinline__ bool bin_of_distance(float d, const GridParams &g, int &b)
+{
+    if (d < g.rmin) return false;
+    if (d >= g.rmax) return false;
+    b = (int)__fdiv_rn(__fsub_rn(d, g.rmin), g.bin);
+    return true;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- per-device context
+// One stream and a few grow-only scratch buffers per device, so the stateless entry
+// points do not pay cudaMalloc/cudaFree on every call.
+struct DeviceCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    static const int NBUF = 12;
+    void *buf[NBUF] = {nullptr};
+    size_t cap[NBUF] = {0};
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+    int sm_count = 0;
+};
+
+// returns nullptr (and sets the error string) on failure
+DeviceCtx *get_ctx(int dev);
+// grow-only device scratch buffer `slot`; returns nullptr on failure
+void *ctx_buffer(DeviceCtx *c, int slot, size_t bytes);
+void *ctx_pinned(DeviceCtx *c, size_t bytes);
+
+}  // namespace frmc

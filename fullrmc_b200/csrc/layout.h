@@ -1,0 +1,51 @@
+// layout.h -- the device-resident atom store layout (host-side description).
+//
+// Atoms are kept ELEMENT-SORTED (stable, so original order is preserved inside an
+// element) in one array of 16-byte records
+//     float4 { x, y, z, meta }      meta = (molecule_rank << 8) | element      (u32 bits)
+// plus a parallel u32 array `orig` with the atom's original index.  Each element's
+// segment is padded to a multiple of SEG_PAD records with NaN coordinates
+// (meta = 0xFFFFFFFF, orig = 0xFFFFFFFF): NaN fails every range test, so padding
+// never contributes and no kernel needs a bounds check inside a segment.
+//
+// Why sorted: a (tile I, tile J) pair then touches one unordered element pair, so the
+// full-histogram kernel needs only 4 x histSize shared-memory counters per CTA
+// ({intra,inter} x {[a,b],[b,a]}) instead of 2 x nEl^2 x histSize, whatever nEl is.
+// The reference's ORDERED output ([el[i], el[j]] with i<j in original order,
+// pairs_histograms.pyx:289-335) is recovered from `orig`.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace frmc {
+
+static const int SEG_PAD = 256;
+static const uint32_t PAD_META = 0xFFFFFFFFu;
+
+struct HostLayout {
+    int64_t n = 0;           // real atoms
+    int64_t npad = 0;        // records including padding
+    int nEl = 0;
+    std::vector<int64_t> seg_start;   // [nEl+1] padded start position of each element segment
+    std::vector<int64_t> seg_count;   // [nEl]   real atoms per element
+    std::vector<float> rec;           // [npad*4] x,y,z,meta(bits)
+    std::vector<uint32_t> orig;       // [npad]  original index or 0xFFFFFFFF
+    std::vector<int32_t> inv;         // [n]     original index -> position
+    float lo[3], hi[3];               // coordinate bounds (mode selection)
+    bool finite = true;
+};
+
+// Builds the sorted layout.  Returns 0 or a negative FRMC_E* code (error string set).
+int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, HostLayout &out);
+
+// One unit of full-histogram work: I-tile [i0, i0 + 256*ni) x J-range [j0, j1) (padded positions).
+// ea/eb are the (segment) elements of the two ranges; when ea == eb only pairs p<q count.
+struct WorkItem {
+    int32_t i0, ni, j0, j1;
+    int32_t ea, eb, tri, pad;
+};
+
+// Builds the balanced upper-triangle work list; items with index % nshards == shard are kept.
+void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, int nshards, std::vector<WorkItem> &items);
+
+}  // namespace frmc

@@ -1,0 +1,168 @@
+"""DeviceStore -- Python face of the stateful C ABI (``frmc_store_*``, ``frmc_propose`` ...).
+
+One store holds the system (fractional coordinates, molecule and element indexes) on one
+GPU in the element-sorted 16-byte-record layout (csrc/layout.h), any number of r-grids
+(each with its running integer histograms) and the models (constraints) evaluated on them.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+from .model import ModelSpec
+
+_F32, _I32 = np.float32, np.int32
+
+
+class DeviceStore(object):
+    """Device-resident coordinate store + running pair histograms.
+
+    :Parameters:
+        #. boxCoords (float32 (N,3)): engine.boxCoordinates (fractional; Cartesian when not isPBC).
+        #. basis (float32 (3,3)): engine.basisVectors.
+        #. isPBC (bool): engine.isPBC.
+        #. moleculeIndex, elementIndex (int32 (N,)): engine.moleculesIndex / elementsIndex.
+        #. numberOfElements (int): engine.numberOfElements.
+        #. device (None, int): CUDA device; default from $FULLRMC_B200_DEVICE / $LOCAL_RANK / 0.
+    """
+
+    def __init__(self, boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, device=None):
+        self._lib = L.load_library()
+        self._handle = None
+        coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
+        basis = L.as_array(basis, "basis", _F32, 2)
+        mol = L.as_array(moleculeIndex, "moleculeIndex", _I32, 1)
+        el = L.as_array(elementIndex, "elementIndex", _I32, 1)
+        if coords.shape[1] != 3 or basis.shape != (3, 3):
+            raise ValueError("boxCoords must be (N,3) and basis (3,3)")
+        if mol.shape[0] != coords.shape[0] or el.shape[0] != coords.shape[0]:
+            raise ValueError("moleculeIndex/elementIndex length must equal the number of atoms")
+        self.device = L.device_index() if device is None else int(device)
+        self.numberOfAtoms = coords.shape[0]
+        self.numberOfElements = int(numberOfElements)
+        self.isPBC = bool(isPBC)
+        h = self._lib.frmc_store_create(self.device, coords.shape[0], L.ptr(coords, L.c_f32p), L.ptr(basis, L.c_f32p),
+                                        int(self.isPBC), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p),
+                                        self.numberOfElements)
+        if not h:
+            raise L.FullrmcB200Error("frmc_store_create: " + L.last_error())
+        self._handle = ctypes.c_void_p(h)
+        self._grids = []          # (rmin, rmax, bin, hs)
+        self._models = []         # ModelSpec
+        self._keep = []           # arrays referenced by descriptors during frmc_model_add
+        self._chi2 = np.zeros(8, dtype=_F32)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if self._handle is not None:
+            self._lib.frmc_store_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) the store launches on."""
+        return int(self._lib.frmc_store_stream(self._handle) or 0)
+
+    # ------------------------------------------------------------------ configuration
+    def add_grid(self, minDistance, maxDistance, bin, histSize):
+        g = L.check(self._lib.frmc_grid_add(self._handle, float(_F32(minDistance)), float(_F32(maxDistance)),
+                                            float(_F32(bin)), int(histSize)), "add_grid")
+        self._grids.append((float(minDistance), float(maxDistance), float(bin), int(histSize)))
+        return g
+
+    def add_model(self, grid, spec):
+        if not isinstance(spec, ModelSpec):
+            raise TypeError("spec must be a ModelSpec")
+        desc, keep = spec.build_desc()
+        m = L.check(self._lib.frmc_model_add(self._handle, int(grid), ctypes.byref(desc)), "add_model")
+        self._models.append(spec)
+        return m
+
+    def set_scale(self, model, scale):
+        L.check(self._lib.frmc_model_set_scale(self._handle, int(model), float(_F32(scale))), "set_scale")
+
+    @property
+    def n_models(self):
+        return len(self._models)
+
+    # ------------------------------------------------------------------ compute_data
+    def compute_data(self):
+        """Full histogram of every grid + totals; returns float32 chi^2 per model."""
+        L.check(self._lib.frmc_compute_data(self._handle, L.ptr(self._chi2, L.c_f32p)), "compute_data")
+        return self._chi2[:self.n_models].copy()
+
+    def compute_data_shard(self, shard, nshards):
+        """This rank's share of the tile work list only (device-resident partial counts)."""
+        L.check(self._lib.frmc_compute_data_shard(self._handle, int(shard), int(nshards)), "compute_data_shard")
+
+    def counts_pointer(self, grid):
+        """(device pointer, number of int64 cells) of the grid's committed counts [2][nEl*nEl][hs]."""
+        n = ctypes.c_int64(0)
+        p = self._lib.frmc_grid_counts_ptr(self._handle, int(grid), ctypes.byref(n))
+        if not p:
+            raise L.FullrmcB200Error("grid_counts_ptr: " + L.last_error())
+        return int(p), int(n.value)
+
+    def finalize_data(self):
+        L.check(self._lib.frmc_finalize_data(self._handle, L.ptr(self._chi2, L.c_f32p)), "finalize_data")
+        return self._chi2[:self.n_models].copy()
+
+    # ------------------------------------------------------------------ per-move path
+    def propose(self, indexes, movedBoxCoordinates):
+        """compute_before_move + compute_after_move in one pass; returns chi^2-after per model."""
+        idx = np.ascontiguousarray(indexes, dtype=_I32)
+        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
+        if moved.shape != (idx.shape[0], 3):
+            raise ValueError("movedBoxCoordinates must be (k,3)")
+        L.check(self._lib.frmc_propose(self._handle, L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(moved, L.c_f32p),
+                                       L.ptr(self._chi2, L.c_f32p)), "propose")
+        return self._chi2[:self.n_models].copy()
+
+    def accept(self):
+        L.check(self._lib.frmc_accept(self._handle), "accept")
+
+    def reject(self):
+        L.check(self._lib.frmc_reject(self._handle), "reject")
+
+    # ------------------------------------------------------------------ export
+    def export_data(self, grid=0):
+        """The reference's data["intra"], data["inter"]: float32 (nEl,nEl,hs) arrays."""
+        hs = self._grids[grid][3]
+        nEl = self.numberOfElements
+        hintra = np.empty((nEl, nEl, hs), dtype=_F32)
+        hinter = np.empty((nEl, nEl, hs), dtype=_F32)
+        L.check(self._lib.frmc_export_data(self._handle, int(grid), L.ptr(hintra, L.c_f32p), L.ptr(hinter, L.c_f32p)),
+                "export_data")
+        return hintra, hinter
+
+    def export_total(self, model, staged=False):
+        out = np.empty(self._models[model].experimental.shape[0], dtype=_F32)
+        L.check(self._lib.frmc_export_total(self._handle, int(model), int(bool(staged)), L.ptr(out, L.c_f32p)),
+                "export_total")
+        return out
+
+    def get_coords(self):
+        out = np.empty((self.numberOfAtoms, 3), dtype=_F32)
+        L.check(self._lib.frmc_store_get_coords(self._handle, L.ptr(out, L.c_f32p)), "get_coords")
+        return out
+
+    def set_coords(self, boxCoords, basis=None):
+        coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
+        b = None if basis is None else L.as_array(basis, "basis", _F32, 2)
+        L.check(self._lib.frmc_store_set_coords(self._handle, L.ptr(coords, L.c_f32p), L.ptr(b, L.c_f32p)), "set_coords")
+
+    @property
+    def edge_overflow(self):
+        return int(self._lib.frmc_store_edge_overflow(self._handle))

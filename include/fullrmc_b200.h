@@ -1,0 +1,196 @@
+/*
+ * fullrmc_b200.h -- C ABI of the B200-native pair-histogram backend for fullrmc.
+ *
+ * This is the drop-in boundary.  Every entry point takes
+ * plain pointers and sizes (no torch / numpy / C++ types), returns 0 on success
+ * and a negative FRMC_E* code on failure; the message is available from
+ * frmc_last_error().  No exception crosses this boundary.  Handles are not
+ * thread-safe (one host thread per store, like the reference Engine).
+ *
+ * Citations are relative to the reference tree (bachiraoun/fullrmc v4.1.0).
+ *
+ * Arithmetic contract: distances and bin indices are computed in fp32 with the
+ * reference's exact operation order, no FMA contraction, IEEE sqrt and divide,
+ * round-half-away-from-zero minimum image (Extensions/pairs_distances.pyx:31-32),
+ * bin rule `d<min skip; d>=max skip; (int)((d-min)/bin)`
+ * (Extensions/pairs_histograms.pyx:58-63).  Counts are integers on the device
+ * and converted to float32 at this boundary (exact below 2^24 per cell, where the
+ * reference's own `+= 1.0f` saturates).  A bin index that rounds up to histSize
+ * (undefined behaviour in the reference, boundscheck(False)) is dropped and
+ * counted in *edge_overflow.
+ */
+#ifndef FULLRMC_B200_H
+#define FULLRMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRMC_OK 0
+#define FRMC_EINVAL (-1)    /* bad argument (shape, range, NULL) */
+#define FRMC_ECUDA (-2)     /* CUDA runtime error */
+#define FRMC_ENOMEM (-3)    /* allocation failure */
+#define FRMC_ESTATE (-4)    /* call not valid in the handle's current state */
+#define FRMC_ELIMIT (-5)    /* exceeds a documented limit (elements, molecules, group size) */
+
+#define FRMC_MAX_ELEMENTS 16      /* distinct element indices per store */
+#define FRMC_MAX_GROUP 64         /* atoms moved by one proposal */
+#define FRMC_MAX_GRIDS 4          /* r-grids per store */
+#define FRMC_MAX_MODELS 8         /* models (constraints) per store */
+
+/* model kinds: which constraint-level total is produced from the histogram */
+#define FRMC_KIND_PDF 0   /* G(r)   PairDistributionConstraints.py:847-895   */
+#define FRMC_KIND_PCF 1   /* g(r)   PairCorrelationConstraints.py:126-169    */
+#define FRMC_KIND_SQ 2    /* S(Q)   StructureFactorConstraints.py:780-822    */
+#define FRMC_KIND_RSQ 3   /* S(Q)-1 StructureFactorConstraints.py:1253-1260  */
+
+const char *frmc_last_error(void);
+const char *frmc_version(void);
+/* number of visible CUDA devices, or a negative error code (no CPU fallback exists) */
+int frmc_device_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Stateless entry points: one per reference extension function on the hot path.
+ * Inputs are HOST pointers, borrowed for the duration of the call; outputs are HOST
+ * buffers owned by the caller.  coords are C-contiguous [n,3] fp32 (fractional when
+ * isPBC, Cartesian otherwise); basis is [3,3] row-major, rows = lattice vectors.
+ * ---------------------------------------------------------------------------------- */
+
+/* Generic "k points against n coords" kernel behind the ten functions of
+ * Extensions/pairs_distances.pyx (def wrappers :483-1024, cdef kernels :45-471).
+ *   points     [k,3]                 explicit points (from_index == NULL) or ignored
+ *   from_index [k] or NULL           take point t = coords[from_index[t]]
+ *   start      [k] or NULL           first coords row written for point t (allAtoms=False -> index)
+ *   ibc_sign   +1: point-coords[i] (every difference kernel of the reference, :142-270)
+ *              -1: coords[i]-point (sign used inside the IBC to-point distance kernel :414-434;
+ *                  only visible when want_diff=1)
+ *   want_diff  0: distances, out is [n,k]; 1: difference vectors, out is [n,3,k]
+ * Rows below start[t] are written as 0 (the reference leaves them uninitialised). */
+int frmc_points_to_coords(int dev, const float *points, const int32_t *from_index, const int64_t *start,
+                          int64_t k, const float *coords, int64_t n, const float *basis, int isPBC,
+                          int ibc_sign, int want_diff, float *out);
+
+/* Extensions/pairs_distances.pyx:483-525 from_to_points_differences: row-wise
+ * boundaryConditions(pointsTo[i]-pointsFrom[i]); out is [n,3]. */
+int frmc_from_to_points_differences(int dev, const float *points_from, const float *points_to, int64_t n,
+                                    const float *basis, int isPBC, float *out);
+
+/* Extensions/pairs_histograms.pyx:150-217 multiple_pairs_histograms_coords.
+ * hintra/hinter: [nEl,nEl,hs] fp32, overwritten (the reference returns fresh np.zeros arrays). */
+int frmc_multiple_pairs_histograms_coords(int dev, const int32_t *indexes, int64_t k, const float *coords,
+                                          int64_t n, const float *basis, int isPBC, const int32_t *mol,
+                                          const int32_t *el, int nEl, float rmin, float rmax, float bin,
+                                          int hs, int allAtoms, float *hintra, float *hinter,
+                                          uint64_t *edge_overflow);
+
+/* Extensions/pairs_histograms.pyx:289-335 full_pairs_histograms_coords (ordered upper
+ * triangle [el[i],el[j]], i<j).  shard/nshards split the tile work list across callers
+ * (one process per GPU); each caller gets its partial histogram, the sum over shards is
+ * the full result.  nshards=1 for the plain drop-in call. */
+int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
+                                      const int32_t *mol, const int32_t *el, int nEl, float rmin,
+                                      float rmax, float bin, int hs, int shard, int nshards,
+                                      float *hintra, float *hinter, uint64_t *edge_overflow);
+
+/* Extensions/pairs_histograms.pyx:225-281 multiple_pairs_histograms_dists; distances is
+ * [n,k] row-major, column t belongs to indexes[t].  (:343-383 full_* = arange, allAtoms=0) */
+int frmc_multiple_pairs_histograms_dists(int dev, const int32_t *indexes, int64_t k, const float *distances,
+                                         int64_t n, const int32_t *mol, const int32_t *el, int nEl,
+                                         float rmin, float rmax, float bin, int hs, int allAtoms,
+                                         float *hintra, float *hinter, uint64_t *edge_overflow);
+
+/* Extensions/pairs_histograms.pyx:77-141 single_pairs_histograms: IN-PLACE update of
+ * hintra/hinter from one precomputed distance row (element stride dstride). */
+int frmc_single_pairs_histograms(int dev, int32_t atomIndex, const float *distances, int64_t dstride,
+                                 int64_t n, const int32_t *mol, const int32_t *el, int nEl, int hs,
+                                 float *hintra, float *hinter, float rmin, float rmax, float bin,
+                                 int allAtoms, uint64_t *edge_overflow);
+
+/* Extensions/reciprocal_space.pyx:82-109 Gr_to_sq and :42-73 gr_to_sq (double-precision
+ * term, fp32 accumulate, r in index order) and :118-145 sq_to_Gr (documented math; the
+ * reference function itself raises TypeError, so it has no oracle). */
+int frmc_Gr_to_sq(int dev, const float *distances, const float *Gr, int64_t n, const float *qrange, int64_t m,
+                  float *sq);
+int frmc_gr_to_sq(int dev, const float *distances, const float *gr, int64_t n, const float *qrange, int64_t m,
+                  float rho, float *sq);
+int frmc_sq_to_Gr(int dev, const float *qvalues, const float *rvalues, const float *sq, int64_t m, int64_t n,
+                  float *Gr);
+
+/* ------------------------------------------------------------------------------------
+ * Stateful fast path: device-resident coordinate store + running histograms.
+ * Replaces compute_data / compute_before_move / compute_after_move / accept_move /
+ * reject_move of the three constraints (PairDistributionConstraints.py:1001-1166,
+ * PairCorrelationConstraints.py:263-392, StructureFactorConstraints.py:933-1096).
+ * ---------------------------------------------------------------------------------- */
+typedef struct frmc_store frmc_store;
+
+/* Constraint-level constants for one model, prepared on the host with the reference's
+ * own numpy expressions so the device epilogue can mirror them bit for bit.
+ * All pointers are HOST pointers, copied at frmc_model_add time. */
+typedef struct frmc_model_desc {
+    int32_t kind;           /* FRMC_KIND_* */
+    int32_t n_pairs;        /* element pairs in sorted(combinations_with_replacement) order */
+    const int32_t *pair_a;  /* [n_pairs] element index idi (PairDistributionConstraints.py:864) */
+    const int32_t *pair_b;  /* [n_pairs] element index idj */
+    const float *pair_w;    /* [n_pairs] w_ij as float32 (:487-489) */
+    const float *pair_D;    /* [n_pairs] D_ij = float32(N_ij / volume) (:867-874) */
+    const float *shell_volumes; /* [hs]  (:758) */
+    const float *prefactor;     /* [hs] (4.*PI*shellCenters*rho0) as numpy evaluates it (:881); unused for PCF unless scale!=1 */
+    const float *shape;         /* [hs] or NULL, shape-function array subtracted (:883-884) */
+    float scale;                /* fitted scale factor applied when != 1 (:886-888) */
+    int32_t n_out;              /* length of the model total: hs (PDF/PCF) or nQ (SQ/RSQ) */
+    const float *experimental;  /* [n_out] experimental data */
+    const float *data_weights;  /* [n_out] or NULL (usedDataWeights, :835-838) */
+    const float *gr2sq;         /* [hs,n_out] row-major Gr2SqMatrix (SQ/RSQ), else NULL (StructureFactorConstraints.py:302-312) */
+    int32_t sq_exact;           /* 1: sequential fp32 accumulation over r (bit-exact vs numpy, :772-773); 0: split-r fast sum */
+} frmc_model_desc;
+
+frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const float *basis, int isPBC,
+                              const int32_t *mol, const int32_t *el, int nEl);
+void frmc_store_destroy(frmc_store *s);
+/* re-upload all coordinates (set_pdb / set_boundary_conditions / external edits); invalidates data */
+int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis);
+int frmc_store_get_coords(frmc_store *s, float *coords_out);
+/* CUDA stream the store launches on (a cudaStream_t), so callers can time with events on it */
+void *frmc_store_stream(frmc_store *s);
+
+/* register an r-grid (minDistance, maxDistance, bin, histSize); returns grid id >= 0 */
+int frmc_grid_add(frmc_store *s, float rmin, float rmax, float bin, int hs);
+/* register a model on a grid; returns model id >= 0 */
+int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *desc);
+int frmc_model_set_scale(frmc_store *s, int model, float scale);
+
+/* compute_data: full histogram of every grid (tiled kernel), totals and chi^2 per model.
+ * chi2 [n_models] fp32 (np.add.reduce result), may be NULL. */
+int frmc_compute_data(frmc_store *s, float *chi2);
+/* sharded variant for one-process-per-GPU runs: computes this caller's partial integer
+ * histograms only (device resident); combine with frmc_grid_counts_ptr + an NCCL
+ * allreduce issued by the host plumbing, then call frmc_finalize_data. */
+int frmc_compute_data_shard(frmc_store *s, int shard, int nshards);
+/* DEVICE pointer to grid's committed counts: int64 [2][nEl*nEl][hs] (0=intra,1=inter) */
+void *frmc_grid_counts_ptr(frmc_store *s, int grid, int64_t *n_cells);
+int frmc_finalize_data(frmc_store *s, float *chi2);
+
+/* compute_before_move + compute_after_move fused: group `indexes` (original atom indices)
+ * moves to `moved` ([k,3] box coordinates, not wrapped).  One pass over the store forms
+ * after-minus-before for every grid, then totals and chi^2 per model.  The proposal stays
+ * staged until frmc_accept / frmc_reject. */
+int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *moved, float *chi2_after);
+int frmc_accept(frmc_store *s);
+int frmc_reject(frmc_store *s);
+
+/* export committed histograms as the reference's data["intra"], data["inter"] (fp32 [nEl,nEl,hs]) */
+int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter);
+/* export the staged (after-move) or committed model total (length n_out) */
+int frmc_export_total(frmc_store *s, int model, int staged, float *out);
+/* events where the fp32 bin index rounded up to histSize (dropped), summed over the store's life */
+uint64_t frmc_store_edge_overflow(frmc_store *s);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t frmc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FULLRMC_B200_H */

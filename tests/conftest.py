@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ref_modules():
+    """The reference's own compiled Cython modules (oracle/_ref), or None when not built.
+    Built here from /root/reference by oracle/build_ref.py; travels to the GPU box as .so files."""
+    from oracle import build_ref
+    if not build_ref.is_built():
+        build_ref.build()
+    return build_ref.load()
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import pairhist
+    pairhist.build()
+    return pairhist
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")

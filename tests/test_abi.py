@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, and the Python mirrors validate arguments like the Cython wrappers."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "fullrmc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(frmc_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fullrmc_b200 import _lib
+    lib = _lib.load_library()
+    names = _header_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(lib, name), "library does not export %s" % name
+    # and the ctypes table binds exactly the header's functions
+    assert sorted(_lib.SIGNATURES.keys()) == names
+
+
+def test_model_desc_layout_matches_header():
+    """field order of the ctypes mirror follows struct frmc_model_desc"""
+    from fullrmc_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "fullrmc_b200.h")).read()
+    body = re.search(r"typedef struct frmc_model_desc \{(.*?)\} frmc_model_desc;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"([a-zA-Z0-9_]+)\s*;", body)
+    assert fields == [f[0] for f in _lib.ModelDesc._fields_]
+
+
+def test_version_and_error_strings():
+    from fullrmc_b200 import _lib
+    lib = _lib.load_library()
+    assert b"sm_100a" in lib.frmc_version()
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_argument_validation_mirrors_cython():
+    """None -> TypeError, wrong dtype / ndim -> ValueError (Cython typed-buffer behaviour)"""
+    from fullrmc_b200.Core import pairs_histograms as ph
+    n = 10
+    box = np.zeros((n, 3), dtype=np.float32)
+    basis = np.eye(3, dtype=np.float32)
+    mol = np.zeros(n, dtype=np.int32)
+    el = np.zeros(n, dtype=np.int32)
+    kw = dict(basis=basis, isPBC=True, moleculeIndex=mol, elementIndex=el, numberOfElements=1,
+              minDistance=0.0, maxDistance=1.0, bin=0.1, histSize=10)
+    with pytest.raises(TypeError):
+        ph.full_pairs_histograms_coords(boxCoords=None, **kw)
+    with pytest.raises(ValueError):
+        ph.full_pairs_histograms_coords(boxCoords=box.astype(np.float64), **kw)
+    with pytest.raises(ValueError):
+        ph.full_pairs_histograms_coords(boxCoords=box.reshape(-1), **kw)
+    with pytest.raises(ValueError):
+        ph.full_pairs_histograms_coords(boxCoords=box, **dict(kw, elementIndex=el.astype(np.int64)))
+    with pytest.raises(ValueError):
+        ph.full_pairs_histograms_coords(boxCoords=box, **dict(kw, moleculeIndex=mol[:5]))
+
+
+def test_no_cpu_fallback_without_gpu():
+    """without a CUDA device every compute entry point fails loudly"""
+    from fullrmc_b200 import _lib
+    lib = _lib.load_library()
+    if lib.frmc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from fullrmc_b200.Core import pairs_histograms as ph
+    n = 10
+    rng = np.random.default_rng(0)
+    kw = dict(basis=np.eye(3, dtype=np.float32), isPBC=True, moleculeIndex=np.zeros(n, dtype=np.int32),
+              elementIndex=np.zeros(n, dtype=np.int32), numberOfElements=1, minDistance=0.0, maxDistance=1.0,
+              bin=0.1, histSize=10)
+    with pytest.raises(RuntimeError):
+        ph.full_pairs_histograms_coords(boxCoords=rng.random((n, 3), dtype=np.float32), **kw)
+    from fullrmc_b200.store import DeviceStore
+    with pytest.raises(RuntimeError):
+        DeviceStore(rng.random((n, 3), dtype=np.float32), kw["basis"], True, kw["moleculeIndex"], kw["elementIndex"], 1)
+
+
+def test_product_does_not_import_oracle():
+    """the shipped package never references the oracle"""
+    pkg = os.path.join(ROOT, "fullrmc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "pairhist_oracle" not in text, f
