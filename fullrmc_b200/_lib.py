@@ -81,6 +81,8 @@ SIGNATURES = {
     "frmc_export_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_export_total": (_I, [_VP, _I, _I, c_f32p]),
     "frmc_store_edge_overflow": (ctypes.c_uint64, [_VP]),
+    "frmc_store_set_timing": (_I, [_VP, _I]),
+    "frmc_store_get_timing": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double), c_u64p]),
 }
 
 

@@ -18,5 +18,5 @@ for f in common stateless fullhist store; do
   OBJS+=("$OUT/$f.o")
 done
 wait
-"$NVCC" -shared -o "$OUT/libfullrmc_b200.so" "${OBJS[@]}" -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libfullrmc_b200.so" "${OBJS[@]}" -lcudart
 echo "built $OUT/libfullrmc_b200.so"

@@ -334,25 +334,24 @@ chi2_kernel(const ModelDev *__restrict__ models, int n_models, float *__restrict
         const int l = base + group;
         const bool live = l < nl;
         const int off = live ? leaf_off[l] : 0, len = live ? leaf_len[l] : 0;
-        float res;
-        if (len < 8) {
-            res = 0.0f;
-            if (lane8 == 0) for (int i = 0; i < len; ++i) res = __fadd_rn(res, v[off + i]);
-            // keep the warp converged for the shuffles below
-            float dummy = 0.f;
-            dummy = __shfl_xor_sync(0xFFFFFFFFu, dummy, 1); dummy = __shfl_xor_sync(0xFFFFFFFFu, dummy, 2);
-            dummy = __shfl_xor_sync(0xFFFFFFFFu, dummy, 4);
-        } else {
-            const int main_len = len - (len % 8);
-            float r = v[off + lane8];
+        // leaves shorter than 8 (only a whole array with n < 8) are summed sequentially from 0;
+        // otherwise lane j owns accumulator r[j].  The shuffles sit on ONE converged code path.
+        const bool big = len >= 8;
+        const int main_len = big ? len - (len % 8) : 0;
+        float r = 0.0f;
+        if (big) {
+            r = v[off + lane8];
             for (int i = 8; i < main_len; i += 8) r = __fadd_rn(r, v[off + i + lane8]);
-            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
-            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
-            r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
-            res = r;
-            if (lane8 == 0) for (int i = main_len; i < len; ++i) res = __fadd_rn(res, v[off + i]);
         }
-        if (live && lane8 == 0) leaf_sum[l] = res;
+        __syncwarp();
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
+        float res = big ? r : 0.0f;
+        if (live && lane8 == 0) {
+            for (int i = main_len; i < len; ++i) res = __fadd_rn(res, v[off + i]);
+            leaf_sum[l] = res;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) chi2_out[m] = pairwise_combine(leaf_sum, n);
@@ -388,6 +387,7 @@ struct frmc_store {
     int32_t *d_inv = nullptr;
     WorkItem *d_items = nullptr;
     int n_items = 0, R = 1;
+    int items_shard = -1, items_nshards = -1;   // which slice of the work list d_items holds
     int64_t chunkJ = 256;
     HostLayout lay;                  // rec freed after upload; segments + inv kept
     int *d_next = nullptr;
@@ -405,7 +405,47 @@ struct frmc_store {
     float chi2_staged[FRMC_MAX_MODELS];
     float chi2_committed[FRMC_MAX_MODELS];
     uint64_t overflow_total = 0;
+    // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Pending { int which; cudaEvent_t a, b; };
+    std::vector<Pending> ev_pending;
+    double kernel_ms[4] = {0, 0, 0, 0};
+    uint64_t kernel_launches[4] = {0, 0, 0, 0};
 };
+
+enum { TIME_DELTA = 0, TIME_FULL = 1, TIME_EPILOGUE = 2, TIME_COMMIT = 3 };
+
+static cudaEvent_t timing_begin(frmc_store *s)
+{
+    if (!s->timing) return nullptr;
+    cudaEvent_t e;
+    if (!s->ev_pool.empty()) { e = s->ev_pool.back(); s->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, s->stream);
+    return e;
+}
+
+static void timing_end(frmc_store *s, int which, cudaEvent_t a)
+{
+    if (!a) return;
+    cudaEvent_t b;
+    if (!s->ev_pool.empty()) { b = s->ev_pool.back(); s->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&b) != cudaSuccess) { s->ev_pool.push_back(a); return; }
+    cudaEventRecord(b, s->stream);
+    s->ev_pending.push_back({which, a, b});
+}
+
+// call after the stream has been synchronised
+static void timing_flush(frmc_store *s)
+{
+    for (auto &p : s->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { s->kernel_ms[p.which] += ms; s->kernel_launches[p.which]++; }
+        s->ev_pool.push_back(p.a); s->ev_pool.push_back(p.b);
+    }
+    s->ev_pending.clear();
+}
 
 static GridSet make_gridset(frmc_store *s)
 {
@@ -445,6 +485,7 @@ static int upload_layout(frmc_store *s, const float *coords)
 
 static int upload_items(frmc_store *s, int shard, int nshards)
 {
+    if (s->d_items && s->items_shard == shard && s->items_nshards == nshards) return FRMC_OK;
     std::vector<WorkItem> items;
     choose_tiling(s->npad, s->ctx->sm_count, s->R, s->chunkJ);
     build_work_items(s->lay, s->R, s->chunkJ, shard, nshards, items);
@@ -454,6 +495,7 @@ static int upload_items(frmc_store *s, int shard, int nshards)
     if (!items.empty())
         FRMC_CUDA(cudaMemcpyAsync(s->d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    s->items_shard = shard; s->items_nshards = nshards;
     return FRMC_OK;
 }
 
@@ -484,6 +526,7 @@ static int launch_epilogue(frmc_store *s)
         max_out = std::max(max_out, m.dev.n_out);
         if (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ) max_q = std::max(max_q, m.dev.n_out);
     }
+    cudaEvent_t t0 = timing_begin(s);
     dim3 g1((unsigned)((max_hs + 127) / 128), (unsigned)nm);
     rfun_kernel<<<g1, 128, 0, s->stream>>>(s->d_models, nm, gs, s->nEl);
     FRMC_LAUNCH_CHECK();
@@ -496,6 +539,7 @@ static int launch_epilogue(frmc_store *s)
     if (smem > 40 * 1024) FRMC_CUDA(cudaFuncSetAttribute(chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     chi2_kernel<<<nm, 256, smem, s->stream>>>(s->d_models, nm, s->h_chi2);
     FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_EPILOGUE, t0);
     return FRMC_OK;
 }
 
@@ -557,6 +601,8 @@ void frmc_store_destroy(frmc_store *s)
     for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); }
     cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_inv); cudaFree(s->d_items); cudaFree(s->d_next);
     cudaFree(s->d_overflow); cudaFree(s->d_models); cudaFree(s->d_prop_in); cudaFree(s->d_prop);
+    for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->h_prop) cudaFreeHost(s->h_prop);
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -572,6 +618,7 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
     if (basis) for (int i = 0; i < 9; ++i) s->L.b[i] = basis[i];
     int rc = upload_layout(s, coords);
     if (rc) return rc;
+    s->items_shard = s->items_nshards = -1;
     for (auto &g : s->grids) g.valid = false;
     s->state = 0;
     GridSet gs = make_gridset(s);
@@ -678,8 +725,6 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
     FRMC_REQUIRE(nshards >= 1 && shard >= 0 && shard < nshards, FRMC_EINVAL, "bad shard %d of %d", shard, nshards);
     FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
     FRMC_CUDA(cudaSetDevice(s->dev));
-    static thread_local int last_shard = 0, last_nshards = 1;
-    (void)last_shard; (void)last_nshards;
     int rc = upload_items(s, shard, nshards);
     if (rc) return rc;
     const int mode = current_mode(s, nullptr, nullptr);
@@ -688,9 +733,11 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
         FRMC_CUDA(cudaMemsetAsync(g.dev.delta, 0, sizeof(int) * 2 * g.dev.cells, s->stream));
         FRMC_CUDA(cudaMemsetAsync(s->d_next, 0, sizeof(int) * 4, s->stream));
         if (s->n_items > 0) {
+            cudaEvent_t t0 = timing_begin(s);
             rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->R, s->d_atoms, s->d_orig, s->d_items, s->n_items,
                                   s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
             if (rc) return rc;
+            timing_end(s, TIME_FULL, t0);
         }
         g.valid = true;
     }
@@ -713,6 +760,7 @@ int frmc_finalize_data(frmc_store *s, float *chi2)
     for (auto &m : s->models)
         FRMC_CUDA(cudaMemcpyAsync(m.total_committed, m.dev.total, sizeof(float) * m.dev.n_out, cudaMemcpyDeviceToDevice, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    timing_flush(s);
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_committed[i] = s->h_chi2[i];
         if (chi2) chi2[i] = s->h_chi2[i];
@@ -761,6 +809,7 @@ int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *move
     long long cap = (long long)s->ctx->sm_count * 8;
     int grid = (int)std::max<long long>(1, std::min(want, cap));
 #define LAUNCH_DELTA(M) delta_kernel<M><<<grid, 256, 0, s->stream>>>(s->d_atoms, (int)s->npad, s->d_prop, s->L, gs, s->nEl, s->d_overflow)
+    cudaEvent_t t0 = timing_begin(s);
     switch (mode) {
         case MODE_IBC: LAUNCH_DELTA(MODE_IBC); break;
         case MODE_ORTHO_FAST: LAUNCH_DELTA(MODE_ORTHO_FAST); break;
@@ -770,9 +819,11 @@ int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *move
     }
 #undef LAUNCH_DELTA
     FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_DELTA, t0);
     int rc = launch_epilogue(s);
     if (rc) return rc;
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    timing_flush(s);
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_staged[i] = s->h_chi2[i];
         if (chi2_after) chi2_after[i] = s->h_chi2[i];
@@ -790,8 +841,10 @@ int frmc_accept(frmc_store *s)
     long long cells = 0;
     for (auto &g : s->grids) cells = std::max(cells, 2 * g.dev.cells);
     int grid = (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 4));
+    cudaEvent_t t0 = timing_begin(s);
     commit_kernel<<<grid, 256, 0, s->stream>>>(gs, s->d_atoms, s->d_prop);
     FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_COMMIT, t0);
     for (auto &m : s->models)
         FRMC_CUDA(cudaMemcpyAsync(m.total_committed, m.dev.total, sizeof(float) * m.dev.n_out, cudaMemcpyDeviceToDevice, s->stream));
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], s->prop_lo[c]); s->hi[c] = std::max(s->hi[c], s->prop_hi[c]); }
@@ -809,8 +862,10 @@ int frmc_reject(frmc_store *s)
     long long cells = 0;
     for (auto &g : s->grids) cells = std::max(cells, 2 * g.dev.cells);
     int grid = (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 4));
+    cudaEvent_t t0 = timing_begin(s);
     clear_delta_kernel<<<grid, 256, 0, s->stream>>>(gs);
     FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_COMMIT, t0);
     s->state = 0;
     return FRMC_OK;
 }
@@ -840,6 +895,25 @@ int frmc_export_total(frmc_store *s, int model, int staged, float *out)
     FRMC_CUDA(cudaMemcpyAsync(out, staged ? m.dev.total : m.total_committed, sizeof(float) * m.dev.n_out,
                               cudaMemcpyDeviceToHost, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    return FRMC_OK;
+}
+
+int frmc_store_set_timing(frmc_store *s, int on)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    s->timing = on != 0;
+    if (on) for (int i = 0; i < 4; ++i) { s->kernel_ms[i] = 0; s->kernel_launches[i] = 0; }
+    return FRMC_OK;
+}
+
+int frmc_store_get_timing(frmc_store *s, int which, double *ms_total, uint64_t *launches)
+{
+    FRMC_REQUIRE(s && which >= 0 && which < 4, FRMC_EINVAL, "bad timing query");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    timing_flush(s);
+    if (ms_total) *ms_total = s->kernel_ms[which];
+    if (launches) *launches = s->kernel_launches[which];
     return FRMC_OK;
 }
 

@@ -163,6 +163,20 @@ class DeviceStore(object):
         b = None if basis is None else L.as_array(basis, "basis", _F32, 2)
         L.check(self._lib.frmc_store_set_coords(self._handle, L.ptr(coords, L.c_f32p), L.ptr(b, L.c_f32p)), "set_coords")
 
+    # ------------------------------------------------------------------ timing (bench.py)
+    TIMERS = {"delta": 0, "full": 1, "epilogue": 2, "commit": 3}
+
+    def set_timing(self, on=True):
+        L.check(self._lib.frmc_store_set_timing(self._handle, int(bool(on))), "set_timing")
+
+    def get_timing(self, which):
+        """(accumulated device ms, timed launches) of one kernel class since set_timing(True)."""
+        ms = ctypes.c_double(0.0)
+        n = ctypes.c_uint64(0)
+        L.check(self._lib.frmc_store_get_timing(self._handle, self.TIMERS[which], ctypes.byref(ms), ctypes.byref(n)),
+                "get_timing")
+        return float(ms.value), int(n.value)
+
     @property
     def edge_overflow(self):
         return int(self._lib.frmc_store_edge_overflow(self._handle))

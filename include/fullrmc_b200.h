@@ -187,6 +187,12 @@ int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter);
 int frmc_export_total(frmc_store *s, int model, int staged, float *out);
 /* events where the fp32 bin index rounded up to histSize (dropped), summed over the store's life */
 uint64_t frmc_store_edge_overflow(frmc_store *s);
+/* Optional per-kernel timing with CUDA events on the store's stream (bench.py's roofline leg).
+ * which: 0 = per-move delta pass, 1 = full-histogram kernel, 2 = epilogue (G(r)/S(Q)/chi^2 kernels),
+ * 3 = commit/clear kernels.  get_timing synchronises the stream and returns the accumulated
+ * device time in ms and the number of timed launches since timing was switched on. */
+int frmc_store_set_timing(frmc_store *s, int on);
+int frmc_store_get_timing(frmc_store *s, int which, double *ms_total, uint64_t *launches);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t frmc_launch_count(void);
 

@@ -1,0 +1,270 @@
+"""GPU parity tests of the stateful device path (DeviceStore: compute_data, propose, accept,
+reject) against the reference sequence compute_before_move / compute_after_move / accept_move
+(PairDistributionConstraints.py:1044-1152) restated with the oracle.
+
+Bars: running histograms bit-exact (ordered arrays, which implies the symmetrised sums the
+physics uses); G(r), g(r), S(Q) totals and chi^2 bit-exact against the numpy restatement
+(the north_star tolerance is 1e-6 relative; the device epilogue mirrors numpy's fp32 operation
+and summation order, so equality is asserted and the tolerance is the fallback bar)."""
+import numpy as np
+import pytest
+
+import cases as C
+from oracle import epilogue as ep
+
+pytestmark = pytest.mark.gpu
+
+F32 = np.float32
+ELEMENTS = ["O", "Si", "Ti", "Ni", "Zr"]
+CASES = {c["name"]: c for c in C.make_cases()}
+
+
+def _system_meta(case):
+    nEl = case["numberOfElements"]
+    els = ELEMENTS[:nEl]
+    counts = np.bincount(case["elementIndex"], minlength=nEl)
+    n_per = {els[i]: int(max(counts[i], 2)) for i in range(nEl)}      # empty classes: keep D_ij finite
+    weights = {"O": 8.0, "Si": 14.0, "Ti": 22.0, "Ni": 28.0, "Zr": 40.0}
+    wdict = ep.normalized_weighting(n_per, {e: weights[e] for e in els})
+    wdict = {k: F32(v) for k, v in wdict.items()}
+    if case["isPBC"]:
+        volume = F32(abs(np.linalg.det(case["basis"].astype(np.float64))))
+    else:
+        volume = F32(case["boxCoords"].shape[0] / 0.0333679)
+    rho0 = F32(case["boxCoords"].shape[0]) / F32(volume)
+    return els, n_per, wdict, volume, rho0
+
+
+def _grid_arrays(case):
+    hs = case["histSize"]
+    edges = (case["minDistance"] + case["bin"] * np.arange(hs + 1, dtype=np.float64)).astype(F32)
+    centers = ((edges[:-1] + edges[1:]) / F32(2.)).astype(F32)
+    return centers, ep.shell_arrays_from_edges(edges)
+
+
+def _build(case, kinds, rng, with_weights=False, with_shape=False, scale=1.0):
+    """DeviceStore + ModelSpecs + matching oracle closures for the requested model kinds"""
+    from fullrmc_b200.model import ModelSpec
+    from fullrmc_b200.store import DeviceStore
+    els, n_per, wdict, volume, rho0 = _system_meta(case)
+    centers, shellv = _grid_arrays(case)
+    hs = case["histSize"]
+    store = DeviceStore(case["boxCoords"], case["basis"], case["isPBC"], case["moleculeIndex"], case["elementIndex"],
+                        case["numberOfElements"])
+    g = store.add_grid(case["minDistance"], case["maxDistance"], case["bin"], hs)
+    q = np.linspace(0.5, 20.0, 97).astype(F32)
+    gr2sq = ep.gr2sq_matrix(q, centers)
+    oracles = []
+    for kind in kinds:
+        n_out = hs if kind in ("PDF", "PCF") else q.shape[0]
+        exp = rng.normal(0.0 if kind != "PCF" else 1.0, 0.5, n_out).astype(F32)
+        dw = rng.random(n_out).astype(F32) if with_weights else None
+        shape = (0.01 * rng.standard_normal(hs)).astype(F32) if (with_shape and kind in ("PDF", "PCF")) else None
+        spec = ModelSpec(kind, els, n_per, wdict, volume, rho0, centers, shellv, exp, data_weights=dw,
+                         shape_array=shape, scale_factor=scale, q_values=q if kind in ("SQ", "RSQ") else None)
+        store.add_model(g, spec)
+        common = dict(elements=els, n_per_element=n_per, weighting=wdict, volume=volume, rho0=rho0,
+                      shell_centers=centers, shell_volumes=shellv)
+
+        def total(intra, inter, kind=kind, shape=shape, common=common):
+            if kind == "PDF":
+                return ep.total_Gr(intra, inter, shape_array=shape, scale_factor=scale, **common)
+            if kind == "PCF":
+                return ep.total_gr(intra, inter, shape_array=shape, scale_factor=scale, **common)
+            return ep.total_Sq(intra, inter, gr2sq=gr2sq, scale_factor=scale, reduced=(kind == "RSQ"), **common)
+        oracles.append((total, exp, dw))
+    return store, oracles
+
+
+def _check_models(store, oracles, intra, inter, chi2, staged):
+    for m, (total, exp, dw) in enumerate(oracles):
+        want = total(intra, inter)
+        got = store.export_total(m, staged=staged)
+        scale = max(1e-30, float(np.max(np.abs(want))))
+        assert np.max(np.abs(got - want)) <= 1e-6 * scale, "model %d total outside 1e-6" % m
+        assert np.array_equal(got, want), "model %d total not bit-exact (max diff %g)" % (m, np.max(np.abs(got - want)))
+        want_chi = ep.standard_error(exp, want, dw)
+        assert abs(float(chi2[m]) - float(want_chi)) <= 1e-6 * abs(float(want_chi))
+        assert F32(chi2[m]) == F32(want_chi), "model %d chi2 %r != %r" % (m, chi2[m], want_chi)
+
+
+def _hist_kw(case):
+    return dict(basis=case["basis"], isPBC=case["isPBC"], numberOfElements=case["numberOfElements"],
+                minDistance=case["minDistance"], maxDistance=case["maxDistance"], bin=case["bin"],
+                histSize=case["histSize"])
+
+
+def _run_sequence(case, kinds, orc, n_moves=12, seed=0, sigma=0.02, **model_kw):
+    rng = np.random.default_rng(seed)
+    store, oracles = _build(case, kinds, rng, **model_kw)
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    box = case["boxCoords"].copy()
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+
+    chi2 = store.compute_data()
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+    gi, ge = store.export_data(0)
+    assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e)
+    _check_models(store, oracles, data_i, data_e, chi2, staged=False)
+
+    accepted = 0
+    for step in range(n_moves):
+        idx = C.group_for(case, rng)
+        moved = (box[idx] + rng.normal(0, sigma, (idx.shape[0], 3)).astype(F32)).astype(F32)
+        # reference sequence (PairDistributionConstraints.py:1044-1129)
+        bi, be = ep.move_delta(fns, idx, box, kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"],
+                               kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"],
+                               kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+        new_i = data_i - bi + ai
+        new_e = data_e - be + ae
+        chi2 = store.propose(idx, moved)
+        _check_models(store, oracles, new_i, new_e, chi2, staged=True)
+        if step % 3 != 2:                      # accept two moves out of three
+            store.accept()
+            data_i, data_e, box = new_i, new_e, tmp
+            accepted += 1
+        else:
+            store.reject()
+        gi, ge = store.export_data(0)
+        assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e), "running histograms diverged at step %d" % step
+    assert accepted > 0
+    assert np.array_equal(store.get_coords(), box)
+    assert store.edge_overflow == 0
+    # the incrementally updated state equals a from-scratch recomputation (symmetrised)
+    fi, fe = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+    sym = lambda h: h + h.transpose(1, 0, 2)
+    assert np.array_equal(sym(data_i), sym(fi)) and np.array_equal(sym(data_e), sym(fe))
+    store.close()
+
+
+def test_atomic_orthorhombic_pdf_and_sq(orc):
+    _run_sequence(CASES["ortho_atomic"], ["PDF", "SQ"], orc, seed=1)
+
+
+def test_molecular_triclinic_pcf_with_weights(orc):
+    _run_sequence(CASES["tri_molecular"], ["PCF"], orc, seed=2, with_weights=True)
+
+
+def test_unwrapped_triclinic_reduced_sq_scaled(orc):
+    _run_sequence(CASES["tri_unwrapped"], ["RSQ", "PDF"], orc, seed=3, scale=0.93, with_shape=True)
+
+
+def test_unwrapped_orthorhombic(orc):
+    _run_sequence(CASES["ortho_unwrapped"], ["PDF"], orc, seed=4, sigma=0.2)
+
+
+def test_non_periodic_nanoparticle_pdf_with_shape(orc):
+    _run_sequence(CASES["ibc_nanoparticle"], ["PDF", "PCF"], orc, seed=5, sigma=0.3, with_shape=True, scale=1.07)
+
+
+def test_lattice_and_coincident_atoms(orc):
+    _run_sequence(CASES["lattice_half"], ["PDF"], orc, seed=6, sigma=0.05)
+    _run_sequence(CASES["coincident_empty_class"], ["PDF", "SQ"], orc, seed=7)
+
+
+def test_five_elements_cfg4_like(orc):
+    _run_sequence(CASES["cfg4_small"], ["PDF", "SQ"], orc, seed=8, n_moves=9)
+
+
+def test_wrap_mode_switch_when_a_move_leaves_the_unit_cell(orc):
+    """fast wrap (|frac diff| < 1.5) must hand over to the general wrap when accepted moves drift"""
+    case = dict(CASES["ortho_atomic"])
+    rng = np.random.default_rng(9)
+    store, oracles = _build(case, ["PDF"], rng)
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    box = case["boxCoords"].copy()
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    store.compute_data()
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+    for shift in (0.3, 0.9, 2.4, -3.1):
+        idx = np.array([int(rng.integers(0, box.shape[0]))], dtype=np.int32)
+        moved = (box[idx] + F32(shift)).astype(F32)
+        bi, be = ep.move_delta(fns, idx, box, kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"],
+                               kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"],
+                               kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+        data_i, data_e, box = data_i - bi + ai, data_e - be + ae, tmp
+        chi2 = store.propose(idx, moved)
+        _check_models(store, oracles, data_i, data_e, chi2, staged=True)
+        store.accept()
+    gi, ge = store.export_data(0)
+    assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e)
+    # and a full recomputation on the drifted coordinates uses the general wrap too
+    store.compute_data()
+    fi, fe = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+    gi, ge = store.export_data(0)
+    assert np.array_equal(gi, fi) and np.array_equal(ge, fe)
+    store.close()
+
+
+def test_state_machine_errors():
+    from fullrmc_b200.store import DeviceStore
+    case = CASES["tiny_13"]
+    store = DeviceStore(case["boxCoords"], case["basis"], True, case["moleculeIndex"], case["elementIndex"], 3)
+    store.add_grid(case["minDistance"], case["maxDistance"], case["bin"], case["histSize"])
+    idx = np.array([1], dtype=np.int32)
+    with pytest.raises(RuntimeError):
+        store.propose(idx, case["boxCoords"][idx])          # compute_data first
+    store.compute_data()
+    with pytest.raises(RuntimeError):
+        store.accept()                                      # nothing staged
+    store.propose(idx, case["boxCoords"][idx])
+    with pytest.raises(RuntimeError):
+        store.propose(idx, case["boxCoords"][idx])          # already staged
+    store.reject()
+    with pytest.raises(ValueError):
+        store.propose(np.array([99], dtype=np.int32), case["boxCoords"][idx])
+    store.close()
+
+
+def test_two_grids_one_pass(orc):
+    """NiTi-like setup: a fine PDF grid and a coarse S(Q) grid fed by the same pass over the store"""
+    from fullrmc_b200.model import ModelSpec
+    from fullrmc_b200.store import DeviceStore
+    case = CASES["ortho_atomic"]
+    rng = np.random.default_rng(10)
+    els, n_per, wdict, volume, rho0 = _system_meta(case)
+    store = DeviceStore(case["boxCoords"], case["basis"], True, case["moleculeIndex"], case["elementIndex"], 3)
+    grids = []
+    for (rmin, b, hs) in ((F32(0.005), F32(0.01), 1200), (F32(0.2856), F32(0.2), 60)):
+        edges = (rmin + b * np.arange(hs + 1, dtype=np.float64)).astype(F32)
+        centers = ((edges[:-1] + edges[1:]) / F32(2.)).astype(F32)
+        grids.append(dict(rmin=edges[0], rmax=edges[-1], bin=b, hs=hs, centers=centers, sv=ep.shell_arrays_from_edges(edges)))
+    q = np.linspace(0.6, 12.0, 64).astype(F32)
+    exps = [rng.normal(0, 0.4, 1200).astype(F32), rng.normal(0, 0.4, 64).astype(F32)]
+    for gi_, (g, kind) in enumerate(zip(grids, ("PDF", "RSQ"))):
+        gid = store.add_grid(g["rmin"], g["rmax"], g["bin"], g["hs"])
+        store.add_model(gid, ModelSpec(kind, els, n_per, wdict, volume, rho0, g["centers"], g["sv"], exps[gi_],
+                                       q_values=q if kind == "RSQ" else None))
+    chi2 = store.compute_data()
+    box = case["boxCoords"].copy()
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+
+    def oracle_chi2(boxc):
+        out = []
+        for gi_, (g, kind) in enumerate(zip(grids, ("PDF", "RSQ"))):
+            hi, he = orc.full_pairs_histograms_coords(boxCoords=boxc, basis=case["basis"], isPBC=True, moleculeIndex=mol,
+                                                      elementIndex=el, numberOfElements=3, minDistance=g["rmin"],
+                                                      maxDistance=g["rmax"], bin=g["bin"], histSize=g["hs"])
+            common = dict(elements=els, n_per_element=n_per, weighting=wdict, volume=volume, rho0=rho0,
+                          shell_centers=g["centers"], shell_volumes=g["sv"])
+            tot = ep.total_Gr(hi, he, **common) if kind == "PDF" else \
+                ep.total_Sq(hi, he, gr2sq=ep.gr2sq_matrix(q, g["centers"]), reduced=True, **common)
+            out.append(ep.standard_error(exps[gi_], tot))
+        return out
+    want = oracle_chi2(box)
+    assert F32(chi2[0]) == F32(want[0]) and F32(chi2[1]) == F32(want[1])
+    for step in range(4):
+        idx = np.array([int(rng.integers(0, box.shape[0]))], dtype=np.int32)
+        moved = (box[idx] + rng.normal(0, 0.03, (1, 3)).astype(F32)).astype(F32)
+        chi2 = store.propose(idx, moved)
+        tmp = box.copy(); tmp[idx] = moved
+        want = oracle_chi2(tmp)       # k=1: ordered running state == from-scratch state
+        assert F32(chi2[0]) == F32(want[0]) and F32(chi2[1]) == F32(want[1])
+        store.accept(); box = tmp
+    store.close()
