@@ -78,9 +78,12 @@ SIGNATURES = {
     "frmc_propose": (_I, [_VP, c_i32p, _I, c_f32p, c_f32p]),
     "frmc_accept": (_I, [_VP]),
     "frmc_reject": (_I, [_VP]),
+    "frmc_step": (_I, [_VP, _I, c_i32p, _I, c_f32p, c_f32p]),
+    "frmc_store_replay_proposal": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double)]),
     "frmc_export_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_export_total": (_I, [_VP, _I, _I, c_f32p]),
     "frmc_store_edge_overflow": (ctypes.c_uint64, [_VP]),
+    "frmc_store_debug_stamps": (_I, [_VP, c_i64p, _I]),
     "frmc_store_set_timing": (_I, [_VP, _I]),
     "frmc_store_get_timing": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double), c_u64p]),
 }

@@ -226,11 +226,14 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
     if (ov) atomicAdd(overflow, ov);
 }
 
-// counts (u64) -> fp32 [nEl,nEl,hs] x2
+// counts (64-bit, SIGNED: the reference's running ordered arrays data-before+after may hold
+// negative cells, because M removes a pair from [el_moved, el_other] while the full histogram
+// had put it in [el_lower_index, el_higher_index]; only the symmetrised sum is a count)
+// -> fp32 [nEl,nEl,hs] x2
 __global__ void counts64_to_float_kernel(const unsigned long long *__restrict__ counts, float *__restrict__ out, long long cells2)
 {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < cells2) out[c] = (float)counts[c];
+    if (c < cells2) out[c] = (float)(long long)counts[c];
 }
 
 size_t full_hist_smem_bytes(int hs) { return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(unsigned int) * 4 * (size_t)hs; }

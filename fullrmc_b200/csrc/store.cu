@@ -6,12 +6,18 @@
 // reject_move of PairDistributionConstraint, PairCorrelationConstraint and
 // StructureFactorConstraint (Constraints/PairDistributionConstraints.py:1001-1166,
 // PairCorrelationConstraints.py:263-392, StructureFactorConstraints.py:933-1096).
+//
+// Per Metropolis step the device runs TWO kernels (delta pass, fused epilogue) and, after
+// the host's decision, one commit-or-clear kernel; the host spins on a pinned completion
+// counter instead of synchronising the stream.
 #include "common.cuh"
 #include "layout.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <immintrin.h>
 
 namespace frmc {
 
@@ -23,58 +29,133 @@ void choose_tiling(int64_t npad, int sm_count, int &R, int64_t &chunkJ);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
 
 // ------------------------------------------------------------------ device-side descriptors
+// Per grid the store keeps the reference's ORDERED arrays data["intra"], data["inter"]
+// (counts, int64, signed) plus the SYMMETRISED totals per unordered element pair
+//     tot[sym(a,b)][r] = intra[a,b]+intra[b,a]+inter[a,b]+inter[b,a]   (a != b)
+//                      = intra[a,a]+inter[a,a]                          (a == b)
+// which is all that reaches G(r) (PairDistributionConstraints.py:867-876).  `stot` is the
+// STAGED copy (committed totals + the proposal's signed events): the epilogue reads only
+// stot (nEl(nEl+1)/2 cells per bin) instead of 2*nEl^2 ordered cells + deltas.
 struct GridDev {
     GridParams g;
+    int nsym;                        // nEl*(nEl+1)/2
+    int pad;
     long long cells;                 // nEl*nEl*hs
-    unsigned long long *counts;      // committed [2][cells]  (0 intra, 1 inter)
-    int *delta;                      // staged after-minus-before [2][cells]
+    unsigned long long *counts;      // committed ordered counts [2][cells]  (0 intra, 1 inter)
+    int *delta;                      // staged after-minus-before, ordered  [2][cells]
+    int *tot;                        // committed symmetrised totals (int32) [nsym][hs]
+    int *stot;                       // staged symmetrised totals (tot + proposal, int32) [nsym][hs]
 };
 
 struct GridSet {
     int n;
     float t2lo, t2hi;                // union of the grids' d^2 windows (cheap first test)
+    int pad;
     GridDev grid[FRMC_MAX_GRIDS];
 };
 
-struct Proposal {                    // device copy of the staged move
+struct ProposalIn {                  // passed BY VALUE as a kernel parameter (constant bank)
     int k;
-    int pos[FRMC_MAX_GROUP];         // positions in the sorted store
-    float4 oldc[FRMC_MAX_GROUP];     // current records of the group atoms
-    float4 newc[FRMC_MAX_GROUP];     // same meta, moved coordinates
+    int pos[FRMC_MAX_GROUP];         // positions in the sorted store (host lookup in the inverse permutation)
+    float moved[3 * FRMC_MAX_GROUP]; // moved box coordinates
 };
 
-struct ProposalIn {                  // what the host sends: original indices + moved box coords
+struct Proposal {                    // device copy kept for the commit kernel
     int k;
-    int idx[FRMC_MAX_GROUP];
-    float moved[3 * FRMC_MAX_GROUP];
+    int pos[FRMC_MAX_GROUP];
+    float4 newc[FRMC_MAX_GROUP];     // same meta, moved coordinates
 };
 
 struct ModelDev {
     int kind, grid, n_pairs, n_out, hs, sq_exact;
     float scale;
-    const int *pa, *pb;
-    const float *w, *D, *sv, *pref, *shape, *expv, *wts, *gr2sq;
+    const int *psym;                 // [n_pairs] symmetrised pair index of (idi, idj)
+    const float *w, *D, *rD, *sv, *pref, *shape, *expv, *wts, *gr2sq;   // rD[p] = RN(1/D[p]) when the 3-op division is proven exact, else NaN
     float *rfun;                     // [hs]    r-space function of the staged state (G(r) or g(r))
     float *total;                    // [n_out] staged model total
+    const int *pw_sched;             // [4][pw_leaves] numpy pairwise-sum schedule for n_out terms
+    int pw_leaves;
+    int nq_pad;                      // row stride of gr2sq on the device (n_out rounded up to 32, zero filled)
 };
 
-// ------------------------------------------------------------------ kernels: proposal
-__global__ void prep_proposal_kernel(const ProposalIn *__restrict__ in, const int *__restrict__ inv,
-                                     const float4 *__restrict__ atoms, Proposal *__restrict__ out)
+struct ModelSet {                    // passed BY VALUE to the epilogue (constant bank: no dependent descriptor load)
+    int n;
+    int pad;
+    ModelDev m[FRMC_MAX_MODELS];
+};
+
+__host__ __device__ __forceinline__ int sym_index(int a, int b, int nEl)
 {
-    int t = threadIdx.x;
-    int k = in->k;
-    if (t == 0) out->k = k;
-    if (t < k) {
-        int p = inv[in->idx[t]];
-        float4 o = atoms[p];
-        out->pos[t] = p;
-        out->oldc[t] = o;
-        out->newc[t] = make_float4(in->moved[3 * t], in->moved[3 * t + 1], in->moved[3 * t + 2], o.w);
+    if (a > b) { int t = a; a = b; b = t; }
+    return a * nEl - (a * (a - 1)) / 2 + (b - a);
+}
+
+// ------------------------------------------------------------------ kernels: bookkeeping
+// tot, stot <- symmetrised sums of the ordered counts (after compute_data / all-reduce)
+// Symmetrised cells are int32: enough for every configuration whose cells stay below 2^31 (the
+// fp32 reference is only exact below 2^24 per cell); larger totals raise *too_big.
+__global__ void symmetrise_kernel(GridDev G, int nEl, int *__restrict__ too_big)
+{
+    const int hs = G.g.hs;
+    const long long n = (long long)G.nsym * hs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / hs), r = (int)(i - (long long)s * hs);
+        // invert sym_index: find a with first(a) <= s < first(a+1)
+        int a = 0;
+        while (a + 1 < nEl && (a + 1) * nEl - ((a + 1) * a) / 2 <= s) ++a;
+        const int b = a + (s - (a * nEl - (a * (a - 1)) / 2));
+        const long long ab = ((long long)a * nEl + b) * hs + r, ba = ((long long)b * nEl + a) * hs + r;
+        long long v = (long long)G.counts[ab] + (long long)G.counts[G.cells + ab];
+        if (a != b) v += (long long)G.counts[ba] + (long long)G.counts[G.cells + ba];
+        if (v > 0x3FFFFFFFll || v < -0x3FFFFFFFll) *too_big = 1;
+        G.tot[i] = (int)v;
+        G.stot[i] = (int)v;
     }
 }
 
-__device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab, const GridSet &gs, int nEl,
+struct TotalsCopy {
+    int n;
+    int len[FRMC_MAX_MODELS];
+    const float *src[FRMC_MAX_MODELS];
+    float *dst[FRMC_MAX_MODELS];
+};
+
+// accept: fold the staged deltas into the committed state, clear them, move the atoms and
+// promote the staged model totals to committed
+__global__ void commit_kernel(GridSet gs, float4 *__restrict__ atoms, const Proposal *__restrict__ prop, TotalsCopy tc)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int gi = 0; gi < gs.n; ++gi) {
+        const GridDev &G = gs.grid[gi];
+        for (long long c = tid; c < 2 * G.cells; c += stride) {
+            const int d = G.delta[c];
+            if (d) { G.counts[c] = (unsigned long long)((long long)G.counts[c] + d); G.delta[c] = 0; }
+        }
+        const long long ns = (long long)G.nsym * G.g.hs;
+        for (long long c = tid; c < ns; c += stride) G.tot[c] = G.stot[c];
+    }
+    if (tid < prop->k) atoms[prop->pos[tid]] = prop->newc[tid];
+    for (int m = 0; m < tc.n; ++m)
+        for (long long i = tid; i < tc.len[m]; i += stride) tc.dst[m][i] = tc.src[m][i];
+}
+
+// reject: clear the staged deltas
+__global__ void clear_delta_kernel(GridSet gs)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int gi = 0; gi < gs.n; ++gi) {
+        const GridDev &G = gs.grid[gi];
+        for (long long c = tid; c < 2 * G.cells; c += stride)
+            if (G.delta[c]) G.delta[c] = 0;
+        const long long ns = (long long)G.nsym * G.g.hs;
+        for (long long c = tid; c < ns; c += stride) G.stot[c] = G.tot[c];
+    }
+}
+
+// ------------------------------------------------------------------ kernels: delta pass
+__device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab, int sym, const GridSet &gs,
                                           unsigned long long &ov)
 {
 #pragma unroll 1
@@ -82,53 +163,76 @@ __device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab
         const GridDev &G = gs.grid[gi];
         if (in_range(d2, G.g)) {
             int b = bin_index(d2, G.g);
-            if (b < G.g.hs) atomicAdd(&G.delta[(same ? 0 : G.cells) + (long long)slab * G.g.hs + b], sign);
-            else ++ov;
+            if (b < G.g.hs) {
+                atomicAdd(&G.delta[(same ? 0 : G.cells) + (long long)slab * G.g.hs + b], sign);
+                atomicAdd(&G.stot[(long long)sym * G.g.hs + b], sign);
+            } else {
+                ++ov;
+            }
         }
     }
 }
 
 // One streaming pass over the whole store: every atom record is read ONCE (coalesced
-// 16-byte loads) and tested against the old and the new position of every group atom;
-// the signed events (-1 old, +1 new) land in the int32 delta histograms of every grid.
-// Pairs inside the group are handled by block 0 with the reference's M-F convention
-// (PairDistributionConstraints.py:1053-1078: the pair (t,u), u earlier in the index
-// list, survives once in slab [el_t, el_u]).
+// 16-byte loads, DELTA_UNROLL independent loads in flight per thread) and tested against the
+// old and the new position of every group atom; the signed events (-1 old, +1 new) land in
+// the int32 delta histograms of every grid.  Pairs inside the group are handled by block 0
+// with the reference's M-F convention (PairDistributionConstraints.py:1053-1078: the pair
+// (t,u), u earlier in the index list, survives once in slab [el_t, el_u]).
+// compute_before_move + compute_after_move = this one launch.  Algorithmic traffic: 16 B/atom.
+static const int DELTA_UNROLL = 4;
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
-delta_kernel(const float4 *__restrict__ atoms, int npad, const Proposal *__restrict__ prop, Lattice L,
-             GridSet gs, int nEl, unsigned long long *__restrict__ overflow)
+delta_kernel(const float4 *__restrict__ atoms, int npad, const ProposalIn in, Proposal *__restrict__ prop,
+             Lattice L, GridSet gs, int nEl, unsigned long long *__restrict__ overflow)
 {
     __shared__ float4 sOld[FRMC_MAX_GROUP];
     __shared__ float4 sNew[FRMC_MAX_GROUP];
     __shared__ int sPos[FRMC_MAX_GROUP];
-    const int k = prop->k;
+    const int k = in.k;
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
-        sOld[t] = prop->oldc[t]; sNew[t] = prop->newc[t]; sPos[t] = prop->pos[t];
+        const int p = in.pos[t];
+        const float4 o = atoms[p];
+        const float4 nw = make_float4(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], o.w);
+        sOld[t] = o; sNew[t] = nw; sPos[t] = p;
+        if (blockIdx.x == 0) { prop->pos[t] = p; prop->newc[t] = nw; }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) prop->k = k;
     __syncthreads();
     unsigned long long ov = 0;
-    const int stride = gridDim.x * blockDim.x;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npad; p += stride) {
-        const float4 a = atoms[p];
-        const uint32_t mj = __float_as_uint(a.w);
-        if (mj == PAD_META) continue;
-        bool ingroup = false;
-        for (int t = 0; t < k; ++t) ingroup |= (sPos[t] == p);
-        if (ingroup) continue;
-        const int ej = mj & 0xFF;
-        for (int t = 0; t < k; ++t) {
-            const float4 o = sOld[t], nw = sNew[t];
-            const uint32_t mt = __float_as_uint(o.w);
-            const float d2o = dist2<MODE>(o.x, o.y, o.z, a.x, a.y, a.z, L);
-            const float d2n = dist2<MODE>(nw.x, nw.y, nw.z, a.x, a.y, a.z, L);
-            const bool ho = (d2o >= gs.t2lo) && (d2o < gs.t2hi);
-            const bool hn = (d2n >= gs.t2lo) && (d2n < gs.t2hi);
-            if (ho || hn) {
-                const int same = (mt >> 8) == (mj >> 8);
-                const int slab = (int)(mt & 0xFF) * nEl + ej;
-                if (ho) delta_hit(d2o, -1, same, slab, gs, nEl, ov);
-                if (hn) delta_hit(d2n, +1, same, slab, gs, nEl, ov);
+    const int T = gridDim.x * blockDim.x;
+    for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < npad; p0 += DELTA_UNROLL * T) {
+        float4 a[DELTA_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DELTA_UNROLL; ++u) {
+            const int p = p0 + u * T;
+            a[u] = (p < npad) ? atoms[p] : make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+        }
+#pragma unroll
+        for (int u = 0; u < DELTA_UNROLL; ++u) {
+            const int p = p0 + u * T;
+            const uint32_t mj = __float_as_uint(a[u].w);
+            if (mj == PAD_META) continue;
+            bool ingroup = false;
+            for (int t = 0; t < k; ++t) ingroup |= (sPos[t] == p);
+            if (ingroup) continue;
+            const int ej = mj & 0xFF;
+            for (int t = 0; t < k; ++t) {
+                const float4 o = sOld[t], nw = sNew[t];
+                const uint32_t mt = __float_as_uint(o.w);
+                const float d2o = dist2<MODE>(o.x, o.y, o.z, a[u].x, a[u].y, a[u].z, L);
+                const float d2n = dist2<MODE>(nw.x, nw.y, nw.z, a[u].x, a[u].y, a[u].z, L);
+                const bool ho = (d2o >= gs.t2lo) && (d2o < gs.t2hi);
+                const bool hn = (d2n >= gs.t2lo) && (d2n < gs.t2hi);
+                if (ho || hn) {
+                    const int same = (mt >> 8) == (mj >> 8);
+                    const int et = (int)(mt & 0xFF);
+                    const int slab = et * nEl + ej;
+                    const int sym = sym_index(et, ej, nEl);
+                    if (ho) delta_hit(d2o, -1, same, slab, sym, gs, ov);
+                    if (hn) delta_hit(d2n, +1, same, slab, sym, gs, ov);
+                }
             }
         }
     }
@@ -140,200 +244,48 @@ delta_kernel(const float4 *__restrict__ atoms, int npad, const Proposal *__restr
             const float4 ot = sOld[t], ou = sOld[u], nt = sNew[t], nu = sNew[u];
             const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
             const int same = (mt >> 8) == (mu >> 8);
-            const int slab = (int)(mt & 0xFF) * nEl + (int)(mu & 0xFF);
+            const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+            const int slab = et * nEl + eu;
+            const int sym = sym_index(et, eu, nEl);
             const float d2o = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
             const float d2n = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
-            if ((d2o >= gs.t2lo) && (d2o < gs.t2hi)) delta_hit(d2o, -1, same, slab, gs, nEl, ov);
-            if ((d2n >= gs.t2lo) && (d2n < gs.t2hi)) delta_hit(d2n, +1, same, slab, gs, nEl, ov);
+            if ((d2o >= gs.t2lo) && (d2o < gs.t2hi)) delta_hit(d2o, -1, same, slab, sym, gs, ov);
+            if ((d2n >= gs.t2lo) && (d2n < gs.t2hi)) delta_hit(d2n, +1, same, slab, sym, gs, ov);
         }
     }
     if (ov) atomicAdd(overflow, ov);
 }
 
-// accept: fold the staged delta into the committed counts, clear it, move the atoms
-__global__ void commit_kernel(GridSet gs, float4 *__restrict__ atoms, const Proposal *__restrict__ prop)
-{
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int gi = 0; gi < gs.n; ++gi) {
-        const GridDev &G = gs.grid[gi];
-        for (long long c = tid; c < 2 * G.cells; c += stride) {
-            const int d = G.delta[c];
-            if (d) { G.counts[c] = (unsigned long long)((long long)G.counts[c] + d); G.delta[c] = 0; }
-        }
-    }
-    if (tid < prop->k) atoms[prop->pos[tid]] = prop->newc[tid];
-}
-
-// reject: clear the staged delta
-__global__ void clear_delta_kernel(GridSet gs)
-{
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int gi = 0; gi < gs.n; ++gi) {
-        const GridDev &G = gs.grid[gi];
-        for (long long c = tid; c < 2 * G.cells; c += stride)
-            if (G.delta[c]) G.delta[c] = 0;
-    }
-}
-
-// ------------------------------------------------------------------ kernels: epilogue
-// r-space function of every model, one thread per (model, bin).  Mirrors the numpy
-// expressions of __get_total_Gr / __get_total_gr / __get_total_Sq operation by operation
-// in fp32 (numpy >= 2 scalar promotion: every scalar is fp32):
-//   for pair in sorted pairs:  Gr += (wij*nij)/Dij          (PairDistributionConstraints.py:855-876)
-//   Gr /= shellVolumes                                      (:878)
-//   Gr  = prefactor*(Gr-1)                                  (:881)   [PDF, SQ, RSQ]
-//   Gr -= shape ; Gr *= scale (when != 1)                   (:883-888) [PDF]
-//   PCF: gr -= shape; if scale != 1: gr = 1 + (prefactor*(gr-1)*scale)/prefactor   (PairCorrelationConstraints.py:153-163)
-__global__ void rfun_kernel(const ModelDev *__restrict__ models, int n_models, GridSet gs, int nEl)
-{
-    const int m = blockIdx.y;
-    if (m >= n_models) return;
-    const ModelDev M = models[m];
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= M.hs) return;
-    const GridDev &G = gs.grid[M.grid];
-    const unsigned long long *ci = G.counts, *ce = G.counts + G.cells;
-    const int *di = G.delta, *de = G.delta + G.cells;
-    float acc = 0.0f;
-    for (int p = 0; p < M.n_pairs; ++p) {
-        const int a = M.pa[p], b = M.pb[p];
-        const long long ab = ((long long)a * nEl + b) * M.hs + r;
-        float n;
-        if (a == b) {
-            n = __fadd_rn((float)((long long)ci[ab] + di[ab]), (float)((long long)ce[ab] + de[ab]));
-        } else {
-            const long long ba = ((long long)b * nEl + a) * M.hs + r;
-            n = __fadd_rn((float)((long long)ci[ab] + di[ab]), (float)((long long)ci[ba] + di[ba]));
-            n = __fadd_rn(n, (float)((long long)ce[ab] + de[ab]));
-            n = __fadd_rn(n, (float)((long long)ce[ba] + de[ba]));
-        }
-        acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(M.w[p], n), M.D[p]));
-    }
-    acc = __fdiv_rn(acc, M.sv[r]);
-    float out;
-    if (M.kind == FRMC_KIND_PCF) {
-        out = acc;
-        if (M.shape) out = __fsub_rn(out, M.shape[r]);
-        if (M.scale != 1.0f) {
-            float Gr = __fmul_rn(M.pref[r], __fsub_rn(out, 1.0f));
-            Gr = __fmul_rn(Gr, M.scale);
-            out = __fadd_rn(1.0f, __fdiv_rn(Gr, M.pref[r]));
-        }
-        M.total[r] = out;
-    } else {
-        out = __fmul_rn(M.pref[r], __fsub_rn(acc, 1.0f));
-        if (M.kind == FRMC_KIND_PDF) {
-            if (M.shape) out = __fsub_rn(out, M.shape[r]);
-            if (M.scale != 1.0f) out = __fmul_rn(out, M.scale);
-            M.total[r] = out;
-        }
-    }
-    M.rfun[r] = out;
-}
-
-// S(Q_m) = sum_r G(r)*M[r,m] (+1), one thread per Q, r in index order, fp32 multiply then
-// fp32 add with no FMA: bit-identical to np.sum(Gr.reshape((-1,1))*Gr2SqMatrix, axis=0)
-// (StructureFactorConstraints.py:772-773), which accumulates rows sequentially.
-// One warp per CTA so that the nQ/32 independent chains spread over as many SMs.
-__global__ void __launch_bounds__(32)
-sq_kernel(const ModelDev *__restrict__ models, int n_models)
-{
-    const int m = blockIdx.y;
-    if (m >= n_models) return;
-    const ModelDev M = models[m];
-    if (M.kind != FRMC_KIND_SQ && M.kind != FRMC_KIND_RSQ) return;
-    const int q = blockIdx.x * 32 + threadIdx.x;
-    if (blockIdx.x * 32 >= M.n_out) return;
-    const int qq = min(q, M.n_out - 1);
-    const float *__restrict__ col = M.gr2sq + qq;
-    const float *__restrict__ G = M.rfun;
-    const int hs = M.hs, nq = M.n_out;
-    float acc = 0.0f;
-    int r = 0;
-    for (; r + 8 <= hs; r += 8) {
-        float g[8], c[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { g[u] = G[r + u]; c[u] = col[(long long)(r + u) * nq]; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, __fmul_rn(g[u], c[u]));
-    }
-    for (; r < hs; ++r) acc = __fadd_rn(acc, __fmul_rn(G[r], col[(long long)r * nq]));
-    float s = acc;
-    if (M.kind == FRMC_KIND_SQ) {
-        s = __fadd_rn(s, 1.0f);
-        if (M.scale != 1.0f) s = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(s, 1.0f)), 1.0f);   // scale*(Sq-1)+1  (:775-778)
-    } else {
-        if (M.scale != 1.0f) s = __fmul_rn(M.scale, s);                                      // (:1258-1260)
-    }
-    if (q < M.n_out) M.total[q] = s;
-}
-
+// ------------------------------------------------------------------ kernels: fused epilogue
 // numpy's pairwise float32 summation (numpy/_core/src/umath/loops_utils.h.src,
 // FLOAT_pairwise_sum): blocks of <=128 summed with 8 interleaved accumulators combined as
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), remainder added sequentially, larger arrays split
 // at n/2 rounded down to a multiple of 8.  Reproduced exactly so chi^2 equals
 // np.add.reduce(w*(exp-model)**2) bit for bit (PairDistributionConstraints.py:833-838).
-static const int PW_MAX_LEAVES = 1024;
+static const int PW_MAX_LEAVES = 512;
+static const int EPI_THREADS = 512;
+static const int EPI_MAX_PAIRS = FRMC_MAX_ELEMENTS * (FRMC_MAX_ELEMENTS + 1) / 2;
 
-__device__ float pairwise_combine(const float *leafsum, int n)
-{
-    struct Frame { int n; int state; float left; };
-    Frame st[40];
-    int sp = 0, next = 0;
-    st[0].n = n; st[0].state = 0; st[0].left = 0.f;
-    float ret = 0.f;
-    while (sp >= 0) {
-        Frame &f = st[sp];
-        if (f.n <= 128) { ret = leafsum[next++]; --sp; continue; }
-        int n2 = f.n / 2; n2 -= n2 % 8;
-        if (f.state == 0) { f.state = 1; ++sp; st[sp].n = n2; st[sp].state = 0; continue; }
-        if (f.state == 1) { f.left = ret; f.state = 2; ++sp; st[sp].n = f.n - n2; st[sp].state = 0; continue; }
-        ret = __fadd_rn(f.left, ret); --sp;
-    }
-    return ret;
-}
+// The recursion tree depends only on n, so the host precomputes it once per model
+// (pairwise_schedule): the leaves (offset, length) left to right, and the post-order list of
+// combine steps val[dst] += val[src] over the leaf sums (n_leaves - 1 steps, result in val[0]).
+struct PairwiseScratch {
+    int leaf_off[PW_MAX_LEAVES];
+    int leaf_len[PW_MAX_LEAVES];
+    int op_dst[PW_MAX_LEAVES];
+    int op_src[PW_MAX_LEAVES];
+    float leaf_sum[PW_MAX_LEAVES];
+};
 
-// chi^2 of every model: one CTA (256 threads) per model.
-__global__ void __launch_bounds__(256)
-chi2_kernel(const ModelDev *__restrict__ models, int n_models, float *__restrict__ chi2_out)
+// whole CTA (EPI_THREADS threads, all must call); v[0..n) in shared memory; the schedule
+// (leaves + combine steps) is already staged in ps; result valid in thread 0
+__device__ float block_pairwise_sum(const float *v, int nl, PairwiseScratch &ps)
 {
-    extern __shared__ float v[];             // [n_out] terms
-    __shared__ int leaf_off[PW_MAX_LEAVES];
-    __shared__ int leaf_len[PW_MAX_LEAVES];
-    __shared__ float leaf_sum[PW_MAX_LEAVES];
-    __shared__ int n_leaves;
-    const int m = blockIdx.x;
-    if (m >= n_models) return;
-    const ModelDev M = models[m];
-    const int n = M.n_out;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float d = __fsub_rn(M.expv[i], M.total[i]);
-        float t = __fmul_rn(d, d);
-        if (M.wts) t = __fmul_rn(M.wts[i], t);
-        v[i] = t;
-    }
-    if (threadIdx.x == 0) {
-        // enumerate the leaves of the recursion left to right
-        int so[40], sn[40], sp = 0, nl = 0;
-        so[0] = 0; sn[0] = n;
-        while (sp >= 0) {
-            int o = so[sp], c = sn[sp]; --sp;
-            if (c <= 128) { leaf_off[nl] = o; leaf_len[nl] = c; ++nl; continue; }
-            int n2 = c / 2; n2 -= n2 % 8;
-            ++sp; so[sp] = o + n2; sn[sp] = c - n2;
-            ++sp; so[sp] = o; sn[sp] = n2;
-        }
-        n_leaves = nl;
-    }
-    __syncthreads();
     const int group = threadIdx.x >> 3, lane8 = threadIdx.x & 7;
-    const int nl = n_leaves;
-    for (int base = 0; base < nl; base += 32) {
+    for (int base = 0; base < nl; base += EPI_THREADS / 8) {
         const int l = base + group;
         const bool live = l < nl;
-        const int off = live ? leaf_off[l] : 0, len = live ? leaf_len[l] : 0;
+        const int off = live ? ps.leaf_off[l] : 0, len = live ? ps.leaf_len[l] : 0;
         // leaves shorter than 8 (only a whole array with n < 8) are summed sequentially from 0;
         // otherwise lane j owns accumulator r[j].  The shuffles sit on ONE converged code path.
         const bool big = len >= 8;
@@ -350,11 +302,335 @@ chi2_kernel(const ModelDev *__restrict__ models, int n_models, float *__restrict
         float res = big ? r : 0.0f;
         if (live && lane8 == 0) {
             for (int i = main_len; i < len; ++i) res = __fadd_rn(res, v[off + i]);
-            leaf_sum[l] = res;
+            ps.leaf_sum[l] = res;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) chi2_out[m] = pairwise_combine(leaf_sum, n);
+    float out = 0.f;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nl - 1; ++i) ps.leaf_sum[ps.op_dst[i]] = __fadd_rn(ps.leaf_sum[ps.op_dst[i]], ps.leaf_sum[ps.op_src[i]]);
+        out = ps.leaf_sum[0];
+    }
+    return out;
+}
+
+static const int SQ_ROWS = 64;       // matrix rows per cp.async stage (8 KB per 32-column slab)
+static const int SQ_STAGES = 4;
+static const int SQ_WARPS = 2;        // consumer warps per CTA (warps 0 and 4: same SM sub-partition, so one hides the other's LDS latency)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > 50000000u) __trap();     // never hang the GPU on a lost transaction
+}
+
+// (w*n)/D with IEEE rounding.  D is a per-pair constant, so the quotient is formed from the
+// correctly rounded reciprocal with one residual correction (Markstein): q0 = x*rD,
+// r = fma(-q0, D, x) (exact), q = fma(r, rD, q0).  For every pair this shortcut is CHECKED
+// against __fdiv_rn over the whole count range at model registration (validate_fastdiv_kernel);
+// a pair that fails any count keeps the full division (rD = NaN).
+__device__ __forceinline__ float div_by_const(float x, float D, float rD)
+{
+    const float q0 = __fmul_rn(x, rD);
+    const float r = __fmaf_rn(-q0, D, x);
+    return __fmaf_rn(r, rD, q0);
+}
+
+// ok[p] stays 1 iff div_by_const(w*n, D, rD) == __fdiv_rn(w*n, D) for every integer count n in
+// [0, 2^22] and for 2^22 further counts spread up to 2^30 (the int32 running totals' range).
+__global__ void validate_fastdiv_kernel(const float *__restrict__ w, const float *__restrict__ D, int n_pairs, int *__restrict__ ok,
+                                        float *__restrict__ rD_out)
+{
+    const int p = blockIdx.y;
+    if (p >= n_pairs) return;
+    const float wp = w[p], Dp = D[p], rD = __frcp_rn(Dp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) rD_out[p] = rD;
+    bool good = true;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ll << 23); i += (long long)gridDim.x * blockDim.x) {
+        const long long n = (i < (1ll << 22)) ? i : ((i - (1ll << 22)) * 255 + (1ll << 22));
+        const float x = __fmul_rn(wp, (float)(int)n);
+        if (__float_as_uint(div_by_const(x, Dp, rD)) != __float_as_uint(__fdiv_rn(x, Dp))) good = false;
+    }
+    if (!good) ok[p] = 0;
+}
+
+// ONE launch for every model: grid = (max Q slices, n_models), EPI_THREADS threads; the model
+// descriptors travel by value in the kernel parameters.
+//
+//  1. r-space function of the staged state for ALL bins, redundantly per CTA (it only needs the
+//     nsym x hs staged symmetrised totals, L2 resident), mirroring the numpy expressions of
+//     __get_total_Gr / __get_total_gr / __get_total_Sq operation by operation in fp32
+//     (numpy >= 2 scalar promotion: every scalar is fp32):
+//        for pair in sorted pairs:  Gr += (wij*nij)/Dij          (PairDistributionConstraints.py:855-876)
+//        Gr /= shellVolumes                                      (:878)
+//        Gr  = prefactor*(Gr-1)                                  (:881)   [PDF, SQ, RSQ]
+//        Gr -= shape ; Gr *= scale (when != 1)                   (:883-888) [PDF]
+//        PCF: gr -= shape; if scale != 1: gr = 1 + (prefactor*(gr-1)*scale)/prefactor  (PairCorrelationConstraints.py:153-163)
+//     All loads of a thread's bins are issued before any arithmetic (one L2 round trip).
+//  2. PDF/PCF (one CTA): chi^2 with numpy's pairwise order, publish.
+//  3. SQ/RSQ (CTA x owns Q columns [32x, 32x+32)): S(Q_m) = sum_r G(r)*M[r,m] (+1), r in index
+//     order, fp32 multiply then fp32 add, no FMA: bit-identical to
+//     np.sum(Gr.reshape((-1,1))*Gr2SqMatrix, axis=0) (StructureFactorConstraints.py:772-773),
+//     which accumulates rows sequentially.  The chain of hs dependent FADDs (4 cycles each) is
+//     the floor, ~2 us at hs=1000.  The matrix is stored pre-tiled ([Q slab][r/4][lane][r%4],
+//     zero padded to 64 rows), so a 64-row chunk of a slab is 8 KB contiguous: warp 0 alone runs
+//     a 4-stage ring of TMA bulk copies (cp.async.bulk + mbarrier, no CTA barrier in the loop),
+//     reads four rows per LDS.128 and keeps the FADD chain fed by forming products 16 rows ahead.
+//     The last CTA to finish (ticket) computes chi^2.
+//  4. publish: chi2 to pinned host memory, system fence, then the per-model launch counter the
+//     host spins on.
+static const unsigned SQ_CHUNK_BYTES = SQ_ROWS * 32 * sizeof(float);
+
+// lane 0 of warp 0 only
+__device__ __forceinline__ void sq_issue(const ModelDev &M, float *ring, unsigned long long *mbar, int slab, int chunk, int n_chunks)
+{
+    if (chunk < n_chunks) {
+        const int stage = chunk % SQ_STAGES;
+        const float *src = M.gr2sq + ((size_t)slab * n_chunks + chunk) * (SQ_ROWS * 32);
+        mbar_expect_tx(&mbar[stage], SQ_CHUNK_BYTES);
+        bulk_g2s(ring + stage * (SQ_ROWS * 32), src, SQ_CHUNK_BYTES, &mbar[stage]);
+    }
+}
+
+__global__ void __launch_bounds__(EPI_THREADS, 1)
+epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
+                unsigned int *__restrict__ dev_seq, volatile unsigned int *__restrict__ host_seq,
+                unsigned int *__restrict__ tickets, long long *__restrict__ stamps)
+{
+#define EPI_STAMP(i) do { if (stamps && threadIdx.x == 0 && blockIdx.x == 0) { stamps[blockIdx.y * 8 + (i)] = clock64(); \
+        unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[64 + blockIdx.y * 8 + (i)] = (long long)gt_; } } while (0)
+    extern __shared__ __align__(16) float epi_smem[];   // [hs_pad] G(r) | [out_pad] chi2 terms | SQ: ring [SQ_STAGES][SQ_ROWS][32]
+    __shared__ int s_psym[EPI_MAX_PAIRS + 16];
+    __shared__ float s_w[EPI_MAX_PAIRS + 16], s_D[EPI_MAX_PAIRS + 16], s_rD[EPI_MAX_PAIRS + 16];
+    __shared__ PairwiseScratch ps;
+    __shared__ int s_last;
+    __shared__ __align__(8) unsigned long long mbar_all[SQ_WARPS * SQ_STAGES];
+    EPI_STAMP(0);
+
+    const int m = blockIdx.y;
+    if (m >= ms.n) return;
+    const ModelDev &M = ms.m[m];
+    const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
+    const int hs = M.hs, nq = M.n_out;
+    const int nblk = is_sq ? (nq + 32 * SQ_WARPS - 1) / (32 * SQ_WARPS) : 1;
+    if ((int)blockIdx.x >= nblk) return;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int hs_pad = (hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS;
+    // consumer warps: warp 0 -> Q slab 2x, warp 4 -> Q slab 2x+1 (each its own ring and mbarriers)
+    const int cw = (wrp == 0) ? 0 : ((wrp == 4) ? 1 : -1);
+    const int slab = blockIdx.x * SQ_WARPS + (cw < 0 ? 0 : cw);
+    const int q0 = slab * 32;
+    const bool consumer = is_sq && cw >= 0 && q0 < nq;
+    float *ring = epi_smem + (cw < 0 ? 0 : cw) * (SQ_STAGES * SQ_ROWS * 32);   // first: keeps the TMA destinations 128-byte aligned
+    unsigned long long *mbar = mbar_all + (cw < 0 ? 0 : cw) * SQ_STAGES;
+    float *sG = epi_smem + (is_sq ? SQ_WARPS * SQ_STAGES * SQ_ROWS * 32 : 0);
+    float *sT = sG + hs_pad;
+    const int n_chunks = (hs + SQ_ROWS - 1) / SQ_ROWS;
+
+    // start streaming the matrix before anything else: it overlaps the G(r) phase
+    if (consumer) {
+        if (lane == 0) {
+            for (int st = 0; st < SQ_STAGES; ++st) mbar_init(&mbar[st], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            for (int c = 0; c < SQ_STAGES - 1; ++c) sq_issue(M, ring, mbar, slab, c, n_chunks);
+        }
+        __syncwarp();
+    }
+
+    const int np = M.n_pairs;
+    // pair table, padded to a multiple of 16 with weight-0 entries: (0*n)/1 = 0 and acc+0 == acc
+    const int np_pad = (np + 15) / 16 * 16;
+    for (int p = tid; p < np_pad; p += EPI_THREADS) {
+        const bool real = p < np;
+        s_psym[p] = real ? M.psym[p] : 0; s_w[p] = real ? M.w[p] : 0.0f;
+        s_D[p] = real ? M.D[p] : 1.0f; s_rD[p] = real ? M.rD[p] : 1.0f;
+    }
+    {   // chi^2 summation schedule (needed at the very end; fetched now, off the critical path)
+        const int nl = M.pw_leaves;
+        for (int i = tid; i < nl; i += EPI_THREADS) {
+            ps.leaf_off[i] = M.pw_sched[i]; ps.leaf_len[i] = M.pw_sched[nl + i];
+            ps.op_dst[i] = M.pw_sched[2 * nl + i]; ps.op_src[i] = M.pw_sched[3 * nl + i];
+        }
+    }
+    for (int r = hs + tid; r < hs_pad; r += EPI_THREADS) sG[r] = 0.0f;
+    __syncthreads();
+    EPI_STAMP(1);
+
+    // ---- 1. r-space function: EPI_BINS bins per thread per round, all loads first
+    {
+        const int *__restrict__ stot = gs.grid[M.grid].stot;
+        constexpr int EPI_BINS = 2, PB = 16;
+        for (int rb = tid; rb < hs; rb += EPI_BINS * EPI_THREADS) {
+            float acc[EPI_BINS];
+#pragma unroll
+            for (int j = 0; j < EPI_BINS; ++j) acc[j] = 0.0f;
+            for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_pad); p0 += PB) {
+                int c[EPI_BINS][PB];
+#pragma unroll
+                for (int j = 0; j < EPI_BINS; ++j) {
+                    const int r = min(rb + j * EPI_THREADS, hs - 1);
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) c[j][u] = stot[(long long)s_psym[p0 + u] * hs + r];
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const float w = s_w[p0 + u], D = s_D[p0 + u], rD = s_rD[p0 + u];
+                    if (rD == rD) {                       // block-uniform: proven 3-op exact division
+#pragma unroll
+                        for (int j = 0; j < EPI_BINS; ++j)
+                            acc[j] = __fadd_rn(acc[j], div_by_const(__fmul_rn(w, (float)c[j][u]), D, rD));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < EPI_BINS; ++j)
+                            acc[j] = __fadd_rn(acc[j], __fdiv_rn(__fmul_rn(w, (float)c[j][u]), D));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < EPI_BINS; ++j) {
+                const int r = rb + j * EPI_THREADS;
+                if (r >= hs) continue;
+                float a = __fdiv_rn(acc[j], M.sv[r]);
+                float out;
+                if (M.kind == FRMC_KIND_PCF) {
+                    out = a;
+                    if (M.shape) out = __fsub_rn(out, M.shape[r]);
+                    if (M.scale != 1.0f) {
+                        float Gr = __fmul_rn(M.pref[r], __fsub_rn(out, 1.0f));
+                        Gr = __fmul_rn(Gr, M.scale);
+                        out = __fadd_rn(1.0f, __fdiv_rn(Gr, M.pref[r]));
+                    }
+                } else {
+                    out = __fmul_rn(M.pref[r], __fsub_rn(a, 1.0f));
+                    if (M.kind == FRMC_KIND_PDF) {
+                        if (M.shape) out = __fsub_rn(out, M.shape[r]);
+                        if (M.scale != 1.0f) out = __fmul_rn(out, M.scale);
+                    }
+                }
+                sG[r] = out;
+                if (blockIdx.x == 0) {
+                    M.rfun[r] = out;
+                    if (!is_sq) M.total[r] = out;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    EPI_STAMP(2);
+
+    float chi2 = 0.f;
+    if (!is_sq) {
+        // ---- 2. chi^2 of an r-space model
+        for (int i = tid; i < hs; i += EPI_THREADS) {
+            float d = __fsub_rn(M.expv[i], sG[i]);
+            float t = __fmul_rn(d, d);
+            if (M.wts) t = __fmul_rn(M.wts[i], t);
+            sT[i] = t;
+        }
+        __syncthreads();
+        chi2 = block_pairwise_sum(sT, M.pw_leaves, ps);
+    } else {
+        // ---- 3. S(Q) slice: single-warp producer/consumer over the TMA ring
+        if (consumer) {
+            float acc = 0.0f;
+            for (int c = 0; c < ((M.sq_exact & 2) ? 0 : n_chunks); ++c) {
+                const int stage = c % SQ_STAGES;
+                if (lane == 0) sq_issue(M, ring, mbar, slab, c + SQ_STAGES - 1, n_chunks);   // refills the stage consumed last iteration
+                mbar_wait(&mbar[stage], (unsigned)((c / SQ_STAGES) & 1));
+                const float4 *mt = reinterpret_cast<const float4 *>(ring + stage * (SQ_ROWS * 32)) + lane;   // [r/4][lane]
+                const float4 *gv = reinterpret_cast<const float4 *>(sG + c * SQ_ROWS);                     // [r/4]
+                float prod[16], nxt[16];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 a = mt[u * 32], g = gv[u];
+                    prod[4 * u] = __fmul_rn(g.x, a.x); prod[4 * u + 1] = __fmul_rn(g.y, a.y);
+                    prod[4 * u + 2] = __fmul_rn(g.z, a.z); prod[4 * u + 3] = __fmul_rn(g.w, a.w);
+                }
+#pragma unroll
+                for (int b = 0; b < SQ_ROWS / 4; b += 4) {
+                    if (b + 4 < SQ_ROWS / 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 a = mt[(b + 4 + u) * 32], g = gv[b + 4 + u];
+                            nxt[4 * u] = __fmul_rn(g.x, a.x); nxt[4 * u + 1] = __fmul_rn(g.y, a.y);
+                            nxt[4 * u + 2] = __fmul_rn(g.z, a.z); nxt[4 * u + 3] = __fmul_rn(g.w, a.w);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, prod[u]);   // rows beyond hs are zero rows: acc + 0
+                    if (b + 4 < SQ_ROWS / 4) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) prod[u] = nxt[u];
+                    }
+                }
+                __syncwarp();                          // all lanes done with this stage before it is refilled
+            }
+            if (q0 + lane < nq) {
+                float sv = acc;
+                if (M.kind == FRMC_KIND_SQ) {
+                    sv = __fadd_rn(sv, 1.0f);
+                    if (M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
+                } else {
+                    if (M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                                      // (:1258-1260)
+                }
+                M.total[q0 + lane] = sv;
+            }
+            __threadfence();
+        }
+        EPI_STAMP(3);
+        // last CTA of this model (ticket) owns the chi^2
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int t = atomicAdd(&tickets[m], 1u);
+            s_last = (t == (unsigned int)(nblk - 1));
+            if (s_last) tickets[m] = 0u;               // re-arm for the next launch
+        }
+        __syncthreads();
+        EPI_STAMP(4);
+        if (!s_last) return;
+        __threadfence();
+        for (int i = tid; i < nq; i += EPI_THREADS) {
+            float d = __fsub_rn(M.expv[i], __ldcg(M.total + i));
+            float t = __fmul_rn(d, d);
+            if (M.wts) t = __fmul_rn(M.wts[i], t);
+            sT[i] = t;
+        }
+        __syncthreads();
+        chi2 = block_pairwise_sum(sT, M.pw_leaves, ps);
+    }
+    // ---- 4. publish
+    if (stamps && tid == 0) stamps[blockIdx.y * 8 + 5] = clock64();
+    if (tid == 0) {
+        chi2_out[m] = chi2;
+        __threadfence_system();
+        const unsigned int v = dev_seq[m] + 1u;
+        dev_seq[m] = v;
+        host_seq[m] = v;
+    }
 }
 
 }  // namespace frmc
@@ -384,27 +660,28 @@ struct frmc_store {
     std::vector<int32_t> h_mol, h_el;
     float4 *d_atoms = nullptr;
     uint32_t *d_orig = nullptr;
-    int32_t *d_inv = nullptr;
     WorkItem *d_items = nullptr;
     int n_items = 0, R = 1;
     int items_shard = -1, items_nshards = -1;   // which slice of the work list d_items holds
     int64_t chunkJ = 256;
-    HostLayout lay;                  // rec freed after upload; segments + inv kept
+    HostLayout lay;                  // rec freed after upload; segments + inverse permutation kept
     int *d_next = nullptr;
     unsigned long long *d_overflow = nullptr;
     std::vector<GridHost> grids;
     std::vector<ModelHost> models;
-    ModelDev *d_models = nullptr;
     bool models_dirty = true;
-    ProposalIn *h_prop = nullptr;    // pinned
-    ProposalIn *d_prop_in = nullptr;
+    ProposalIn prop_in;              // staged proposal, handed to the delta kernel by value
     Proposal *d_prop = nullptr;
-    float *h_chi2 = nullptr;         // pinned, device-visible
+    float *h_chi2 = nullptr;         // pinned, device-visible: [FRMC_MAX_MODELS] chi2 then [FRMC_MAX_MODELS] u32 sequence numbers
+    volatile unsigned int *h_seq = nullptr;
+    unsigned int *d_seq = nullptr;   // [FRMC_MAX_MODELS] launch counters + [FRMC_MAX_MODELS] tickets
+    long long *d_stamps = nullptr;   // [FRMC_MAX_MODELS][8] clock64 phase stamps of the last epilogue (debug)
+    unsigned int seq_expected = 0;
+    size_t epi_smem = 0;
     float prop_lo[3], prop_hi[3];
     int state = 0;                   // 0 idle, 1 proposal staged
     float chi2_staged[FRMC_MAX_MODELS];
     float chi2_committed[FRMC_MAX_MODELS];
-    uint64_t overflow_total = 0;
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -470,12 +747,10 @@ static int upload_layout(frmc_store *s, const float *coords)
     if (!s->d_atoms) {
         FRMC_CUDA(cudaMalloc(&s->d_atoms, sizeof(float4) * std::max<int64_t>(s->npad, 1)));
         FRMC_CUDA(cudaMalloc(&s->d_orig, sizeof(uint32_t) * std::max<int64_t>(s->npad, 1)));
-        FRMC_CUDA(cudaMalloc(&s->d_inv, sizeof(int32_t) * std::max<int64_t>(s->n, 1)));
     }
     if (s->npad > 0) {
         FRMC_CUDA(cudaMemcpyAsync(s->d_atoms, s->lay.rec.data(), sizeof(float4) * s->npad, cudaMemcpyHostToDevice, s->stream));
         FRMC_CUDA(cudaMemcpyAsync(s->d_orig, s->lay.orig.data(), sizeof(uint32_t) * s->npad, cudaMemcpyHostToDevice, s->stream));
-        FRMC_CUDA(cudaMemcpyAsync(s->d_inv, s->lay.inv.data(), sizeof(int32_t) * s->n, cudaMemcpyHostToDevice, s->stream));
     }
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     std::vector<float>().swap(s->lay.rec);
@@ -502,17 +777,33 @@ static int upload_items(frmc_store *s, int shard, int nshards)
 static int sync_models(frmc_store *s)
 {
     if (!s->models_dirty) return FRMC_OK;
-    std::vector<ModelDev> tmp;
-    for (auto &m : s->models) tmp.push_back(m.dev);
-    if (!s->d_models) FRMC_CUDA(cudaMalloc(&s->d_models, sizeof(ModelDev) * FRMC_MAX_MODELS));
-    if (!tmp.empty())
-        FRMC_CUDA(cudaMemcpyAsync(s->d_models, tmp.data(), sizeof(ModelDev) * tmp.size(), cudaMemcpyHostToDevice, s->stream));
-    FRMC_CUDA(cudaStreamSynchronize(s->stream));   // tmp goes out of scope
+    size_t smem = 0;
+    for (auto &m : s->models) {
+        const bool is_sq = (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ);
+        size_t need = sizeof(float) * ((size_t)(m.dev.hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS + (size_t)(m.dev.n_out + 31) / 32 * 32 +
+                                       (is_sq ? (size_t)SQ_WARPS * SQ_STAGES * SQ_ROWS * 32 : 0));
+        smem = std::max(smem, need);
+    }
+    FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "model needs %zu B of shared memory in the epilogue (limit 200 KiB)", smem);
+    FRMC_CUDA(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    // one shared-memory carveout for every kernel of the per-move pipeline: consecutive launches
+    // with different carveouts make the SMs reconfigure (and drain) in between
+    const int carve = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(commit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(clear_delta_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(delta_kernel<MODE_IBC>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(delta_kernel<MODE_ORTHO_FAST>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(delta_kernel<MODE_TRI_FAST>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(delta_kernel<MODE_ORTHO_GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(delta_kernel<MODE_TRI_GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaGetLastError();
+    s->epi_smem = smem;
     s->models_dirty = false;
     return FRMC_OK;
 }
 
-// totals + chi^2 of every model from (counts + delta); results land in s->h_chi2 after a stream sync
+// totals + chi^2 of every model from the staged totals; results land in s->h_chi2 once h_seq == seq_expected
 static int launch_epilogue(frmc_store *s)
 {
     const int nm = (int)s->models.size();
@@ -520,31 +811,76 @@ static int launch_epilogue(frmc_store *s)
     int rc = sync_models(s);
     if (rc) return rc;
     GridSet gs = make_gridset(s);
-    int max_hs = 0, max_out = 0, max_q = 0;
-    for (auto &m : s->models) {
-        max_hs = std::max(max_hs, m.dev.hs);
-        max_out = std::max(max_out, m.dev.n_out);
-        if (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ) max_q = std::max(max_q, m.dev.n_out);
+    ModelSet ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = nm;
+    int max_q = 1;
+    for (int i = 0; i < nm; ++i) {
+        ms.m[i] = s->models[i].dev;
+        if (ms.m[i].kind == FRMC_KIND_SQ || ms.m[i].kind == FRMC_KIND_RSQ) max_q = std::max(max_q, ms.m[i].n_out);
     }
     cudaEvent_t t0 = timing_begin(s);
-    dim3 g1((unsigned)((max_hs + 127) / 128), (unsigned)nm);
-    rfun_kernel<<<g1, 128, 0, s->stream>>>(s->d_models, nm, gs, s->nEl);
-    FRMC_LAUNCH_CHECK();
-    if (max_q > 0) {
-        dim3 g2((unsigned)((max_q + 31) / 32), (unsigned)nm);
-        sq_kernel<<<g2, 32, 0, s->stream>>>(s->d_models, nm);
-        FRMC_LAUNCH_CHECK();
-    }
-    size_t smem = sizeof(float) * (size_t)max_out;
-    if (smem > 40 * 1024) FRMC_CUDA(cudaFuncSetAttribute(chi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chi2_kernel<<<nm, 256, smem, s->stream>>>(s->d_models, nm, s->h_chi2);
+    dim3 grid((unsigned)((max_q + 32 * SQ_WARPS - 1) / (32 * SQ_WARPS)), (unsigned)nm);
+    epilogue_kernel<<<grid, EPI_THREADS, s->epi_smem, s->stream>>>(ms, gs, s->h_chi2, s->d_seq, s->h_seq,
+                                                                   s->d_seq + FRMC_MAX_MODELS, s->d_stamps);
     FRMC_LAUNCH_CHECK();
     timing_end(s, TIME_EPILOGUE, t0);
     return FRMC_OK;
 }
 
+// wait for the epilogue of the launch numbered s->seq_expected: spin on the pinned per-model
+// counters the epilogue publishes (a few hundred ns after the kernel retires), falling back
+// to a stream synchronise to surface errors.
+static int wait_epilogue(frmc_store *s)
+{
+    const size_t nm = s->models.size();
+    if (nm == 0 || s->timing) { FRMC_CUDA(cudaStreamSynchronize(s->stream)); timing_flush(s); return FRMC_OK; }
+    unsigned long long spins = 0;
+    for (size_t m = 0; m < nm; ++m) {
+        while (s->h_seq[m] != s->seq_expected) {
+            _mm_pause();
+            if ((++spins & 0xFFFFF) == 0) {           // every ~1M polls: make sure the stream is still alive
+                cudaError_t e = cudaStreamQuery(s->stream);
+                if (e == cudaSuccess) break;          // finished without publishing -> checked below
+                if (e != cudaErrorNotReady) { set_error("stream error while waiting for chi2: %s", cudaGetErrorString(e)); return FRMC_ECUDA; }
+            }
+        }
+        if (s->h_seq[m] != s->seq_expected) {
+            FRMC_CUDA(cudaStreamSynchronize(s->stream));
+            FRMC_REQUIRE(s->h_seq[m] == s->seq_expected, FRMC_ECUDA, "epilogue finished without publishing chi2 (seq %u, expected %u)",
+                         (unsigned)s->h_seq[m], s->seq_expected);
+        }
+    }
+    return FRMC_OK;
+}
+
+// numpy's FLOAT_pairwise_sum recursion for n terms, flattened: leaves left to right and the
+// post-order combine steps (the left child's result lives in its first leaf's slot).
+static int pairwise_walk(int o, int c, std::vector<int> &off, std::vector<int> &len, std::vector<int> &dst, std::vector<int> &src)
+{
+    if (c <= 128) { off.push_back(o); len.push_back(c); return (int)off.size() - 1; }
+    int n2 = c / 2; n2 -= n2 % 8;
+    int l = pairwise_walk(o, n2, off, len, dst, src);
+    int r = pairwise_walk(o + n2, c - n2, off, len, dst, src);
+    dst.push_back(l); src.push_back(r);
+    return l;
+}
+
+static void pairwise_schedule(int n, std::vector<int> &sched, int &n_leaves)
+{
+    std::vector<int> off, len, dst, src;
+    pairwise_walk(0, n, off, len, dst, src);
+    n_leaves = (int)off.size();
+    dst.resize(n_leaves, 0); src.resize(n_leaves, 0);
+    sched.clear();
+    sched.insert(sched.end(), off.begin(), off.end());
+    sched.insert(sched.end(), len.begin(), len.end());
+    sched.insert(sched.end(), dst.begin(), dst.end());
+    sched.insert(sched.end(), src.begin(), src.end());
+}
+
 template <typename T>
-static int dev_copy(frmc_store *s, ModelHost &mh, const T *src, size_t count, const T **dst)
+static int dev_copy(ModelHost &mh, const T *src, size_t count, const T **dst)
 {
     *dst = nullptr;
     if (!src || count == 0) return FRMC_OK;
@@ -553,6 +889,71 @@ static int dev_copy(frmc_store *s, ModelHost &mh, const T *src, size_t count, co
     mh.owned.push_back(p);
     FRMC_CUDA(cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice));
     *dst = (const T *)p;
+    return FRMC_OK;
+}
+
+static int current_mode(frmc_store *s, const float *extra_lo, const float *extra_hi)
+{
+    float lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = extra_lo ? std::min(s->lo[c], extra_lo[c]) : s->lo[c];
+        hi[c] = extra_hi ? std::max(s->hi[c], extra_hi[c]) : s->hi[c];
+    }
+    return choose_mode_from_bounds(s->L.b, s->isPBC, lo, hi);
+}
+
+static int launch_cells_grid(frmc_store *s)
+{
+    long long cells = 0;
+    for (auto &g : s->grids) cells = std::max(cells, 2 * g.dev.cells);
+    return (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 2));
+}
+
+// the per-move pipeline: delta pass (proposal by value) + fused epilogue, two launches
+static int launch_propose(frmc_store *s, int mode)
+{
+    GridSet gs = make_gridset(s);
+    long long want = (s->npad + 256 * DELTA_UNROLL - 1) / (256 * DELTA_UNROLL);
+    long long cap = (long long)s->ctx->sm_count * 8;
+    int grid = (int)std::max<long long>(1, std::min(want, cap));
+#define LAUNCH_DELTA(M) delta_kernel<M><<<grid, 256, 0, s->stream>>>(s->d_atoms, (int)s->npad, s->prop_in, s->d_prop, s->L, gs, s->nEl, s->d_overflow)
+    cudaEvent_t t0 = timing_begin(s);
+    switch (mode) {
+        case MODE_IBC: LAUNCH_DELTA(MODE_IBC); break;
+        case MODE_ORTHO_FAST: LAUNCH_DELTA(MODE_ORTHO_FAST); break;
+        case MODE_TRI_FAST: LAUNCH_DELTA(MODE_TRI_FAST); break;
+        case MODE_ORTHO_GEN: LAUNCH_DELTA(MODE_ORTHO_GEN); break;
+        default: LAUNCH_DELTA(MODE_TRI_GEN); break;
+    }
+#undef LAUNCH_DELTA
+    FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_DELTA, t0);
+    return launch_epilogue(s);
+}
+
+static int stage_proposal(frmc_store *s, const int32_t *indexes, int k, const float *moved)
+{
+    FRMC_REQUIRE(s && indexes && moved, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group size %d outside 1..%d", k, FRMC_MAX_GROUP);
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is already staged; accept or reject it first");
+    FRMC_REQUIRE(!s->grids.empty(), FRMC_ESTATE, "no grid registered");
+    for (auto &g : s->grids) FRMC_REQUIRE(g.valid, FRMC_ESTATE, "call frmc_compute_data before proposing moves");
+    ProposalIn &h = s->prop_in;
+    h.k = k;
+    for (int c = 0; c < 3; ++c) { s->prop_lo[c] = INFINITY; s->prop_hi[c] = -INFINITY; }
+    bool finite = true;
+    for (int t = 0; t < k; ++t) {
+        FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", indexes[t], (long long)s->n - 1);
+        h.pos[t] = s->lay.inv[indexes[t]];
+        for (int c = 0; c < 3; ++c) {
+            float v = moved[3 * t + c];
+            h.moved[3 * t + c] = v;
+            if (!(v == v) || isinf(v)) finite = false;
+            s->prop_lo[c] = std::min(s->prop_lo[c], v);
+            s->prop_hi[c] = std::max(s->prop_hi[c], v);
+        }
+    }
+    FRMC_REQUIRE(finite, FRMC_EINVAL, "moved coordinates contain NaN or Inf");
     return FRMC_OK;
 }
 
@@ -570,6 +971,7 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     for (int i = 0; i < 9; ++i) s->L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     s->h_mol.assign(mol, mol + n);
     s->h_el.assign(el, el + n);
+    memset(&s->prop_in, 0, sizeof(s->prop_in));
     auto fail = [&](const char *what) -> frmc_store * {
         std::string msg = std::string(what) + ": " + frmc_last_error();
         frmc_store_destroy(s);
@@ -582,10 +984,15 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     if (cudaMalloc(&s->d_next, sizeof(int) * 4) != cudaSuccess) return fail("alloc");
     if (cudaMalloc(&s->d_overflow, sizeof(unsigned long long)) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_overflow, 0, sizeof(unsigned long long));
-    if (cudaMalloc(&s->d_prop_in, sizeof(ProposalIn)) != cudaSuccess) return fail("alloc");
     if (cudaMalloc(&s->d_prop, sizeof(Proposal)) != cudaSuccess) return fail("alloc");
-    if (cudaMallocHost(&s->h_prop, sizeof(ProposalIn)) != cudaSuccess) return fail("pinned alloc");
-    if (cudaHostAlloc(&s->h_chi2, sizeof(float) * FRMC_MAX_MODELS, cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
+    cudaMemset(s->d_prop, 0, sizeof(Proposal));
+    if (cudaHostAlloc(&s->h_chi2, sizeof(float) * 2 * FRMC_MAX_MODELS, cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
+    s->h_seq = reinterpret_cast<volatile unsigned int *>(s->h_chi2 + FRMC_MAX_MODELS);
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) s->h_seq[i] = 0u;
+    if (cudaMalloc(&s->d_seq, sizeof(unsigned int) * 2 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
+    cudaMemset(s->d_seq, 0, sizeof(unsigned int) * 2 * FRMC_MAX_MODELS);
+    if (cudaMalloc(&s->d_stamps, sizeof(long long) * 16 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
+    cudaMemset(s->d_stamps, 0, sizeof(long long) * 16 * FRMC_MAX_MODELS);
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) { s->h_chi2[i] = 0.f; s->chi2_staged[i] = 0.f; s->chi2_committed[i] = 0.f; }
     return s;
 }
@@ -598,12 +1005,11 @@ void frmc_store_destroy(frmc_store *s)
     for (auto &m : s->models) {
         for (void *p : m.owned) cudaFree(p);
     }
-    for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); }
-    cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_inv); cudaFree(s->d_items); cudaFree(s->d_next);
-    cudaFree(s->d_overflow); cudaFree(s->d_models); cudaFree(s->d_prop_in); cudaFree(s->d_prop);
+    for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); cudaFree(g.dev.tot); cudaFree(g.dev.stot); }
+    cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next);
+    cudaFree(s->d_overflow); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps);
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
-    if (s->h_prop) cudaFreeHost(s->h_prop);
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -622,7 +1028,7 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
     for (auto &g : s->grids) g.valid = false;
     s->state = 0;
     GridSet gs = make_gridset(s);
-    if (gs.n) { clear_delta_kernel<<<s->ctx->sm_count, 256, 0, s->stream>>>(gs); FRMC_LAUNCH_CHECK(); }
+    if (gs.n) { clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs); FRMC_LAUNCH_CHECK(); }
     return FRMC_OK;
 }
 
@@ -648,12 +1054,19 @@ int frmc_grid_add(frmc_store *s, float rmin, float rmax, float bin, int hs)
     FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "cannot add a grid while a proposal is staged");
     FRMC_CUDA(cudaSetDevice(s->dev));
     GridHost gh;
+    memset(&gh.dev, 0, sizeof(gh.dev));
     gh.dev.g = make_grid(rmin, rmax, bin, hs);
+    gh.dev.nsym = s->nEl * (s->nEl + 1) / 2;
     gh.dev.cells = (long long)s->nEl * s->nEl * hs;
+    const long long ns = (long long)gh.dev.nsym * hs;
     FRMC_CUDA(cudaMalloc(&gh.dev.counts, sizeof(unsigned long long) * 2 * gh.dev.cells));
     FRMC_CUDA(cudaMalloc(&gh.dev.delta, sizeof(int) * 2 * gh.dev.cells));
+    FRMC_CUDA(cudaMalloc(&gh.dev.tot, sizeof(int) * ns));
+    FRMC_CUDA(cudaMalloc(&gh.dev.stot, sizeof(int) * ns));
     FRMC_CUDA(cudaMemsetAsync(gh.dev.counts, 0, sizeof(unsigned long long) * 2 * gh.dev.cells, s->stream));
     FRMC_CUDA(cudaMemsetAsync(gh.dev.delta, 0, sizeof(int) * 2 * gh.dev.cells, s->stream));
+    FRMC_CUDA(cudaMemsetAsync(gh.dev.tot, 0, sizeof(int) * ns, s->stream));
+    FRMC_CUDA(cudaMemsetAsync(gh.dev.stot, 0, sizeof(int) * ns, s->stream));
     s->grids.push_back(gh);
     return (int)s->grids.size() - 1;
 }
@@ -664,32 +1077,73 @@ int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *d)
     FRMC_REQUIRE(grid >= 0 && grid < (int)s->grids.size(), FRMC_EINVAL, "unknown grid %d", grid);
     FRMC_REQUIRE(s->models.size() < FRMC_MAX_MODELS, FRMC_ELIMIT, "at most %d models per store", FRMC_MAX_MODELS);
     FRMC_REQUIRE(d->kind >= FRMC_KIND_PDF && d->kind <= FRMC_KIND_RSQ, FRMC_EINVAL, "unknown model kind %d", d->kind);
-    FRMC_REQUIRE(d->n_pairs >= 1 && d->pair_a && d->pair_b && d->pair_w && d->pair_D, FRMC_EINVAL, "bad pair table");
+    FRMC_REQUIRE(d->n_pairs >= 1 && d->n_pairs <= EPI_MAX_PAIRS && d->pair_a && d->pair_b && d->pair_w && d->pair_D,
+                 FRMC_EINVAL, "bad pair table (n_pairs=%d)", d->n_pairs);
     FRMC_REQUIRE(d->shell_volumes && d->prefactor && d->experimental && d->n_out >= 1, FRMC_EINVAL, "missing model arrays");
     const int hs = s->grids[grid].dev.g.hs;
     const bool is_sq = (d->kind == FRMC_KIND_SQ || d->kind == FRMC_KIND_RSQ);
     FRMC_REQUIRE(is_sq ? (d->gr2sq != nullptr) : (d->n_out == hs), FRMC_EINVAL,
                  "model output length %d inconsistent with grid histSize %d", d->n_out, hs);
-    FRMC_REQUIRE(d->n_out <= 128 * PW_MAX_LEAVES / 2, FRMC_ELIMIT, "model output too long (%d)", d->n_out);
-    for (int p = 0; p < d->n_pairs; ++p)
+    FRMC_REQUIRE(d->n_out <= 64 * PW_MAX_LEAVES, FRMC_ELIMIT, "model output too long (%d)", d->n_out);
+    std::vector<int> psym(d->n_pairs);
+    for (int p = 0; p < d->n_pairs; ++p) {
         FRMC_REQUIRE(d->pair_a[p] >= 0 && d->pair_a[p] < s->nEl && d->pair_b[p] >= 0 && d->pair_b[p] < s->nEl,
                      FRMC_EINVAL, "pair %d references an element outside 0..%d", p, s->nEl - 1);
+        psym[p] = sym_index(d->pair_a[p], d->pair_b[p], s->nEl);
+    }
     FRMC_CUDA(cudaSetDevice(s->dev));
     ModelHost mh;
     memset(&mh.dev, 0, sizeof(mh.dev));
     mh.dev.kind = d->kind; mh.dev.grid = grid; mh.dev.n_pairs = d->n_pairs; mh.dev.n_out = d->n_out;
     mh.dev.hs = hs; mh.dev.sq_exact = d->sq_exact; mh.dev.scale = d->scale;
     int rc;
-    if ((rc = dev_copy(s, mh, d->pair_a, d->n_pairs, &mh.dev.pa))) return rc;
-    if ((rc = dev_copy(s, mh, d->pair_b, d->n_pairs, &mh.dev.pb))) return rc;
-    if ((rc = dev_copy(s, mh, d->pair_w, d->n_pairs, &mh.dev.w))) return rc;
-    if ((rc = dev_copy(s, mh, d->pair_D, d->n_pairs, &mh.dev.D))) return rc;
-    if ((rc = dev_copy(s, mh, d->shell_volumes, hs, &mh.dev.sv))) return rc;
-    if ((rc = dev_copy(s, mh, d->prefactor, hs, &mh.dev.pref))) return rc;
-    if ((rc = dev_copy(s, mh, d->shape, hs, &mh.dev.shape))) return rc;
-    if ((rc = dev_copy(s, mh, d->experimental, d->n_out, &mh.dev.expv))) return rc;
-    if ((rc = dev_copy(s, mh, d->data_weights, d->n_out, &mh.dev.wts))) return rc;
-    if (is_sq && (rc = dev_copy(s, mh, d->gr2sq, (size_t)hs * d->n_out, &mh.dev.gr2sq))) return rc;
+    if ((rc = dev_copy(mh, psym.data(), (size_t)d->n_pairs, &mh.dev.psym))) return rc;
+    if ((rc = dev_copy(mh, d->pair_w, (size_t)d->n_pairs, &mh.dev.w))) return rc;
+    if ((rc = dev_copy(mh, d->pair_D, (size_t)d->n_pairs, &mh.dev.D))) return rc;
+    {   // reciprocal table for the 3-op exact division, each pair validated on the device
+        int *d_ok = nullptr;
+        float *d_rD = nullptr;
+        std::vector<int> ok((size_t)d->n_pairs, 1);
+        std::vector<float> rD((size_t)d->n_pairs, 0.f);
+        FRMC_CUDA(cudaMalloc(&d_ok, sizeof(int) * d->n_pairs));
+        FRMC_CUDA(cudaMalloc(&d_rD, sizeof(float) * d->n_pairs));
+        FRMC_CUDA(cudaMemcpy(d_ok, ok.data(), sizeof(int) * d->n_pairs, cudaMemcpyHostToDevice));
+        validate_fastdiv_kernel<<<dim3(64, (unsigned)d->n_pairs), 256, 0, s->stream>>>(mh.dev.w, mh.dev.D, d->n_pairs, d_ok, d_rD);
+        ++g_launch_count;
+        cudaError_t e = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(ok.data(), d_ok, sizeof(int) * d->n_pairs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(rD.data(), d_rD, sizeof(float) * d->n_pairs, cudaMemcpyDeviceToHost);
+        cudaFree(d_ok); cudaFree(d_rD);
+        if (e != cudaSuccess) { set_error("fast-division validation failed: %s", cudaGetErrorString(e)); return FRMC_ECUDA; }
+        for (int p = 0; p < d->n_pairs; ++p) {
+            const float Dp = d->pair_D[p];
+            const bool sane = (Dp == Dp) && !isinf(Dp) && fabsf(Dp) > 1e-30f && fabsf(Dp) < 1e30f && (rD[p] == rD[p]);
+            if (!(ok[p] && sane)) rD[p] = __builtin_nanf("");
+        }
+        if ((rc = dev_copy(mh, (const float *)rD.data(), rD.size(), &mh.dev.rD))) return rc;
+    }
+    if ((rc = dev_copy(mh, d->shell_volumes, (size_t)hs, &mh.dev.sv))) return rc;
+    if ((rc = dev_copy(mh, d->prefactor, (size_t)hs, &mh.dev.pref))) return rc;
+    if ((rc = dev_copy(mh, d->shape, (size_t)hs, &mh.dev.shape))) return rc;
+    if ((rc = dev_copy(mh, d->experimental, (size_t)d->n_out, &mh.dev.expv))) return rc;
+    if ((rc = dev_copy(mh, d->data_weights, (size_t)d->n_out, &mh.dev.wts))) return rc;
+    if (is_sq) {
+        // pre-tiled, zero-padded copy: [Q slab of 32][r/4][lane][r%4], rows padded to a multiple of SQ_ROWS,
+        // so that one 64-row chunk of one slab is 8 KB contiguous (one TMA bulk copy) and four
+        // consecutive rows of a column sit in one 16-byte word
+        const int nslab = (d->n_out + 31) / 32;
+        const int rows_pad = (hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS;
+        mh.dev.nq_pad = nslab * 32;
+        std::vector<float> tiled((size_t)nslab * rows_pad * 32, 0.0f);
+        for (int r = 0; r < hs; ++r)
+            for (int q = 0; q < d->n_out; ++q)
+                tiled[(((size_t)(q / 32) * (rows_pad / 4) + r / 4) * 32 + (q % 32)) * 4 + (r % 4)] = d->gr2sq[(size_t)r * d->n_out + q];
+        if ((rc = dev_copy(mh, (const float *)tiled.data(), tiled.size(), &mh.dev.gr2sq))) return rc;
+    }
+    std::vector<int> sched;
+    pairwise_schedule(d->n_out, sched, mh.dev.pw_leaves);
+    FRMC_REQUIRE(mh.dev.pw_leaves <= PW_MAX_LEAVES, FRMC_ELIMIT, "model output too long (%d)", d->n_out);
+    if ((rc = dev_copy(mh, (const int *)sched.data(), sched.size(), &mh.dev.pw_sched))) return rc;
     void *p = nullptr;
     FRMC_CUDA(cudaMalloc(&p, sizeof(float) * hs)); mh.owned.push_back(p); mh.dev.rfun = (float *)p;
     FRMC_CUDA(cudaMalloc(&p, sizeof(float) * d->n_out)); mh.owned.push_back(p); mh.dev.total = (float *)p;
@@ -707,16 +1161,6 @@ int frmc_model_set_scale(frmc_store *s, int model, float scale)
     s->models[model].dev.scale = scale;
     s->models_dirty = true;
     return FRMC_OK;
-}
-
-static int current_mode(frmc_store *s, const float *extra_lo, const float *extra_hi)
-{
-    float lo[3], hi[3];
-    for (int c = 0; c < 3; ++c) {
-        lo[c] = extra_lo ? std::min(s->lo[c], extra_lo[c]) : s->lo[c];
-        hi[c] = extra_hi ? std::max(s->hi[c], extra_hi[c]) : s->hi[c];
-    }
-    return choose_mode_from_bounds(s->L.b, s->isPBC, lo, hi);
 }
 
 int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
@@ -755,12 +1199,22 @@ int frmc_finalize_data(frmc_store *s, float *chi2)
 {
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
     FRMC_CUDA(cudaSetDevice(s->dev));
+    for (auto &g : s->grids) {
+        const long long ns = (long long)g.dev.nsym * g.dev.g.hs;
+        int grid = (int)std::max<long long>(1, std::min<long long>((ns + 255) / 256, (long long)s->ctx->sm_count * 2));
+        symmetrise_kernel<<<grid, 256, 0, s->stream>>>(g.dev, s->nEl, s->d_next + 2);
+        FRMC_LAUNCH_CHECK();
+    }
+    int too_big = 0;
+    FRMC_CUDA(cudaMemcpyAsync(&too_big, s->d_next + 2, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    ++s->seq_expected;
     int rc = launch_epilogue(s);
     if (rc) return rc;
     for (auto &m : s->models)
         FRMC_CUDA(cudaMemcpyAsync(m.total_committed, m.dev.total, sizeof(float) * m.dev.n_out, cudaMemcpyDeviceToDevice, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     timing_flush(s);
+    FRMC_REQUIRE(!too_big, FRMC_ELIMIT, "a symmetrised histogram cell exceeds 2^30 counts (int32 running totals)");
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_committed[i] = s->h_chi2[i];
         if (chi2) chi2[i] = s->h_chi2[i];
@@ -777,53 +1231,15 @@ int frmc_compute_data(frmc_store *s, float *chi2)
 
 int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *moved, float *chi2_after)
 {
-    FRMC_REQUIRE(s && indexes && moved, FRMC_EINVAL, "NULL argument");
-    FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group size %d outside 1..%d", k, FRMC_MAX_GROUP);
-    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is already staged; accept or reject it first");
-    FRMC_REQUIRE(!s->grids.empty(), FRMC_ESTATE, "no grid registered");
-    for (auto &g : s->grids) FRMC_REQUIRE(g.valid, FRMC_ESTATE, "call frmc_compute_data before proposing moves");
-    FRMC_CUDA(cudaSetDevice(s->dev));
-    ProposalIn *h = s->h_prop;
-    h->k = k;
-    for (int c = 0; c < 3; ++c) { s->prop_lo[c] = INFINITY; s->prop_hi[c] = -INFINITY; }
-    bool finite = true;
-    for (int t = 0; t < k; ++t) {
-        FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", indexes[t], (long long)s->n - 1);
-        h->idx[t] = indexes[t];
-        for (int c = 0; c < 3; ++c) {
-            float v = moved[3 * t + c];
-            h->moved[3 * t + c] = v;
-            if (!(v == v) || isinf(v)) finite = false;
-            s->prop_lo[c] = std::min(s->prop_lo[c], v);
-            s->prop_hi[c] = std::max(s->prop_hi[c], v);
-        }
-    }
-    FRMC_REQUIRE(finite, FRMC_EINVAL, "moved coordinates contain NaN or Inf");
-    const int mode = current_mode(s, s->prop_lo, s->prop_hi);
-    FRMC_CUDA(cudaMemcpyAsync(s->d_prop_in, h, sizeof(int) * (1 + FRMC_MAX_GROUP) + sizeof(float) * 3 * k,
-                              cudaMemcpyHostToDevice, s->stream));
-    prep_proposal_kernel<<<1, FRMC_MAX_GROUP, 0, s->stream>>>(s->d_prop_in, s->d_inv, s->d_atoms, s->d_prop);
-    FRMC_LAUNCH_CHECK();
-    GridSet gs = make_gridset(s);
-    long long want = (s->npad + 255) / 256;
-    long long cap = (long long)s->ctx->sm_count * 8;
-    int grid = (int)std::max<long long>(1, std::min(want, cap));
-#define LAUNCH_DELTA(M) delta_kernel<M><<<grid, 256, 0, s->stream>>>(s->d_atoms, (int)s->npad, s->d_prop, s->L, gs, s->nEl, s->d_overflow)
-    cudaEvent_t t0 = timing_begin(s);
-    switch (mode) {
-        case MODE_IBC: LAUNCH_DELTA(MODE_IBC); break;
-        case MODE_ORTHO_FAST: LAUNCH_DELTA(MODE_ORTHO_FAST); break;
-        case MODE_TRI_FAST: LAUNCH_DELTA(MODE_TRI_FAST); break;
-        case MODE_ORTHO_GEN: LAUNCH_DELTA(MODE_ORTHO_GEN); break;
-        default: LAUNCH_DELTA(MODE_TRI_GEN); break;
-    }
-#undef LAUNCH_DELTA
-    FRMC_LAUNCH_CHECK();
-    timing_end(s, TIME_DELTA, t0);
-    int rc = launch_epilogue(s);
+    int rc = stage_proposal(s, indexes, k, moved);
     if (rc) return rc;
-    FRMC_CUDA(cudaStreamSynchronize(s->stream));
-    timing_flush(s);
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    const int mode = current_mode(s, s->prop_lo, s->prop_hi);
+    ++s->seq_expected;
+    rc = launch_propose(s, mode);
+    if (rc) return rc;
+    rc = wait_epilogue(s);
+    if (rc) return rc;
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_staged[i] = s->h_chi2[i];
         if (chi2_after) chi2_after[i] = s->h_chi2[i];
@@ -838,15 +1254,14 @@ int frmc_accept(frmc_store *s)
     FRMC_REQUIRE(s->state == 1, FRMC_ESTATE, "no staged proposal to accept");
     FRMC_CUDA(cudaSetDevice(s->dev));
     GridSet gs = make_gridset(s);
-    long long cells = 0;
-    for (auto &g : s->grids) cells = std::max(cells, 2 * g.dev.cells);
-    int grid = (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 4));
+    TotalsCopy tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.n = (int)s->models.size();
+    for (int m = 0; m < tc.n; ++m) { tc.len[m] = s->models[m].dev.n_out; tc.src[m] = s->models[m].dev.total; tc.dst[m] = s->models[m].total_committed; }
     cudaEvent_t t0 = timing_begin(s);
-    commit_kernel<<<grid, 256, 0, s->stream>>>(gs, s->d_atoms, s->d_prop);
+    commit_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs, s->d_atoms, s->d_prop, tc);
     FRMC_LAUNCH_CHECK();
     timing_end(s, TIME_COMMIT, t0);
-    for (auto &m : s->models)
-        FRMC_CUDA(cudaMemcpyAsync(m.total_committed, m.dev.total, sizeof(float) * m.dev.n_out, cudaMemcpyDeviceToDevice, s->stream));
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], s->prop_lo[c]); s->hi[c] = std::max(s->hi[c], s->prop_hi[c]); }
     for (size_t i = 0; i < s->models.size(); ++i) s->chi2_committed[i] = s->chi2_staged[i];
     s->state = 0;
@@ -859,15 +1274,54 @@ int frmc_reject(frmc_store *s)
     FRMC_REQUIRE(s->state == 1, FRMC_ESTATE, "no staged proposal to reject");
     FRMC_CUDA(cudaSetDevice(s->dev));
     GridSet gs = make_gridset(s);
-    long long cells = 0;
-    for (auto &g : s->grids) cells = std::max(cells, 2 * g.dev.cells);
-    int grid = (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 4));
     cudaEvent_t t0 = timing_begin(s);
-    clear_delta_kernel<<<grid, 256, 0, s->stream>>>(gs);
+    clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs);
     FRMC_LAUNCH_CHECK();
     timing_end(s, TIME_COMMIT, t0);
     s->state = 0;
     return FRMC_OK;
+}
+
+int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const float *moved, float *chi2_after)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    if (s->state == 1) {
+        FRMC_REQUIRE(previous == 0 || previous == 1, FRMC_EINVAL, "a proposal is staged: previous must be 1 (accept) or 0 (reject)");
+        int rc = previous ? frmc_accept(s) : frmc_reject(s);
+        if (rc) return rc;
+    }
+    return frmc_propose(s, indexes, k, moved, chi2_after);
+}
+
+int frmc_store_replay_proposal(frmc_store *s, int reps, double *ms_per_launch)
+{
+    FRMC_REQUIRE(s && reps >= 1 && ms_per_launch, FRMC_EINVAL, "bad arguments");
+    FRMC_REQUIRE(s->state == 1, FRMC_ESTATE, "stage a proposal with frmc_propose first");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    const int mode = current_mode(s, s->prop_lo, s->prop_hi);
+    const bool timing = s->timing;
+    s->timing = false;
+    cudaEvent_t e0, e1;
+    FRMC_CUDA(cudaEventCreate(&e0));
+    FRMC_CUDA(cudaEventCreate(&e1));
+    int rc = FRMC_OK;
+    FRMC_CUDA(cudaEventRecord(e0, s->stream));
+    for (int i = 0; i < reps && rc == FRMC_OK; ++i) { ++s->seq_expected; rc = launch_propose(s, mode); }
+    FRMC_CUDA(cudaEventRecord(e1, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_launch = (double)ms / reps;
+    // the replays stacked reps extra copies of the delta: clear and stage the proposal once more
+    GridSet gs = make_gridset(s);
+    clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs);
+    FRMC_LAUNCH_CHECK();
+    ++s->seq_expected;
+    if (rc == FRMC_OK) rc = launch_propose(s, mode);
+    if (rc == FRMC_OK) rc = wait_epilogue(s);
+    s->timing = timing;
+    return rc;
 }
 
 int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter)
@@ -914,6 +1368,15 @@ int frmc_store_get_timing(frmc_store *s, int which, double *ms_total, uint64_t *
     timing_flush(s);
     if (ms_total) *ms_total = s->kernel_ms[which];
     if (launches) *launches = s->kernel_launches[which];
+    return FRMC_OK;
+}
+
+int frmc_store_debug_stamps(frmc_store *s, int64_t *out, int n)
+{
+    FRMC_REQUIRE(s && out && n >= 1 && n <= 16 * FRMC_MAX_MODELS, FRMC_EINVAL, "bad arguments");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    FRMC_CUDA(cudaMemcpy(out, s->d_stamps, sizeof(long long) * n, cudaMemcpyDeviceToHost));
     return FRMC_OK;
 }
 

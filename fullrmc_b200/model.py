@@ -91,7 +91,7 @@ class ModelSpec(object):
         self.data_weights = None if data_weights is None else np.ascontiguousarray(data_weights, dtype=FLOAT_TYPE)
         self.shape_array = None if shape_array is None else np.ascontiguousarray(shape_array, dtype=FLOAT_TYPE)
         self.scale_factor = FLOAT_TYPE(scale_factor)
-        self.sq_exact = bool(sq_exact)
+        self.sq_exact = int(sq_exact)
         self.gr2sq = None
         if self.kind in (KIND_SQ, KIND_RSQ):
             if gr2sq is None:
@@ -149,5 +149,5 @@ class ModelSpec(object):
         d.experimental = L.ptr(self.experimental, L.c_f32p)
         d.data_weights = L.ptr(self.data_weights, L.c_f32p)
         d.gr2sq = L.ptr(self.gr2sq, L.c_f32p)
-        d.sq_exact = 1 if self.sq_exact else 0
+        d.sq_exact = int(self.sq_exact)
         return d, keep

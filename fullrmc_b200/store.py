@@ -130,6 +130,24 @@ class DeviceStore(object):
                                        L.ptr(self._chi2, L.c_f32p)), "propose")
         return self._chi2[:self.n_models].copy()
 
+    def step(self, previous, indexes, movedBoxCoordinates):
+        """Resolve the staged proposal (previous: True accept / False reject / None nothing staged)
+        and evaluate the next one with a single call into the library."""
+        idx = np.ascontiguousarray(indexes, dtype=_I32)
+        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
+        if moved.shape != (idx.shape[0], 3):
+            raise ValueError("movedBoxCoordinates must be (k,3)")
+        prev = -1 if previous is None else int(bool(previous))
+        L.check(self._lib.frmc_step(self._handle, prev, L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(moved, L.c_f32p),
+                                    L.ptr(self._chi2, L.c_f32p)), "step")
+        return self._chi2[:self.n_models].copy()
+
+    def replay_proposal(self, reps):
+        """Average device time (ms) of the staged proposal's pipeline over `reps` back-to-back launches."""
+        ms = ctypes.c_double(0.0)
+        L.check(self._lib.frmc_store_replay_proposal(self._handle, int(reps), ctypes.byref(ms)), "replay_proposal")
+        return float(ms.value)
+
     def accept(self):
         L.check(self._lib.frmc_accept(self._handle), "accept")
 

@@ -180,6 +180,13 @@ int frmc_finalize_data(frmc_store *s, float *chi2);
 int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *moved, float *chi2_after);
 int frmc_accept(frmc_store *s);
 int frmc_reject(frmc_store *s);
+/* One host call per Metropolis step: resolve the staged proposal (previous = 1 accept, 0 reject;
+ * ignored when nothing is staged) and evaluate the next one. */
+int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const float *moved, float *chi2_after);
+/* Measurement helper: re-launch the staged proposal's device pipeline `reps` times back to back
+ * (no host round trip in between) and return the average device time per launch, CUDA events on
+ * the store's stream.  The staged state is restored afterwards. */
+int frmc_store_replay_proposal(frmc_store *s, int reps, double *ms_per_launch);
 
 /* export committed histograms as the reference's data["intra"], data["inter"] (fp32 [nEl,nEl,hs]) */
 int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter);
@@ -193,6 +200,9 @@ uint64_t frmc_store_edge_overflow(frmc_store *s);
  * device time in ms and the number of timed launches since timing was switched on. */
 int frmc_store_set_timing(frmc_store *s, int on);
 int frmc_store_get_timing(frmc_store *s, int which, double *ms_total, uint64_t *launches);
+/* Debug: clock64() stamps of the last epilogue launch, [model][8]: 0 start, 1 pair table staged,
+ * 2 r-space function done, 3 S(Q) slice done, 4 ticket taken, 5 chi^2 done (CTA x=0 of each model). */
+int frmc_store_debug_stamps(frmc_store *s, int64_t *out, int n);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t frmc_launch_count(void);
 
