@@ -66,6 +66,8 @@ struct Proposal {                    // device copy kept for the commit kernel
     float4 newc[FRMC_MAX_GROUP];     // same meta, moved coordinates
 };
 
+static const int EPI_INLINE_PAIRS = 16;   // pair tables up to this size ride in the kernel parameters
+
 struct ModelDev {
     int kind, grid, n_pairs, n_out, hs, sq_exact;
     float scale;
@@ -76,6 +78,11 @@ struct ModelDev {
     const int *pw_sched;             // [4][pw_leaves] numpy pairwise-sum schedule for n_out terms
     int pw_leaves;
     int nq_pad;                      // row stride of gr2sq on the device (n_out rounded up to 32, zero filled)
+    int n_stages;                    // S(Q) ring depth chosen by the host from the shared-memory budget
+    int pad0;
+    // pair table inline (n_pairs <= EPI_INLINE_PAIRS): travels in the kernel parameters, no dependent load
+    int i_psym[EPI_INLINE_PAIRS];
+    float i_w[EPI_INLINE_PAIRS], i_D[EPI_INLINE_PAIRS], i_rD[EPI_INLINE_PAIRS];
 };
 
 struct ModelSet {                    // passed BY VALUE to the epilogue (constant bank: no dependent descriptor load)
@@ -182,14 +189,20 @@ __device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab
 // compute_before_move + compute_after_move = this one launch.  Algorithmic traffic: 16 B/atom.
 static const int DELTA_UNROLL = 4;
 
+struct DeltaShared {
+    float4 sOld[FRMC_MAX_GROUP];
+    float4 sNew[FRMC_MAX_GROUP];
+    int sPos[FRMC_MAX_GROUP];
+};
+
+// body of the delta pass, shared by the stand-alone kernel and the fused propose kernel
 template <int MODE>
-__global__ void __launch_bounds__(256)
-delta_kernel(const float4 *__restrict__ atoms, int npad, const ProposalIn in, Proposal *__restrict__ prop,
-             Lattice L, GridSet gs, int nEl, unsigned long long *__restrict__ overflow)
+__device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__restrict__ atoms, int npad, const ProposalIn &in,
+                                           Proposal *__restrict__ prop, const Lattice &L, const GridSet &gs, int nEl,
+                                           unsigned long long *__restrict__ overflow)
 {
-    __shared__ float4 sOld[FRMC_MAX_GROUP];
-    __shared__ float4 sNew[FRMC_MAX_GROUP];
-    __shared__ int sPos[FRMC_MAX_GROUP];
+    float4 *sOld = sh.sOld, *sNew = sh.sNew;
+    int *sPos = sh.sPos;
     const int k = in.k;
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const int p = in.pos[t];
@@ -256,6 +269,23 @@ delta_kernel(const float4 *__restrict__ atoms, int npad, const ProposalIn in, Pr
     if (ov) atomicAdd(overflow, ov);
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(256)
+delta_kernel(const float4 *__restrict__ atoms, int npad, const ProposalIn in, Proposal *__restrict__ prop,
+             Lattice L, GridSet gs, int nEl, unsigned long long *__restrict__ overflow, long long *__restrict__ stamps)
+{
+    __shared__ DeltaShared sh;
+    if (stamps && threadIdx.x == 0) {       // debug timeline (globaltimer ns): first start / last end over all CTAs
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long *>(stamps + 120), gt);
+    }
+    delta_body<MODE>(sh, atoms, npad, in, prop, L, gs, nEl, overflow);
+    if (stamps && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long *>(stamps + 121), gt);
+    }
+}
+
 // ------------------------------------------------------------------ kernels: fused epilogue
 // numpy's pairwise float32 summation (numpy/_core/src/umath/loops_utils.h.src,
 // FLOAT_pairwise_sum): blocks of <=128 summed with 8 interleaved accumulators combined as
@@ -315,8 +345,7 @@ __device__ float block_pairwise_sum(const float *v, int nl, PairwiseScratch &ps)
 }
 
 static const int SQ_ROWS = 64;       // matrix rows per cp.async stage (8 KB per 32-column slab)
-static const int SQ_STAGES = 4;
-static const int SQ_WARPS = 2;        // consumer warps per CTA (warps 0 and 4: same SM sub-partition, so one hides the other's LDS latency)
+static const int SQ_MAX_STAGES = 26;  // ring stages (8 KB each); a whole [hs x 32] slab stays resident when hs <= 64*stages
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -396,98 +425,141 @@ __global__ void validate_fastdiv_kernel(const float *__restrict__ w, const float
 //     np.sum(Gr.reshape((-1,1))*Gr2SqMatrix, axis=0) (StructureFactorConstraints.py:772-773),
 //     which accumulates rows sequentially.  The chain of hs dependent FADDs (4 cycles each) is
 //     the floor, ~2 us at hs=1000.  The matrix is stored pre-tiled ([Q slab][r/4][lane][r%4],
-//     zero padded to 64 rows), so a 64-row chunk of a slab is 8 KB contiguous: warp 0 alone runs
-//     a 4-stage ring of TMA bulk copies (cp.async.bulk + mbarrier, no CTA barrier in the loop),
-//     reads four rows per LDS.128 and keeps the FADD chain fed by forming products 16 rows ahead.
+//     zero padded to 64 rows), so a 64-row chunk of a slab is 8 KB contiguous: lane 0 fetches
+//     the whole slab with TMA bulk copies (cp.async.bulk + one mbarrier per chunk) at kernel
+//     start, up to 26 chunks = 1664 rows resident in shared memory (longer slabs reuse the
+//     stages as a ring); warp 0 reads four rows per LDS.128 and forms products 16 rows ahead.
 //     The last CTA to finish (ticket) computes chi^2.
 //  4. publish: chi2 to pinned host memory, system fence, then the per-model launch counter the
 //     host spins on.
 static const unsigned SQ_CHUNK_BYTES = SQ_ROWS * 32 * sizeof(float);
 
-// lane 0 of warp 0 only
+// 16-byte shared load the compiler may not sink towards its use (software-pipelined S(Q) loop)
+__device__ __forceinline__ float4 lds128(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+// lane 0 of the consumer warp only
 __device__ __forceinline__ void sq_issue(const ModelDev &M, float *ring, unsigned long long *mbar, int slab, int chunk, int n_chunks)
 {
     if (chunk < n_chunks) {
-        const int stage = chunk % SQ_STAGES;
+        const int stage = chunk % M.n_stages;
         const float *src = M.gr2sq + ((size_t)slab * n_chunks + chunk) * (SQ_ROWS * 32);
         mbar_expect_tx(&mbar[stage], SQ_CHUNK_BYTES);
         bulk_g2s(ring + stage * (SQ_ROWS * 32), src, SQ_CHUNK_BYTES, &mbar[stage]);
     }
 }
 
-__global__ void __launch_bounds__(EPI_THREADS, 1)
-epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
-                unsigned int *__restrict__ dev_seq, volatile unsigned int *__restrict__ host_seq,
-                unsigned int *__restrict__ tickets, long long *__restrict__ stamps)
-{
-#define EPI_STAMP(i) do { if (stamps && threadIdx.x == 0 && blockIdx.x == 0) { stamps[blockIdx.y * 8 + (i)] = clock64(); \
-        unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[64 + blockIdx.y * 8 + (i)] = (long long)gt_; } } while (0)
-    extern __shared__ __align__(16) float epi_smem[];   // [hs_pad] G(r) | [out_pad] chi2 terms | SQ: ring [SQ_STAGES][SQ_ROWS][32]
-    __shared__ int s_psym[EPI_MAX_PAIRS + 16];
-    __shared__ float s_w[EPI_MAX_PAIRS + 16], s_D[EPI_MAX_PAIRS + 16], s_rD[EPI_MAX_PAIRS + 16];
-    __shared__ PairwiseScratch ps;
-    __shared__ int s_last;
-    __shared__ __align__(8) unsigned long long mbar_all[SQ_WARPS * SQ_STAGES];
-    EPI_STAMP(0);
+struct EpiShared {
+    int s_psym[EPI_MAX_PAIRS + 16];
+    float s_w[EPI_MAX_PAIRS + 16], s_D[EPI_MAX_PAIRS + 16], s_rD[EPI_MAX_PAIRS + 16];
+    PairwiseScratch ps;
+    int s_last;
+    unsigned long long mbar[SQ_MAX_STAGES];
+};
 
-    const int m = blockIdx.y;
-    if (m >= ms.n) return;
-    const ModelDev &M = ms.m[m];
+#define EPI_STAMP(i) do { if (stamps && threadIdx.x == 0 && slab == 0) { stamps[m * 8 + (i)] = clock64(); \
+        unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[64 + m * 8 + (i)] = (long long)gt_; } } while (0)
+
+// part 1 of an epilogue CTA (model M, Q slab `slab`): start the TMA stream of the matrix slab.
+// Called first thing in the kernel so the copies overlap everything that precedes the S(Q) loop.
+__device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem, const ModelDev &M, int slab)
+{
     const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
     const int hs = M.hs, nq = M.n_out;
-    const int nblk = is_sq ? (nq + 32 * SQ_WARPS - 1) / (32 * SQ_WARPS) : 1;
-    if ((int)blockIdx.x >= nblk) return;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int hs_pad = (hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS;
-    // consumer warps: warp 0 -> Q slab 2x, warp 4 -> Q slab 2x+1 (each its own ring and mbarriers)
-    const int cw = (wrp == 0) ? 0 : ((wrp == 4) ? 1 : -1);
-    const int slab = blockIdx.x * SQ_WARPS + (cw < 0 ? 0 : cw);
+    const int nst = M.n_stages;
     const int q0 = slab * 32;
-    const bool consumer = is_sq && cw >= 0 && q0 < nq;
-    float *ring = epi_smem + (cw < 0 ? 0 : cw) * (SQ_STAGES * SQ_ROWS * 32);   // first: keeps the TMA destinations 128-byte aligned
-    unsigned long long *mbar = mbar_all + (cw < 0 ? 0 : cw) * SQ_STAGES;
-    float *sG = epi_smem + (is_sq ? SQ_WARPS * SQ_STAGES * SQ_ROWS * 32 : 0);
+    float *ring = epi_smem;                              // first: keeps the TMA destinations 128-byte aligned
+    float *sG = epi_smem + (is_sq ? nst * SQ_ROWS * 32 : 0);
     float *sT = sG + hs_pad;
     const int n_chunks = (hs + SQ_ROWS - 1) / SQ_ROWS;
-
-    // start streaming the matrix before anything else: it overlaps the G(r) phase
-    if (consumer) {
+    const bool resident = n_chunks <= nst;
+    unsigned long long *mbar = es.mbar;
+    (void)lane; (void)wrp; (void)q0; (void)ring; (void)sT; (void)nq; (void)resident; (void)mbar;
+    // start streaming the matrix slab before anything else: it overlaps the G(r) phase.
+    // Resident case (whole slab fits the ring): ONE mbarrier, a few large bulk copies.
+    if (is_sq && wrp == 0) {
         if (lane == 0) {
-            for (int st = 0; st < SQ_STAGES; ++st) mbar_init(&mbar[st], 1);
+            for (int st = 0; st < (resident ? 1 : nst); ++st) mbar_init(&mbar[st], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            for (int c = 0; c < SQ_STAGES - 1; ++c) sq_issue(M, ring, mbar, slab, c, n_chunks);
+            if (resident) {
+                const unsigned total = (unsigned)n_chunks * SQ_CHUNK_BYTES;
+                const float *src = M.gr2sq + (size_t)slab * n_chunks * (SQ_ROWS * 32);
+                mbar_expect_tx(&mbar[0], total);
+                for (unsigned off = 0; off < total; off += 4 * SQ_CHUNK_BYTES) {
+                    const unsigned bytes = min(4 * SQ_CHUNK_BYTES, total - off);
+                    bulk_g2s(reinterpret_cast<char *>(ring) + off, reinterpret_cast<const char *>(src) + off, bytes, &mbar[0]);
+                }
+            } else {
+                for (int c = 0; c < nst; ++c) sq_issue(M, ring, mbar, slab, c, n_chunks);
+            }
         }
         __syncwarp();
     }
 
-    const int np = M.n_pairs;
+}
+
+// part 2: r-space function, chi^2 / S(Q) slice, ticket, publish (steps 1-4 above)
+__device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, const ModelSet &ms, const GridSet &gs, int m, int slab,
+                                             float *__restrict__ chi2_out, unsigned int *__restrict__ dev_seq,
+                                             volatile unsigned int *__restrict__ host_seq, unsigned int *__restrict__ tickets,
+                                             long long *__restrict__ stamps)
+{
+    const ModelDev &M = ms.m[m];
+    const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
+    const int hs = M.hs, nq = M.n_out;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int hs_pad = (hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS;
+    const int nst = M.n_stages;
+    const int q0 = slab * 32;
+    float *ring = epi_smem;                              // first: keeps the TMA destinations 128-byte aligned
+    float *sG = epi_smem + (is_sq ? nst * SQ_ROWS * 32 : 0);
+    float *sT = sG + hs_pad;
+    const int n_chunks = (hs + SQ_ROWS - 1) / SQ_ROWS;
+    const bool resident = n_chunks <= nst;
+    unsigned long long *mbar = es.mbar;
+    (void)lane; (void)wrp; (void)q0; (void)ring; (void)sT; (void)nq; (void)resident; (void)mbar;
+    const int nblk = is_sq ? (nq + 31) / 32 : 1;
+    int *s_psym = es.s_psym;
+    float *s_w = es.s_w, *s_D = es.s_D, *s_rD = es.s_rD;
+    PairwiseScratch &ps = es.ps;
+    int &s_last = es.s_last;
     // pair table, padded to a multiple of 16 with weight-0 entries: (0*n)/1 = 0 and acc+0 == acc
+    const int np = M.n_pairs;
     const int np_pad = (np + 15) / 16 * 16;
+    const bool inline_pairs = np <= EPI_INLINE_PAIRS;
     for (int p = tid; p < np_pad; p += EPI_THREADS) {
         const bool real = p < np;
-        s_psym[p] = real ? M.psym[p] : 0; s_w[p] = real ? M.w[p] : 0.0f;
-        s_D[p] = real ? M.D[p] : 1.0f; s_rD[p] = real ? M.rD[p] : 1.0f;
-    }
-    {   // chi^2 summation schedule (needed at the very end; fetched now, off the critical path)
-        const int nl = M.pw_leaves;
-        for (int i = tid; i < nl; i += EPI_THREADS) {
-            ps.leaf_off[i] = M.pw_sched[i]; ps.leaf_len[i] = M.pw_sched[nl + i];
-            ps.op_dst[i] = M.pw_sched[2 * nl + i]; ps.op_src[i] = M.pw_sched[3 * nl + i];
+        if (inline_pairs) {
+            s_psym[p] = real ? M.i_psym[p] : 0; s_w[p] = real ? M.i_w[p] : 0.0f;
+            s_D[p] = real ? M.i_D[p] : 1.0f; s_rD[p] = real ? M.i_rD[p] : 1.0f;
+        } else {
+            s_psym[p] = real ? M.psym[p] : 0; s_w[p] = real ? M.w[p] : 0.0f;
+            s_D[p] = real ? M.D[p] : 1.0f; s_rD[p] = real ? M.rD[p] : 1.0f;
         }
     }
     for (int r = hs + tid; r < hs_pad; r += EPI_THREADS) sG[r] = 0.0f;
     __syncthreads();
     EPI_STAMP(1);
 
-    // ---- 1. r-space function: EPI_BINS bins per thread per round, all loads first
+    // ---- 1. r-space function: EPI_BINS bins per thread per round, every load issued before any arithmetic
     {
         const int *__restrict__ stot = gs.grid[M.grid].stot;
         constexpr int EPI_BINS = 2, PB = 16;
         for (int rb = tid; rb < hs; rb += EPI_BINS * EPI_THREADS) {
-            float acc[EPI_BINS];
+            float acc[EPI_BINS], svr[EPI_BINS], prf[EPI_BINS], shp[EPI_BINS];
 #pragma unroll
-            for (int j = 0; j < EPI_BINS; ++j) acc[j] = 0.0f;
+            for (int j = 0; j < EPI_BINS; ++j) {
+                const int r = min(rb + j * EPI_THREADS, hs - 1);
+                acc[j] = 0.0f;
+                svr[j] = M.sv[r]; prf[j] = M.pref[r]; shp[j] = M.shape ? M.shape[r] : 0.0f;
+            }
             for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_pad); p0 += PB) {
                 int c[EPI_BINS][PB];
 #pragma unroll
@@ -514,29 +586,36 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
             for (int j = 0; j < EPI_BINS; ++j) {
                 const int r = rb + j * EPI_THREADS;
                 if (r >= hs) continue;
-                float a = __fdiv_rn(acc[j], M.sv[r]);
+                float a = __fdiv_rn(acc[j], svr[j]);
                 float out;
                 if (M.kind == FRMC_KIND_PCF) {
                     out = a;
-                    if (M.shape) out = __fsub_rn(out, M.shape[r]);
+                    if (M.shape) out = __fsub_rn(out, shp[j]);
                     if (M.scale != 1.0f) {
-                        float Gr = __fmul_rn(M.pref[r], __fsub_rn(out, 1.0f));
+                        float Gr = __fmul_rn(prf[j], __fsub_rn(out, 1.0f));
                         Gr = __fmul_rn(Gr, M.scale);
-                        out = __fadd_rn(1.0f, __fdiv_rn(Gr, M.pref[r]));
+                        out = __fadd_rn(1.0f, __fdiv_rn(Gr, prf[j]));
                     }
                 } else {
-                    out = __fmul_rn(M.pref[r], __fsub_rn(a, 1.0f));
+                    out = __fmul_rn(prf[j], __fsub_rn(a, 1.0f));
                     if (M.kind == FRMC_KIND_PDF) {
-                        if (M.shape) out = __fsub_rn(out, M.shape[r]);
+                        if (M.shape) out = __fsub_rn(out, shp[j]);
                         if (M.scale != 1.0f) out = __fmul_rn(out, M.scale);
                     }
                 }
                 sG[r] = out;
-                if (blockIdx.x == 0) {
+                if (slab == 0) {
                     M.rfun[r] = out;
                     if (!is_sq) M.total[r] = out;
                 }
             }
+        }
+    }
+    {   // chi^2 summation schedule (needed at the very end): fetched here, its latency hides behind the barrier
+        const int nl = M.pw_leaves;
+        for (int i = tid; i < nl; i += EPI_THREADS) {
+            ps.leaf_off[i] = M.pw_sched[i]; ps.leaf_len[i] = M.pw_sched[nl + i];
+            ps.op_dst[i] = M.pw_sched[2 * nl + i]; ps.op_src[i] = M.pw_sched[3 * nl + i];
         }
     }
     __syncthreads();
@@ -554,13 +633,33 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
         __syncthreads();
         chi2 = block_pairwise_sum(sT, M.pw_leaves, ps);
     } else {
-        // ---- 3. S(Q) slice: single-warp producer/consumer over the TMA ring
-        if (consumer) {
+        // ---- 3. S(Q) slice: warp 0 consumes the slab chunk by chunk (refilling the ring only when the slab does not fit)
+        if (wrp == 0) {
             float acc = 0.0f;
+            if (resident && !(M.sq_exact & 2)) {
+                // whole slab in shared memory, rows contiguous: flat loop over groups of 4 rows with an
+                // 8-group (32-row) register prefetch, so the FADD chain never waits for a shared load
+                if (!(M.sq_exact & 8)) mbar_wait(&mbar[0], 0u);
+                const float4 *mt = reinterpret_cast<const float4 *>(ring) + lane;   // group g: mt[g*32]
+                const float4 *gv = reinterpret_cast<const float4 *>(sG);            // group g: gv[g]
+                const int ngroups = hs_pad / 4;                                      // multiple of 16
+                // plain loads in a deeply unrolled loop: ptxas interleaves the LDS.128 of later groups with
+                // the FADD chain of earlier ones (4.6 cycles/row measured, tools/ubench.cu)
+#pragma unroll 1
+                for (int g0 = 0; g0 < ngroups; g0 += 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 a = mt[(g0 + j) * 32], g = gv[g0 + j];
+                        acc = __fadd_rn(acc, __fmul_rn(g.x, a.x));      // rows beyond hs are zero rows: acc + 0
+                        acc = __fadd_rn(acc, __fmul_rn(g.y, a.y));
+                        acc = __fadd_rn(acc, __fmul_rn(g.z, a.z));
+                        acc = __fadd_rn(acc, __fmul_rn(g.w, a.w));
+                    }
+                }
+            } else
             for (int c = 0; c < ((M.sq_exact & 2) ? 0 : n_chunks); ++c) {
-                const int stage = c % SQ_STAGES;
-                if (lane == 0) sq_issue(M, ring, mbar, slab, c + SQ_STAGES - 1, n_chunks);   // refills the stage consumed last iteration
-                mbar_wait(&mbar[stage], (unsigned)((c / SQ_STAGES) & 1));
+                const int stage = c % nst;
+                mbar_wait(&mbar[stage], (unsigned)((c / nst) & 1));
                 const float4 *mt = reinterpret_cast<const float4 *>(ring + stage * (SQ_ROWS * 32)) + lane;   // [r/4][lane]
                 const float4 *gv = reinterpret_cast<const float4 *>(sG + c * SQ_ROWS);                     // [r/4]
                 float prod[16], nxt[16];
@@ -587,7 +686,10 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
                         for (int u = 0; u < 16; ++u) prod[u] = nxt[u];
                     }
                 }
-                __syncwarp();                          // all lanes done with this stage before it is refilled
+                if (c + nst < n_chunks) {              // slab larger than the ring: refill this stage
+                    __syncwarp();                      // all lanes done with it
+                    if (lane == 0) sq_issue(M, ring, mbar, slab, c + nst, n_chunks);
+                }
             }
             if (q0 + lane < nq) {
                 float sv = acc;
@@ -623,7 +725,11 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
         chi2 = block_pairwise_sum(sT, M.pw_leaves, ps);
     }
     // ---- 4. publish
-    if (stamps && tid == 0) stamps[blockIdx.y * 8 + 5] = clock64();
+    if (stamps && tid == 0) {
+        stamps[m * 8 + 5] = clock64();
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long *>(stamps + 122), gt);
+    }
     if (tid == 0) {
         chi2_out[m] = chi2;
         __threadfence_system();
@@ -631,6 +737,124 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
         dev_seq[m] = v;
         host_seq[m] = v;
     }
+}
+
+__global__ void __launch_bounds__(EPI_THREADS, 1)
+epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
+                unsigned int *__restrict__ dev_seq, volatile unsigned int *__restrict__ host_seq,
+                unsigned int *__restrict__ tickets, long long *__restrict__ stamps)
+{
+    extern __shared__ __align__(128) float epi_smem[];   // SQ: ring [n_stages][SQ_ROWS][32] | [hs_pad] G(r) | [out_pad] chi2 terms
+    __shared__ __align__(16) EpiShared es;
+    const int m = blockIdx.y, slab = blockIdx.x;
+    if (m >= ms.n) return;
+    const ModelDev &M = ms.m[m];
+    const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
+    if (slab >= (is_sq ? (M.n_out + 31) / 32 : 1)) return;
+    EPI_STAMP(0);
+    epilogue_prefetch(es, epi_smem, M, slab);
+    epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps);
+}
+
+// ------------------------------------------------------------------ kernels: fused Metropolis step
+// ONE cooperative launch per proposal: (0) the epilogue CTAs start the TMA stream of their
+// matrix slab, (1) every CTA helps resolve the PREVIOUS proposal (commit or clear the staged
+// deltas, move the accepted atoms), grid barrier, (2) every CTA runs its share of the delta
+// pass, grid barrier, (3) the first n_epi CTAs run the epilogue of their (model, Q slab), the
+// others have exited.  Kernel boundaries cost ~3 us each on this part (profiles/), the two
+// software grid barriers ~1 us each.
+struct EpiMap {
+    int n;                           // number of epilogue CTAs
+    unsigned char model[128];
+    unsigned char slab[128];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// every thread of the CTA calls it after its last global write / atomic of the phase
+__device__ __forceinline__ void grid_arrive(unsigned long long *bar)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(bar, 1ull);
+}
+__device__ __forceinline__ void grid_wait(const unsigned long long *bar, unsigned long long target)
+{
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_u64(bar) < target)
+            if (++spins > (1u << 28)) __trap();        // co-residency is guaranteed by the cooperative launch; never hang
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void resolve_body(const GridSet &gs, float4 *__restrict__ atoms, const Proposal *__restrict__ prop,
+                                             const TotalsCopy &tc, int prev)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool accept = prev == 1;
+    for (int gi = 0; gi < gs.n; ++gi) {
+        const GridDev &G = gs.grid[gi];
+        for (long long c = tid; c < 2 * G.cells; c += stride) {
+            const int d = G.delta[c];
+            if (d) { if (accept) G.counts[c] = (unsigned long long)((long long)G.counts[c] + d); G.delta[c] = 0; }
+        }
+        const long long ns = (long long)G.nsym * G.g.hs;
+        if (accept) { for (long long c = tid; c < ns; c += stride) G.tot[c] = G.stot[c]; }
+        else        { for (long long c = tid; c < ns; c += stride) G.stot[c] = G.tot[c]; }
+    }
+    if (accept) {
+        if (tid < prop->k) atoms[prop->pos[tid]] = prop->newc[tid];
+        for (int m = 0; m < tc.n; ++m)
+            for (long long i = tid; i < tc.len[m]; i += stride) tc.dst[m][i] = tc.src[m][i];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EPI_THREADS, 1)
+propose_kernel(float4 *__restrict__ atoms, int npad, const ProposalIn in, Proposal *__restrict__ prop, Lattice L, GridSet gs,
+               int nEl, unsigned long long *__restrict__ overflow, const ModelSet ms, const EpiMap em, int prev,
+               const TotalsCopy tc, unsigned long long *__restrict__ bars, unsigned long long launch_no, unsigned long long resolve_no,
+               float *__restrict__ chi2_out, unsigned int *__restrict__ dev_seq, volatile unsigned int *__restrict__ host_seq,
+               unsigned int *__restrict__ tickets, long long *__restrict__ stamps)
+{
+    extern __shared__ __align__(128) float epi_smem[];
+    __shared__ __align__(16) EpiShared es;
+    __shared__ DeltaShared dsh;
+    const bool epi = (int)blockIdx.x < em.n;
+    const int m = epi ? em.model[blockIdx.x] : 0, slab = epi ? em.slab[blockIdx.x] : 0;
+    if (stamps && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long *>(stamps + 120), gt);
+    }
+    // (0) matrix slab stream
+    if (epi) epilogue_prefetch(es, epi_smem, ms.m[m], slab);
+    // barrier counters are monotonic across launches: bars[1] advances on every launch (launch_no),
+    // bars[0] only on launches that resolve a previous proposal (resolve_no, counted by the host)
+    const unsigned long long target = launch_no * gridDim.x;
+    // (1) resolve the previous proposal
+    if (prev) {
+        resolve_body(gs, atoms, prop, tc, prev);
+        grid_arrive(bars + 0);
+        grid_wait(bars + 0, resolve_no * gridDim.x);
+    }
+    // (2) delta pass of this proposal
+    delta_body<MODE>(dsh, atoms, npad, in, prop, L, gs, nEl, overflow);
+    grid_arrive(bars + 1);
+    if (stamps && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long *>(stamps + 121), gt);
+    }
+    if (!epi) return;
+    grid_wait(bars + 1, target);
+    // (3) epilogue
+    EPI_STAMP(0);
+    epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps);
 }
 
 }  // namespace frmc
@@ -678,6 +902,13 @@ struct frmc_store {
     long long *d_stamps = nullptr;   // [FRMC_MAX_MODELS][8] clock64 phase stamps of the last epilogue (debug)
     unsigned int seq_expected = 0;
     size_t epi_smem = 0;
+    // fused per-move path (one cooperative launch per proposal)
+    bool use_fused = true;
+    bool fused_ok = false;           // checked in sync_models: cooperative launch + occupancy + epilogue CTA count
+    int pending = 0;                 // deferred resolution of the last proposal: 0 none, 1 accept, 2 reject
+    unsigned long long *d_bars = nullptr;
+    unsigned long long fused_launches = 0, fused_resolves = 0;
+    EpiMap epi_map;
     float prop_lo[3], prop_hi[3];
     int state = 0;                   // 0 idle, 1 proposal staged
     float chi2_staged[FRMC_MAX_MODELS];
@@ -778,13 +1009,20 @@ static int sync_models(frmc_store *s)
 {
     if (!s->models_dirty) return FRMC_OK;
     size_t smem = 0;
+    const size_t budget = 200 * 1024;
     for (auto &m : s->models) {
         const bool is_sq = (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ);
-        size_t need = sizeof(float) * ((size_t)(m.dev.hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS + (size_t)(m.dev.n_out + 31) / 32 * 32 +
-                                       (is_sq ? (size_t)SQ_WARPS * SQ_STAGES * SQ_ROWS * 32 : 0));
-        smem = std::max(smem, need);
+        const size_t base = sizeof(float) * ((size_t)(m.dev.hs + SQ_ROWS - 1) / SQ_ROWS * SQ_ROWS + (size_t)(m.dev.n_out + 31) / 32 * 32);
+        FRMC_REQUIRE(base + (is_sq ? 2 * SQ_ROWS * 32 * sizeof(float) : 0) <= budget, FRMC_ELIMIT,
+                     "model needs more than %zu B of shared memory in the epilogue", budget);
+        m.dev.n_stages = 1;
+        if (is_sq) {
+            const int n_chunks = (m.dev.hs + SQ_ROWS - 1) / SQ_ROWS;
+            int fit = (int)((budget - base) / (SQ_ROWS * 32 * sizeof(float)));
+            m.dev.n_stages = std::max(2, std::min(std::min(fit, SQ_MAX_STAGES), n_chunks));
+        }
+        smem = std::max(smem, base + (is_sq ? (size_t)m.dev.n_stages * SQ_ROWS * 32 * sizeof(float) : 0));
     }
-    FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "model needs %zu B of shared memory in the epilogue (limit 200 KiB)", smem);
     FRMC_CUDA(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     // one shared-memory carveout for every kernel of the per-move pipeline: consecutive launches
     // with different carveouts make the SMs reconfigure (and drain) in between
@@ -799,6 +1037,37 @@ static int sync_models(frmc_store *s)
     cudaFuncSetAttribute(delta_kernel<MODE_TRI_GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     cudaGetLastError();
     s->epi_smem = smem;
+    // fused path: epilogue CTA map, shared-memory attribute of every instantiation, co-residency check
+    memset(&s->epi_map, 0, sizeof(s->epi_map));
+    int n_epi = 0;
+    bool fits = true;
+    for (size_t mi = 0; mi < s->models.size(); ++mi) {
+        const ModelDev &d = s->models[mi].dev;
+        const bool is_sq = (d.kind == FRMC_KIND_SQ || d.kind == FRMC_KIND_RSQ);
+        const int nblk = is_sq ? (d.n_out + 31) / 32 : 1;
+        for (int x = 0; x < nblk; ++x) {
+            if (n_epi >= 128 || x > 255) { fits = false; break; }
+            s->epi_map.model[n_epi] = (unsigned char)mi; s->epi_map.slab[n_epi] = (unsigned char)x; ++n_epi;
+        }
+    }
+    s->epi_map.n = fits ? n_epi : 0;
+    s->fused_ok = false;
+    if (s->use_fused && fits && n_epi >= 1 && n_epi <= s->ctx->sm_count) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->dev);
+        const int fsmem = (int)std::max<size_t>(smem, 48 * 1024);
+        bool ok = coop != 0;
+#define FUSED_ATTR(M) do { \
+            if (cudaFuncSetAttribute(propose_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem) != cudaSuccess) ok = false; \
+            cudaFuncSetAttribute(propose_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+            int per_sm = 0; \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propose_kernel<M>, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) ok = false; \
+        } while (0)
+        FUSED_ATTR(MODE_IBC); FUSED_ATTR(MODE_ORTHO_FAST); FUSED_ATTR(MODE_TRI_FAST); FUSED_ATTR(MODE_ORTHO_GEN); FUSED_ATTR(MODE_TRI_GEN);
+#undef FUSED_ATTR
+        cudaGetLastError();
+        s->fused_ok = ok;
+    }
     s->models_dirty = false;
     return FRMC_OK;
 }
@@ -820,7 +1089,7 @@ static int launch_epilogue(frmc_store *s)
         if (ms.m[i].kind == FRMC_KIND_SQ || ms.m[i].kind == FRMC_KIND_RSQ) max_q = std::max(max_q, ms.m[i].n_out);
     }
     cudaEvent_t t0 = timing_begin(s);
-    dim3 grid((unsigned)((max_q + 32 * SQ_WARPS - 1) / (32 * SQ_WARPS)), (unsigned)nm);
+    dim3 grid((unsigned)((max_q + 31) / 32), (unsigned)nm);
     epilogue_kernel<<<grid, EPI_THREADS, s->epi_smem, s->stream>>>(ms, gs, s->h_chi2, s->d_seq, s->h_seq,
                                                                    s->d_seq + FRMC_MAX_MODELS, s->d_stamps);
     FRMC_LAUNCH_CHECK();
@@ -909,14 +1178,81 @@ static int launch_cells_grid(frmc_store *s)
     return (int)std::max<long long>(1, std::min<long long>((cells + 255) / 256, (long long)s->ctx->sm_count * 2));
 }
 
-// the per-move pipeline: delta pass (proposal by value) + fused epilogue, two launches
+static TotalsCopy make_totals_copy(frmc_store *s)
+{
+    TotalsCopy tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.n = (int)s->models.size();
+    for (int m = 0; m < tc.n; ++m) { tc.len[m] = s->models[m].dev.n_out; tc.src[m] = s->models[m].dev.total; tc.dst[m] = s->models[m].total_committed; }
+    return tc;
+}
+
+// apply a deferred accept / reject with the stand-alone kernels (needed before anything other than
+// the next fused proposal looks at the device state)
+static int flush_pending(frmc_store *s)
+{
+    if (!s->pending) return FRMC_OK;
+    GridSet gs = make_gridset(s);
+    cudaEvent_t t0 = timing_begin(s);
+    if (s->pending == 1) commit_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs, s->d_atoms, s->d_prop, make_totals_copy(s));
+    else clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs);
+    FRMC_LAUNCH_CHECK();
+    timing_end(s, TIME_COMMIT, t0);
+    s->pending = 0;
+    return FRMC_OK;
+}
+
+template <int MODE>
+static int launch_fused_t(frmc_store *s)
+{
+    GridSet gs = make_gridset(s);
+    ModelSet ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = (int)s->models.size();
+    for (int i = 0; i < ms.n; ++i) ms.m[i] = s->models[i].dev;
+    TotalsCopy tc = make_totals_copy(s);
+    int npad = (int)s->npad, nEl = s->nEl, prev = s->pending;
+    unsigned long long launch_no = ++s->fused_launches;
+    if (prev) ++s->fused_resolves;
+    unsigned long long resolve_no = s->fused_resolves;
+    unsigned int *tickets = s->d_seq + FRMC_MAX_MODELS;
+    volatile unsigned int *hseq = s->h_seq;
+    void *args[] = {&s->d_atoms, &npad, &s->prop_in, &s->d_prop, &s->L, &gs, &nEl, &s->d_overflow, &ms, &s->epi_map, &prev, &tc,
+                    &s->d_bars, &launch_no, &resolve_no, &s->h_chi2, &s->d_seq, &hseq, &tickets, &s->d_stamps};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)propose_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
+                                                args, s->epi_smem, s->stream);
+    if (e != cudaSuccess) {
+        --s->fused_launches; if (prev) --s->fused_resolves;
+        set_error("cooperative launch of the fused propose kernel failed: %s", cudaGetErrorString(e));
+        return FRMC_ECUDA;
+    }
+    ++g_launch_count;
+    s->pending = 0;
+    return FRMC_OK;
+}
+
+// the per-move pipeline.  Fused path: ONE cooperative launch (resolve previous + delta pass +
+// epilogue).  Fallback (timing mode, FRMC_NO_FUSED=1, too many epilogue CTAs): delta pass
+// (proposal by value) + fused epilogue, two launches, after the pending resolution.
 static int launch_propose(frmc_store *s, int mode)
 {
+    int rc = sync_models(s);
+    if (rc) return rc;
+    if (s->fused_ok && !s->timing) {
+        switch (mode) {
+            case MODE_IBC: return launch_fused_t<MODE_IBC>(s);
+            case MODE_ORTHO_FAST: return launch_fused_t<MODE_ORTHO_FAST>(s);
+            case MODE_TRI_FAST: return launch_fused_t<MODE_TRI_FAST>(s);
+            case MODE_ORTHO_GEN: return launch_fused_t<MODE_ORTHO_GEN>(s);
+            default: return launch_fused_t<MODE_TRI_GEN>(s);
+        }
+    }
+    if ((rc = flush_pending(s))) return rc;
     GridSet gs = make_gridset(s);
     long long want = (s->npad + 256 * DELTA_UNROLL - 1) / (256 * DELTA_UNROLL);
     long long cap = (long long)s->ctx->sm_count * 8;
     int grid = (int)std::max<long long>(1, std::min(want, cap));
-#define LAUNCH_DELTA(M) delta_kernel<M><<<grid, 256, 0, s->stream>>>(s->d_atoms, (int)s->npad, s->prop_in, s->d_prop, s->L, gs, s->nEl, s->d_overflow)
+#define LAUNCH_DELTA(M) delta_kernel<M><<<grid, 256, 0, s->stream>>>(s->d_atoms, (int)s->npad, s->prop_in, s->d_prop, s->L, gs, s->nEl, s->d_overflow, s->d_stamps)
     cudaEvent_t t0 = timing_begin(s);
     switch (mode) {
         case MODE_IBC: LAUNCH_DELTA(MODE_IBC); break;
@@ -991,8 +1327,12 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) s->h_seq[i] = 0u;
     if (cudaMalloc(&s->d_seq, sizeof(unsigned int) * 2 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_seq, 0, sizeof(unsigned int) * 2 * FRMC_MAX_MODELS);
+    if (cudaMalloc(&s->d_bars, sizeof(unsigned long long) * 4) != cudaSuccess) return fail("alloc");
+    cudaMemset(s->d_bars, 0, sizeof(unsigned long long) * 4);
+    { const char *e = getenv("FRMC_NO_FUSED"); s->use_fused = !(e && e[0] == '1'); }
     if (cudaMalloc(&s->d_stamps, sizeof(long long) * 16 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_stamps, 0, sizeof(long long) * 16 * FRMC_MAX_MODELS);
+    { long long big = 0x7FFFFFFFFFFFFFFFll; cudaMemcpy(s->d_stamps + 120, &big, sizeof(big), cudaMemcpyHostToDevice); }
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) { s->h_chi2[i] = 0.f; s->chi2_staged[i] = 0.f; s->chi2_committed[i] = 0.f; }
     return s;
 }
@@ -1007,7 +1347,7 @@ void frmc_store_destroy(frmc_store *s)
     }
     for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); cudaFree(g.dev.tot); cudaFree(g.dev.stot); }
     cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next);
-    cudaFree(s->d_overflow); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps);
+    cudaFree(s->d_overflow); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps); cudaFree(s->d_bars);
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
@@ -1021,6 +1361,7 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
 {
     FRMC_REQUIRE(s && coords, FRMC_EINVAL, "NULL argument");
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     if (basis) for (int i = 0; i < 9; ++i) s->L.b[i] = basis[i];
     int rc = upload_layout(s, coords);
     if (rc) return rc;
@@ -1036,6 +1377,7 @@ int frmc_store_get_coords(frmc_store *s, float *coords_out)
 {
     FRMC_REQUIRE(s && coords_out, FRMC_EINVAL, "NULL argument");
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     std::vector<float> rec((size_t)s->npad * 4);
     FRMC_CUDA(cudaMemcpyAsync(rec.data(), s->d_atoms, sizeof(float4) * s->npad, cudaMemcpyDeviceToHost, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
@@ -1053,6 +1395,8 @@ int frmc_grid_add(frmc_store *s, float rmin, float rmax, float bin, int hs)
     FRMC_REQUIRE(hs >= 1 && bin > 0.f, FRMC_EINVAL, "bad grid (hs=%d, bin=%g)", hs, bin);
     FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "cannot add a grid while a proposal is staged");
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    s->models_dirty = true;
     GridHost gh;
     memset(&gh.dev, 0, sizeof(gh.dev));
     gh.dev.g = make_grid(rmin, rmax, bin, hs);
@@ -1092,6 +1436,7 @@ int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *d)
         psym[p] = sym_index(d->pair_a[p], d->pair_b[p], s->nEl);
     }
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     ModelHost mh;
     memset(&mh.dev, 0, sizeof(mh.dev));
     mh.dev.kind = d->kind; mh.dev.grid = grid; mh.dev.n_pairs = d->n_pairs; mh.dev.n_out = d->n_out;
@@ -1121,6 +1466,10 @@ int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *d)
             if (!(ok[p] && sane)) rD[p] = __builtin_nanf("");
         }
         if ((rc = dev_copy(mh, (const float *)rD.data(), rD.size(), &mh.dev.rD))) return rc;
+        if (d->n_pairs <= EPI_INLINE_PAIRS)
+            for (int p = 0; p < d->n_pairs; ++p) {
+                mh.dev.i_psym[p] = psym[p]; mh.dev.i_w[p] = d->pair_w[p]; mh.dev.i_D[p] = d->pair_D[p]; mh.dev.i_rD[p] = rD[p];
+            }
     }
     if ((rc = dev_copy(mh, d->shell_volumes, (size_t)hs, &mh.dev.sv))) return rc;
     if ((rc = dev_copy(mh, d->prefactor, (size_t)hs, &mh.dev.pref))) return rc;
@@ -1169,7 +1518,9 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
     FRMC_REQUIRE(nshards >= 1 && shard >= 0 && shard < nshards, FRMC_EINVAL, "bad shard %d of %d", shard, nshards);
     FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
     FRMC_CUDA(cudaSetDevice(s->dev));
-    int rc = upload_items(s, shard, nshards);
+    int rc = flush_pending(s);
+    if (rc) return rc;
+    rc = upload_items(s, shard, nshards);
     if (rc) return rc;
     const int mode = current_mode(s, nullptr, nullptr);
     for (auto &g : s->grids) {
@@ -1191,6 +1542,7 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
 void *frmc_grid_counts_ptr(frmc_store *s, int grid, int64_t *n_cells)
 {
     if (!s || grid < 0 || grid >= (int)s->grids.size()) { set_error("unknown grid %d", grid); return nullptr; }
+    if (flush_pending(s)) return nullptr;
     if (n_cells) *n_cells = 2 * s->grids[grid].dev.cells;
     return s->grids[grid].dev.counts;
 }
@@ -1253,18 +1605,13 @@ int frmc_accept(frmc_store *s)
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
     FRMC_REQUIRE(s->state == 1, FRMC_ESTATE, "no staged proposal to accept");
     FRMC_CUDA(cudaSetDevice(s->dev));
-    GridSet gs = make_gridset(s);
-    TotalsCopy tc;
-    memset(&tc, 0, sizeof(tc));
-    tc.n = (int)s->models.size();
-    for (int m = 0; m < tc.n; ++m) { tc.len[m] = s->models[m].dev.n_out; tc.src[m] = s->models[m].dev.total; tc.dst[m] = s->models[m].total_committed; }
-    cudaEvent_t t0 = timing_begin(s);
-    commit_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs, s->d_atoms, s->d_prop, tc);
-    FRMC_LAUNCH_CHECK();
-    timing_end(s, TIME_COMMIT, t0);
+    // the device-side commit is deferred: the next fused proposal resolves it in its first phase,
+    // anything else that looks at the device state calls flush_pending() first
+    s->pending = 1;
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], s->prop_lo[c]); s->hi[c] = std::max(s->hi[c], s->prop_hi[c]); }
     for (size_t i = 0; i < s->models.size(); ++i) s->chi2_committed[i] = s->chi2_staged[i];
     s->state = 0;
+    if (!(s->fused_ok && !s->timing)) return flush_pending(s);
     return FRMC_OK;
 }
 
@@ -1273,12 +1620,9 @@ int frmc_reject(frmc_store *s)
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
     FRMC_REQUIRE(s->state == 1, FRMC_ESTATE, "no staged proposal to reject");
     FRMC_CUDA(cudaSetDevice(s->dev));
-    GridSet gs = make_gridset(s);
-    cudaEvent_t t0 = timing_begin(s);
-    clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs);
-    FRMC_LAUNCH_CHECK();
-    timing_end(s, TIME_COMMIT, t0);
+    s->pending = 2;
     s->state = 0;
+    if (!(s->fused_ok && !s->timing)) return flush_pending(s);
     return FRMC_OK;
 }
 
@@ -1329,6 +1673,7 @@ int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter)
     FRMC_REQUIRE(s && hintra && hinter, FRMC_EINVAL, "NULL argument");
     FRMC_REQUIRE(grid >= 0 && grid < (int)s->grids.size(), FRMC_EINVAL, "unknown grid %d", grid);
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     GridDev &G = s->grids[grid].dev;
     float *d_out = (float *)ctx_buffer(s->ctx, 5, sizeof(float) * 2 * G.cells);
     if (!d_out) return FRMC_ENOMEM;
@@ -1345,6 +1690,7 @@ int frmc_export_total(frmc_store *s, int model, int staged, float *out)
     FRMC_REQUIRE(s && out, FRMC_EINVAL, "NULL argument");
     FRMC_REQUIRE(model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     ModelHost &m = s->models[model];
     FRMC_CUDA(cudaMemcpyAsync(out, staged ? m.dev.total : m.total_committed, sizeof(float) * m.dev.n_out,
                               cudaMemcpyDeviceToHost, s->stream));
@@ -1355,6 +1701,7 @@ int frmc_export_total(frmc_store *s, int model, int staged, float *out)
 int frmc_store_set_timing(frmc_store *s, int on)
 {
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    { int frc = flush_pending(s); if (frc) return frc; }
     s->timing = on != 0;
     if (on) for (int i = 0; i < 4; ++i) { s->kernel_ms[i] = 0; s->kernel_launches[i] = 0; }
     return FRMC_OK;
