@@ -99,13 +99,6 @@ def n_pairs(n):
     return n * (n - 1) // 2
 
 
-class _DevArray(object):
-    """zero-copy view of a raw device pointer for torch.as_tensor (NCCL all-reduce of the counts)"""
-
-    def __init__(self, ptr, n, typestr="<i8"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def build_models(store, system, grid, exp_g, exp_s, q):
     from fullrmc_b200.model import ModelSpec
     common = dict(elements=system.elements, n_per_element=system.numberOfAtomsPerElement, weighting=system.weighting,
@@ -144,15 +137,19 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
     accepted = 0
     launches0 = t0 = None
     prev = None
+    mv = np.empty((1, 3), dtype=np.float32)
+    idx_list = idx_all.tolist()
+    step = store.step
     for it in range(total):
         if it == warm:
             launches0 = int(lib.frmc_launch_count())
             t0 = time.perf_counter()
-        i = idx_all[it:it + 1]
-        moved = box[i] + disp[it:it + 1]
-        chi_new = float(np.sum(store.step(prev, i, moved).astype(np.float64)))
+        ii = idx_list[it]
+        np.add(box[ii], disp[it], out=mv[0])
+        chi = step(prev, idx_all[it:it + 1], mv)
+        chi_new = float(chi[0]) + float(chi[1])
         if chi_new <= chi_old:                    # Engine.py:3310-3317 with tolerance 0
-            prev = True; box[i] = moved; chi_old = chi_new
+            prev = True; box[ii] = mv[0]; chi_old = chi_new
             if it >= warm:
                 accepted += 1
         else:
@@ -312,7 +309,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from fullrmc_b200 import _lib, synthetic
+    from fullrmc_b200 import _lib, parallel, synthetic
     from fullrmc_b200.Core import pairs_histograms as ph
     from fullrmc_b200.store import DeviceStore
 
@@ -325,7 +322,19 @@ def run_b200(args):
     os.environ["FULLRMC_B200_DEVICE"] = str(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the communicator comes up; the contract is ONE JSON
+        # line on stdout, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load_library()
     hbm_gbs, peak_src, sm_max_mhz = measured_peaks()
 
@@ -337,8 +346,7 @@ def run_b200(args):
     exp_s = smooth_target(NQ, 102, 1.0)
     store = DeviceStore(system.boxCoords, system.basis, True, system.moleculeIndex, system.elementIndex, 5, device=local)
     g = build_models(store, system, grid, exp_g, exp_s, q)
-    ptr, ncells = store.counts_pointer(g)
-    counts = torch.as_tensor(_DevArray(ptr, ncells), device="cuda:%d" % local)
+    counts = parallel.counts_tensor(store, g)           # int64 view of the store's device histogram
     ext = torch.cuda.ExternalStream(store.stream, device=local)
 
     def barrier():
@@ -347,10 +355,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def step():
-        store.compute_data_shard(rank, world)
-        if world > 1:
-            dist.all_reduce(counts)             # int64 sum over NVLink; issued on the store's stream
-        return store.finalize_data()
+        # this rank's tile shard -> NCCL all-reduce(sum) of the int64 counts over NVLink (issued on the
+        # store's stream) -> device epilogue
+        return parallel.compute_data_sharded(store, rank, world, tensors=[counts])
 
     sampler = ClockSampler(local)
     with torch.cuda.stream(ext):

@@ -56,6 +56,7 @@ SIGNATURES = {
                                                    _F, _F, _F, _I, _I, c_f32p, c_f32p, c_u64p]),
     "frmc_full_pairs_histograms_coords": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, _F, _F, _F, _I,
                                                _I, _I, c_f32p, c_f32p, c_u64p]),
+    "frmc_debug_work_items": (_I, [_I64, c_i32p, _I, _I, _I, _I, c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,
                                                   _I, c_f32p, c_f32p, c_u64p]),
     "frmc_single_pairs_histograms": (_I, [_I, ctypes.c_int32, c_f32p, _I64, _I64, c_i32p, c_i32p, _I, _I, c_f32p,

@@ -305,6 +305,43 @@ int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *coun
 
 using namespace frmc;
 
+// Host-only inspection of the multi-GPU decomposition (no device needed): number of work items and
+// of atom pairs covered by shard `shard` of `nshards` for a system with the given element indexes.
+// Summed over the shards the pair count is n(n-1)/2; used by the CPU tests of the sharding logic.
+extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,
+                                     int64_t *n_items, int64_t *n_pairs)
+{
+    FRMC_REQUIRE(n >= 0 && el && n_items && n_pairs, FRMC_EINVAL, "bad arguments");
+    FRMC_REQUIRE(nshards >= 1 && shard >= 0 && shard < nshards, FRMC_EINVAL, "bad shard %d of %d", shard, nshards);
+    std::vector<float> coords((size_t)n * 3, 0.f);
+    std::vector<int32_t> mol((size_t)n, 0);
+    HostLayout lay;
+    int rc = build_layout(coords.data(), n, mol.data(), el, nEl, lay);
+    if (rc) return rc;
+    int R; int64_t chunkJ;
+    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, R, chunkJ);
+    std::vector<WorkItem> items;
+    build_work_items(lay, R, chunkJ, shard, nshards, items);
+    auto real_in = [&](int e, int64_t a, int64_t b) -> int64_t {   // real atoms of segment e inside positions [a, b)
+        const int64_t end = lay.seg_start[e] + lay.seg_count[e];
+        return std::max<int64_t>(0, std::min(b, end) - std::max(a, lay.seg_start[e]));
+    };
+    int64_t pairs = 0;
+    for (const WorkItem &w : items) {
+        const int64_t i0 = w.i0, i1 = w.i0 + (int64_t)w.ni * SEG_PAD;
+        if (w.ea != w.eb) {
+            pairs += real_in(w.ea, i0, i1) * real_in(w.eb, w.j0, w.j1);
+        } else {
+            const int64_t end = lay.seg_start[w.ea] + lay.seg_count[w.ea];
+            for (int64_t p = i0; p < std::min(i1, end); ++p)                 // pairs p < q, q in [j0, j1)
+                pairs += std::max<int64_t>(0, std::min<int64_t>(w.j1, end) - std::max<int64_t>(w.j0, p + 1));
+        }
+    }
+    *n_items = (int64_t)items.size();
+    *n_pairs = pairs;
+    return FRMC_OK;
+}
+
 extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
                                                  const int32_t *mol, const int32_t *el, int nEl, float rmin, float rmax,
                                                  float bin, int hs, int shard, int nshards, float *hintra,

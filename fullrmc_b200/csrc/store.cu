@@ -215,12 +215,22 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
     __syncthreads();
     unsigned long long ov = 0;
     const int T = gridDim.x * blockDim.x;
+    // double-buffered: the DELTA_UNROLL loads of the next batch are in flight while this batch is processed
+    const float4 padrec = make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+    float4 nxt[DELTA_UNROLL];
+    {
+        const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? atoms[p] : padrec; }
+    }
     for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < npad; p0 += DELTA_UNROLL * T) {
         float4 a[DELTA_UNROLL];
 #pragma unroll
-        for (int u = 0; u < DELTA_UNROLL; ++u) {
-            const int p = p0 + u * T;
-            a[u] = (p < npad) ? atoms[p] : make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+        for (int u = 0; u < DELTA_UNROLL; ++u) a[u] = nxt[u];
+        {
+            const int q0 = p0 + DELTA_UNROLL * T;
+#pragma unroll
+            for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = q0 + u * T; nxt[u] = (p < npad) ? atoms[p] : padrec; }
         }
 #pragma unroll
         for (int u = 0; u < DELTA_UNROLL; ++u) {

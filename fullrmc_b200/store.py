@@ -51,6 +51,8 @@ class DeviceStore(object):
         self._models = []         # ModelSpec
         self._keep = []           # arrays referenced by descriptors during frmc_model_add
         self._chi2 = np.zeros(8, dtype=_F32)
+        self._chi2_ptr = L.ptr(self._chi2, L.c_f32p)
+        self._step_fn = self._lib.frmc_step
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -132,15 +134,21 @@ class DeviceStore(object):
 
     def step(self, previous, indexes, movedBoxCoordinates):
         """Resolve the staged proposal (previous: True accept / False reject / None nothing staged)
-        and evaluate the next one with a single call into the library."""
-        idx = np.ascontiguousarray(indexes, dtype=_I32)
-        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
-        if moved.shape != (idx.shape[0], 3):
+        and evaluate the next one with a single call into the library.  Returns a VIEW of the
+        chi^2 buffer (valid until the next call); this is the lean entry point for tight loops."""
+        idx, moved = indexes, movedBoxCoordinates
+        if not (type(idx) is np.ndarray and idx.dtype == _I32 and idx.flags.c_contiguous):
+            idx = np.ascontiguousarray(idx, dtype=_I32)
+        if not (type(moved) is np.ndarray and moved.dtype == _F32 and moved.flags.c_contiguous):
+            moved = np.ascontiguousarray(moved, dtype=_F32)
+        k = idx.shape[0]
+        if moved.size != 3 * k:
             raise ValueError("movedBoxCoordinates must be (k,3)")
-        prev = -1 if previous is None else int(bool(previous))
-        L.check(self._lib.frmc_step(self._handle, prev, L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(moved, L.c_f32p),
-                                    L.ptr(self._chi2, L.c_f32p)), "step")
-        return self._chi2[:self.n_models].copy()
+        prev = -1 if previous is None else (1 if previous else 0)
+        rc = self._step_fn(self._handle, prev, idx.ctypes.data_as(L.c_i32p), k, moved.ctypes.data_as(L.c_f32p), self._chi2_ptr)
+        if rc < 0:
+            L.check(rc, "step")
+        return self._chi2[:len(self._models)]
 
     def replay_proposal(self, reps):
         """Average device time (ms) of the staged proposal's pipeline over `reps` back-to-back launches."""

@@ -94,6 +94,11 @@ int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, c
                                       float rmax, float bin, int hs, int shard, int nshards,
                                       float *hintra, float *hinter, uint64_t *edge_overflow);
 
+/* Host-only view of the multi-GPU decomposition of the full histogram (runs without a device):
+ * work items and atom pairs assigned to `shard` of `nshards`; over all shards the pairs sum to n(n-1)/2. */
+int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,
+                          int64_t *n_items, int64_t *n_pairs);
+
 /* Extensions/pairs_histograms.pyx:225-281 multiple_pairs_histograms_dists; distances is
  * [n,k] row-major, column t belongs to indexes[t].  (:343-383 full_* = arange, allAtoms=0) */
 int frmc_multiple_pairs_histograms_dists(int dev, const int32_t *indexes, int64_t k, const float *distances,
