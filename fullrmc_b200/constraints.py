@@ -1,0 +1,209 @@
+"""Device-backed mirrors of the three hot-path constraints' five methods.
+
+Reference classes (method names, argument meaning and state attributes are kept):
+
+* PairDistributionConstraint   Constraints/PairDistributionConstraints.py:1001-1166
+* PairCorrelationConstraint    Constraints/PairCorrelationConstraints.py:263-392
+* StructureFactorConstraint / ReducedStructureFactorConstraint
+                               Constraints/StructureFactorConstraints.py:933-1096, :1235-1260
+
+``compute_data / compute_before_move / compute_after_move / accept_move / reject_move`` are
+what ``Engine.__on_runtime_step_try_move`` calls (Engine.py:3302-3338).  Here they drive ONE
+shared :class:`~fullrmc_b200.store.DeviceStore`: every constraint registered on a
+:class:`DeviceBackend` is evaluated by the same pass over the device-resident coordinates
+(SURVEY.md section 7.2-6b), so a move costs one kernel launch however many constraints
+listen.  The Engine keeps calling the constraints one after another; the first
+``compute_after_move`` of a move triggers the device evaluation, the others read its result,
+and ``accept_move`` / ``reject_move`` resolve the staged proposal once.
+
+These classes stand alone (the reference's own classes need pdbparser / pyrep, which the
+GPU box does not have); INTEGRATION.md shows the three-line subclass a fullrmc maintainer
+writes to put them behind the real constraint classes.
+"""
+import numpy as np
+
+from .model import FLOAT_TYPE, ModelSpec, shell_volumes_from_edges
+from .store import DeviceStore
+
+
+class DeviceBackend(object):
+    """One device store per engine; constraints register their r-grid and model on it."""
+
+    def __init__(self, boxCoordinates, basisVectors, isPBC, moleculesIndex, elementsIndex, elements,
+                 numberOfAtomsPerElement, volume, numberDensity, device=None):
+        self.elements = list(elements)
+        self.numberOfAtomsPerElement = dict(numberOfAtomsPerElement)
+        self.volume = FLOAT_TYPE(volume)
+        self.numberDensity = FLOAT_TYPE(numberDensity)
+        self.store = DeviceStore(boxCoordinates, basisVectors, isPBC, moleculesIndex, elementsIndex,
+                                 len(self.elements), device=device)
+        self.constraints = []
+        self._grids = {}
+        self._move = None            # (indexes, moved) of the proposal being evaluated
+        self._chi2 = None            # chi^2 per model of the staged proposal
+        self._resolved = True
+        self._dirty = True           # committed data need a compute_data pass
+
+    # -------------------------------------------------------------- registration
+    def _grid(self, minDistance, maxDistance, bin, histSize):
+        key = (float(minDistance), float(maxDistance), float(bin), int(histSize))
+        if key not in self._grids:
+            self._grids[key] = self.store.add_grid(minDistance, maxDistance, bin, histSize)
+        return self._grids[key]
+
+    def _register(self, constraint, grid_key, spec):
+        g = self._grid(*grid_key)
+        constraint._model = self.store.add_model(g, spec)
+        constraint._grid = g
+        self.constraints.append(constraint)
+        self._dirty = True
+
+    # -------------------------------------------------------------- engine-facing protocol
+    def _compute_data(self):
+        if self._dirty:
+            self._committed = self.store.compute_data()
+            self._dirty = False
+        return self._committed
+
+    def _before(self, relativeIndexes):
+        # compute_before_move needs no device work of its own: the delta pass forms
+        # after-minus-before in one sweep (PairDistributionConstraints.py:1053-1078 + :1095-1120)
+        self._compute_data()
+        idx = np.ascontiguousarray(relativeIndexes, dtype=np.int32)
+        if self._move is None or not np.array_equal(self._move[0], idx):
+            self._move = (idx, None)
+            self._chi2 = None
+
+    def _after(self, relativeIndexes, movedBoxCoordinates):
+        idx = np.ascontiguousarray(relativeIndexes, dtype=np.int32)
+        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=np.float32)
+        same = (self._chi2 is not None and self._move is not None and self._move[1] is not None and
+                np.array_equal(self._move[0], idx) and np.array_equal(self._move[1], moved))
+        if not same:
+            if not self._resolved:
+                raise RuntimeError("previous move was neither accepted nor rejected")
+            self._chi2 = self.store.propose(idx, moved).copy()
+            self._move = (idx, moved)
+            self._resolved = False
+        return self._chi2
+
+    def _resolve(self, accept):
+        if not self._resolved:
+            (self.store.accept if accept else self.store.reject)()
+            if accept:
+                self._committed = self._chi2.copy()
+            self._resolved = True
+            self._move = None
+            self._chi2 = None
+
+    def close(self):
+        self.store.close()
+
+
+class _DeviceExperimentalConstraint(object):
+    """Shared implementation of the five methods; subclasses fix the model kind."""
+    KIND = None
+
+    def __init__(self, backend, experimentalData, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
+                 weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None):
+        self.backend = backend
+        self.experimentalData = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
+        self.minimumDistance = FLOAT_TYPE(minDistance)
+        self.maximumDistance = FLOAT_TYPE(maxDistance)
+        self.bin = FLOAT_TYPE(bin)
+        self.histogramSize = int(histSize)
+        self.shellCenters = np.ascontiguousarray(shellCenters, dtype=FLOAT_TYPE)
+        self.shellVolumes = np.ascontiguousarray(shellVolumes, dtype=FLOAT_TYPE)
+        self.standardError = None
+        self.afterMoveStandardError = None
+        self.tried = 0
+        self.accepted = 0
+        spec = ModelSpec(self.KIND, backend.elements, backend.numberOfAtomsPerElement, weighting, backend.volume,
+                         backend.numberDensity, self.shellCenters, self.shellVolumes, self.experimentalData,
+                         data_weights=dataWeights, shape_array=shapeArray, scale_factor=scaleFactor, q_values=qValues)
+        backend._register(self, (self.minimumDistance, self.maximumDistance, self.bin, self.histogramSize), spec)
+
+    # -- the reference's properties
+    @property
+    def data(self):
+        """{"intra", "inter"} float32 (nEl,nEl,histSize) arrays, exported from the device on demand
+        (save / plot / parity; never needed in the Monte-Carlo loop)."""
+        self.backend._compute_data()
+        intra, inter = self.backend.store.export_data(self._grid)
+        return {"intra": intra, "inter": inter}
+
+    def get_constraint_total(self, staged=False):
+        """model total (G(r), g(r) or S(Q)) of the committed (or staged) state"""
+        self.backend._compute_data()
+        return self.backend.store.export_total(self._model, staged=staged)
+
+    # -- the five methods (Core/Constraint.py:732-748)
+    def compute_data(self, update=True):
+        self.backend._dirty = self.backend._dirty or update
+        chi2 = self.backend._compute_data()
+        if update:
+            self.standardError = FLOAT_TYPE(chi2[self._model])
+        return self.data, FLOAT_TYPE(chi2[self._model])
+
+    def compute_before_move(self, realIndexes, relativeIndexes):
+        self.backend._before(relativeIndexes)
+        if self.standardError is None:
+            self.standardError = FLOAT_TYPE(self.backend._committed[self._model])
+
+    def compute_after_move(self, realIndexes, relativeIndexes, movedBoxCoordinates):
+        chi2 = self.backend._after(relativeIndexes, movedBoxCoordinates)
+        self.afterMoveStandardError = FLOAT_TYPE(chi2[self._model])
+        self.tried += 1
+
+    def accept_move(self, realIndexes, relativeIndexes):
+        self.backend._resolve(True)
+        self.standardError = self.afterMoveStandardError
+        self.afterMoveStandardError = None
+        self.accepted += 1
+
+    def reject_move(self, realIndexes, relativeIndexes):
+        self.backend._resolve(False)
+        self.afterMoveStandardError = None
+
+
+class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
+    """G(r) constraint; experimentalData is the (n,2) [r, G(r)] array of the reference
+    (set_experimental_data / set_limits, PairDistributionConstraints.py:700-768)."""
+    KIND = "PDF"
+
+    def __init__(self, backend, experimentalData, weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0):
+        exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
+        r = exp[:, 0]
+        b = FLOAT_TYPE(r[1] - r[0])                                            # :726
+        rmin = FLOAT_TYPE(r[0] - b / 2.)                                       # :747
+        rmax = FLOAT_TYPE(r[-1] + b / 2.)                                      # :748
+        edges = np.array([x - b / 2. for x in r] + [r[-1] + b / 2.], dtype=FLOAT_TYPE)   # :751-753
+        hs = len(edges) - 1
+        super(DevicePairDistributionConstraint, self).__init__(
+            backend, exp[:, 1], rmin, rmax, b, hs, np.array(r, dtype=FLOAT_TYPE), shell_volumes_from_edges(edges),
+            weighting, dataWeights, shapeArray, scaleFactor)
+
+
+class DevicePairCorrelationConstraint(DevicePairDistributionConstraint):
+    """g(r) constraint (PairCorrelationConstraints.py:126-169)."""
+    KIND = "PCF"
+
+
+class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
+    """S(Q) constraint: experimentalData is (m,2) [Q, S(Q)]; the r-grid is the reference's
+    (StructureFactorConstraints.py:330-350: edges = arange(rmin, rmax, dr))."""
+    KIND = "SQ"
+
+    def __init__(self, backend, experimentalData, weighting, rmin, rmax, dr, dataWeights=None, scaleFactor=1.0):
+        exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
+        edges = np.arange(rmin, rmax, dr).astype(FLOAT_TYPE)                   # :337-341
+        centers = (edges[0:-1] + edges[1:]) / FLOAT_TYPE(2.)                   # :346
+        hs = len(edges) - 1
+        super(DeviceStructureFactorConstraint, self).__init__(
+            backend, exp[:, 1], edges[0], edges[-1], FLOAT_TYPE(dr), hs, centers, shell_volumes_from_edges(edges),
+            weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0])
+
+
+class DeviceReducedStructureFactorConstraint(DeviceStructureFactorConstraint):
+    """S(Q)-1 normalisation (StructureFactorConstraints.py:1235-1260)."""
+    KIND = "RSQ"

@@ -268,3 +268,71 @@ def test_two_grids_one_pass(orc):
         assert F32(chi2[0]) == F32(want[0]) and F32(chi2[1]) == F32(want[1])
         store.accept(); box = tmp
     store.close()
+
+
+def test_constraint_mirrors_five_method_protocol(orc):
+    """DevicePairDistributionConstraint + DeviceReducedStructureFactorConstraint driven exactly like
+    Engine.__on_runtime_step_try_move drives the reference constraints (Engine.py:3302-3338):
+    before/after for every constraint, Metropolis on the summed chi^2, accept_move/reject_move on all."""
+    from fullrmc_b200.constraints import (DeviceBackend, DevicePairDistributionConstraint,
+                                          DeviceReducedStructureFactorConstraint)
+    case = CASES["ortho_atomic"]
+    rng = np.random.default_rng(21)
+    els, n_per, wdict, volume, rho0 = _system_meta(case)
+    box = case["boxCoords"].copy()
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    backend = DeviceBackend(box, case["basis"], True, mol, el, els, n_per, volume, rho0)
+    # PDF from an "experimental" r column (bin 0.02), S(Q)-1 on its own coarse r-grid (NiTi-like, SURVEY 8a a15)
+    r = (0.01 + 0.02 * np.arange(650)).astype(F32)
+    exp_pdf = np.stack([r, rng.normal(0, 0.3, 650).astype(F32)], axis=1).astype(F32)
+    q = np.linspace(0.5, 15.0, 117).astype(F32)
+    exp_sq = np.stack([q, rng.normal(0, 0.2, 117).astype(F32)], axis=1).astype(F32)
+    pdf = DevicePairDistributionConstraint(backend, exp_pdf, wdict)
+    rsf = DeviceReducedStructureFactorConstraint(backend, exp_sq, wdict, rmin=0.3, rmax=14.0, dr=0.2)
+    constraints = [pdf, rsf]
+
+    def oracle(boxc):
+        out = []
+        for c, kind in ((pdf, "PDF"), (rsf, "RSQ")):
+            hi, he = orc.full_pairs_histograms_coords(boxCoords=boxc, basis=case["basis"], isPBC=True, moleculeIndex=mol,
+                                                      elementIndex=el, numberOfElements=3, minDistance=c.minimumDistance,
+                                                      maxDistance=c.maximumDistance, bin=c.bin, histSize=c.histogramSize)
+            common = dict(elements=els, n_per_element=n_per, weighting=wdict, volume=volume, rho0=rho0,
+                          shell_centers=c.shellCenters, shell_volumes=c.shellVolumes)
+            if kind == "PDF":
+                tot = ep.total_Gr(hi, he, **common)
+            else:
+                tot = ep.total_Sq(hi, he, gr2sq=ep.gr2sq_matrix(q, c.shellCenters), reduced=True, **common)
+            out.append(ep.standard_error(c.experimentalData, tot))
+        return out
+
+    for c in constraints:
+        data, err = c.compute_data()
+    want = oracle(box)
+    assert F32(pdf.standardError) == F32(want[0]) and F32(rsf.standardError) == F32(want[1])
+    assert pdf.data["inter"].sum() > 0
+    total_old = float(pdf.standardError) + float(rsf.standardError)
+    n_acc = 0
+    for step in range(8):
+        idx = np.array([int(rng.integers(0, box.shape[0]))], dtype=np.int32)
+        moved = (box[idx] + rng.normal(0, 0.02, (1, 3)).astype(F32)).astype(F32)
+        for c in constraints:
+            c.compute_before_move(idx, idx)
+            c.compute_after_move(idx, idx, moved)
+        tmp = box.copy(); tmp[idx] = moved
+        want = oracle(tmp)
+        assert F32(pdf.afterMoveStandardError) == F32(want[0])
+        assert F32(rsf.afterMoveStandardError) == F32(want[1])
+        total_new = float(pdf.afterMoveStandardError) + float(rsf.afterMoveStandardError)
+        if total_new <= total_old:
+            for c in constraints:
+                c.accept_move(idx, idx)
+            box, total_old = tmp, total_new
+            n_acc += 1
+        else:
+            for c in constraints:
+                c.reject_move(idx, idx)
+        assert F32(pdf.standardError) == F32(oracle(box)[0])
+    assert pdf.tried == 8 and rsf.tried == 8 and pdf.accepted == n_acc
+    assert np.array_equal(backend.store.get_coords(), box)
+    backend.close()
