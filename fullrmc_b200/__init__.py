@@ -16,4 +16,4 @@ There is no CPU fallback: importing works anywhere, but every compute call raise
 """
 __version__ = "0.1.0"
 
-from ._lib import FullrmcB200Error, library_path, load_library  # noqa: F401
+from ._lib import FullrmcB200Error, library_path, load_library, set_edge_spill  # noqa: F401

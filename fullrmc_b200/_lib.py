@@ -49,6 +49,7 @@ SIGNATURES = {
     "frmc_last_error": (ctypes.c_char_p, []),
     "frmc_version": (ctypes.c_char_p, []),
     "frmc_device_count": (_I, []),
+    "frmc_set_edge_spill": (_I, [_I]),
     "frmc_launch_count": (ctypes.c_uint64, []),
     "frmc_points_to_coords": (_I, [_I, c_f32p, c_i32p, c_i64p, _I64, c_f32p, _I64, c_f32p, _I, _I, _I, c_f32p]),
     "frmc_from_to_points_differences": (_I, [_I, c_f32p, c_f32p, _I64, c_f32p, _I, c_f32p]),
@@ -131,6 +132,13 @@ def check(rc, what):
     msg = "%s: %s" % (what, last_error())
     cls = _ERR_CLASSES.get(rc, FullrmcB200Error)
     raise cls(msg)
+
+
+def set_edge_spill(on):
+    """Edge-bin policy for grids and stateless calls created from now on (see include/fullrmc_b200.h):
+    False (default) drops pairs whose fp32 bin index rounds up to histSize, True reproduces the
+    reference's in-array spill of that unchecked write.  Returns the previous setting."""
+    return bool(load_library().frmc_set_edge_spill(int(bool(on))))
 
 
 def device_index():

@@ -207,3 +207,18 @@ class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
 class DeviceReducedStructureFactorConstraint(DeviceStructureFactorConstraint):
     """S(Q)-1 normalisation (StructureFactorConstraints.py:1235-1260)."""
     KIND = "RSQ"
+
+
+_KIND_CLASS = {}
+
+
+def make_device_constraint(backend, kind, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
+                           weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None):
+    """Build a device constraint from the quantities a reference constraint has already derived
+    (limits, bin, histogram size, shell arrays, weighting scheme) -- what the subclass recipe of
+    INTEGRATION.md hands over."""
+    if not _KIND_CLASS:
+        for name in ("PDF", "PCF", "SQ", "RSQ"):
+            _KIND_CLASS[name] = type("Device%sConstraint" % name, (_DeviceExperimentalConstraint,), {"KIND": name})
+    return _KIND_CLASS[kind](backend, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
+                             weighting, dataWeights, shapeArray, scaleFactor, qValues)

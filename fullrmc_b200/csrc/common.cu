@@ -10,6 +10,7 @@ namespace frmc {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launch_count = 0;
+int g_edge_spill = 0;
 
 void set_error(const char *fmt, ...)
 {
@@ -163,5 +164,12 @@ int frmc_device_count(void)
 }
 
 uint64_t frmc_launch_count(void) { return frmc::g_launch_count; }
+
+int frmc_set_edge_spill(int on)
+{
+    int old = frmc::g_edge_spill;
+    frmc::g_edge_spill = on ? 1 : 0;
+    return old;
+}
 
 }

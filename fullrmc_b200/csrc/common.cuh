@@ -70,7 +70,12 @@ struct GridParams {
     float rmin, rmax, bin;
     float t2min, t2max;
     int hs;
+    int spill;      // 1: reproduce the reference's unchecked write when bin == histSize (flat index spills
+    int pad;        //    into the next [a,b] slab of the same array); 0: drop.  Counted either way.
 };
+
+// global default for new grids / stateless calls (frmc_set_edge_spill)
+extern int g_edge_spill;
 
 // smallest non-negative fp32 t such that fl(sqrtf(t)) >= r
 float sqrt_threshold(float r);

@@ -126,12 +126,20 @@ void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, i
 // ------------------------------------------------------------------ the kernel
 static const int JS = 512;   // J atoms staged per shared-memory sub-tile
 
+// where an overflowing event goes when the reference's unchecked write is reproduced: straight to the
+// global ordered histogram (rare: a pair within an ulp of maxDistance)
+struct SpillTarget {
+    unsigned long long *counts;   // [2][nEl*nEl][hs]
+    long long cells;
+    int slab_ab, slab_ba;
+};
+
 template <int MODE, int R, bool TRI>
 __device__ __forceinline__ void sweep_subtile(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int cnt,
                                               int jbase, const float (&xi)[R], const float (&yi)[R],
                                               const float (&zi)[R], const uint32_t (&mi)[R], const uint32_t (&oi)[R],
                                               int p0, bool cross, const Lattice &L, const GridParams &g,
-                                              unsigned int *__restrict__ sh, unsigned long long &ov)
+                                              unsigned int *__restrict__ sh, unsigned long long &ov, const SpillTarget &sp)
 {
 #pragma unroll 4
     for (int q = 0; q < cnt; ++q) {
@@ -142,13 +150,15 @@ __device__ __forceinline__ void sweep_subtile(const float4 *__restrict__ sJ, con
             if (in_range(d2, g)) {
                 if (!TRI || (p0 + r * SEG_PAD < jbase + q)) {
                     int b = bin_index(d2, g);
+                    uint32_t mj = __float_as_uint(a.w);
+                    int same = ((mi[r] >> 8) == (mj >> 8)) ? 0 : 2;          // slots 0,1 intra; 2,3 inter
+                    int ord = (cross && (oi[r] > sO[q])) ? 1 : 0;            // 1: the J atom comes first in original order
                     if (b < g.hs) {
-                        uint32_t mj = __float_as_uint(a.w);
-                        int same = ((mi[r] >> 8) == (mj >> 8)) ? 0 : 2;          // slots 0,1 intra; 2,3 inter
-                        int ord = (cross && (oi[r] > sO[q])) ? 1 : 0;            // 1: the J atom comes first in original order
                         atomicAdd(&sh[(same + ord) * g.hs + b], 1u);
                     } else {
                         ++ov;
+                        const long long flat = (long long)(ord ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+                        if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[(same ? sp.cells : 0) + flat], 1ull);
                     }
                 }
             }
@@ -199,6 +209,8 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         }
         const bool cross = (w.ea != w.eb);
         const int p0 = w.i0 + tid;
+        SpillTarget sp;
+        sp.counts = counts; sp.cells = cells; sp.slab_ab = w.ea * nEl + w.eb; sp.slab_ba = w.eb * nEl + w.ea;
 
         for (int js = w.j0; js < w.j1; js += JS) {
             const int cnt = min(JS, w.j1 - js);
@@ -206,9 +218,9 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
             for (int q = tid; q < cnt; q += 256) { sJ[q] = atoms[js + q]; sO[q] = orig[js + q]; }
             __syncthreads();
             if (w.tri && js < w.i0 + w.ni * SEG_PAD)
-                sweep_subtile<MODE, R, true>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov);
+                sweep_subtile<MODE, R, true>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov, sp);
             else
-                sweep_subtile<MODE, R, false>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov);
+                sweep_subtile<MODE, R, false>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov, sp);
         }
         __syncthreads();
         // flush the CTA-private counters of this item into the ordered global histogram

@@ -92,12 +92,9 @@ rows_hist_kernel(const float *__restrict__ coords, const int *__restrict__ mol, 
             float d2 = dist2<MODE>(r.x, r.y, r.z, xj, yj, zj, L);
             if (in_range(d2, g)) {
                 int b = bin_index(d2, g);
-                if (b < g.hs) {
-                    long long at = ((long long)r.el * nEl + ej) * g.hs + b + ((mj == r.mol) ? 0 : cells);
-                    atomicAdd(&counts[at], 1u);
-                } else {
-                    ++ov;
-                }
+                long long flat = ((long long)r.el * nEl + ej) * g.hs + b;
+                if (b >= g.hs) ++ov;
+                if (b < g.hs || (g.spill && flat < cells)) atomicAdd(&counts[flat + ((mj == r.mol) ? 0 : cells)], 1u);
             }
         }
     }
@@ -120,10 +117,13 @@ __global__ void dists_hist_kernel(const float *__restrict__ distances, long long
     float d = distances[i * stride_row + t * stride_col];
     int b;
     if (!bin_of_distance(d, g, b)) return;
-    if (b >= g.hs || b < 0) { atomicAdd(overflow, 1ull); return; }
     const long long cells = (long long)nEl * nEl * g.hs;
-    long long at = ((long long)el[a] * nEl + el[i]) * g.hs + b + ((mol[i] == mol[a]) ? 0 : cells);
-    atomicAdd(&counts[at], 1u);
+    const long long flat = ((long long)el[a] * nEl + el[i]) * g.hs + b;
+    if (b >= g.hs || b < 0) {
+        atomicAdd(overflow, 1ull);
+        if (!g.spill || b < 0 || flat >= cells) return;
+    }
+    atomicAdd(&counts[flat + ((mol[i] == mol[a]) ? 0 : cells)], 1u);
 }
 
 // counts (u32) -> fp32, optionally added onto an existing fp32 histogram (in-place API)
@@ -195,6 +195,8 @@ GridParams make_grid(float rmin, float rmax, float bin, int hs)
     g.rmin = rmin; g.rmax = rmax; g.bin = bin; g.hs = hs;
     g.t2min = sqrt_threshold(rmin);
     g.t2max = sqrt_threshold(rmax);
+    g.spill = g_edge_spill;
+    g.pad = 0;
     return g;
 }
 

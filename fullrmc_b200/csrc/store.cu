@@ -162,7 +162,7 @@ __global__ void clear_delta_kernel(GridSet gs)
 }
 
 // ------------------------------------------------------------------ kernels: delta pass
-__device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab, int sym, const GridSet &gs,
+__device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab, int sym, const GridSet &gs, int nEl,
                                           unsigned long long &ov)
 {
 #pragma unroll 1
@@ -175,6 +175,13 @@ __device__ __forceinline__ void delta_hit(float d2, int sign, int same, int slab
                 atomicAdd(&G.stot[(long long)sym * G.g.hs + b], sign);
             } else {
                 ++ov;
+                // reference-compatible spill of the unchecked write: flat index runs into the next slab
+                const long long flat = (long long)slab * G.g.hs + b;
+                if (G.g.spill && flat < G.cells) {
+                    const int s2 = (int)(flat / G.g.hs), b2 = (int)(flat - (long long)s2 * G.g.hs);
+                    atomicAdd(&G.delta[(same ? 0 : G.cells) + flat], sign);
+                    atomicAdd(&G.stot[(long long)sym_index(s2 / nEl, s2 % nEl, nEl) * G.g.hs + b2], sign);
+                }
             }
         }
     }
@@ -253,8 +260,8 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
                     const int et = (int)(mt & 0xFF);
                     const int slab = et * nEl + ej;
                     const int sym = sym_index(et, ej, nEl);
-                    if (ho) delta_hit(d2o, -1, same, slab, sym, gs, ov);
-                    if (hn) delta_hit(d2n, +1, same, slab, sym, gs, ov);
+                    if (ho) delta_hit(d2o, -1, same, slab, sym, gs, nEl, ov);
+                    if (hn) delta_hit(d2n, +1, same, slab, sym, gs, nEl, ov);
                 }
             }
         }
@@ -272,8 +279,8 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
             const int sym = sym_index(et, eu, nEl);
             const float d2o = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
             const float d2n = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
-            if ((d2o >= gs.t2lo) && (d2o < gs.t2hi)) delta_hit(d2o, -1, same, slab, sym, gs, ov);
-            if ((d2n >= gs.t2lo) && (d2n < gs.t2hi)) delta_hit(d2n, +1, same, slab, sym, gs, ov);
+            if ((d2o >= gs.t2lo) && (d2o < gs.t2hi)) delta_hit(d2o, -1, same, slab, sym, gs, nEl, ov);
+            if ((d2n >= gs.t2lo) && (d2n < gs.t2hi)) delta_hit(d2n, +1, same, slab, sym, gs, nEl, ov);
         }
     }
     if (ov) atomicAdd(overflow, ov);

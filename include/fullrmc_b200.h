@@ -48,6 +48,13 @@ extern "C" {
 
 const char *frmc_last_error(void);
 const char *frmc_version(void);
+/* Edge-bin policy for grids / stateless calls created AFTER the call.  The reference writes
+ * hist[a,b,bin] with boundscheck(False); when fp32 rounding makes bin == histSize (a pair within an
+ * ulp of maxDistance; happens in Examples/atomicNiTi within 10 moves) that write lands in the next
+ * [a,b] slab's first bin (or outside the array for the last slab).  on=0 (default): such events are
+ * dropped; on=1: the in-array spill is reproduced so trajectories stay bit-identical to the
+ * reference's.  Either way they are counted in edge_overflow.  Returns the previous setting. */
+int frmc_set_edge_spill(int on);
 /* number of visible CUDA devices, or a negative error code (no CPU fallback exists) */
 int frmc_device_count(void);
 

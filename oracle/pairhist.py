@@ -48,6 +48,11 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+def set_emulate_spill(on):
+    """reproduce (True) or drop (False, default) the reference's out-of-bounds write when bin == histSize"""
+    lib().orc_set_emulate_spill(int(bool(on)))
+
+
 def max_threads():
     return int(lib().orc_max_threads())
 

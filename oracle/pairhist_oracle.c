@@ -114,6 +114,13 @@ void orc_pairs_differences(const float *point, const float *coords, int64_t n, c
  * The reference does no bounds check (boundscheck(False)); a bin index that lands
  * on histSize because of fp32 rounding is undefined behaviour there.  Here it is
  * dropped and counted in *overflow so the GPU path can report the same events. */
+/* orc_emulate_spill != 0: reproduce what the reference's unchecked write actually does on this
+ * platform when bin == histSize: the flat index (a*nEl+b)*hs + bin lands in the NEXT slab's first
+ * bins (same array); events that would leave the array are dropped.  Either way the event is
+ * counted in *overflow.  Default 0: drop (the physically meaningful behaviour). */
+static int orc_emulate_spill = 0;
+void orc_set_emulate_spill(int on) { orc_emulate_spill = on; }
+
 static inline void orc_bin_one(float d, int same_mol, int32_t ea, int32_t eb, int nEl, int hs,
                                float rmin, float rmax, float bin, float *hintra, float *hinter,
                                uint64_t *overflow)
@@ -121,8 +128,11 @@ static inline void orc_bin_one(float d, int same_mol, int32_t ea, int32_t eb, in
     if (d < rmin) return;
     if (d >= rmax) return;
     int32_t b = (int32_t)((d - rmin) / bin);
-    if (b >= hs || b < 0) { if (overflow) (*overflow)++; return; }
     int64_t at = ((int64_t)ea * nEl + eb) * hs + b;
+    if (b >= hs || b < 0) {
+        if (overflow) (*overflow)++;
+        if (!orc_emulate_spill || b < 0 || at >= (int64_t)nEl * nEl * hs) return;
+    }
     if (same_mol) hintra[at] += 1.0f; else hinter[at] += 1.0f;
 }
 

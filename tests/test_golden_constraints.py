@@ -1,0 +1,163 @@
+"""Golden trajectories recorded from the UNMODIFIED reference constraint classes
+(tests/gen_golden_constraints.py: PairDistributionConstraint, PairCorrelationConstraint,
+StructureFactorConstraint, ReducedStructureFactorConstraint on the shipped NiTi / THF / SiOx
+example inputs and a synthetic triclinic system), replayed
+
+* on the CPU through the oracle restatement (pins oracle/epilogue.py and the M-F sequence
+  against the reference's own class code), and
+* on the GPU through the device constraint mirrors (the parity test of the stateful path).
+
+Bar: chi^2 after every move, the committed chi^2, totals and the final data arrays bit-exact.
+
+Edge bins: in the NiTi example a Ni-Ni pair lands within an ulp of the S(Q) grid's maxDistance at
+move 9, its fp32 bin index equals histSize and the reference's unchecked write spills into the
+next slab ([ni,ti], bin 0).  These replays therefore run with the reference-compatible spill
+switched on (oracle.set_emulate_spill / fullrmc_b200.set_edge_spill); the default policy (drop and
+count) is exercised in tests/test_gpu_stateless.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import epilogue as ep
+
+F32 = np.float32
+NAMES = ["niti", "thf", "siox", "synth"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, "constraints_%s.npz" % name))
+
+
+def _constraint_desc(g, ci):
+    d = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("c%d/" % ci)}
+    d["kind"] = str(d["kind"])
+    d["weighting"] = {str(p): F32(w) for p, w in zip(d["pairs"], d["pair_w"])}
+    d["dataWeights"] = None if d["dataWeights"].shape[0] == 0 else d["dataWeights"]
+    d["shapeArray"] = None if d["shapeArray"].shape[0] == 0 else d["shapeArray"]
+    return d
+
+
+def _system(g):
+    elements = [str(e) for e in g["elements"]]
+    counts = np.bincount(g["elementIndex"], minlength=len(elements))
+    n_per = {elements[i]: int(counts[i]) for i in range(len(elements))}
+    return elements, n_per
+
+
+def _oracle_total(d, intra, inter, elements, n_per, volume, rho0):
+    common = dict(elements=elements, n_per_element=n_per, weighting=d["weighting"], volume=volume, rho0=rho0,
+                  shell_centers=d["shellCenters"], shell_volumes=d["shellVolumes"])
+    sf = float(d["scaleFactor"])
+    if d["kind"] == "PDF":
+        return ep.total_Gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, **common)
+    if d["kind"] == "PCF":
+        return ep.total_gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, **common)
+    return ep.total_Sq(intra, inter, gr2sq=ep.gr2sq_matrix(d["qValues"], d["shellCenters"]), scale_factor=sf,
+                       reduced=(d["kind"] == "RSQ"), **common)
+
+
+@pytest.fixture
+def spill_oracle(orc):
+    orc.set_emulate_spill(True)
+    yield orc
+    orc.set_emulate_spill(False)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_restatement_reproduces_reference_classes(name, golden_dir, spill_oracle):
+    orc = spill_oracle
+    g = _load(golden_dir, name)
+    elements, n_per = _system(g)
+    volume, rho0 = F32(g["volume"]), F32(g["numberDensity"])
+    box = g["boxCoords"].copy()
+    basis, pbc, mol, el = g["basis"], bool(g["isPBC"]), g["moleculeIndex"], g["elementIndex"]
+    nc = int(g["n_constraints"])
+    descs = [_constraint_desc(g, ci) for ci in range(nc)]
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    data = []
+    for ci, d in enumerate(descs):
+        hi, he = orc.full_pairs_histograms_coords(boxCoords=box, basis=basis, isPBC=pbc, moleculeIndex=mol, elementIndex=el,
+                                                  numberOfElements=len(elements), minDistance=d["minDistance"],
+                                                  maxDistance=d["maxDistance"], bin=d["bin"], histSize=int(d["histSize"]),
+                                                  ncores=orc.max_threads())
+        assert np.array_equal(hi, d["start_intra"]) and np.array_equal(he, d["start_inter"])
+        tot = _oracle_total(d, hi, he, elements, n_per, volume, rho0)
+        assert np.array_equal(tot, d["start_total"]), "constraint %d total differs from the reference class" % ci
+        chi = ep.standard_error(d["experimental"], tot, d["dataWeights"])
+        assert F32(chi) == F32(g["start_stdErr"][ci])
+        data.append([hi, he])
+    steps = g["steps/idx"].shape[0]
+    for s in range(steps):
+        k = int(g["steps/k"][s])
+        idx = g["steps/idx"][s, :k].astype(np.int32)
+        moved = g["steps/moved"][s, :k]
+        tmp = box.copy(); tmp[idx] = moved
+        staged = []
+        for ci, d in enumerate(descs):
+            args = (basis, pbc, mol, el, len(elements), d["minDistance"], d["maxDistance"], d["bin"], int(d["histSize"]))
+            bi, be = ep.move_delta(fns, idx, box, *args)
+            ai, ae = ep.move_delta(fns, idx, tmp, *args)
+            ni, ne = data[ci][0] - bi + ai, data[ci][1] - be + ae
+            chi = ep.standard_error(d["experimental"], _oracle_total(d, ni, ne, elements, n_per, volume, rho0), d["dataWeights"])
+            assert F32(chi) == F32(g["steps/chi2_after"][s, ci]), "step %d constraint %d" % (s, ci)
+            staged.append([ni, ne])
+        if bool(g["steps/accepted"][s]):
+            data, box = staged, tmp
+    for ci, d in enumerate(descs):
+        assert np.array_equal(data[ci][0], d["final_intra"]) and np.array_equal(data[ci][1], d["final_inter"])
+        assert np.array_equal(_oracle_total(d, data[ci][0], data[ci][1], elements, n_per, volume, rho0), d["final_total"])
+    assert np.array_equal(box, g["final_boxCoords"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_device_constraints_reproduce_reference_classes(name, golden_dir):
+    import fullrmc_b200
+    from fullrmc_b200.constraints import DeviceBackend, make_device_constraint
+    previous = fullrmc_b200.set_edge_spill(True)
+    try:
+        _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint)
+    finally:
+        fullrmc_b200.set_edge_spill(previous)
+
+
+def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
+    g = _load(golden_dir, name)
+    elements, n_per = _system(g)
+    backend = DeviceBackend(g["boxCoords"], g["basis"], bool(g["isPBC"]), g["moleculeIndex"], g["elementIndex"], elements,
+                            n_per, g["volume"], g["numberDensity"])
+    nc = int(g["n_constraints"])
+    cons = []
+    for ci in range(nc):
+        d = _constraint_desc(g, ci)
+        cons.append((d, make_device_constraint(backend, d["kind"], d["experimental"], d["minDistance"], d["maxDistance"], d["bin"],
+                                               int(d["histSize"]), d["shellCenters"], d["shellVolumes"], d["weighting"],
+                                               dataWeights=d["dataWeights"], shapeArray=d["shapeArray"],
+                                               scaleFactor=float(d["scaleFactor"]),
+                                               qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None)))
+    for ci, (d, c) in enumerate(cons):
+        data, err = c.compute_data()
+        assert np.array_equal(data["intra"], d["start_intra"]) and np.array_equal(data["inter"], d["start_inter"])
+        assert np.array_equal(c.get_constraint_total(), d["start_total"])
+        assert F32(err) == F32(g["start_stdErr"][ci])
+    steps = g["steps/idx"].shape[0]
+    for s in range(steps):
+        k = int(g["steps/k"][s])
+        idx = g["steps/idx"][s, :k].astype(np.int32)
+        moved = np.ascontiguousarray(g["steps/moved"][s, :k])
+        for d, c in cons:
+            c.compute_before_move(idx, idx)
+            c.compute_after_move(idx, idx, moved)
+        for ci, (d, c) in enumerate(cons):
+            assert F32(c.afterMoveStandardError) == F32(g["steps/chi2_after"][s, ci]), "step %d constraint %d" % (s, ci)
+        for d, c in cons:
+            (c.accept_move if bool(g["steps/accepted"][s]) else c.reject_move)(idx, idx)
+    for ci, (d, c) in enumerate(cons):
+        data = c.data
+        assert np.array_equal(data["intra"], d["final_intra"]) and np.array_equal(data["inter"], d["final_inter"])
+        assert np.array_equal(c.get_constraint_total(), d["final_total"])
+        assert F32(c.standardError) == F32(d["final_stdErr"])
+    assert np.array_equal(backend.store.get_coords(), g["final_boxCoords"])
+    backend.close()

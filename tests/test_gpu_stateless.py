@@ -185,6 +185,42 @@ def test_edge_bin_overflow_is_counted_like_the_oracle(ph, orc):
     assert np.array_equal(hi, ri) and np.array_equal(he, re_) and ph.LAST_EDGE_OVERFLOW == ov
 
 
+def test_edge_bin_spill_mode_reproduces_the_reference_write(ph, orc, ref_modules):
+    """with set_edge_spill(True) the in-array spill of the reference's unchecked write is reproduced:
+    compared with the oracle in spill mode and, when built, with the compiled reference itself"""
+    import fullrmc_b200
+    rng = np.random.default_rng(8)
+    hs = 37
+    b = np.float32(0.1)
+    rmax = np.float32(np.float32(hs) * b) + np.float32(3e-6)
+    n = 3000
+    box = rng.random((n, 3), dtype=np.float32)
+    basis = np.diag([9.0, 9.0, 9.0]).astype(np.float32)
+    el = np.zeros(n, np.int32); el[n // 2:] = 1        # element 1 only at the high indexes: slabs [0,0],[0,1],[1,1] used, [1,0] empty
+    kw = dict(basis=basis, isPBC=True, moleculeIndex=np.arange(n, dtype=np.int32), elementIndex=el,
+              numberOfElements=2, minDistance=np.float32(0.0), maxDistance=rmax, bin=b, histSize=hs)
+    previous = fullrmc_b200.set_edge_spill(True)
+    orc.set_emulate_spill(True)
+    try:
+        ri, re_, ov = orc.full_pairs_histograms_coords(boxCoords=box, return_overflow=True, **kw)
+        hi, he = ph.full_pairs_histograms_coords(boxCoords=box, **kw)
+        assert ov > 0 and ph.LAST_EDGE_OVERFLOW == ov
+        assert np.array_equal(hi, ri) and np.array_equal(he, re_)
+        idx = np.arange(0, n, 5, dtype=np.int32)
+        ri2, re2, ov2 = orc.multiple_pairs_histograms_coords(indexes=idx, boxCoords=box, return_overflow=True, **kw)
+        hi2, he2 = ph.multiple_pairs_histograms_coords(indexes=idx, boxCoords=box, **kw)
+        assert np.array_equal(hi2, ri2) and np.array_equal(he2, re2) and ph.LAST_EDGE_OVERFLOW == ov2
+    finally:
+        fullrmc_b200.set_edge_spill(previous)
+        orc.set_emulate_spill(False)
+    # the spill lands where the reference itself writes (all spills stay inside the array here:
+    # slab [1,1] pairs would leave it, so only compare when none of its events overflowed)
+    if ref_modules is not None:
+        fi, fe = ref_modules[1].full_pairs_histograms_coords(boxCoords=box, **kw)
+        same = np.array_equal(fe[:1], he[:1]) and np.array_equal(fe[1, 0], he[1, 0])
+        assert same, "in-array spill differs from the compiled reference"
+
+
 def test_empty_and_degenerate_inputs(ph):
     basis = np.eye(3, dtype=np.float32)
     kw = dict(basis=basis, isPBC=True, numberOfElements=2, minDistance=np.float32(0.0), maxDistance=np.float32(1.0),
