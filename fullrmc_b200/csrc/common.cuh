@@ -109,9 +109,12 @@ __device__ __forceinline__ float wrap_fast(float d)
 // components reach the distance.  Saves the copysign.
 __device__ __forceinline__ float wrap_fast_nosign(float d)
 {
-    const float T = __int_as_float(0x3EFFFFFF);
-    float a = fabsf(d);
-    return (a >= T) ? __fsub_rn(a, 1.0f) : a;
+    // FSETP + predicated FADD (2 issue slots; the select form the compiler picks costs 3):
+    // r = (|d| >= T) ? |d| - 1 : d     -- the sign of the unwrapped branch is irrelevant (squared later)
+    float r;
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 a;\n\tabs.f32 a, %1;\n\tsetp.ge.f32 p, a, 0f3EFFFFFF;\n\t"
+        "mov.f32 %0, %1;\n\t@p add.rn.f32 %0, a, 0fBF800000;\n\t}" : "=f"(r) : "f"(d));
+    return r;
 }
 
 // squared real distance between two stored positions, reference operation order:

@@ -134,33 +134,72 @@ struct SpillTarget {
     int slab_ab, slab_ba;
 };
 
-template <int MODE, int R, bool TRI>
+// Per-warp hit queue.  In-range pairs are rare (0.3-3 % of the pairs swept), so binning them where they are
+// found runs sqrt/div/atomic with one or two lanes alive and, inlined per register atom and unroll step, bloats
+// the loop past the instruction cache (ncu: "no instruction" was the top stall).  Instead a hit is pushed as
+// {d2 bits, slot} into a warp-private shared-memory stack with ballot-computed offsets, and the warp bins 32
+// entries at a time with every lane busy.  Integer counts make the order of binning irrelevant.
+static const int QCAP = 32 + 32 * 4;   // < 32 pending + one register-tile row of pushes (R <= 4)
+
+__device__ __forceinline__ void bin_hit(uint2 e, const GridParams &g, unsigned int *__restrict__ sh,
+                                        unsigned long long &ov, const SpillTarget &sp)
+{
+    const int b = bin_index(__uint_as_float(e.x), g);
+    const int slot = (int)e.y;                    // bit 1: inter, bit 0: the J atom comes first in original order
+    if (b < g.hs) {
+        atomicAdd(&sh[slot * g.hs + b], 1u);
+    } else {
+        ++ov;
+        const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+        if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+    }
+}
+
+template <int MODE, int R>
 __device__ __forceinline__ void sweep_subtile(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int cnt,
                                               int jbase, const float (&xi)[R], const float (&yi)[R],
                                               const float (&zi)[R], const uint32_t (&mi)[R], const uint32_t (&oi)[R],
-                                              int p0, bool cross, const Lattice &L, const GridParams &g,
-                                              unsigned int *__restrict__ sh, unsigned long long &ov, const SpillTarget &sp)
+                                              int p0, bool tri, bool cross, const Lattice &L, const GridParams &g,
+                                              uint2 *__restrict__ wq, int &qn, unsigned int *__restrict__ sh,
+                                              unsigned long long &ov, const SpillTarget &sp)
 {
-#pragma unroll 4
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 2
     for (int q = 0; q < cnt; ++q) {
         const float4 a = sJ[q];
+        // all R distances first, ONE warp-uniform branch for the (rare) in-range work of the register tile
+        float d2[R];
+        bool hit[R];
+        bool any = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            float d2 = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
-            if (in_range(d2, g)) {
-                if (!TRI || (p0 + r * SEG_PAD < jbase + q)) {
-                    int b = bin_index(d2, g);
-                    uint32_t mj = __float_as_uint(a.w);
-                    int same = ((mi[r] >> 8) == (mj >> 8)) ? 0 : 2;          // slots 0,1 intra; 2,3 inter
-                    int ord = (cross && (oi[r] > sO[q])) ? 1 : 0;            // 1: the J atom comes first in original order
-                    if (b < g.hs) {
-                        atomicAdd(&sh[(same + ord) * g.hs + b], 1u);
-                    } else {
-                        ++ov;
-                        const long long flat = (long long)(ord ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-                        if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[(same ? sp.cells : 0) + flat], 1ull);
+            d2[r] = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
+            hit[r] = in_range(d2[r], g);
+            any |= hit[r];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+            const uint32_t mj = __float_as_uint(a.w);
+            const uint32_t oj = sO[q];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool h = hit[r] && (!tri || (p0 + r * SEG_PAD < jbase + q));
+                const unsigned bal = __ballot_sync(0xffffffffu, h);
+                if (bal) {
+                    if (h) {
+                        const uint32_t slot = (((mi[r] >> 8) == (mj >> 8)) ? 0u : 2u) | ((cross && (oi[r] > oj)) ? 1u : 0u);
+                        wq[qn + __popc(bal & lt)] = make_uint2(__float_as_uint(d2[r]), slot);
                     }
+                    qn += __popc(bal);
                 }
+            }
+            if (qn >= 32) {
+                __syncwarp();
+                do {
+                    qn -= 32;
+                    bin_hit(wq[qn + lane], g, sh, ov, sp);
+                } while (qn >= 32);
+                __syncwarp();
             }
         }
     }
@@ -177,7 +216,9 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sJ = reinterpret_cast<float4 *>(smem_raw);
     uint32_t *sO = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * JS);
-    unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS);
+    uint2 *wq = reinterpret_cast<uint2 *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS) + (threadIdx.x >> 5) * QCAP;
+    unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS +
+                                                        sizeof(uint2) * QCAP * (256 / 32));
     __shared__ int s_item;
 
     const int tid = threadIdx.x;
@@ -209,6 +250,7 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         }
         const bool cross = (w.ea != w.eb);
         const int p0 = w.i0 + tid;
+        int qn = 0;                          // entries in this warp's hit queue (warp-uniform)
         SpillTarget sp;
         sp.counts = counts; sp.cells = cells; sp.slab_ab = w.ea * nEl + w.eb; sp.slab_ba = w.eb * nEl + w.ea;
 
@@ -217,11 +259,13 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
             __syncthreads();                  // previous sub-tile fully consumed
             for (int q = tid; q < cnt; q += 256) { sJ[q] = atoms[js + q]; sO[q] = orig[js + q]; }
             __syncthreads();
-            if (w.tri && js < w.i0 + w.ni * SEG_PAD)
-                sweep_subtile<MODE, R, true>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov, sp);
-            else
-                sweep_subtile<MODE, R, false>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, cross, L, g, sh, ov, sp);
+            const bool tri = w.tri && js < w.i0 + w.ni * SEG_PAD;
+            sweep_subtile<MODE, R>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, tri, cross, L, g, wq, qn, sh, ov, sp);
         }
+        // bin what is left in this warp's queue (< 32 entries) before the item's counters are flushed
+        __syncwarp();
+        if ((tid & 31) < qn) bin_hit(wq[tid & 31], g, sh, ov, sp);
+        qn = 0;
         __syncthreads();
         // flush the CTA-private counters of this item into the ordered global histogram
         const int slab_ab = w.ea * nEl + w.eb, slab_ba = w.eb * nEl + w.ea;
@@ -248,7 +292,10 @@ __global__ void counts64_to_float_kernel(const unsigned long long *__restrict__ 
     if (c < cells2) out[c] = (float)(long long)counts[c];
 }
 
-size_t full_hist_smem_bytes(int hs) { return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(unsigned int) * 4 * (size_t)hs; }
+size_t full_hist_smem_bytes(int hs)
+{
+    return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(uint2) * QCAP * (256 / 32) + sizeof(unsigned int) * 4 * (size_t)hs;
+}
 
 template <int MODE, int R>
 static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms, const uint32_t *orig,
