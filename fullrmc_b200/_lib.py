@@ -50,6 +50,7 @@ SIGNATURES = {
     "frmc_version": (ctypes.c_char_p, []),
     "frmc_device_count": (_I, []),
     "frmc_set_edge_spill": (_I, [_I]),
+    "frmc_set_block_culling": (_I, [_I]),
     "frmc_launch_count": (ctypes.c_uint64, []),
     "frmc_points_to_coords": (_I, [_I, c_f32p, c_i32p, c_i64p, _I64, c_f32p, _I64, c_f32p, _I, _I, _I, c_f32p]),
     "frmc_from_to_points_differences": (_I, [_I, c_f32p, c_f32p, _I64, c_f32p, _I, c_f32p]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "frmc_export_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_export_total": (_I, [_VP, _I, _I, c_f32p]),
     "frmc_store_edge_overflow": (ctypes.c_uint64, [_VP]),
+    "frmc_store_swept_pairs": (ctypes.c_uint64, [_VP]),
     "frmc_store_debug_stamps": (_I, [_VP, c_i64p, _I]),
     "frmc_store_set_timing": (_I, [_VP, _I]),
     "frmc_store_get_timing": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double), c_u64p]),
@@ -139,6 +141,11 @@ def set_edge_spill(on):
     False (default) drops pairs whose fp32 bin index rounds up to histSize, True reproduces the
     reference's in-array spill of that unchecked write.  Returns the previous setting."""
     return bool(load_library().frmc_set_edge_spill(int(bool(on))))
+
+
+def set_block_culling(on):
+    """Full-histogram block culling (default on; results are identical either way).  Returns the previous setting."""
+    return bool(load_library().frmc_set_block_culling(int(bool(on))))
 
 
 def device_index():

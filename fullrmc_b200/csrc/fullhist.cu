@@ -10,18 +10,76 @@
 #include "layout.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
+int g_no_cull = 0;   // debug: sweep every block pair (frmc_set_block_culling)
 
 // ------------------------------------------------------------------ host: layout + work list
-int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, HostLayout &out)
+// k-d ordering of one element's atoms: split the longest box axis at a record count that is a multiple
+// of the unit (1024 = one register-tiled I-tile, then 256 = one block, then 32), so that every aligned
+// group of 1024 / 256 / 32 consecutive records is a compact box -- about 2x fewer surviving block pairs
+// than a Morton curve, whose 256-record runs are elongated.  nth_element on 16-byte points; the first
+// levels fork threads (the stateless entry point pays this on every call).
+struct KdPoint { float f[3]; uint32_t idx; };
+
+// run fn(begin, end, part) over [0, n) in up to `parts` contiguous slices, one thread each
+template <typename F>
+static void parallel_slices(int64_t n, int parts, F fn)
+{
+    if (parts < 1) parts = 1;
+    if (n < 65536 || parts == 1) { fn((int64_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    const int64_t step = (n + parts - 1) / parts;
+    int part = 0;
+    for (int64_t a = 0; a < n; a += step, ++part) th.emplace_back(fn, a, std::min(n, a + step), part);
+    for (auto &t : th) t.join();
+}
+
+static void kd_order(KdPoint *a, size_t len, const float *lo, const float *hi, int fork_levels)
+{
+    size_t unit;
+    if (len > 1024) unit = 1024; else if (len > 256) unit = 256; else if (len > 32) unit = 32; else return;
+    const size_t nb = (len + unit - 1) / unit;
+    const size_t k = (nb / 2) * unit;
+    int ax = 0;
+    if (hi[1] - lo[1] > hi[ax] - lo[ax]) ax = 1;
+    if (hi[2] - lo[2] > hi[ax] - lo[ax]) ax = 2;
+    if (ax == 0) std::nth_element(a, a + k, a + len, [](const KdPoint &x, const KdPoint &y) { return x.f[0] < y.f[0]; });
+    else if (ax == 1) std::nth_element(a, a + k, a + len, [](const KdPoint &x, const KdPoint &y) { return x.f[1] < y.f[1]; });
+    else std::nth_element(a, a + k, a + len, [](const KdPoint &x, const KdPoint &y) { return x.f[2] < y.f[2]; });
+    const float cut = a[k].f[ax];
+    float lhi[3] = {hi[0], hi[1], hi[2]}, rlo[3] = {lo[0], lo[1], lo[2]};
+    lhi[ax] = cut; rlo[ax] = cut;
+    if (fork_levels > 0 && len > 16384) {
+        std::thread t(kd_order, a, k, lo, lhi, fork_levels - 1);
+        kd_order(a + k, len - k, rlo, hi, fork_levels - 1);
+        t.join();
+    } else {
+        kd_order(a, k, lo, lhi, 0);
+        kd_order(a + k, len - k, rlo, hi, 0);
+    }
+}
+
+int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC, HostLayout &out)
 {
     FRMC_REQUIRE(n >= 0 && n < (1ll << 31) - 4096, FRMC_ELIMIT, "atom count %lld outside 0..2^31", (long long)n);
     FRMC_REQUIRE(nEl >= 1 && nEl <= FRMC_MAX_ELEMENTS, FRMC_ELIMIT, "numberOfElements %d outside 1..%d", nEl, FRMC_MAX_ELEMENTS);
+    const bool timing = getenv("FRMC_LAYOUT_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[layout] %-10s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     out.n = n; out.nEl = nEl;
     out.seg_count.assign(nEl, 0);
     out.seg_start.assign(nEl + 1, 0);
@@ -52,36 +110,107 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
             rank[i] = (int32_t)(std::lower_bound(keys.begin(), keys.end(), mol[i]) - keys.begin());
     }
 
-    out.rec.assign((size_t)out.npad * 4, 0.f);
-    out.orig.assign((size_t)out.npad, 0xFFFFFFFFu);
-    out.inv.assign((size_t)n, 0);
+    lap("count+mol");
+    out.rec.resize((size_t)out.npad * 4);
+    out.orig.resize((size_t)out.npad);
+    out.inv.resize((size_t)n);
     const float qnan = __builtin_nanf("");
     uint32_t padmeta = PAD_META;
     float padmeta_f;
     memcpy(&padmeta_f, &padmeta, 4);
-    for (int64_t p = 0; p < out.npad; ++p) {
-        out.rec[4 * p + 0] = qnan; out.rec[4 * p + 1] = qnan; out.rec[4 * p + 2] = qnan; out.rec[4 * p + 3] = padmeta_f;
-    }
-    std::vector<int64_t> cursor(out.seg_start.begin(), out.seg_start.end() - 1);
-    for (int c = 0; c < 3; ++c) { out.lo[c] = INFINITY; out.hi[c] = -INFINITY; }
-    out.finite = true;
-    for (int64_t i = 0; i < n; ++i) {
-        int64_t p = cursor[el[i]]++;
-        uint32_t m = (uint32_t)(direct ? mol[i] : rank[i]);
-        uint32_t meta = (m << 8) | (uint32_t)el[i];
-        float mf;
-        memcpy(&mf, &meta, 4);
-        for (int c = 0; c < 3; ++c) {
-            float v = coords[3 * i + c];
-            out.rec[4 * p + c] = v;
-            if (!(v == v) || isinf(v)) out.finite = false;
-            if (v < out.lo[c]) out.lo[c] = v;
-            if (v > out.hi[c]) out.hi[c] = v;
+    for (int e = 0; e < nEl; ++e)                         // only the padding records need the NaN fill
+        for (int64_t p = out.seg_start[e] + out.seg_count[e]; p < out.seg_start[e + 1]; ++p) {
+            out.rec[4 * p + 0] = qnan; out.rec[4 * p + 1] = qnan; out.rec[4 * p + 2] = qnan; out.rec[4 * p + 3] = padmeta_f;
+            out.orig[p] = 0xFFFFFFFFu;
         }
-        out.rec[4 * p + 3] = mf;
-        out.orig[p] = (uint32_t)i;
-        out.inv[i] = (int32_t)p;
+    const int hw = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    {
+        std::vector<float> plo((size_t)hw * 3, INFINITY), phi((size_t)hw * 3, -INFINITY);
+        std::vector<int> pfin((size_t)hw, 1);
+        parallel_slices(n, hw, [&](int64_t a, int64_t b, int part) {
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            int fin = 1;
+            for (int64_t i = a; i < b; ++i)
+                for (int c = 0; c < 3; ++c) {
+                    const float v = coords[3 * i + c];
+                    if (!(v == v) || isinf(v)) { fin = 0; continue; }
+                    if (v < lo[c]) lo[c] = v;
+                    if (v > hi[c]) hi[c] = v;
+                }
+            for (int c = 0; c < 3; ++c) { plo[(size_t)part * 3 + c] = lo[c]; phi[(size_t)part * 3 + c] = hi[c]; }
+            pfin[(size_t)part] = fin;
+        });
+        out.finite = true;
+        for (int c = 0; c < 3; ++c) { out.lo[c] = INFINITY; out.hi[c] = -INFINITY; }
+        for (int t = 0; t < hw; ++t) {
+            for (int c = 0; c < 3; ++c) {
+                out.lo[c] = std::min(out.lo[c], plo[(size_t)t * 3 + c]);
+                out.hi[c] = std::max(out.hi[c], phi[(size_t)t * 3 + c]);
+            }
+            if (!pfin[(size_t)t]) out.finite = false;
+        }
     }
+
+    lap("alloc+bounds");
+    // gather each element's atoms (original order), then k-d order them on the periodically reduced
+    // coordinates (a block must not straddle the seam because of integer offsets)
+    std::vector<KdPoint> pts((size_t)n);
+    {
+        std::vector<int64_t> cursor((size_t)nEl, 0);
+        int64_t at = 0;
+        for (int e = 0; e < nEl; ++e) { cursor[e] = at; at += out.seg_count[e]; }
+        for (int64_t i = 0; i < n; ++i) {
+            KdPoint &q = pts[(size_t)cursor[el[i]]++];
+            for (int c = 0; c < 3; ++c) {
+                const float v = coords[3 * i + c];
+                q.f[c] = ((v == v) && !isinf(v)) ? (isPBC ? (v - floorf(v)) : v) : 0.f;
+            }
+            q.idx = (uint32_t)i;
+        }
+    }
+    lap("gather");
+    {
+        // fork while a half still has > 16k points: short-lived threads, a few per core at most
+        const int fork_levels = (hw > 1) ? 6 : 0;
+        std::vector<std::thread> workers;
+        int64_t at = 0;
+        float blo[3], bhi[3];
+        for (int c = 0; c < 3; ++c) {
+            blo[c] = isPBC ? 0.f : out.lo[c];
+            bhi[c] = isPBC ? 1.f : out.hi[c];
+        }
+        for (int e = 0; e < nEl; ++e) {
+            KdPoint *base = pts.data() + at;
+            const size_t len = (size_t)out.seg_count[e];
+            at += out.seg_count[e];
+            if (len <= 32) continue;
+            if (n > 65536 && hw > 1) workers.emplace_back(kd_order, base, len, blo, bhi, fork_levels);
+            else kd_order(base, len, blo, bhi, 0);
+        }
+        for (auto &t : workers) t.join();
+    }
+    lap("kd");
+    {
+        // pts is element-major; record position = padded segment start + rank inside the element
+        std::vector<int64_t> shift((size_t)nEl, 0);      // position - index into pts
+        int64_t at = 0;
+        for (int e = 0; e < nEl; ++e) { shift[e] = out.seg_start[e] - at; at += out.seg_count[e]; }
+        parallel_slices(n, hw, [&](int64_t a, int64_t b, int) {
+            for (int64_t k = a; k < b; ++k) {
+                const int64_t i = pts[(size_t)k].idx;
+                const int64_t p = k + shift[el[i]];
+                uint32_t m = (uint32_t)(direct ? mol[i] : rank[i]);
+                uint32_t meta = (m << 8) | (uint32_t)el[i];
+                float mf;
+                memcpy(&mf, &meta, 4);
+                for (int c = 0; c < 3; ++c) out.rec[4 * p + c] = coords[3 * i + c];
+                out.rec[4 * p + 3] = mf;
+                out.orig[p] = (uint32_t)i;
+                out.inv[i] = (int32_t)p;
+            }
+        });
+    }
+    lap("scatter");
     if (n == 0) for (int c = 0; c < 3; ++c) { out.lo[c] = 0.f; out.hi[c] = 0.f; }
     if (!out.finite) out.hi[0] = INFINITY;   // forces the general wrap
     return FRMC_OK;
@@ -96,12 +225,12 @@ void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, i
         if (lay.seg_count[ea] == 0) continue;
         const int64_t a0 = lay.seg_start[ea];
         const int64_t a1 = a0 + (lay.seg_count[ea] + SEG_PAD - 1) / SEG_PAD * SEG_PAD;
-        for (int64_t i0 = a0; i0 < a1; i0 += TI) {
-            const int64_t i1 = std::min(i0 + TI, a1);
-            for (int eb = ea; eb < lay.nEl; ++eb) {
-                if (lay.seg_count[eb] == 0) continue;
-                const int64_t b0 = lay.seg_start[eb];
-                const int64_t b1 = b0 + (lay.seg_count[eb] + SEG_PAD - 1) / SEG_PAD * SEG_PAD;
+        for (int eb = ea; eb < lay.nEl; ++eb) {
+            if (lay.seg_count[eb] == 0) continue;
+            const int64_t b0 = lay.seg_start[eb];
+            const int64_t b1 = b0 + (lay.seg_count[eb] + SEG_PAD - 1) / SEG_PAD * SEG_PAD;
+            for (int64_t i0 = a0; i0 < a1; i0 += TI) {
+                const int64_t i1 = std::min(i0 + TI, a1);
                 for (int64_t c0 = b0; c0 < b1; c0 += chunkJ) {
                     const int64_t j1 = std::min(c0 + chunkJ, b1);
                     int64_t j0 = c0;
@@ -134,106 +263,257 @@ struct SpillTarget {
     int slab_ab, slab_ba;
 };
 
-// Per-warp hit queue.  In-range pairs are rare (0.3-3 % of the pairs swept), so binning them where they are
-// found runs sqrt/div/atomic with one or two lanes alive and, inlined per register atom and unroll step, bloats
-// the loop past the instruction cache (ncu: "no instruction" was the top stall).  Instead a hit is pushed as
-// {d2 bits, slot} into a warp-private shared-memory stack with ballot-computed offsets, and the warp bins 32
-// entries at a time with every lane busy.  Integer counts make the order of binning irrelevant.
-static const int QCAP = 32 + 32 * 4;   // < 32 pending + one register-tile row of pushes (R <= 4)
+// Lane-private hit queues.  In-range pairs are 0.3 % (plain sweep of a sparse box) to 50 % (maxDistance
+// near half the box) of the pairs swept.  Binning a pair where it is found runs sqrt/div/atomic with a lane
+// or two alive and, inlined per register atom and unroll step, bloats the loop past the instruction cache
+// (ncu: "no instruction" was the top stall).  So the sweep only RECORDS a hit -- a predicated 4-byte store of
+// (q << 2 | r) into the lane's own column of a shared-memory array, no branch, no vote -- and the lanes bin
+// their columns together when one of them is nearly full or the staged block ends.  The bin pass recomputes
+// d2 from the same operands with the same instruction sequence, so it sees the identical value; integer
+// counts make the order of binning irrelevant.
+static const int LQ_CAP = 16;          // entries per lane; [slot][thread] layout: a lane always hits its own bank
 
-__device__ __forceinline__ void bin_hit(uint2 e, const GridParams &g, unsigned int *__restrict__ sh,
-                                        unsigned long long &ov, const SpillTarget &sp)
+template <int MODE, int R>
+__device__ __forceinline__ void bin_lane_queue(const uint32_t *__restrict__ lq, int n, const float4 *__restrict__ sJ,
+                                               const uint32_t *__restrict__ sO, int jbase, const float (&xi)[R],
+                                               const float (&yi)[R], const float (&zi)[R], const uint32_t (&mi)[R],
+                                               const uint32_t (&oi)[R], int p0, bool tri, bool cross, const Lattice &L,
+                                               const GridParams &g, unsigned int *__restrict__ sh,
+                                               unsigned long long &ov, const SpillTarget &sp)
 {
-    const int b = bin_index(__uint_as_float(e.x), g);
-    const int slot = (int)e.y;                    // bit 1: inter, bit 0: the J atom comes first in original order
-    if (b < g.hs) {
-        atomicAdd(&sh[slot * g.hs + b], 1u);
-    } else {
-        ++ov;
-        const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-        if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+    for (int k = 0; k < n; ++k) {
+        const uint32_t e = lq[k * 256];
+        const int q = (int)(e >> 2), r = (int)(e & 3u);
+        float x = xi[0], y = yi[0], z = zi[0];
+        uint32_t m = mi[0], o = oi[0];
+#pragma unroll
+        for (int rr = 1; rr < R; ++rr)
+            if (r == rr) { x = xi[rr]; y = yi[rr]; z = zi[rr]; m = mi[rr]; o = oi[rr]; }
+        if (tri && !(p0 + r * SEG_PAD < jbase + q)) continue;      // diagonal tile: only p < q counts
+        const float4 a = sJ[q];
+        const float d2 = dist2<MODE>(x, y, z, a.x, a.y, a.z, L);
+        const int b = bin_index(d2, g);
+        const uint32_t mj = __float_as_uint(a.w);
+        // slot bit 1: inter-molecular, bit 0: the J atom comes first in original order
+        const int slot = (((m >> 8) == (mj >> 8)) ? 0 : 2) | ((cross && (o > sO[q])) ? 1 : 0);
+        if (b < g.hs) {
+            atomicAdd(&sh[slot * g.hs + b], 1u);
+        } else {
+            ++ov;
+            const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+            if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+        }
     }
 }
 
+// one staged block of SEG_PAD J records against the thread's R register atoms
 template <int MODE, int R>
-__device__ __forceinline__ void sweep_subtile(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int cnt,
-                                              int jbase, const float (&xi)[R], const float (&yi)[R],
-                                              const float (&zi)[R], const uint32_t (&mi)[R], const uint32_t (&oi)[R],
-                                              int p0, bool tri, bool cross, const Lattice &L, const GridParams &g,
-                                              uint2 *__restrict__ wq, int &qn, unsigned int *__restrict__ sh,
-                                              unsigned long long &ov, const SpillTarget &sp)
+__device__ __forceinline__ void sweep_block(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int jbase,
+                                            const float (&xi)[R], const float (&yi)[R], const float (&zi)[R],
+                                            const uint32_t (&mi)[R], const uint32_t (&oi)[R], int p0, bool tri, bool cross,
+                                            const Lattice &L, const GridParams &g, unsigned submask,
+                                            uint32_t *__restrict__ lq, unsigned int *__restrict__ sh,
+                                            unsigned long long &ov, const SpillTarget &sp)
 {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 2
-    for (int q = 0; q < cnt; ++q) {
-        const float4 a = sJ[q];
-        // all R distances first, ONE warp-uniform branch for the (rare) in-range work of the register tile
-        float d2[R];
-        bool hit[R];
-        bool any = false;
+    // 32-bit shared-window addresses: the push is STS + IADD under the hit predicate
+    const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(lq);
+    const uint32_t wfull = w0 + (LQ_CAP - 2 * R) * 1024u;
+    uint32_t wp = w0;                            // next free slot of this lane's queue (stride 256 words)
+#pragma unroll 1
+    for (int q = 0; q < SEG_PAD; q += 2) {
+        // 32-record sub-blocks whose box is out of reach of every I block are stepped over (CTA-uniform)
+        if (!((submask >> (q >> 5)) & 1u)) { q += 30; continue; }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            d2[r] = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
-            hit[r] = in_range(d2[r], g);
-            any |= hit[r];
-        }
-        if (__any_sync(0xffffffffu, any)) {
-            const uint32_t mj = __float_as_uint(a.w);
-            const uint32_t oj = sO[q];
+        for (int u = 0; u < 2; ++u) {
+            const float4 a = sJ[q + u];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const bool h = hit[r] && (!tri || (p0 + r * SEG_PAD < jbase + q));
-                const unsigned bal = __ballot_sync(0xffffffffu, h);
-                if (bal) {
-                    if (h) {
-                        const uint32_t slot = (((mi[r] >> 8) == (mj >> 8)) ? 0u : 2u) | ((cross && (oi[r] > oj)) ? 1u : 0u);
-                        wq[qn + __popc(bal & lt)] = make_uint2(__float_as_uint(d2[r]), slot);
-                    }
-                    qn += __popc(bal);
+                const float d2 = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
+                if (in_range(d2, g)) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"((uint32_t)(((q + u) << 2) | r)) : "memory");
+                    wp += 1024u;
                 }
             }
-            if (qn >= 32) {
-                __syncwarp();
-                do {
-                    qn -= 32;
-                    bin_hit(wq[qn + lane], g, sh, ov, sp);
-                } while (qn >= 32);
-                __syncwarp();
-            }
+        }
+        if (__any_sync(0xffffffffu, wp > wfull)) {
+            bin_lane_queue<MODE, R>(lq, (int)((wp - w0) >> 10), sJ, sO, jbase, xi, yi, zi, mi, oi, p0, tri, cross, L, g, sh, ov, sp);
+            wp = w0;
+            __syncwarp();
         }
     }
+    bin_lane_queue<MODE, R>(lq, (int)((wp - w0) >> 10), sJ, sO, jbase, xi, yi, zi, mi, oi, p0, tri, cross, L, g, sh, ov, sp);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ block bounding boxes + culling
+// One record pair per SEG_PAD block, then one per 32-record sub-block: {lo.xyz, eps} {hi.xyz, empty}
+// (18 float4 per block in all).  Under PBC the coordinates are first
+// reduced to their fractional part (exact in fp32), so a block never straddles the periodic seam just
+// because its atoms carry different integer offsets.  eps bounds the rounding of fl(xi - xj) on the raw
+// coordinates.  Atoms with a non-finite component pair with nothing (their d2 is NaN/inf) and are left out.
+__global__ void block_bbox_kernel(const float4 *__restrict__ atoms, int nblocks, int pbc, float4 *__restrict__ bbox)
+{
+    const int blk = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (blk >= nblocks) return;
+    float4 *__restrict__ sbox = bbox + 2 * (size_t)nblocks;      // 8 sub-blocks of 32 records per block
+    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY}, bmax = 0.f;
+    for (int sb = 0; sb < SEG_PAD / 32; ++sb) {
+        const float4 a = atoms[(size_t)blk * SEG_PAD + sb * 32 + lane];
+        const float v[3] = {a.x, a.y, a.z};
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, amax = 0.f;
+        if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                amax = fmaxf(amax, fabsf(v[c]));
+                const float f = pbc ? (v[c] - floorf(v[c])) : v[c];
+                lo[c] = f; hi[c] = f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        if (lane == 0) {
+            const size_t at = 2 * ((size_t)blk * (SEG_PAD / 32) + sb);
+            sbox[at + 0] = make_float4(lo[0], lo[1], lo[2], 1e-6f * (1.0f + amax));
+            sbox[at + 1] = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? 0.f : 1.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { blo[c] = fminf(blo[c], lo[c]); bhi[c] = fmaxf(bhi[c], hi[c]); }
+        bmax = fmaxf(bmax, amax);
+    }
+    if (lane == 0) {
+        bbox[2 * blk + 0] = make_float4(blo[0], blo[1], blo[2], 1e-6f * (1.0f + bmax));
+        bbox[2 * blk + 1] = make_float4(bhi[0], bhi[1], bhi[2], (blo[0] <= bhi[0]) ? 0.f : 1.f);
+    }
+}
+
+// Lower bound on the reference's computed distance between any atom of block I and any atom of block J.
+// Per axis the (periodic) separation of two points is at least |wrap(centre difference)| - half widths;
+// the reference's per-axis round() wrap yields exactly that periodic separation.  Diagonal basis / no PBC:
+// the axis bounds combine Euclidean-wise (h = |L_cc| or 1).  General basis: |r| >= |f_c| / |column c of
+// B^-1| for every axis, so the largest single-axis bound is used (h_c = that reciprocal height).
+// Everything errs on the near side: eps margins on the gaps, 1e-4 relative slack on the cut.
+struct CullParams {
+    float h[3];
+    float t2cut;
+    int pbc, euclid, enabled, pad;
+};
+
+__device__ __forceinline__ bool blocks_far(const float4 loI, const float4 hiI, const float4 loJ, const float4 hiJ,
+                                           const CullParams &cp)
+{
+    if (hiI.w != 0.f || hiJ.w != 0.f) return true;          // no finite atom on one side: nothing can be in range
+    const float eps = loI.w + loJ.w;
+    const float li[3] = {loI.x, loI.y, loI.z}, ui[3] = {hiI.x, hiI.y, hiI.z};
+    const float lj[3] = {loJ.x, loJ.y, loJ.z}, uj[3] = {hiJ.x, hiJ.y, hiJ.z};
+    float s = 0.f, m = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float half = 0.5f * ((ui[c] - li[c]) + (uj[c] - lj[c]));
+        float d = 0.5f * ((lj[c] + uj[c]) - (li[c] + ui[c]));
+        if (cp.pbc) d -= rintf(d);
+        const float gap = fmaxf(fabsf(d) - half - eps, 0.f) * cp.h[c];
+        s += gap * gap;
+        m = fmaxf(m, gap * gap);
+    }
+    return (cp.euclid ? s : m) > cp.t2cut;
+}
+
+CullParams make_cull(const Lattice &L, int mode, const GridParams &g)
+{
+    CullParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.t2cut = g.t2max * 1.0001f;
+    cp.enabled = std::isfinite(cp.t2cut) ? 1 : 0;
+    cp.pbc = (mode != MODE_IBC);
+    if (mode == MODE_IBC) {
+        cp.euclid = 1; cp.h[0] = cp.h[1] = cp.h[2] = 1.0f;
+    } else if (mode == MODE_ORTHO_FAST || mode == MODE_ORTHO_GEN) {
+        cp.euclid = 1;
+        cp.h[0] = fabsf(L.b[0]); cp.h[1] = fabsf(L.b[4]); cp.h[2] = fabsf(L.b[8]);
+    } else {
+        // heights of the cell: 1 / |column c of B^-1|, B rows = lattice vectors
+        const double a[9] = {L.b[0], L.b[1], L.b[2], L.b[3], L.b[4], L.b[5], L.b[6], L.b[7], L.b[8]};
+        const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        if (!(fabs(det) > 0.0) || !std::isfinite(det)) { cp.enabled = 0; return cp; }
+        double inv[9];
+        inv[0] = (a[4] * a[8] - a[5] * a[7]) / det; inv[1] = (a[2] * a[7] - a[1] * a[8]) / det; inv[2] = (a[1] * a[5] - a[2] * a[4]) / det;
+        inv[3] = (a[5] * a[6] - a[3] * a[8]) / det; inv[4] = (a[0] * a[8] - a[2] * a[6]) / det; inv[5] = (a[2] * a[3] - a[0] * a[5]) / det;
+        inv[6] = (a[3] * a[7] - a[4] * a[6]) / det; inv[7] = (a[1] * a[6] - a[0] * a[7]) / det; inv[8] = (a[0] * a[4] - a[1] * a[3]) / det;
+        cp.euclid = 0;
+        for (int c = 0; c < 3; ++c) {
+            const double col = sqrt(inv[c] * inv[c] + inv[3 + c] * inv[3 + c] + inv[6 + c] * inv[6 + c]);
+            if (!(col > 0.0) || !std::isfinite(col)) { cp.enabled = 0; return cp; }
+            cp.h[c] = (float)((1.0 / col) * (1.0 - 1e-5));
+        }
+    }
+    for (int c = 0; c < 3; ++c) if (!std::isfinite(cp.h[c])) cp.enabled = 0;
+    return cp;
 }
 
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
+// stats[0] += edge overflow events, stats[1] += (SEG_PAD I records x 32 J records) units actually swept.
 template <int MODE, int R>
-__global__ void __launch_bounds__(256)
-full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig,
+__global__ void __launch_bounds__(256, 4)
+full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const float4 *__restrict__ bbox,
                  const WorkItem *__restrict__ items, int n_items, int *__restrict__ next_item, Lattice L,
-                 GridParams g, int nEl, unsigned long long *__restrict__ counts,
-                 unsigned long long *__restrict__ overflow)
+                 GridParams g, CullParams cp, int nblocks, int nEl, unsigned long long *__restrict__ counts,
+                 unsigned long long *__restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sJ = reinterpret_cast<float4 *>(smem_raw);
     uint32_t *sO = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * JS);
-    uint2 *wq = reinterpret_cast<uint2 *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS) + (threadIdx.x >> 5) * QCAP;
+    uint32_t *lq = reinterpret_cast<uint32_t *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS) + threadIdx.x;
     unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS +
-                                                        sizeof(uint2) * QCAP * (256 / 32));
+                                                        sizeof(uint32_t) * LQ_CAP * 256);
     __shared__ int s_item;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = threadIdx.x & 31;
     const int nsh = 4 * g.hs;
     for (int c = tid; c < nsh; c += 256) sh[c] = 0u;
-    unsigned long long ov = 0;
+    unsigned long long ov = 0, swept = 0;
     const long long cells = (long long)nEl * nEl * g.hs;
+    int cur_slab = -1;                        // element pair the shared counters currently hold
+    unsigned int since_flush = 0;             // block pairs swept into the counters since the last flush
+    SpillTarget sp;
+    sp.counts = counts; sp.cells = cells; sp.slab_ab = 0; sp.slab_ba = 0;
 
     while (true) {
-        __syncthreads();                      // previous item's flush done, s_item consumed
+        __syncthreads();                      // s_item consumed, previous item's sweeps done
         if (tid == 0) s_item = atomicAdd(next_item, 1);
         __syncthreads();
         const int it = s_item;
+        WorkItem w;
+        w.ea = -1; w.eb = -1;
+        if (it < n_items) w = items[it];
+        const int slab = (it < n_items) ? w.ea * nEl + w.eb : -2;
+        // The counters belong to one element pair at a time; the item list is ordered by pair, so this
+        // flush happens a handful of times per CTA (32-bit counters: also before 2^31 pairs pile up).
+        if (slab != cur_slab || since_flush >= 32768u - 64u) {
+            __syncthreads();                  // every warp has binned its queues (sweep_block ends with that)
+            if (cur_slab >= 0) {
+                for (int c = tid; c < nsh; c += 256) {
+                    const unsigned int v = sh[c];
+                    if (v) {
+                        sh[c] = 0u;
+                        const int slot = c / g.hs, b = c - slot * g.hs;
+                        const long long at = ((slot >> 1) ? cells : 0) + (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+                        atomicAdd(&counts[at], (unsigned long long)v);
+                    }
+                }
+            }
+            cur_slab = slab;
+            since_flush = 0;
+            sp.slab_ab = w.ea * nEl + w.eb; sp.slab_ba = w.eb * nEl + w.ea;
+            __syncthreads();
+        }
         if (it >= n_items) break;
-        const WorkItem w = items[it];
 
         float xi[R], yi[R], zi[R];
         uint32_t mi[R], oi[R];
@@ -250,36 +530,63 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         }
         const bool cross = (w.ea != w.eb);
         const int p0 = w.i0 + tid;
-        int qn = 0;                          // entries in this warp's hit queue (warp-uniform)
-        SpillTarget sp;
-        sp.counts = counts; sp.cells = cells; sp.slab_ab = w.ea * nEl + w.eb; sp.slab_ba = w.eb * nEl + w.ea;
+        const int bi = w.i0 / SEG_PAD;
 
-        for (int js = w.j0; js < w.j1; js += JS) {
-            const int cnt = min(JS, w.j1 - js);
-            __syncthreads();                  // previous sub-tile fully consumed
-            for (int q = tid; q < cnt; q += 256) { sJ[q] = atoms[js + q]; sO[q] = orig[js + q]; }
-            __syncthreads();
-            const bool tri = w.tri && js < w.i0 + w.ni * SEG_PAD;
-            sweep_subtile<MODE, R>(sJ, sO, cnt, js, xi, yi, zi, mi, oi, p0, tri, cross, L, g, wq, qn, sh, ov, sp);
-        }
-        // bin what is left in this warp's queue (< 32 entries) before the item's counters are flushed
-        __syncwarp();
-        if ((tid & 31) < qn) bin_hit(wq[tid & 31], g, sh, ov, sp);
-        qn = 0;
-        __syncthreads();
-        // flush the CTA-private counters of this item into the ordered global histogram
-        const int slab_ab = w.ea * nEl + w.eb, slab_ba = w.eb * nEl + w.ea;
-        for (int c = tid; c < nsh; c += 256) {
-            const unsigned int v = sh[c];
-            if (v) {
-                sh[c] = 0u;
-                const int slot = c / g.hs, b = c - slot * g.hs;
-                const long long at = ((slot >> 1) ? cells : 0) + (long long)((slot & 1) ? slab_ba : slab_ab) * g.hs + b;
-                atomicAdd(&counts[at], (unsigned long long)v);
+        // J blocks of this item, 32 per round: lane l tests block l against the I blocks (every warp
+        // computes the same survivor mask, so the CTA stays in step without exchanging it)
+        for (int jr = w.j0; jr < w.j1; jr += 32 * SEG_PAD) {
+            const int jb = jr + lane * SEG_PAD;
+            bool near = jb < w.j1;
+            if (near && cp.enabled) {
+                const int bj = jb / SEG_PAD;
+                const float4 loJ = bbox[2 * bj], hiJ = bbox[2 * bj + 1];
+                bool far = true;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
+                near = !far;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, near);
+            while (mask) {
+                const int jb0 = jr + (__ffs(mask) - 1) * SEG_PAD;
+                mask &= mask - 1;
+                int nb = 1, jb1 = jb0;
+                if (mask) { jb1 = jr + (__ffs(mask) - 1) * SEG_PAD; mask &= mask - 1; nb = 2; }
+                __syncthreads();              // previous staged blocks fully consumed
+                sJ[tid] = atoms[jb0 + tid]; sO[tid] = orig[jb0 + tid];
+                if (nb == 2) { sJ[SEG_PAD + tid] = atoms[jb1 + tid]; sO[SEG_PAD + tid] = orig[jb1 + tid]; }
+                __syncthreads();
+                // second level: lanes 0-7 / 8-15 test the 32-record sub-blocks of the two staged blocks
+                unsigned sub = 0xFFFFu;
+                if (cp.enabled) {
+                    const int which = lane >> 3, sb = lane & 7;
+                    bool nr = false;
+                    if (which < nb) {
+                        const size_t at = 2 * ((size_t)nblocks + (size_t)((which ? jb1 : jb0) / SEG_PAD) * (SEG_PAD / 32) + sb);
+                        const float4 loJ = bbox[at], hiJ = bbox[at + 1];
+                        bool far = true;
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
+                        nr = !far;
+                    }
+                    sub = __ballot_sync(0xffffffffu, nr);
+                }
+                if (nb == 1) sub &= 0xFFu;
+#pragma unroll 1
+                for (int b = 0; b < nb; ++b) {
+                    const int jbb = b ? jb1 : jb0;
+                    const bool tri = w.tri && jbb < w.i0 + w.ni * SEG_PAD;
+                    sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, mi, oi, p0, tri, cross, L, g,
+                                         (sub >> (8 * b)) & 0xFFu, lq, sh, ov, sp);
+                }
+                since_flush += (unsigned)(nb * w.ni);
+                swept += (unsigned)(__popc(sub & 0xFFFFu) * w.ni);
             }
         }
     }
-    if (ov) atomicAdd(overflow, ov);
+    if (ov) atomicAdd(&stats[0], ov);
+    if (tid == 0 && swept) atomicAdd(&stats[1], swept);
 }
 
 // counts (64-bit, SIGNED: the reference's running ordered arrays data-before+after may hold
@@ -294,13 +601,13 @@ __global__ void counts64_to_float_kernel(const unsigned long long *__restrict__ 
 
 size_t full_hist_smem_bytes(int hs)
 {
-    return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(uint2) * QCAP * (256 / 32) + sizeof(unsigned int) * 4 * (size_t)hs;
+    return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(uint32_t) * LQ_CAP * 256 + sizeof(unsigned int) * 4 * (size_t)hs;
 }
 
 template <int MODE, int R>
-static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms, const uint32_t *orig,
+static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms, const uint32_t *orig, const float4 *bbox,
                          const WorkItem *items, int n_items, int *next_item, const Lattice &L, const GridParams &g,
-                         int nEl, unsigned long long *counts, unsigned long long *overflow)
+                         const CullParams &cp, int nblocks, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
     size_t smem = full_hist_smem_bytes(g.hs);
     FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "histSize %d needs %zu B of shared memory per CTA (limit 200 KiB)", g.hs, smem);
@@ -311,21 +618,29 @@ static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms,
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(n_items, sm_count * per_sm);
     if (grid < 1) return FRMC_OK;
-    kern<<<grid, 256, smem, stream>>>(atoms, orig, items, n_items, next_item, L, g, nEl, counts, overflow);
+    kern<<<grid, 256, smem, stream>>>(atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
     FRMC_LAUNCH_CHECK();
     return FRMC_OK;
 }
 
-// Launch the tiled kernel on prepared device arrays.  next_item must be zeroed by the caller
-// (stream-ordered) before every launch.
+// Launch the block-box pass and the tiled kernel on prepared device arrays.  next_item must be zeroed
+// by the caller (stream-ordered) before every launch; bbox is scratch for 18 float4 per SEG_PAD block;
+// stats[0] accumulates edge-overflow events, stats[1] swept block pairs.
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     const WorkItem *items, int n_items, int *next_item, const Lattice &L, const GridParams &g,
-                     int nEl, unsigned long long *counts, unsigned long long *overflow)
+                     int64_t npad, float4 *bbox, const WorkItem *items, int n_items, int *next_item, const Lattice &L,
+                     const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
+    CullParams cp = make_cull(L, mode, g);
+    if (g_no_cull) cp.enabled = 0;
+    const int nblocks = (int)(npad / SEG_PAD);
+    if (cp.enabled && nblocks > 0) {
+        block_bbox_kernel<<<(nblocks * 32 + 255) / 256, 256, 0, stream>>>(atoms, nblocks, cp.pbc, bbox);
+        FRMC_LAUNCH_CHECK();
+    }
 #define FH_CASE(M)                                                                                         \
     case M:                                                                                                \
-        return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, items, n_items, next_item, L, g, nEl, counts, overflow) \
-                        : launch_full_t<M, 1>(stream, sm_count, atoms, orig, items, n_items, next_item, L, g, nEl, counts, overflow);
+        return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats) \
+                        : launch_full_t<M, 1>(stream, sm_count, atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
     switch (mode) {
         FH_CASE(MODE_IBC)
         FH_CASE(MODE_ORTHO_FAST)
@@ -338,11 +653,35 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const f
     return FRMC_EINVAL;
 }
 
-// Tile-shape heuristic: R register atoms per thread (I-tile = 256*R) and the J-chunk
-// length, chosen so that there are enough work items to balance sm_count x occupancy CTAs.
-void choose_tiling(int64_t npad, int sm_count, int &R, int64_t &chunkJ)
+// Does block culling remove most of the sweep?  Estimated from the reach (maxDistance + one block
+// extent, both ways) against the cell heights / coordinate spans; decides the register tiling below.
+bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g)
 {
-    R = (npad >= 32768) ? 4 : 1;
+    if (g_no_cull || n <= 0) return false;
+    const CullParams cp = make_cull(L, mode, g);
+    if (!cp.enabled) return false;
+    double span[3], vol = 1.0;
+    for (int c = 0; c < 3; ++c) {
+        span[c] = (mode == MODE_IBC) ? (double)hi[c] - (double)lo[c] : (double)cp.h[c];
+        if (!(span[c] > 0.0) || !std::isfinite(span[c])) return false;
+        vol *= span[c];
+    }
+    const double per_el = std::max(1.0, (double)n / std::max(1, nEl));
+    const double extent = cbrt(vol * (double)SEG_PAD / per_el);
+    const double reach = 2.0 * ((double)g.rmax + extent);
+    double frac = 1.0;
+    for (int c = 0; c < 3; ++c) frac *= std::min(1.0, reach / span[c]);
+    return frac < 0.5;
+}
+
+// Tile-shape heuristic: R register atoms per thread (I-tile = 256*R) and the J-chunk length, chosen so
+// that there are enough work items to balance sm_count x occupancy CTAs.  R = 4 amortises the shared-
+// memory load of a J record over four pairs (23.4 issue slots per pair instead of 26) and is right when
+// every block pair has to be swept; when culling bites, R = 1 keeps the culled unit at one 256-atom block
+// (about 2.5x fewer pairs swept than with a 1024-atom I-tile).
+void choose_tiling(int64_t npad, int sm_count, bool sparse, int &R, int64_t &chunkJ)
+{
+    R = (npad >= 32768 && !sparse) ? 4 : 1;
     const double target_items = 16.0 * sm_count * 4;
     double ti = 256.0 * R;
     double cj = (double)npad * (double)npad / (2.0 * ti * target_items);
@@ -367,6 +706,13 @@ using namespace frmc;
 // Host-only inspection of the multi-GPU decomposition (no device needed): number of work items and
 // of atom pairs covered by shard `shard` of `nshards` for a system with the given element indexes.
 // Summed over the shards the pair count is n(n-1)/2; used by the CPU tests of the sharding logic.
+extern "C" int frmc_set_block_culling(int on)
+{
+    int old = !g_no_cull;
+    g_no_cull = on ? 0 : 1;
+    return old;
+}
+
 extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,
                                      int64_t *n_items, int64_t *n_pairs)
 {
@@ -375,10 +721,10 @@ extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int 
     std::vector<float> coords((size_t)n * 3, 0.f);
     std::vector<int32_t> mol((size_t)n, 0);
     HostLayout lay;
-    int rc = build_layout(coords.data(), n, mol.data(), el, nEl, lay);
+    int rc = build_layout(coords.data(), n, mol.data(), el, nEl, 1, lay);
     if (rc) return rc;
     int R; int64_t chunkJ;
-    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, R, chunkJ);
+    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, false, R, chunkJ);
     std::vector<WorkItem> items;
     build_work_items(lay, R, chunkJ, shard, nshards, items);
     auto real_in = [&](int e, int64_t a, int64_t b) -> int64_t {   // real atoms of segment e inside positions [a, b)
@@ -415,33 +761,34 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     DeviceCtx *c = get_ctx(dev);
     if (!c) return FRMC_ECUDA;
     HostLayout lay;
-    int rc = build_layout(coords, n, mol, el, nEl, lay);
+    int rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
     if (rc) return rc;
     Lattice L;
     for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     GridParams g = make_grid(rmin, rmax, bin, hs);
     int mode = choose_mode_from_bounds(L.b, isPBC, lay.lo, lay.hi);
     int R; int64_t chunkJ;
-    choose_tiling(lay.npad, c->sm_count, R, chunkJ);
+    choose_tiling(lay.npad, c->sm_count, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g), R, chunkJ);
     std::vector<WorkItem> items;
     build_work_items(lay, R, chunkJ, shard, nshards, items);
 
     float4 *d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float) * 4 * (size_t)lay.npad);
     uint32_t *d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);
     WorkItem *d_items = (WorkItem *)ctx_buffer(c, 2, sizeof(WorkItem) * items.size());
-    unsigned long long *d_counts = (unsigned long long *)ctx_buffer(c, 4, sizeof(unsigned long long) * (2 * cells + 2));
+    unsigned long long *d_counts = (unsigned long long *)ctx_buffer(c, 4, sizeof(unsigned long long) * (2 * cells + 3));
+    float4 *d_bbox = (float4 *)ctx_buffer(c, 3, sizeof(float4) * 18 * (size_t)(lay.npad / SEG_PAD + 1));
     float *d_out = (float *)ctx_buffer(c, 5, sizeof(float) * 2 * cells);
-    if (!d_atoms || !d_orig || !d_items || !d_counts || !d_out) return FRMC_ENOMEM;
+    if (!d_atoms || !d_orig || !d_items || !d_counts || !d_out || !d_bbox) return FRMC_ENOMEM;
     unsigned long long *d_ov = d_counts + 2 * cells;
-    int *d_next = (int *)(d_counts + 2 * cells + 1);
-    FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (2 * cells + 2), c->stream));
+    int *d_next = (int *)(d_counts + 2 * cells + 2);
+    FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (2 * cells + 3), c->stream));
     if (lay.npad > 0) {
         FRMC_CUDA(cudaMemcpyAsync(d_atoms, lay.rec.data(), sizeof(float) * 4 * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
         FRMC_CUDA(cudaMemcpyAsync(d_orig, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
     }
     if (!items.empty()) {
         FRMC_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
-        rc = full_hist_launch(c->stream, c->sm_count, mode, R, d_atoms, d_orig, d_items, (int)items.size(), d_next, L, g, nEl, d_counts, d_ov);
+        rc = full_hist_launch(c->stream, c->sm_count, mode, R, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), d_next, L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);

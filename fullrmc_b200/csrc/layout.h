@@ -1,14 +1,20 @@
 // layout.h -- the device-resident atom store layout (host-side description).
 //
-// Atoms are kept ELEMENT-SORTED (stable, so original order is preserved inside an
-// element) in one array of 16-byte records
+// Atoms are kept ELEMENT-SORTED and, inside an element, in K-D ORDER of the (periodically
+// reduced) box coordinates -- every aligned run of 1024 / 256 / 32 records is a compact box --
+// in one array of 16-byte records
 //     float4 { x, y, z, meta }      meta = (molecule_rank << 8) | element      (u32 bits)
 // plus a parallel u32 array `orig` with the atom's original index.  Each element's
 // segment is padded to a multiple of SEG_PAD records with NaN coordinates
 // (meta = 0xFFFFFFFF, orig = 0xFFFFFFFF): NaN fails every range test, so padding
 // never contributes and no kernel needs a bounds check inside a segment.
 //
-// Why sorted: a (tile I, tile J) pair then touches one unordered element pair, so the
+// Why k-d order: a block of SEG_PAD consecutive records is then spatially compact, its
+// bounding box is small, and the full-histogram kernel skips every (I block, J block) whose boxes
+// are provably farther apart than maxDistance (fullhist.cu).  Counts are integers, so the order
+// in which pairs are visited never shows in the result.
+//
+// Why element-sorted: a (tile I, tile J) pair then touches one unordered element pair, so the
 // full-histogram kernel needs only 4 x histSize shared-memory counters per CTA
 // ({intra,inter} x {[a,b],[b,a]}) instead of 2 x nEl^2 x histSize, whatever nEl is.
 // The reference's ORDERED output ([el[i], el[j]] with i<j in original order,
@@ -36,7 +42,8 @@ struct HostLayout {
 };
 
 // Builds the sorted layout.  Returns 0 or a negative FRMC_E* code (error string set).
-int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, HostLayout &out);
+// isPBC selects how a coordinate maps to a cell (fractional part vs. position inside the bounds).
+int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC, HostLayout &out);
 
 // One unit of full-histogram work: I-tile [i0, i0 + 256*ni) x J-range [j0, j1) (padded positions).
 // ea/eb are the (segment) elements of the two ranges; when ea == eb only pairs p<q count.
@@ -45,7 +52,8 @@ struct WorkItem {
     int32_t ea, eb, tri, pad;
 };
 
-// Builds the balanced upper-triangle work list; items with index % nshards == shard are kept.
+// Builds the upper-triangle work list, ordered by element pair (a CTA walking it flushes its
+// shared-memory counters only when the pair changes); items with index % nshards == shard are kept.
 void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, int nshards, std::vector<WorkItem> &items);
 
 }  // namespace frmc

@@ -23,9 +23,10 @@ namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     const WorkItem *items, int n_items, int *next_item, const Lattice &L, const GridParams &g,
-                     int nEl, unsigned long long *counts, unsigned long long *overflow);
-void choose_tiling(int64_t npad, int sm_count, int &R, int64_t &chunkJ);
+                     int64_t npad, float4 *bbox, const WorkItem *items, int n_items, int *next_item, const Lattice &L,
+                     const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
+void choose_tiling(int64_t npad, int sm_count, bool sparse, int &R, int64_t &chunkJ);
+bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
 
 // ------------------------------------------------------------------ device-side descriptors
@@ -903,11 +904,12 @@ struct frmc_store {
     uint32_t *d_orig = nullptr;
     WorkItem *d_items = nullptr;
     int n_items = 0, R = 1;
-    int items_shard = -1, items_nshards = -1;   // which slice of the work list d_items holds
+    int items_shard = -1, items_nshards = -1, items_sparse = -1;   // which slice / tiling of the work list d_items holds
     int64_t chunkJ = 256;
     HostLayout lay;                  // rec freed after upload; segments + inverse permutation kept
     int *d_next = nullptr;
-    unsigned long long *d_overflow = nullptr;
+    unsigned long long *d_overflow = nullptr;   // [0] edge-overflow events, [1] block pairs swept by the last compute_data
+    float4 *d_bbox = nullptr;                   // 2 records per SEG_PAD block (full-histogram culling)
     std::vector<GridHost> grids;
     std::vector<ModelHost> models;
     bool models_dirty = true;
@@ -988,13 +990,14 @@ static GridSet make_gridset(frmc_store *s)
 
 static int upload_layout(frmc_store *s, const float *coords)
 {
-    int rc = build_layout(coords, s->n, s->h_mol.data(), s->h_el.data(), s->nEl, s->lay);
+    int rc = build_layout(coords, s->n, s->h_mol.data(), s->h_el.data(), s->nEl, s->isPBC, s->lay);
     if (rc) return rc;
     s->npad = s->lay.npad;
     for (int c = 0; c < 3; ++c) { s->lo[c] = s->lay.lo[c]; s->hi[c] = s->lay.hi[c]; }
     if (!s->d_atoms) {
         FRMC_CUDA(cudaMalloc(&s->d_atoms, sizeof(float4) * std::max<int64_t>(s->npad, 1)));
         FRMC_CUDA(cudaMalloc(&s->d_orig, sizeof(uint32_t) * std::max<int64_t>(s->npad, 1)));
+        FRMC_CUDA(cudaMalloc(&s->d_bbox, sizeof(float4) * 18 * (size_t)(s->npad / SEG_PAD + 1)));
     }
     if (s->npad > 0) {
         FRMC_CUDA(cudaMemcpyAsync(s->d_atoms, s->lay.rec.data(), sizeof(float4) * s->npad, cudaMemcpyHostToDevice, s->stream));
@@ -1006,11 +1009,12 @@ static int upload_layout(frmc_store *s, const float *coords)
     return FRMC_OK;
 }
 
-static int upload_items(frmc_store *s, int shard, int nshards)
+static int upload_items(frmc_store *s, int shard, int nshards, bool sparse)
 {
-    if (s->d_items && s->items_shard == shard && s->items_nshards == nshards) return FRMC_OK;
+    if (s->d_items && s->items_shard == shard && s->items_nshards == nshards && s->items_sparse == (int)sparse) return FRMC_OK;
     std::vector<WorkItem> items;
-    choose_tiling(s->npad, s->ctx->sm_count, s->R, s->chunkJ);
+    s->items_sparse = (int)sparse;
+    choose_tiling(s->npad, s->ctx->sm_count, sparse, s->R, s->chunkJ);
     build_work_items(s->lay, s->R, s->chunkJ, shard, nshards, items);
     if (s->d_items) { cudaFree(s->d_items); s->d_items = nullptr; }
     s->n_items = (int)items.size();
@@ -1333,10 +1337,10 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     };
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create");
     if (upload_layout(s, coords)) return fail("layout upload");
-    if (upload_items(s, 0, 1)) return fail("work list upload");
+    if (upload_items(s, 0, 1, false)) return fail("work list upload");
     if (cudaMalloc(&s->d_next, sizeof(int) * 4) != cudaSuccess) return fail("alloc");
-    if (cudaMalloc(&s->d_overflow, sizeof(unsigned long long)) != cudaSuccess) return fail("alloc");
-    cudaMemset(s->d_overflow, 0, sizeof(unsigned long long));
+    if (cudaMalloc(&s->d_overflow, 2 * sizeof(unsigned long long)) != cudaSuccess) return fail("alloc");
+    cudaMemset(s->d_overflow, 0, 2 * sizeof(unsigned long long));
     if (cudaMalloc(&s->d_prop, sizeof(Proposal)) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_prop, 0, sizeof(Proposal));
     if (cudaHostAlloc(&s->h_chi2, sizeof(float) * 2 * FRMC_MAX_MODELS, cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
@@ -1364,7 +1368,7 @@ void frmc_store_destroy(frmc_store *s)
     }
     for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); cudaFree(g.dev.tot); cudaFree(g.dev.stot); }
     cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next);
-    cudaFree(s->d_overflow); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps); cudaFree(s->d_bars);
+    cudaFree(s->d_overflow); cudaFree(s->d_bbox); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps); cudaFree(s->d_bars);
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
@@ -1537,17 +1541,20 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
     FRMC_CUDA(cudaSetDevice(s->dev));
     int rc = flush_pending(s);
     if (rc) return rc;
-    rc = upload_items(s, shard, nshards);
-    if (rc) return rc;
     const int mode = current_mode(s, nullptr, nullptr);
+    bool sparse = !s->grids.empty();          // R = 1 tiling only when culling pays for every grid
+    for (auto &g : s->grids) sparse = sparse && culling_pays(s->L, mode, s->lo, s->hi, s->n, s->nEl, g.dev.g);
+    rc = upload_items(s, shard, nshards, sparse);
+    if (rc) return rc;
     for (auto &g : s->grids) {
         FRMC_CUDA(cudaMemsetAsync(g.dev.counts, 0, sizeof(unsigned long long) * 2 * g.dev.cells, s->stream));
         FRMC_CUDA(cudaMemsetAsync(g.dev.delta, 0, sizeof(int) * 2 * g.dev.cells, s->stream));
         FRMC_CUDA(cudaMemsetAsync(s->d_next, 0, sizeof(int) * 4, s->stream));
         if (s->n_items > 0) {
             cudaEvent_t t0 = timing_begin(s);
-            rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->R, s->d_atoms, s->d_orig, s->d_items, s->n_items,
-                                  s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
+            FRMC_CUDA(cudaMemsetAsync(s->d_overflow + 1, 0, sizeof(unsigned long long), s->stream));
+            rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->R, s->d_atoms, s->d_orig, s->npad, s->d_bbox, s->d_items,
+                                  s->n_items, s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
             if (rc) return rc;
             timing_end(s, TIME_FULL, t0);
         }
@@ -1752,6 +1759,16 @@ uint64_t frmc_store_edge_overflow(frmc_store *s)
     cudaMemcpyAsync(&ov, s->d_overflow, sizeof(ov), cudaMemcpyDeviceToHost, s->stream);
     cudaStreamSynchronize(s->stream);
     return ov;
+}
+
+uint64_t frmc_store_swept_pairs(frmc_store *s)
+{
+    if (!s) return 0;
+    unsigned long long blocks = 0;
+    cudaSetDevice(s->dev);
+    cudaMemcpyAsync(&blocks, s->d_overflow + 1, sizeof(blocks), cudaMemcpyDeviceToHost, s->stream);
+    cudaStreamSynchronize(s->stream);
+    return blocks * (unsigned long long)SEG_PAD * 32ull;
 }
 
 }  // extern "C"

@@ -206,3 +206,8 @@ class DeviceStore(object):
     @property
     def edge_overflow(self):
         return int(self._lib.frmc_store_edge_overflow(self._handle))
+
+    @property
+    def swept_pairs(self):
+        """distance evaluations of the last compute_data (block culling skips the rest of n(n-1)/2)"""
+        return int(self._lib.frmc_store_swept_pairs(self._handle))

@@ -55,6 +55,11 @@ const char *frmc_version(void);
  * dropped; on=1: the in-array spill is reproduced so trajectories stay bit-identical to the
  * reference's.  Either way they are counted in edge_overflow.  Returns the previous setting. */
 int frmc_set_edge_spill(int on);
+/* Block culling of the full-histogram kernels (default on): atoms are stored in Morton order, each
+ * 256-atom block carries a bounding box, and block pairs provably farther apart than maxDistance are
+ * not swept.  The result is identical either way (tests sweep both); on=0 forces the reference's plain
+ * O(N^2) sweep, for measurement.  Returns the previous setting. */
+int frmc_set_block_culling(int on);
 /* number of visible CUDA devices, or a negative error code (no CPU fallback exists) */
 int frmc_device_count(void);
 
@@ -206,6 +211,9 @@ int frmc_export_data(frmc_store *s, int grid, float *hintra, float *hinter);
 int frmc_export_total(frmc_store *s, int model, int staged, float *out);
 /* events where the fp32 bin index rounded up to histSize (dropped), summed over the store's life */
 uint64_t frmc_store_edge_overflow(frmc_store *s);
+/* distance evaluations (pairs of records actually swept, padding included) of the last
+ * frmc_compute_data / _shard on this store; n(n-1)/2 is the reference's count */
+uint64_t frmc_store_swept_pairs(frmc_store *s);
 /* Optional per-kernel timing with CUDA events on the store's stream (bench.py's roofline leg).
  * which: 0 = per-move delta pass, 1 = full-histogram kernel, 2 = epilogue (G(r)/S(Q)/chi^2 kernels),
  * 3 = commit/clear kernels.  get_timing synchronises the stream and returns the accumulated

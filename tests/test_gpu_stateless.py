@@ -149,6 +149,63 @@ def test_full_histogram_multi_tile_against_oracle(name, n, nEl, basis, spread, m
     assert hi.sum(dtype=np.float64) + he.sum(dtype=np.float64) == ri.sum(dtype=np.float64) + re_.sum(dtype=np.float64)
 
 
+_TRI = np.array([[120, 0, 0], [17, 115, 0], [-13, 21, 118]], dtype=np.float32)
+
+
+@pytest.mark.parametrize("name,n,nEl,basis,isPBC,spread,rmax", [
+    ("ortho_fast", 50000, 2, np.diag([120.0, 118.0, 122.0]), True, None, 9.0),
+    ("tri_fast", 44000, 3, _TRI, True, None, 9.0),
+    ("ortho_general_unwrapped", 42000, 2, np.diag([120.0, 118.0, 122.0]), True, 2.3, 9.0),
+    ("tri_general_unwrapped", 40000, 2, _TRI, True, 1.7, 9.0),
+    ("infinite_boundaries", 40000, 2, np.diag([120.0, 118.0, 122.0]), False, None, 9.0),
+    ("rmax_beyond_half_box", 20000, 2, np.diag([40.0, 41.0, 39.0]), True, None, 30.0),
+])
+def test_block_culling_never_changes_the_histogram(name, n, nEl, basis, isPBC, spread, rmax, ph, orc):
+    """Morton-ordered blocks whose bounding boxes are farther apart than maxDistance are skipped; the
+    histogram must equal the plain O(N^2) sweep and the oracle in every geometry mode (periodic seam,
+    unwrapped coordinates, skewed cell, no PBC, maxDistance larger than half the box)."""
+    from fullrmc_b200 import _lib, synthetic
+    s = synthetic.random_system(n, 23, np.asarray(basis, dtype=np.float32), n_elements=nEl, molecule_size=7, isPBC=isPBC,
+                                spread=spread)
+    hs = 300
+    kw = dict(s.hist_kwargs(), minDistance=np.float32(0.5), maxDistance=np.float32(rmax),
+              bin=np.float32((rmax - 0.5) / hs), histSize=hs)
+    culled = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, **kw)
+    old = _lib.set_block_culling(False)
+    try:
+        plain = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, **kw)
+    finally:
+        _lib.set_block_culling(old)
+    ri, re_ = orc.full_pairs_histograms_coords(boxCoords=s.boxCoords, ncores=orc.max_threads(), **kw)
+    assert ri.sum() + re_.sum() > 0
+    assert np.array_equal(plain[0], ri) and np.array_equal(plain[1], re_)
+    assert np.array_equal(culled[0], ri) and np.array_equal(culled[1], re_)
+
+
+def test_block_culling_skips_most_of_a_sparse_system():
+    """the store reports how many distance evaluations the last compute_data made"""
+    from fullrmc_b200 import _lib, synthetic
+    from fullrmc_b200.store import DeviceStore
+    s = synthetic.cfg5(120000, seed=3)
+    st = DeviceStore(s.boxCoords, s.basis, s.isPBC, s.moleculeIndex, s.elementIndex, s.numberOfElements)
+    g = st.add_grid(0.0, 8.0, 0.02, 400)
+    st.compute_data()
+    swept = st.swept_pairs
+    intra, inter = st.export_data(g)
+    old = _lib.set_block_culling(False)
+    try:
+        st.compute_data()
+        swept_all = st.swept_pairs
+        intra2, inter2 = st.export_data(g)
+    finally:
+        _lib.set_block_culling(old)
+        st.close()
+    n = s.boxCoords.shape[0]
+    assert swept_all >= n * (n - 1) // 2
+    assert 0 < swept < 0.25 * swept_all
+    assert np.array_equal(intra, intra2) and np.array_equal(inter, inter2)
+
+
 def test_full_histogram_shards_sum_to_whole(ph):
     """the multi-GPU decomposition: per-shard partial histograms add up to the single-call result"""
     from fullrmc_b200 import synthetic
