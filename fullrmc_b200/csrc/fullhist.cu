@@ -263,86 +263,122 @@ struct SpillTarget {
     int slab_ab, slab_ba;
 };
 
-// Lane-private hit queues.  In-range pairs are 0.3 % (plain sweep of a sparse box) to 50 % (maxDistance
-// near half the box) of the pairs swept.  Binning a pair where it is found runs sqrt/div/atomic with a lane
-// or two alive and, inlined per register atom and unroll step, bloats the loop past the instruction cache
-// (ncu: "no instruction" was the top stall).  So the sweep only RECORDS a hit -- a predicated 4-byte store of
-// (q << 2 | r) into the lane's own column of a shared-memory array, no branch, no vote -- and the lanes bin
-// their columns together when one of them is nearly full or the staged block ends.  The bin pass recomputes
-// d2 from the same operands with the same instruction sequence, so it sees the identical value; integer
-// counts make the order of binning irrelevant.
-static const int LQ_CAP = 16;          // entries per lane; [slot][thread] layout: a lane always hits its own bank
+// Lane-private hit queues, warp-balanced binning.  In-range pairs are 0.3 % (plain sweep of a sparse box)
+// to 50 % (maxDistance near half the box) of the pairs swept.  Binning a pair where it is found runs
+// sqrt/div/atomic with a lane or two alive and, inlined per register atom and unroll step, bloats the loop
+// past the instruction cache (ncu: "no instruction" was the top stall).  So the sweep only RECORDS a hit --
+// a predicated 4-byte store of (i << 8 | q) into the lane's own column of a shared-memory array and a
+// predicated pointer bump: no branch, no vote -- and when a column is nearly full or the staged block ends
+// the warp bins ALL its columns together, entry f of the concatenated columns going to lane f % 32 (the
+// owner column is found by a 5-step search over the scanned column lengths).  The I tile is kept in shared
+// memory as well so that any lane can bin any entry.  The bin pass recomputes d2 from the same operands
+// with the same instruction sequence, so it sees the identical value; integer counts make the order of
+// binning irrelevant.
+template <int R> struct SweepShape {
+    static const int U = (R == 1) ? 4 : 2;          // J records per drain check
+    static const int CAP = (R == 1) ? 12 : 16;      // queue entries per lane; [slot][thread] layout: own bank
+};
 
 template <int MODE, int R>
-__device__ __forceinline__ void bin_lane_queue(const uint32_t *__restrict__ lq, int n, const float4 *__restrict__ sJ,
-                                               const uint32_t *__restrict__ sO, int jbase, const float (&xi)[R],
-                                               const float (&yi)[R], const float (&zi)[R], const uint32_t (&mi)[R],
-                                               const uint32_t (&oi)[R], int p0, bool tri, bool cross, const Lattice &L,
-                                               const GridParams &g, unsigned int *__restrict__ sh,
-                                               unsigned long long &ov, const SpillTarget &sp)
+__device__ __forceinline__ void bin_warp_queues(const uint32_t *__restrict__ lq0 /* column of lane 0 of this warp */,
+                                                int n, const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO,
+                                                const float4 *__restrict__ sI, const uint32_t *__restrict__ sIO,
+                                                int i0, int jbase, bool tri, bool cross, const Lattice &L,
+                                                const GridParams &g, unsigned int *__restrict__ sh,
+                                                unsigned long long &ov, const SpillTarget &sp)
 {
-    for (int k = 0; k < n; ++k) {
-        const uint32_t e = lq[k * 256];
-        const int q = (int)(e >> 2), r = (int)(e & 3u);
-        float x = xi[0], y = yi[0], z = zi[0];
-        uint32_t m = mi[0], o = oi[0];
+    const int lane = threadIdx.x & 31;
+    int incl = n;                                  // inclusive scan of the column lengths
 #pragma unroll
-        for (int rr = 1; rr < R; ++rr)
-            if (r == rr) { x = xi[rr]; y = yi[rr]; z = zi[rr]; m = mi[rr]; o = oi[rr]; }
-        if (tri && !(p0 + r * SEG_PAD < jbase + q)) continue;      // diagonal tile: only p < q counts
-        const float4 a = sJ[q];
-        const float d2 = dist2<MODE>(x, y, z, a.x, a.y, a.z, L);
-        const int b = bin_index(d2, g);
-        const uint32_t mj = __float_as_uint(a.w);
-        // slot bit 1: inter-molecular, bit 0: the J atom comes first in original order
-        const int slot = (((m >> 8) == (mj >> 8)) ? 0 : 2) | ((cross && (o > sO[q])) ? 1 : 0);
-        if (b < g.hs) {
-            atomicAdd(&sh[slot * g.hs + b], 1u);
-        } else {
-            ++ov;
-            const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-            if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    for (int f0 = 0; f0 < total; f0 += 32) {
+        const int f = f0 + lane;
+        int l = 0;                                 // owner column = number of columns that end at or before f
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
+            if (v <= f) l += step;
+        }
+        const int first = __shfl_sync(0xffffffffu, excl, l & 31);
+        if (f < total) {
+            const uint32_t e = lq0[(f - first) * 256 + l];
+            const int q = (int)(e & 0xFFu), i = (int)(e >> 8);
+            if (!tri || (i0 + i < jbase + q)) {    // diagonal tile: only p < q counts
+                const float4 a = sI[i], c = sJ[q];
+                const float d2 = dist2<MODE>(a.x, a.y, a.z, c.x, c.y, c.z, L);
+                const int b = bin_index(d2, g);
+                const uint32_t mi = __float_as_uint(a.w), mj = __float_as_uint(c.w);
+                // slot bit 1: inter-molecular, bit 0: the J atom comes first in original order
+                const int slot = (((mi >> 8) == (mj >> 8)) ? 0 : 2) | ((cross && (sIO[i] > sO[q])) ? 1 : 0);
+                if (b < g.hs) {
+                    atomicAdd(&sh[slot * g.hs + b], 1u);
+                } else {
+                    ++ov;
+                    const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+                    if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+                }
+            }
         }
     }
+    __syncwarp();
 }
 
 // one staged block of SEG_PAD J records against the thread's R register atoms
 template <int MODE, int R>
 __device__ __forceinline__ void sweep_block(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int jbase,
                                             const float (&xi)[R], const float (&yi)[R], const float (&zi)[R],
-                                            const uint32_t (&mi)[R], const uint32_t (&oi)[R], int p0, bool tri, bool cross,
-                                            const Lattice &L, const GridParams &g, unsigned submask,
+                                            const float4 *__restrict__ sI, const uint32_t *__restrict__ sIO, int i0,
+                                            bool tri, bool cross, const Lattice &Lc, const GridParams &g, unsigned submask,
                                             uint32_t *__restrict__ lq, unsigned int *__restrict__ sh,
                                             unsigned long long &ov, const SpillTarget &sp)
 {
+    const int U = SweepShape<R>::U, CAP = SweepShape<R>::CAP;
+    // lattice in plain registers: from the constant bank the compiler re-reads it (LDCU) every iteration
+    Lattice L = Lc;
+    if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
+        asm volatile("" : "+f"(L.b[0]), "+f"(L.b[4]), "+f"(L.b[8]));
+    }
+    float t2min = g.t2min, t2max = g.t2max;
+    asm volatile("" : "+f"(t2min), "+f"(t2max));
     // 32-bit shared-window addresses: the push is STS + IADD under the hit predicate
     const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(lq);
-    const uint32_t wfull = w0 + (LQ_CAP - 2 * R) * 1024u;
+    const uint32_t wfull = w0 + (uint32_t)(CAP - U * R) * 1024u;
     uint32_t wp = w0;                            // next free slot of this lane's queue (stride 256 words)
+    const uint32_t *lq0 = lq - (threadIdx.x & 31);
+    uint32_t tid8 = threadIdx.x << 8;            // opaque, or the compiler rebuilds it under every hit predicate
+    asm volatile("" : "+r"(tid8));
+    // 32-record sub-blocks whose box is out of reach of every I block are not in submask (CTA-uniform)
+    for (unsigned sm = submask; sm; sm &= sm - 1u) {
+        const int qb = (__ffs(sm) - 1) * 32;
 #pragma unroll 1
-    for (int q = 0; q < SEG_PAD; q += 2) {
-        // 32-record sub-blocks whose box is out of reach of every I block are stepped over (CTA-uniform)
-        if (!((submask >> (q >> 5)) & 1u)) { q += 30; continue; }
+        for (int q = qb; q < qb + 32; q += U) {
+            const uint32_t ev = tid8 + (uint32_t)q;          // entry = (r * SEG_PAD + tid) << 8 | (q + u)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const float4 a = sJ[q + u];
+            for (int u = 0; u < U; ++u) {
+                const float4 a = sJ[q + u];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float d2 = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
-                if (in_range(d2, g)) {
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"((uint32_t)(((q + u) << 2) | r)) : "memory");
-                    wp += 1024u;
+                for (int r = 0; r < R; ++r) {
+                    const float d2 = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
+                    if ((d2 >= t2min) && (d2 < t2max)) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"(ev + (uint32_t)(((r * SEG_PAD) << 8) + u)) : "memory");
+                        wp += 1024u;
+                    }
                 }
             }
-        }
-        if (__any_sync(0xffffffffu, wp > wfull)) {
-            bin_lane_queue<MODE, R>(lq, (int)((wp - w0) >> 10), sJ, sO, jbase, xi, yi, zi, mi, oi, p0, tri, cross, L, g, sh, ov, sp);
-            wp = w0;
-            __syncwarp();
+            if (__any_sync(0xffffffffu, wp > wfull)) {
+                __syncwarp();
+                bin_warp_queues<MODE, R>(lq0, (int)((wp - w0) >> 10), sJ, sO, sI, sIO, i0, jbase, tri, cross, Lc, g, sh, ov, sp);
+                wp = w0;
+            }
         }
     }
-    bin_lane_queue<MODE, R>(lq, (int)((wp - w0) >> 10), sJ, sO, jbase, xi, yi, zi, mi, oi, p0, tri, cross, L, g, sh, ov, sp);
     __syncwarp();
+    bin_warp_queues<MODE, R>(lq0, (int)((wp - w0) >> 10), sJ, sO, sI, sIO, i0, jbase, tri, cross, Lc, g, sh, ov, sp);
 }
 
 // ------------------------------------------------------------------ block bounding boxes + culling
@@ -460,7 +496,7 @@ CullParams make_cull(const Lattice &L, int mode, const GridParams &g)
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
 // stats[0] += edge overflow events, stats[1] += (SEG_PAD I records x 32 J records) units actually swept.
 template <int MODE, int R>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (R == 1) ? 5 : 3)
 full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const float4 *__restrict__ bbox,
                  const WorkItem *__restrict__ items, int n_items, int *__restrict__ next_item, Lattice L,
                  GridParams g, CullParams cp, int nblocks, int nEl, unsigned long long *__restrict__ counts,
@@ -469,9 +505,11 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sJ = reinterpret_cast<float4 *>(smem_raw);
     uint32_t *sO = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * JS);
-    uint32_t *lq = reinterpret_cast<uint32_t *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS) + threadIdx.x;
-    unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS +
-                                                        sizeof(uint32_t) * LQ_CAP * 256);
+    unsigned char *cur = smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS;
+    float4 *sI = reinterpret_cast<float4 *>(cur);                       cur += sizeof(float4) * SEG_PAD * R;
+    uint32_t *sIO = reinterpret_cast<uint32_t *>(cur);                  cur += sizeof(uint32_t) * SEG_PAD * R;
+    uint32_t *lq = reinterpret_cast<uint32_t *>(cur) + threadIdx.x;     cur += sizeof(uint32_t) * SweepShape<R>::CAP * 256;
+    unsigned int *sh = reinterpret_cast<unsigned int *>(cur);
     __shared__ int s_item;
 
     const int tid = threadIdx.x, lane = threadIdx.x & 31;
@@ -515,21 +553,22 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         }
         if (it >= n_items) break;
 
+        // the I tile: coordinates in registers for the sweep, the full records in shared memory for the
+        // bin pass (made visible by the staging barrier below; the loop-top barrier protects the rewrite)
         float xi[R], yi[R], zi[R];
-        uint32_t mi[R], oi[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+            float4 a = make_float4(__int_as_float(0x7FC00000), __int_as_float(0x7FC00000), __int_as_float(0x7FC00000),
+                                   __uint_as_float(PAD_META));     // NaN: never in range
+            uint32_t o = 0xFFFFFFFFu;
             if (r < w.ni) {
                 const int p = w.i0 + r * SEG_PAD + tid;
-                const float4 a = atoms[p];
-                xi[r] = a.x; yi[r] = a.y; zi[r] = a.z; mi[r] = __float_as_uint(a.w); oi[r] = orig[p];
-            } else {
-                xi[r] = yi[r] = zi[r] = __int_as_float(0x7FC00000);   // NaN: never in range
-                mi[r] = PAD_META; oi[r] = 0xFFFFFFFFu;
+                a = atoms[p]; o = orig[p];
             }
+            xi[r] = a.x; yi[r] = a.y; zi[r] = a.z;
+            sI[r * SEG_PAD + tid] = a; sIO[r * SEG_PAD + tid] = o;
         }
         const bool cross = (w.ea != w.eb);
-        const int p0 = w.i0 + tid;
         const int bi = w.i0 / SEG_PAD;
 
         // J blocks of this item, 32 per round: lane l tests block l against the I blocks (every warp
@@ -577,7 +616,7 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
                 for (int b = 0; b < nb; ++b) {
                     const int jbb = b ? jb1 : jb0;
                     const bool tri = w.tri && jbb < w.i0 + w.ni * SEG_PAD;
-                    sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, mi, oi, p0, tri, cross, L, g,
+                    sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, sI, sIO, w.i0, tri, cross, L, g,
                                          (sub >> (8 * b)) & 0xFFu, lq, sh, ov, sp);
                 }
                 since_flush += (unsigned)(nb * w.ni);
@@ -599,9 +638,11 @@ __global__ void counts64_to_float_kernel(const unsigned long long *__restrict__ 
     if (c < cells2) out[c] = (float)(long long)counts[c];
 }
 
-size_t full_hist_smem_bytes(int hs)
+size_t full_hist_smem_bytes(int hs, int R)
 {
-    return (sizeof(float4) + sizeof(uint32_t)) * JS + sizeof(uint32_t) * LQ_CAP * 256 + sizeof(unsigned int) * 4 * (size_t)hs;
+    const size_t cap = (R == 1) ? SweepShape<1>::CAP : SweepShape<4>::CAP;
+    return (sizeof(float4) + sizeof(uint32_t)) * (JS + (size_t)SEG_PAD * R) + sizeof(uint32_t) * cap * 256 +
+           sizeof(unsigned int) * 4 * (size_t)hs;
 }
 
 template <int MODE, int R>
@@ -609,7 +650,7 @@ static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms,
                          const WorkItem *items, int n_items, int *next_item, const Lattice &L, const GridParams &g,
                          const CullParams &cp, int nblocks, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
-    size_t smem = full_hist_smem_bytes(g.hs);
+    size_t smem = full_hist_smem_bytes(g.hs, R);
     FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "histSize %d needs %zu B of shared memory per CTA (limit 200 KiB)", g.hs, smem);
     auto kern = full_hist_kernel<MODE, R>;
     FRMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
