@@ -47,51 +47,99 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every 10 ms from a thread
+    (the timed region of the culled histogram is a fraction of a second), nvidia-smi -lms 200 as fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = str(gpu_index)
-        self.rows = []
+        self.gpu = int(gpu_index)
+        self.rows = []          # (sm_mhz, max_mhz, set(reasons))
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                pass
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", self.gpu], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+                                          "-lms", "200", "-i", str(self._physical_index())], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _poll_nvml(self):
+        n = self.nvml
+        names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
         try:
-            self.proc.wait(timeout=2)
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            mx = 0.0
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                rs = set(k for k, attr in names if bits & int(getattr(n, attr, 0)))
+                self.rows.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                rs = set(name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8])
+                         if v.lower().startswith("active"))
+                self.rows.append((float(r[1]), float(r[2]), rs))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [r[0] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons |= r[2]
         busy = [x for x in sm if x >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(r[1] for r in self.rows), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -387,6 +435,11 @@ def run_b200(args):
     value = P / (ms_per_step * 1e-3) / 1e9
     counts_host = counts.cpu().numpy().copy()
     in_range_pairs = int(counts_host.sum())
+    swept_local = store.swept_pairs                      # distance evaluations of this rank's last step
+    tsw = torch.tensor([swept_local], dtype=torch.float64, device="cuda:%d" % local)
+    if world > 1:
+        dist.all_reduce(tsw)
+    swept_total = int(tsw[0])
 
     # ---- e2e: the reference-facing stateless call with HOST buffers (host sort + H2D + kernel + D2H)
     kw = dict(system.hist_kwargs(), **grid.kwargs())
@@ -416,19 +469,32 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # instruction-issue ceiling of the tiled kernel: 25 issue slots per pair on the orthorhombic
-    # fast path (cuobjdump -sass), 128 FP32 lanes per SM, at the clock seen under load
+    # The dominant kernel is bound by FP32 instruction issue, not by HBM or tensor cores: after block culling it
+    # evaluates `swept` distances (the rest of the N(N-1)/2 pairs are provably out of range), each of which needs
+    # at least 19 exact fp32 operations on the orthorhombic fast path (3 sub, 3 compare + 3 predicated add for the
+    # minimum image, 6 mul, 2 add, 2 range compares; DESIGN.md "Kernels").  peak = lanes x clock / 19.
     sm_mhz = clocks.get("sm_mhz") or sm_max_mhz
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    issue_peak = n_sm * 128 * sm_mhz * 1e6 / 25.0 / 1e9
-    kernel_gpairs = (P / world) / (ms_kernel_launch * 1e-3) / 1e9 if ms_kernel_launch > 0 else None
+    issue_peak = n_sm * 128 * sm_mhz * 1e6 / 19.0 / 1e9
+    kernel_gevals = swept_local / (ms_kernel_launch * 1e-3) / 1e9 if ms_kernel_launch > 0 else None
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "fullhist_ncu_traffic.json")
+    if os.path.exists(tpath) and n == 1000000 and world == 1:
+        try:
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg5: synthetic %d-atom cubic box (L=%.2f A), 5 elements, full pair histogram, rmin 0, "
                                "bin %.2f, hs %d, + G(r), S(Q) (nQ=%d), chi2 epilogue" % (n, float(system.basis[0, 0]), BIN, HS, NQ),
-                   "pairs_per_step": P, "in_range_pairs": in_range_pairs, "parallelism": "tile-list shards x%d + NCCL allreduce(int64)" % world,
+                   "pairs_per_step": P, "pairs_swept_per_step": swept_total, "swept_fraction": swept_total / float(P),
+                   "in_range_pairs": in_range_pairs, "parallelism": "tile-list shards x%d + NCCL allreduce(int64)" % world,
+                   "value_counts": "all N(N-1)/2 pairs the reference evaluates; pairs in blocks whose bounding boxes are "
+                                   "farther apart than maxDistance are skipped, the histogram is bit-identical",
                    "l2_policy": "inputs (16 B/atom = %.1f MB) are L2-resident by design; the kernel is issue-bound, not HBM-bound" % (16e-6 * npad),
                    "chi2": [float(c) for c in chi2]},
         "clocks": clocks,
@@ -437,11 +503,13 @@ def run_b200(args):
                 "api": "fullrmc_b200.Core.pairs_histograms.full_pairs_histograms_coords (host numpy in/out)",
                 "consistent_with_store_path": agree},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp32-issue (not hbm/tensor: O(N^2) CUDA-core arithmetic on L2/smem-resident data)",
-                     "achieved": kernel_gpairs, "peak": issue_peak, "unit": "Gpairs/s per GPU",
-                     "frac": (kernel_gpairs / issue_peak) if kernel_gpairs else None, "traffic": None,
-                     "kernel_ms_per_launch": ms_kernel_launch,
-                     "peak_source": "%d SMs x 128 lanes x %.0f MHz (median under load) / 25 issue slots per pair" % (n_sm, sm_mhz)},
+        "roofline": {"bound": "fp32-issue (neither hbm nor tensor: exact fp32 minimum-image arithmetic on shared-memory/"
+                              "register-resident tiles; DRAM traffic is ~1 pass over 16 B/atom)",
+                     "achieved": kernel_gevals, "peak": issue_peak, "unit": "G distance evaluations/s per GPU",
+                     "frac": (kernel_gevals / issue_peak) if kernel_gevals else None, "traffic": traffic,
+                     "kernel_ms_per_launch": ms_kernel_launch, "evaluations_per_launch": swept_local,
+                     "peak_source": "%d SMs x 128 lanes x %.0f MHz (median under load) / 19 fp32 issue slots per evaluation"
+                                    % (n_sm, sm_mhz)},
     }
     if world == 1 and not args.no_permove:
         pm = per_move_leg(system, grid, q, args.permove_evals, args.permove_warm, "cfg5: %d-atom cubic box, k=1 translations, hs %d, nQ %d"
@@ -469,7 +537,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--natoms", type=int, default=1000000)
