@@ -720,7 +720,7 @@ bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[
 // memory load of a J record over four pairs (23.4 issue slots per pair instead of 26) and is right when
 // every block pair has to be swept; when culling bites, R = 1 keeps the culled unit at one 256-atom block
 // (about 2.5x fewer pairs swept than with a 1024-atom I-tile).
-void choose_tiling(int64_t npad, int sm_count, bool sparse, int &R, int64_t &chunkJ)
+void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ)
 {
     R = (npad >= 32768 && !sparse) ? 4 : 1;
     const double target_items = 16.0 * sm_count * 4;
@@ -729,6 +729,9 @@ void choose_tiling(int64_t npad, int sm_count, bool sparse, int &R, int64_t &chu
     int64_t c = (int64_t)(cj / JS) * JS;
     if (c < JS) c = JS;
     if (c > 16384) c = 16384;
+    // culled items vary in cost (0 .. chunkJ/256 block sweeps); with the list split over several GPUs a
+    // shorter chunk trims the tail (measured at 8 GPUs: 4.27 -> 4.02 ms; costs 1.7 % on one GPU)
+    if (sparse && nshards >= 4 && c > 4096) c = 4096;
     if (npad < 8192) c = 256;   // tiny systems: finest split
     chunkJ = c;
 }
@@ -765,7 +768,7 @@ extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int 
     int rc = build_layout(coords.data(), n, mol.data(), el, nEl, 1, lay);
     if (rc) return rc;
     int R; int64_t chunkJ;
-    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, false, R, chunkJ);
+    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, false, nshards, R, chunkJ);
     std::vector<WorkItem> items;
     build_work_items(lay, R, chunkJ, shard, nshards, items);
     auto real_in = [&](int e, int64_t a, int64_t b) -> int64_t {   // real atoms of segment e inside positions [a, b)
@@ -809,7 +812,7 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     GridParams g = make_grid(rmin, rmax, bin, hs);
     int mode = choose_mode_from_bounds(L.b, isPBC, lay.lo, lay.hi);
     int R; int64_t chunkJ;
-    choose_tiling(lay.npad, c->sm_count, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g), R, chunkJ);
+    choose_tiling(lay.npad, c->sm_count, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g), nshards, R, chunkJ);
     std::vector<WorkItem> items;
     build_work_items(lay, R, chunkJ, shard, nshards, items);
 

@@ -25,7 +25,7 @@ GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
                      int64_t npad, float4 *bbox, const WorkItem *items, int n_items, int *next_item, const Lattice &L,
                      const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
-void choose_tiling(int64_t npad, int sm_count, bool sparse, int &R, int64_t &chunkJ);
+void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ);
 bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
 
@@ -1014,7 +1014,7 @@ static int upload_items(frmc_store *s, int shard, int nshards, bool sparse)
     if (s->d_items && s->items_shard == shard && s->items_nshards == nshards && s->items_sparse == (int)sparse) return FRMC_OK;
     std::vector<WorkItem> items;
     s->items_sparse = (int)sparse;
-    choose_tiling(s->npad, s->ctx->sm_count, sparse, s->R, s->chunkJ);
+    choose_tiling(s->npad, s->ctx->sm_count, sparse, nshards, s->R, s->chunkJ);
     build_work_items(s->lay, s->R, s->chunkJ, shard, nshards, items);
     if (s->d_items) { cudaFree(s->d_items); s->d_items = nullptr; }
     s->n_items = (int)items.size();
