@@ -518,14 +518,15 @@ def run_b200(args):
         pm4 = per_move_leg(s4, grid, q, args.permove_evals, args.permove_warm, "cfg4: 100000-atom 5-element triclinic box, k=1 translations, hs %d, nQ %d"
                            % (HS, NQ), hbm_gbs, peak_src, local)
         if not args.no_cpu:
-            pm["cpu_baseline"] = per_move_cpu_baseline(system, grid, q, 12)
-            pm4["cpu_baseline"] = per_move_cpu_baseline(s4, grid, q, 60)
+            pm["cpu_baseline"] = per_move_cpu_baseline(system, grid, q, 300)      # ~10 s of CPU work
+            pm4["cpu_baseline"] = per_move_cpu_baseline(s4, grid, q, 2500)        # ~10 s
         line["per_move"] = pm
         line["per_move_cfg4"] = pm4
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, kind, desc, _ = cpu_full_hist_sample(n, max(1, 48 // cores), cores)
-        v1, kind1, desc1, _ = cpu_full_hist_sample(n, 24, 1)
+        scale = max(1, n // 1000000)                                           # ~10 s of CPU work per leg at 1 M atoms
+        v, kind, desc, _ = cpu_full_hist_sample(n, max(1, 480 // scale), cores)
+        v1, kind1, desc1, _ = cpu_full_hist_sample(n, max(1, 600 // scale), 1)
         line["cpu_baseline"] = {"value": v1, "unit": "Gpairs/s", "cores": 1, "kind": kind1, "sample": desc1,
                                 "all_cores": {"value": v, "cores": cores, "sample": desc,
                                               "note": "harness-level row sharding; the reference itself is single-threaded"}}

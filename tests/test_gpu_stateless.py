@@ -182,6 +182,50 @@ def test_block_culling_never_changes_the_histogram(name, n, nEl, basis, isPBC, s
     assert np.array_equal(culled[0], ri) and np.array_equal(culled[1], re_)
 
 
+def _adversarial_systems():
+    """coordinate sets chosen to stress the bounding-box bound: the periodic seam, exact 0/1, unwrapped
+    offsets, degenerate (flat / linear) boxes, a strongly skewed cell, large non-periodic coordinates"""
+    rng = np.random.default_rng(77)
+    n = 5200
+    out = []
+    ortho = np.diag([60.0, 55.0, 65.0]).astype(np.float32)
+    skew = np.array([[60, 0, 0], [48, 30, 0], [-35, 25, 40]], dtype=np.float32)
+    # two tight clusters on either side of the seam in x, one in the middle
+    c = np.concatenate([rng.normal([0.01, 0.3, 0.3], 0.012, (n // 3, 3)), rng.normal([0.99, 0.3, 0.3], 0.012, (n // 3, 3)),
+                        rng.normal([0.5, 0.7, 0.7], 0.05, (n - 2 * (n // 3), 3))]).astype(np.float32)
+    out.append(("seam_clusters", c, ortho, True))
+    # exact grid values including 0, 1, -0.0 and whole-cell offsets
+    g = (rng.integers(0, 33, (n, 3)) / 32.0).astype(np.float32)
+    g[::7] += np.float32(3.0); g[1::7] -= np.float32(2.0); g[2::11] = np.float32(-0.0)
+    out.append(("lattice_points_and_offsets", g, ortho, True))
+    # all atoms in one plane / on one line: zero-width boxes
+    flat = rng.random((n, 3)).astype(np.float32); flat[:, 2] = np.float32(0.25)
+    out.append(("flat_sheet", flat, ortho, True))
+    line = rng.random((n, 3)).astype(np.float32); line[:, 1] = np.float32(0.5); line[:, 2] = np.float32(0.999999)
+    out.append(("line", line, skew, True))
+    out.append(("skewed_cell", rng.random((n, 3)).astype(np.float32), skew, True))
+    out.append(("skewed_cell_unwrapped", (rng.random((n, 3)) * 5.0 - 2.5).astype(np.float32), skew, True))
+    far = (rng.random((n, 3)) * 90.0 + np.array([480.0, -520.0, 3.0])).astype(np.float32)
+    out.append(("non_periodic_large_coordinates", far, np.eye(3, dtype=np.float32), False))
+    return out
+
+
+@pytest.mark.parametrize("name,coords,basis,isPBC", _adversarial_systems(), ids=[a[0] for a in _adversarial_systems()])
+@pytest.mark.parametrize("rmax", [2.5, 7.0, 26.0])
+def test_block_culling_adversarial_geometries(name, coords, basis, isPBC, rmax, ph, orc):
+    n = coords.shape[0]
+    rng = np.random.default_rng(5)
+    el = rng.integers(0, 2, n).astype(np.int32)
+    mol = (np.arange(n) // 3).astype(np.int32)
+    hs = 50
+    kw = dict(basis=basis, isPBC=isPBC, moleculeIndex=mol, elementIndex=el, numberOfElements=2,
+              minDistance=np.float32(0.0), maxDistance=np.float32(rmax), bin=np.float32(rmax / hs), histSize=hs)
+    hi, he = ph.full_pairs_histograms_coords(boxCoords=coords, **kw)
+    ri, re_, ov = orc.full_pairs_histograms_coords(boxCoords=coords, ncores=orc.max_threads(), return_overflow=True, **kw)
+    assert np.array_equal(hi, ri) and np.array_equal(he, re_)
+    assert ph.LAST_EDGE_OVERFLOW == ov
+
+
 def test_block_culling_skips_most_of_a_sparse_system():
     """the store reports how many distance evaluations the last compute_data made"""
     from fullrmc_b200 import _lib, synthetic
