@@ -74,6 +74,9 @@ SIGNATURES = {
     "frmc_grid_add": (_I, [_VP, _F, _F, _F, _I]),
     "frmc_model_add": (_I, [_VP, _I, ctypes.POINTER(ModelDesc)]),
     "frmc_model_set_scale": (_I, [_VP, _I, _F]),
+    "frmc_model_set_adjust": (_I, [_VP, _I, _I, _F, _F]),
+    "frmc_model_get_scale": (_I, [_VP, _I, c_f32p, c_f32p]),
+    "frmc_store_set_accepted": (_I, [_VP, ctypes.c_uint64]),
     "frmc_compute_data": (_I, [_VP, c_f32p]),
     "frmc_compute_data_shard": (_I, [_VP, _I, _I]),
     "frmc_grid_counts_ptr": (_VP, [_VP, _I, c_i64p]),

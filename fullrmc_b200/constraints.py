@@ -65,6 +65,15 @@ class DeviceBackend(object):
             self._dirty = False
         return self._committed
 
+    def _evaluate_committed(self):
+        """totals and chi^2 of the committed histograms again (no histogram pass): what the reference's
+        compute_data(update=False) returns when nothing moved; the scale factor may be refitted"""
+        if self._dirty:
+            return self._compute_data()
+        if not self._resolved:
+            raise RuntimeError("a move is staged; accept or reject it first")
+        return self.store.finalize_data()
+
     def _before(self, relativeIndexes):
         # compute_before_move needs no device work of its own: the delta pass forms
         # after-minus-before in one sweep (PairDistributionConstraints.py:1053-1078 + :1095-1120)
@@ -105,7 +114,7 @@ class _DeviceExperimentalConstraint(object):
     KIND = None
 
     def __init__(self, backend, experimentalData, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
-                 weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None):
+                 weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None, adjustScaleFactor=(0, 0.8, 1.2)):
         self.backend = backend
         self.experimentalData = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         self.minimumDistance = FLOAT_TYPE(minDistance)
@@ -122,6 +131,9 @@ class _DeviceExperimentalConstraint(object):
                          backend.numberDensity, self.shellCenters, self.shellVolumes, self.experimentalData,
                          data_weights=dataWeights, shape_array=shapeArray, scale_factor=scaleFactor, q_values=qValues)
         backend._register(self, (self.minimumDistance, self.maximumDistance, self.bin, self.histogramSize), spec)
+        self.adjustScaleFactor = (int(adjustScaleFactor[0]), FLOAT_TYPE(adjustScaleFactor[1]), FLOAT_TYPE(adjustScaleFactor[2]))
+        if self.adjustScaleFactor[0]:
+            backend.store.set_adjust_scale_factor(self._model, *self.adjustScaleFactor)     # Core/Constraint.py:1196-1230
 
     # -- the reference's properties
     @property
@@ -132,6 +144,16 @@ class _DeviceExperimentalConstraint(object):
         intra, inter = self.backend.store.export_data(self._grid)
         return {"intra": intra, "inter": inter}
 
+    @property
+    def scaleFactor(self):
+        """the constraint's scale factor (accept_move stores the fitted value, PairDistributionConstraints.py:1150)"""
+        return self.backend.store.get_scale(self._model)[0]
+
+    @property
+    def fittedScaleFactor(self):
+        """the scale factor the last evaluation used (the reference's _fittedScaleFactor)"""
+        return self.backend.store.get_scale(self._model)[1]
+
     def get_constraint_total(self, staged=False):
         """model total (G(r), g(r) or S(Q)) of the committed (or staged) state"""
         self.backend._compute_data()
@@ -139,8 +161,11 @@ class _DeviceExperimentalConstraint(object):
 
     # -- the five methods (Core/Constraint.py:732-748)
     def compute_data(self, update=True):
-        self.backend._dirty = self.backend._dirty or update
-        chi2 = self.backend._compute_data()
+        if update:
+            self.backend._dirty = True
+            chi2 = self.backend._compute_data()
+        else:
+            chi2 = self.backend._evaluate_committed()
         if update:
             self.standardError = FLOAT_TYPE(chi2[self._model])
         return self.data, FLOAT_TYPE(chi2[self._model])
@@ -171,7 +196,8 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
     (set_experimental_data / set_limits, PairDistributionConstraints.py:700-768)."""
     KIND = "PDF"
 
-    def __init__(self, backend, experimentalData, weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0):
+    def __init__(self, backend, experimentalData, weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0,
+                 adjustScaleFactor=(0, 0.8, 1.2)):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         r = exp[:, 0]
         b = FLOAT_TYPE(r[1] - r[0])                                            # :726
@@ -181,7 +207,7 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
         hs = len(edges) - 1
         super(DevicePairDistributionConstraint, self).__init__(
             backend, exp[:, 1], rmin, rmax, b, hs, np.array(r, dtype=FLOAT_TYPE), shell_volumes_from_edges(edges),
-            weighting, dataWeights, shapeArray, scaleFactor)
+            weighting, dataWeights, shapeArray, scaleFactor, adjustScaleFactor=adjustScaleFactor)
 
 
 class DevicePairCorrelationConstraint(DevicePairDistributionConstraint):
@@ -194,14 +220,15 @@ class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
     (StructureFactorConstraints.py:330-350: edges = arange(rmin, rmax, dr))."""
     KIND = "SQ"
 
-    def __init__(self, backend, experimentalData, weighting, rmin, rmax, dr, dataWeights=None, scaleFactor=1.0):
+    def __init__(self, backend, experimentalData, weighting, rmin, rmax, dr, dataWeights=None, scaleFactor=1.0,
+                 adjustScaleFactor=(0, 0.8, 1.2)):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         edges = np.arange(rmin, rmax, dr).astype(FLOAT_TYPE)                   # :337-341
         centers = (edges[0:-1] + edges[1:]) / FLOAT_TYPE(2.)                   # :346
         hs = len(edges) - 1
         super(DeviceStructureFactorConstraint, self).__init__(
             backend, exp[:, 1], edges[0], edges[-1], FLOAT_TYPE(dr), hs, centers, shell_volumes_from_edges(edges),
-            weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0])
+            weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0], adjustScaleFactor=adjustScaleFactor)
 
 
 class DeviceReducedStructureFactorConstraint(DeviceStructureFactorConstraint):
@@ -213,7 +240,8 @@ _KIND_CLASS = {}
 
 
 def make_device_constraint(backend, kind, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
-                           weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None):
+                           weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None,
+                           adjustScaleFactor=(0, 0.8, 1.2)):
     """Build a device constraint from the quantities a reference constraint has already derived
     (limits, bin, histogram size, shell arrays, weighting scheme) -- what the subclass recipe of
     INTEGRATION.md hands over."""
@@ -221,4 +249,4 @@ def make_device_constraint(backend, kind, experimental, minDistance, maxDistance
         for name in ("PDF", "PCF", "SQ", "RSQ"):
             _KIND_CLASS[name] = type("Device%sConstraint" % name, (_DeviceExperimentalConstraint,), {"KIND": name})
     return _KIND_CLASS[kind](backend, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
-                             weighting, dataWeights, shapeArray, scaleFactor, qValues)
+                             weighting, dataWeights, shapeArray, scaleFactor, qValues, adjustScaleFactor)

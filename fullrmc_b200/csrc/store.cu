@@ -80,7 +80,8 @@ struct ModelDev {
     int pw_leaves;
     int nq_pad;                      // row stride of gr2sq on the device (n_out rounded up to 32, zero filled)
     int n_stages;                    // S(Q) ring depth chosen by the host from the shared-memory budget
-    int pad0;
+    int refit;                       // this evaluation refits the scale factor (engine.accepted % frequency == 0; set per launch)
+    float sf_min, sf_max;            // clip range of the fitted value (Core/Constraint.py:1392-1393)
     // pair table inline (n_pairs <= EPI_INLINE_PAIRS): travels in the kernel parameters, no dependent load
     int i_psym[EPI_INLINE_PAIRS];
     float i_w[EPI_INLINE_PAIRS], i_D[EPI_INLINE_PAIRS], i_rD[EPI_INLINE_PAIRS];
@@ -476,8 +477,34 @@ struct EpiShared {
     float s_w[EPI_MAX_PAIRS + 16], s_D[EPI_MAX_PAIRS + 16], s_rD[EPI_MAX_PAIRS + 16];
     PairwiseScratch ps;
     int s_last;
+    float s_sf;                      // scale factor of this evaluation (fitted or the committed one)
     unsigned long long mbar[SQ_MAX_STAGES];
 };
+
+// ExperimentalConstraint.fit_scale_factor (Core/Constraint.py:1363-1395): SF = sum(w*M*E) / sum(M**2) in
+// numpy's fp32 pairwise order, clipped.  mv/ev = model / experimental value of element i as the calling
+// constraint hands them over (G(r); 4*pi*r*rho0*(g-1); S(Q)-1).  Whole CTA; result in es.s_sf.
+template <typename FM, typename FE>
+__device__ __forceinline__ void fit_scale_factor(EpiShared &es, float *sT, const ModelDev &M, int n, FM mv, FE ev)
+{
+    for (int i = threadIdx.x; i < n; i += EPI_THREADS) {
+        const float m = mv(i);
+        sT[i] = M.wts ? __fmul_rn(__fmul_rn(M.wts[i], m), ev(i)) : __fmul_rn(m, ev(i));
+    }
+    __syncthreads();
+    const float s1 = block_pairwise_sum(sT, M.pw_leaves, es.ps);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += EPI_THREADS) { const float m = mv(i); sT[i] = __fmul_rn(m, m); }
+    __syncthreads();
+    const float s2 = block_pairwise_sum(sT, M.pw_leaves, es.ps);
+    if (threadIdx.x == 0) {
+        float sf = __fdiv_rn(s1, s2);
+        if (M.sf_min > sf) sf = M.sf_min;          // max(SF, minimum): Python keeps SF unless minimum > SF
+        if (M.sf_max < sf) sf = M.sf_max;          // min(SF, maximum)
+        es.s_sf = sf;
+    }
+    __syncthreads();
+}
 
 #define EPI_STAMP(i) do { if (stamps && threadIdx.x == 0 && slab == 0) { stamps[m * 8 + (i)] = clock64(); \
         unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[64 + m * 8 + (i)] = (long long)gt_; } } while (0)
@@ -606,10 +633,11 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 if (r >= hs) continue;
                 float a = __fdiv_rn(acc[j], svr[j]);
                 float out;
+                const bool defer = M.refit && !is_sq;      // r-space refit: scale applied after the fit below
                 if (M.kind == FRMC_KIND_PCF) {
                     out = a;
                     if (M.shape) out = __fsub_rn(out, shp[j]);
-                    if (M.scale != 1.0f) {
+                    if (!defer && M.scale != 1.0f) {
                         float Gr = __fmul_rn(prf[j], __fsub_rn(out, 1.0f));
                         Gr = __fmul_rn(Gr, M.scale);
                         out = __fadd_rn(1.0f, __fdiv_rn(Gr, prf[j]));
@@ -618,11 +646,11 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                     out = __fmul_rn(prf[j], __fsub_rn(a, 1.0f));
                     if (M.kind == FRMC_KIND_PDF) {
                         if (M.shape) out = __fsub_rn(out, shp[j]);
-                        if (M.scale != 1.0f) out = __fmul_rn(out, M.scale);
+                        if (!defer && M.scale != 1.0f) out = __fmul_rn(out, M.scale);
                     }
                 }
                 sG[r] = out;
-                if (slab == 0) {
+                if (slab == 0 && !defer) {
                     M.rfun[r] = out;
                     if (!is_sq) M.total[r] = out;
                 }
@@ -640,7 +668,33 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     EPI_STAMP(2);
 
     float chi2 = 0.f;
+    if (tid == 0) es.s_sf = M.scale;
     if (!is_sq) {
+        if (M.refit) {
+            // ---- 1b. scale-factor refit on the unscaled function (PairDistributionConstraints.py:886-888;
+            //          PairCorrelationConstraints.py:171-184 fits on G(r) = 4 pi r rho0 (g - 1))
+            if (M.kind == FRMC_KIND_PCF)
+                fit_scale_factor(es, sT, M, hs, [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(sG[i], 1.0f)); },
+                                 [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(M.expv[i], 1.0f)); });
+            else
+                fit_scale_factor(es, sT, M, hs, [&](int i) { return sG[i]; }, [&](int i) { return M.expv[i]; });
+            const float sf = es.s_sf;
+            for (int i = tid; i < hs; i += EPI_THREADS) {
+                float out = sG[i];
+                if (sf != 1.0f) {
+                    if (M.kind == FRMC_KIND_PCF) {
+                        float Gr = __fmul_rn(M.pref[i], __fsub_rn(out, 1.0f));
+                        Gr = __fmul_rn(Gr, sf);
+                        out = __fadd_rn(1.0f, __fdiv_rn(Gr, M.pref[i]));
+                    } else {
+                        out = __fmul_rn(out, sf);
+                    }
+                }
+                sG[i] = out;
+                M.rfun[i] = out; M.total[i] = out;
+            }
+            __syncthreads();
+        }
         // ---- 2. chi^2 of an r-space model
         for (int i = tid; i < hs; i += EPI_THREADS) {
             float d = __fsub_rn(M.expv[i], sG[i]);
@@ -713,9 +767,9 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 float sv = acc;
                 if (M.kind == FRMC_KIND_SQ) {
                     sv = __fadd_rn(sv, 1.0f);
-                    if (M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
+                    if (!M.refit && M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
                 } else {
-                    if (M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                                      // (:1258-1260)
+                    if (!M.refit && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                                      // (:1258-1260)
                 }
                 M.total[q0 + lane] = sv;
             }
@@ -733,6 +787,19 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         EPI_STAMP(4);
         if (!s_last) return;
         __threadfence();
+        if (M.refit) {
+            // ---- 3b. refit on S(Q)-1 against experimental-1 (StructureFactorConstraints.py:824-834, inherited by
+            //          the reduced constraint), then scale the slices the other CTAs left unscaled
+            fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(M.total + i), 1.0f); },
+                             [&](int i) { return __fsub_rn(M.expv[i], 1.0f); });
+            const float sf = es.s_sf;
+            if (sf != 1.0f)
+                for (int i = tid; i < nq; i += EPI_THREADS) {
+                    const float sv = __ldcg(M.total + i);
+                    M.total[i] = (M.kind == FRMC_KIND_SQ) ? __fadd_rn(__fmul_rn(sf, __fsub_rn(sv, 1.0f)), 1.0f) : __fmul_rn(sf, sv);
+                }
+            __syncthreads();
+        }
         for (int i = tid; i < nq; i += EPI_THREADS) {
             float d = __fsub_rn(M.expv[i], __ldcg(M.total + i));
             float t = __fmul_rn(d, d);
@@ -750,6 +817,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     }
     if (tid == 0) {
         chi2_out[m] = chi2;
+        chi2_out[2 * FRMC_MAX_MODELS + m] = es.s_sf;       // the scale factor this evaluation used
         __threadfence_system();
         const unsigned int v = dev_seq[m] + 1u;
         dev_seq[m] = v;
@@ -883,6 +951,8 @@ using namespace frmc;
 struct ModelHost {
     ModelDev dev;                    // device pointers (owned)
     float *total_committed = nullptr;
+    int adjust_freq = 0;             // scale-factor refit every `freq` accepted moves (0: never)
+    float sf_staged = 1.0f;          // scale factor the last evaluation used
     std::vector<void *> owned;
 };
 
@@ -915,7 +985,7 @@ struct frmc_store {
     bool models_dirty = true;
     ProposalIn prop_in;              // staged proposal, handed to the delta kernel by value
     Proposal *d_prop = nullptr;
-    float *h_chi2 = nullptr;         // pinned, device-visible: [FRMC_MAX_MODELS] chi2 then [FRMC_MAX_MODELS] u32 sequence numbers
+    float *h_chi2 = nullptr;         // pinned, device-visible: [FRMC_MAX_MODELS] chi2, [FRMC_MAX_MODELS] u32 sequence numbers, [FRMC_MAX_MODELS] scale factors used
     volatile unsigned int *h_seq = nullptr;
     unsigned int *d_seq = nullptr;   // [FRMC_MAX_MODELS] launch counters + [FRMC_MAX_MODELS] tickets
     long long *d_stamps = nullptr;   // [FRMC_MAX_MODELS][8] clock64 phase stamps of the last epilogue (debug)
@@ -931,6 +1001,7 @@ struct frmc_store {
     float prop_lo[3], prop_hi[3];
     int state = 0;                   // 0 idle, 1 proposal staged
     float chi2_staged[FRMC_MAX_MODELS];
+    unsigned long long accepted = 0;  // the engine's count of accepted moves (refit schedule, Core/Constraint.py:1418-1422)
     float chi2_committed[FRMC_MAX_MODELS];
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
     bool timing = false;
@@ -1093,6 +1164,14 @@ static int sync_models(frmc_store *s)
     return FRMC_OK;
 }
 
+// per-launch copy of a model descriptor: the refit flag follows the engine's accepted count
+static ModelDev launch_model(const frmc_store *s, const ModelHost &mh)
+{
+    ModelDev d = mh.dev;
+    d.refit = (mh.adjust_freq > 0 && (s->accepted % (unsigned long long)mh.adjust_freq) == 0) ? 1 : 0;
+    return d;
+}
+
 // totals + chi^2 of every model from the staged totals; results land in s->h_chi2 once h_seq == seq_expected
 static int launch_epilogue(frmc_store *s)
 {
@@ -1106,7 +1185,7 @@ static int launch_epilogue(frmc_store *s)
     ms.n = nm;
     int max_q = 1;
     for (int i = 0; i < nm; ++i) {
-        ms.m[i] = s->models[i].dev;
+        ms.m[i] = launch_model(s, s->models[i]);
         if (ms.m[i].kind == FRMC_KIND_SQ || ms.m[i].kind == FRMC_KIND_RSQ) max_q = std::max(max_q, ms.m[i].n_out);
     }
     cudaEvent_t t0 = timing_begin(s);
@@ -1230,7 +1309,7 @@ static int launch_fused_t(frmc_store *s)
     ModelSet ms;
     memset(&ms, 0, sizeof(ms));
     ms.n = (int)s->models.size();
-    for (int i = 0; i < ms.n; ++i) ms.m[i] = s->models[i].dev;
+    for (int i = 0; i < ms.n; ++i) ms.m[i] = launch_model(s, s->models[i]);
     TotalsCopy tc = make_totals_copy(s);
     int npad = (int)s->npad, nEl = s->nEl, prev = s->pending;
     unsigned long long launch_no = ++s->fused_launches;
@@ -1343,7 +1422,7 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     cudaMemset(s->d_overflow, 0, 2 * sizeof(unsigned long long));
     if (cudaMalloc(&s->d_prop, sizeof(Proposal)) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_prop, 0, sizeof(Proposal));
-    if (cudaHostAlloc(&s->h_chi2, sizeof(float) * 2 * FRMC_MAX_MODELS, cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
+    if (cudaHostAlloc(&s->h_chi2, sizeof(float) * 3 * FRMC_MAX_MODELS, cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
     s->h_seq = reinterpret_cast<volatile unsigned int *>(s->h_chi2 + FRMC_MAX_MODELS);
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) s->h_seq[i] = 0u;
     if (cudaMalloc(&s->d_seq, sizeof(unsigned int) * 2 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
@@ -1533,6 +1612,31 @@ int frmc_model_set_scale(frmc_store *s, int model, float scale)
     return FRMC_OK;
 }
 
+int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min, float sf_max)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    FRMC_REQUIRE(frequency >= 0, FRMC_EINVAL, "negative frequency");
+    s->models[model].adjust_freq = frequency;
+    s->models[model].dev.sf_min = sf_min;
+    s->models[model].dev.sf_max = sf_max;
+    return FRMC_OK;
+}
+
+int frmc_model_get_scale(frmc_store *s, int model, float *committed, float *last_used)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    if (committed) *committed = s->models[model].dev.scale;
+    if (last_used) *last_used = s->models[model].sf_staged;
+    return FRMC_OK;
+}
+
+int frmc_store_set_accepted(frmc_store *s, uint64_t accepted)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    s->accepted = accepted;
+    return FRMC_OK;
+}
+
 int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
 {
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
@@ -1574,7 +1678,9 @@ void *frmc_grid_counts_ptr(frmc_store *s, int grid, int64_t *n_cells)
 int frmc_finalize_data(frmc_store *s, float *chi2)
 {
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
     FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
     for (auto &g : s->grids) {
         const long long ns = (long long)g.dev.nsym * g.dev.g.hs;
         int grid = (int)std::max<long long>(1, std::min<long long>((ns + 255) / 256, (long long)s->ctx->sm_count * 2));
@@ -1593,6 +1699,7 @@ int frmc_finalize_data(frmc_store *s, float *chi2)
     FRMC_REQUIRE(!too_big, FRMC_ELIMIT, "a symmetrised histogram cell exceeds 2^30 counts (int32 running totals)");
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_committed[i] = s->h_chi2[i];
+        s->models[i].sf_staged = s->h_chi2[2 * FRMC_MAX_MODELS + i];
         if (chi2) chi2[i] = s->h_chi2[i];
     }
     return FRMC_OK;
@@ -1618,6 +1725,7 @@ int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *move
     if (rc) return rc;
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_staged[i] = s->h_chi2[i];
+        s->models[i].sf_staged = s->h_chi2[2 * FRMC_MAX_MODELS + i];
         if (chi2_after) chi2_after[i] = s->h_chi2[i];
     }
     s->state = 1;
@@ -1633,7 +1741,12 @@ int frmc_accept(frmc_store *s)
     // anything else that looks at the device state calls flush_pending() first
     s->pending = 1;
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], s->prop_lo[c]); s->hi[c] = std::max(s->hi[c], s->prop_hi[c]); }
-    for (size_t i = 0; i < s->models.size(); ++i) s->chi2_committed[i] = s->chi2_staged[i];
+    for (size_t i = 0; i < s->models.size(); ++i) {
+        s->chi2_committed[i] = s->chi2_staged[i];
+        // accept_move: _set_fitted_scale_factor_value(self._fittedScaleFactor) (PairDistributionConstraints.py:1150)
+        if (s->models[i].adjust_freq > 0) s->models[i].dev.scale = s->models[i].sf_staged;
+    }
+    ++s->accepted;
     s->state = 0;
     if (!(s->fused_ok && !s->timing)) return flush_pending(s);
     return FRMC_OK;

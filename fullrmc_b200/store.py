@@ -95,6 +95,22 @@ class DeviceStore(object):
     def set_scale(self, model, scale):
         L.check(self._lib.frmc_model_set_scale(self._handle, int(model), float(_F32(scale))), "set_scale")
 
+    def set_adjust_scale_factor(self, model, frequency, minimum, maximum):
+        """ExperimentalConstraint.set_adjust_scale_factor (Core/Constraint.py:1160-1177): refit the scale factor in
+        every evaluation made while accepted % frequency == 0, clipped to [minimum, maximum]; 0 switches it off."""
+        L.check(self._lib.frmc_model_set_adjust(self._handle, int(model), int(frequency), float(_F32(minimum)),
+                                                float(_F32(maximum))), "set_adjust_scale_factor")
+
+    def get_scale(self, model):
+        """(the model's scale factor, the scale factor the last evaluation used)"""
+        a = ctypes.c_float(0.0); b = ctypes.c_float(0.0)
+        L.check(self._lib.frmc_model_get_scale(self._handle, int(model), ctypes.byref(a), ctypes.byref(b)), "get_scale")
+        return _F32(a.value), _F32(b.value)
+
+    def set_accepted(self, accepted):
+        """re-base the store's count of accepted moves on engine.accepted (it drives the refit schedule)"""
+        L.check(self._lib.frmc_store_set_accepted(self._handle, int(accepted)), "set_accepted")
+
     @property
     def n_models(self):
         return len(self._models)

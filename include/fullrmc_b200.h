@@ -178,6 +178,16 @@ int frmc_grid_add(frmc_store *s, float rmin, float rmax, float bin, int hs);
 /* register a model on a grid; returns model id >= 0 */
 int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *desc);
 int frmc_model_set_scale(frmc_store *s, int model, float scale);
+/* Scale-factor refit (ExperimentalConstraint.set_adjust_scale_factor / fit_scale_factor /
+ * get_adjusted_scale_factor, Core/Constraint.py:1363-1423): when frequency > 0 every evaluation made while
+ * accepted % frequency == 0 fits SF = sum(w*M*E)/sum(M^2) (numpy fp32 pairwise order, on G(r) for the
+ * r-space kinds and on S(Q)-1 for the Q-space kinds), clips it to [sf_min, sf_max] and scales the total
+ * with it; frmc_accept makes the last used value the model's scale factor (accept_move,
+ * PairDistributionConstraints.py:1150).  `accepted` is the engine's count of accepted moves: the store
+ * counts its own frmc_accept calls, frmc_store_set_accepted re-bases it. */
+int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min, float sf_max);
+int frmc_model_get_scale(frmc_store *s, int model, float *committed, float *last_used);
+int frmc_store_set_accepted(frmc_store *s, uint64_t accepted);
 
 /* compute_data: full histogram of every grid (tiled kernel), totals and chi^2 per model.
  * chi2 [n_models] fp32 (np.add.reduce result), may be NULL. */

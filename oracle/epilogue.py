@@ -101,33 +101,42 @@ def _weighted_sum(intra, inter, elements, n_per_element, weighting, volume, cast
 
 
 def total_Gr(intra, inter, elements, n_per_element, weighting, volume, rho0, shell_centers, shell_volumes,
-             shape_array=None, scale_factor=1.0):
-    """PairDistributionConstraint.__get_total_Gr (PairDistributionConstraints.py:847-895)."""
+             shape_array=None, scale_factor=1.0, refit=None):
+    """PairDistributionConstraint.__get_total_Gr (PairDistributionConstraints.py:847-895).
+    refit = (experimental, data_weights, sf_min, sf_max): this evaluation refits the scale factor
+    (get_adjusted_scale_factor, Core/Constraint.py:1397-1423) and the function returns (total, SF)."""
     volume, rho0 = FLOAT_TYPE(volume), FLOAT_TYPE(rho0)
     Gr = _weighted_sum(intra, inter, elements, n_per_element, weighting, volume, cast_D=True)
     Gr /= shell_volumes
     Gr = (4. * PI * shell_centers * rho0) * (Gr - 1)
     if shape_array is not None:
         Gr -= shape_array
+    if refit is not None:
+        scale_factor = fit_scale_factor(refit[0], Gr, refit[1], refit[2], refit[3])
     if scale_factor != 1:
         Gr *= FLOAT_TYPE(scale_factor)
-    return Gr
+    return Gr if refit is None else (Gr, FLOAT_TYPE(scale_factor))
 
 
 def total_gr(intra, inter, elements, n_per_element, weighting, volume, rho0, shell_centers, shell_volumes,
-             shape_array=None, scale_factor=1.0):
-    """PairCorrelationConstraint.__get_total_gr (PairCorrelationConstraints.py:126-169)."""
+             shape_array=None, scale_factor=1.0, refit=None):
+    """PairCorrelationConstraint.__get_total_gr (PairCorrelationConstraints.py:126-169); refit as in total_Gr,
+    fitted on G(r) = 4 pi r rho0 (g - 1) (:171-184)."""
     volume, rho0 = FLOAT_TYPE(volume), FLOAT_TYPE(rho0)
     gr = _weighted_sum(intra, inter, elements, n_per_element, weighting, volume, cast_D=False)
     gr /= shell_volumes
     if shape_array is not None:
         gr -= shape_array
+    if refit is not None:
+        expGr = (4. * PI * shell_centers * rho0) * (refit[0] - 1)
+        Gr_ = (4. * PI * shell_centers * rho0) * (gr - 1)
+        scale_factor = fit_scale_factor(expGr, Gr_, refit[1], refit[2], refit[3])
     if scale_factor != 1:
         scale_factor = FLOAT_TYPE(scale_factor)
         Gr = (4. * PI * shell_centers * rho0) * (gr - 1)
         Gr *= scale_factor
         gr = 1. + Gr / (4. * PI * shell_centers * rho0)
-    return gr
+    return gr if refit is None else (gr, FLOAT_TYPE(scale_factor))
 
 
 def Sq_from_Gr(Gr, gr2sq, reduced=False):
@@ -137,16 +146,21 @@ def Sq_from_Gr(Gr, gr2sq, reduced=False):
 
 
 def total_Sq(intra, inter, elements, n_per_element, weighting, volume, rho0, shell_centers, shell_volumes,
-             gr2sq, scale_factor=1.0, reduced=False, return_Gr=False):
-    """StructureFactorConstraint.__get_total_Sq (StructureFactorConstraints.py:780-822)."""
+             gr2sq, scale_factor=1.0, reduced=False, return_Gr=False, refit=None):
+    """StructureFactorConstraint.__get_total_Sq (StructureFactorConstraints.py:780-822); refit as in total_Gr,
+    fitted on S(Q)-1 against experimental-1 (:824-834; the reduced constraint inherits that override)."""
     volume, rho0 = FLOAT_TYPE(volume), FLOAT_TYPE(rho0)
     Gr = _weighted_sum(intra, inter, elements, n_per_element, weighting, volume, cast_D=False)
     Gr /= shell_volumes
     Gr = (FLOAT_TYPE(4.) * PI * shell_centers * rho0) * (Gr - 1)
     Sq = Sq_from_Gr(Gr, gr2sq, reduced=reduced)
+    if refit is not None:
+        scale_factor = fit_scale_factor(refit[0] - 1, Sq - 1, refit[1], refit[2], refit[3])
     if scale_factor != 1:
         scale_factor = FLOAT_TYPE(scale_factor)
         Sq = scale_factor * Sq if reduced else scale_factor * (Sq - 1) + 1
+    if refit is not None:
+        return Sq, FLOAT_TYPE(scale_factor)
     if return_Gr:
         return Sq, Gr
     return Sq

@@ -77,6 +77,7 @@ def describe(c, kind):
         d["qValues"] = np.asarray(g("experimentalQValues"), np.float32)
     d["dataWeights"] = np.zeros(0, np.float32) if c._usedDataWeights is None else np.asarray(c._usedDataWeights, np.float32)
     d["shapeArray"] = np.zeros(0, np.float32) if getattr(c, "_shapeArray", None) is None else np.asarray(c._shapeArray, np.float32)
+    d["adjustScaleFactor"] = np.array([c.adjustScaleFactorFrequency, c.adjustScaleFactorMinimum, c.adjustScaleFactorMaximum], np.float64)
     return d
 
 
@@ -88,7 +89,12 @@ def fit_total(c, kind, E):
     return np.asarray(getattr(c, fn)(c.data, rho0=E.numberDensity), np.float32)
 
 
+ONLY = set(sys.argv[1:])        # optional case names on the command line: regenerate just those
+
+
 def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sigma, out_dir):
+    if ONLY and name not in ONLY:
+        return
     box, basis, isPBC, mol, el, elements = arrays
     E = H.fake_engine(fullrmc, box, basis, isPBC, mol, el, elements)
     constraints = make_constraints(E)
@@ -108,7 +114,7 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
         out["c%d/start_total" % ci] = fit_total(c, kind, E)
     out["start_stdErr"] = np.array(start, np.float32)
     rbasis = np.linalg.inv(basis.astype(np.float64)) if isPBC else np.eye(3)
-    idx_log, moved_log, chi_log, acc_log, k_log = [], [], [], [], []
+    idx_log, moved_log, chi_log, acc_log, k_log, sf_log = [], [], [], [], [], []
     total_old = sum(float(c.standardError) for c, _ in constraints)
     for step in range(n_steps):
         idx = np.asarray(groups[int(rng.integers(0, len(groups)))], dtype=np.int32)
@@ -118,6 +124,7 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
             c.compute_before_move(realIndexes=idx, relativeIndexes=idx)
             c.compute_after_move(realIndexes=idx, relativeIndexes=idx, movedBoxCoordinates=moved)
         chis = [np.float32(c.afterMoveStandardError) for c, _ in constraints]
+        sf_log.append([np.float32(c._fittedScaleFactor) for c, _ in constraints])     # the scale factor this evaluation used
         total_new = sum(float(x) for x in chis)
         accept = total_new <= total_old or step % 5 == 4            # also exercise uphill accepts
         for c, _ in constraints:
@@ -133,9 +140,11 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
     out["steps/moved"] = np.array(moved_log, np.float32)
     out["steps/chi2_after"] = np.array(chi_log, np.float32)
     out["steps/accepted"] = np.array(acc_log, np.bool_)
+    out["steps/scale_used"] = np.array(sf_log, np.float32)
     for ci, (c, kind) in enumerate(constraints):
         out["c%d/final_intra" % ci], out["c%d/final_inter" % ci] = c.data["intra"].copy(), c.data["inter"].copy()
         out["c%d/final_stdErr" % ci] = np.float32(c.standardError)
+        out["c%d/final_scaleFactor" % ci] = np.float32(c.scaleFactor)
         out["c%d/final_total" % ci] = fit_total(c, kind, E)
     out["final_boxCoords"] = np.asarray(E.boxCoordinates, np.float32).copy()
     path = os.path.join(out_dir, "constraints_%s.npz" % name)
@@ -205,6 +214,31 @@ def main():
         return [(pdf, "PDF"), (sf, "SQ")]
     groups = [[3 * m, 3 * m + 1, 3 * m + 2] for m in range(n // 3)]
     run_case("synth", fullrmc, arrays, synth, groups, 30, 4, 0.25, out_dir)
+
+    # ---- scale-factor refit (Core/Constraint.py:1363-1423).  NiTi as shipped switches it on for both constraints
+    #      (Examples/atomicNiTi/run.py:102-103); a short frequency makes 40 steps cross several refit windows.
+    d = os.path.join(EX, "atomicNiTi")
+    arrays_niti = engine_arrays(*read_pdb(os.path.join(d, "system.pdb")))
+    def niti_sf(E):
+        cons = niti(E)
+        for c, _ in cons:
+            c.set_adjust_scale_factor((4, 0.8, 1.2))
+        return cons
+    nn = arrays_niti[0].shape[0]
+    run_case("niti_sf", fullrmc, arrays_niti, niti_sf, [[i] for i in range(nn)], 40, 11, 0.15, out_dir)
+
+    # synthetic: g(r) with data weights + full S(Q), refit every 3 accepted moves with a tight clip range
+    rng2 = np.random.default_rng(45)
+    def synth_sf(E):
+        r = (0.05 + 0.05 * np.arange(300)).astype(np.float32)
+        pcf = PairCorrelationConstraint(experimentalData=np.stack([r, 1 + rng2.normal(0, 0.2, 300).astype(np.float32)], 1).astype(np.float32),
+                                        weighting="atomicNumber", scaleFactor=0.97, dataWeights=rng2.random(300),
+                                        adjustScaleFactor=(3, 0.9, 1.02))
+        q = np.linspace(0.6, 14.0, 150).astype(np.float32)
+        sf = StructureFactorConstraint(experimentalData=np.stack([q, 1 + rng2.normal(0, 0.1, 150).astype(np.float32)], 1).astype(np.float32),
+                                       weighting="atomicNumber", scaleFactor=1.05, adjustScaleFactor=(3, 0.7, 1.3))
+        return [(pcf, "PCF"), (sf, "SQ")]
+    run_case("synth_sf", fullrmc, arrays, synth_sf, groups, 30, 5, 0.25, out_dir)
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ import pytest
 from oracle import epilogue as ep
 
 F32 = np.float32
-NAMES = ["niti", "thf", "siox", "synth"]
+NAMES = ["niti", "thf", "siox", "synth", "niti_sf", "synth_sf"]     # *_sf: scale-factor refit switched on
 
 
 def _load(golden_dir, name):
@@ -36,6 +36,8 @@ def _constraint_desc(g, ci):
     d["weighting"] = {str(p): F32(w) for p, w in zip(d["pairs"], d["pair_w"])}
     d["dataWeights"] = None if d["dataWeights"].shape[0] == 0 else d["dataWeights"]
     d["shapeArray"] = None if d["shapeArray"].shape[0] == 0 else d["shapeArray"]
+    adj = d.get("adjustScaleFactor")
+    d["adjust"] = (0, 0.0, 0.0) if adj is None else (int(adj[0]), F32(adj[1]), F32(adj[2]))
     return d
 
 
@@ -46,16 +48,22 @@ def _system(g):
     return elements, n_per
 
 
-def _oracle_total(d, intra, inter, elements, n_per, volume, rho0):
+def _oracle_total(d, intra, inter, elements, n_per, volume, rho0, sf=None, accepted=None):
+    """(total, scale factor used): the committed factor sf, or a refit when the constraint adjusts its scale
+    factor and accepted % frequency == 0 (get_adjusted_scale_factor, Core/Constraint.py:1397-1423)"""
     common = dict(elements=elements, n_per_element=n_per, weighting=d["weighting"], volume=volume, rho0=rho0,
                   shell_centers=d["shellCenters"], shell_volumes=d["shellVolumes"])
-    sf = float(d["scaleFactor"])
+    sf = float(d["scaleFactor"]) if sf is None else float(sf)
+    freq, lo, hi = d["adjust"]
+    refit = (d["experimental"], d["dataWeights"], lo, hi) if (freq and accepted is not None and accepted % freq == 0) else None
     if d["kind"] == "PDF":
-        return ep.total_Gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, **common)
-    if d["kind"] == "PCF":
-        return ep.total_gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, **common)
-    return ep.total_Sq(intra, inter, gr2sq=ep.gr2sq_matrix(d["qValues"], d["shellCenters"]), scale_factor=sf,
-                       reduced=(d["kind"] == "RSQ"), **common)
+        out = ep.total_Gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, refit=refit, **common)
+    elif d["kind"] == "PCF":
+        out = ep.total_gr(intra, inter, shape_array=d["shapeArray"], scale_factor=sf, refit=refit, **common)
+    else:
+        out = ep.total_Sq(intra, inter, gr2sq=ep.gr2sq_matrix(d["qValues"], d["shellCenters"]), scale_factor=sf,
+                          reduced=(d["kind"] == "RSQ"), refit=refit, **common)
+    return out if refit is not None else (out, F32(sf))
 
 
 @pytest.fixture
@@ -83,31 +91,40 @@ def test_oracle_restatement_reproduces_reference_classes(name, golden_dir, spill
                                                   maxDistance=d["maxDistance"], bin=d["bin"], histSize=int(d["histSize"]),
                                                   ncores=orc.max_threads())
         assert np.array_equal(hi, d["start_intra"]) and np.array_equal(he, d["start_inter"])
-        tot = _oracle_total(d, hi, he, elements, n_per, volume, rho0)
+        tot, _ = _oracle_total(d, hi, he, elements, n_per, volume, rho0, accepted=0)
         assert np.array_equal(tot, d["start_total"]), "constraint %d total differs from the reference class" % ci
         chi = ep.standard_error(d["experimental"], tot, d["dataWeights"])
         assert F32(chi) == F32(g["start_stdErr"][ci])
         data.append([hi, he])
     steps = g["steps/idx"].shape[0]
+    sfs = [F32(d["scaleFactor"]) for d in descs]          # committed scale factors
+    accepted = 0                                           # engine.accepted
     for s in range(steps):
         k = int(g["steps/k"][s])
         idx = g["steps/idx"][s, :k].astype(np.int32)
         moved = g["steps/moved"][s, :k]
         tmp = box.copy(); tmp[idx] = moved
-        staged = []
+        staged, used = [], []
         for ci, d in enumerate(descs):
             args = (basis, pbc, mol, el, len(elements), d["minDistance"], d["maxDistance"], d["bin"], int(d["histSize"]))
             bi, be = ep.move_delta(fns, idx, box, *args)
             ai, ae = ep.move_delta(fns, idx, tmp, *args)
             ni, ne = data[ci][0] - bi + ai, data[ci][1] - be + ae
-            chi = ep.standard_error(d["experimental"], _oracle_total(d, ni, ne, elements, n_per, volume, rho0), d["dataWeights"])
+            tot, sf_used = _oracle_total(d, ni, ne, elements, n_per, volume, rho0, sf=sfs[ci], accepted=accepted)
+            chi = ep.standard_error(d["experimental"], tot, d["dataWeights"])
             assert F32(chi) == F32(g["steps/chi2_after"][s, ci]), "step %d constraint %d" % (s, ci)
-            staged.append([ni, ne])
+            if "steps/scale_used" in g.files:
+                assert F32(sf_used) == F32(g["steps/scale_used"][s, ci]), "step %d constraint %d scale factor" % (s, ci)
+            staged.append([ni, ne]); used.append(F32(sf_used))
         if bool(g["steps/accepted"][s]):
-            data, box = staged, tmp
+            data, box, sfs = staged, tmp, used             # accept_move commits the factor the evaluation used
+            accepted += 1
     for ci, d in enumerate(descs):
         assert np.array_equal(data[ci][0], d["final_intra"]) and np.array_equal(data[ci][1], d["final_inter"])
-        assert np.array_equal(_oracle_total(d, data[ci][0], data[ci][1], elements, n_per, volume, rho0), d["final_total"])
+        tot, _ = _oracle_total(d, data[ci][0], data[ci][1], elements, n_per, volume, rho0, sf=sfs[ci], accepted=accepted)
+        assert np.array_equal(tot, d["final_total"])
+        if "c%d/final_scaleFactor" % ci in g.files:
+            assert F32(sfs[ci]) == F32(g["c%d/final_scaleFactor" % ci])
     assert np.array_equal(box, g["final_boxCoords"])
 
 
@@ -136,7 +153,8 @@ def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
                                                int(d["histSize"]), d["shellCenters"], d["shellVolumes"], d["weighting"],
                                                dataWeights=d["dataWeights"], shapeArray=d["shapeArray"],
                                                scaleFactor=float(d["scaleFactor"]),
-                                               qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None)))
+                                               qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None,
+                                               adjustScaleFactor=d["adjust"])))
     for ci, (d, c) in enumerate(cons):
         data, err = c.compute_data()
         assert np.array_equal(data["intra"], d["start_intra"]) and np.array_equal(data["inter"], d["start_inter"])
@@ -152,12 +170,20 @@ def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
             c.compute_after_move(idx, idx, moved)
         for ci, (d, c) in enumerate(cons):
             assert F32(c.afterMoveStandardError) == F32(g["steps/chi2_after"][s, ci]), "step %d constraint %d" % (s, ci)
+            if "steps/scale_used" in g.files:
+                assert F32(c.fittedScaleFactor) == F32(g["steps/scale_used"][s, ci]), "step %d constraint %d scale factor" % (s, ci)
         for d, c in cons:
             (c.accept_move if bool(g["steps/accepted"][s]) else c.reject_move)(idx, idx)
+    refits = any(d["adjust"][0] for d, _ in cons)
     for ci, (d, c) in enumerate(cons):
         data = c.data
         assert np.array_equal(data["intra"], d["final_intra"]) and np.array_equal(data["inter"], d["final_inter"])
-        assert np.array_equal(c.get_constraint_total(), d["final_total"])
         assert F32(c.standardError) == F32(d["final_stdErr"])
+        if "c%d/final_scaleFactor" % ci in g.files:
+            assert F32(c.scaleFactor) == F32(g["c%d/final_scaleFactor" % ci])
+        if refits:
+            # the recorded final total is a fresh evaluation at the final accepted count (it may refit): do the same
+            c.compute_data(update=False)
+        assert np.array_equal(c.get_constraint_total(), d["final_total"])
     assert np.array_equal(backend.store.get_coords(), g["final_boxCoords"])
     backend.close()
