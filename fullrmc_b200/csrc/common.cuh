@@ -77,6 +77,22 @@ struct GridParams {
 // global default for new grids / stateless calls (frmc_set_edge_spill)
 extern int g_edge_spill;
 
+// Lower bound on the reference's computed distance between any atom of block I and any atom of block J.
+// Per axis the (periodic) separation of two points is at least |wrap(centre difference)| - half widths;
+// the reference's per-axis round() wrap yields exactly that periodic separation.  Diagonal basis / no PBC:
+// the axis bounds combine Euclidean-wise (h = |L_cc| or 1).  General basis: |r| >= |f_c| / |column c of
+// B^-1| for every axis, so the largest single-axis bound is used (h_c = that reciprocal height).
+// Everything errs on the near side: eps margins on the gaps, 1e-4 relative slack on the cut.
+struct CullParams {
+    float h[3];
+    float t2cut;
+    int pbc, euclid, enabled, pad;
+};
+
+// culling parameters for a geometry mode and the largest d^2 of interest (host; fullhist.cu)
+CullParams make_cull(const Lattice &L, int mode, const GridParams &g);
+extern int g_no_cull;   // debug: sweep every block pair (frmc_set_block_culling)
+
 // smallest non-negative fp32 t such that fl(sqrtf(t)) >= r
 float sqrt_threshold(float r);
 
@@ -167,6 +183,26 @@ __device__ __forceinline__ void diff3(float px, float py, float pz, float cx, fl
     } else {
         rx = dx; ry = dy; rz = dz;
     }
+}
+
+__device__ __forceinline__ bool blocks_far(const float4 loI, const float4 hiI, const float4 loJ, const float4 hiJ,
+                                           const CullParams &cp)
+{
+    if (hiI.w != 0.f || hiJ.w != 0.f) return true;          // no finite atom on one side: nothing can be in range
+    const float eps = loI.w + loJ.w;
+    const float li[3] = {loI.x, loI.y, loI.z}, ui[3] = {hiI.x, hiI.y, hiI.z};
+    const float lj[3] = {loJ.x, loJ.y, loJ.z}, uj[3] = {hiJ.x, hiJ.y, hiJ.z};
+    float s = 0.f, m = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float half = 0.5f * ((ui[c] - li[c]) + (uj[c] - lj[c]));
+        float d = 0.5f * ((lj[c] + uj[c]) - (li[c] + ui[c]));
+        if (cp.pbc) d -= rintf(d);
+        const float gap = fmaxf(fabsf(d) - half - eps, 0.f) * cp.h[c];
+        s += gap * gap;
+        m = fmaxf(m, gap * gap);
+    }
+    return (cp.euclid ? s : m) > cp.t2cut;
 }
 
 __device__ __forceinline__ bool in_range(float d2, const GridParams &g)

@@ -20,7 +20,7 @@
 namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
-int g_no_cull = 0;   // debug: sweep every block pair (frmc_set_block_culling)
+int g_no_cull = 0;
 
 // ------------------------------------------------------------------ host: layout + work list
 // k-d ordering of one element's atoms: split the longest box axis at a record count that is a multiple
@@ -427,38 +427,6 @@ __global__ void block_bbox_kernel(const float4 *__restrict__ atoms, int nblocks,
         bbox[2 * blk + 0] = make_float4(blo[0], blo[1], blo[2], 1e-6f * (1.0f + bmax));
         bbox[2 * blk + 1] = make_float4(bhi[0], bhi[1], bhi[2], (blo[0] <= bhi[0]) ? 0.f : 1.f);
     }
-}
-
-// Lower bound on the reference's computed distance between any atom of block I and any atom of block J.
-// Per axis the (periodic) separation of two points is at least |wrap(centre difference)| - half widths;
-// the reference's per-axis round() wrap yields exactly that periodic separation.  Diagonal basis / no PBC:
-// the axis bounds combine Euclidean-wise (h = |L_cc| or 1).  General basis: |r| >= |f_c| / |column c of
-// B^-1| for every axis, so the largest single-axis bound is used (h_c = that reciprocal height).
-// Everything errs on the near side: eps margins on the gaps, 1e-4 relative slack on the cut.
-struct CullParams {
-    float h[3];
-    float t2cut;
-    int pbc, euclid, enabled, pad;
-};
-
-__device__ __forceinline__ bool blocks_far(const float4 loI, const float4 hiI, const float4 loJ, const float4 hiJ,
-                                           const CullParams &cp)
-{
-    if (hiI.w != 0.f || hiJ.w != 0.f) return true;          // no finite atom on one side: nothing can be in range
-    const float eps = loI.w + loJ.w;
-    const float li[3] = {loI.x, loI.y, loI.z}, ui[3] = {hiI.x, hiI.y, hiI.z};
-    const float lj[3] = {loJ.x, loJ.y, loJ.z}, uj[3] = {hiJ.x, hiJ.y, hiJ.z};
-    float s = 0.f, m = 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float half = 0.5f * ((ui[c] - li[c]) + (uj[c] - lj[c]));
-        float d = 0.5f * ((lj[c] + uj[c]) - (li[c] + ui[c]));
-        if (cp.pbc) d -= rintf(d);
-        const float gap = fmaxf(fabsf(d) - half - eps, 0.f) * cp.h[c];
-        s += gap * gap;
-        m = fmaxf(m, gap * gap);
-    }
-    return (cp.euclid ? s : m) > cp.t2cut;
 }
 
 CullParams make_cull(const Lattice &L, int mode, const GridParams &g)

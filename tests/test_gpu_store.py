@@ -202,6 +202,69 @@ def test_wrap_mode_switch_when_a_move_leaves_the_unit_cell(orc):
     store.close()
 
 
+def _large_sparse_case(kind):
+    """many blocks of the k-d ordered store and a maxDistance far below the cell size (the regime in which the
+    full-histogram kernel culls most block pairs); molecules of 5, two elements"""
+    rng = np.random.default_rng(404)
+    n = 26000
+    el = rng.integers(0, 2, n)
+    mol = np.arange(n) // 5
+    if kind == "ortho":
+        return C._case("sparse_ortho", rng.random((n, 3), dtype=F32), np.diag([110.0, 104.0, 98.0]), True, mol, el, 2, 0.0, 6.0, 0.05, 120)
+    if kind == "tri_unwrapped":
+        box = (rng.random((n, 3), dtype=F32) * F32(2.6) - F32(0.8)).astype(F32)
+        return C._case("sparse_tri", box, np.array([[110, 0, 0], [21, 100, 0], [-17, 25, 96]]), True, mol, el, 2, 0.3, 6.3, 0.05, 120)
+    box = (rng.random((n, 3), dtype=F32) * F32(100.0) - F32(30.0)).astype(F32)
+    return C._case("sparse_ibc", box, np.eye(3), False, mol, el, 2, 0.0, 6.0, 0.05, 120)
+
+
+@pytest.mark.parametrize("kind", ["ortho", "tri_unwrapped", "non_periodic"])
+def test_move_sequences_on_large_sparse_systems(kind, orc):
+    """long jumps, seam crossings and molecule moves in a store whose compute_data culls most block pairs: the
+    running histograms and chi^2 must stay identical to the reference sequence, through both resolve paths"""
+    case = _large_sparse_case(kind)
+    rng = np.random.default_rng(9)
+    store, oracles = _build(case, ["PDF", "SQ"], rng)
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    box = case["boxCoords"].copy()
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    store.compute_data()
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, ncores=orc.max_threads(), **kw)
+    span = F32(1.0) if case["isPBC"] else F32(100.0)
+    previous = None
+    for step in range(36):
+        idx = C.group_for(case, rng)
+        jump = (0.45 if step % 4 == 0 else 0.004) * span            # every fourth move is a long jump (often across the seam)
+        moved = (box[idx] + rng.normal(0, jump, (1, 3)).astype(F32)).astype(F32)
+        args = (kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"], kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+        bi, be = ep.move_delta(fns, idx, box, *args)
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, *args)
+        new_i, new_e = data_i - bi + ai, data_e - be + ae
+        if step < 18:
+            chi2 = store.propose(idx, moved)                         # explicit resolve kernels, state exported every step
+            _check_models(store, oracles, new_i, new_e, chi2, staged=True)
+            accept = step % 3 != 2
+            (store.accept if accept else store.reject)()
+            if accept:
+                data_i, data_e, box = new_i, new_e, tmp
+            gi, ge = store.export_data(0)
+            assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e), "running histograms diverged at step %d" % step
+        else:
+            chi2 = store.step(previous, idx, moved).copy()           # fused path: the resolve rides in the next launch
+            for m, (total, exp, dw) in enumerate(oracles):
+                assert F32(chi2[m]) == F32(ep.standard_error(exp, total(new_i, new_e), dw)), "step %d model %d" % (step, m)
+            previous = step % 3 != 2
+            if previous:
+                data_i, data_e, box = new_i, new_e, tmp
+    (store.accept if previous else store.reject)()
+    gi, ge = store.export_data(0)
+    assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e)
+    assert np.array_equal(store.get_coords(), box)
+    store.close()
+
+
 def test_state_machine_errors():
     from fullrmc_b200.store import DeviceStore
     case = CASES["tiny_13"]
