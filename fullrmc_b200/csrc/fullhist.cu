@@ -240,7 +240,11 @@ void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, i
                         if (j0 < i0) j0 = i0;             // q > p >= i0: records before the I-tile never pair with it
                         tri = (j0 < i1) ? 1 : 0;          // ranges overlap: per-pair p<q test needed
                     }
-                    if ((serial++ % nshards) != shard) continue;
+                    // rows are dealt out boustrophedon (0..S-1, S-1..0, ...): the J range of a same-element row
+                    // shrinks linearly with the tile index, and plain round-robin would hand shard 0 the larger row
+                    // of every group of S
+                    const int64_t pos = serial++ % (2 * (int64_t)nshards);
+                    if ((pos < nshards ? pos : 2 * (int64_t)nshards - 1 - pos) != shard) continue;
                     WorkItem w;
                     w.i0 = (int32_t)i0; w.ni = (int32_t)((i1 - i0) / SEG_PAD);
                     w.j0 = (int32_t)j0; w.j1 = (int32_t)j1;
@@ -461,14 +465,81 @@ CullParams make_cull(const Lattice &L, int mode, const GridParams &g)
     return cp;
 }
 
+// ------------------------------------------------------------------ surviving block pairs, built on the device
+// A ROW (host, layout.h:WorkItem) is one I tile against the whole J range of one element pair.  One warp
+// per row tests the row's J blocks 32 at a time against the tile's boxes and writes the survivors; rows are
+// then cut into ITEMS of at most PAIR_ITEM_BLOCKS surviving blocks, the units the sweep kernel's atomic
+// counter hands out.  Items therefore cost about the same and none is empty: no CTA walks culled work, and
+// the tail of a launch is one item long (what limited the 8-GPU efficiency of the chunked list).
+// Two passes (count, exclusive scan, fill) size the lists exactly; the host reads the two totals back.
+static const int PAIR_ITEM_BLOCKS = 8;
+
+__global__ void pair_list_kernel(const WorkItem *__restrict__ rows, int n_rows, const float4 *__restrict__ bbox, CullParams cp,
+                                 int *__restrict__ row_cnt, int *__restrict__ row_items, const int *__restrict__ row_start,
+                                 const int *__restrict__ row_item_start, uint32_t *__restrict__ entries, int4 *__restrict__ items,
+                                 int fill)
+{
+    const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const WorkItem w = rows[r];
+    const int bi = w.i0 / SEG_PAD, jb0 = w.j0 / SEG_PAD, jb1 = w.j1 / SEG_PAD;
+    const unsigned lt = (1u << lane) - 1u;
+    const int base = fill ? row_start[r] : 0;
+    int cnt = 0;
+    for (int jr = jb0; jr < jb1; jr += 32) {
+        const int bj = jr + lane;
+        bool near = bj < jb1;
+        if (near && cp.enabled) {
+            const float4 loJ = bbox[2 * bj], hiJ = bbox[2 * bj + 1];
+            bool far = true;
+            for (int t = 0; t < w.ni; ++t) far = far && blocks_far(bbox[2 * (bi + t)], bbox[2 * (bi + t) + 1], loJ, hiJ, cp);
+            near = !far;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, near);
+        if (fill && near) entries[base + cnt + __popc(bal & lt)] = (uint32_t)bj;
+        cnt += __popc(bal);
+    }
+    const int n_it = (cnt + PAIR_ITEM_BLOCKS - 1) / PAIR_ITEM_BLOCKS;
+    if (!fill) {
+        if (lane == 0) { row_cnt[r] = cnt; row_items[r] = n_it; }
+    } else {
+        const int ibase = row_item_start[r];
+        for (int j = lane; j < n_it; j += 32)
+            items[ibase + j] = make_int4(r, base + j * PAIR_ITEM_BLOCKS, min(PAIR_ITEM_BLOCKS, cnt - j * PAIR_ITEM_BLOCKS), 0);
+    }
+}
+
+// exclusive scan of two int arrays of length n by ONE CTA of 1024 threads; totals[0], totals[1] receive the sums
+__global__ void __launch_bounds__(1024) scan2_kernel(const int *__restrict__ a, const int *__restrict__ b, int n,
+                                                     int *__restrict__ sa, int *__restrict__ sb, int *__restrict__ totals)
+{
+    __shared__ int pa[1024], pb[1024];
+    const int t = threadIdx.x;
+    const int chunk = (n + 1023) / 1024;
+    const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    int xa = 0, xb = 0;
+    for (int i = lo; i < hi; ++i) { xa += a[i]; xb += b[i]; }
+    pa[t] = xa; pb[t] = xb;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int va = (t >= o) ? pa[t - o] : 0, vb = (t >= o) ? pb[t - o] : 0;
+        __syncthreads();
+        pa[t] += va; pb[t] += vb;
+        __syncthreads();
+    }
+    int ra = pa[t] - xa, rb = pb[t] - xb;       // exclusive prefix of this thread's chunk
+    for (int i = lo; i < hi; ++i) { sa[i] = ra; sb[i] = rb; ra += a[i]; rb += b[i]; }
+    if (t == 1023) { totals[0] = pa[t]; totals[1] = pb[t]; }
+}
+
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
 // stats[0] += edge overflow events, stats[1] += (SEG_PAD I records x 32 J records) units actually swept.
 template <int MODE, int R>
 __global__ void __launch_bounds__(256, (R == 1) ? 5 : 3)
 full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const float4 *__restrict__ bbox,
-                 const WorkItem *__restrict__ items, int n_items, int *__restrict__ next_item, Lattice L,
-                 GridParams g, CullParams cp, int nblocks, int nEl, unsigned long long *__restrict__ counts,
-                 unsigned long long *__restrict__ stats)
+                 const WorkItem *__restrict__ rows, const uint32_t *__restrict__ entries, const int4 *__restrict__ items,
+                 int n_items, int *__restrict__ next_item, Lattice L, GridParams g, CullParams cp, int nblocks, int nEl,
+                 unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sJ = reinterpret_cast<float4 *>(smem_raw);
@@ -497,7 +568,8 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         const int it = s_item;
         WorkItem w;
         w.ea = -1; w.eb = -1;
-        if (it < n_items) w = items[it];
+        int4 item = make_int4(0, 0, 0, 0);    // {row, first entry, surviving J blocks (<= PAIR_ITEM_BLOCKS), -}
+        if (it < n_items) { item = items[it]; w = rows[item.x]; }
         const int slab = (it < n_items) ? w.ea * nEl + w.eb : -2;
         // The counters belong to one element pair at a time; the item list is ordered by pair, so this
         // flush happens a handful of times per CTA (32-bit counters: also before 2^31 pairs pile up).
@@ -539,57 +611,43 @@ full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ 
         const bool cross = (w.ea != w.eb);
         const int bi = w.i0 / SEG_PAD;
 
-        // J blocks of this item, 32 per round: lane l tests block l against the I blocks (every warp
-        // computes the same survivor mask, so the CTA stays in step without exchanging it)
-        for (int jr = w.j0; jr < w.j1; jr += 32 * SEG_PAD) {
-            const int jb = jr + lane * SEG_PAD;
-            bool near = jb < w.j1;
-            if (near && cp.enabled) {
-                const int bj = jb / SEG_PAD;
-                const float4 loJ = bbox[2 * bj], hiJ = bbox[2 * bj + 1];
-                bool far = true;
+        // the item's surviving J blocks, staged two at a time
+        const bool same_el = (w.ea == w.eb);
+        for (int e = 0; e < item.z; e += 2) {
+            const int nb = (e + 1 < item.z) ? 2 : 1;
+            const int jb0 = (int)entries[item.y + e] * SEG_PAD;
+            const int jb1 = (nb == 2) ? (int)entries[item.y + e + 1] * SEG_PAD : jb0;
+            __syncthreads();                  // previous staged blocks fully consumed
+            sJ[tid] = atoms[jb0 + tid]; sO[tid] = orig[jb0 + tid];
+            if (nb == 2) { sJ[SEG_PAD + tid] = atoms[jb1 + tid]; sO[SEG_PAD + tid] = orig[jb1 + tid]; }
+            __syncthreads();
+            // second level: lanes 0-7 / 8-15 test the 32-record sub-blocks of the two staged blocks (every warp
+            // computes the same mask, so the CTA stays in step without exchanging it)
+            unsigned sub = 0xFFFFu;
+            if (cp.enabled) {
+                const int which = lane >> 3, sb = lane & 7;
+                bool nr = false;
+                if (which < nb) {
+                    const size_t at = 2 * ((size_t)nblocks + (size_t)((which ? jb1 : jb0) / SEG_PAD) * (SEG_PAD / 32) + sb);
+                    const float4 loJ = bbox[at], hiJ = bbox[at + 1];
+                    bool far = true;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
-                near = !far;
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, near);
-            while (mask) {
-                const int jb0 = jr + (__ffs(mask) - 1) * SEG_PAD;
-                mask &= mask - 1;
-                int nb = 1, jb1 = jb0;
-                if (mask) { jb1 = jr + (__ffs(mask) - 1) * SEG_PAD; mask &= mask - 1; nb = 2; }
-                __syncthreads();              // previous staged blocks fully consumed
-                sJ[tid] = atoms[jb0 + tid]; sO[tid] = orig[jb0 + tid];
-                if (nb == 2) { sJ[SEG_PAD + tid] = atoms[jb1 + tid]; sO[SEG_PAD + tid] = orig[jb1 + tid]; }
-                __syncthreads();
-                // second level: lanes 0-7 / 8-15 test the 32-record sub-blocks of the two staged blocks
-                unsigned sub = 0xFFFFu;
-                if (cp.enabled) {
-                    const int which = lane >> 3, sb = lane & 7;
-                    bool nr = false;
-                    if (which < nb) {
-                        const size_t at = 2 * ((size_t)nblocks + (size_t)((which ? jb1 : jb0) / SEG_PAD) * (SEG_PAD / 32) + sb);
-                        const float4 loJ = bbox[at], hiJ = bbox[at + 1];
-                        bool far = true;
-#pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
-                        nr = !far;
-                    }
-                    sub = __ballot_sync(0xffffffffu, nr);
+                    for (int r = 0; r < R; ++r)
+                        if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
+                    nr = !far;
                 }
-                if (nb == 1) sub &= 0xFFu;
+                sub = __ballot_sync(0xffffffffu, nr);
+            }
+            if (nb == 1) sub &= 0xFFu;
 #pragma unroll 1
-                for (int b = 0; b < nb; ++b) {
-                    const int jbb = b ? jb1 : jb0;
-                    const bool tri = w.tri && jbb < w.i0 + w.ni * SEG_PAD;
-                    sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, sI, sIO, w.i0, tri, cross, L, g,
-                                         (sub >> (8 * b)) & 0xFFu, lq, sh, ov, sp);
-                }
-                since_flush += (unsigned)(nb * w.ni);
-                swept += (unsigned)(__popc(sub & 0xFFFFu) * w.ni);
+            for (int b = 0; b < nb; ++b) {
+                const int jbb = b ? jb1 : jb0;
+                const bool tri = same_el && jbb < w.i0 + w.ni * SEG_PAD;      // J block inside the I tile: only p < q counts
+                sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, sI, sIO, w.i0, tri, cross, L, g,
+                                     (sub >> (8 * b)) & 0xFFu, lq, sh, ov, sp);
             }
+            since_flush += (unsigned)(nb * w.ni);
+            swept += (unsigned)(__popc(sub & 0xFFFFu) * w.ni);
         }
     }
     if (ov) atomicAdd(&stats[0], ov);
@@ -615,8 +673,9 @@ size_t full_hist_smem_bytes(int hs, int R)
 
 template <int MODE, int R>
 static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms, const uint32_t *orig, const float4 *bbox,
-                         const WorkItem *items, int n_items, int *next_item, const Lattice &L, const GridParams &g,
-                         const CullParams &cp, int nblocks, int nEl, unsigned long long *counts, unsigned long long *stats)
+                         const WorkItem *rows, const uint32_t *entries, const int4 *items, int n_items, int *next_item,
+                         const Lattice &L, const GridParams &g, const CullParams &cp, int nblocks, int nEl,
+                         unsigned long long *counts, unsigned long long *stats)
 {
     size_t smem = full_hist_smem_bytes(g.hs, R);
     FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "histSize %d needs %zu B of shared memory per CTA (limit 200 KiB)", g.hs, smem);
@@ -627,29 +686,72 @@ static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms,
     if (per_sm < 1) per_sm = 1;
     int grid = std::min(n_items, sm_count * per_sm);
     if (grid < 1) return FRMC_OK;
-    kern<<<grid, 256, smem, stream>>>(atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
+    kern<<<grid, 256, smem, stream>>>(atoms, orig, bbox, rows, entries, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
     FRMC_LAUNCH_CHECK();
     return FRMC_OK;
 }
 
-// Launch the block-box pass and the tiled kernel on prepared device arrays.  next_item must be zeroed
-// by the caller (stream-ordered) before every launch; bbox is scratch for 18 float4 per SEG_PAD block;
-// stats[0] accumulates edge-overflow events, stats[1] swept block pairs.
+// grow-only device buffer owned by the caller's PairLists
+template <typename T>
+static int ensure_capacity(T **buf, size_t *cap, size_t need, cudaStream_t stream)
+{
+    if (*cap >= need && *buf) return FRMC_OK;
+    if (*buf) { FRMC_CUDA(cudaStreamSynchronize(stream)); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    const size_t want = need + need / 4 + 1024;
+    FRMC_CUDA(cudaMalloc((void **)buf, sizeof(T) * want));
+    *cap = want;
+    return FRMC_OK;
+}
+
+void PairLists::release()
+{
+    cudaFree(row_ints); cudaFree(entries); cudaFree(items);
+    row_ints = nullptr; entries = nullptr; items = nullptr; row_cap = entries_cap = items_cap = 0;
+}
+
+// Box pass, surviving-pair lists, then the sweep, on prepared device arrays.  next_item must be zeroed by the
+// caller (stream-ordered) before every launch; bbox is scratch for 18 float4 per SEG_PAD block; lists holds
+// the grow-only list buffers; stats[0] accumulates edge-overflow events, stats[1] swept (256 x 32) units.
+// Synchronises the stream once (the list sizes come back to the host).
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     int64_t npad, float4 *bbox, const WorkItem *items, int n_items, int *next_item, const Lattice &L,
-                     const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
+                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
+                     const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
     CullParams cp = make_cull(L, mode, g);
     if (g_no_cull) cp.enabled = 0;
     const int nblocks = (int)(npad / SEG_PAD);
-    if (cp.enabled && nblocks > 0) {
+    if (n_rows <= 0 || nblocks <= 0) return FRMC_OK;
+    if (cp.enabled) {
         block_bbox_kernel<<<(nblocks * 32 + 255) / 256, 256, 0, stream>>>(atoms, nblocks, cp.pbc, bbox);
         FRMC_LAUNCH_CHECK();
     }
+    // row scratch: cnt, items, start, item_start [n_rows each] + 2 totals
+    int rc = ensure_capacity(&lists.row_ints, &lists.row_cap, (size_t)4 * n_rows + 2, stream);
+    if (rc) return rc;
+    int *row_cnt = lists.row_ints, *row_items = row_cnt + n_rows, *row_start = row_items + n_rows,
+        *row_item_start = row_start + n_rows, *totals = row_item_start + n_rows;
+    const int list_grid = (int)(((long long)n_rows * 32 + 255) / 256);
+    pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, nullptr, nullptr, nullptr, nullptr, 0);
+    FRMC_LAUNCH_CHECK();
+    scan2_kernel<<<1, 1024, 0, stream>>>(row_cnt, row_items, n_rows, row_start, row_item_start, totals);
+    FRMC_LAUNCH_CHECK();
+    int h_tot[2] = {0, 0};
+    FRMC_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, stream));
+    FRMC_CUDA(cudaStreamSynchronize(stream));
+    FRMC_REQUIRE(h_tot[0] >= 0 && h_tot[1] >= 0, FRMC_ELIMIT, "more than 2^31 surviving block pairs");
+    lists.n_entries = h_tot[0]; lists.n_items = h_tot[1];
+    if (h_tot[1] == 0) return FRMC_OK;
+    rc = ensure_capacity(&lists.entries, &lists.entries_cap, (size_t)h_tot[0], stream);
+    if (rc) return rc;
+    rc = ensure_capacity(&lists.items, &lists.items_cap, (size_t)h_tot[1], stream);
+    if (rc) return rc;
+    pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, row_start, row_item_start,
+                                                    lists.entries, lists.items, 1);
+    FRMC_LAUNCH_CHECK();
 #define FH_CASE(M)                                                                                         \
     case M:                                                                                                \
-        return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats) \
-                        : launch_full_t<M, 1>(stream, sm_count, atoms, orig, bbox, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
+        return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, bbox, rows, lists.entries, lists.items, lists.n_items, next_item, L, g, cp, nblocks, nEl, counts, stats) \
+                        : launch_full_t<M, 1>(stream, sm_count, atoms, orig, bbox, rows, lists.entries, lists.items, lists.n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
     switch (mode) {
         FH_CASE(MODE_IBC)
         FH_CASE(MODE_ORTHO_FAST)
@@ -683,25 +785,15 @@ bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[
     return frac < 0.5;
 }
 
-// Tile-shape heuristic: R register atoms per thread (I-tile = 256*R) and the J-chunk length, chosen so
-// that there are enough work items to balance sm_count x occupancy CTAs.  R = 4 amortises the shared-
+// Tile-shape heuristic: R register atoms per thread (I-tile = 256*R).  R = 4 amortises the shared-
 // memory load of a J record over four pairs (23.4 issue slots per pair instead of 26) and is right when
 // every block pair has to be swept; when culling bites, R = 1 keeps the culled unit at one 256-atom block
 // (about 2.5x fewer pairs swept than with a 1024-atom I-tile).
 void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ)
 {
+    (void)sm_count; (void)nshards;
     R = (npad >= 32768 && !sparse) ? 4 : 1;
-    const double target_items = 16.0 * sm_count * 4;
-    double ti = 256.0 * R;
-    double cj = (double)npad * (double)npad / (2.0 * ti * target_items);
-    int64_t c = (int64_t)(cj / JS) * JS;
-    if (c < JS) c = JS;
-    if (c > 16384) c = 16384;
-    // culled items vary in cost (0 .. chunkJ/256 block sweeps); with the list split over several GPUs a
-    // shorter chunk trims the tail (measured at 8 GPUs: 4.27 -> 4.02 ms; costs 1.7 % on one GPU)
-    if (sparse && nshards >= 4 && c > 4096) c = 4096;
-    if (npad < 8192) c = 256;   // tiny systems: finest split
-    chunkJ = c;
+    chunkJ = (int64_t)1 << 40;      // a row of the pair list spans the whole J range of its element pair
 }
 
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2)
@@ -800,7 +892,9 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     }
     if (!items.empty()) {
         FRMC_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
-        rc = full_hist_launch(c->stream, c->sm_count, mode, R, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), d_next, L, g, nEl, d_counts, d_ov);
+        static PairLists stateless_lists[64];          // per device, grow-only, like the context's scratch buffers
+        rc = full_hist_launch(c->stream, c->sm_count, mode, R, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(),
+                              stateless_lists[c->dev & 63], d_next, L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);

@@ -22,6 +22,7 @@
 #pragma once
 #include <cstdint>
 #include <vector>
+#include <cuda_runtime.h>
 
 namespace frmc {
 
@@ -45,15 +46,26 @@ struct HostLayout {
 // isPBC selects how a coordinate maps to a cell (fractional part vs. position inside the bounds).
 int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC, HostLayout &out);
 
-// One unit of full-histogram work: I-tile [i0, i0 + 256*ni) x J-range [j0, j1) (padded positions).
-// ea/eb are the (segment) elements of the two ranges; when ea == eb only pairs p<q count.
+// One ROW of full-histogram work: I-tile [i0, i0 + 256*ni) x J-range [j0, j1) (padded positions; with
+// chunkJ = "everything" the whole J range of the element pair).  ea/eb are the (segment) elements of the
+// two ranges; when ea == eb only pairs p<q count.  The device cuts rows into items of surviving blocks.
 struct WorkItem {
     int32_t i0, ni, j0, j1;
     int32_t ea, eb, tri, pad;
 };
 
-// Builds the upper-triangle work list, ordered by element pair (a CTA walking it flushes its
-// shared-memory counters only when the pair changes); items with index % nshards == shard are kept.
+// Builds the upper-triangle row list, ordered by element pair (a CTA walking it flushes its
+// shared-memory counters only when the pair changes); rows with index % nshards == shard are kept.
 void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, int nshards, std::vector<WorkItem> &items);
+
+// Device-side lists of surviving block pairs (fullhist.cu), grow-only, owned by whoever launches the kernel.
+struct PairLists {
+    int *row_ints = nullptr;        // [4*n_rows + 2] count / items / start / item start per row + two totals
+    uint32_t *entries = nullptr;    // surviving J block of every (row, k)
+    int4 *items = nullptr;          // {row, first entry, blocks, -}
+    size_t row_cap = 0, entries_cap = 0, items_cap = 0;
+    int n_entries = 0, n_items = 0; // of the last launch
+    void release();
+};
 
 }  // namespace frmc

@@ -18,13 +18,16 @@
 #include <cstring>
 #include <vector>
 #include <immintrin.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     int64_t npad, float4 *bbox, const WorkItem *items, int n_items, int *next_item, const Lattice &L,
-                     const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
+                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
+                     const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
 void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ);
 bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
@@ -972,7 +975,8 @@ struct frmc_store {
     std::vector<int32_t> h_mol, h_el;
     float4 *d_atoms = nullptr;
     uint32_t *d_orig = nullptr;
-    WorkItem *d_items = nullptr;
+    WorkItem *d_items = nullptr;     // rows of the pair list (I tile x J range of an element pair)
+    PairLists lists;                 // device-built surviving block pairs, cut into items
     int n_items = 0, R = 1;
     int items_shard = -1, items_nshards = -1, items_sparse = -1;   // which slice / tiling of the work list d_items holds
     int64_t chunkJ = 256;
@@ -1001,6 +1005,10 @@ struct frmc_store {
     float prop_lo[3], prop_hi[3];
     int state = 0;                   // 0 idle, 1 proposal staged
     float chi2_staged[FRMC_MAX_MODELS];
+    // host-side phase timers of frmc_propose (FRMC_STEP_TIMING=1): launch call, wait for chi2, whole call; printed at destroy
+    bool step_timing = false;
+    double t_launch = 0, t_wait = 0, t_call = 0;
+    unsigned long long n_calls = 0;
     unsigned long long accepted = 0;  // the engine's count of accepted moves (refit schedule, Core/Constraint.py:1418-1422)
     float chi2_committed[FRMC_MAX_MODELS];
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
@@ -1408,6 +1416,7 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     s->h_mol.assign(mol, mol + n);
     s->h_el.assign(el, el + n);
     memset(&s->prop_in, 0, sizeof(s->prop_in));
+    s->step_timing = getenv("FRMC_STEP_TIMING") != nullptr;
     auto fail = [&](const char *what) -> frmc_store * {
         std::string msg = std::string(what) + ": " + frmc_last_error();
         frmc_store_destroy(s);
@@ -1439,6 +1448,9 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
 
 void frmc_store_destroy(frmc_store *s)
 {
+    if (s && s->step_timing && s->n_calls)
+        fprintf(stderr, "[step timing] %llu proposals: launch call %.2f us, wait for chi2 %.2f us (per proposal)\n", s->n_calls,
+                s->t_launch / s->n_calls, s->t_wait / s->n_calls);
     if (!s) return;
     cudaSetDevice(s->dev);
     if (s->stream) cudaStreamSynchronize(s->stream);
@@ -1447,6 +1459,7 @@ void frmc_store_destroy(frmc_store *s)
     }
     for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); cudaFree(g.dev.tot); cudaFree(g.dev.stot); }
     cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next);
+    s->lists.release();
     cudaFree(s->d_overflow); cudaFree(s->d_bbox); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps); cudaFree(s->d_bars);
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
@@ -1658,7 +1671,7 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
             cudaEvent_t t0 = timing_begin(s);
             FRMC_CUDA(cudaMemsetAsync(s->d_overflow + 1, 0, sizeof(unsigned long long), s->stream));
             rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->R, s->d_atoms, s->d_orig, s->npad, s->d_bbox, s->d_items,
-                                  s->n_items, s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
+                                  s->n_items, s->lists, s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
             if (rc) return rc;
             timing_end(s, TIME_FULL, t0);
         }
@@ -1719,10 +1732,19 @@ int frmc_propose(frmc_store *s, const int32_t *indexes, int k, const float *move
     FRMC_CUDA(cudaSetDevice(s->dev));
     const int mode = current_mode(s, s->prop_lo, s->prop_hi);
     ++s->seq_expected;
+    std::chrono::steady_clock::time_point c0, c1, c2;
+    if (s->step_timing) c0 = std::chrono::steady_clock::now();
     rc = launch_propose(s, mode);
     if (rc) return rc;
+    if (s->step_timing) c1 = std::chrono::steady_clock::now();
     rc = wait_epilogue(s);
     if (rc) return rc;
+    if (s->step_timing) {
+        c2 = std::chrono::steady_clock::now();
+        s->t_launch += std::chrono::duration<double, std::micro>(c1 - c0).count();
+        s->t_wait += std::chrono::duration<double, std::micro>(c2 - c1).count();
+        ++s->n_calls;
+    }
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_staged[i] = s->h_chi2[i];
         s->models[i].sf_staged = s->h_chi2[2 * FRMC_MAX_MODELS + i];
