@@ -153,20 +153,32 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
 
     lap("alloc+bounds");
     // gather each element's atoms (original order), then k-d order them on the periodically reduced
-    // coordinates (a block must not straddle the seam because of integer offsets)
-    std::vector<KdPoint> pts((size_t)n);
+    // coordinates (a block must not straddle the seam because of integer offsets).  Slices of the input
+    // are gathered in parallel: per-slice element counts give every slice its own write cursor per element.
+    static_assert(sizeof(KdPoint) == 4 * sizeof(float), "KdPoint must overlay 4 floats");
+    out.kd.resize((size_t)std::max<int64_t>(n, 1) * 4);
+    KdPoint *pts = reinterpret_cast<KdPoint *>(out.kd.data());
     {
-        std::vector<int64_t> cursor((size_t)nEl, 0);
+        std::vector<int64_t> slice_cnt((size_t)hw * nEl, 0);
+        parallel_slices(n, hw, [&](int64_t a, int64_t b, int part) {
+            int64_t *c = &slice_cnt[(size_t)part * nEl];
+            for (int64_t i = a; i < b; ++i) c[el[i]]++;
+        });
+        std::vector<int64_t> cursor((size_t)hw * nEl, 0);
         int64_t at = 0;
-        for (int e = 0; e < nEl; ++e) { cursor[e] = at; at += out.seg_count[e]; }
-        for (int64_t i = 0; i < n; ++i) {
-            KdPoint &q = pts[(size_t)cursor[el[i]]++];
-            for (int c = 0; c < 3; ++c) {
-                const float v = coords[3 * i + c];
-                q.f[c] = ((v == v) && !isinf(v)) ? (isPBC ? (v - floorf(v)) : v) : 0.f;
+        for (int e = 0; e < nEl; ++e)
+            for (int t = 0; t < hw; ++t) { cursor[(size_t)t * nEl + e] = at; at += slice_cnt[(size_t)t * nEl + e]; }
+        parallel_slices(n, hw, [&](int64_t a, int64_t b, int part) {
+            int64_t *cur = &cursor[(size_t)part * nEl];
+            for (int64_t i = a; i < b; ++i) {
+                KdPoint &q = pts[(size_t)cur[el[i]]++];
+                for (int c = 0; c < 3; ++c) {
+                    const float v = coords[3 * i + c];
+                    q.f[c] = ((v == v) && !isinf(v)) ? (isPBC ? (v - floorf(v)) : v) : 0.f;
+                }
+                q.idx = (uint32_t)i;
             }
-            q.idx = (uint32_t)i;
-        }
+        });
     }
     lap("gather");
     {
@@ -180,7 +192,7 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
             bhi[c] = isPBC ? 1.f : out.hi[c];
         }
         for (int e = 0; e < nEl; ++e) {
-            KdPoint *base = pts.data() + at;
+            KdPoint *base = pts + at;
             const size_t len = (size_t)out.seg_count[e];
             at += out.seg_count[e];
             if (len <= 32) continue;
@@ -864,7 +876,22 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     const int64_t cells = (int64_t)nEl * nEl * hs;
     DeviceCtx *c = get_ctx(dev);
     if (!c) return FRMC_ECUDA;
-    HostLayout lay;
+    // the layout scratch lives for the thread: repeated calls (an Engine calling compute_data) reuse its pages, and
+    // the two arrays that travel to the device are page-locked once per growth so the H2D copies run at link speed
+    static thread_local HostLayout lay;
+    static thread_local void *pinned_rec = nullptr, *pinned_orig = nullptr;
+    {
+        const size_t need = (size_t)n + (size_t)SEG_PAD * nEl;
+        auto pin = [](auto &vec, size_t need_elems, void *&reg) {
+            if (vec.capacity() >= need_elems && reg == (void *)vec.data()) return;
+            if (reg) { cudaHostUnregister(reg); reg = nullptr; }
+            if (vec.capacity() < need_elems) vec.reserve(need_elems + need_elems / 4);
+            if (cudaHostRegister(vec.data(), vec.capacity() * sizeof(vec[0]), cudaHostRegisterPortable) == cudaSuccess) reg = vec.data();
+            else cudaGetLastError();            // pageable copies still work
+        };
+        pin(lay.rec, need * 4, pinned_rec);
+        pin(lay.orig, need, pinned_orig);
+    }
     int rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
     if (rc) return rc;
     Lattice L;

@@ -38,6 +38,7 @@ struct HostLayout {
     std::vector<float> rec;           // [npad*4] x,y,z,meta(bits)
     std::vector<uint32_t> orig;       // [npad]  original index or 0xFFFFFFFF
     std::vector<int32_t> inv;         // [n]     original index -> position
+    std::vector<float> kd;            // scratch of the k-d ordering (4 floats per atom), kept to reuse its pages
     float lo[3], hi[3];               // coordinate bounds (mode selection)
     bool finite = true;
 };
