@@ -544,7 +544,7 @@ def main():
     ap.add_argument("--natoms", type=int, default=1000000)
     ap.add_argument("--permove-evals", type=int, default=3000)
     ap.add_argument("--permove-warm", type=int, default=200)
-    ap.add_argument("--ref-rows", type=int, default=96, help="sampled rows per reference step")
+    ap.add_argument("--ref-rows", type=int, default=1600, help="sampled rows per reference step")
     ap.add_argument("--no-permove", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

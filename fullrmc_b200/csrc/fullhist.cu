@@ -292,7 +292,7 @@ struct SpillTarget {
 // binning irrelevant.
 template <int R> struct SweepShape {
     static const int U = (R == 1) ? 4 : 2;          // J records per drain check
-    static const int CAP = (R == 1) ? 12 : 16;      // queue entries per lane; [slot][thread] layout: own bank
+    static const int CAP = (R == 1) ? 20 : 16;      // queue entries per lane; [slot][thread] layout: own bank
 };
 
 template <int MODE, int R>
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(1024) scan2_kernel(const int *__restrict__ a, 
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
 // stats[0] += edge overflow events, stats[1] += (SEG_PAD I records x 32 J records) units actually swept.
 template <int MODE, int R>
-__global__ void __launch_bounds__(256, (R == 1) ? 5 : 3)
+__global__ void __launch_bounds__(256, (R == 1) ? 4 : 3)
 full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const float4 *__restrict__ bbox,
                  const WorkItem *__restrict__ rows, const uint32_t *__restrict__ entries, const int4 *__restrict__ items,
                  int n_items, int *__restrict__ next_item, Lattice L, GridParams g, CullParams cp, int nblocks, int nEl,
