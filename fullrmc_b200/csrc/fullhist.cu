@@ -829,6 +829,23 @@ extern "C" int frmc_set_block_culling(int on)
     return old;
 }
 
+// Host-only inspection of the store layout (no device needed): the original index of every record of the
+// element-sorted, k-d ordered store (0xFFFFFFFF for padding) and the padded segment starts.  Used by the CPU
+// tests of the ordering (permutation, element segments, compactness of the 256-record blocks).
+extern "C" int frmc_debug_layout(int64_t n, const float *coords, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
+                                 int64_t capacity, uint32_t *orig_out, int64_t *npad_out, int64_t *seg_start_out)
+{
+    FRMC_REQUIRE(n >= 0 && coords && mol && el && orig_out && npad_out && seg_start_out, FRMC_EINVAL, "bad arguments");
+    HostLayout lay;
+    int rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
+    if (rc) return rc;
+    FRMC_REQUIRE(capacity >= lay.npad, FRMC_EINVAL, "orig_out holds %lld records, the layout has %lld", (long long)capacity, (long long)lay.npad);
+    for (int64_t p = 0; p < lay.npad; ++p) orig_out[p] = lay.orig[(size_t)p];
+    for (int e = 0; e <= nEl; ++e) seg_start_out[e] = lay.seg_start[(size_t)e];
+    *npad_out = lay.npad;
+    return FRMC_OK;
+}
+
 extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,
                                      int64_t *n_items, int64_t *n_pairs)
 {

@@ -106,6 +106,11 @@ int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, c
                                       float rmax, float bin, int hs, int shard, int nshards,
                                       float *hintra, float *hinter, uint64_t *edge_overflow);
 
+/* Host-only inspection of the store layout (no device needed): original index of every record of the
+ * element-sorted, k-d ordered store (0xFFFFFFFF = padding), padded record count, padded segment start of
+ * every element (nEl + 1 values).  orig_out must hold n + 256 * nEl records. */
+int frmc_debug_layout(int64_t n, const float *coords, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
+                      int64_t capacity, uint32_t *orig_out, int64_t *npad_out, int64_t *seg_start_out);
 /* Host-only view of the multi-GPU decomposition of the full histogram (runs without a device):
  * work items and atom pairs assigned to `shard` of `nshards`; over all shards the pairs sum to n(n-1)/2. */
 int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,
