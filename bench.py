@@ -181,31 +181,47 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
     idx_all = rng.integers(0, n, total).astype(np.int32)
     inv = np.linalg.inv(system.basis.astype(np.float64))
     disp = (rng.normal(0.0, 0.1, (total, 3)) @ inv).astype(np.float32)
-    box = system.boxCoords.copy()
-    accepted = 0
-    launches0 = t0 = None
-    prev = None
-    mv = np.empty((1, 3), dtype=np.float32)
     idx_list = idx_all.tolist()
     step = store.step
-    for it in range(total):
-        if it == warm:
-            launches0 = int(lib.frmc_launch_count())
-            t0 = time.perf_counter()
-        ii = idx_list[it]
-        np.add(box[ii], disp[it], out=mv[0])
-        chi = step(prev, idx_all[it:it + 1], mv)
-        chi_new = float(chi[0]) + float(chi[1])
-        if chi_new <= chi_old:                    # Engine.py:3310-3317 with tolerance 0
-            prev = True; box[ii] = mv[0]; chi_old = chi_new
-            if it >= warm:
-                accepted += 1
-        else:
-            prev = False
-    (store.accept if prev else store.reject)()
-    store.get_timing("delta")                     # synchronises the stream
-    wall = time.perf_counter() - t0
-    launches = int(lib.frmc_launch_count()) - launches0
+    chi_start = chi_old
+
+    def metropolis_run():
+        """the proposal sequence with host Metropolis (tolerance 0), timed wall-clock after `warm` steps"""
+        box = system.boxCoords.copy()
+        chi_prev = chi_start
+        accepted = 0
+        launches0 = t0 = None
+        prev = None
+        mv = np.empty((1, 3), dtype=np.float32)
+        for it in range(total):
+            if it == warm:
+                launches0 = int(lib.frmc_launch_count())
+                t0 = time.perf_counter()
+            ii = idx_list[it]
+            np.add(box[ii], disp[it], out=mv[0])
+            chi = step(prev, idx_all[it:it + 1], mv)
+            chi_new = float(chi[0]) + float(chi[1])
+            if chi_new <= chi_prev:                    # Engine.py:3310-3317 with tolerance 0
+                prev = True; box[ii] = mv[0]; chi_prev = chi_new
+                if it >= warm:
+                    accepted += 1
+            else:
+                prev = False
+        (store.accept if prev else store.reject)()
+        store.get_timing("delta")                     # synchronises the stream
+        wall = time.perf_counter() - t0
+        return wall, accepted, int(lib.frmc_launch_count()) - launches0, box, chi_prev
+
+    # (1) one cooperative launch per proposal
+    wall_launch, accepted_launch, launches_launch, box, chi_end = metropolis_run()
+    # (2) the same sequence from the same start through the persistent kernel
+    store.set_coords(system.boxCoords, system.basis)
+    store.compute_data()
+    store.set_persistent(True)
+    wall, accepted, launches, box2, chi_end2 = metropolis_run()
+    started, served = store.persistent_stats()
+    store.set_persistent(False)
+    same_trajectory = bool(accepted == accepted_launch and chi_end == chi_end2 and np.array_equal(box, box2))
     # device-only time of the propose pipeline: the same CUDA graph launched back to back, CUDA events
     i = idx_all[:1]
     store.propose(i, box[i] + disp[:1])
@@ -232,8 +248,14 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
                             "launched back to back, CUDA events): inputs resident in HBM/L2",
         "us_per_eval_device": 1e3 * ms_pipeline,
         "e2e": {"value": evals_s, "unit": "evals/s", "us_per_eval": 1e6 * wall / n_evals,
-                "h2d_bytes_per_step": 1028, "d2h_bytes_per_step": 4 * 2 + 4 * 2,
-                "api": "DeviceStore.step (frmc_step): resolve previous move + propose next, chi2 read back, host Metropolis"},
+                "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 4 * 2 + 4 * 2 + 4 * 2,
+                "api": "DeviceStore.step (frmc_step) with set_persistent(True): resolve previous move + propose next through the "
+                       "resident kernel (command in mapped pinned memory), chi2 read back, host Metropolis",
+                "persistent_kernels_started": started, "proposals_served": served,
+                "launch_per_proposal": {"value": n_evals / wall_launch, "us_per_eval": 1e6 * wall_launch / n_evals,
+                                        "gpu_launches": launches_launch, "h2d_bytes_per_step": 1028,
+                                        "api": "DeviceStore.step, one cooperative launch per proposal (default mode)"},
+                "same_trajectory_both_modes": same_trajectory},
         "evals": n_evals, "accepted": accepted, "gpu_launches": launches,
         "event_bracketed_us": {"delta_pass": 1e3 * ms_delta / max(n_delta, 1), "epilogue": 1e3 * ms_epi / max(n_delta, 1),
                                "commit_or_clear": 1e3 * ms_commit / max(n_delta, 1),

@@ -78,6 +78,8 @@ SIGNATURES = {
     "frmc_model_set_adjust": (_I, [_VP, _I, _I, _F, _F]),
     "frmc_model_get_scale": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_store_set_accepted": (_I, [_VP, ctypes.c_uint64]),
+    "frmc_store_set_persistent": (_I, [_VP, _I]),
+    "frmc_store_persistent_stats": (_I, [_VP, c_u64p, c_u64p]),
     "frmc_compute_data": (_I, [_VP, c_f32p]),
     "frmc_compute_data_shard": (_I, [_VP, _I, _I]),
     "frmc_grid_counts_ptr": (_VP, [_VP, _I, c_i64p]),
@@ -85,7 +87,9 @@ SIGNATURES = {
     "frmc_propose": (_I, [_VP, c_i32p, _I, c_f32p, c_f32p]),
     "frmc_accept": (_I, [_VP]),
     "frmc_reject": (_I, [_VP]),
-    "frmc_step": (_I, [_VP, _I, c_i32p, _I, c_f32p, c_f32p]),
+    # array arguments as plain addresses: the tight loop passes arr.__array_interface__["data"][0] (1 us) instead of
+    # building a typed ctypes pointer per call (4 us each)
+    "frmc_step": (_I, [_VP, _I, _VP, _I, _VP, c_f32p]),
     "frmc_store_replay_proposal": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double)]),
     "frmc_export_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_export_total": (_I, [_VP, _I, _I, c_f32p]),

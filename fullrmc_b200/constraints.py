@@ -30,13 +30,16 @@ class DeviceBackend(object):
     """One device store per engine; constraints register their r-grid and model on it."""
 
     def __init__(self, boxCoordinates, basisVectors, isPBC, moleculesIndex, elementsIndex, elements,
-                 numberOfAtomsPerElement, volume, numberDensity, device=None):
+                 numberOfAtomsPerElement, volume, numberDensity, device=None, persistent=False):
         self.elements = list(elements)
         self.numberOfAtomsPerElement = dict(numberOfAtomsPerElement)
         self.volume = FLOAT_TYPE(volume)
         self.numberDensity = FLOAT_TYPE(numberDensity)
         self.store = DeviceStore(boxCoordinates, basisVectors, isPBC, moleculesIndex, elementsIndex,
                                  len(self.elements), device=device)
+        if persistent:
+            # one resident kernel serves the whole run of moves (DeviceStore.set_persistent); same results
+            self.store.set_persistent(True)
         self.constraints = []
         self._grids = {}
         self._move = None            # (indexes, moved) of the proposal being evaluated

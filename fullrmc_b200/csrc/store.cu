@@ -218,7 +218,7 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
     const int k = in.k;
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const int p = in.pos[t];
-        const float4 o = atoms[p];
+        const float4 o = __ldcg(atoms + p);
         const float4 nw = make_float4(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], o.w);
         sOld[t] = o; sNew[t] = nw; sPos[t] = p;
         if (blockIdx.x == 0) { prop->pos[t] = p; prop->newc[t] = nw; }
@@ -233,7 +233,7 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
     {
         const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
-        for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? atoms[p] : padrec; }
+        for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
     }
     for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < npad; p0 += DELTA_UNROLL * T) {
         float4 a[DELTA_UNROLL];
@@ -242,7 +242,7 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
         {
             const int q0 = p0 + DELTA_UNROLL * T;
 #pragma unroll
-            for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = q0 + u * T; nxt[u] = (p < npad) ? atoms[p] : padrec; }
+            for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = q0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
         }
 #pragma unroll
         for (int u = 0; u < DELTA_UNROLL; ++u) {
@@ -614,7 +614,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 for (int j = 0; j < EPI_BINS; ++j) {
                     const int r = min(rb + j * EPI_THREADS, hs - 1);
 #pragma unroll
-                    for (int u = 0; u < PB; ++u) c[j][u] = stot[(long long)s_psym[p0 + u] * hs + r];
+                    for (int u = 0; u < PB; ++u) c[j][u] = __ldcg(stot + (long long)s_psym[p0 + u] * hs + r);
                 }
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
@@ -890,17 +890,19 @@ __device__ __forceinline__ void resolve_body(const GridSet &gs, float4 *__restri
     for (int gi = 0; gi < gs.n; ++gi) {
         const GridDev &G = gs.grid[gi];
         for (long long c = tid; c < 2 * G.cells; c += stride) {
-            const int d = G.delta[c];
-            if (d) { if (accept) G.counts[c] = (unsigned long long)((long long)G.counts[c] + d); G.delta[c] = 0; }
+            // __ldcg throughout: in the persistent kernel these cells were changed by other CTAs since this SM last
+            // read them, and L1 is only coherent across kernel boundaries
+            const int d = __ldcg(G.delta + c);
+            if (d) { if (accept) G.counts[c] = (unsigned long long)((long long)__ldcg(G.counts + c) + d); G.delta[c] = 0; }
         }
         const long long ns = (long long)G.nsym * G.g.hs;
-        if (accept) { for (long long c = tid; c < ns; c += stride) G.tot[c] = G.stot[c]; }
-        else        { for (long long c = tid; c < ns; c += stride) G.stot[c] = G.tot[c]; }
+        if (accept) { for (long long c = tid; c < ns; c += stride) G.tot[c] = __ldcg(G.stot + c); }
+        else        { for (long long c = tid; c < ns; c += stride) G.stot[c] = __ldcg(G.tot + c); }
     }
     if (accept) {
-        if (tid < prop->k) atoms[prop->pos[tid]] = prop->newc[tid];
+        if (tid < __ldcg(&prop->k)) atoms[__ldcg(&prop->pos[tid])] = __ldcg(&prop->newc[tid]);
         for (int m = 0; m < tc.n; ++m)
-            for (long long i = tid; i < tc.len[m]; i += stride) tc.dst[m][i] = tc.src[m][i];
+            for (long long i = tid; i < tc.len[m]; i += stride) tc.dst[m][i] = __ldcg(tc.src[m] + i);
     }
 }
 
@@ -944,6 +946,158 @@ propose_kernel(float4 *__restrict__ atoms, int npad, const ProposalIn in, Propos
     // (3) epilogue
     EPI_STAMP(0);
     epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps);
+}
+
+// ------------------------------------------------------------------ persistent variant of the per-move kernel
+// One cooperative launch serves a whole run of proposals: the host writes a command (moved atoms + how the
+// previous proposal was resolved) into mapped pinned memory, thread 0 of CTA 0 polls it, relays it through
+// device memory to the other CTAs, and every CTA runs resolve -> delta pass -> (epilogue CTAs) G(r)/S(Q)/chi^2
+// exactly like propose_kernel.  What disappears is the launch itself: ~4.5 us of cudaLaunchCooperativeKernel on
+// the host and ~3 us of start-up on the device per evaluated move.  The kernel gives the GPU back when no
+// command arrives for idle_ns (a watchdog, so a stalled or crashed host never leaves it spinning) or on QUIT.
+enum : int { CMD_EVAL = 1, CMD_QUIT = 2 };
+
+// Mapped pinned host memory.  A single-atom command fits two 16-byte chunks, each written by the host with ONE
+// aligned 16-byte store and each carrying the command number, so the device validates them independently and a
+// k = 1 proposal costs one PCIe read round trip to fetch; further atoms (k > 1) are read from pos/moved afterwards
+// (the host fills those before the chunks).
+struct alignas(64) HostCmd {
+    unsigned int a_seq, a_word, a_pos0, a_mx0;   // chunk A: number, op | prev << 8 | k << 16, atom 0: position, moved x
+    unsigned int b_my0, b_mz0, b_seq, b_pad;     // chunk B: atom 0 moved y, z, number again
+    unsigned int alive;                          // written by the device: 1 while the kernel polls, 0 once it has left
+    unsigned int pad[7];
+    int pos[FRMC_MAX_GROUP];
+    float moved[3 * FRMC_MAX_GROUP];
+};
+
+struct DevCmd {                       // device memory: CTA 0's relay to the grid
+    unsigned int seq;
+    int op, prev, pad;
+    ProposalIn in;
+};
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const unsigned int *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EPI_THREADS, 1)
+propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd *dcmd, Proposal *__restrict__ prop, Lattice L,
+                    GridSet gs, int nEl, unsigned long long *__restrict__ overflow, const ModelSet ms, const EpiMap em,
+                    const TotalsCopy tc, unsigned long long *__restrict__ bars, unsigned int first_seq, unsigned long long idle_ns,
+                    float *__restrict__ chi2_out, unsigned int *__restrict__ dev_seq, volatile unsigned int *__restrict__ host_seq,
+                    unsigned int *__restrict__ tickets)
+{
+    extern __shared__ __align__(128) float epi_smem[];
+    __shared__ __align__(16) EpiShared es;
+    __shared__ DeltaShared dsh;
+    __shared__ ProposalIn s_in;
+    __shared__ int s_op, s_prev;
+    const bool epi = (int)blockIdx.x < em.n;
+    const int m = epi ? em.model[blockIdx.x] : 0, slab = epi ? em.slab[blockIdx.x] : 0;
+    if (epi) epilogue_prefetch(es, epi_smem, ms.m[m], slab);      // the slab stays resident for the whole run
+    unsigned int expect = first_seq;
+    unsigned long long n_delta = 0, n_resolve = 0;                // barrier generations, counted identically by every CTA
+    for (;;) {
+        // (a) CTA 0 fetches the next command from the host and relays it
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                int op = CMD_QUIT;
+                for (;;) {
+                    const uint4 A = ld_volatile_v4(&hcmd->a_seq), B = ld_volatile_v4(&hcmd->b_my0);
+                    if (A.x == expect && B.z == expect) {
+                        op = (int)(A.y & 0xFFu);
+                        dcmd->prev = (int)((A.y >> 8) & 0xFFu);
+                        dcmd->in.k = (int)(A.y >> 16);
+                        dcmd->in.pos[0] = (int)A.z;
+                        dcmd->in.moved[0] = __uint_as_float(A.w);
+                        dcmd->in.moved[1] = __uint_as_float(B.x);
+                        dcmd->in.moved[2] = __uint_as_float(B.y);
+                        break;
+                    }
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > idle_ns) break;           // idle: give the GPU back
+                }
+                dcmd->op = op;
+                s_op = op;
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (s_op == CMD_EVAL) {
+                const int k = __ldcg(&dcmd->in.k);           // written by thread 0 of this CTA just above
+                for (int t = 1 + threadIdx.x; t < k; t += blockDim.x) {
+                    dcmd->in.pos[t] = (int)ld_volatile_u32((const unsigned int *)&hcmd->pos[t]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        dcmd->in.moved[3 * t + c] = __uint_as_float(ld_volatile_u32((const unsigned int *)&hcmd->moved[3 * t + c]));
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_u32(&dcmd->seq, expect);
+        }
+        // (b) every CTA picks the command up (L2 loads: another CTA wrote it)
+        if (threadIdx.x == 0) {
+            while (ld_acquire_u32(&dcmd->seq) != expect) { }
+            s_op = __ldcg(&dcmd->op); s_prev = __ldcg(&dcmd->prev);
+        }
+        __syncthreads();
+        const int op = s_op, prev = s_prev;
+        if (op != CMD_EVAL) break;
+        {
+            const int k = __ldcg(&dcmd->in.k);
+            for (int t = threadIdx.x; t < k; t += blockDim.x) {
+                s_in.pos[t] = __ldcg(&dcmd->in.pos[t]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s_in.moved[3 * t + c] = __ldcg(&dcmd->in.moved[3 * t + c]);
+            }
+            if (threadIdx.x == 0) s_in.k = k;
+        }
+        __syncthreads();
+        // (1) resolve the previous proposal
+        if (prev) {
+            resolve_body(gs, atoms, prop, tc, prev);
+            grid_arrive(bars + 0);
+            ++n_resolve;
+            grid_wait(bars + 0, n_resolve * gridDim.x);
+        }
+        // (2) delta pass of this proposal
+        delta_body<MODE>(dsh, atoms, npad, s_in, prop, L, gs, nEl, overflow);
+        grid_arrive(bars + 1);
+        ++n_delta;
+        // (3) epilogue; the other CTAs go straight back to waiting (the host sends the next command only after chi^2)
+        if (epi) {
+            grid_wait(bars + 1, n_delta * gridDim.x);
+            epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, nullptr);
+        }
+        ++expect;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned int *>(&hcmd->alive) = 0u;
+        __threadfence_system();
+    }
 }
 
 }  // namespace frmc
@@ -1009,6 +1163,17 @@ struct frmc_store {
     bool step_timing = false;
     double t_launch = 0, t_wait = 0, t_call = 0;
     unsigned long long n_calls = 0;
+    // persistent per-move kernel (propose_loop_kernel)
+    bool persist_enabled = false;    // frmc_store_set_persistent
+    bool persist_ok = false;         // every model fits the resident-slab epilogue, no refit schedule (sync_models)
+    bool persist_running = false;
+    int persist_mode = -1;           // geometry mode the running kernel was instantiated for
+    HostCmd *h_cmd = nullptr;        // mapped pinned
+    DevCmd *d_cmd = nullptr;
+    unsigned long long *d_pbars = nullptr;   // the persistent kernel's own two barrier counters
+    unsigned int cmd_seq = 0;        // last command number written
+    int last_prev = 0;               // resolution carried by the last command (to resend it if the kernel had left)
+    unsigned long long persist_launches = 0, persist_cmds = 0;
     unsigned long long accepted = 0;  // the engine's count of accepted moves (refit schedule, Core/Constraint.py:1418-1422)
     float chi2_committed[FRMC_MAX_MODELS];
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
@@ -1052,6 +1217,11 @@ static void timing_flush(frmc_store *s)
     }
     s->ev_pending.clear();
 }
+
+// persistent per-move kernel lifecycle (defined further down)
+static void write_cmd(frmc_store *s, int op, int prev);
+static int stop_persistent(frmc_store *s);
+static int launch_persistent(frmc_store *s, int mode);
 
 static GridSet make_gridset(frmc_store *s)
 {
@@ -1168,6 +1338,24 @@ static int sync_models(frmc_store *s)
         cudaGetLastError();
         s->fused_ok = ok;
     }
+    // the persistent kernel keeps every S(Q) slab resident in shared memory for its whole life and carries the
+    // model constants in its launch parameters: no ring refills, no per-evaluation refit schedule
+    s->persist_ok = s->fused_ok && !s->models.empty();
+    for (auto &m : s->models) {
+        const bool is_sq = (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ);
+        if (is_sq && (m.dev.hs + SQ_ROWS - 1) / SQ_ROWS > m.dev.n_stages) s->persist_ok = false;
+        if (m.adjust_freq > 0) s->persist_ok = false;
+    }
+    if (s->persist_ok) {
+        int per_sm = 0;
+#define PERSIST_ATTR(M) do { \
+            if (cudaFuncSetAttribute(propose_loop_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)) != cudaSuccess) s->persist_ok = false; \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propose_loop_kernel<M>, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->persist_ok = false; \
+        } while (0)
+        PERSIST_ATTR(MODE_IBC); PERSIST_ATTR(MODE_ORTHO_FAST); PERSIST_ATTR(MODE_TRI_FAST); PERSIST_ATTR(MODE_ORTHO_GEN); PERSIST_ATTR(MODE_TRI_GEN);
+#undef PERSIST_ATTR
+        cudaGetLastError();
+    }
     s->models_dirty = false;
     return FRMC_OK;
 }
@@ -1216,6 +1404,16 @@ static int wait_epilogue(frmc_store *s)
     for (size_t m = 0; m < nm; ++m) {
         while (s->h_seq[m] != s->seq_expected) {
             _mm_pause();
+            if (s->persist_running && (spins & 0xFFF) == 0xFFF && *reinterpret_cast<volatile unsigned int *>(&s->h_cmd->alive) == 0u) {
+                // the kernel left on its watchdog just as the command was written: start a new one, send it again
+                FRMC_CUDA(cudaStreamSynchronize(s->stream));
+                s->persist_running = false;
+                if (s->h_seq[m] == s->seq_expected) break;
+                int rrc = launch_persistent(s, s->persist_mode);
+                if (rrc) return rrc;
+                --s->persist_cmds;                 // the same proposal, sent again
+                write_cmd(s, CMD_EVAL, s->last_prev);
+            }
             if ((++spins & 0xFFFFF) == 0) {           // every ~1M polls: make sure the stream is still alive
                 cudaError_t e = cudaStreamQuery(s->stream);
                 if (e == cudaSuccess) break;          // finished without publishing -> checked below
@@ -1299,6 +1497,7 @@ static TotalsCopy make_totals_copy(frmc_store *s)
 // the next fused proposal looks at the device state)
 static int flush_pending(frmc_store *s)
 {
+    { int prc = stop_persistent(s); if (prc) return prc; }      // anything that looks at the device state ends the run
     if (!s->pending) return FRMC_OK;
     GridSet gs = make_gridset(s);
     cudaEvent_t t0 = timing_begin(s);
@@ -1339,13 +1538,110 @@ static int launch_fused_t(frmc_store *s)
     return FRMC_OK;
 }
 
+// ---- persistent per-move kernel: lifecycle
+static void write_cmd(frmc_store *s, int op, int prev)
+{
+    HostCmd *h = s->h_cmd;
+    const ProposalIn &in = s->prop_in;
+    const int k = (op == CMD_EVAL) ? in.k : 0;
+    for (int t = 1; t < k; ++t) {
+        h->pos[t] = in.pos[t];
+        h->moved[3 * t] = in.moved[3 * t]; h->moved[3 * t + 1] = in.moved[3 * t + 1]; h->moved[3 * t + 2] = in.moved[3 * t + 2];
+    }
+    _mm_sfence();                                     // entries 1.. are visible before the chunks that announce them
+    const unsigned int seq = ++s->cmd_seq;
+    unsigned int mx, my, mz;
+    memcpy(&mx, &in.moved[0], 4); memcpy(&my, &in.moved[1], 4); memcpy(&mz, &in.moved[2], 4);
+    const __m128i A = _mm_set_epi32((int)mx, in.pos[0], (int)((unsigned)op | ((unsigned)prev << 8) | ((unsigned)k << 16)), (int)seq);
+    const __m128i B = _mm_set_epi32(0, (int)seq, (int)mz, (int)my);
+    _mm_store_si128(reinterpret_cast<__m128i *>(&h->b_my0), B);      // one aligned 16-byte store per chunk
+    _mm_store_si128(reinterpret_cast<__m128i *>(&h->a_seq), A);
+    _mm_sfence();
+    if (op == CMD_EVAL) ++s->persist_cmds;
+}
+
+static int stop_persistent(frmc_store *s)
+{
+    if (!s->persist_running) return FRMC_OK;
+    if (*reinterpret_cast<volatile unsigned int *>(&s->h_cmd->alive)) write_cmd(s, CMD_QUIT, 0);
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    s->persist_running = false;
+    return FRMC_OK;
+}
+
+template <int MODE>
+static int launch_persistent_t(frmc_store *s)
+{
+    GridSet gs = make_gridset(s);
+    ModelSet ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = (int)s->models.size();
+    for (int i = 0; i < ms.n; ++i) ms.m[i] = launch_model(s, s->models[i]);
+    TotalsCopy tc = make_totals_copy(s);
+    int npad = (int)s->npad, nEl = s->nEl;
+    unsigned int *tickets = s->d_seq + FRMC_MAX_MODELS;
+    volatile unsigned int *hseq = s->h_seq;
+    unsigned int first_seq = s->cmd_seq + 1;
+    unsigned long long idle_ns = 2000000ull;          // 2 ms without a command: leave
+    if (const char *e = getenv("FRMC_PERSIST_IDLE_US")) idle_ns = 1000ull * (unsigned long long)std::max(10, atoi(e));
+    FRMC_CUDA(cudaMemsetAsync(s->d_pbars, 0, 2 * sizeof(unsigned long long), s->stream));
+    FRMC_CUDA(cudaMemsetAsync(s->d_cmd, 0, sizeof(unsigned int), s->stream));          // relay seq: 0 is never a command number... (numbers start at 1)
+    *reinterpret_cast<volatile unsigned int *>(&s->h_cmd->alive) = 1u;
+    _mm_sfence();
+    void *args[] = {&s->d_atoms, &npad, &s->h_cmd, &s->d_cmd, &s->d_prop, &s->L, &gs, &nEl, &s->d_overflow, &ms, &s->epi_map, &tc,
+                    &s->d_pbars, &first_seq, &idle_ns, &s->h_chi2, &s->d_seq, &hseq, &tickets};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)propose_loop_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
+                                                args, s->epi_smem, s->stream);
+    if (e != cudaSuccess) {
+        set_error("cooperative launch of the persistent propose kernel failed: %s", cudaGetErrorString(e));
+        return FRMC_ECUDA;
+    }
+    ++g_launch_count;
+    ++s->persist_launches;
+    s->persist_running = true;
+    return FRMC_OK;
+}
+
+static int launch_persistent(frmc_store *s, int mode)
+{
+    s->persist_mode = mode;
+    switch (mode) {
+        case MODE_IBC: return launch_persistent_t<MODE_IBC>(s);
+        case MODE_ORTHO_FAST: return launch_persistent_t<MODE_ORTHO_FAST>(s);
+        case MODE_TRI_FAST: return launch_persistent_t<MODE_TRI_FAST>(s);
+        case MODE_ORTHO_GEN: return launch_persistent_t<MODE_ORTHO_GEN>(s);
+        default: return launch_persistent_t<MODE_TRI_GEN>(s);
+    }
+}
+
+// one proposal through the persistent kernel: (re)start it when needed, send the command
+static int propose_persistent(frmc_store *s, int mode)
+{
+    int rc = FRMC_OK;
+    const bool alive = s->persist_running && *reinterpret_cast<volatile unsigned int *>(&s->h_cmd->alive) != 0u;
+    if (!alive || s->persist_mode != mode) {
+        rc = stop_persistent(s);                      // also reaps a kernel that left on its own (watchdog)
+        if (rc) return rc;
+        rc = launch_persistent(s, mode);
+        if (rc) return rc;
+    }
+    s->last_prev = s->pending;
+    write_cmd(s, CMD_EVAL, s->pending);
+    s->pending = 0;
+    return FRMC_OK;
+}
+
 // the per-move pipeline.  Fused path: ONE cooperative launch (resolve previous + delta pass +
 // epilogue).  Fallback (timing mode, FRMC_NO_FUSED=1, too many epilogue CTAs): delta pass
 // (proposal by value) + fused epilogue, two launches, after the pending resolution.
 static int launch_propose(frmc_store *s, int mode)
 {
-    int rc = sync_models(s);
+    int rc = FRMC_OK;
+    if (s->models_dirty && (rc = stop_persistent(s))) return rc;     // the running kernel carries the old constants
+    rc = sync_models(s);
     if (rc) return rc;
+    if (s->persist_enabled && s->persist_ok && !s->timing) return propose_persistent(s, mode);
+    if ((rc = stop_persistent(s))) return rc;
     if (s->fused_ok && !s->timing) {
         switch (mode) {
             case MODE_IBC: return launch_fused_t<MODE_IBC>(s);
@@ -1439,6 +1735,12 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     if (cudaMalloc(&s->d_bars, sizeof(unsigned long long) * 4) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_bars, 0, sizeof(unsigned long long) * 4);
     { const char *e = getenv("FRMC_NO_FUSED"); s->use_fused = !(e && e[0] == '1'); }
+    if (cudaHostAlloc((void **)&s->h_cmd, sizeof(HostCmd), cudaHostAllocMapped) != cudaSuccess) return fail("pinned alloc");
+    memset(s->h_cmd, 0, sizeof(HostCmd));
+    if (cudaMalloc((void **)&s->d_cmd, sizeof(DevCmd)) != cudaSuccess) return fail("alloc");
+    cudaMemset(s->d_cmd, 0, sizeof(DevCmd));
+    if (cudaMalloc((void **)&s->d_pbars, sizeof(unsigned long long) * 2) != cudaSuccess) return fail("alloc");
+    { const char *e = getenv("FRMC_PERSISTENT"); s->persist_enabled = (e && e[0] == '1'); }
     if (cudaMalloc(&s->d_stamps, sizeof(long long) * 16 * FRMC_MAX_MODELS) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_stamps, 0, sizeof(long long) * 16 * FRMC_MAX_MODELS);
     { long long big = 0x7FFFFFFFFFFFFFFFll; cudaMemcpy(s->d_stamps + 120, &big, sizeof(big), cudaMemcpyHostToDevice); }
@@ -1453,6 +1755,7 @@ void frmc_store_destroy(frmc_store *s)
                 s->t_launch / s->n_calls, s->t_wait / s->n_calls);
     if (!s) return;
     cudaSetDevice(s->dev);
+    if (s->h_cmd) stop_persistent(s);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &m : s->models) {
         for (void *p : m.owned) cudaFree(p);
@@ -1464,6 +1767,8 @@ void frmc_store_destroy(frmc_store *s)
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
+    if (s->h_cmd) cudaFreeHost(s->h_cmd);
+    cudaFree(s->d_cmd); cudaFree(s->d_pbars);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1643,6 +1948,22 @@ int frmc_model_get_scale(frmc_store *s, int model, float *committed, float *last
     return FRMC_OK;
 }
 
+int frmc_store_set_persistent(frmc_store *s, int on)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    if (!on) { int rc = stop_persistent(s); if (rc) return rc; }
+    s->persist_enabled = on != 0;
+    return FRMC_OK;
+}
+
+int frmc_store_persistent_stats(frmc_store *s, uint64_t *kernel_launches, uint64_t *commands)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    if (kernel_launches) *kernel_launches = s->persist_launches;
+    if (commands) *commands = s->persist_cmds;
+    return FRMC_OK;
+}
+
 int frmc_store_set_accepted(frmc_store *s, uint64_t accepted)
 {
     FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
@@ -1804,6 +2125,10 @@ int frmc_store_replay_proposal(frmc_store *s, int reps, double *ms_per_launch)
     const int mode = current_mode(s, s->prop_lo, s->prop_hi);
     const bool timing = s->timing;
     s->timing = false;
+    // back-to-back launches are the point of the replay: it always runs the launch-per-proposal kernels
+    const bool persist = s->persist_enabled;
+    { int prc = stop_persistent(s); if (prc) return prc; }
+    s->persist_enabled = false;
     cudaEvent_t e0, e1;
     FRMC_CUDA(cudaEventCreate(&e0));
     FRMC_CUDA(cudaEventCreate(&e1));
@@ -1824,6 +2149,7 @@ int frmc_store_replay_proposal(frmc_store *s, int reps, double *ms_per_launch)
     if (rc == FRMC_OK) rc = launch_propose(s, mode);
     if (rc == FRMC_OK) rc = wait_epilogue(s);
     s->timing = timing;
+    s->persist_enabled = persist;
     return rc;
 }
 
@@ -1889,6 +2215,7 @@ int frmc_store_debug_stamps(frmc_store *s, int64_t *out, int n)
 uint64_t frmc_store_edge_overflow(frmc_store *s)
 {
     if (!s) return 0;
+    stop_persistent(s);
     unsigned long long ov = 0;
     cudaSetDevice(s->dev);
     cudaMemcpyAsync(&ov, s->d_overflow, sizeof(ov), cudaMemcpyDeviceToHost, s->stream);
@@ -1899,6 +2226,7 @@ uint64_t frmc_store_edge_overflow(frmc_store *s)
 uint64_t frmc_store_swept_pairs(frmc_store *s)
 {
     if (!s) return 0;
+    stop_persistent(s);
     unsigned long long blocks = 0;
     cudaSetDevice(s->dev);
     cudaMemcpyAsync(&blocks, s->d_overflow + 1, sizeof(blocks), cudaMemcpyDeviceToHost, s->stream);

@@ -107,6 +107,17 @@ class DeviceStore(object):
         L.check(self._lib.frmc_model_get_scale(self._handle, int(model), ctypes.byref(a), ctypes.byref(b)), "get_scale")
         return _F32(a.value), _F32(b.value)
 
+    def set_persistent(self, on=True):
+        """Keep one cooperative kernel resident across a run of propose/step calls (include/fullrmc_b200.h:
+        frmc_store_set_persistent); results are identical, the per-move kernel launch disappears."""
+        L.check(self._lib.frmc_store_set_persistent(self._handle, int(bool(on))), "set_persistent")
+
+    def persistent_stats(self):
+        """(persistent kernels started, proposals they served)"""
+        a = ctypes.c_uint64(0); b = ctypes.c_uint64(0)
+        L.check(self._lib.frmc_store_persistent_stats(self._handle, ctypes.byref(a), ctypes.byref(b)), "persistent_stats")
+        return int(a.value), int(b.value)
+
     def set_accepted(self, accepted):
         """re-base the store's count of accepted moves on engine.accepted (it drives the refit schedule)"""
         L.check(self._lib.frmc_store_set_accepted(self._handle, int(accepted)), "set_accepted")
@@ -161,7 +172,8 @@ class DeviceStore(object):
         if moved.size != 3 * k:
             raise ValueError("movedBoxCoordinates must be (k,3)")
         prev = -1 if previous is None else (1 if previous else 0)
-        rc = self._step_fn(self._handle, prev, idx.ctypes.data_as(L.c_i32p), k, moved.ctypes.data_as(L.c_f32p), self._chi2_ptr)
+        rc = self._step_fn(self._handle, prev, idx.__array_interface__["data"][0], k, moved.__array_interface__["data"][0],
+                           self._chi2_ptr)
         if rc < 0:
             L.check(rc, "step")
         return self._chi2[:len(self._models)]

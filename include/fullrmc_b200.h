@@ -193,6 +193,15 @@ int frmc_model_set_scale(frmc_store *s, int model, float scale);
 int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min, float sf_max);
 int frmc_model_get_scale(frmc_store *s, int model, float *committed, float *last_used);
 int frmc_store_set_accepted(frmc_store *s, uint64_t accepted);
+/* Persistent per-move kernel (default off; FRMC_PERSISTENT=1 switches it on for new stores).  When on, frmc_propose /
+ * frmc_step keep ONE cooperative kernel resident across a run of proposals and hand it each move through mapped
+ * pinned memory, which removes the per-move kernel launch (about 8 us of the ~38 us round trip).  Results are
+ * identical.  Every other entry point that touches the device ends the run first; the kernel also leaves by
+ * itself after 2 ms without a proposal (FRMC_PERSIST_IDLE_US) and is restarted on demand.  Falls back to one
+ * launch per proposal for models whose S(Q) slab does not fit shared memory or that refit their scale factor.
+ * frmc_store_persistent_stats: kernels started and proposals served so far. */
+int frmc_store_set_persistent(frmc_store *s, int on);
+int frmc_store_persistent_stats(frmc_store *s, uint64_t *kernel_launches, uint64_t *commands);
 
 /* compute_data: full histogram of every grid (tiled kernel), totals and chi^2 per model.
  * chi2 [n_models] fp32 (np.add.reduce result), may be NULL. */

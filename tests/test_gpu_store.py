@@ -42,6 +42,9 @@ def _grid_arrays(case):
     return centers, ep.shell_arrays_from_edges(edges)
 
 
+PERSISTENT = False       # flipped by test_persistent_kernel_*: every store built below keeps one kernel resident
+
+
 def _build(case, kinds, rng, with_weights=False, with_shape=False, scale=1.0):
     """DeviceStore + ModelSpecs + matching oracle closures for the requested model kinds"""
     from fullrmc_b200.model import ModelSpec
@@ -51,6 +54,8 @@ def _build(case, kinds, rng, with_weights=False, with_shape=False, scale=1.0):
     hs = case["histSize"]
     store = DeviceStore(case["boxCoords"], case["basis"], case["isPBC"], case["moleculeIndex"], case["elementIndex"],
                         case["numberOfElements"])
+    if PERSISTENT:
+        store.set_persistent(True)
     g = store.add_grid(case["minDistance"], case["maxDistance"], case["bin"], hs)
     q = np.linspace(0.5, 20.0, 97).astype(F32)
     gr2sq = ep.gr2sq_matrix(q, centers)
@@ -259,6 +264,72 @@ def test_move_sequences_on_large_sparse_systems(kind, orc):
             if previous:
                 data_i, data_e, box = new_i, new_e, tmp
     (store.accept if previous else store.reject)()
+    gi, ge = store.export_data(0)
+    assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e)
+    assert np.array_equal(store.get_coords(), box)
+    store.close()
+
+
+@pytest.fixture
+def persistent_mode():
+    global PERSISTENT
+    PERSISTENT = True
+    yield
+    PERSISTENT = False
+
+
+def test_persistent_kernel_reference_sequences(orc, persistent_mode):
+    """the same sequences through the persistent per-move kernel (one cooperative launch serving a run of
+    proposals, commands through mapped pinned memory): every check of _run_sequence exports the state, so the
+    kernel is stopped and restarted after every move -- the lifecycle path"""
+    _run_sequence(CASES["ortho_atomic"], ["PDF", "SQ"], orc, n_moves=9, seed=21)
+    _run_sequence(CASES["tri_molecular"], ["PCF", "RSQ"], orc, n_moves=9, seed=22, with_weights=True)
+    _run_sequence(CASES["ibc_nanoparticle"], ["PDF"], orc, n_moves=6, seed=23, with_shape=True)
+
+
+@pytest.mark.parametrize("kind", ["ortho", "tri_unwrapped"])
+def test_persistent_kernel_long_run(kind, orc, persistent_mode):
+    """a run of proposals served by ONE resident kernel (no state export in between): chi^2 of every step and the
+    final state equal the reference sequence; the kernel is started once or twice, not once per move"""
+    import time
+    case = _large_sparse_case(kind)
+    rng = np.random.default_rng(31)
+    store, oracles = _build(case, ["PDF", "SQ"], rng)
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    box = case["boxCoords"].copy()
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    store.compute_data()
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, ncores=orc.max_threads(), **kw)
+    args = (kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"], kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+    moves = []
+    for step in range(40):
+        idx = C.group_for(case, rng)
+        moves.append((idx, rng.normal(0, 0.45 if step % 5 == 0 else 0.004, (1, 3)).astype(F32)))
+    # device first, back to back (the oracle in between would let the kernel's idle watchdog fire every move)
+    chis, previous = [], None
+    dbox = box.copy()
+    for step, (idx, shift) in enumerate(moves):
+        moved = (dbox[idx] + shift).astype(F32)
+        chis.append(store.step(previous, idx, moved).copy())
+        previous = step % 3 != 2
+        if previous:
+            dbox[idx] = moved
+        if step == 25:
+            time.sleep(0.05)                                 # longer than the idle watchdog: the kernel leaves and is restarted
+    (store.accept if previous else store.reject)()
+    started, served = store.persistent_stats()
+    assert served == 40 and 1 <= started <= 10, (started, served)      # restarts: the sleep, wrap-mode switches of long jumps
+    for step, (idx, shift) in enumerate(moves):
+        moved = (box[idx] + shift).astype(F32)
+        bi, be = ep.move_delta(fns, idx, box, *args)
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, *args)
+        new_i, new_e = data_i - bi + ai, data_e - be + ae
+        for m, (total, exp, dw) in enumerate(oracles):
+            assert F32(chis[step][m]) == F32(ep.standard_error(exp, total(new_i, new_e), dw)), "step %d model %d" % (step, m)
+        if step % 3 != 2:
+            data_i, data_e, box = new_i, new_e, tmp
     gi, ge = store.export_data(0)
     assert np.array_equal(gi, data_i) and np.array_equal(ge, data_e)
     assert np.array_equal(store.get_coords(), box)
