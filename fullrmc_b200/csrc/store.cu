@@ -970,10 +970,9 @@ struct alignas(64) HostCmd {
     float moved[3 * FRMC_MAX_GROUP];
 };
 
-struct DevCmd {                       // device memory: CTA 0's relay to the grid
-    unsigned int seq;
-    int op, prev, pad;
-    ProposalIn in;
+struct alignas(64) DevCmd {           // device memory: CTA 0's relay to the grid, same two self-validating chunks
+    uint4 a, b;
+    ProposalIn in;                    // atoms 1.. of a group move (written, and fenced, before the chunks)
 };
 
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p)
@@ -988,15 +987,9 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const unsigned int *p)
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+__device__ __forceinline__ void st_volatile_v4(uint4 *p, uint4 v)
 {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 template <int MODE>
@@ -1011,7 +1004,7 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
     __shared__ __align__(16) EpiShared es;
     __shared__ DeltaShared dsh;
     __shared__ ProposalIn s_in;
-    __shared__ int s_op, s_prev;
+    __shared__ uint4 s_a, s_b;             // the command's two chunks
     const bool epi = (int)blockIdx.x < em.n;
     const int m = epi ? em.model[blockIdx.x] : 0, slab = epi ? em.slab[blockIdx.x] : 0;
     if (epi) epilogue_prefetch(es, epi_smem, ms.m[m], slab);      // the slab stays resident for the whole run
@@ -1023,56 +1016,53 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
             if (threadIdx.x == 0) {
                 unsigned long long t0, t1;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                int op = CMD_QUIT;
+                uint4 A = make_uint4(expect, (unsigned)CMD_QUIT, 0u, 0u), B = make_uint4(0u, 0u, expect, 0u);
                 for (;;) {
-                    const uint4 A = ld_volatile_v4(&hcmd->a_seq), B = ld_volatile_v4(&hcmd->b_my0);
-                    if (A.x == expect && B.z == expect) {
-                        op = (int)(A.y & 0xFFu);
-                        dcmd->prev = (int)((A.y >> 8) & 0xFFu);
-                        dcmd->in.k = (int)(A.y >> 16);
-                        dcmd->in.pos[0] = (int)A.z;
-                        dcmd->in.moved[0] = __uint_as_float(A.w);
-                        dcmd->in.moved[1] = __uint_as_float(B.x);
-                        dcmd->in.moved[2] = __uint_as_float(B.y);
-                        break;
-                    }
+                    const uint4 hA = ld_volatile_v4(&hcmd->a_seq), hB = ld_volatile_v4(&hcmd->b_my0);
+                    if (hA.x == expect && hB.z == expect) { A = hA; B = hB; break; }
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > idle_ns) break;           // idle: give the GPU back
+                    if (t1 - t0 > idle_ns) break;           // idle: give the GPU back (relayed as QUIT)
                 }
-                dcmd->op = op;
-                s_op = op;
-                __threadfence_system();
+                s_a = A; s_b = B;
             }
             __syncthreads();
-            if (s_op == CMD_EVAL) {
-                const int k = __ldcg(&dcmd->in.k);           // written by thread 0 of this CTA just above
+            const int k = (int)(s_a.y >> 16);
+            if ((int)(s_a.y & 0xFFu) == CMD_EVAL && k > 1) {
+                __threadfence_system();                     // entries 1.. were written before the chunks
                 for (int t = 1 + threadIdx.x; t < k; t += blockDim.x) {
                     dcmd->in.pos[t] = (int)ld_volatile_u32((const unsigned int *)&hcmd->pos[t]);
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         dcmd->in.moved[3 * t + c] = __uint_as_float(ld_volatile_u32((const unsigned int *)&hcmd->moved[3 * t + c]));
                 }
+                __threadfence();
+                __syncthreads();
             }
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_u32(&dcmd->seq, expect);
+            if (threadIdx.x == 0) { st_volatile_v4(&dcmd->b, s_b); st_volatile_v4(&dcmd->a, s_a); }
         }
-        // (b) every CTA picks the command up (L2 loads: another CTA wrote it)
+        // (b) every CTA picks the command up: one L2 round trip for a single-atom move
         if (threadIdx.x == 0) {
-            while (ld_acquire_u32(&dcmd->seq) != expect) { }
-            s_op = __ldcg(&dcmd->op); s_prev = __ldcg(&dcmd->prev);
+            uint4 A, B;
+            do { A = ld_volatile_v4(&dcmd->a.x); B = ld_volatile_v4(&dcmd->b.x); } while (A.x != expect || B.z != expect);
+            s_a = A; s_b = B;
         }
         __syncthreads();
-        const int op = s_op, prev = s_prev;
+        const int op = (int)(s_a.y & 0xFFu), prev = (int)((s_a.y >> 8) & 0xFFu);
         if (op != CMD_EVAL) break;
         {
-            const int k = __ldcg(&dcmd->in.k);
-            for (int t = threadIdx.x; t < k; t += blockDim.x) {
-                s_in.pos[t] = __ldcg(&dcmd->in.pos[t]);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) s_in.moved[3 * t + c] = __ldcg(&dcmd->in.moved[3 * t + c]);
+            const int k = (int)(s_a.y >> 16);
+            if (threadIdx.x == 0) {
+                s_in.k = k; s_in.pos[0] = (int)s_a.z;
+                s_in.moved[0] = __uint_as_float(s_a.w); s_in.moved[1] = __uint_as_float(s_b.x); s_in.moved[2] = __uint_as_float(s_b.y);
             }
-            if (threadIdx.x == 0) s_in.k = k;
+            if (k > 1) {
+                __threadfence();
+                for (int t = 1 + threadIdx.x; t < k; t += blockDim.x) {
+                    s_in.pos[t] = __ldcg(&dcmd->in.pos[t]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) s_in.moved[3 * t + c] = __ldcg(&dcmd->in.moved[3 * t + c]);
+                }
+            }
         }
         __syncthreads();
         // (1) resolve the previous proposal
@@ -1585,7 +1575,7 @@ static int launch_persistent_t(frmc_store *s)
     unsigned long long idle_ns = 2000000ull;          // 2 ms without a command: leave
     if (const char *e = getenv("FRMC_PERSIST_IDLE_US")) idle_ns = 1000ull * (unsigned long long)std::max(10, atoi(e));
     FRMC_CUDA(cudaMemsetAsync(s->d_pbars, 0, 2 * sizeof(unsigned long long), s->stream));
-    FRMC_CUDA(cudaMemsetAsync(s->d_cmd, 0, sizeof(unsigned int), s->stream));          // relay seq: 0 is never a command number... (numbers start at 1)
+    FRMC_CUDA(cudaMemsetAsync(s->d_cmd, 0, 2 * sizeof(uint4), s->stream));            // relay chunks: 0 is never a command number
     *reinterpret_cast<volatile unsigned int *>(&s->h_cmd->alive) = 1u;
     _mm_sfence();
     void *args[] = {&s->d_atoms, &npad, &s->h_cmd, &s->d_cmd, &s->d_prop, &s->L, &gs, &nEl, &s->d_overflow, &ms, &s->epi_map, &tc,
