@@ -336,6 +336,35 @@ def test_persistent_kernel_long_run(kind, orc, persistent_mode):
     store.close()
 
 
+def test_two_persistent_stores_take_turns(orc, persistent_mode):
+    """two stores with resident kernels on one GPU cannot run at once (each kernel fills the device): the one
+    that is waiting leaves on its idle watchdog and is restarted later; results stay those of the reference"""
+    case = CASES["ortho_atomic"]
+    rng = np.random.default_rng(77)
+    stores = [_build(case, ["PDF"], rng) for _ in range(2)]
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    args = (kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"], kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+    box = case["boxCoords"]
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+    for st, _ in stores:
+        st.compute_data()
+    for step in range(6):
+        idx = C.group_for(case, rng)
+        moved = (box[idx] + rng.normal(0, 0.02, (idx.shape[0], 3)).astype(F32)).astype(F32)
+        bi, be = ep.move_delta(fns, idx, box, *args)
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, *args)
+        for st, oracles in stores:                              # the same move on both stores, alternating
+            chi2 = st.step(None, idx, moved).copy()
+            total, exp, dw = oracles[0]
+            assert F32(chi2[0]) == F32(ep.standard_error(exp, total(data_i - bi + ai, data_e - be + ae), dw))
+            st.reject()
+    for st, _ in stores:
+        st.close()
+
+
 def test_state_machine_errors():
     from fullrmc_b200.store import DeviceStore
     case = CASES["tiny_13"]
