@@ -1,11 +1,18 @@
 // fullhist.cu -- full-system pair histogram (full_pairs_histograms_coords,
-// Extensions/pairs_histograms.pyx:289-335) as a tiled upper-triangle kernel over the
-// element-sorted atom store (layout.h).
+// Extensions/pairs_histograms.pyx:289-335) over the element-sorted, k-d ordered atom store (layout.h).
 //
-// Bound: FP32 issue slots (O(N^2) arithmetic on O(N) data that lives in shared memory
-// and registers), plus shared-memory atomics for the in-range pairs.  Not HBM, not
-// tensor cores: the minimum image needs exact fp32 wrap/compare sequences that have no
-// GEMM form.  DESIGN.md section "Kernels" has the instruction budget.
+// Pipeline of one launch (full_hist_launch):
+//   block_bbox_kernel    one bounding box per 256-record block and per 32-record sub-block
+//   pair_list_kernel x2  + scan2_kernel: the (I tile, J block) pairs whose boxes are within maxDistance,
+//                        cut into items of <= 8 surviving blocks (exact: a skipped pair cannot hold a hit)
+//   full_hist_kernel     persistent CTAs take items from an atomic counter; sweep with the reference's fp32
+//                        operation order, hits queued per lane and binned by the whole warp, counts in
+//                        CTA-private shared memory, flushed with 64-bit atomics per element pair
+//
+// Bound: FP32 instruction issue on the pairs that cannot be excluded (19 exact operations per distance on the
+// orthorhombic fast path), plus the bin pass of the in-range pairs.  Not HBM (one pass over 20 B/atom) and
+// not tensor cores: the minimum image needs exact fp32 wrap/compare sequences that have no GEMM form.
+// DESIGN.md section 4.1 and profiles/r1_fullhist_ncu_summary.md have the instruction budget and the ncu numbers.
 #include "common.cuh"
 #include "layout.h"
 
@@ -22,7 +29,7 @@ namespace frmc {
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int g_no_cull = 0;
 
-// ------------------------------------------------------------------ host: layout + work list
+// ------------------------------------------------------------------ host: layout + row list
 // k-d ordering of one element's atoms: split the longest box axis at a record count that is a multiple
 // of the unit (1024 = one register-tiled I-tile, then 256 = one block, then 32), so that every aligned
 // group of 1024 / 256 / 32 consecutive records is a compact box -- about 2x fewer surviving block pairs
@@ -228,9 +235,9 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
     return FRMC_OK;
 }
 
-void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, int nshards, std::vector<WorkItem> &items)
+void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vector<WorkItem> &rows)
 {
-    items.clear();
+    rows.clear();
     const int64_t TI = (int64_t)SEG_PAD * R;
     int64_t serial = 0;
     for (int ea = 0; ea < lay.nEl; ++ea) {
@@ -243,26 +250,18 @@ void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, i
             const int64_t b1 = b0 + (lay.seg_count[eb] + SEG_PAD - 1) / SEG_PAD * SEG_PAD;
             for (int64_t i0 = a0; i0 < a1; i0 += TI) {
                 const int64_t i1 = std::min(i0 + TI, a1);
-                for (int64_t c0 = b0; c0 < b1; c0 += chunkJ) {
-                    const int64_t j1 = std::min(c0 + chunkJ, b1);
-                    int64_t j0 = c0;
-                    int tri = 0;
-                    if (ea == eb) {
-                        if (j1 <= i0 + 1) continue;       // no q > p in this chunk
-                        if (j0 < i0) j0 = i0;             // q > p >= i0: records before the I-tile never pair with it
-                        tri = (j0 < i1) ? 1 : 0;          // ranges overlap: per-pair p<q test needed
-                    }
-                    // rows are dealt out boustrophedon (0..S-1, S-1..0, ...): the J range of a same-element row
-                    // shrinks linearly with the tile index, and plain round-robin would hand shard 0 the larger row
-                    // of every group of S
-                    const int64_t pos = serial++ % (2 * (int64_t)nshards);
-                    if ((pos < nshards ? pos : 2 * (int64_t)nshards - 1 - pos) != shard) continue;
-                    WorkItem w;
-                    w.i0 = (int32_t)i0; w.ni = (int32_t)((i1 - i0) / SEG_PAD);
-                    w.j0 = (int32_t)j0; w.j1 = (int32_t)j1;
-                    w.ea = ea; w.eb = eb; w.tri = tri; w.pad = 0;
-                    items.push_back(w);
-                }
+                // same element: q > p >= i0, records before the I-tile never pair with it
+                const int64_t j0 = (ea == eb) ? i0 : b0;
+                // rows are dealt out boustrophedon (0..S-1, S-1..0, ...): the J range of a same-element row
+                // shrinks linearly with the tile index, and plain round-robin would hand shard 0 the larger row
+                // of every group of S
+                const int64_t pos = serial++ % (2 * (int64_t)nshards);
+                if ((pos < nshards ? pos : 2 * (int64_t)nshards - 1 - pos) != shard) continue;
+                WorkItem w;
+                w.i0 = (int32_t)i0; w.ni = (int32_t)((i1 - i0) / SEG_PAD);
+                w.j0 = (int32_t)j0; w.j1 = (int32_t)b1;
+                w.ea = ea; w.eb = eb; w.pad0 = 0; w.pad1 = 0;
+                rows.push_back(w);
             }
         }
     }
@@ -797,15 +796,13 @@ bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[
     return frac < 0.5;
 }
 
-// Tile-shape heuristic: R register atoms per thread (I-tile = 256*R).  R = 4 amortises the shared-
+// Tile-shape heuristic: returns R, the register atoms per thread (I-tile = 256*R).  R = 4 amortises the shared-
 // memory load of a J record over four pairs (23.4 issue slots per pair instead of 26) and is right when
 // every block pair has to be swept; when culling bites, R = 1 keeps the culled unit at one 256-atom block
 // (about 2.5x fewer pairs swept than with a 1024-atom I-tile).
-void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ)
+int choose_tiling(int64_t npad, bool sparse)
 {
-    (void)sm_count; (void)nshards;
-    R = (npad >= 32768 && !sparse) ? 4 : 1;
-    chunkJ = (int64_t)1 << 40;      // a row of the pair list spans the whole J range of its element pair
+    return (npad >= 32768 && !sparse) ? 4 : 1;
 }
 
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2)
@@ -856,10 +853,10 @@ extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int 
     HostLayout lay;
     int rc = build_layout(coords.data(), n, mol.data(), el, nEl, 1, lay);
     if (rc) return rc;
-    int R; int64_t chunkJ;
-    choose_tiling(lay.npad, sm_count > 0 ? sm_count : 148, false, nshards, R, chunkJ);
+    (void)sm_count;
+    const int R = choose_tiling(lay.npad, false);
     std::vector<WorkItem> items;
-    build_work_items(lay, R, chunkJ, shard, nshards, items);
+    build_rows(lay, R, shard, nshards, items);
     auto real_in = [&](int e, int64_t a, int64_t b) -> int64_t {   // real atoms of segment e inside positions [a, b)
         const int64_t end = lay.seg_start[e] + lay.seg_count[e];
         return std::max<int64_t>(0, std::min(b, end) - std::max(a, lay.seg_start[e]));
@@ -915,10 +912,9 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     GridParams g = make_grid(rmin, rmax, bin, hs);
     int mode = choose_mode_from_bounds(L.b, isPBC, lay.lo, lay.hi);
-    int R; int64_t chunkJ;
-    choose_tiling(lay.npad, c->sm_count, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g), nshards, R, chunkJ);
+    const int R = choose_tiling(lay.npad, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g));
     std::vector<WorkItem> items;
-    build_work_items(lay, R, chunkJ, shard, nshards, items);
+    build_rows(lay, R, shard, nshards, items);
 
     float4 *d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float) * 4 * (size_t)lay.npad);
     uint32_t *d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);

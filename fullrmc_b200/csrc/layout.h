@@ -47,17 +47,17 @@ struct HostLayout {
 // isPBC selects how a coordinate maps to a cell (fractional part vs. position inside the bounds).
 int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC, HostLayout &out);
 
-// One ROW of full-histogram work: I-tile [i0, i0 + 256*ni) x J-range [j0, j1) (padded positions; with
-// chunkJ = "everything" the whole J range of the element pair).  ea/eb are the (segment) elements of the
-// two ranges; when ea == eb only pairs p<q count.  The device cuts rows into items of surviving blocks.
+// One ROW of full-histogram work: I-tile [i0, i0 + 256*ni) x the J range [j0, j1) of one element pair
+// (padded positions).  ea/eb are the (segment) elements of the two ranges; when ea == eb the J range starts
+// at the tile and only pairs p<q count.  The device cuts rows into items of surviving blocks.
 struct WorkItem {
     int32_t i0, ni, j0, j1;
-    int32_t ea, eb, tri, pad;
+    int32_t ea, eb, pad0, pad1;
 };
 
 // Builds the upper-triangle row list, ordered by element pair (a CTA walking it flushes its
 // shared-memory counters only when the pair changes); rows with index % nshards == shard are kept.
-void build_work_items(const HostLayout &lay, int R, int64_t chunkJ, int shard, int nshards, std::vector<WorkItem> &items);
+void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vector<WorkItem> &rows);
 
 // Device-side lists of surviving block pairs (fullhist.cu), grow-only, owned by whoever launches the kernel.
 struct PairLists {

@@ -28,7 +28,7 @@ GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
                      int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
                      const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
-void choose_tiling(int64_t npad, int sm_count, bool sparse, int nshards, int &R, int64_t &chunkJ);
+int choose_tiling(int64_t npad, bool sparse);
 bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
 
@@ -1123,7 +1123,6 @@ struct frmc_store {
     PairLists lists;                 // device-built surviving block pairs, cut into items
     int n_items = 0, R = 1;
     int items_shard = -1, items_nshards = -1, items_sparse = -1;   // which slice / tiling of the work list d_items holds
-    int64_t chunkJ = 256;
     HostLayout lay;                  // rec freed after upload; segments + inverse permutation kept
     int *d_next = nullptr;
     unsigned long long *d_overflow = nullptr;   // [0] edge-overflow events, [1] block pairs swept by the last compute_data
@@ -1253,8 +1252,8 @@ static int upload_items(frmc_store *s, int shard, int nshards, bool sparse)
     if (s->d_items && s->items_shard == shard && s->items_nshards == nshards && s->items_sparse == (int)sparse) return FRMC_OK;
     std::vector<WorkItem> items;
     s->items_sparse = (int)sparse;
-    choose_tiling(s->npad, s->ctx->sm_count, sparse, nshards, s->R, s->chunkJ);
-    build_work_items(s->lay, s->R, s->chunkJ, shard, nshards, items);
+    s->R = choose_tiling(s->npad, sparse);
+    build_rows(s->lay, s->R, shard, nshards, items);
     if (s->d_items) { cudaFree(s->d_items); s->d_items = nullptr; }
     s->n_items = (int)items.size();
     FRMC_CUDA(cudaMalloc(&s->d_items, sizeof(WorkItem) * std::max<size_t>(items.size(), 1)));
