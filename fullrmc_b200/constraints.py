@@ -22,7 +22,7 @@ writes to put them behind the real constraint classes.
 """
 import numpy as np
 
-from .model import FLOAT_TYPE, ModelSpec, shell_volumes_from_edges
+from .model import FLOAT_TYPE, PI, ModelSpec, shell_volumes_from_edges
 from .store import DeviceStore
 
 
@@ -42,6 +42,11 @@ class DeviceBackend(object):
             self.store.set_persistent(True)
         self.constraints = []
         self._grids = {}
+        self.basisVectors = np.ascontiguousarray(basisVectors, dtype=FLOAT_TYPE)
+        self.isPBC = bool(isPBC)
+        self.moleculesIndex = np.ascontiguousarray(moleculesIndex, dtype=np.int32)
+        self.elementsIndex = np.ascontiguousarray(elementsIndex, dtype=np.int32)
+        self.accepted = 0            # the engine's accepted-move count (refit and shape-refresh schedules)
         self._move = None            # (indexes, moved) of the proposal being evaluated
         self._chi2 = None            # chi^2 per model of the staged proposal
         self._resolved = True
@@ -104,6 +109,7 @@ class DeviceBackend(object):
             (self.store.accept if accept else self.store.reject)()
             if accept:
                 self._committed = self._chi2.copy()
+                self.accepted += 1
             self._resolved = True
             self._move = None
             self._chi2 = None
@@ -117,7 +123,8 @@ class _DeviceExperimentalConstraint(object):
     KIND = None
 
     def __init__(self, backend, experimentalData, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
-                 weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None, adjustScaleFactor=(0, 0.8, 1.2)):
+                 weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None, adjustScaleFactor=(0, 0.8, 1.2),
+                 shapeFuncParams=None, shapeWeighting=None):
         self.backend = backend
         self.experimentalData = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         self.minimumDistance = FLOAT_TYPE(minDistance)
@@ -134,6 +141,19 @@ class _DeviceExperimentalConstraint(object):
                          backend.numberDensity, self.shellCenters, self.shellVolumes, self.experimentalData,
                          data_weights=dataWeights, shape_array=shapeArray, scale_factor=scaleFactor, q_values=qValues)
         backend._register(self, (self.minimumDistance, self.maximumDistance, self.bin, self.histogramSize), spec)
+        # shape function refreshed from the running configuration (set_shape_function_parameters with a dict,
+        # PairDistributionConstraints.py:502-567): defaults and types as there
+        self._shapeFuncParams, self._shapeUpdateFreq, self._lastShapeUpdate = None, 0, None
+        self._shapeWeighting = shapeWeighting if shapeWeighting is not None else weighting
+        self._shapeArray = None if shapeArray is None else np.ascontiguousarray(shapeArray, dtype=FLOAT_TYPE)
+        if shapeFuncParams is not None:
+            if self.KIND not in ("PDF", "PCF"):
+                raise ValueError("only r-space constraints take shape function parameters")
+            p = dict(shapeFuncParams)
+            self._shapeFuncParams = {"rmin": FLOAT_TYPE(p.get("rmin", 0.00)), "rmax": p.get("rmax", None),
+                                     "dr": FLOAT_TYPE(p.get("dr", 0.5)), "qmin": FLOAT_TYPE(p.get("qmin", 0.001)),
+                                     "qmax": FLOAT_TYPE(p.get("qmax", 0.75)), "dq": FLOAT_TYPE(p.get("dq", 0.005))}
+            self._shapeUpdateFreq = int(p.get("updateFreq", 1000))
         self.adjustScaleFactor = (int(adjustScaleFactor[0]), FLOAT_TYPE(adjustScaleFactor[1]), FLOAT_TYPE(adjustScaleFactor[2]))
         if self.adjustScaleFactor[0]:
             backend.store.set_adjust_scale_factor(self._model, *self.adjustScaleFactor)     # Core/Constraint.py:1196-1230
@@ -156,6 +176,48 @@ class _DeviceExperimentalConstraint(object):
     def fittedScaleFactor(self):
         """the scale factor the last evaluation used (the reference's _fittedScaleFactor)"""
         return self.backend.store.get_scale(self._model)[1]
+
+    # -- shape function (PairDistributionConstraints.py:316-374)
+    def _update_shape_array(self):
+        from . import shape
+        b = self.backend
+        p = self._shapeFuncParams
+        coords = b.store.get_coords()
+        rmax = p["rmax"]
+        if rmax is None:
+            rmax = shape.auto_rmax(b.isPBC, b.basisVectors, coords)        # IBC: box coordinates are the real ones
+        arr = shape.get_Gr_shape_function(self.shellCenters, coords, b.basisVectors, b.isPBC, b.moleculesIndex, b.elementsIndex,
+                                          b.elements, b.numberOfAtomsPerElement, b.volume, self._shapeWeighting,
+                                          qmin=p["qmin"], qmax=p["qmax"], dq=p["dq"], rmin=p["rmin"], rmax=rmax, dr=p["dr"])
+        if self.KIND == "PCF":                                              # get_gr_shape_function (Collection.py:112-126)
+            arr = arr / (FLOAT_TYPE(4.) * PI * b.numberDensity * self.shellCenters)
+        self._shapeArray = arr
+        b.store.set_shape(self._model, arr)
+
+    def _reset_standard_error(self):
+        chi2 = self.backend._evaluate_committed()
+        self.standardError = FLOAT_TYPE(chi2[self._model])
+
+    def runtime_initialize(self):
+        """what Engine.run triggers before the first step (_runtime_initialize, :351-360)"""
+        if self._shapeFuncParams is not None and self._shapeArray is None:
+            self.backend._compute_data()
+            self._update_shape_array()
+        self.backend._compute_data()
+        self._reset_standard_error()
+        self._lastShapeUpdate = self.backend.accepted
+
+    def runtime_on_step(self):
+        """what Engine.run triggers before every step (_runtime_on_step, :362-374); returns True when the shape
+        array was rebuilt (the caller then refreshes the engine's total standard error)"""
+        if self._shapeUpdateFreq and self._shapeFuncParams is not None:
+            acc = self.backend.accepted
+            if self._lastShapeUpdate != acc and not (acc % self._shapeUpdateFreq):
+                self._update_shape_array()
+                self._reset_standard_error()
+                self._lastShapeUpdate = acc
+                return True
+        return False
 
     def get_constraint_total(self, staged=False):
         """model total (G(r), g(r) or S(Q)) of the committed (or staged) state"""
@@ -200,7 +262,7 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
     KIND = "PDF"
 
     def __init__(self, backend, experimentalData, weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0,
-                 adjustScaleFactor=(0, 0.8, 1.2)):
+                 adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         r = exp[:, 0]
         b = FLOAT_TYPE(r[1] - r[0])                                            # :726
@@ -210,7 +272,8 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
         hs = len(edges) - 1
         super(DevicePairDistributionConstraint, self).__init__(
             backend, exp[:, 1], rmin, rmax, b, hs, np.array(r, dtype=FLOAT_TYPE), shell_volumes_from_edges(edges),
-            weighting, dataWeights, shapeArray, scaleFactor, adjustScaleFactor=adjustScaleFactor)
+            weighting, dataWeights, shapeArray, scaleFactor, adjustScaleFactor=adjustScaleFactor,
+            shapeFuncParams=shapeFuncParams, shapeWeighting=shapeWeighting)
 
 
 class DevicePairCorrelationConstraint(DevicePairDistributionConstraint):
@@ -244,7 +307,7 @@ _KIND_CLASS = {}
 
 def make_device_constraint(backend, kind, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
                            weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None,
-                           adjustScaleFactor=(0, 0.8, 1.2)):
+                           adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None):
     """Build a device constraint from the quantities a reference constraint has already derived
     (limits, bin, histogram size, shell arrays, weighting scheme) -- what the subclass recipe of
     INTEGRATION.md hands over."""
@@ -252,4 +315,5 @@ def make_device_constraint(backend, kind, experimental, minDistance, maxDistance
         for name in ("PDF", "PCF", "SQ", "RSQ"):
             _KIND_CLASS[name] = type("Device%sConstraint" % name, (_DeviceExperimentalConstraint,), {"KIND": name})
     return _KIND_CLASS[kind](backend, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
-                             weighting, dataWeights, shapeArray, scaleFactor, qValues, adjustScaleFactor)
+                             weighting, dataWeights, shapeArray, scaleFactor, qValues, adjustScaleFactor, shapeFuncParams,
+                             shapeWeighting)

@@ -1919,6 +1919,29 @@ int frmc_model_set_scale(frmc_store *s, int model, float scale)
     return FRMC_OK;
 }
 
+int frmc_model_set_shape(frmc_store *s, int model, const float *shape)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    ModelHost &mh = s->models[model];
+    FRMC_REQUIRE(mh.dev.kind == FRMC_KIND_PDF || mh.dev.kind == FRMC_KIND_PCF, FRMC_EINVAL, "only r-space models carry a shape array");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }          // also ends a persistent run: its L1 may hold the old array
+    if (!shape) {
+        if (mh.dev.shape) { mh.dev.shape = nullptr; s->models_dirty = true; }
+        return FRMC_OK;
+    }
+    if (!mh.dev.shape) {
+        void *p = nullptr;
+        FRMC_CUDA(cudaMalloc(&p, sizeof(float) * mh.dev.hs));
+        mh.owned.push_back(p);
+        mh.dev.shape = (const float *)p;
+        s->models_dirty = true;
+    }
+    FRMC_CUDA(cudaMemcpyAsync((void *)mh.dev.shape, shape, sizeof(float) * mh.dev.hs, cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    return FRMC_OK;
+}
+
 int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min, float sf_max)
 {
     FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);

@@ -95,6 +95,14 @@ class DeviceStore(object):
     def set_scale(self, model, scale):
         L.check(self._lib.frmc_model_set_scale(self._handle, int(model), float(_F32(scale))), "set_scale")
 
+    def set_shape(self, model, shape_array):
+        """replace (None: drop) the shape-function array of an r-space model; follow with finalize_data()"""
+        if shape_array is None:
+            L.check(self._lib.frmc_model_set_shape(self._handle, int(model), None), "set_shape")
+            return
+        a = np.ascontiguousarray(shape_array, dtype=_F32)
+        L.check(self._lib.frmc_model_set_shape(self._handle, int(model), L.ptr(a, L.c_f32p)), "set_shape")
+
     def set_adjust_scale_factor(self, model, frequency, minimum, maximum):
         """ExperimentalConstraint.set_adjust_scale_factor (Core/Constraint.py:1160-1177): refit the scale factor in
         every evaluation made while accepted % frequency == 0, clipped to [minimum, maximum]; 0 switches it off."""

@@ -183,6 +183,10 @@ int frmc_grid_add(frmc_store *s, float rmin, float rmax, float bin, int hs);
 /* register a model on a grid; returns model id >= 0 */
 int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *desc);
 int frmc_model_set_scale(frmc_store *s, int model, float scale);
+/* replace (or, with NULL, drop) the shape-function array [histSize] an r-space model subtracts
+ * (PairDistributionConstraints.py:882-883): what _update_shape_array does every shapeUpdateFreq accepted
+ * moves (:316-343, :362-374).  Follow with frmc_finalize_data to refresh the committed chi^2. */
+int frmc_model_set_shape(frmc_store *s, int model, const float *shape);
 /* Scale-factor refit (ExperimentalConstraint.set_adjust_scale_factor / fit_scale_factor /
  * get_adjusted_scale_factor, Core/Constraint.py:1363-1423): when frequency > 0 every evaluation made while
  * accepted % frequency == 0 fits SF = sum(w*M*E)/sum(M^2) (numpy fp32 pairwise order, on G(r) for the

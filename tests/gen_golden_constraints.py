@@ -107,16 +107,37 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
             out["c%d/%s" % (ci, k)] = v
     rng = np.random.default_rng(seed)
     start = []
+    shaped = [ci for ci, (c, kind) in enumerate(constraints) if getattr(c, "_shapeFuncParams", None) is not None]
+    shape_log = {ci: [] for ci in shaped}          # (step at which the array was (re)built, array)
+    if shaped:
+        object.__setattr__(E, "_Engine__totalStandardError", 0.0)
+        object.__setattr__(E, "update_total_standard_error", lambda: None)
     for ci, (c, kind) in enumerate(constraints):
         data, err = c.compute_data()
         start.append(np.float32(c.standardError))
         out["c%d/start_intra" % ci], out["c%d/start_inter" % ci] = data["intra"].copy(), data["inter"].copy()
         out["c%d/start_total" % ci] = fit_total(c, kind, E)
+    for ci in shaped:                              # Engine.run: _runtime_initialize builds the first shape array
+        c = constraints[ci][0]
+        c._runtime_initialize()
+        shape_log[ci].append((-1, np.asarray(c._shapeArray, np.float32).copy()))
+        start[ci] = np.float32(c.standardError)
+        out["c%d/start_total" % ci] = fit_total(c, constraints[ci][1], E)
+        out["c%d/shapeFuncParams" % ci] = np.array([c._shapeFuncParams[k] if c._shapeFuncParams[k] is not None else np.nan
+                                                    for k in ("rmin", "rmax", "dr", "qmin", "qmax", "dq")], np.float64)
+        out["c%d/shapeUpdateFreq" % ci] = np.int32(c._shapeUpdateFreq)
     out["start_stdErr"] = np.array(start, np.float32)
     rbasis = np.linalg.inv(basis.astype(np.float64)) if isPBC else np.eye(3)
     idx_log, moved_log, chi_log, acc_log, k_log, sf_log = [], [], [], [], [], []
     total_old = sum(float(c.standardError) for c, _ in constraints)
     for step in range(n_steps):
+        for ci in shaped:                          # Engine.run calls _runtime_on_step before every move
+            c = constraints[ci][0]
+            before = c._lastShapeUpdate
+            c._runtime_on_step()
+            if c._lastShapeUpdate != before:
+                shape_log[ci].append((step, np.asarray(c._shapeArray, np.float32).copy()))
+                total_old = sum(float(cc.standardError) for cc, _ in constraints)
         idx = np.asarray(groups[int(rng.integers(0, len(groups)))], dtype=np.int32)
         shift = (rng.normal(0.0, sigma, (1, 3)) @ rbasis).astype(np.float32)          # rigid translation of the group
         moved = (E.boxCoordinates[idx] + shift).astype(np.float32)
@@ -146,6 +167,9 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
         out["c%d/final_stdErr" % ci] = np.float32(c.standardError)
         out["c%d/final_scaleFactor" % ci] = np.float32(c.scaleFactor)
         out["c%d/final_total" % ci] = fit_total(c, kind, E)
+    for ci in shaped:
+        out["c%d/shape_steps" % ci] = np.array([t for t, _ in shape_log[ci]], np.int32)
+        out["c%d/shape_arrays" % ci] = np.array([a for _, a in shape_log[ci]], np.float32)
     out["final_boxCoords"] = np.asarray(E.boxCoordinates, np.float32).copy()
     path = os.path.join(out_dir, "constraints_%s.npz" % name)
     np.savez_compressed(path, **out)
@@ -226,6 +250,20 @@ def main():
         return cons
     nn = arrays_niti[0].shape[0]
     run_case("niti_sf", fullrmc, arrays_niti, niti_sf, [[i] for i in range(nn)], 40, 11, 0.15, out_dir)
+
+    # ---- config 3 with its shape function (Examples/SiOxNanosphere/run.py:41-47; Constraints/Collection.py:20-125),
+    #      refreshed every 4 accepted moves instead of every 1000
+    d = os.path.join(EX, "SiOxNanosphere")
+    arrays_siox = engine_arrays(*read_pdb(os.path.join(d, "SiOx.pdb")))
+    def siox_shape(E):
+        object.__setattr__(E, "_Engine__numberDensity", FLOAT_TYPE(0.0125))
+        object.__setattr__(E, "_Engine__volume", FLOAT_TYPE(E.numberOfAtoms / 0.0125))
+        pdf = PairDistributionConstraint(experimentalData=os.path.join(d, "SiOx.gr"), weighting="atomicNumber")
+        pdf.set_shape_function_parameters({'rmin': 0., 'rmax': None, 'dr': 0.5, 'qmin': 0.0001, 'qmax': 0.6, 'dq': 0.005,
+                                           'updateFreq': 4})
+        return [(pdf, "PDF")]
+    ns = arrays_siox[0].shape[0]
+    run_case("siox_shape", fullrmc, arrays_siox, siox_shape, [[i] for i in range(ns)], 24, 13, 0.2, out_dir)
 
     # synthetic: g(r) with data weights + full S(Q), refit every 3 accepted moves with a tight clip range
     rng2 = np.random.default_rng(45)

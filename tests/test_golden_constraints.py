@@ -23,7 +23,8 @@ import pytest
 from oracle import epilogue as ep
 
 F32 = np.float32
-NAMES = ["niti", "thf", "siox", "synth", "niti_sf", "synth_sf"]     # *_sf: scale-factor refit switched on
+NAMES = ["niti", "thf", "siox", "synth", "niti_sf", "synth_sf", "siox_shape"]   # *_sf: scale-factor refit; *_shape: shape function refresh
+Z = {"o": 8.0, "si": 14.0, "ti": 22.0, "ni": 28.0, "zr": 40.0, "c": 6.0, "h": 1.0}
 
 
 def _load(golden_dir, name):
@@ -36,6 +37,9 @@ def _constraint_desc(g, ci):
     d["weighting"] = {str(p): F32(w) for p, w in zip(d["pairs"], d["pair_w"])}
     d["dataWeights"] = None if d["dataWeights"].shape[0] == 0 else d["dataWeights"]
     d["shapeArray"] = None if d["shapeArray"].shape[0] == 0 else d["shapeArray"]
+    sp = d.get("shapeFuncParams")
+    d["shapeParams"] = None if sp is None else dict(rmin=sp[0], rmax=None if np.isnan(sp[1]) else sp[1], dr=sp[2], qmin=sp[3],
+                                                    qmax=sp[4], dq=sp[5], updateFreq=int(d["shapeUpdateFreq"]))
     adj = d.get("adjustScaleFactor")
     d["adjust"] = (0, 0.0, 0.0) if adj is None else (int(adj[0]), F32(adj[1]), F32(adj[2]))
     return d
@@ -91,19 +95,46 @@ def test_oracle_restatement_reproduces_reference_classes(name, golden_dir, spill
                                                   maxDistance=d["maxDistance"], bin=d["bin"], histSize=int(d["histSize"]),
                                                   ncores=orc.max_threads())
         assert np.array_equal(hi, d["start_intra"]) and np.array_equal(he, d["start_inter"])
+        data.append([hi, he])
+        if d["shapeParams"] is not None:
+            continue                                       # checked below, once the first shape array exists
         tot, _ = _oracle_total(d, hi, he, elements, n_per, volume, rho0, accepted=0)
         assert np.array_equal(tot, d["start_total"]), "constraint %d total differs from the reference class" % ci
         chi = ep.standard_error(d["experimental"], tot, d["dataWeights"])
         assert F32(chi) == F32(g["start_stdErr"][ci])
-        data.append([hi, he])
     steps = g["steps/idx"].shape[0]
     sfs = [F32(d["scaleFactor"]) for d in descs]          # committed scale factors
     accepted = 0                                           # engine.accepted
+    # shape function refreshed from the running configuration (Collection.py:20-125): host arithmetic of
+    # fullrmc_b200.shape pinned here with the oracle's histogram, on the device in the GPU test
+    from fullrmc_b200 import model as fm, shape as fshape
+    shape_w = fm.faber_ziman_weights(n_per, {e: Z[e] for e in elements})
+    last_shape = {}
+
+    def rebuild_shape(ci, d, coords, k):
+        p = d["shapeParams"]
+        rmax = p["rmax"] if p["rmax"] is not None else fshape.auto_rmax(pbc, basis, coords)
+        arr = fshape.get_Gr_shape_function(d["shellCenters"], coords, basis, pbc, mol, el, elements, n_per, volume, shape_w,
+                                           qmin=p["qmin"], qmax=p["qmax"], dq=p["dq"], rmin=p["rmin"], rmax=rmax, dr=p["dr"],
+                                           full_histogram=lambda **kw: orc.full_pairs_histograms_coords(ncores=orc.max_threads(), **kw))
+        assert np.array_equal(arr, d["shape_arrays"][k]), "constraint %d shape array %d differs from the reference's" % (ci, k)
+        d["shapeArray"] = arr
+        last_shape[ci] = [accepted, k + 1]
+
+    for ci, d in enumerate(descs):
+        if d["shapeParams"] is not None:
+            rebuild_shape(ci, d, box, 0)
+            tot, _ = _oracle_total(d, data[ci][0], data[ci][1], elements, n_per, volume, rho0, accepted=0)
+            assert F32(ep.standard_error(d["experimental"], tot, d["dataWeights"])) == F32(g["start_stdErr"][ci])
     for s in range(steps):
         k = int(g["steps/k"][s])
         idx = g["steps/idx"][s, :k].astype(np.int32)
         moved = g["steps/moved"][s, :k]
         tmp = box.copy(); tmp[idx] = moved
+        for ci, d in enumerate(descs):                      # _runtime_on_step (PairDistributionConstraints.py:362-374)
+            if d["shapeParams"] is not None and last_shape[ci][0] != accepted and accepted % d["shapeParams"]["updateFreq"] == 0:
+                assert int(d["shape_steps"][last_shape[ci][1]]) == s
+                rebuild_shape(ci, d, box, last_shape[ci][1])
         staged, used = [], []
         for ci, d in enumerate(descs):
             args = (basis, pbc, mol, el, len(elements), d["minDistance"], d["maxDistance"], d["bin"], int(d["histSize"]))
@@ -141,8 +172,10 @@ def test_device_constraints_reproduce_reference_classes(name, golden_dir):
 
 
 def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
+    from fullrmc_b200 import model as fm
     g = _load(golden_dir, name)
     elements, n_per = _system(g)
+    shape_w = fm.faber_ziman_weights(n_per, {e: Z[e] for e in elements})
     backend = DeviceBackend(g["boxCoords"], g["basis"], bool(g["isPBC"]), g["moleculeIndex"], g["elementIndex"], elements,
                             n_per, g["volume"], g["numberDensity"])
     nc = int(g["n_constraints"])
@@ -154,10 +187,17 @@ def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
                                                dataWeights=d["dataWeights"], shapeArray=d["shapeArray"],
                                                scaleFactor=float(d["scaleFactor"]),
                                                qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None,
-                                               adjustScaleFactor=d["adjust"])))
+                                               adjustScaleFactor=d["adjust"], shapeFuncParams=d["shapeParams"],
+                                               shapeWeighting=shape_w)))
+    n_shapes = {}
     for ci, (d, c) in enumerate(cons):
         data, err = c.compute_data()
         assert np.array_equal(data["intra"], d["start_intra"]) and np.array_equal(data["inter"], d["start_inter"])
+        if d["shapeParams"] is not None:                    # Engine.run: _runtime_initialize builds the first shape array
+            c.runtime_initialize()
+            assert np.array_equal(c._shapeArray, d["shape_arrays"][0])
+            n_shapes[ci] = 1
+            err = c.standardError
         assert np.array_equal(c.get_constraint_total(), d["start_total"])
         assert F32(err) == F32(g["start_stdErr"][ci])
     steps = g["steps/idx"].shape[0]
@@ -165,6 +205,11 @@ def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
         k = int(g["steps/k"][s])
         idx = g["steps/idx"][s, :k].astype(np.int32)
         moved = np.ascontiguousarray(g["steps/moved"][s, :k])
+        for ci, (d, c) in enumerate(cons):                  # Engine.run: _runtime_on_step before every move
+            if d["shapeParams"] is not None and c.runtime_on_step():
+                assert int(d["shape_steps"][n_shapes[ci]]) == s
+                assert np.array_equal(c._shapeArray, d["shape_arrays"][n_shapes[ci]]), "shape array %d" % n_shapes[ci]
+                n_shapes[ci] += 1
         for d, c in cons:
             c.compute_before_move(idx, idx)
             c.compute_after_move(idx, idx, moved)
@@ -174,6 +219,8 @@ def _replay_on_device(name, golden_dir, DeviceBackend, make_device_constraint):
                 assert F32(c.fittedScaleFactor) == F32(g["steps/scale_used"][s, ci]), "step %d constraint %d scale factor" % (s, ci)
         for d, c in cons:
             (c.accept_move if bool(g["steps/accepted"][s]) else c.reject_move)(idx, idx)
+    for ci, n in n_shapes.items():
+        assert n == len(cons[ci][0]["shape_steps"])          # every refresh of the reference happened here too
     refits = any(d["adjust"][0] for d, _ in cons)
     for ci, (d, c) in enumerate(cons):
         data = c.data
