@@ -76,6 +76,8 @@ SIGNATURES = {
     "frmc_model_add": (_I, [_VP, _I, ctypes.POINTER(ModelDesc)]),
     "frmc_model_set_scale": (_I, [_VP, _I, _F]),
     "frmc_model_set_shape": (_I, [_VP, _I, c_f32p]),
+    "frmc_model_set_window": (_I, [_VP, _I, c_f32p, _I]),
+    "frmc_model_set_multiframe_prior": (_I, [_VP, _I, c_f32p, _F]),
     "frmc_model_set_adjust": (_I, [_VP, _I, _I, _F, _F]),
     "frmc_model_get_scale": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_store_set_accepted": (_I, [_VP, ctypes.c_uint64]),

@@ -177,6 +177,21 @@ class _DeviceExperimentalConstraint(object):
         """the scale factor the last evaluation used (the reference's _fittedScaleFactor)"""
         return self.backend.store.get_scale(self._model)[1]
 
+    # -- optional tail of the total (PairDistributionConstraints.py:676-713; Core/Constraint.py:1160-1177)
+    def set_window_function(self, windowFunction):
+        """windowFunction: float32 array no longer than the data, or None; normalised here like the reference does"""
+        if windowFunction is not None:
+            windowFunction = np.array(windowFunction, dtype=FLOAT_TYPE)
+            windowFunction /= np.sum(windowFunction)
+        self.windowFunction = windowFunction
+        self.backend.store.set_window_function(self._model, windowFunction)
+        self.backend._dirty = True
+
+    def set_multiframe_prior(self, multiframePrior, multiframeWeight):
+        """total = multiframePrior + multiframeWeight * total; (None, None) switches it off"""
+        self.backend.store.set_multiframe_prior(self._model, multiframePrior, 0.0 if multiframeWeight is None else multiframeWeight)
+        self.backend._dirty = True
+
     # -- shape function (PairDistributionConstraints.py:316-374)
     def _update_shape_array(self):
         from . import shape

@@ -85,6 +85,10 @@ struct ModelDev {
     int n_stages;                    // S(Q) ring depth chosen by the host from the shared-memory budget
     int refit;                       // this evaluation refits the scale factor (engine.accepted % frequency == 0; set per launch)
     float sf_min, sf_max;            // clip range of the fitted value (Core/Constraint.py:1392-1393)
+    const float *prior;              // [n_out] multiframe prior or NULL: total = prior + mf_weight * total (Core/Constraint.py:1160-1177)
+    float mf_weight;
+    const float *window;             // [n_window] normalised window function or NULL: total = np.convolve(total, window, "same")
+    int n_window;
     // pair table inline (n_pairs <= EPI_INLINE_PAIRS): travels in the kernel parameters, no dependent load
     int i_psym[EPI_INLINE_PAIRS];
     float i_w[EPI_INLINE_PAIRS], i_D[EPI_INLINE_PAIRS], i_rD[EPI_INLINE_PAIRS];
@@ -484,6 +488,18 @@ struct EpiShared {
     unsigned long long mbar[SQ_MAX_STAGES];
 };
 
+// element i of np.convolve(a, v, "same") for len(a) = n >= len(v) = nw (sequential fp32 accumulation; numpy's
+// correlate uses its dot kernel, whose summation order is not specified: this branch is within 1e-6, not bit-exact)
+template <typename FA>
+__device__ __forceinline__ float convolve_same(FA a, int n, const float *__restrict__ v, int nw, int i)
+{
+    const int nf = i + (nw - 1) / 2;
+    const int m0 = max(0, nf - (nw - 1)), m1 = min(n - 1, nf);
+    float acc = 0.0f;
+    for (int m = m0; m <= m1; ++m) acc = __fadd_rn(acc, __fmul_rn(a(m), v[nf - m]));
+    return acc;
+}
+
 // ExperimentalConstraint.fit_scale_factor (Core/Constraint.py:1363-1395): SF = sum(w*M*E) / sum(M**2) in
 // numpy's fp32 pairwise order, clipped.  mv/ev = model / experimental value of element i as the calling
 // constraint hands them over (G(r); 4*pi*r*rho0*(g-1); S(Q)-1).  Whole CTA; result in es.s_sf.
@@ -636,7 +652,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 if (r >= hs) continue;
                 float a = __fdiv_rn(acc[j], svr[j]);
                 float out;
-                const bool defer = M.refit && !is_sq;      // r-space refit: scale applied after the fit below
+                const bool defer = !is_sq && (M.refit || M.prior || M.window);   // scale, prior, window applied in stage 1b
                 if (M.kind == FRMC_KIND_PCF) {
                     out = a;
                     if (M.shape) out = __fsub_rn(out, shp[j]);
@@ -673,15 +689,19 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     float chi2 = 0.f;
     if (tid == 0) es.s_sf = M.scale;
     if (!is_sq) {
-        if (M.refit) {
+        if (M.refit || M.prior || M.window) {
             // ---- 1b. scale-factor refit on the unscaled function (PairDistributionConstraints.py:886-888;
-            //          PairCorrelationConstraints.py:171-184 fits on G(r) = 4 pi r rho0 (g - 1))
-            if (M.kind == FRMC_KIND_PCF)
-                fit_scale_factor(es, sT, M, hs, [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(sG[i], 1.0f)); },
-                                 [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(M.expv[i], 1.0f)); });
-            else
-                fit_scale_factor(es, sT, M, hs, [&](int i) { return sG[i]; }, [&](int i) { return M.expv[i]; });
-            const float sf = es.s_sf;
+            //          PairCorrelationConstraints.py:171-184 fits on G(r) = 4 pi r rho0 (g - 1)), then scale,
+            //          multiframe prior (:890) and window convolution (:892-893)
+            float sf = M.scale;
+            if (M.refit) {
+                if (M.kind == FRMC_KIND_PCF)
+                    fit_scale_factor(es, sT, M, hs, [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(sG[i], 1.0f)); },
+                                     [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(M.expv[i], 1.0f)); });
+                else
+                    fit_scale_factor(es, sT, M, hs, [&](int i) { return sG[i]; }, [&](int i) { return M.expv[i]; });
+                sf = es.s_sf;
+            }
             for (int i = tid; i < hs; i += EPI_THREADS) {
                 float out = sG[i];
                 if (sf != 1.0f) {
@@ -693,9 +713,17 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                         out = __fmul_rn(out, sf);
                     }
                 }
+                if (M.prior) out = __fadd_rn(M.prior[i], __fmul_rn(M.mf_weight, out));
                 sG[i] = out;
-                M.rfun[i] = out; M.total[i] = out;
             }
+            __syncthreads();
+            if (M.window) {
+                for (int i = tid; i < hs; i += EPI_THREADS) sT[i] = convolve_same([&](int m) { return sG[m]; }, hs, M.window, M.n_window, i);
+                __syncthreads();
+                for (int i = tid; i < hs; i += EPI_THREADS) sG[i] = sT[i];
+                __syncthreads();
+            }
+            for (int i = tid; i < hs; i += EPI_THREADS) { M.rfun[i] = sG[i]; M.total[i] = sG[i]; }
             __syncthreads();
         }
         // ---- 2. chi^2 of an r-space model
@@ -770,9 +798,9 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 float sv = acc;
                 if (M.kind == FRMC_KIND_SQ) {
                     sv = __fadd_rn(sv, 1.0f);
-                    if (!M.refit && M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
+                    if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
                 } else {
-                    if (!M.refit && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                                      // (:1258-1260)
+                    if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                            // (:1258-1260)
                 }
                 M.total[q0 + lane] = sv;
             }
@@ -790,18 +818,31 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         EPI_STAMP(4);
         if (!s_last) return;
         __threadfence();
-        if (M.refit) {
+        if (M.refit || M.prior || M.window) {
             // ---- 3b. refit on S(Q)-1 against experimental-1 (StructureFactorConstraints.py:824-834, inherited by
-            //          the reduced constraint), then scale the slices the other CTAs left unscaled
-            fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(M.total + i), 1.0f); },
-                             [&](int i) { return __fsub_rn(M.expv[i], 1.0f); });
-            const float sf = es.s_sf;
-            if (sf != 1.0f)
-                for (int i = tid; i < nq; i += EPI_THREADS) {
-                    const float sv = __ldcg(M.total + i);
-                    M.total[i] = (M.kind == FRMC_KIND_SQ) ? __fadd_rn(__fmul_rn(sf, __fsub_rn(sv, 1.0f)), 1.0f) : __fmul_rn(sf, sv);
-                }
+            //          the reduced constraint), then scale the slices the other CTAs left unscaled, prior, window
+            float sf = M.scale;
+            if (M.refit) {
+                fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(M.total + i), 1.0f); },
+                                 [&](int i) { return __fsub_rn(M.expv[i], 1.0f); });
+                sf = es.s_sf;
+            }
+            for (int i = tid; i < nq; i += EPI_THREADS) {
+                float sv = __ldcg(M.total + i);
+                if (sf != 1.0f) sv = (M.kind == FRMC_KIND_SQ) ? __fadd_rn(__fmul_rn(sf, __fsub_rn(sv, 1.0f)), 1.0f) : __fmul_rn(sf, sv);
+                if (M.prior) sv = __fadd_rn(M.prior[i], __fmul_rn(M.mf_weight, sv));
+                M.total[i] = sv;
+            }
+            __threadfence();
             __syncthreads();
+            if (M.window) {
+                for (int i = tid; i < nq; i += EPI_THREADS)
+                    sT[i] = convolve_same([&](int m) { return __ldcg(M.total + m); }, nq, M.window, M.n_window, i);
+                __syncthreads();
+                for (int i = tid; i < nq; i += EPI_THREADS) M.total[i] = sT[i];
+                __threadfence();
+                __syncthreads();
+            }
         }
         for (int i = tid; i < nq; i += EPI_THREADS) {
             float d = __fsub_rn(M.expv[i], __ldcg(M.total + i));
@@ -1940,6 +1981,39 @@ int frmc_model_set_shape(frmc_store *s, int model, const float *shape)
     FRMC_CUDA(cudaMemcpyAsync((void *)mh.dev.shape, shape, sizeof(float) * mh.dev.hs, cudaMemcpyHostToDevice, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     return FRMC_OK;
+}
+
+// replace one optional per-model array (device copy owned by the model); n == 0 / NULL switches it off
+static int set_model_array(frmc_store *s, ModelHost &mh, const float **slot, const float *src, size_t n)
+{
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    s->models_dirty = true;                    // the descriptor travels by value with every launch
+    if (!src || n == 0) { *slot = nullptr; return FRMC_OK; }
+    void *p = nullptr;
+    FRMC_CUDA(cudaMalloc(&p, sizeof(float) * n));
+    mh.owned.push_back(p);
+    FRMC_CUDA(cudaMemcpyAsync(p, src, sizeof(float) * n, cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    *slot = (const float *)p;
+    return FRMC_OK;
+}
+
+int frmc_model_set_window(frmc_store *s, int model, const float *window, int n_window)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    ModelHost &mh = s->models[model];
+    FRMC_REQUIRE(n_window >= 0 && n_window <= mh.dev.n_out, FRMC_EINVAL, "window length %d outside 0..%d", n_window, mh.dev.n_out);
+    mh.dev.n_window = window ? n_window : 0;
+    return set_model_array(s, mh, &mh.dev.window, window, (size_t)n_window);
+}
+
+int frmc_model_set_multiframe_prior(frmc_store *s, int model, const float *prior, float weight)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    ModelHost &mh = s->models[model];
+    mh.dev.mf_weight = weight;
+    return set_model_array(s, mh, &mh.dev.prior, prior, (size_t)mh.dev.n_out);
 }
 
 int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min, float sf_max)

@@ -103,6 +103,24 @@ class DeviceStore(object):
         a = np.ascontiguousarray(shape_array, dtype=_F32)
         L.check(self._lib.frmc_model_set_shape(self._handle, int(model), L.ptr(a, L.c_f32p)), "set_shape")
 
+    def set_window_function(self, model, window):
+        """normalised window function convolved with the model total (set_window_function,
+        PairDistributionConstraints.py:676-713); None switches it off"""
+        if window is None:
+            L.check(self._lib.frmc_model_set_window(self._handle, int(model), None, 0), "set_window_function")
+            return
+        w = np.ascontiguousarray(window, dtype=_F32)
+        L.check(self._lib.frmc_model_set_window(self._handle, int(model), L.ptr(w, L.c_f32p), int(w.shape[0])), "set_window_function")
+
+    def set_multiframe_prior(self, model, prior, weight):
+        """total = prior + weight * total (Core/Constraint.py:1160-1177); prior None switches it off"""
+        if prior is None:
+            L.check(self._lib.frmc_model_set_multiframe_prior(self._handle, int(model), None, 0.0), "set_multiframe_prior")
+            return
+        a = np.ascontiguousarray(prior, dtype=_F32)
+        L.check(self._lib.frmc_model_set_multiframe_prior(self._handle, int(model), L.ptr(a, L.c_f32p), float(_F32(weight))),
+                "set_multiframe_prior")
+
     def set_adjust_scale_factor(self, model, frequency, minimum, maximum):
         """ExperimentalConstraint.set_adjust_scale_factor (Core/Constraint.py:1160-1177): refit the scale factor in
         every evaluation made while accepted % frequency == 0, clipped to [minimum, maximum]; 0 switches it off."""

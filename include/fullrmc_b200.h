@@ -187,6 +187,13 @@ int frmc_model_set_scale(frmc_store *s, int model, float scale);
  * (PairDistributionConstraints.py:882-883): what _update_shape_array does every shapeUpdateFreq accepted
  * moves (:316-343, :362-374).  Follow with frmc_finalize_data to refresh the committed chi^2. */
 int frmc_model_set_shape(frmc_store *s, int model, const float *shape);
+/* window function (set_window_function, PairDistributionConstraints.py:676-713; already normalised by the
+ * caller as there): total = np.convolve(total, window, "same") after scale and prior (:892-893).  This branch
+ * is within 1e-6 of numpy, not bit-exact (numpy's dot kernel fixes no summation order).  NULL / 0: off. */
+int frmc_model_set_window(frmc_store *s, int model, const float *window, int n_window);
+/* multiframe prior and weight (Core/Constraint.py:1160-1177): total = prior + weight * total, between the scale
+ * factor and the window.  prior [n_out]; NULL: off. */
+int frmc_model_set_multiframe_prior(frmc_store *s, int model, const float *prior, float weight);
 /* Scale-factor refit (ExperimentalConstraint.set_adjust_scale_factor / fit_scale_factor /
  * get_adjusted_scale_factor, Core/Constraint.py:1363-1423): when frequency > 0 every evaluation made while
  * accepted % frequency == 0 fits SF = sum(w*M*E)/sum(M^2) (numpy fp32 pairwise order, on G(r) for the

@@ -166,6 +166,16 @@ def total_Sq(intra, inter, elements, n_per_element, weighting, volume, rho0, she
     return Sq
 
 
+def apply_prior_and_window(total, prior=None, weight=None, window=None):
+    """tail of __get_total_Gr / __get_total_gr / __get_total_Sq after the scale factor: multiframe prior
+    (Core/Constraint.py:1160-1177) then window convolution (PairDistributionConstraints.py:890-893)."""
+    if weight is not None:
+        total = prior + FLOAT_TYPE(weight) * total
+    if window is not None:
+        total = np.convolve(total, window, 'same')
+    return total
+
+
 def standard_error(experimental, model, data_weights=None):
     """compute_standard_error (PairDistributionConstraints.py:810-838; StructureFactorConstraints.py:742-770)."""
     diff = experimental - model

@@ -365,6 +365,60 @@ def test_two_persistent_stores_take_turns(orc, persistent_mode):
         st.close()
 
 
+@pytest.mark.parametrize("kinds", [("PDF", "SQ"), ("PCF", "RSQ")])
+def test_window_function_and_multiframe_prior(kinds, orc):
+    """the optional tail of the model totals: total = convolve(prior + weight * total, window, "same")
+    (Core/Constraint.py:1160-1177, PairDistributionConstraints.py:890-893).  numpy's convolution fixes no summation
+    order, so this branch is held to 1e-6 (the north-star tolerance), not to bit equality."""
+    case = CASES["ortho_atomic"]
+    rng = np.random.default_rng(3)
+    store, oracles = _build(case, list(kinds), rng, scale=0.93)
+    tails = []
+    for m, (total, exp, dw) in enumerate(oracles):
+        n_out = exp.shape[0]
+        window = np.hanning(9 + 2 * m).astype(F32); window /= np.sum(window)
+        prior = (0.05 * rng.standard_normal(n_out)).astype(F32)
+        weight = F32(0.6 + 0.1 * m)
+        store.set_multiframe_prior(m, prior, weight)
+        store.set_window_function(m, window)
+        tails.append((prior, weight, window))
+    kw = _hist_kw(case)
+    mol, el = case["moleculeIndex"], case["elementIndex"]
+    box = case["boxCoords"].copy()
+    fns = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords)
+    args = (kw["basis"], kw["isPBC"], mol, el, kw["numberOfElements"], kw["minDistance"], kw["maxDistance"], kw["bin"], kw["histSize"])
+    data_i, data_e = orc.full_pairs_histograms_coords(boxCoords=box, moleculeIndex=mol, elementIndex=el, **kw)
+
+    def check(chi2, intra, inter, staged):
+        for m, (total, exp, dw) in enumerate(oracles):
+            prior, weight, window = tails[m]
+            ref = ep.apply_prior_and_window(total(intra, inter), prior, weight, window)
+            got = store.export_total(m, staged=staged)
+            scale = float(np.max(np.abs(ref)))
+            assert np.max(np.abs(got - ref)) <= 1e-6 * scale, "model %d total" % m
+            ref_chi = float(ep.standard_error(exp, ref, dw))
+            assert abs(float(chi2[m]) - ref_chi) <= 2e-6 * abs(ref_chi), "model %d chi2" % m
+
+    check(store.compute_data(), data_i, data_e, staged=False)
+    for step in range(4):
+        idx = C.group_for(case, rng)
+        moved = (box[idx] + rng.normal(0, 0.02, (idx.shape[0], 3)).astype(F32)).astype(F32)
+        bi, be = ep.move_delta(fns, idx, box, *args)
+        tmp = box.copy(); tmp[idx] = moved
+        ai, ae = ep.move_delta(fns, idx, tmp, *args)
+        chi2 = store.propose(idx, moved)
+        check(chi2, data_i - bi + ai, data_e - be + ae, staged=True)
+        store.accept()
+        data_i, data_e, box = data_i - bi + ai, data_e - be + ae, tmp
+    # switching both off restores the bit-exact totals
+    for m in range(len(oracles)):
+        store.set_multiframe_prior(m, None, 0.0)
+        store.set_window_function(m, None)
+    chi2 = store.compute_data()
+    _check_models(store, oracles, data_i, data_e, chi2, staged=False)
+    store.close()
+
+
 def test_state_machine_errors():
     from fullrmc_b200.store import DeviceStore
     case = CASES["tiny_13"]
