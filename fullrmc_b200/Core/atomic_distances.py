@@ -1,0 +1,71 @@
+"""Drop-in for the coordinate entry points of ``fullrmc.Core.atomic_distances`` (reference:
+Extensions/atomic_distances.pyx), the hot loop of InterMolecularDistanceConstraint and its relatives
+(Constraints/DistanceConstraints.py:552-737).
+
+``multiple_atomic_distances_coords`` (:326-417) and ``full_atomic_distances_coords`` (:500-567) keep the
+reference's names, keyword names, dtypes and return convention ``(nintra, dintra, ninter, dinter)``, each a new
+``[numberOfElements, numberOfElements, 1]`` array (int32 counts, float32 distance sums).  Results are bit-identical
+to the reference, float sums included: the device adds the hits in the reference's loop order
+(csrc/atomdist.cu).  ``ncores`` is accepted and ignored.
+"""
+import numpy as np
+
+from .. import _lib as L
+
+_F32, _I32 = np.float32, np.int32
+
+
+def _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance):
+    return (int(bool(interMolecular)) | int(bool(intraMolecular)) << 1 | int(bool(countWithinLimits)) << 2 |
+            int(bool(reduceDistanceToUpper)) << 3 | int(bool(reduceDistanceToLower)) << 4 | int(bool(reduceDistance)) << 5)
+
+
+def _limits(lowerLimit, upperLimit, nT):
+    lo = L.as_array(lowerLimit, "lowerLimit", _F32, 3)
+    up = L.as_array(upperLimit, "upperLimit", _F32, 3)
+    for name, a in (("lowerLimit", lo), ("upperLimit", up)):
+        # the reference's own assertions (atomic_distances.pyx:369-371)
+        assert a.shape[0] == a.shape[1] and a.shape[0] == nT, \
+            "%s array must have numberOfElements columns and numberOfElements rows" % name
+        assert a.shape[2] == 1, "%s array third dimension must have a length of exactly 1" % name
+    return np.ascontiguousarray(lo), np.ascontiguousarray(up)
+
+
+def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements,
+                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, reduceDistance=False,
+                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, countWithinLimits=True,
+                                     allAtoms=True, ncores=1):
+    """atomic_distances.pyx:326-417"""
+    lib = L.load_library()
+    idx = L.as_array(indexes, "indexes", _I32, 1)
+    coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
+    b = L.as_array(basis, "basis", _F32, 2)
+    mol = L.as_array(moleculeIndex, "moleculeIndex", _I32, 1)
+    el = L.as_array(elementIndex, "elementIndex", _I32, 1)
+    nT = int(numberOfElements)
+    lo, up = _limits(lowerLimit, upperLimit, nT)
+    n = coords.shape[0]
+    if mol.shape[0] != n or el.shape[0] != n:
+        raise ValueError("moleculeIndex/elementIndex length must equal the number of atoms (%d)" % n)
+    nintra = np.zeros((nT, nT, 1), _I32); ninter = np.zeros((nT, nT, 1), _I32)
+    dintra = np.zeros((nT, nT, 1), _F32); dinter = np.zeros((nT, nT, 1), _F32)
+    rc = lib.frmc_multiple_atomic_distances_coords(
+        L.device_index(), L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(coords, L.c_f32p), n, L.ptr(b, L.c_f32p), int(bool(isPBC)),
+        L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p), nT, L.ptr(lo, L.c_f32p), L.ptr(up, L.c_f32p),
+        _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance),
+        int(bool(allAtoms)), L.ptr(nintra, L.c_i32p), L.ptr(dintra, L.c_f32p), L.ptr(ninter, L.c_i32p), L.ptr(dinter, L.c_f32p))
+    L.check(rc, "multiple_atomic_distances_coords")
+    return nintra, dintra, ninter, dinter
+
+
+def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, lowerLimit, upperLimit,
+                                 interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=False,
+                                 reduceDistanceToLower=False, countWithinLimits=True, ncores=1):
+    """atomic_distances.pyx:500-567"""
+    coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
+    return multiple_atomic_distances_coords(np.arange(coords.shape[0], dtype=_I32), coords, basis, isPBC, moleculeIndex,
+                                            elementIndex, numberOfElements, lowerLimit, upperLimit, interMolecular=interMolecular,
+                                            intraMolecular=intraMolecular, reduceDistance=reduceDistance,
+                                            reduceDistanceToUpper=reduceDistanceToUpper,
+                                            reduceDistanceToLower=reduceDistanceToLower, countWithinLimits=countWithinLimits,
+                                            allAtoms=False, ncores=ncores)

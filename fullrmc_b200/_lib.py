@@ -58,6 +58,10 @@ SIGNATURES = {
                                                    _F, _F, _F, _I, _I, c_f32p, c_f32p, c_u64p]),
     "frmc_full_pairs_histograms_coords": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, _F, _F, _F, _I,
                                                _I, _I, c_f32p, c_f32p, c_u64p]),
+    "frmc_multiple_atomic_distances_coords": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, c_f32p, c_f32p, _I, _I,
+                                                   c_i32p, c_f32p, c_i32p, c_f32p]),
+    "frmc_full_atomic_distances_coords": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, c_f32p, c_f32p, _I,
+                                               c_i32p, c_f32p, c_i32p, c_f32p]),
     "frmc_debug_work_items": (_I, [_I64, c_i32p, _I, _I, _I, _I, c_i64p, c_i64p]),
     "frmc_debug_layout": (_I, [_I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,

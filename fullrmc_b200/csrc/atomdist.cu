@@ -1,0 +1,240 @@
+// atomdist.cu -- the distance-constraint kernels of Extensions/atomic_distances.pyx:
+// multiple_atomic_distances_coords (:326-417) and full_atomic_distances_coords (:500-567), i.e. for every listed
+// atom a and every other atom i >= start the pairs whose distance lies inside (or, countWithinLimits = 0,
+// outside) the [lower, upper) window of their type pair contribute one count and their (optionally reduced)
+// distance to [type_a, type_i] of the intra- or inter-molecular arrays.
+//
+// Parity contract: counts are integers; the distance SUMS are float32 `+=` in the reference's loop order (listed
+// atom, then i ascending), which a parallel reduction cannot reproduce.  So the sweep (same exact fp32 distance
+// arithmetic and d^2 thresholds as the histogram kernels) only EMITS the hits -- key (row, i), payload (slot,
+// value) -- into a device list; the list is radix-sorted by key (cub) and one thread per output cell adds its
+// entries in that order.  Hits are the exception by construction (the constraint exists to keep atoms apart);
+// the list grows on demand and the call fails loudly beyond FRMC_ATOMDIST_MAX_HITS.
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstring>
+#include <vector>
+
+namespace frmc {
+
+enum : int { AD_INTER = 1, AD_INTRA = 2, AD_WITHIN = 4, AD_TO_UPPER = 8, AD_TO_LOWER = 16, AD_REDUCE = 32 };
+static const unsigned long long FRMC_ATOMDIST_MAX_HITS = 1ull << 28;
+
+struct AdRow { float x, y, z; int mol; int type; int index; int start; int row; };
+static const int AD_ROWS = 128;
+static const int AD_MAX_TYPES = 16;
+
+struct AdLimits {                    // per [type_i * nT + type_a]: window and its exact d^2 thresholds
+    float lower[AD_MAX_TYPES * AD_MAX_TYPES], upper[AD_MAX_TYPES * AD_MAX_TYPES];
+    float t2lower[AD_MAX_TYPES * AD_MAX_TYPES], t2upper[AD_MAX_TYPES * AD_MAX_TYPES];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+atomdist_hits_kernel(const float *__restrict__ coords, const int *__restrict__ mol, const int *__restrict__ type, long long n,
+                     const int *__restrict__ idx, long long k, int allAtoms, Lattice L, const AdLimits *__restrict__ lim, int nT,
+                     int flags, int *__restrict__ counts /* [2][nT*nT] */, unsigned long long *__restrict__ n_hits,
+                     unsigned long long capacity, unsigned long long *__restrict__ keys, unsigned long long *__restrict__ vals)
+{
+    __shared__ AdRow rows[AD_ROWS];
+    __shared__ float s_lo[AD_MAX_TYPES * AD_MAX_TYPES], s_up[AD_MAX_TYPES * AD_MAX_TYPES];
+    __shared__ float s_t2lo[AD_MAX_TYPES * AD_MAX_TYPES], s_t2up[AD_MAX_TYPES * AD_MAX_TYPES];
+    for (int t = threadIdx.x; t < nT * nT; t += blockDim.x) {
+        s_lo[t] = lim->lower[t]; s_up[t] = lim->upper[t]; s_t2lo[t] = lim->t2lower[t]; s_t2up[t] = lim->t2upper[t];
+    }
+    const bool inter = flags & AD_INTER, intra = flags & AD_INTRA, within = flags & AD_WITHIN;
+    for (long long r0 = (long long)blockIdx.y * AD_ROWS; r0 < k; r0 += (long long)gridDim.y * AD_ROWS) {
+        const int nr = (int)min((long long)AD_ROWS, k - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr; t += blockDim.x) {
+            const int a = idx[r0 + t];
+            AdRow r;
+            r.x = coords[3 * (long long)a]; r.y = coords[3 * (long long)a + 1]; r.z = coords[3 * (long long)a + 2];
+            r.mol = mol[a]; r.type = type[a]; r.index = a; r.start = allAtoms ? 0 : a; r.row = (int)(r0 + t);
+            rows[t] = r;
+        }
+        __syncthreads();
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const float xi = coords[3 * i], yi = coords[3 * i + 1], zi = coords[3 * i + 2];
+            const int mi = mol[i], ti = type[i];
+            for (int t = 0; t < nr; ++t) {
+                const AdRow &r = rows[t];
+                if (i < r.start || i == r.index) continue;
+                const bool same = (mi == r.mol);
+                if (same ? !intra : !inter) continue;
+                const float d2 = dist2<MODE>(r.x, r.y, r.z, xi, yi, zi, L);
+                const int w = ti * nT + r.type;                    // limits are indexed [type_i, type_a] (:77-78)
+                // distance >= lower && distance < upper  <=>  d2 >= t2lower && d2 < t2upper (exact, common.cuh)
+                const bool in_window = (d2 >= s_t2lo[w]) && (d2 < s_t2up[w]);
+                // the reference skips NaN distances nowhere: `d < lower` and `d >= upper` are both false for NaN, so a
+                // NaN pair counts when countWithinLimits (and its sum becomes NaN); outside-mode skips it only if it is
+                // in the window, which a NaN never is
+                const bool is_nan = d2 != d2;
+                const bool hit = within ? (in_window || is_nan) : !in_window;
+                if (!hit) continue;
+                float d = __fsqrt_rn(d2);
+                const float lower = s_lo[w], upper = s_up[w];
+                if (flags & AD_TO_UPPER) d = fabsf(__fsub_rn(upper, d));
+                else if (flags & AD_TO_LOWER) d = fabsf(__fsub_rn(lower, d));
+                else if (flags & AD_REDUCE) d = (d > __fdiv_rn(__fadd_rn(lower, upper), 2.0f)) ? fabsf(__fsub_rn(upper, d)) : fabsf(__fsub_rn(lower, d));
+                const int cell = (same ? 0 : nT * nT) + r.type * nT + ti;   // outputs are indexed [type_a, type_i] (:111-117)
+                atomicAdd(&counts[cell], 1);
+                const unsigned long long at = atomicAdd(n_hits, 1ull);
+                if (at < capacity) {
+                    keys[at] = ((unsigned long long)(unsigned)r.row << 32) | (unsigned long long)(unsigned)i;
+                    vals[at] = ((unsigned long long)(unsigned)cell << 32) | (unsigned long long)__float_as_uint(d);
+                }
+            }
+        }
+    }
+}
+
+// one thread per output cell walks the (row, i)-sorted hits and adds its own in that order
+__global__ void atomdist_sum_kernel(const unsigned long long *__restrict__ vals, unsigned long long n_hits, int cells,
+                                    float *__restrict__ sums)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= cells) return;
+    float acc = 0.0f;
+    for (unsigned long long e = 0; e < n_hits; ++e) {
+        const unsigned long long v = vals[e];
+        if ((int)(v >> 32) == cell) acc = __fadd_rn(acc, __uint_as_float((unsigned)v));
+    }
+    sums[cell] = acc;
+}
+
+}  // namespace frmc
+
+using namespace frmc;
+
+// grow-only hit-list scratch per device (keys, values and their sorted copies, cub temp storage)
+struct AdScratch {
+    unsigned long long *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    void *temp = nullptr;
+    size_t cap = 0, temp_bytes = 0;
+};
+static AdScratch g_ad[64];
+
+static int ad_reserve(AdScratch &sc, size_t cap, cudaStream_t stream)
+{
+    if (sc.cap >= cap) return FRMC_OK;
+    FRMC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(sc.keys); cudaFree(sc.vals); cudaFree(sc.keys2); cudaFree(sc.vals2); cudaFree(sc.temp);
+    sc = AdScratch();
+    FRMC_CUDA(cudaMalloc((void **)&sc.keys, sizeof(unsigned long long) * cap));
+    FRMC_CUDA(cudaMalloc((void **)&sc.vals, sizeof(unsigned long long) * cap));
+    FRMC_CUDA(cudaMalloc((void **)&sc.keys2, sizeof(unsigned long long) * cap));
+    FRMC_CUDA(cudaMalloc((void **)&sc.vals2, sizeof(unsigned long long) * cap));
+    size_t bytes = 0;
+    FRMC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)std::min<size_t>(cap, 1u << 30), 0, 64, stream));
+    FRMC_CUDA(cudaMalloc(&sc.temp, bytes));
+    sc.temp_bytes = bytes;
+    sc.cap = cap;
+    return FRMC_OK;
+}
+
+extern "C" int frmc_multiple_atomic_distances_coords(int dev, const int32_t *indexes, int64_t k, const float *coords, int64_t n,
+                                                     const float *basis, int isPBC, const int32_t *mol, const int32_t *type, int nT,
+                                                     const float *lowerLimit, const float *upperLimit, int flags, int allAtoms,
+                                                     int32_t *nintra, float *dintra, int32_t *ninter, float *dinter)
+{
+    FRMC_REQUIRE(n >= 0 && k >= 0, FRMC_EINVAL, "negative size");
+    FRMC_REQUIRE(nT >= 1 && nT <= AD_MAX_TYPES, FRMC_ELIMIT, "numberOfElements %d outside 1..%d", nT, AD_MAX_TYPES);
+    FRMC_REQUIRE(lowerLimit && upperLimit && nintra && dintra && ninter && dinter, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(n == 0 || (coords && mol && type), FRMC_EINVAL, "NULL input array");
+    FRMC_REQUIRE(k == 0 || indexes, FRMC_EINVAL, "NULL indexes");
+    FRMC_REQUIRE(n < (1ll << 32) && k < (1ll << 32), FRMC_ELIMIT, "more than 2^32 atoms or rows");
+    const int cells = nT * nT;
+    for (int64_t i = 0; i < n; ++i)
+        FRMC_REQUIRE(type[i] >= 0 && type[i] < nT, FRMC_EINVAL, "elementIndex[%lld]=%d outside 0..%d", (long long)i, type[i], nT - 1);
+    for (int64_t t = 0; t < k; ++t)
+        FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < n, FRMC_EINVAL, "indexes[%lld]=%d outside 0..%lld", (long long)t, indexes[t], (long long)n - 1);
+    DeviceCtx *c = get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    memset(nintra, 0, sizeof(int32_t) * cells); memset(ninter, 0, sizeof(int32_t) * cells);
+    memset(dintra, 0, sizeof(float) * cells); memset(dinter, 0, sizeof(float) * cells);
+    if (k == 0 || n == 0) return FRMC_OK;
+
+    Lattice L;
+    for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
+    const int mode = choose_mode(L.b, isPBC, coords, n);
+    AdLimits lim;
+    for (int w = 0; w < cells; ++w) {
+        lim.lower[w] = lowerLimit[w]; lim.upper[w] = upperLimit[w];
+        lim.t2lower[w] = sqrt_threshold(lowerLimit[w]); lim.t2upper[w] = sqrt_threshold(upperLimit[w]);
+    }
+    float *d_coords = (float *)ctx_buffer(c, 0, sizeof(float) * 3 * n);
+    int *d_mol = (int *)ctx_buffer(c, 1, sizeof(int) * n);
+    int *d_type = (int *)ctx_buffer(c, 2, sizeof(int) * n);
+    int *d_idx = (int *)ctx_buffer(c, 3, sizeof(int) * k);
+    int *d_counts = (int *)ctx_buffer(c, 4, sizeof(int) * 2 * cells + 16);
+    AdLimits *d_lim = (AdLimits *)ctx_buffer(c, 5, sizeof(AdLimits));
+    float *d_sums = (float *)ctx_buffer(c, 6, sizeof(float) * 2 * cells);
+    if (!d_coords || !d_mol || !d_type || !d_idx || !d_counts || !d_lim || !d_sums) return FRMC_ENOMEM;
+    unsigned long long *d_nhits = (unsigned long long *)(d_counts + 2 * cells + (2 * cells) % 2);
+    FRMC_CUDA(cudaMemcpyAsync(d_coords, coords, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_mol, mol, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_type, type, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_idx, indexes, sizeof(int) * k, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_lim, &lim, sizeof(AdLimits), cudaMemcpyHostToDevice, c->stream));
+
+    AdScratch &sc = g_ad[dev & 63];
+    int rc = ad_reserve(sc, std::max<size_t>(sc.cap, 1u << 20), c->stream);
+    if (rc) return rc;
+    const long long chunks = (k + AD_ROWS - 1) / AD_ROWS;
+    const long long want = (n + 255) / 256, capx = (long long)c->sm_count * 8;
+    dim3 grid((unsigned)std::min(want, capx), (unsigned)std::min<long long>(chunks, 4096));
+    unsigned long long hits = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * 2 * cells + 16, c->stream));
+#define LAUNCH_AD(M) atomdist_hits_kernel<M><<<grid, 256, 0, c->stream>>>(d_coords, d_mol, d_type, n, d_idx, k, allAtoms, L, d_lim, nT, flags, \
+                                                                              d_counts, d_nhits, (unsigned long long)sc.cap, sc.keys, sc.vals)
+        switch (mode) {
+            case MODE_IBC: LAUNCH_AD(MODE_IBC); break;
+            case MODE_ORTHO_FAST: LAUNCH_AD(MODE_ORTHO_FAST); break;
+            case MODE_TRI_FAST: LAUNCH_AD(MODE_TRI_FAST); break;
+            case MODE_ORTHO_GEN: LAUNCH_AD(MODE_ORTHO_GEN); break;
+            default: LAUNCH_AD(MODE_TRI_GEN); break;
+        }
+#undef LAUNCH_AD
+        FRMC_LAUNCH_CHECK();
+        FRMC_CUDA(cudaMemcpyAsync(&hits, d_nhits, sizeof(hits), cudaMemcpyDeviceToHost, c->stream));
+        FRMC_CUDA(cudaStreamSynchronize(c->stream));
+        if (hits <= sc.cap) break;
+        FRMC_REQUIRE(hits <= FRMC_ATOMDIST_MAX_HITS && attempt == 0, FRMC_ELIMIT,
+                     "%llu pairs fall in the counted range; the ordered float sums are limited to %llu", hits, FRMC_ATOMDIST_MAX_HITS);
+        rc = ad_reserve(sc, (size_t)(hits + hits / 8), c->stream);      // second pass with room for all of them
+        if (rc) return rc;
+    }
+    std::vector<int> h_counts((size_t)2 * cells);
+    std::vector<float> h_sums((size_t)2 * cells, 0.0f);
+    FRMC_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
+    if (hits > 0) {
+        size_t bytes = sc.temp_bytes;
+        FRMC_CUDA(cub::DeviceRadixSort::SortPairs(sc.temp, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)hits, 0, 64, c->stream));
+        ++g_launch_count;
+        atomdist_sum_kernel<<<(2 * cells + 63) / 64, 64, 0, c->stream>>>(sc.vals2, hits, 2 * cells, d_sums);
+        FRMC_LAUNCH_CHECK();
+        FRMC_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums, sizeof(float) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
+    }
+    FRMC_CUDA(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < cells; ++w) {
+        nintra[w] = h_counts[(size_t)w]; ninter[w] = h_counts[(size_t)cells + w];
+        dintra[w] = h_sums[(size_t)w]; dinter[w] = h_sums[(size_t)cells + w];
+    }
+    return FRMC_OK;
+}
+
+extern "C" int frmc_full_atomic_distances_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
+                                                 const int32_t *mol, const int32_t *type, int nT, const float *lowerLimit,
+                                                 const float *upperLimit, int flags, int32_t *nintra, float *dintra,
+                                                 int32_t *ninter, float *dinter)
+{
+    FRMC_REQUIRE(n >= 0 && n < (1ll << 31), FRMC_EINVAL, "bad atom count");
+    std::vector<int32_t> idx((size_t)n);
+    for (int64_t i = 0; i < n; ++i) idx[(size_t)i] = (int32_t)i;
+    return frmc_multiple_atomic_distances_coords(dev, idx.data(), n, coords, n, basis, isPBC, mol, type, nT, lowerLimit, upperLimit,
+                                                 flags, 0, nintra, dintra, ninter, dinter);
+}

@@ -140,6 +140,27 @@ int frmc_gr_to_sq(int dev, const float *distances, const float *gr, int64_t n, c
 int frmc_sq_to_Gr(int dev, const float *qvalues, const float *rvalues, const float *sq, int64_t m, int64_t n,
                   float *Gr);
 
+/* ---- distance-constraint kernels (Extensions/atomic_distances.pyx) --------------
+ * multiple_atomic_distances_coords (:326-417) / full_atomic_distances_coords (:500-567): counts and float32 sums
+ * of the (optionally reduced) distances of the pairs inside -- or, without FRMC_AD_WITHIN, outside -- the
+ * [lower, upper) window of their type pair.  lowerLimit / upperLimit [nT*nT] are indexed [type_i, type_a];
+ * nintra, dintra, ninter, dinter [nT*nT] are indexed [type_a, type_i] (the reference's [nT,nT,1] arrays).
+ * The sums are accumulated in the reference's loop order, so they are bit-identical to it. */
+#define FRMC_AD_INTER 1      /* interMolecular        */
+#define FRMC_AD_INTRA 2      /* intraMolecular        */
+#define FRMC_AD_WITHIN 4     /* countWithinLimits     */
+#define FRMC_AD_TO_UPPER 8   /* reduceDistanceToUpper */
+#define FRMC_AD_TO_LOWER 16  /* reduceDistanceToLower */
+#define FRMC_AD_REDUCE 32    /* reduceDistance        */
+int frmc_multiple_atomic_distances_coords(int dev, const int32_t *indexes, int64_t k, const float *coords, int64_t n,
+                                          const float *basis, int isPBC, const int32_t *mol, const int32_t *type, int nT,
+                                          const float *lowerLimit, const float *upperLimit, int flags, int allAtoms,
+                                          int32_t *nintra, float *dintra, int32_t *ninter, float *dinter);
+int frmc_full_atomic_distances_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
+                                      const int32_t *mol, const int32_t *type, int nT, const float *lowerLimit,
+                                      const float *upperLimit, int flags, int32_t *nintra, float *dintra,
+                                      int32_t *ninter, float *dinter);
+
 /* ------------------------------------------------------------------------------------
  * Stateful fast path: device-resident coordinate store + running histograms.
  * Replaces compute_data / compute_before_move / compute_after_move / accept_move /

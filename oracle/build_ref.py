@@ -32,6 +32,8 @@ OUT = os.path.join(HERE, "_ref")
 MODULES = ("pairs_distances", "pairs_histograms", "reciprocal_space")
 # only needed to IMPORT the reference's Engine/constraint classes (golden-vector generation); not on the path
 EXTRA_MODULES = ("boundary_conditions_collection",)
+# the distance-constraint kernels (atomic_distances.pyx imports pairs_distances)
+NEXT_MODULES = ("atomic_distances",)
 
 
 def is_built():
@@ -70,7 +72,7 @@ def build(force=False):
                           include_dirs=[np.get_include()],
                           extra_compile_args=["-O2", "-ffp-contract=off", "-w"],
                           define_macros=[("NPY_NO_DEPRECATED_API", "NPY_1_7_API_VERSION")])
-                for m in MODULES + EXTRA_MODULES if os.path.exists(os.path.join(ext_dir, m + ".pyx"))]
+                for m in MODULES + EXTRA_MODULES + NEXT_MODULES if os.path.exists(os.path.join(ext_dir, m + ".pyx"))]
         exts = cythonize(exts, build_dir=os.path.join(tmp, "cy"), language_level=2, quiet=True,
                          compiler_directives={"legacy_implicit_noexcept": True})
         dist = Distribution({"name": "fullrmc_ref_kernels", "ext_modules": exts})

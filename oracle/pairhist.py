@@ -176,3 +176,41 @@ def gr_to_sq(distances, gr, qrange, rho):
     lib().orc_gr_to_sq(_p(distances, _f32p), _p(gr, _f32p), ctypes.c_int64(distances.shape[0]), _p(qrange, _f32p),
                        ctypes.c_int64(qrange.shape[0]), ctypes.c_float(rho), _p(sq, _f32p))
     return sq
+
+
+# ---------------------------------------------------------------- atomic distances (Extensions/atomic_distances.pyx)
+def _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance):
+    return (int(bool(interMolecular)) | int(bool(intraMolecular)) << 1 | int(bool(countWithinLimits)) << 2 |
+            int(bool(reduceDistanceToUpper)) << 3 | int(bool(reduceDistanceToLower)) << 4 | int(bool(reduceDistance)) << 5)
+
+
+def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements,
+                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, reduceDistance=False,
+                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, countWithinLimits=True,
+                                     allAtoms=True, ncores=1):
+    """atomic_distances.pyx:326-417; returns (nintra, dintra, ninter, dinter), each [nT, nT, 1]"""
+    indexes, coords, basis = _i32(indexes), _f32(boxCoords), _f32(basis)
+    mol, el = _i32(moleculeIndex), _i32(elementIndex)
+    nT = int(numberOfElements)
+    lo, up = _f32(lowerLimit).reshape(-1), _f32(upperLimit).reshape(-1)
+    assert lo.shape[0] == nT * nT and up.shape[0] == nT * nT
+    nintra = np.zeros((nT, nT, 1), np.int32); ninter = np.zeros((nT, nT, 1), np.int32)
+    dintra = np.zeros((nT, nT, 1), np.float32); dinter = np.zeros((nT, nT, 1), np.float32)
+    fn = lib().orc_multiple_atomic_distances_coords
+    fn.restype = None
+    fn(_p(indexes, _i32p), ctypes.c_int64(indexes.shape[0]), _p(coords, _f32p), ctypes.c_int64(coords.shape[0]), _p(basis, _f32p),
+       int(bool(isPBC)), _p(mol, _i32p), _p(el, _i32p), nT, _p(lo, _f32p), _p(up, _f32p),
+       _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance),
+       int(bool(allAtoms)), _p(nintra, _i32p), _p(dintra, _f32p), _p(ninter, _i32p), _p(dinter, _f32p))
+    return nintra, dintra, ninter, dinter
+
+
+def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, lowerLimit, upperLimit,
+                                 interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=False,
+                                 reduceDistanceToLower=False, countWithinLimits=True, ncores=1):
+    """atomic_distances.pyx:500-567"""
+    coords = _f32(boxCoords)
+    return multiple_atomic_distances_coords(np.arange(coords.shape[0], dtype=np.int32), coords, basis, isPBC, moleculeIndex,
+                                            elementIndex, numberOfElements, lowerLimit, upperLimit, interMolecular, intraMolecular,
+                                            reduceDistance, reduceDistanceToUpper, reduceDistanceToLower, countWithinLimits,
+                                            allAtoms=False, ncores=ncores)

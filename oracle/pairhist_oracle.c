@@ -278,6 +278,52 @@ void orc_gr_to_sq(const float *distances, const float *gr, int64_t n, const floa
     }
 }
 
+/* ---------------------------------------------------------------- atomic distances
+ * Extensions/atomic_distances.pyx:42-118 (_single_atomic_distances_dists) driven by
+ * multiple_atomic_distances_coords (:326-417) / full_atomic_distances_coords (:500-567): for every listed atom a
+ * and every other atom i >= start, a pair whose distance falls inside (countWithinLimits) or outside the
+ * [lower, upper) window of its type pair adds its (optionally reduced) distance to dintra/dinter[type_a, type_i]
+ * and one to nintra/ninter, in exactly this loop order (the float sums depend on it).  Limits are indexed
+ * [type_i, type_a], outputs [type_a, type_i].  flags: bit0 interMolecular, bit1 intraMolecular,
+ * bit2 countWithinLimits, bit3 reduceDistanceToUpper, bit4 reduceDistanceToLower, bit5 reduceDistance. */
+void orc_multiple_atomic_distances_coords(const int32_t *indexes, int64_t k, const float *coords, int64_t n,
+                                          const float *basis, int isPBC, const int32_t *mol, const int32_t *el, int nT,
+                                          const float *lowerLimit, const float *upperLimit, int flags, int allAtoms,
+                                          int32_t *nintra, float *dintra, int32_t *ninter, float *dinter)
+{
+    const int inter = flags & 1, intra = (flags >> 1) & 1, within = (flags >> 2) & 1;
+    const int toUpper = (flags >> 3) & 1, toLower = (flags >> 4) & 1, reduce = (flags >> 5) & 1;
+    for (int64_t t = 0; t < k; ++t) {
+        const int32_t a = indexes[t];
+        const float px = coords[3 * (int64_t)a], py = coords[3 * (int64_t)a + 1], pz = coords[3 * (int64_t)a + 2];
+        const int32_t am = mol[a], ae = el[a];
+        const int64_t start = allAtoms ? 0 : a;
+        for (int64_t i = start; i < n; ++i) {
+            if (i == a) continue;
+            const int32_t im = mol[i];
+            if (!intra && im == am) continue;
+            if (!inter && im != am) continue;
+            float distance = isPBC ? orc_dist_pbc(px, py, pz, coords + 3 * i, basis) : orc_dist_ibc(px, py, pz, coords + 3 * i);
+            const int32_t ie = el[i];
+            const float lower = lowerLimit[ie * nT + ae], upper = upperLimit[ie * nT + ae];
+            if (within) {
+                if (distance < lower) continue;
+                if (distance >= upper) continue;
+            } else if (distance >= lower && distance < upper) {
+                continue;
+            }
+            if (toUpper) distance = (float)fabs(upper - distance);
+            else if (toLower) distance = (float)fabs(lower - distance);
+            else if (reduce) {
+                if (distance > (lower + upper) / 2.0f) distance = (float)fabs(upper - distance);
+                else distance = (float)fabs(lower - distance);
+            }
+            if (im == am) { dintra[ae * nT + ie] += distance; nintra[ae * nT + ie] += 1; }
+            else { dinter[ae * nT + ie] += distance; ninter[ae * nT + ie] += 1; }
+        }
+    }
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP
