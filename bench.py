@@ -347,6 +347,45 @@ def cpu_full_hist_sample(n, rows_per_core, cores, seed=5):
         "wall %.1fs incl. start-up" % (R, n, pairs, cores, wall), busy
 
 
+# ----------------------------------------------------------------------------- distance-constraint leg
+def distance_leg(system, no_cpu):
+    """full_atomic_distances_coords (Extensions/atomic_distances.pyx:500-567) of cfg4 through the stateless host call,
+    with the compiled reference timed on sampled rows beside it"""
+    from fullrmc_b200 import _lib
+    from fullrmc_b200.Core import atomic_distances as ad
+    lib = _lib.load_library()
+    n, nT = system.numberOfAtoms, system.numberOfElements
+    lo = np.zeros((nT, nT, 1), np.float32)
+    up = np.full((nT, nT, 1), 1.5, np.float32)                      # InterMolecularDistanceConstraint's default distance
+    kw = dict(boxCoords=system.boxCoords, basis=system.basis, isPBC=system.isPBC, moleculeIndex=system.moleculeIndex,
+              elementIndex=system.elementIndex, numberOfElements=nT, lowerLimit=lo, upperLimit=up, intraMolecular=False,
+              reduceDistanceToUpper=True)
+    ad.full_atomic_distances_coords(**kw)                            # warm
+    l0 = int(lib.frmc_launch_count())
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        nintra, dintra, ninter, dinter = ad.full_atomic_distances_coords(**kw)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"metric": "full_atomic_distances_coords Gpairs/s", "workload": "cfg4: %d atoms, %d types, window [0, 1.5 A), inter-molecular, "
+           "reduced to upper" % (n, nT), "e2e": {"value": n_pairs(n) / dt / 1e9, "unit": "Gpairs/s", "ms_per_call": 1e3 * dt,
+           "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 16 * nT * nT, "api": "fullrmc_b200.Core.atomic_distances.full_atomic_distances_coords"},
+           "pairs_counted": int(ninter.sum()), "gpu_launches": (int(lib.frmc_launch_count()) - l0) // reps,
+           "roofline": None, "note": "stateless first version of this row: plain rows sweep + ordered float sums; no culling yet"}
+    if not no_cpu:
+        from oracle import build_ref
+        import importlib
+        if build_ref.load() is not None:
+            ref = importlib.import_module("fullrmc.Core.atomic_distances")
+            rows = np.linspace(0, n - 2, 400).astype(np.int32)
+            t0 = time.perf_counter()
+            ref.multiple_atomic_distances_coords(indexes=rows, allAtoms=False, ncores=1, **kw)
+            dtc = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": float(np.sum(n - 1 - rows)) / dtc / 1e9, "unit": "Gpairs/s", "cores": 1, "kind": "reference",
+                                   "sample": "400 uniformly spaced rows of the upper triangle (multiple_atomic_distances_coords, allAtoms=False)"}
+    return out
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -544,6 +583,7 @@ def run_b200(args):
             pm4["cpu_baseline"] = per_move_cpu_baseline(s4, grid, q, 2500)        # ~10 s
         line["per_move"] = pm
         line["per_move_cfg4"] = pm4
+        line["distance_constraint_cfg4"] = distance_leg(s4, args.no_cpu)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         scale = max(1, n // 1000000)                                           # ~10 s of CPU work per leg at 1 M atoms
