@@ -371,7 +371,8 @@ def distance_leg(system, no_cpu):
            "reduced to upper" % (n, nT), "e2e": {"value": n_pairs(n) / dt / 1e9, "unit": "Gpairs/s", "ms_per_call": 1e3 * dt,
            "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 16 * nT * nT, "api": "fullrmc_b200.Core.atomic_distances.full_atomic_distances_coords"},
            "pairs_counted": int(ninter.sum()), "gpu_launches": (int(lib.frmc_launch_count()) - l0) // reps,
-           "roofline": None, "note": "stateless first version of this row: plain rows sweep + ordered float sums; no culling yet"}
+           "roofline": None, "note": "stateless version of this row: k-d ordered store + block culling against the largest upper "
+           "limit, hits sorted and summed in the reference's order; the call is dominated by host ordering, copies and syncs"}
     if not no_cpu:
         from oracle import build_ref
         import importlib

@@ -61,11 +61,24 @@ def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeI
 def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, lowerLimit, upperLimit,
                                  interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=False,
                                  reduceDistanceToLower=False, countWithinLimits=True, ncores=1):
-    """atomic_distances.pyx:500-567"""
+    """atomic_distances.pyx:500-567 -- in within-limits mode the device sweeps only the block pairs of the k-d ordered
+    store that can reach the largest upper limit (csrc/atomdist.cu: full_culled)"""
+    lib = L.load_library()
     coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
-    return multiple_atomic_distances_coords(np.arange(coords.shape[0], dtype=_I32), coords, basis, isPBC, moleculeIndex,
-                                            elementIndex, numberOfElements, lowerLimit, upperLimit, interMolecular=interMolecular,
-                                            intraMolecular=intraMolecular, reduceDistance=reduceDistance,
-                                            reduceDistanceToUpper=reduceDistanceToUpper,
-                                            reduceDistanceToLower=reduceDistanceToLower, countWithinLimits=countWithinLimits,
-                                            allAtoms=False, ncores=ncores)
+    b = L.as_array(basis, "basis", _F32, 2)
+    mol = L.as_array(moleculeIndex, "moleculeIndex", _I32, 1)
+    el = L.as_array(elementIndex, "elementIndex", _I32, 1)
+    nT = int(numberOfElements)
+    lo, up = _limits(lowerLimit, upperLimit, nT)
+    n = coords.shape[0]
+    if mol.shape[0] != n or el.shape[0] != n:
+        raise ValueError("moleculeIndex/elementIndex length must equal the number of atoms (%d)" % n)
+    nintra = np.zeros((nT, nT, 1), _I32); ninter = np.zeros((nT, nT, 1), _I32)
+    dintra = np.zeros((nT, nT, 1), _F32); dinter = np.zeros((nT, nT, 1), _F32)
+    rc = lib.frmc_full_atomic_distances_coords(
+        L.device_index(), L.ptr(coords, L.c_f32p), n, L.ptr(b, L.c_f32p), int(bool(isPBC)), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p),
+        nT, L.ptr(lo, L.c_f32p), L.ptr(up, L.c_f32p),
+        _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance),
+        L.ptr(nintra, L.c_i32p), L.ptr(dintra, L.c_f32p), L.ptr(ninter, L.c_i32p), L.ptr(dinter, L.c_f32p))
+    L.check(rc, "full_atomic_distances_coords")
+    return nintra, dintra, ninter, dinter

@@ -11,6 +11,7 @@
 // entries in that order.  Hits are the exception by construction (the constraint exists to keep atoms apart);
 // the list grows on demand and the call fails loudly beyond FRMC_ATOMDIST_MAX_HITS.
 #include "common.cuh"
+#include "layout.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -105,6 +106,75 @@ __global__ void atomdist_sum_kernel(const unsigned long long *__restrict__ vals,
     sums[cell] = acc;
 }
 
+// Culled variant for the full pass in within-limits mode: the windows are a few angstroms wide, so on the k-d
+// ordered store (layout.h) almost every block pair is out of reach of the largest upper limit and is never
+// listed (fullhist.cu: build_pair_lists).  One CTA per item; thread t holds I record t of the item's block and
+// sweeps the staged J blocks.  A pair (p, q) is the reference's (a, i) with a = the smaller ORIGINAL index (the
+// full pass lists atom a against i > a), which fixes both the limits entry [type_i, type_a] and the output cell
+// [type_a, type_i]; the hit's key (a, i) puts it at the reference's place in the summation order.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+atomdist_block_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const WorkItem *__restrict__ rows,
+                      const uint32_t *__restrict__ entries, const int4 *__restrict__ items, int n_items, Lattice L,
+                      const AdLimits *__restrict__ lim, int nT, int flags, int *__restrict__ counts,
+                      unsigned long long *__restrict__ n_hits, unsigned long long capacity, unsigned long long *__restrict__ keys,
+                      unsigned long long *__restrict__ vals)
+{
+    __shared__ float4 sJ[SEG_PAD];
+    __shared__ uint32_t sO[SEG_PAD];
+    __shared__ float s_lo[AD_MAX_TYPES * AD_MAX_TYPES], s_up[AD_MAX_TYPES * AD_MAX_TYPES];
+    __shared__ float s_t2lo[AD_MAX_TYPES * AD_MAX_TYPES], s_t2up[AD_MAX_TYPES * AD_MAX_TYPES];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < nT * nT; t += blockDim.x) {
+        s_lo[t] = lim->lower[t]; s_up[t] = lim->upper[t]; s_t2lo[t] = lim->t2lower[t]; s_t2up[t] = lim->t2upper[t];
+    }
+    const bool inter = flags & AD_INTER, intra = flags & AD_INTRA;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int4 item = items[it];
+        const WorkItem w = rows[item.x];
+        const int p = w.i0 + tid;
+        const float4 a = atoms[p];
+        const uint32_t ma = __float_as_uint(a.w), oa = orig[p];
+        const int ta = (int)(ma & 0xFFu);
+        for (int e = 0; e < item.z; ++e) {
+            const int jb = (int)entries[item.y + e] * SEG_PAD;
+            __syncthreads();
+            sJ[tid] = atoms[jb + tid]; sO[tid] = orig[jb + tid];
+            __syncthreads();
+            if (ma == PAD_META) continue;
+            const bool tri = (w.ea == w.eb) && jb < w.i0 + w.ni * SEG_PAD;
+            for (int q = 0; q < SEG_PAD; ++q) {
+                const float4 c = sJ[q];
+                const uint32_t mc = __float_as_uint(c.w);
+                if (mc == PAD_META) continue;
+                if (tri && !(p < jb + q)) continue;
+                const bool same = (ma >> 8) == (mc >> 8);
+                if (same ? !intra : !inter) continue;
+                const float d2 = dist2<MODE>(a.x, a.y, a.z, c.x, c.y, c.z, L);
+                const uint32_t oc = sO[q];
+                const int tc = (int)(mc & 0xFFu);
+                const bool a_first = oa < oc;                           // the reference's listed atom is the smaller original index
+                const int t_a = a_first ? ta : tc, t_i = a_first ? tc : ta;
+                const int wdx = t_i * nT + t_a;
+                const bool in_window = (d2 >= s_t2lo[wdx]) && (d2 < s_t2up[wdx]);
+                if (!(in_window || d2 != d2)) continue;
+                float d = __fsqrt_rn(d2);
+                const float lower = s_lo[wdx], upper = s_up[wdx];
+                if (flags & AD_TO_UPPER) d = fabsf(__fsub_rn(upper, d));
+                else if (flags & AD_TO_LOWER) d = fabsf(__fsub_rn(lower, d));
+                else if (flags & AD_REDUCE) d = (d > __fdiv_rn(__fadd_rn(lower, upper), 2.0f)) ? fabsf(__fsub_rn(upper, d)) : fabsf(__fsub_rn(lower, d));
+                const int cell = (same ? 0 : nT * nT) + t_a * nT + t_i;
+                atomicAdd(&counts[cell], 1);
+                const unsigned long long at = atomicAdd(n_hits, 1ull);
+                if (at < capacity) {
+                    keys[at] = ((unsigned long long)(a_first ? oa : oc) << 32) | (unsigned long long)(a_first ? oc : oa);
+                    vals[at] = ((unsigned long long)(unsigned)cell << 32) | (unsigned long long)__float_as_uint(d);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace frmc
 
 using namespace frmc;
@@ -132,6 +202,29 @@ static int ad_reserve(AdScratch &sc, size_t cap, cudaStream_t stream)
     FRMC_CUDA(cudaMalloc(&sc.temp, bytes));
     sc.temp_bytes = bytes;
     sc.cap = cap;
+    return FRMC_OK;
+}
+
+// sort the hits by (listed atom, other atom), add them per output cell in that order, hand the arrays back
+static int ad_finish(DeviceCtx *c, AdScratch &sc, unsigned long long hits, int cells, const int *d_counts, float *d_sums,
+                     int32_t *nintra, float *dintra, int32_t *ninter, float *dinter)
+{
+    std::vector<int> h_counts((size_t)2 * cells);
+    std::vector<float> h_sums((size_t)2 * cells, 0.0f);
+    FRMC_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
+    if (hits > 0) {
+        size_t bytes = sc.temp_bytes;
+        FRMC_CUDA(cub::DeviceRadixSort::SortPairs(sc.temp, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)hits, 0, 64, c->stream));
+        ++g_launch_count;
+        atomdist_sum_kernel<<<(2 * cells + 63) / 64, 64, 0, c->stream>>>(sc.vals2, hits, 2 * cells, d_sums);
+        FRMC_LAUNCH_CHECK();
+        FRMC_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums, sizeof(float) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
+    }
+    FRMC_CUDA(cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < cells; ++w) {
+        nintra[w] = h_counts[(size_t)w]; ninter[w] = h_counts[(size_t)cells + w];
+        dintra[w] = h_sums[(size_t)w]; dinter[w] = h_sums[(size_t)cells + w];
+    }
     return FRMC_OK;
 }
 
@@ -208,23 +301,89 @@ extern "C" int frmc_multiple_atomic_distances_coords(int dev, const int32_t *ind
         rc = ad_reserve(sc, (size_t)(hits + hits / 8), c->stream);      // second pass with room for all of them
         if (rc) return rc;
     }
-    std::vector<int> h_counts((size_t)2 * cells);
-    std::vector<float> h_sums((size_t)2 * cells, 0.0f);
-    FRMC_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
-    if (hits > 0) {
-        size_t bytes = sc.temp_bytes;
-        FRMC_CUDA(cub::DeviceRadixSort::SortPairs(sc.temp, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)hits, 0, 64, c->stream));
-        ++g_launch_count;
-        atomdist_sum_kernel<<<(2 * cells + 63) / 64, 64, 0, c->stream>>>(sc.vals2, hits, 2 * cells, d_sums);
-        FRMC_LAUNCH_CHECK();
-        FRMC_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums, sizeof(float) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
-    }
-    FRMC_CUDA(cudaStreamSynchronize(c->stream));
+    return ad_finish(c, sc, hits, cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
+}
+
+// the full pass on the k-d ordered store with block culling (within-limits mode only: there the hits are the pairs
+// closer than the largest upper limit); returns 1 when the case does not qualify and the plain rows sweep must run
+static int full_culled(int dev, const float *coords, int64_t n, const float *basis, int isPBC, const int32_t *mol,
+                       const int32_t *type, int nT, const float *lowerLimit, const float *upperLimit, int flags,
+                       int32_t *nintra, float *dintra, int32_t *ninter, float *dinter)
+{
+    if (!(flags & AD_WITHIN) || g_no_cull || n < 4096) return 1;
+    const int cells = nT * nT;
+    DeviceCtx *c = get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    Lattice L;
+    for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
+    AdLimits lim;
+    float t2cut = 0.0f;
     for (int w = 0; w < cells; ++w) {
-        nintra[w] = h_counts[(size_t)w]; ninter[w] = h_counts[(size_t)cells + w];
-        dintra[w] = h_sums[(size_t)w]; dinter[w] = h_sums[(size_t)cells + w];
+        lim.lower[w] = lowerLimit[w]; lim.upper[w] = upperLimit[w];
+        lim.t2lower[w] = sqrt_threshold(lowerLimit[w]); lim.t2upper[w] = sqrt_threshold(upperLimit[w]);
+        t2cut = std::max(t2cut, lim.t2upper[w]);
+        if (upperLimit[w] != upperLimit[w]) return 1;                    // NaN limits: let the plain sweep decide
     }
-    return FRMC_OK;
+    static thread_local HostLayout lay;
+    int rc = build_layout(coords, n, mol, type, nT, isPBC, lay);
+    if (rc) return rc;
+    if (!lay.finite) return 1;                                            // NaN coordinates count as hits in the reference: plain sweep
+    const int mode = choose_mode_from_bounds(L.b, isPBC, lay.lo, lay.hi);
+    GridParams g;
+    memset(&g, 0, sizeof(g));
+    g.t2max = t2cut;
+    const CullParams cp = make_cull(L, mode, g);
+    if (!cp.enabled) return 1;
+    std::vector<WorkItem> rows;
+    build_rows(lay, 1, 0, 1, rows);
+    if (rows.empty()) return 1;
+
+    float4 *d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float4) * (size_t)lay.npad);
+    uint32_t *d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);
+    WorkItem *d_rows = (WorkItem *)ctx_buffer(c, 2, sizeof(WorkItem) * rows.size());
+    float4 *d_bbox = (float4 *)ctx_buffer(c, 3, sizeof(float4) * 18 * (size_t)(lay.npad / SEG_PAD + 1));
+    int *d_counts = (int *)ctx_buffer(c, 4, sizeof(int) * 2 * cells + 16);
+    AdLimits *d_lim = (AdLimits *)ctx_buffer(c, 5, sizeof(AdLimits));
+    float *d_sums = (float *)ctx_buffer(c, 6, sizeof(float) * 2 * cells);
+    if (!d_atoms || !d_orig || !d_rows || !d_bbox || !d_counts || !d_lim || !d_sums) return FRMC_ENOMEM;
+    unsigned long long *d_nhits = (unsigned long long *)(d_counts + 2 * cells + (2 * cells) % 2);
+    FRMC_CUDA(cudaMemcpyAsync(d_atoms, lay.rec.data(), sizeof(float4) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_orig, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_rows, rows.data(), sizeof(WorkItem) * rows.size(), cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_lim, &lim, sizeof(AdLimits), cudaMemcpyHostToDevice, c->stream));
+    static PairLists lists[64];
+    PairLists &pl = lists[dev & 63];
+    rc = build_pair_lists(c->stream, d_atoms, lay.npad, d_bbox, d_rows, (int)rows.size(), cp, pl);
+    if (rc) return rc;
+    AdScratch &sc = g_ad[dev & 63];
+    rc = ad_reserve(sc, std::max<size_t>(sc.cap, 1u << 20), c->stream);
+    if (rc) return rc;
+    unsigned long long hits = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * 2 * cells + 16, c->stream));
+        if (pl.n_items > 0) {
+            const int grid = std::min(pl.n_items, c->sm_count * 8);
+#define LAUNCH_ADB(M) atomdist_block_kernel<M><<<grid, 256, 0, c->stream>>>(d_atoms, d_orig, d_rows, pl.entries, pl.items, pl.n_items, L, d_lim, \
+                                                                            nT, flags, d_counts, d_nhits, (unsigned long long)sc.cap, sc.keys, sc.vals)
+            switch (mode) {
+                case MODE_IBC: LAUNCH_ADB(MODE_IBC); break;
+                case MODE_ORTHO_FAST: LAUNCH_ADB(MODE_ORTHO_FAST); break;
+                case MODE_TRI_FAST: LAUNCH_ADB(MODE_TRI_FAST); break;
+                case MODE_ORTHO_GEN: LAUNCH_ADB(MODE_ORTHO_GEN); break;
+                default: LAUNCH_ADB(MODE_TRI_GEN); break;
+            }
+#undef LAUNCH_ADB
+            FRMC_LAUNCH_CHECK();
+        }
+        FRMC_CUDA(cudaMemcpyAsync(&hits, d_nhits, sizeof(hits), cudaMemcpyDeviceToHost, c->stream));
+        FRMC_CUDA(cudaStreamSynchronize(c->stream));
+        if (hits <= sc.cap) break;
+        FRMC_REQUIRE(hits <= FRMC_ATOMDIST_MAX_HITS && attempt == 0, FRMC_ELIMIT,
+                     "%llu pairs fall in the counted range; the ordered float sums are limited to %llu", hits, FRMC_ATOMDIST_MAX_HITS);
+        rc = ad_reserve(sc, (size_t)(hits + hits / 8), c->stream);
+        if (rc) return rc;
+    }
+    return ad_finish(c, sc, hits, cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
 }
 
 extern "C" int frmc_full_atomic_distances_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
@@ -233,6 +392,13 @@ extern "C" int frmc_full_atomic_distances_coords(int dev, const float *coords, i
                                                  int32_t *ninter, float *dinter)
 {
     FRMC_REQUIRE(n >= 0 && n < (1ll << 31), FRMC_EINVAL, "bad atom count");
+    FRMC_REQUIRE(nT >= 1 && nT <= AD_MAX_TYPES, FRMC_ELIMIT, "numberOfElements %d outside 1..%d", nT, AD_MAX_TYPES);
+    FRMC_REQUIRE(lowerLimit && upperLimit && nintra && dintra && ninter && dinter, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(n == 0 || (coords && mol && type), FRMC_EINVAL, "NULL input array");
+    for (int64_t i = 0; i < n; ++i)
+        FRMC_REQUIRE(type[i] >= 0 && type[i] < nT, FRMC_EINVAL, "elementIndex[%lld]=%d outside 0..%d", (long long)i, type[i], nT - 1);
+    const int rc = full_culled(dev, coords, n, basis, isPBC, mol, type, nT, lowerLimit, upperLimit, flags, nintra, dintra, ninter, dinter);
+    if (rc != 1) return rc;
     std::vector<int32_t> idx((size_t)n);
     for (int64_t i = 0; i < n; ++i) idx[(size_t)i] = (int32_t)i;
     return frmc_multiple_atomic_distances_coords(dev, idx.data(), n, coords, n, basis, isPBC, mol, type, nT, lowerLimit, upperLimit,

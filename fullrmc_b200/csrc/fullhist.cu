@@ -720,17 +720,14 @@ void PairLists::release()
     row_ints = nullptr; entries = nullptr; items = nullptr; row_cap = entries_cap = items_cap = 0;
 }
 
-// Box pass, surviving-pair lists, then the sweep, on prepared device arrays.  next_item must be zeroed by the
-// caller (stream-ordered) before every launch; bbox is scratch for 18 float4 per SEG_PAD block; lists holds
-// the grow-only list buffers; stats[0] accumulates edge-overflow events, stats[1] swept (256 x 32) units.
-// Synchronises the stream once (the list sizes come back to the host).
-int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
-                     const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
+// Box pass and surviving-pair lists for `rows` under the culling parameters cp (bbox: 18 float4 per SEG_PAD
+// block of scratch; lists: grow-only buffers).  Synchronises the stream once: the list sizes come back to
+// the host.  Used by the histogram sweep below and by the distance-constraint sweep (atomdist.cu).
+int build_pair_lists(cudaStream_t stream, const float4 *atoms, int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows,
+                     const CullParams &cp, PairLists &lists)
 {
-    CullParams cp = make_cull(L, mode, g);
-    if (g_no_cull) cp.enabled = 0;
     const int nblocks = (int)(npad / SEG_PAD);
+    lists.n_entries = lists.n_items = 0;
     if (n_rows <= 0 || nblocks <= 0) return FRMC_OK;
     if (cp.enabled) {
         block_bbox_kernel<<<(nblocks * 32 + 255) / 256, 256, 0, stream>>>(atoms, nblocks, cp.pbc, bbox);
@@ -759,6 +756,23 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const f
     pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, row_start, row_item_start,
                                                     lists.entries, lists.items, 1);
     FRMC_LAUNCH_CHECK();
+    return FRMC_OK;
+}
+
+// Box pass, surviving-pair lists, then the sweep, on prepared device arrays.  next_item must be zeroed by the
+// caller (stream-ordered) before every launch; stats[0] accumulates edge-overflow events, stats[1] swept
+// (256 x 32) units.
+int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
+                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
+                     const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
+{
+    CullParams cp = make_cull(L, mode, g);
+    if (g_no_cull) cp.enabled = 0;
+    const int nblocks = (int)(npad / SEG_PAD);
+    if (n_rows <= 0 || nblocks <= 0) return FRMC_OK;
+    int rc = build_pair_lists(stream, atoms, npad, bbox, rows, n_rows, cp, lists);
+    if (rc) return rc;
+    if (lists.n_items == 0) return FRMC_OK;
 #define FH_CASE(M)                                                                                         \
     case M:                                                                                                \
         return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, bbox, rows, lists.entries, lists.items, lists.n_items, next_item, L, g, cp, nblocks, nEl, counts, stats) \

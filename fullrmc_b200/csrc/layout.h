@@ -69,4 +69,9 @@ struct PairLists {
     void release();
 };
 
+struct CullParams;
+// box pass + surviving block pairs of `rows`, cut into items (fullhist.cu)
+int build_pair_lists(cudaStream_t stream, const float4 *atoms, int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows,
+                     const CullParams &cp, PairLists &lists);
+
 }  // namespace frmc

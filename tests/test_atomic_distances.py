@@ -66,11 +66,19 @@ def test_device_matches_oracle_on_larger_systems(n, nT, pbc, orc):
     lo = np.zeros((nT, nT, 1), np.float32)
     up = (1.2 + rng.random((nT, nT, 1))).astype(np.float32); up = ((up + up.transpose(1, 0, 2)) / 2).astype(np.float32)
     kw = dict(boxCoords=box, basis=basis, isPBC=pbc, moleculeIndex=mol, elementIndex=el, numberOfElements=nT, lowerLimit=lo, upperLimit=up)
+    from fullrmc_b200 import _lib
     for flags in (dict(intraMolecular=False), dict(reduceDistanceToUpper=True, intraMolecular=False), dict()):
-        got = ad.full_atomic_distances_coords(**kw, **flags)
+        got = ad.full_atomic_distances_coords(**kw, **flags)            # k-d ordered store, block pairs out of reach culled
         ref = orc.full_atomic_distances_coords(**kw, **flags)
         for key, a, b in zip(KEYS, got, ref):
             assert np.array_equal(a, b), (flags, key)
+        old = _lib.set_block_culling(False)                            # the plain rows sweep over the same input
+        try:
+            plain = ad.full_atomic_distances_coords(**kw, **flags)
+        finally:
+            _lib.set_block_culling(old)
+        for key, a, b in zip(KEYS, plain, ref):
+            assert np.array_equal(a, b), (flags, key, "plain")
         assert int(ref[2].sum()) > 100                      # the case really has close contacts
         idx = rng.integers(0, n, 40).astype(np.int32)
         got = ad.multiple_atomic_distances_coords(indexes=idx, **kw, **flags)
