@@ -503,6 +503,30 @@ def run_b200(args):
         dist.all_reduce(tsw)
     swept_total = int(tsw[0])
 
+    # ---- the same histogram with culling switched off: the reference's own O(N^2) sweep, every pair evaluated
+    #      (2 steps at N=1; the result must be the identical integer histogram)
+    brute = None
+    if world == 1 and not args.no_brute:
+        _lib.set_block_culling(False)
+        try:
+            with torch.cuda.stream(ext):
+                step()                                               # rebuilds the row list for the R=4 tiling
+                store.set_timing(True)
+                b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
+                b0.record(ext)
+                for _ in range(2):
+                    chi2_b = step()
+                b1.record(ext)
+                torch.cuda.synchronize()
+                ms_b = b0.elapsed_time(b1) / 2
+                store.set_timing(False)
+            same = bool(np.array_equal(counts.cpu().numpy(), counts_host) and np.array_equal(chi2_b, chi2))
+            brute = {"ms_per_step": ms_b, "value": P / (ms_b * 1e-3) / 1e9, "unit": "Gpairs/s", "pairs_swept": store.swept_pairs,
+                     "identical_histogram_and_chi2": same,
+                     "note": "culling off (frmc_set_block_culling(0)): all N(N-1)/2 pairs evaluated, R=4 register tiling"}
+        finally:
+            _lib.set_block_culling(True)
+
     # ---- e2e: the reference-facing stateless call with HOST buffers (host sort + H2D + kernel + D2H)
     kw = dict(system.hist_kwargs(), **grid.kwargs())
     e2e_steps = max(1, min(args.steps, 3))
@@ -554,7 +578,7 @@ def run_b200(args):
         "config": {"workload": "cfg5: synthetic %d-atom cubic box (L=%.2f A), 5 elements, full pair histogram, rmin 0, "
                                "bin %.2f, hs %d, + G(r), S(Q) (nQ=%d), chi2 epilogue" % (n, float(system.basis[0, 0]), BIN, HS, NQ),
                    "pairs_per_step": P, "pairs_swept_per_step": swept_total, "swept_fraction": swept_total / float(P),
-                   "in_range_pairs": in_range_pairs, "parallelism": "tile-list shards x%d + NCCL allreduce(int64)" % world,
+                   "in_range_pairs": in_range_pairs, "brute_force_sweep": brute, "parallelism": "tile-list shards x%d + NCCL allreduce(int64)" % world,
                    "value_counts": "all N(N-1)/2 pairs the reference evaluates; pairs in blocks whose bounding boxes are "
                                    "farther apart than maxDistance are skipped, the histogram is bit-identical",
                    "l2_policy": "inputs (16 B/atom = %.1f MB) are L2-resident by design; the kernel is issue-bound, not HBM-bound" % (16e-6 * npad),
@@ -609,6 +633,7 @@ def main():
     ap.add_argument("--permove-warm", type=int, default=200)
     ap.add_argument("--ref-rows", type=int, default=1600, help="sampled rows per reference step")
     ap.add_argument("--no-permove", action="store_true")
+    ap.add_argument("--no-brute", action="store_true", help="skip the culling-off leg of the full histogram")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
