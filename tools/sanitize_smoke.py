@@ -1,0 +1,43 @@
+"""Small multi-block workloads through every kernel of the library, for compute-sanitizer runs:
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+    SAN_SKIP_STORE=1 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py"""
+import os
+import sys, numpy as np
+sys.path.insert(0, "/root/repo")
+from fullrmc_b200 import synthetic
+from fullrmc_b200.Core import pairs_histograms as ph, atomic_distances as ad
+from fullrmc_b200.store import DeviceStore
+from fullrmc_b200.model import ModelSpec
+# small but multi-block systems through every new kernel
+for n, basis, pbc in ((9000, np.diag([70.0, 66.0, 72.0]).astype(np.float32), True), (40000, np.array([[90, 0, 0], [11, 86, 0], [-8, 14, 88]], np.float32), True)):
+    s = synthetic.random_system(n, 3, basis, n_elements=3, molecule_size=4, isPBC=pbc)
+    kw = dict(s.hist_kwargs(), minDistance=np.float32(0.0), maxDistance=np.float32(7.0), bin=np.float32(0.05), histSize=140)
+    hi, he = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, **kw)
+    print("full hist", n, hi.sum() + he.sum())
+    lo = np.zeros((3, 3, 1), np.float32); up = np.full((3, 3, 1), 2.0, np.float32)
+    r = ad.full_atomic_distances_coords(s.boxCoords, s.basis, pbc, s.moleculeIndex, s.elementIndex, 3, lo, up, intraMolecular=False)
+    print("atomdist", int(r[2].sum()))
+if os.environ.get("SAN_SKIP_STORE"):
+    print("done (stateless kernels only)"); sys.exit(0)
+s = synthetic.random_system(20000, 5, np.diag([60.0, 60.0, 60.0]).astype(np.float32), n_elements=2)
+grid = synthetic.RGrid(0.0, 0.05, 200)
+q = synthetic.q_values(nq=64)
+st = DeviceStore(s.boxCoords, s.basis, True, s.moleculeIndex, s.elementIndex, 2)
+g = st.add_grid(grid.minDistance, grid.maxDistance, grid.bin, grid.hs)
+common = dict(elements=s.elements, n_per_element=s.numberOfAtomsPerElement, weighting=s.weighting, volume=s.volume, rho0=s.numberDensity,
+              shell_centers=grid.shellCenters, shell_volumes=grid.shellVolumes)
+st.add_model(g, ModelSpec("PDF", experimental=np.zeros(200, np.float32), **common))
+st.add_model(g, ModelSpec("SQ", experimental=np.ones(64, np.float32), q_values=q, **common))
+print("chi2", st.compute_data())
+rng = np.random.default_rng(1)
+for mode in (False, True):
+    st.set_persistent(mode)
+    prev = None
+    for it in range(12):
+        i = rng.integers(0, 20000, 1).astype(np.int32)
+        chi = st.step(prev, i, (s.boxCoords[i] + rng.normal(0, 0.01, (1, 3))).astype(np.float32)).copy()
+        prev = it % 2 == 0
+    (st.accept if prev else st.reject)()
+    print("persistent", mode, chi)
+st.close()
+print("done")
