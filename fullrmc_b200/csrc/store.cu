@@ -12,6 +12,7 @@
 // counter instead of synchronising the stream.
 #include "common.cuh"
 #include "layout.h"
+#include "store_view.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -56,18 +57,6 @@ struct GridSet {
     float t2lo, t2hi;                // union of the grids' d^2 windows (cheap first test)
     int pad;
     GridDev grid[FRMC_MAX_GRIDS];
-};
-
-struct ProposalIn {                  // passed BY VALUE as a kernel parameter (constant bank)
-    int k;
-    int pos[FRMC_MAX_GROUP];         // positions in the sorted store (host lookup in the inverse permutation)
-    float moved[3 * FRMC_MAX_GROUP]; // moved box coordinates
-};
-
-struct Proposal {                    // device copy kept for the commit kernel
-    int k;
-    int pos[FRMC_MAX_GROUP];
-    float4 newc[FRMC_MAX_GROUP];     // same meta, moved coordinates
 };
 
 static const int EPI_INLINE_PAIRS = 16;   // pair tables up to this size ride in the kernel parameters
@@ -1598,6 +1587,22 @@ static int stop_persistent(frmc_store *s)
     s->persist_running = false;
     return FRMC_OK;
 }
+
+namespace frmc {
+int store_view(frmc_store *s, StoreView *out)
+{
+    FRMC_REQUIRE(s && out, FRMC_EINVAL, "NULL argument");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    int rc = stop_persistent(s);
+    if (rc) return rc;
+    out->dev = s->dev; out->stream = s->stream; out->sm_count = s->ctx->sm_count; out->ctx = s->ctx;
+    out->atoms = s->d_atoms; out->orig = s->d_orig; out->n = s->n; out->npad = s->npad; out->inv = s->lay.inv.data();
+    out->L = s->L; out->isPBC = s->isPBC;
+    for (int c = 0; c < 3; ++c) { out->lo[c] = s->lo[c]; out->hi[c] = s->hi[c]; }
+    out->pending = s->pending; out->prop = s->d_prop;
+    return FRMC_OK;
+}
+}  // namespace frmc
 
 template <int MODE>
 static int launch_persistent_t(frmc_store *s)
