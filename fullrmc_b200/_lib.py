@@ -97,6 +97,11 @@ SIGNATURES = {
     # array arguments as plain addresses: the tight loop passes arr.__array_interface__["data"][0] (1 us) instead of
     # building a typed ctypes pointer per call (4 us each)
     "frmc_step": (_I, [_VP, _I, _VP, _I, _VP, c_f32p]),
+    "frmc_run_batch": (_I, [_VP, _I, c_i32p, c_i32p, c_f32p, c_f32p, _F, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p,
+                            ctypes.POINTER(ctypes.c_double)]),
+    "frmc_store_batch_stats": (_I, [_VP, c_u64p, c_u64p, c_u64p]),
+    "frmc_store_committed_chi2": (_I, [_VP, c_f32p]),
+    "frmc_store_batch_stamps": (_I, [_VP, c_i64p, _I]),
     "frmc_store_replay_proposal": (_I, [_VP, _I, ctypes.POINTER(ctypes.c_double)]),
     "frmc_export_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_export_total": (_I, [_VP, _I, _I, c_f32p]),

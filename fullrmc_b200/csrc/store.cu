@@ -558,13 +558,27 @@ __device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem
 
 }
 
+// Where a BATCH evaluation (batch_kernel: several proposals in flight) reads its counts and leaves its results:
+// the counts are the COMMITTED symmetrised totals plus the proposal's own symmetrised delta, the model total and
+// chi^2 go to per-proposal buffers, and nothing is published to the host (the kernel decides itself).
+struct EpiOut {
+    const int *add;          // [nsym][hs] the proposal's symmetrised delta on this model's grid
+    float *total;            // [n_out]    model total of this proposal
+    float *res;              // [2*FRMC_MAX_MODELS] chi2 per model, then the scale factor each evaluation used
+    unsigned int *mticket;   // counts the models of this proposal that have their chi2
+    float *ptotal;           // the proposal's total standard error, sum_m chi2_m / varianceSquared_m (Engine.py:3024-3029)
+    const float *var2;       // [n_models]
+};
+
 // part 2: r-space function, chi^2 / S(Q) slice, ticket, publish (steps 1-4 above)
+template <bool BATCH>
 __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, const ModelSet &ms, const GridSet &gs, int m, int slab,
                                              float *__restrict__ chi2_out, unsigned int *__restrict__ dev_seq,
                                              volatile unsigned int *__restrict__ host_seq, unsigned int *__restrict__ tickets,
-                                             long long *__restrict__ stamps)
+                                             long long *__restrict__ stamps, const EpiOut &eo)
 {
     const ModelDev &M = ms.m[m];
+    float *const total = BATCH ? eo.total : M.total;
     const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
     const int hs = M.hs, nq = M.n_out;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -603,7 +617,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
 
     // ---- 1. r-space function: EPI_BINS bins per thread per round, every load issued before any arithmetic
     {
-        const int *__restrict__ stot = gs.grid[M.grid].stot;
+        const int *__restrict__ stot = BATCH ? gs.grid[M.grid].tot : gs.grid[M.grid].stot;
         constexpr int EPI_BINS = 2, PB = 16;
         for (int rb = tid; rb < hs; rb += EPI_BINS * EPI_THREADS) {
             float acc[EPI_BINS], svr[EPI_BINS], prf[EPI_BINS], shp[EPI_BINS];
@@ -620,6 +634,13 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                     const int r = min(rb + j * EPI_THREADS, hs - 1);
 #pragma unroll
                     for (int u = 0; u < PB; ++u) c[j][u] = __ldcg(stot + (long long)s_psym[p0 + u] * hs + r);
+                    if (BATCH) {
+                        int e[PB];
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) e[u] = __ldcg(eo.add + (long long)s_psym[p0 + u] * hs + r);
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) c[j][u] += e[u];
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
@@ -659,8 +680,8 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 }
                 sG[r] = out;
                 if (slab == 0 && !defer) {
-                    M.rfun[r] = out;
-                    if (!is_sq) M.total[r] = out;
+                    if (!BATCH) M.rfun[r] = out;
+                    if (!is_sq) total[r] = out;
                 }
             }
         }
@@ -712,7 +733,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 for (int i = tid; i < hs; i += EPI_THREADS) sG[i] = sT[i];
                 __syncthreads();
             }
-            for (int i = tid; i < hs; i += EPI_THREADS) { M.rfun[i] = sG[i]; M.total[i] = sG[i]; }
+            for (int i = tid; i < hs; i += EPI_THREADS) { if (!BATCH) M.rfun[i] = sG[i]; total[i] = sG[i]; }
             __syncthreads();
         }
         // ---- 2. chi^2 of an r-space model
@@ -791,7 +812,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 } else {
                     if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                            // (:1258-1260)
                 }
-                M.total[q0 + lane] = sv;
+                total[q0 + lane] = sv;
             }
             __threadfence();
         }
@@ -812,29 +833,29 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
             //          the reduced constraint), then scale the slices the other CTAs left unscaled, prior, window
             float sf = M.scale;
             if (M.refit) {
-                fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(M.total + i), 1.0f); },
+                fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(total + i), 1.0f); },
                                  [&](int i) { return __fsub_rn(M.expv[i], 1.0f); });
                 sf = es.s_sf;
             }
             for (int i = tid; i < nq; i += EPI_THREADS) {
-                float sv = __ldcg(M.total + i);
+                float sv = __ldcg(total + i);
                 if (sf != 1.0f) sv = (M.kind == FRMC_KIND_SQ) ? __fadd_rn(__fmul_rn(sf, __fsub_rn(sv, 1.0f)), 1.0f) : __fmul_rn(sf, sv);
                 if (M.prior) sv = __fadd_rn(M.prior[i], __fmul_rn(M.mf_weight, sv));
-                M.total[i] = sv;
+                total[i] = sv;
             }
             __threadfence();
             __syncthreads();
             if (M.window) {
                 for (int i = tid; i < nq; i += EPI_THREADS)
-                    sT[i] = convolve_same([&](int m) { return __ldcg(M.total + m); }, nq, M.window, M.n_window, i);
+                    sT[i] = convolve_same([&](int m) { return __ldcg(total + m); }, nq, M.window, M.n_window, i);
                 __syncthreads();
-                for (int i = tid; i < nq; i += EPI_THREADS) M.total[i] = sT[i];
+                for (int i = tid; i < nq; i += EPI_THREADS) total[i] = sT[i];
                 __threadfence();
                 __syncthreads();
             }
         }
         for (int i = tid; i < nq; i += EPI_THREADS) {
-            float d = __fsub_rn(M.expv[i], __ldcg(M.total + i));
+            float d = __fsub_rn(M.expv[i], __ldcg(total + i));
             float t = __fmul_rn(d, d);
             if (M.wts) t = __fmul_rn(M.wts[i], t);
             sT[i] = t;
@@ -847,6 +868,35 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         stamps[m * 8 + 5] = clock64();
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(reinterpret_cast<unsigned long long *>(stamps + 122), gt);
+    }
+    if (BATCH) {
+        // the last model of this proposal to finish forms the engine's total standard error: np.sum of the float32
+        // list [chi2_m / varianceSquared_m] (Engine.py:3024-3029; sequential for fewer than 8 terms, numpy's
+        // 8-accumulator tree for exactly 8)
+        if (tid == 0) {
+            eo.res[m] = chi2;
+            eo.res[FRMC_MAX_MODELS + m] = es.s_sf;
+            __threadfence();
+            const unsigned int t = atomicAdd(eo.mticket, 1u);
+            if (t == (unsigned int)(ms.n - 1)) {
+                *eo.mticket = 0u;                      // re-arm: the proposal may be evaluated again after an accept
+                __threadfence();
+                float term[FRMC_MAX_MODELS];
+#pragma unroll
+                for (int i = 0; i < FRMC_MAX_MODELS; ++i) term[i] = (i < ms.n) ? __fdiv_rn(__ldcg(eo.res + i), eo.var2[i]) : 0.0f;
+                float tot;
+                if (ms.n == 8) {
+                    tot = __fadd_rn(__fadd_rn(__fadd_rn(term[0], term[1]), __fadd_rn(term[2], term[3])),
+                                    __fadd_rn(__fadd_rn(term[4], term[5]), __fadd_rn(term[6], term[7])));
+                } else {
+                    tot = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < FRMC_MAX_MODELS; ++i) if (i < ms.n) tot = __fadd_rn(tot, term[i]);
+                }
+                *eo.ptotal = tot;
+            }
+        }
+        return;
     }
     if (tid == 0) {
         chi2_out[m] = chi2;
@@ -872,7 +922,7 @@ epilogue_kernel(const ModelSet ms, GridSet gs, float *__restrict__ chi2_out,
     if (slab >= (is_sq ? (M.n_out + 31) / 32 : 1)) return;
     EPI_STAMP(0);
     epilogue_prefetch(es, epi_smem, M, slab);
-    epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps);
+    epilogue_run<false>(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps, EpiOut{});
 }
 
 // ------------------------------------------------------------------ kernels: fused Metropolis step
@@ -975,7 +1025,7 @@ propose_kernel(float4 *__restrict__ atoms, int npad, const ProposalIn in, Propos
     grid_wait(bars + 1, target);
     // (3) epilogue
     EPI_STAMP(0);
-    epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps);
+    epilogue_run<false>(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, stamps, EpiOut{});
 }
 
 // ------------------------------------------------------------------ persistent variant of the per-move kernel
@@ -1109,7 +1159,7 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
         // (3) epilogue; the other CTAs go straight back to waiting (the host sends the next command only after chi^2)
         if (epi) {
             grid_wait(bars + 1, n_delta * gridDim.x);
-            epilogue_run(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, nullptr);
+            epilogue_run<false>(es, epi_smem, ms, gs, m, slab, chi2_out, dev_seq, host_seq, tickets, nullptr, EpiOut{});
         }
         ++expect;
         __syncthreads();
@@ -1120,6 +1170,371 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
     }
 }
 
+
+// ------------------------------------------------------------------ a run of proposals resolved on the device
+// Engine.__on_runtime_step_try_move (Engine.py:3302-3338) for a whole RUN of proposals in one cooperative launch:
+// the proposals' before/after deltas come from ONE pass over the store (every record is tested against the old and
+// the new position of every moved atom of every proposal: 16 B/atom of traffic for the whole batch), and the
+// sequential part of the Metropolis chain -- chi^2 of proposal j depends on which earlier proposals were accepted --
+// is resolved on the device in ROUNDS:
+//   * G groups of epilogue CTAs evaluate the next G unresolved proposals in parallel, each on
+//     (committed totals + its own delta);
+//   * after a grid barrier every CTA walks their total standard errors in order with the engine's rule
+//     (new > old: rejected unless the next pre-drawn random number <= tolerance) up to the first accepted one;
+//     evaluations made beyond it are void and are repeated in the next round;
+//   * the accepted proposal is committed by all CTAs (ordered counts, symmetrised totals, atoms, model totals) and
+//     the deltas of the proposals behind it are corrected for the pairs (their atoms) x (the atoms that just
+//     moved): those pairs were formed against the positions at the start of the batch.
+// A proposal that moves an atom already moved by an accepted proposal of the same batch cannot be corrected; the
+// batch stops in front of it (BatchRun::stopped) and the host starts the next batch there.
+// The result is the sequential path's, bit for bit: the counts are integers and each evaluation sees exactly the
+// totals the sequential path would have staged.
+static const int BATCH_MAX_PROPS = 32;
+static const int BATCH_MAX_GROUPS = 16;
+static const int BATCH_STAMP_SLOTS = 4 + 5 * 64;   // start, cleared, delta pass done, end; 5 per round
+
+struct BatchIn {                      // by value
+    int n_prop, n_atoms;
+    int out_base;                     // index of proposal 0 in the call-wide output arrays
+    int pad;
+    int first[BATCH_MAX_PROPS + 1];   // atoms of proposal j: [first[j], first[j+1])
+    unsigned int share[BATCH_MAX_PROPS];   // bit i: earlier proposal i moves an atom of proposal j
+    int pos[FRMC_MAX_GROUP];          // positions in the sorted store
+    float moved[3 * FRMC_MAX_GROUP];
+};
+
+struct BatchRun {                     // device memory, carried from launch to launch of one call
+    float total;                      // the engine's totalStandardError
+    int n_rand;                       // random numbers consumed
+    int stopped;                      // a conflict ended the run at proposal n_done
+    int n_done;                       // proposals resolved (call-wide index)
+    int n_accepted;
+    int rounds;                       // evaluation rounds (statistics)
+    int pad[2];
+    float cchi2[FRMC_MAX_MODELS];     // chi2 per model of the committed state
+    float csf[FRMC_MAX_MODELS];
+};
+
+struct BatchDev {                     // by value: the batch's device buffers
+    int *bsym[FRMC_MAX_GRIDS];        // [BATCH_MAX_PROPS][nsym*hs]  symmetrised delta per proposal
+    int *bdelta[FRMC_MAX_GRIDS];      // [BATCH_MAX_PROPS][2*cells]  ordered delta per proposal
+    float *btotal[FRMC_MAX_MODELS];   // [BATCH_MAX_PROPS][n_out]
+    float *total_committed[FRMC_MAX_MODELS];
+    float *res;                       // [BATCH_MAX_PROPS][2*FRMC_MAX_MODELS]
+    float *ptotal;                    // [BATCH_MAX_PROPS]
+    unsigned int *tickets;            // [BATCH_MAX_PROPS][FRMC_MAX_MODELS] slab tickets, then [BATCH_MAX_PROPS] model tickets
+    unsigned long long *bov;          // [BATCH_MAX_PROPS] edge-overflow events per proposal
+    BatchRun *run;
+    const float *rand;                // call-wide
+    float *out_chi2;                  // call-wide [n][n_models]
+    int *out_dec;                     // call-wide [n]: 0 rejected, 1 accepted, 2 accepted within the tolerance
+    float var2[FRMC_MAX_MODELS];
+    float tol;
+    int n_groups;                     // G
+};
+
+struct BatchShared {
+    float4 sOld[FRMC_MAX_GROUP];
+    float4 sNew[FRMC_MAX_GROUP];
+    int sPos[FRMC_MAX_GROUP];
+    int sProp[FRMC_MAX_GROUP];
+    float s_pt[BATCH_MAX_GROUPS], s_rand[BATCH_MAX_GROUPS];
+    int s_jstar, s_cur, s_ri, s_stopped;
+    float s_total;
+    unsigned long long s_bar;
+};
+
+// one signed event of proposal `j` (the batch's delta_hit)
+__device__ __forceinline__ void batch_hit(float d2, int sign, int same, int slab, int sym, int j, const GridSet &gs, const BatchDev &bd,
+                                          int nEl, unsigned long long &ov)
+{
+#pragma unroll 1
+    for (int gi = 0; gi < gs.n; ++gi) {
+        const GridDev &G = gs.grid[gi];
+        if (in_range(d2, G.g)) {
+            int *bdel = bd.bdelta[gi] + (long long)j * 2 * G.cells;
+            int *bsy = bd.bsym[gi] + (long long)j * G.nsym * G.g.hs;
+            const int b = bin_index(d2, G.g);
+            if (b < G.g.hs) {
+                atomicAdd(&bdel[(same ? 0 : G.cells) + (long long)slab * G.g.hs + b], sign);
+                atomicAdd(&bsy[(long long)sym * G.g.hs + b], sign);
+            } else {
+                ++ov;
+                const long long flat = (long long)slab * G.g.hs + b;
+                if (G.g.spill && flat < G.cells) {
+                    const int s2 = (int)(flat / G.g.hs), b2 = (int)(flat - (long long)s2 * G.g.hs);
+                    atomicAdd(&bdel[(same ? 0 : G.cells) + flat], sign);
+                    atomicAdd(&bsy[(long long)sym_index(s2 / nEl, s2 % nEl, nEl) * G.g.hs + b2], sign);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void zero_ints(int *p, long long n)
+{
+    // p is 16-byte aligned and the allocation ends on a multiple of four ints (the host pads it)
+    int4 *q = reinterpret_cast<int4 *>(p);
+    const long long n4 = (n + 3) >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        q[i] = make_int4(0, 0, 0, 0);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EPI_THREADS, 1)
+batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, GridSet gs, int nEl, const ModelSet ms, const EpiMap em,
+             const BatchDev bd, unsigned long long *__restrict__ bars, unsigned long long *__restrict__ overflow,
+             long long *__restrict__ stamps)
+{
+    extern __shared__ __align__(128) float epi_smem[];
+    __shared__ __align__(16) EpiShared es;
+    __shared__ BatchShared bs;
+    const int tid = threadIdx.x;
+    // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST launch
+#define BATCH_STAMP(i) do { if (stamps && blockIdx.x == 0 && tid == 0 && (i) < BATCH_STAMP_SLOTS) { \
+        unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[(i)] = (long long)gt_; } } while (0)
+    BATCH_STAMP(0);
+    if (__ldcg(&bd.run->stopped)) return;            // an earlier launch of this call hit a conflict: nothing to do (uniform)
+    const int G = bd.n_groups;
+    const int group = (int)blockIdx.x / em.n, e_idx = (int)blockIdx.x - group * em.n;
+    const bool epi = group < G;
+    const int m = epi ? em.model[e_idx] : 0, slab = epi ? em.slab[e_idx] : 0;
+    if (epi) epilogue_prefetch(es, epi_smem, ms.m[m], slab);
+    // grid barrier generations: the counter only grows; every earlier launch left it at a multiple of the grid size
+    // and fewer than gridDim.x CTAs can have arrived at this launch's first barrier when this one reads it
+    if (tid == 0) {
+        const unsigned long long v = ld_acquire_u64(bars);
+        bs.s_bar = v - v % gridDim.x;
+    }
+    __syncthreads();
+    unsigned long long bar_target = bs.s_bar;
+    const int np = in.n_prop, na = in.n_atoms;
+    // ---- (1) clear the per-proposal buffers, load the moved atoms
+    for (int gi = 0; gi < gs.n; ++gi) {
+        const GridDev &Gd = gs.grid[gi];
+        zero_ints(bd.bsym[gi], (long long)np * Gd.nsym * Gd.g.hs);
+        zero_ints(bd.bdelta[gi], (long long)np * 2 * Gd.cells);
+    }
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < BATCH_MAX_PROPS * (FRMC_MAX_MODELS + 1); i += blockDim.x) bd.tickets[i] = 0u;
+        for (int i = tid; i < BATCH_MAX_PROPS; i += blockDim.x) bd.bov[i] = 0ull;
+    }
+    for (int t = tid; t < na; t += blockDim.x) {
+        const int p = in.pos[t];
+        const float4 o = __ldcg(atoms + p);
+        bs.sOld[t] = o;
+        bs.sNew[t] = make_float4(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], o.w);
+        bs.sPos[t] = p;
+        int j = 0;
+        while (j + 1 < np && in.first[j + 1] <= t) ++j;
+        bs.sProp[t] = j;
+    }
+    grid_arrive(bars);
+    bar_target += gridDim.x;
+    grid_wait(bars, bar_target);
+    BATCH_STAMP(1);
+    // ---- (2) delta pass of the whole batch
+    {
+        const int T = gridDim.x * blockDim.x;
+        const float4 padrec = make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+        float4 nxt[DELTA_UNROLL];
+        {
+            const int p0 = blockIdx.x * blockDim.x + tid;
+#pragma unroll
+            for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
+        }
+        for (int p0 = blockIdx.x * blockDim.x + tid; p0 < npad; p0 += DELTA_UNROLL * T) {
+            float4 a[DELTA_UNROLL];
+#pragma unroll
+            for (int u = 0; u < DELTA_UNROLL; ++u) a[u] = nxt[u];
+            {
+                const int q0 = p0 + DELTA_UNROLL * T;
+#pragma unroll
+                for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = q0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
+            }
+#pragma unroll
+            for (int u = 0; u < DELTA_UNROLL; ++u) {
+                const int p = p0 + u * T;
+                const uint32_t mj = __float_as_uint(a[u].w);
+                if (mj == PAD_META) continue;
+                bool moved_here = false;                 // this record is one of the batch's moved atoms (rare)
+                for (int t = 0; t < na; ++t) moved_here |= (bs.sPos[t] == p);
+                const int ej = mj & 0xFF;
+                for (int t = 0; t < na; ++t) {
+                    const int j = bs.sProp[t];
+                    if (moved_here) {
+                        // a proposal never pairs its atoms with the stored copy of its own atoms (handled below)
+                        bool own = false;
+                        for (int v = in.first[j]; v < in.first[j + 1]; ++v) own |= (bs.sPos[v] == p);
+                        if (own) continue;
+                    }
+                    const float4 o = bs.sOld[t], nw = bs.sNew[t];
+                    const uint32_t mt = __float_as_uint(o.w);
+                    const float d2o = dist2<MODE>(o.x, o.y, o.z, a[u].x, a[u].y, a[u].z, L);
+                    const float d2n = dist2<MODE>(nw.x, nw.y, nw.z, a[u].x, a[u].y, a[u].z, L);
+                    const bool ho = (d2o >= gs.t2lo) && (d2o < gs.t2hi);
+                    const bool hn = (d2n >= gs.t2lo) && (d2n < gs.t2hi);
+                    if (ho || hn) {
+                        const int same = (mt >> 8) == (mj >> 8);
+                        const int et = (int)(mt & 0xFF);
+                        const int slab_ = et * nEl + ej;
+                        const int sym = sym_index(et, ej, nEl);
+                        unsigned long long ov = 0;
+                        if (ho) batch_hit(d2o, -1, same, slab_, sym, j, gs, bd, nEl, ov);
+                        if (hn) batch_hit(d2n, +1, same, slab_, sym, j, gs, bd, nEl, ov);
+                        if (ov) atomicAdd(&bd.bov[j], ov);
+                    }
+                }
+            }
+        }
+        if (blockIdx.x == 0) {
+            // pairs inside a proposal's group: (t,u), u earlier in the list -> slab [el_t, el_u] (the M-F convention)
+            for (int e = tid; e < na * na; e += blockDim.x) {
+                const int t = e / na, u = e - t * na;
+                if (u >= t || bs.sProp[t] != bs.sProp[u]) continue;
+                const float4 ot = bs.sOld[t], ou = bs.sOld[u], nt = bs.sNew[t], nu = bs.sNew[u];
+                const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
+                const int same = (mt >> 8) == (mu >> 8);
+                const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+                const int slab_ = et * nEl + eu;
+                const int sym = sym_index(et, eu, nEl);
+                const float d2o = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
+                const float d2n = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
+                unsigned long long ov = 0;
+                if ((d2o >= gs.t2lo) && (d2o < gs.t2hi)) batch_hit(d2o, -1, same, slab_, sym, bs.sProp[t], gs, bd, nEl, ov);
+                if ((d2n >= gs.t2lo) && (d2n < gs.t2hi)) batch_hit(d2n, +1, same, slab_, sym, bs.sProp[t], gs, bd, nEl, ov);
+                if (ov) atomicAdd(&bd.bov[bs.sProp[t]], ov);
+            }
+        }
+    }
+    grid_arrive(bars);
+    bar_target += gridDim.x;
+    grid_wait(bars, bar_target);
+    BATCH_STAMP(2);
+    // ---- (3) rounds
+    int cur = 0, ri = __ldcg(&bd.run->n_rand), n_acc = 0, rounds = 0;
+    float total = __ldcg(&bd.run->total);
+    unsigned int acc_mask = 0u;
+    bool stopped = false;
+    while (cur < np && !stopped) {
+        ++rounds;
+        const int j = cur + group;
+        if (epi && j < np) {
+            EpiOut eo;
+            const GridDev &Gd = gs.grid[ms.m[m].grid];
+            eo.add = bd.bsym[ms.m[m].grid] + (long long)j * Gd.nsym * Gd.g.hs;
+            eo.total = bd.btotal[m] + (long long)j * ms.m[m].n_out;
+            eo.res = bd.res + j * 2 * FRMC_MAX_MODELS;
+            eo.mticket = bd.tickets + BATCH_MAX_PROPS * FRMC_MAX_MODELS + j;
+            eo.ptotal = bd.ptotal + j;
+            eo.var2 = bd.var2;
+            epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + j * FRMC_MAX_MODELS, nullptr, eo);
+        }
+        BATCH_STAMP(4 + 5 * (rounds - 1) + 0);           // CTA 0's own epilogue done
+        grid_arrive(bars);
+        bar_target += gridDim.x;
+        grid_wait(bars, bar_target);
+        BATCH_STAMP(4 + 5 * (rounds - 1) + 1);           // every epilogue of the round done
+        // decisions: every CTA walks the same numbers to the same conclusion
+        const int nj = min(G, np - cur);
+        if (tid < nj) { bs.s_pt[tid] = __ldcg(bd.ptotal + cur + tid); bs.s_rand[tid] = __ldcg(bd.rand + ri + tid); }
+        __syncthreads();
+        if (tid == 0) {
+            int jstar = -1, jj = cur, used = 0;
+            bool stop = false;
+            float tl = total;
+            for (; jj < cur + nj; ++jj) {
+                if (in.share[jj] & acc_mask) { stop = true; break; }
+                const float nt = bs.s_pt[jj - cur];
+                int dec = 1;
+                if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
+                if (blockIdx.x == 0) {
+                    bd.out_dec[in.out_base + jj] = dec;
+                    for (int mm = 0; mm < ms.n; ++mm) bd.out_chi2[(long long)(in.out_base + jj) * ms.n + mm] = __ldcg(bd.res + jj * 2 * FRMC_MAX_MODELS + mm);
+                }
+                if (dec) { tl = nt; jstar = jj; ++jj; break; }
+            }
+            bs.s_jstar = jstar; bs.s_cur = jj; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
+        }
+        __syncthreads();
+        const int jstar = bs.s_jstar;
+        cur = bs.s_cur; ri = bs.s_ri; stopped = bs.s_stopped != 0; total = bs.s_total;
+        __syncthreads();
+        BATCH_STAMP(4 + 5 * (rounds - 1) + 2);           // decisions made
+        if (jstar >= 0) {
+            // ---- commit proposal jstar (all CTAs), correct the deltas of the proposals behind it
+            acc_mask |= 1u << jstar;
+            ++n_acc;
+            const long long stride = (long long)gridDim.x * blockDim.x;
+            const long long gt = (long long)blockIdx.x * blockDim.x + tid;
+            for (int gi = 0; gi < gs.n; ++gi) {
+                const GridDev &Gd = gs.grid[gi];
+                const long long ns = (long long)Gd.nsym * Gd.g.hs;
+                const int *bsy = bd.bsym[gi] + (long long)jstar * ns;
+                for (long long c = gt; c < ns; c += stride) {
+                    const int v = __ldcg(bsy + c);
+                    if (v) { const int t2 = __ldcg(Gd.tot + c) + v; Gd.tot[c] = t2; Gd.stot[c] = t2; }
+                }
+                const int *bdel = bd.bdelta[gi] + (long long)jstar * 2 * Gd.cells;
+                for (long long c = gt; c < 2 * Gd.cells; c += stride) {
+                    const int d = __ldcg(bdel + c);
+                    if (d) Gd.counts[c] = (unsigned long long)((long long)__ldcg(Gd.counts + c) + d);
+                }
+            }
+            for (int mm = 0; mm < ms.n; ++mm) {
+                const float *src = bd.btotal[mm] + (long long)jstar * ms.m[mm].n_out;
+                for (long long i = gt; i < ms.m[mm].n_out; i += stride) bd.total_committed[mm][i] = __ldcg(src + i);
+            }
+            const int a0 = in.first[jstar], a1 = in.first[jstar + 1];
+            if (blockIdx.x == 0) {
+                for (int t = a0 + tid; t < a1; t += blockDim.x) atoms[bs.sPos[t]] = bs.sNew[t];
+                if (tid < ms.n) {
+                    bd.run->cchi2[tid] = __ldcg(bd.res + jstar * 2 * FRMC_MAX_MODELS + tid);
+                    bd.run->csf[tid] = __ldcg(bd.res + jstar * 2 * FRMC_MAX_MODELS + FRMC_MAX_MODELS + tid);
+                }
+            }
+            // pair (t of a later proposal, u of jstar): the delta pass paired t with u's OLD position
+            const int later0 = a1;                   // atoms are listed in proposal order
+            const long long n_items = (long long)(na - later0) * (a1 - a0);
+            for (long long it = gt; it < n_items; it += stride) {
+                const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
+                const int j2 = bs.sProp[t];
+                const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
+                const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
+                const int same = (mt >> 8) == (mu >> 8);
+                const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+                const int slab_ = et * nEl + eu;
+                const int sym = sym_index(et, eu, nEl);
+                const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
+                const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
+                const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
+                const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
+                unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
+                if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
+                if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
+                if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+            }
+            BATCH_STAMP(4 + 5 * (rounds - 1) + 3);       // CTA 0's share of the commit done
+            grid_arrive(bars);
+            bar_target += gridDim.x;
+            grid_wait(bars, bar_target);
+            BATCH_STAMP(4 + 5 * (rounds - 1) + 4);       // commit visible to everyone
+        }
+    }
+    BATCH_STAMP(3);
+#undef BATCH_STAMP
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long ov = 0;
+        for (int j = 0; j < cur; ++j) ov += __ldcg(bd.bov + j);
+        if (ov) atomicAdd(overflow, ov);
+        BatchRun *r = bd.run;
+        r->total = total; r->n_rand = ri; r->n_done = in.out_base + cur; r->n_accepted += n_acc; r->rounds += rounds;
+        __threadfence();
+        r->stopped = stopped ? 1 : 0;
+    }
+}
 }  // namespace frmc
 
 using namespace frmc;
@@ -1193,6 +1608,18 @@ struct frmc_store {
     unsigned int cmd_seq = 0;        // last command number written
     int last_prev = 0;               // resolution carried by the last command (to resend it if the kernel had left)
     unsigned long long persist_launches = 0, persist_cmds = 0;
+    // runs of proposals resolved on the device (batch_kernel)
+    bool batch_ok = false;           // checked in sync_models: resident S(Q) slabs, no refit schedule, co-residency
+    bool batch_ready = false;        // buffers below match the current grids and models
+    BatchDev bdev;
+    std::vector<void *> batch_owned;
+    unsigned long long *d_bbars = nullptr;
+    float *d_brand = nullptr; size_t brand_cap = 0;
+    float *d_bout_chi2 = nullptr; int *d_bout_dec = nullptr; size_t bout_cap = 0;
+    BatchRun *h_brun = nullptr;      // pinned
+    long long *d_bstamps = nullptr;  // debug timeline of the last batch launch (FRMC_BATCH_STAMPS=1)
+    cudaEvent_t bev0 = nullptr, bev1 = nullptr;
+    unsigned long long batch_launches = 0, batch_rounds = 0, batch_proposals = 0;
     unsigned long long accepted = 0;  // the engine's count of accepted moves (refit schedule, Core/Constraint.py:1418-1422)
     float chi2_committed[FRMC_MAX_MODELS];
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
@@ -1375,6 +1802,25 @@ static int sync_models(frmc_store *s)
 #undef PERSIST_ATTR
         cudaGetLastError();
     }
+    // the batch kernel has the persistent kernel's requirements (resident slabs, constant refit flag)
+    s->batch_ok = s->fused_ok && !s->models.empty();
+    for (auto &m : s->models) {
+        const bool is_sq = (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ);
+        if (is_sq && (m.dev.hs + SQ_ROWS - 1) / SQ_ROWS > m.dev.n_stages) s->batch_ok = false;
+        if (m.adjust_freq > 0) s->batch_ok = false;
+    }
+    if (s->batch_ok) {
+        int per_sm = 0;
+#define BATCH_ATTR(M) do { \
+            if (cudaFuncSetAttribute(batch_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)) != cudaSuccess) s->batch_ok = false; \
+            cudaFuncSetAttribute(batch_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batch_kernel<M>, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->batch_ok = false; \
+        } while (0)
+        BATCH_ATTR(MODE_IBC); BATCH_ATTR(MODE_ORTHO_FAST); BATCH_ATTR(MODE_TRI_FAST); BATCH_ATTR(MODE_ORTHO_GEN); BATCH_ATTR(MODE_TRI_GEN);
+#undef BATCH_ATTR
+        cudaGetLastError();
+    }
+    s->batch_ready = false;
     s->models_dirty = false;
     return FRMC_OK;
 }
@@ -1732,6 +2178,95 @@ static int stage_proposal(frmc_store *s, const int32_t *indexes, int k, const fl
     return FRMC_OK;
 }
 
+
+// ---- runs of proposals resolved on the device
+static int batch_prepare(frmc_store *s)
+{
+    if (s->batch_ready) return FRMC_OK;
+    for (void *p : s->batch_owned) cudaFree(p);
+    s->batch_owned.clear();
+    BatchDev &bd = s->bdev;
+    memset(&bd, 0, sizeof(bd));
+    auto alloc = [&](void **out, size_t bytes) -> int {
+        FRMC_CUDA(cudaMalloc(out, bytes));
+        s->batch_owned.push_back(*out);
+        FRMC_CUDA(cudaMemsetAsync(*out, 0, bytes, s->stream));
+        return FRMC_OK;
+    };
+    int rc;
+    for (size_t g = 0; g < s->grids.size(); ++g) {
+        const GridDev &G = s->grids[g].dev;
+        if ((rc = alloc((void **)&bd.bsym[g], sizeof(int) * ((size_t)BATCH_MAX_PROPS * G.nsym * G.g.hs + 4)))) return rc;
+        if ((rc = alloc((void **)&bd.bdelta[g], sizeof(int) * ((size_t)BATCH_MAX_PROPS * 2 * G.cells + 4)))) return rc;
+    }
+    for (size_t m = 0; m < s->models.size(); ++m) {
+        if ((rc = alloc((void **)&bd.btotal[m], sizeof(float) * (size_t)BATCH_MAX_PROPS * s->models[m].dev.n_out))) return rc;
+        bd.total_committed[m] = s->models[m].total_committed;
+    }
+    if ((rc = alloc((void **)&bd.res, sizeof(float) * BATCH_MAX_PROPS * 2 * FRMC_MAX_MODELS))) return rc;
+    if ((rc = alloc((void **)&bd.ptotal, sizeof(float) * BATCH_MAX_PROPS))) return rc;
+    if ((rc = alloc((void **)&bd.tickets, sizeof(unsigned int) * BATCH_MAX_PROPS * (FRMC_MAX_MODELS + 1)))) return rc;
+    if ((rc = alloc((void **)&bd.bov, sizeof(unsigned long long) * BATCH_MAX_PROPS))) return rc;
+    if ((rc = alloc((void **)&bd.run, sizeof(BatchRun)))) return rc;
+    if (!s->d_bbars) {
+        FRMC_CUDA(cudaMalloc(&s->d_bbars, sizeof(unsigned long long) * 2));
+        FRMC_CUDA(cudaMemsetAsync(s->d_bbars, 0, sizeof(unsigned long long) * 2, s->stream));
+    }
+    if (!s->h_brun) FRMC_CUDA(cudaHostAlloc((void **)&s->h_brun, sizeof(BatchRun), cudaHostAllocDefault));
+    if (!s->bev0) { FRMC_CUDA(cudaEventCreate(&s->bev0)); FRMC_CUDA(cudaEventCreate(&s->bev1)); }
+    bd.n_groups = std::max(1, std::min(BATCH_MAX_GROUPS, s->ctx->sm_count / std::max(1, s->epi_map.n)));
+    if (const char *e = getenv("FRMC_BATCH_GROUPS")) bd.n_groups = std::max(1, std::min(bd.n_groups, atoi(e)));
+    s->batch_ready = true;
+    return FRMC_OK;
+}
+
+template <int MODE>
+static int launch_batch_t(frmc_store *s, const BatchIn &in)
+{
+    GridSet gs = make_gridset(s);
+    ModelSet ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = (int)s->models.size();
+    for (int i = 0; i < ms.n; ++i) { ms.m[i] = s->models[i].dev; ms.m[i].refit = 0; }
+    int npad = (int)s->npad, nEl = s->nEl;
+    unsigned long long *ovf = s->d_overflow;
+    if (!s->d_bstamps && getenv("FRMC_BATCH_STAMPS")) {
+        FRMC_CUDA(cudaMalloc(&s->d_bstamps, sizeof(long long) * BATCH_STAMP_SLOTS));
+    }
+    if (s->d_bstamps) FRMC_CUDA(cudaMemsetAsync(s->d_bstamps, 0, sizeof(long long) * BATCH_STAMP_SLOTS, s->stream));
+    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &s->d_bbars, &ovf, &s->d_bstamps};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)batch_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
+                                                args, s->epi_smem, s->stream);
+    if (e != cudaSuccess) {
+        set_error("cooperative launch of the batch kernel failed: %s", cudaGetErrorString(e));
+        return FRMC_ECUDA;
+    }
+    ++g_launch_count;
+    ++s->batch_launches;
+    return FRMC_OK;
+}
+
+static int launch_batch(frmc_store *s, int mode, const BatchIn &in)
+{
+    switch (mode) {
+        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in);
+        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in);
+        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in);
+        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in);
+        default: return launch_batch_t<MODE_TRI_GEN>(s, in);
+    }
+}
+
+// the engine's decision (Engine.py:3317-3325) on the host, for the sequential fallback of frmc_run_batch
+static float total_standard_error(const float *chi2, const float *var2, int nm)
+{
+    float term[FRMC_MAX_MODELS];
+    for (int i = 0; i < nm; ++i) term[i] = chi2[i] / var2[i];
+    if (nm == 8) return ((term[0] + term[1]) + (term[2] + term[3])) + ((term[4] + term[5]) + (term[6] + term[7]));
+    float t = 0.0f;
+    for (int i = 0; i < nm; ++i) t = t + term[i];
+    return t;
+}
 extern "C" {
 
 frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const float *basis, int isPBC,
@@ -1804,6 +2339,12 @@ void frmc_store_destroy(frmc_store *s)
     if (s->h_chi2) cudaFreeHost(s->h_chi2);
     if (s->h_cmd) cudaFreeHost(s->h_cmd);
     cudaFree(s->d_cmd); cudaFree(s->d_pbars);
+    for (void *p : s->batch_owned) cudaFree(p);
+    cudaFree(s->d_bstamps);
+    cudaFree(s->d_bbars); cudaFree(s->d_brand); cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec);
+    if (s->h_brun) cudaFreeHost(s->h_brun);
+    if (s->bev0) cudaEventDestroy(s->bev0);
+    if (s->bev1) cudaEventDestroy(s->bev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -2206,6 +2747,189 @@ int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const 
         if (rc) return rc;
     }
     return frmc_propose(s, indexes, k, moved, chi2_after);
+}
+
+int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32_t *indexes, const float *moved,
+                   const float *variance_sq, float tolerance, const float *rand, float *total_io,
+                   float *chi2_out, int32_t *decisions, int32_t *n_rand_used, double *device_ms)
+{
+    FRMC_REQUIRE(s && indexes && moved && total_io, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(n >= 1, FRMC_EINVAL, "need at least one proposal");
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_REQUIRE(!s->grids.empty() && !s->models.empty(), FRMC_ESTATE, "a run of proposals needs at least one grid and one model");
+    for (auto &g : s->grids) FRMC_REQUIRE(g.valid, FRMC_ESTATE, "call frmc_compute_data before proposing moves");
+    const int nm = (int)s->models.size();
+    float var2[FRMC_MAX_MODELS];
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) var2[i] = (variance_sq && i < nm) ? variance_sq[i] : 1.0f;
+    // offsets of the groups, sizes checked
+    std::vector<int> first((size_t)n + 1, 0);
+    for (int j = 0; j < n; ++j) {
+        const int k = group_sizes ? group_sizes[j] : 1;
+        FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group size %d of proposal %d outside 1..%d", k, j, FRMC_MAX_GROUP);
+        first[j + 1] = first[j] + k;
+    }
+    const int n_atoms = first[n];
+    float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int t = 0; t < n_atoms; ++t) {
+        FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", indexes[t], (long long)s->n - 1);
+        for (int c = 0; c < 3; ++c) {
+            const float v = moved[3 * t + c];
+            FRMC_REQUIRE(v == v && !isinf(v), FRMC_EINVAL, "moved coordinates contain NaN or Inf");
+            plo[c] = std::min(plo[c], v); phi[c] = std::max(phi[c], v);
+        }
+    }
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    int rc = flush_pending(s);
+    if (rc) return rc;
+    if ((rc = sync_models(s))) return rc;
+    int used_rand = 0;
+    if (device_ms) *device_ms = 0.0;
+    if (!s->batch_ok || s->timing) {
+        // sequential device path (one launch per proposal), same rule, same outputs: models the batch kernel
+        // does not take (S(Q) slab larger than shared memory, scale-factor refit schedule)
+        float total = *total_io;
+        std::vector<float> chi2((size_t)FRMC_MAX_MODELS, 0.f);
+        for (int j = 0; j < n; ++j) {
+            rc = frmc_propose(s, indexes + first[j], first[j + 1] - first[j], moved + 3 * (size_t)first[j], chi2.data());
+            if (rc) return rc;
+            const float nt = total_standard_error(chi2.data(), var2, nm);
+            int dec = 1;
+            if (nt > total) {
+                FRMC_REQUIRE(rand != nullptr, FRMC_EINVAL, "a worse proposal needs a random number and rand is NULL");
+                dec = (rand[used_rand++] > tolerance) ? 0 : 2;
+            }
+            if (chi2_out) for (int m = 0; m < nm; ++m) chi2_out[(size_t)j * nm + m] = chi2[m];
+            if (decisions) decisions[j] = dec;
+            rc = dec ? frmc_accept(s) : frmc_reject(s);
+            if (rc) return rc;
+            if (dec) total = nt;
+        }
+        *total_io = total;
+        if (n_rand_used) *n_rand_used = used_rand;
+        return FRMC_OK;
+    }
+    FRMC_REQUIRE(rand != nullptr, FRMC_EINVAL, "rand is NULL (one pre-drawn number per proposal)");
+    if ((rc = batch_prepare(s))) return rc;
+    // conservative coordinate bounds for the wrap mode: every proposed position may become a stored one
+    for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], plo[c]); s->hi[c] = std::max(s->hi[c], phi[c]); }
+    const int mode = current_mode(s, nullptr, nullptr);
+    // call-wide device arrays
+    if (s->brand_cap < (size_t)n + BATCH_MAX_GROUPS) {
+        cudaFree(s->d_brand); s->d_brand = nullptr; s->brand_cap = 0;
+        FRMC_CUDA(cudaMalloc(&s->d_brand, sizeof(float) * ((size_t)n + BATCH_MAX_GROUPS)));
+        s->brand_cap = (size_t)n + BATCH_MAX_GROUPS;
+    }
+    if (s->bout_cap < (size_t)n) {
+        cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec); s->d_bout_chi2 = nullptr; s->d_bout_dec = nullptr; s->bout_cap = 0;
+        FRMC_CUDA(cudaMalloc(&s->d_bout_chi2, sizeof(float) * (size_t)n * FRMC_MAX_MODELS));
+        FRMC_CUDA(cudaMalloc(&s->d_bout_dec, sizeof(int) * (size_t)n));
+        s->bout_cap = (size_t)n;
+    }
+    FRMC_CUDA(cudaMemsetAsync(s->d_brand, 0, sizeof(float) * ((size_t)n + BATCH_MAX_GROUPS), s->stream));
+    FRMC_CUDA(cudaMemcpyAsync(s->d_brand, rand, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    BatchDev &bd = s->bdev;
+    bd.rand = s->d_brand; bd.out_chi2 = s->d_bout_chi2; bd.out_dec = s->d_bout_dec;
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.var2[i] = var2[i];
+    bd.tol = tolerance;
+    BatchRun run0;
+    memset(&run0, 0, sizeof(run0));
+    run0.total = *total_io;
+    for (int m = 0; m < nm; ++m) { run0.cchi2[m] = s->chi2_committed[m]; run0.csf[m] = s->models[m].dev.scale; }
+    *s->h_brun = run0;
+    FRMC_CUDA(cudaMemcpyAsync(bd.run, s->h_brun, sizeof(BatchRun), cudaMemcpyHostToDevice, s->stream));
+    if (device_ms) FRMC_CUDA(cudaEventRecord(s->bev0, s->stream));
+    int done = 0;
+    while (done < n) {
+        // cut [done, n) into launches of at most BATCH_MAX_PROPS proposals / FRMC_MAX_GROUP atoms
+        int j0 = done;
+        while (j0 < n) {
+            BatchIn in;
+            memset(&in, 0, sizeof(in));
+            in.out_base = j0;
+            int np = 0, na = 0;
+            while (j0 + np < n && np < BATCH_MAX_PROPS && na + (first[j0 + np + 1] - first[j0 + np]) <= FRMC_MAX_GROUP) {
+                const int j = j0 + np;
+                in.first[np] = na;
+                unsigned int share = 0u;
+                for (int t = first[j]; t < first[j + 1]; ++t) {
+                    const int pos = s->lay.inv[indexes[t]];
+                    for (int v = 0; v < na; ++v)
+                        if (in.pos[v] == pos) {
+                            int jp = 0;
+                            while (in.first[jp + 1] <= v && jp + 1 < np) ++jp;
+                            share |= 1u << jp;
+                        }
+                }
+                for (int t = first[j]; t < first[j + 1]; ++t, ++na) {
+                    in.pos[na] = s->lay.inv[indexes[t]];
+                    in.moved[3 * na] = moved[3 * (size_t)t]; in.moved[3 * na + 1] = moved[3 * (size_t)t + 1]; in.moved[3 * na + 2] = moved[3 * (size_t)t + 2];
+                }
+                in.share[np] = share;
+                ++np;
+                in.first[np] = na;
+            }
+            in.n_prop = np; in.n_atoms = na;
+            if ((rc = launch_batch(s, mode, in))) return rc;
+            j0 += np;
+        }
+        FRMC_CUDA(cudaMemcpyAsync(s->h_brun, bd.run, sizeof(BatchRun), cudaMemcpyDeviceToHost, s->stream));
+        FRMC_CUDA(cudaStreamSynchronize(s->stream));
+        const BatchRun &r = *s->h_brun;
+        FRMC_REQUIRE(r.n_done > done && r.n_done <= n, FRMC_ECUDA, "batch kernel made no progress (done %d -> %d of %d)", done, r.n_done, n);
+        done = r.n_done;
+        if (done < n) {
+            FRMC_REQUIRE(r.stopped, FRMC_ECUDA, "batch kernel ended early without a conflict (done %d of %d)", done, n);
+            // a proposal moves an atom that an accepted proposal of its launch had moved: start a new launch at it
+            s->h_brun->stopped = 0;
+            FRMC_CUDA(cudaMemcpyAsync(bd.run, s->h_brun, sizeof(BatchRun), cudaMemcpyHostToDevice, s->stream));
+        }
+    }
+    if (device_ms) {
+        FRMC_CUDA(cudaEventRecord(s->bev1, s->stream));
+        FRMC_CUDA(cudaEventSynchronize(s->bev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->bev0, s->bev1);
+        *device_ms = ms;
+    }
+    if (chi2_out) {
+        FRMC_CUDA(cudaMemcpyAsync(chi2_out, s->d_bout_chi2, sizeof(float) * (size_t)n * nm, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (decisions) FRMC_CUDA(cudaMemcpyAsync(decisions, s->d_bout_dec, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    const BatchRun &r = *s->h_brun;
+    *total_io = r.total;
+    if (n_rand_used) *n_rand_used = r.n_rand;
+    if (r.n_accepted > 0) for (int m = 0; m < nm; ++m) { s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m]; }
+    s->accepted += (unsigned long long)r.n_accepted;
+    s->batch_rounds += (unsigned long long)r.rounds;
+    s->batch_proposals += (unsigned long long)n;
+    return FRMC_OK;
+}
+
+int frmc_store_batch_stats(frmc_store *s, uint64_t *launches, uint64_t *rounds, uint64_t *proposals)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    if (launches) *launches = s->batch_launches;
+    if (rounds) *rounds = s->batch_rounds;
+    if (proposals) *proposals = s->batch_proposals;
+    return FRMC_OK;
+}
+
+int frmc_store_batch_stamps(frmc_store *s, int64_t *out, int n)
+{
+    FRMC_REQUIRE(s && out && n >= 1 && n <= BATCH_STAMP_SLOTS, FRMC_EINVAL, "bad arguments");
+    FRMC_REQUIRE(s->d_bstamps, FRMC_ESTATE, "no batch timeline recorded (set FRMC_BATCH_STAMPS=1 before the first run)");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    FRMC_CUDA(cudaMemcpy(out, s->d_bstamps, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    return FRMC_OK;
+}
+
+int frmc_store_committed_chi2(frmc_store *s, float *chi2)
+{
+    FRMC_REQUIRE(s && chi2, FRMC_EINVAL, "NULL argument");
+    for (size_t i = 0; i < s->models.size(); ++i) chi2[i] = s->chi2_committed[i];
+    return FRMC_OK;
 }
 
 int frmc_store_replay_proposal(frmc_store *s, int reps, double *ms_per_launch)

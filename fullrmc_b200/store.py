@@ -204,6 +204,61 @@ class DeviceStore(object):
             L.check(rc, "step")
         return self._chi2[:len(self._models)]
 
+    def run_batch(self, indexes, movedBoxCoordinates, total, rand, tolerance=0.0, group_sizes=None, variance_squared=None):
+        """A run of proposals tried in order with the engine's acceptance rule, resolved on the device
+        (include/fullrmc_b200.h: frmc_run_batch; Engine.py:3302-3338).
+
+        :Parameters:
+            #. indexes (int32 (A,)): the moved atoms of all proposals back to back.
+            #. movedBoxCoordinates (float32 (A,3)): their proposed box coordinates.
+            #. total (float): engine.totalStandardError before the run.
+            #. rand (float32 (n,)): pre-drawn uniform numbers, one consumed per worse proposal.
+            #. tolerance (float): engine.tolerance.
+            #. group_sizes (None, int32 (n,)): atoms per proposal (None: one each).
+            #. variance_squared (None, float32 (n_models,)): constraint.varianceSquared (None: 1).
+
+        :Returns: dict with chi2 (n, n_models), decisions (n,) int32 (0 rejected / 1 accepted / 2 tolerated),
+            total (float32), rand_used (int), device_ms (float).
+        """
+        idx = np.ascontiguousarray(indexes, dtype=_I32).ravel()
+        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
+        if moved.shape != (idx.shape[0], 3):
+            raise ValueError("movedBoxCoordinates must be (A,3)")
+        if group_sizes is None:
+            n, gs = idx.shape[0], None
+        else:
+            gs = np.ascontiguousarray(group_sizes, dtype=_I32).ravel()
+            n = gs.shape[0]
+            if int(gs.sum()) != idx.shape[0]:
+                raise ValueError("group_sizes must add up to the number of indexes")
+        rnd = np.ascontiguousarray(rand, dtype=_F32).ravel()
+        if rnd.shape[0] < n:
+            raise ValueError("rand must hold one number per proposal")
+        var = None if variance_squared is None else np.ascontiguousarray(variance_squared, dtype=_F32).ravel()
+        if var is not None and var.shape[0] != self.n_models:
+            raise ValueError("variance_squared must hold one value per model")
+        chi2 = np.zeros((n, self.n_models), dtype=_F32)
+        dec = np.zeros(n, dtype=_I32)
+        tot = ctypes.c_float(float(_F32(total)))
+        used = ctypes.c_int32(0)
+        ms = ctypes.c_double(0.0)
+        L.check(self._lib.frmc_run_batch(self._handle, n, L.ptr(gs, L.c_i32p), L.ptr(idx, L.c_i32p), L.ptr(moved, L.c_f32p),
+                                         L.ptr(var, L.c_f32p), float(_F32(tolerance)), L.ptr(rnd, L.c_f32p), ctypes.byref(tot),
+                                         L.ptr(chi2, L.c_f32p), L.ptr(dec, L.c_i32p), ctypes.byref(used), ctypes.byref(ms)),
+                "run_batch")
+        return {"chi2": chi2, "decisions": dec, "total": _F32(tot.value), "rand_used": int(used.value), "device_ms": float(ms.value)}
+
+    def batch_stats(self):
+        """(batch launches, evaluation rounds inside them, proposals resolved)"""
+        a = ctypes.c_uint64(0); b = ctypes.c_uint64(0); c = ctypes.c_uint64(0)
+        L.check(self._lib.frmc_store_batch_stats(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "batch_stats")
+        return int(a.value), int(b.value), int(c.value)
+
+    def committed_chi2(self):
+        out = np.zeros(8, dtype=_F32)
+        L.check(self._lib.frmc_store_committed_chi2(self._handle, L.ptr(out, L.c_f32p)), "committed_chi2")
+        return out[:self.n_models].copy()
+
     def replay_proposal(self, reps):
         """Average device time (ms) of the staged proposal's pipeline over `reps` back-to-back launches."""
         ms = ctypes.c_double(0.0)

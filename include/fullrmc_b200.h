@@ -256,6 +256,31 @@ int frmc_reject(frmc_store *s);
 /* One host call per Metropolis step: resolve the staged proposal (previous = 1 accept, 0 reject;
  * ignored when nothing is staged) and evaluate the next one. */
 int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const float *moved, float *chi2_after);
+/* A RUN of n proposals tried in sequence with the engine's own acceptance rule, resolved on the device
+ * (replaces n rounds of Engine.__on_runtime_step_try_move, Engine.py:3302-3338, for the histogram constraints):
+ *   total_new = sum_m chi2_m / variance_sq[m]           (Engine.compute_total_standard_error, Engine.py:3024-3029)
+ *   total_new > total:  rejected when the NEXT pre-drawn random number > tolerance, else accepted ("tolerated")
+ *   otherwise accepted; an accepted proposal makes total = total_new, moves its atoms and commits its histograms.
+ * Proposal j moves group_sizes[j] atoms (NULL: one atom each); `indexes` / `moved` hold the groups back to back
+ * (original atom indices, [k,3] box coordinates each).  rand: n numbers, consumed in order, one per worse proposal
+ * (generate_random_float is only drawn for those); *n_rand_used returns how many were consumed.  *total_io: the engine's
+ * totalStandardError before / after.  chi2_out [n][n_models] (the chi2 every proposal was judged on), decisions [n]
+ * (0 rejected, 1 accepted, 2 accepted within the tolerance), n_rand_used and device_ms (CUDA-event time of the
+ * launches) may be NULL.  The outcome is identical to n frmc_step calls with that rule on the host.  One pass over
+ * the store serves up to 32 proposals / 64 moved atoms (16 B/atom of traffic for all of them); see batch_kernel in
+ * csrc/store.cu.  Models with a scale-factor refit schedule or an S(Q) slab beyond shared memory run the same
+ * rule with one launch per proposal. */
+int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32_t *indexes, const float *moved,
+                   const float *variance_sq, float tolerance, const float *rand, float *total_io,
+                   float *chi2_out, int32_t *decisions, int32_t *n_rand_used, double *device_ms);
+/* batch launches, evaluation rounds inside them and proposals they resolved so far */
+int frmc_store_batch_stats(frmc_store *s, uint64_t *launches, uint64_t *rounds, uint64_t *proposals);
+/* Debug (FRMC_BATCH_STAMPS=1 in the environment before the first run): globaltimer ns of CTA 0 at the phase
+ * boundaries of the LAST batch launch: [0] start, [1] buffers cleared, [2] delta pass done, [3] end, then per round r
+ * [4+5r..]: own epilogue done, all epilogues done, decisions made, own commit share done, commit visible (0: no commit). */
+int frmc_store_batch_stamps(frmc_store *s, int64_t *out, int n);
+/* chi2 per model of the committed state (constraint.standardError) */
+int frmc_store_committed_chi2(frmc_store *s, float *chi2);
 /* Measurement helper: re-launch the staged proposal's device pipeline `reps` times back to back
  * (no host round trip in between) and return the average device time per launch, CUDA events on
  * the store's stream.  The staged state is restored afterwards. */
