@@ -563,6 +563,7 @@ __device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem
 // chi^2 go to per-proposal buffers, and nothing is published to the host (the kernel decides itself).
 struct EpiOut {
     const int *add;          // [nsym][hs] the proposal's symmetrised delta on this model's grid
+    const int *add2[3];      // deltas of earlier proposals this evaluation ASSUMES accepted (speculation), or null
     float *total;            // [n_out]    model total of this proposal
     float *res;              // [2*FRMC_MAX_MODELS] chi2 per model, then the scale factor each evaluation used
     unsigned int *mticket;   // counts the models of this proposal that have their chi2
@@ -640,6 +641,15 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                         for (int u = 0; u < PB; ++u) e[u] = __ldcg(eo.add + (long long)s_psym[p0 + u] * hs + r);
 #pragma unroll
                         for (int u = 0; u < PB; ++u) c[j][u] += e[u];
+#pragma unroll
+                        for (int x = 0; x < 3; ++x) {
+                            if (eo.add2[x]) {             // block-uniform
+#pragma unroll
+                                for (int u = 0; u < PB; ++u) e[u] = __ldcg(eo.add2[x] + (long long)s_psym[p0 + u] * hs + r);
+#pragma unroll
+                                for (int u = 0; u < PB; ++u) c[j][u] += e[u];
+                            }
+                        }
                     }
                 }
 #pragma unroll
@@ -1191,6 +1201,7 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
 // totals the sequential path would have staged.
 static const int BATCH_MAX_PROPS = 32;
 static const int BATCH_MAX_GROUPS = 16;
+static const int BATCH_MAX_SPEC = 3;   // accepted-but-uncommitted proposals an evaluation may assume (EpiOut::add2)
 static const int BATCH_STAMP_SLOTS = 4 + 5 * 64;   // start, cleared, delta pass done, end; 5 per round
 
 struct BatchIn {                      // by value
@@ -1238,8 +1249,17 @@ struct BatchShared {
     float4 sNew[FRMC_MAX_GROUP];
     int sPos[FRMC_MAX_GROUP];
     int sProp[FRMC_MAX_GROUP];
+    float4 fOld[FRMC_MAX_GROUP];               // the same positions as one-point boxes for blocks_far:
+    float4 fNew[FRMC_MAX_GROUP];               // periodically reduced coordinates, w = rounding margin
     float s_pt[BATCH_MAX_GROUPS], s_rand[BATCH_MAX_GROUPS];
-    int s_jstar, s_cur, s_ri, s_stopped;
+    unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
+    int slot_k[BATCH_MAX_GROUPS];              // this round's plan: slot s evaluates proposal slot_k[s] ...
+    unsigned int slot_A[BATCH_MAX_GROUPS];     // ... on the committed state plus the proposals of this set
+    int slot_child[BATCH_MAX_GROUPS][2];       // slot of the next proposal if this one is rejected [0] / accepted [1], or -1
+    int path_slot[BATCH_MAX_GROUPS], path_dec[BATCH_MAX_GROUPS];   // the walk of the round: slot and decision per proposal
+    int s_nslots, s_last;
+    unsigned int s_acc;
+    int s_cur, s_ri, s_stopped;
     float s_total;
     unsigned long long s_bar;
 };
@@ -1271,6 +1291,15 @@ __device__ __forceinline__ void batch_hit(float d2, int sign, int same, int slab
     }
 }
 
+// a position as a one-point box for blocks_far (block_bbox_kernel's conventions: fractional part under PBC,
+// w = margin for the rounding of fl(xi - xj) on the raw coordinates)
+__device__ __forceinline__ float4 point_box(float x, float y, float z, int pbc)
+{
+    const float amax = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    if (pbc) { x -= floorf(x); y -= floorf(y); z -= floorf(z); }
+    return make_float4(x, y, z, 1e-6f * (1.0f + amax));
+}
+
 __device__ __forceinline__ void zero_ints(int *p, long long n)
 {
     // p is 16-byte aligned and the allocation ends on a multiple of four ints (the host pads it)
@@ -1283,7 +1312,7 @@ __device__ __forceinline__ void zero_ints(int *p, long long n)
 template <int MODE>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
 batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, GridSet gs, int nEl, const ModelSet ms, const EpiMap em,
-             const BatchDev bd, unsigned long long *__restrict__ bars, unsigned long long *__restrict__ overflow,
+             const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars, unsigned long long *__restrict__ overflow,
              long long *__restrict__ stamps)
 {
     extern __shared__ __align__(128) float epi_smem[];
@@ -1325,9 +1354,27 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         bs.sOld[t] = o;
         bs.sNew[t] = make_float4(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], o.w);
         bs.sPos[t] = p;
+        bs.fOld[t] = point_box(o.x, o.y, o.z, cp.pbc);
+        bs.fNew[t] = point_box(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], cp.pbc);
         int j = 0;
         while (j + 1 < np && in.first[j + 1] <= t) ++j;
         bs.sProp[t] = j;
+    }
+    if (tid < BATCH_MAX_PROPS) bs.near[tid] = 0u;
+    __syncthreads();
+    // which earlier proposals would change proposal j's delta if they were accepted (the pairs the commit corrects)
+    for (int e = tid; e < na * na; e += blockDim.x) {
+        const int t = e / na, u = e - t * na;
+        const int jt = bs.sProp[t], ju = bs.sProp[u];
+        if (ju >= jt) continue;
+        const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
+        const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
+        const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
+        const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
+        const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
+        const bool hit = ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) || ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) ||
+                         ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) || ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi));
+        if (hit) atomicOr(&bs.near[jt], 1u << ju);
     }
     grid_arrive(bars);
     bar_target += gridDim.x;
@@ -1356,11 +1403,54 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             for (int u = 0; u < DELTA_UNROLL; ++u) {
                 const int p = p0 + u * T;
                 const uint32_t mj = __float_as_uint(a[u].w);
-                if (mj == PAD_META) continue;
-                bool moved_here = false;                 // this record is one of the batch's moved atoms (rare)
-                for (int t = 0; t < na; ++t) moved_here |= (bs.sPos[t] == p);
+                // the warp holds one aligned 32-record sub-block: its bounding box from the records themselves
+                // (so it is never stale), then lane l tests moved atoms l, l+32 against it; only the moved atoms
+                // whose old or new position can reach the box are swept (exact: blocks_far bounds the computed d^2
+                // from below, common.cuh)
+                unsigned long long near_mask;
+                if (cp.enabled) {
+                    const float v[3] = {a[u].x, a[u].y, a[u].z};
+                    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, amax = 0.f;
+                    if (mj != PAD_META && isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2])) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            amax = fmaxf(amax, fabsf(v[c]));
+                            const float f = cp.pbc ? (v[c] - floorf(v[c])) : v[c];
+                            lo[c] = f; hi[c] = f;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+                        }
+                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                    }
+                    const float4 loJ = make_float4(lo[0], lo[1], lo[2], 1e-6f * (1.0f + amax));
+                    const float4 hiJ = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? 0.f : 1.f);
+                    near_mask = 0ull;
+                    for (int t0 = 0; t0 < na; t0 += 32) {
+                        const int t = t0 + (tid & 31);
+                        bool reach = false;
+                        if (t < na) {
+                            const float4 fo = bs.fOld[t], fn = bs.fNew[t];
+                            reach = !blocks_far(fo, make_float4(fo.x, fo.y, fo.z, 0.f), loJ, hiJ, cp) ||
+                                    !blocks_far(fn, make_float4(fn.x, fn.y, fn.z, 0.f), loJ, hiJ, cp);
+                        }
+                        near_mask |= (unsigned long long)__ballot_sync(0xffffffffu, reach) << t0;
+                    }
+                } else {
+                    near_mask = (na >= 64) ? ~0ull : ((1ull << na) - 1ull);
+                }
+                if (mj == PAD_META || near_mask == 0ull) continue;
+                bool moved_here = false;                 // this record is one of the batch's moved atoms (rare; its
+                                                         // own old position lies in the box, so it is in near_mask)
+                for (unsigned long long mk = near_mask; mk; mk &= mk - 1ull) moved_here |= (bs.sPos[__ffsll((long long)mk) - 1] == p);
                 const int ej = mj & 0xFF;
-                for (int t = 0; t < na; ++t) {
+                for (unsigned long long mk = near_mask; mk; mk &= mk - 1ull) {
+                    const int t = __ffsll((long long)mk) - 1;
                     const int j = bs.sProp[t];
                     if (moved_here) {
                         // a proposal never pairs its atoms with the stored copy of its own atoms (handled below)
@@ -1413,108 +1503,200 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     BATCH_STAMP(2);
     // ---- (3) rounds
     int cur = 0, ri = __ldcg(&bd.run->n_rand), n_acc = 0, rounds = 0;
+    const int acc_before = __ldcg(&bd.run->n_accepted);
     float total = __ldcg(&bd.run->total);
     unsigned int acc_mask = 0u;
     bool stopped = false;
+    const int lane = tid & 31, wrp = tid >> 5;
     while (cur < np && !stopped) {
         ++rounds;
-        const int j = cur + group;
-        if (epi && j < np) {
+        // ---- plan of the round: the G most probable nodes of the decision tree below (cur, nothing assumed).
+        // Node (k, A) = proposal k evaluated on the committed state + the proposals of A (assumed accepted); its
+        // children are (k+1, A) after a rejection and (k+1, A + {k}) after an acceptance, weighted with the
+        // acceptance ratio seen so far.  A node exists only if no proposal of A shares an atom with k (in.share)
+        // or pairs with one of k's atoms (bs.near): then k's delta needs no correction and the counts are exactly
+        // the sequential path's.  Every CTA builds the same plan from the same integers.
+        if (wrp == 0) {
+            const unsigned FULL = 0xFFFFFFFFu;
+            float pa = __fdiv_rn((float)(acc_before + n_acc + 1), (float)(in.out_base + cur + 2));
+            pa = fminf(fmaxf(pa, 0.02f), 0.98f);
+            int ck = (lane == 0) ? cur : -1, cpar = -1, cacc = 0;
+            unsigned int cA = 0u;
+            float cp = (lane == 0) ? 1.0f : 0.0f;
+            int ns = 0;
+            for (int sl = 0; sl < G; ++sl) {
+                const unsigned key = __float_as_uint(cp);                    // cp >= 0: ordered like the floats
+                const unsigned best = __reduce_max_sync(FULL, key);
+                if (best == 0u) break;
+                const int w = __ffs(__ballot_sync(FULL, key == best)) - 1;
+                const int k = __shfl_sync(FULL, ck, w), par = __shfl_sync(FULL, cpar, w), isacc = __shfl_sync(FULL, cacc, w);
+                const unsigned int A = __shfl_sync(FULL, cA, w);
+                const float pr = __shfl_sync(FULL, cp, w);
+                if (lane == 0) {
+                    bs.slot_k[sl] = k; bs.slot_A[sl] = A; bs.slot_child[sl][0] = -1; bs.slot_child[sl][1] = -1;
+                    if (par >= 0) bs.slot_child[par][isacc] = sl;
+                }
+                const int k1 = k + 1;
+                bool rej_ok = false, acc_ok = false;
+                unsigned int A2 = A | (1u << k);
+                if (k1 < np) {
+                    const unsigned int sh = in.share[k1], nr = bs.near[k1];
+                    rej_ok = !((sh & (acc_mask | A)) || (nr & A));
+                    acc_ok = (__popc(A2) <= BATCH_MAX_SPEC) && !((sh & (acc_mask | A2)) || (nr & A2));
+                }
+                const int e = __ffs(__ballot_sync(FULL, cp == 0.0f) & ~(1u << w)) - 1;   // a free lane: at most G+1 are live
+                if (lane == w) {
+                    if (rej_ok) { ck = k1; cp = __fmul_rn(pr, __fsub_rn(1.0f, pa)); cpar = sl; cacc = 0; }
+                    else { ck = -1; cp = 0.0f; }
+                }
+                if (lane == e && acc_ok) { ck = k1; cA = A2; cp = __fmul_rn(pr, pa); cpar = sl; cacc = 1; }
+                ns = sl + 1;
+                __syncwarp();
+            }
+            if (lane == 0) bs.s_nslots = ns;
+        }
+        __syncthreads();
+        const int ns = bs.s_nslots;
+        const int par = rounds & 1;                          // slot buffers alternate: a CTA may still read round r-1's
+        if (epi && group < ns) {
+            const int k = bs.slot_k[group];
+            unsigned int A = bs.slot_A[group];
+            const int sb = par * BATCH_MAX_GROUPS + group;
             EpiOut eo;
             const GridDev &Gd = gs.grid[ms.m[m].grid];
-            eo.add = bd.bsym[ms.m[m].grid] + (long long)j * Gd.nsym * Gd.g.hs;
-            eo.total = bd.btotal[m] + (long long)j * ms.m[m].n_out;
-            eo.res = bd.res + j * 2 * FRMC_MAX_MODELS;
-            eo.mticket = bd.tickets + BATCH_MAX_PROPS * FRMC_MAX_MODELS + j;
-            eo.ptotal = bd.ptotal + j;
+            const long long per = (long long)Gd.nsym * Gd.g.hs;
+            eo.add = bd.bsym[ms.m[m].grid] + (long long)k * per;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                eo.add2[x] = nullptr;
+                if (A) { eo.add2[x] = bd.bsym[ms.m[m].grid] + (long long)(__ffs(A) - 1) * per; A &= A - 1u; }
+            }
+            eo.total = bd.btotal[m] + (long long)sb * ms.m[m].n_out;
+            eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
+            eo.mticket = bd.tickets + BATCH_MAX_PROPS * FRMC_MAX_MODELS + sb;
+            eo.ptotal = bd.ptotal + sb;
             eo.var2 = bd.var2;
-            epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + j * FRMC_MAX_MODELS, nullptr, eo);
+            epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + sb * FRMC_MAX_MODELS, nullptr, eo);
         }
         BATCH_STAMP(4 + 5 * (rounds - 1) + 0);           // CTA 0's own epilogue done
         grid_arrive(bars);
         bar_target += gridDim.x;
         grid_wait(bars, bar_target);
         BATCH_STAMP(4 + 5 * (rounds - 1) + 1);           // every epilogue of the round done
-        // decisions: every CTA walks the same numbers to the same conclusion
-        const int nj = min(G, np - cur);
-        if (tid < nj) { bs.s_pt[tid] = __ldcg(bd.ptotal + cur + tid); bs.s_rand[tid] = __ldcg(bd.rand + ri + tid); }
+        // decisions: every CTA walks the same numbers down the tree to the same conclusion
+        if (tid < ns) bs.s_pt[tid] = __ldcg(bd.ptotal + par * BATCH_MAX_GROUPS + tid);
+        if (tid >= 32 && tid < 32 + BATCH_MAX_GROUPS) bs.s_rand[tid - 32] = __ldcg(bd.rand + ri + tid - 32);
         __syncthreads();
         if (tid == 0) {
-            int jstar = -1, jj = cur, used = 0;
-            bool stop = false;
+            int sl = 0, k = cur, used = 0, last = -1, n_path = 0;
+            unsigned int A = 0u;
             float tl = total;
-            for (; jj < cur + nj; ++jj) {
-                if (in.share[jj] & acc_mask) { stop = true; break; }
-                const float nt = bs.s_pt[jj - cur];
+            for (;;) {
+                const float nt = bs.s_pt[sl];
                 int dec = 1;
                 if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
-                if (blockIdx.x == 0) {
-                    bd.out_dec[in.out_base + jj] = dec;
-                    for (int mm = 0; mm < ms.n; ++mm) bd.out_chi2[(long long)(in.out_base + jj) * ms.n + mm] = __ldcg(bd.res + jj * 2 * FRMC_MAX_MODELS + mm);
-                }
-                if (dec) { tl = nt; jstar = jj; ++jj; break; }
+                bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
+                if (dec) { A |= 1u << k; tl = nt; last = sl; }
+                sl = bs.slot_child[sl][dec ? 1 : 0];
+                ++k;
+                if (sl < 0) break;
             }
-            bs.s_jstar = jstar; bs.s_cur = jj; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
+            // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
+            const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
+            bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
         }
         __syncthreads();
-        const int jstar = bs.s_jstar;
+        if (blockIdx.x == 0) {
+            // decisions and chi2 of the proposals resolved in this round
+            const int n_path = bs.s_cur - cur, per = ms.n + 1;
+            for (int e = tid; e < n_path * per; e += blockDim.x) {
+                const int i = e / per, mm = e - i * per;
+                if (mm == ms.n) bd.out_dec[in.out_base + cur + i] = bs.path_dec[i];
+                else bd.out_chi2[(long long)(in.out_base + cur + i) * ms.n + mm] =
+                         __ldcg(bd.res + (par * BATCH_MAX_GROUPS + bs.path_slot[i]) * 2 * FRMC_MAX_MODELS + mm);
+            }
+        }
+        const unsigned int Aset = bs.s_acc;
+        const int last = bs.s_last;
         cur = bs.s_cur; ri = bs.s_ri; stopped = bs.s_stopped != 0; total = bs.s_total;
         __syncthreads();
         BATCH_STAMP(4 + 5 * (rounds - 1) + 2);           // decisions made
-        if (jstar >= 0) {
-            // ---- commit proposal jstar (all CTAs), correct the deltas of the proposals behind it
-            acc_mask |= 1u << jstar;
-            ++n_acc;
+        if (Aset) {
+            // ---- commit the accepted proposals (all CTAs), correct the deltas of the unresolved proposals
+            acc_mask |= Aset;
+            n_acc += __popc(Aset);
+            int acc_j[BATCH_MAX_SPEC + 1], n_aj = 0;
+            for (unsigned int a = Aset; a; a &= a - 1u) acc_j[n_aj++] = __ffs(a) - 1;
             const long long stride = (long long)gridDim.x * blockDim.x;
             const long long gt = (long long)blockIdx.x * blockDim.x + tid;
-            for (int gi = 0; gi < gs.n; ++gi) {
-                const GridDev &Gd = gs.grid[gi];
-                const long long ns = (long long)Gd.nsym * Gd.g.hs;
-                const int *bsy = bd.bsym[gi] + (long long)jstar * ns;
-                for (long long c = gt; c < ns; c += stride) {
-                    const int v = __ldcg(bsy + c);
-                    if (v) { const int t2 = __ldcg(Gd.tot + c) + v; Gd.tot[c] = t2; Gd.stot[c] = t2; }
+            const int lb = par * BATCH_MAX_GROUPS + last;    // the evaluation that saw all of them
+            // one list of items over all grids and models (symmetrised totals | ordered counts | model totals), so a
+            // thread usually has one item and the whole commit is a single L2 round trip
+            long long n_items_c = 0;
+            for (int gi = 0; gi < gs.n; ++gi) n_items_c += (long long)gs.grid[gi].nsym * gs.grid[gi].g.hs + 2 * gs.grid[gi].cells;
+            for (int mm = 0; mm < ms.n; ++mm) n_items_c += ms.m[mm].n_out;
+            for (long long it0 = gt; it0 < n_items_c; it0 += stride) {
+                long long c = it0;
+                bool done = false;
+                for (int gi = 0; gi < gs.n && !done; ++gi) {
+                    const GridDev &Gd = gs.grid[gi];
+                    const long long ns_ = (long long)Gd.nsym * Gd.g.hs;
+                    if (c < ns_) {
+                        const int t0 = __ldcg(Gd.tot + c);
+                        int v = 0;
+#pragma unroll
+                        for (int x = 0; x <= BATCH_MAX_SPEC; ++x) if (x < n_aj) v += __ldcg(bd.bsym[gi] + (long long)acc_j[x] * ns_ + c);
+                        if (v) { Gd.tot[c] = t0 + v; Gd.stot[c] = t0 + v; }
+                        done = true;
+                    } else if ((c -= ns_) < 2 * Gd.cells) {
+                        const unsigned long long c0 = __ldcg(Gd.counts + c);
+                        int d = 0;
+#pragma unroll
+                        for (int x = 0; x <= BATCH_MAX_SPEC; ++x) if (x < n_aj) d += __ldcg(bd.bdelta[gi] + (long long)acc_j[x] * 2 * Gd.cells + c);
+                        if (d) Gd.counts[c] = (unsigned long long)((long long)c0 + d);
+                        done = true;
+                    } else c -= 2 * Gd.cells;
                 }
-                const int *bdel = bd.bdelta[gi] + (long long)jstar * 2 * Gd.cells;
-                for (long long c = gt; c < 2 * Gd.cells; c += stride) {
-                    const int d = __ldcg(bdel + c);
-                    if (d) Gd.counts[c] = (unsigned long long)((long long)__ldcg(Gd.counts + c) + d);
+                for (int mm = 0; mm < ms.n && !done; ++mm) {
+                    if (c < ms.m[mm].n_out) { bd.total_committed[mm][c] = __ldcg(bd.btotal[mm] + (long long)lb * ms.m[mm].n_out + c); done = true; }
+                    else c -= ms.m[mm].n_out;
                 }
             }
-            for (int mm = 0; mm < ms.n; ++mm) {
-                const float *src = bd.btotal[mm] + (long long)jstar * ms.m[mm].n_out;
-                for (long long i = gt; i < ms.m[mm].n_out; i += stride) bd.total_committed[mm][i] = __ldcg(src + i);
-            }
-            const int a0 = in.first[jstar], a1 = in.first[jstar + 1];
             if (blockIdx.x == 0) {
-                for (int t = a0 + tid; t < a1; t += blockDim.x) atoms[bs.sPos[t]] = bs.sNew[t];
+                for (int x = 0; x < n_aj; ++x)
+                    for (int t = in.first[acc_j[x]] + tid; t < in.first[acc_j[x] + 1]; t += blockDim.x) atoms[bs.sPos[t]] = bs.sNew[t];
                 if (tid < ms.n) {
-                    bd.run->cchi2[tid] = __ldcg(bd.res + jstar * 2 * FRMC_MAX_MODELS + tid);
-                    bd.run->csf[tid] = __ldcg(bd.res + jstar * 2 * FRMC_MAX_MODELS + FRMC_MAX_MODELS + tid);
+                    bd.run->cchi2[tid] = __ldcg(bd.res + lb * 2 * FRMC_MAX_MODELS + tid);
+                    bd.run->csf[tid] = __ldcg(bd.res + lb * 2 * FRMC_MAX_MODELS + FRMC_MAX_MODELS + tid);
                 }
             }
-            // pair (t of a later proposal, u of jstar): the delta pass paired t with u's OLD position
-            const int later0 = a1;                   // atoms are listed in proposal order
-            const long long n_items = (long long)(na - later0) * (a1 - a0);
-            for (long long it = gt; it < n_items; it += stride) {
-                const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
-                const int j2 = bs.sProp[t];
-                const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
-                const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
-                const int same = (mt >> 8) == (mu >> 8);
-                const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
-                const int slab_ = et * nEl + eu;
-                const int sym = sym_index(et, eu, nEl);
-                const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
-                const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
-                const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
-                const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
-                unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
-                if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
-                if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
-                if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+            // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
+            // Proposals resolved in this round need none: their nodes had no such pair (bs.near).
+            const int later0 = in.first[cur];                // atoms are listed in proposal order
+            for (int x = 0; x < n_aj; ++x) {
+                const int a0 = in.first[acc_j[x]], a1 = in.first[acc_j[x] + 1];
+                const long long n_items = (long long)(na - later0) * (a1 - a0);
+                for (long long it = gt; it < n_items; it += stride) {
+                    const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
+                    const int j2 = bs.sProp[t];
+                    if (!((bs.near[j2] >> acc_j[x]) & 1u)) continue;         // no pair in range (the common case)
+                    const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
+                    const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
+                    const int same = (mt >> 8) == (mu >> 8);
+                    const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+                    const int slab_ = et * nEl + eu;
+                    const int sym = sym_index(et, eu, nEl);
+                    const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
+                    const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
+                    const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
+                    const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
+                    unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
+                    if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
+                    if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                    if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
+                    if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                    if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+                }
             }
             BATCH_STAMP(4 + 5 * (rounds - 1) + 3);       // CTA 0's share of the commit done
             grid_arrive(bars);
@@ -2234,7 +2416,13 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in)
         FRMC_CUDA(cudaMalloc(&s->d_bstamps, sizeof(long long) * BATCH_STAMP_SLOTS));
     }
     if (s->d_bstamps) FRMC_CUDA(cudaMemsetAsync(s->d_bstamps, 0, sizeof(long long) * BATCH_STAMP_SLOTS, s->stream));
-    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &s->d_bbars, &ovf, &s->d_bstamps};
+    // sub-block culling of the delta pass against the widest d^2 window of the grids (frmc_set_block_culling(0): off)
+    GridParams gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.t2max = gs.t2hi;
+    CullParams cp = make_cull(s->L, MODE, gw);
+    if (g_no_cull) cp.enabled = 0;
+    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)batch_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
                                                 args, s->epi_smem, s->stream);
     if (e != cudaSuccess) {

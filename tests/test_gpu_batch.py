@@ -137,6 +137,68 @@ def test_batch_equals_sequential_device_path(name, kinds, n, sigma, tol, repeat,
     seq.close(); bat.close()
 
 
+@pytest.mark.parametrize("kind", ["ortho", "tri_unwrapped", "non_periodic"])
+def test_batch_on_large_sparse_systems(kind, orc):
+    """maxDistance far below the cell size: the delta pass skips most (sub-block, moved atom) pairs, most proposals
+    do not interact, and the rounds resolve several acceptances at once on speculative evaluations (committed state
+    + assumed-accepted deltas).  Proposals next to an earlier one (pair corrections), repeated atoms (conflicts),
+    long jumps across the seam and molecule moves are mixed in.  Bars: bit-exact against the sequential device path,
+    against the same run with culling switched off, and against the oracle's histogram of the final coordinates."""
+    from fullrmc_b200 import _lib as fullrmc_b200
+    case = TS._large_sparse_case(kind)
+    box0 = case["boxCoords"]
+    real = box0.astype(np.float64) @ np.asarray(case["basis"], np.float64)
+    rng = np.random.default_rng(77)
+    n = 150
+    span = 1.0 if case["isPBC"] else 100.0
+    props = []
+    for j in range(n):
+        if j % 9 == 8:
+            idx = props[-1][0].copy()                                      # the same atoms again (conflict if accepted)
+        elif j % 3 == 1:
+            d = np.linalg.norm(real - real[props[-1][0][0]], axis=1)       # an atom a few A from the previous proposal's
+            idx = np.array([int(np.argsort(d)[1 + j % 5])], np.int32)
+        else:
+            idx = C.group_for(case, rng)
+        jump = (0.45 if j % 7 == 0 else 0.004) * span
+        moved = (box0[idx] + rng.normal(0, jump, (idx.shape[0], 3)).astype(F32)).astype(F32)
+        props.append((idx, moved))
+    rand = rng.random(n).astype(F32)
+    idx, moved, sizes = flatten(props)
+    var2 = np.array([1.0, 0.6], F32)
+    results = []
+    for mode in ("sequential", "batch", "batch_noculling"):
+        st, _ = TS._build(case, ["PDF", "SQ"], np.random.default_rng(11))
+        total0 = host_total(st.compute_data(), var2)
+        if mode == "sequential":
+            chis, decs, total, used = sequential_run(st, props, total0, rand, 0.3, var2)
+        else:
+            previous = fullrmc_b200.set_block_culling(mode == "batch")
+            try:
+                out = st.run_batch(idx, moved, total0, rand, tolerance=0.3, group_sizes=sizes, variance_squared=var2)
+            finally:
+                fullrmc_b200.set_block_culling(previous)
+            chis, decs, total, used = out["chi2"], out["decisions"], out["total"], out["rand_used"]
+            launches, rounds, resolved = st.batch_stats()
+            assert resolved == n and rounds < n, "no round resolved more than one proposal (%d rounds)" % rounds
+        results.append((st, chis, decs, F32(total), used))
+    s0, chis, decs, total, used = results[0]
+    assert 10 < int((decs > 0).sum()) < n - 10
+    for st, c, d, t, u in results[1:]:
+        assert np.array_equal(d, decs), "decisions differ"
+        assert np.array_equal(c, chis), "chi2 of the proposals differ"
+        assert t == total and u == used
+        compare_stores(s0, st, 2)
+    kw = TS._hist_kw(case)
+    fi, fe = orc.full_pairs_histograms_coords(boxCoords=s0.get_coords(), moleculeIndex=case["moleculeIndex"],
+                                              elementIndex=case["elementIndex"], ncores=orc.max_threads(), **kw)
+    gi, ge = results[1][0].export_data(0)
+    sym = lambda h: h + h.transpose(1, 0, 2)
+    assert np.array_equal(sym(gi), sym(fi)) and np.array_equal(sym(ge), sym(fe))
+    for r in results:
+        r[0].close()
+
+
 def test_batch_two_grids(orc):
     """PDF and S(Q) on different r-grids (the NiTi arrangement): both grids' deltas come from the same pass"""
     from fullrmc_b200.model import ModelSpec
