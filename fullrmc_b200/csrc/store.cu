@@ -564,11 +564,12 @@ __device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem
 struct EpiOut {
     const int *add;          // [nsym][hs] the proposal's symmetrised delta on this model's grid
     const int *add2[3];      // deltas of earlier proposals this evaluation ASSUMES accepted (speculation), or null
-    float *total;            // [n_out]    model total of this proposal
+    unsigned int amask, amask2[3];   // bit s: row s of the delta can be non-zero (rows of untouched element pairs are not read)
+    float *total;            // [n_out]    model total of this evaluation
     float *res;              // [2*FRMC_MAX_MODELS] chi2 per model, then the scale factor each evaluation used
-    unsigned int *mticket;   // counts the models of this proposal that have their chi2
-    float *ptotal;           // the proposal's total standard error, sum_m chi2_m / varianceSquared_m (Engine.py:3024-3029)
-    const float *var2;       // [n_models]
+    float *terms;            // S(Q) models: [n_out] weighted squared residuals; when set the slab CTAs stop there and
+                             // every CTA forms chi2 itself after the grid barrier (no ticket, no last-CTA stage)
+    int warm;                // this CTA has run this (model, slab) before in this launch: tables and schedule are staged
 };
 
 // part 2: r-space function, chi^2 / S(Q) slice, ticket, publish (steps 1-4 above)
@@ -602,6 +603,8 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     const int np = M.n_pairs;
     const int np_pad = (np + 15) / 16 * 16;
     const bool inline_pairs = np <= EPI_INLINE_PAIRS;
+    const bool cold = !BATCH || !eo.warm;
+    if (cold)
     for (int p = tid; p < np_pad; p += EPI_THREADS) {
         const bool real = p < np;
         if (inline_pairs) {
@@ -612,8 +615,10 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
             s_D[p] = real ? M.D[p] : 1.0f; s_rD[p] = real ? M.rD[p] : 1.0f;
         }
     }
-    for (int r = hs + tid; r < hs_pad; r += EPI_THREADS) sG[r] = 0.0f;
-    __syncthreads();
+    if (cold) {
+        for (int r = hs + tid; r < hs_pad; r += EPI_THREADS) sG[r] = 0.0f;
+        __syncthreads();
+    }
     EPI_STAMP(1);
 
     // ---- 1. r-space function: EPI_BINS bins per thread per round, every load issued before any arithmetic
@@ -638,14 +643,16 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                     if (BATCH) {
                         int e[PB];
 #pragma unroll
-                        for (int u = 0; u < PB; ++u) e[u] = __ldcg(eo.add + (long long)s_psym[p0 + u] * hs + r);
+                        for (int u = 0; u < PB; ++u)
+                            e[u] = ((eo.amask >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(eo.add + (long long)s_psym[p0 + u] * hs + r) : 0;
 #pragma unroll
                         for (int u = 0; u < PB; ++u) c[j][u] += e[u];
 #pragma unroll
                         for (int x = 0; x < 3; ++x) {
                             if (eo.add2[x]) {             // block-uniform
 #pragma unroll
-                                for (int u = 0; u < PB; ++u) e[u] = __ldcg(eo.add2[x] + (long long)s_psym[p0 + u] * hs + r);
+                                for (int u = 0; u < PB; ++u)
+                                    e[u] = ((eo.amask2[x] >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(eo.add2[x] + (long long)s_psym[p0 + u] * hs + r) : 0;
 #pragma unroll
                                 for (int u = 0; u < PB; ++u) c[j][u] += e[u];
                             }
@@ -698,6 +705,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     }
     {   // chi^2 summation schedule (needed at the very end): fetched here, its latency hides behind the barrier
         const int nl = M.pw_leaves;
+        if (cold)
         for (int i = tid; i < nl; i += EPI_THREADS) {
             ps.leaf_off[i] = M.pw_sched[i]; ps.leaf_len[i] = M.pw_sched[nl + i];
             ps.op_dst[i] = M.pw_sched[2 * nl + i]; ps.op_src[i] = M.pw_sched[3 * nl + i];
@@ -759,6 +767,10 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         // ---- 3. S(Q) slice: warp 0 consumes the slab chunk by chunk (refilling the ring only when the slab does not fit)
         if (wrp == 0) {
             float acc = 0.0f;
+            // deferred chi2 (batch): this lane's experimental value and weight, fetched ahead of the row loop
+            const bool with_terms = BATCH && eo.terms && (q0 + lane < nq);
+            const float t_exp = with_terms ? M.expv[q0 + lane] : 0.0f;
+            const float t_wts = (with_terms && M.wts) ? M.wts[q0 + lane] : 1.0f;
             if (resident && !(M.sq_exact & 2)) {
                 // whole slab in shared memory, rows contiguous: flat loop over groups of 4 rows with an
                 // 8-group (32-row) register prefetch, so the FADD chain never waits for a shared load
@@ -823,10 +835,17 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                     if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                            // (:1258-1260)
                 }
                 total[q0 + lane] = sv;
+                if (with_terms) {
+                    const float d = __fsub_rn(t_exp, sv);
+                    float t = __fmul_rn(d, d);
+                    if (M.wts) t = __fmul_rn(t_wts, t);
+                    eo.terms[q0 + lane] = t;
+                }
             }
-            __threadfence();
+            if (!(BATCH && eo.terms)) __threadfence();   // deferred: the grid barrier's fence follows at once
         }
         EPI_STAMP(3);
+        if (BATCH && eo.terms) return;                 // uniform: every CTA sums the terms after the grid barrier
         // last CTA of this model (ticket) owns the chi^2
         __syncthreads();
         if (tid == 0) {
@@ -880,32 +899,8 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         atomicMax(reinterpret_cast<unsigned long long *>(stamps + 122), gt);
     }
     if (BATCH) {
-        // the last model of this proposal to finish forms the engine's total standard error: np.sum of the float32
-        // list [chi2_m / varianceSquared_m] (Engine.py:3024-3029; sequential for fewer than 8 terms, numpy's
-        // 8-accumulator tree for exactly 8)
-        if (tid == 0) {
-            eo.res[m] = chi2;
-            eo.res[FRMC_MAX_MODELS + m] = es.s_sf;
-            __threadfence();
-            const unsigned int t = atomicAdd(eo.mticket, 1u);
-            if (t == (unsigned int)(ms.n - 1)) {
-                *eo.mticket = 0u;                      // re-arm: the proposal may be evaluated again after an accept
-                __threadfence();
-                float term[FRMC_MAX_MODELS];
-#pragma unroll
-                for (int i = 0; i < FRMC_MAX_MODELS; ++i) term[i] = (i < ms.n) ? __fdiv_rn(__ldcg(eo.res + i), eo.var2[i]) : 0.0f;
-                float tot;
-                if (ms.n == 8) {
-                    tot = __fadd_rn(__fadd_rn(__fadd_rn(term[0], term[1]), __fadd_rn(term[2], term[3])),
-                                    __fadd_rn(__fadd_rn(term[4], term[5]), __fadd_rn(term[6], term[7])));
-                } else {
-                    tot = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < FRMC_MAX_MODELS; ++i) if (i < ms.n) tot = __fadd_rn(tot, term[i]);
-                }
-                *eo.ptotal = tot;
-            }
-        }
+        // the engine's total standard error is formed by the decision walk of the batch kernel
+        if (tid == 0) { eo.res[m] = chi2; eo.res[FRMC_MAX_MODELS + m] = es.s_sf; }
         return;
     }
     if (tid == 0) {
@@ -1201,8 +1196,10 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
 // totals the sequential path would have staged.
 static const int BATCH_MAX_PROPS = 32;
 static const int BATCH_MAX_GROUPS = 16;
-static const int BATCH_MAX_SPEC = 3;   // accepted-but-uncommitted proposals an evaluation may assume (EpiOut::add2)
+static const int BATCH_MAX_SPEC = 3;
+static const int BATCH_DEFER_MAX_LEAVES = 32;   // longest pairwise schedule a warp sums (n_out up to ~4000)   // accepted-but-uncommitted proposals an evaluation may assume (EpiOut::add2)
 static const int BATCH_STAMP_SLOTS = 4 + 5 * 64;   // start, cleared, delta pass done, end; 5 per round
+static const int BATCH_STAMP_TOTAL = BATCH_STAMP_SLOTS + 64 * 128;   // + per round the EPI_STAMP block of CTA 1 (see tools/probe_batch.py)
 
 struct BatchIn {                      // by value
     int n_prop, n_atoms;
@@ -1229,7 +1226,9 @@ struct BatchRun {                     // device memory, carried from launch to l
 struct BatchDev {                     // by value: the batch's device buffers
     int *bsym[FRMC_MAX_GRIDS];        // [BATCH_MAX_PROPS][nsym*hs]  symmetrised delta per proposal
     int *bdelta[FRMC_MAX_GRIDS];      // [BATCH_MAX_PROPS][2*cells]  ordered delta per proposal
-    float *btotal[FRMC_MAX_MODELS];   // [BATCH_MAX_PROPS][n_out]
+    float *btotal[FRMC_MAX_MODELS];   // [BATCH_MAX_PROPS][n_out]   model totals per evaluation slot (two alternating sets of BATCH_MAX_GROUPS)
+    float *bterm[FRMC_MAX_MODELS];    // [BATCH_MAX_PROPS][n_out]   chi2 terms per evaluation slot of the models in defer_mask
+    unsigned int defer_mask;          // S(Q) models whose chi2 every CTA sums after the grid barrier (EpiOut::terms)
     float *total_committed[FRMC_MAX_MODELS];
     float *res;                       // [BATCH_MAX_PROPS][2*FRMC_MAX_MODELS]
     float *ptotal;                    // [BATCH_MAX_PROPS]
@@ -1253,16 +1252,70 @@ struct BatchShared {
     float4 fNew[FRMC_MAX_GROUP];               // periodically reduced coordinates, w = rounding margin
     float s_pt[BATCH_MAX_GROUPS], s_rand[BATCH_MAX_GROUPS];
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
-    int slot_k[BATCH_MAX_GROUPS];              // this round's plan: slot s evaluates proposal slot_k[s] ...
-    unsigned int slot_A[BATCH_MAX_GROUPS];     // ... on the committed state plus the proposals of this set
-    int slot_child[BATCH_MAX_GROUPS][2];       // slot of the next proposal if this one is rejected [0] / accepted [1], or -1
+    // the launch's speculation tree (built once): slot s evaluates proposal cur + depth[s] on the committed state plus
+    // the proposals {cur + d : bit d of pat[s]}; child = slot of the next proposal after a rejection [0] / an
+    // acceptance [1] (-1: none); anc = its ancestors' slots
+    int shape_depth[BATCH_MAX_GROUPS];
+    unsigned int shape_pat[BATCH_MAX_GROUPS], shape_anc[BATCH_MAX_GROUPS];
+    int shape_child[BATCH_MAX_GROUPS][2];
+    int shape_n;
+    int sched[FRMC_MAX_MODELS][4 * BATCH_DEFER_MAX_LEAVES];   // pairwise-summation schedules of the models in defer_mask
+    unsigned int symmask[BATCH_MAX_PROPS];     // rows of the symmetrised delta proposal j can touch (all ones when unknown)
+    float s_chi[BATCH_MAX_GROUPS][FRMC_MAX_MODELS];                // chi2 per slot and model of the round
+    float pw_scratch[EPI_THREADS / 32][BATCH_DEFER_MAX_LEAVES];    // leaf sums of the per-warp pairwise summation
     int path_slot[BATCH_MAX_GROUPS], path_dec[BATCH_MAX_GROUPS];   // the walk of the round: slot and decision per proposal
-    int s_nslots, s_last;
+    int s_last;
     unsigned int s_acc;
     int s_cur, s_ri, s_stopped;
     float s_total;
     unsigned long long s_bar;
 };
+
+// block_pairwise_sum for ONE warp over v[0..n) in GLOBAL memory (written by other CTAs before a grid barrier); the
+// schedule (leaf offsets | leaf lengths | combine dst | combine src) in shared memory.  Four leaves at a time, 8 lanes
+// per leaf = the 8 accumulators of numpy's unrolled leaf loop (leaves are at most 128 long: 16 elements per lane).
+// Every element a lane needs is loaded before the first addition (one L2 round trip per four leaves).
+// All 32 lanes call; result valid in lane 0.
+__device__ __forceinline__ float warp_pairwise_sum(const float *__restrict__ v, const int *sched, int nl, float *leaf_sum)
+{
+    const int lane = threadIdx.x & 31, group = lane >> 3, lane8 = lane & 7;
+    for (int base = 0; base < nl; base += 4) {
+        const int l = base + group;
+        const bool live = l < nl;
+        const int off = live ? sched[l] : 0, len = live ? sched[nl + l] : 0;
+        const bool big = len >= 8;
+        const int main_len = big ? len - (len % 8) : 0;
+        float x[16], rem[7];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x[u] = (8 * u < main_len) ? __ldcg(v + off + 8 * u + lane8) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 7; ++u) rem[u] = (live && lane8 == 0 && main_len + u < len) ? __ldcg(v + off + main_len + u) : 0.0f;
+        float r = x[0];
+#pragma unroll
+        for (int u = 1; u < 16; ++u) if (8 * u < main_len) r = __fadd_rn(r, x[u]);
+        __syncwarp();
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
+        float res = big ? r : 0.0f;
+        if (live && lane8 == 0) {
+#pragma unroll
+            for (int u = 0; u < 7; ++u) if (main_len + u < len) res = __fadd_rn(res, rem[u]);
+            leaf_sum[l] = res;
+        }
+    }
+    __syncwarp();
+    float out = 0.f;
+    if (lane == 0) {
+        for (int i = 0; i < nl - 1; ++i) {
+            const int d = sched[2 * nl + i], sr = sched[3 * nl + i];
+            leaf_sum[d] = __fadd_rn(leaf_sum[d], leaf_sum[sr]);
+        }
+        out = leaf_sum[0];
+    }
+    __syncwarp();
+    return out;
+}
 
 // one signed event of proposal `j` (the batch's delta_hit)
 __device__ __forceinline__ void batch_hit(float d2, int sign, int same, int slab, int sym, int j, const GridSet &gs, const BatchDev &bd,
@@ -1360,8 +1413,65 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         while (j + 1 < np && in.first[j + 1] <= t) ++j;
         bs.sProp[t] = j;
     }
-    if (tid < BATCH_MAX_PROPS) bs.near[tid] = 0u;
+    if (tid < BATCH_MAX_PROPS) { bs.near[tid] = 0u; bs.symmask[tid] = 0u; }
+    for (int mm = 0; mm < ms.n; ++mm)
+        if ((bd.defer_mask >> mm) & 1u)
+            for (int i = tid; i < 4 * ms.m[mm].pw_leaves; i += blockDim.x) bs.sched[mm][i] = ms.m[mm].pw_sched[i];
+    // ---- the speculation tree: the G most probable nodes below the root (depth 0, nothing assumed), a rejection
+    // weighted 1 - pa and an acceptance pa (the acceptance ratio of this call so far), at most BATCH_MAX_SPEC
+    // assumed acceptances per node.  Same integers, same tree in every CTA.
+    if (tid < 32) {
+        const unsigned FULL = 0xFFFFFFFFu;
+        const int lane = tid;
+        float pa = __fdiv_rn((float)(__ldcg(&bd.run->n_accepted) + 1), (float)(in.out_base + 2));
+        pa = fminf(fmaxf(pa, 0.02f), 0.98f);
+        int cd = (lane == 0) ? 0 : -1, cpar = -1, cacc = 0;
+        unsigned int cP = 0u, cAnc = 0u;
+        float cp = (lane == 0) ? 1.0f : 0.0f;
+        int n_sl = 0;
+        for (int sl = 0; sl < G; ++sl) {
+            const unsigned key = __float_as_uint(cp);                    // cp >= 0: ordered like the floats
+            const unsigned best = __reduce_max_sync(FULL, key);
+            if (best == 0u) break;
+            const int w = __ffs(__ballot_sync(FULL, key == best)) - 1;
+            const int d = __shfl_sync(FULL, cd, w), par = __shfl_sync(FULL, cpar, w), isacc = __shfl_sync(FULL, cacc, w);
+            const unsigned int P = __shfl_sync(FULL, cP, w), anc = __shfl_sync(FULL, cAnc, w);
+            const float pr = __shfl_sync(FULL, cp, w);
+            if (lane == 0) {
+                bs.shape_depth[sl] = d; bs.shape_pat[sl] = P; bs.shape_anc[sl] = anc;
+                bs.shape_child[sl][0] = -1; bs.shape_child[sl][1] = -1;
+                if (par >= 0) bs.shape_child[par][isacc] = sl;
+            }
+            const bool deeper = d + 1 < BATCH_MAX_PROPS;
+            const unsigned int P2 = P | (1u << d);
+            const bool acc_ok = deeper && __popc(P2) <= BATCH_MAX_SPEC;
+            const int e = __ffs(__ballot_sync(FULL, cp == 0.0f) & ~(1u << w)) - 1;   // a free lane: at most G+1 are live
+            if (lane == w) {
+                if (deeper) { cd = d + 1; cp = __fmul_rn(pr, __fsub_rn(1.0f, pa)); cpar = sl; cacc = 0; cAnc = anc | (1u << sl); }
+                else { cd = -1; cp = 0.0f; }
+            }
+            if (lane == e && acc_ok) { cd = d + 1; cP = P2; cp = __fmul_rn(pr, pa); cpar = sl; cacc = 1; cAnc = anc | (1u << sl); }
+            n_sl = sl + 1;
+            __syncwarp();
+        }
+        if (lane == 0) bs.shape_n = n_sl;
+    }
     __syncthreads();
+    {
+        // rows [el_t, *] of the symmetrised delta are the only ones proposal j can touch -- unless there are more than
+        // 32 rows or a grid reproduces the reference's edge-bin spill (the event lands in the next slab)
+        bool any = nEl * (nEl + 1) / 2 > 32;
+        for (int gi = 0; gi < gs.n; ++gi) any = any || gs.grid[gi].g.spill;
+        for (int t = tid; t < na; t += blockDim.x) {
+            unsigned int mk = 0xFFFFFFFFu;
+            if (!any) {
+                mk = 0u;
+                const int et = (int)(__float_as_uint(bs.sOld[t].w) & 0xFF);
+                for (int e2 = 0; e2 < nEl; ++e2) mk |= 1u << sym_index(et, e2, nEl);
+            }
+            atomicOr(&bs.symmask[bs.sProp[t]], mk);
+        }
+    }
     // which earlier proposals would change proposal j's delta if they were accepted (the pairs the commit corrects)
     for (int e = tid; e < na * na; e += blockDim.x) {
         const int t = e / na, u = e - t * na;
@@ -1508,75 +1618,58 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     unsigned int acc_mask = 0u;
     bool stopped = false;
     const int lane = tid & 31, wrp = tid >> 5;
+    bool warm = false;                                   // this CTA's epilogue tables are staged
     while (cur < np && !stopped) {
         ++rounds;
-        // ---- plan of the round: the G most probable nodes of the decision tree below (cur, nothing assumed).
-        // Node (k, A) = proposal k evaluated on the committed state + the proposals of A (assumed accepted); its
-        // children are (k+1, A) after a rejection and (k+1, A + {k}) after an acceptance, weighted with the
-        // acceptance ratio seen so far.  A node exists only if no proposal of A shares an atom with k (in.share)
-        // or pairs with one of k's atoms (bs.near): then k's delta needs no correction and the counts are exactly
-        // the sequential path's.  Every CTA builds the same plan from the same integers.
-        if (wrp == 0) {
-            const unsigned FULL = 0xFFFFFFFFu;
-            float pa = __fdiv_rn((float)(acc_before + n_acc + 1), (float)(in.out_base + cur + 2));
-            pa = fminf(fmaxf(pa, 0.02f), 0.98f);
-            int ck = (lane == 0) ? cur : -1, cpar = -1, cacc = 0;
-            unsigned int cA = 0u;
-            float cp = (lane == 0) ? 1.0f : 0.0f;
-            int ns = 0;
-            for (int sl = 0; sl < G; ++sl) {
-                const unsigned key = __float_as_uint(cp);                    // cp >= 0: ordered like the floats
-                const unsigned best = __reduce_max_sync(FULL, key);
-                if (best == 0u) break;
-                const int w = __ffs(__ballot_sync(FULL, key == best)) - 1;
-                const int k = __shfl_sync(FULL, ck, w), par = __shfl_sync(FULL, cpar, w), isacc = __shfl_sync(FULL, cacc, w);
-                const unsigned int A = __shfl_sync(FULL, cA, w);
-                const float pr = __shfl_sync(FULL, cp, w);
-                if (lane == 0) {
-                    bs.slot_k[sl] = k; bs.slot_A[sl] = A; bs.slot_child[sl][0] = -1; bs.slot_child[sl][1] = -1;
-                    if (par >= 0) bs.slot_child[par][isacc] = sl;
+        unsigned long long t_round = 0;
+        if (stamps && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_round));
+        // ---- the round's nodes: slot s is proposal cur + depth[s] on the committed state + the proposals of its
+        // pattern.  A node is evaluated only if, for it and all its ancestors, no assumed proposal shares an atom with
+        // the node's proposal (in.share) or pairs with one of its atoms (bs.near): then the proposal's delta needs no
+        // correction and the counts are exactly the sequential path's.  Every warp finds the same mask.
+        const int ns = bs.shape_n;
+        unsigned int valid;
+        {
+            bool self = false;
+            unsigned int anc = 0u;
+            if (lane < ns) {
+                const int k = cur + bs.shape_depth[lane];
+                if (k < np) {
+                    const unsigned int A = bs.shape_pat[lane] << cur;
+                    self = !((in.share[k] & (acc_mask | A)) || (bs.near[k] & A));
                 }
-                const int k1 = k + 1;
-                bool rej_ok = false, acc_ok = false;
-                unsigned int A2 = A | (1u << k);
-                if (k1 < np) {
-                    const unsigned int sh = in.share[k1], nr = bs.near[k1];
-                    rej_ok = !((sh & (acc_mask | A)) || (nr & A));
-                    acc_ok = (__popc(A2) <= BATCH_MAX_SPEC) && !((sh & (acc_mask | A2)) || (nr & A2));
-                }
-                const int e = __ffs(__ballot_sync(FULL, cp == 0.0f) & ~(1u << w)) - 1;   // a free lane: at most G+1 are live
-                if (lane == w) {
-                    if (rej_ok) { ck = k1; cp = __fmul_rn(pr, __fsub_rn(1.0f, pa)); cpar = sl; cacc = 0; }
-                    else { ck = -1; cp = 0.0f; }
-                }
-                if (lane == e && acc_ok) { ck = k1; cA = A2; cp = __fmul_rn(pr, pa); cpar = sl; cacc = 1; }
-                ns = sl + 1;
-                __syncwarp();
+                anc = bs.shape_anc[lane];
             }
-            if (lane == 0) bs.s_nslots = ns;
+            const unsigned int vs = __ballot_sync(0xFFFFFFFFu, self);
+            valid = __ballot_sync(0xFFFFFFFFu, self && ((vs & anc) == anc));
         }
-        __syncthreads();
-        const int ns = bs.s_nslots;
         const int par = rounds & 1;                          // slot buffers alternate: a CTA may still read round r-1's
-        if (epi && group < ns) {
-            const int k = bs.slot_k[group];
-            unsigned int A = bs.slot_A[group];
+        if (epi && ((valid >> group) & 1u)) {
+            const int k = cur + bs.shape_depth[group];
+            unsigned int A = bs.shape_pat[group] << cur;
             const int sb = par * BATCH_MAX_GROUPS + group;
             EpiOut eo;
             const GridDev &Gd = gs.grid[ms.m[m].grid];
             const long long per = (long long)Gd.nsym * Gd.g.hs;
             eo.add = bd.bsym[ms.m[m].grid] + (long long)k * per;
+            eo.amask = bs.symmask[k];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                eo.add2[x] = nullptr;
-                if (A) { eo.add2[x] = bd.bsym[ms.m[m].grid] + (long long)(__ffs(A) - 1) * per; A &= A - 1u; }
+                eo.add2[x] = nullptr; eo.amask2[x] = 0u;
+                if (A) {
+                    const int a = __ffs(A) - 1;
+                    eo.add2[x] = bd.bsym[ms.m[m].grid] + (long long)a * per; eo.amask2[x] = bs.symmask[a];
+                    A &= A - 1u;
+                }
             }
             eo.total = bd.btotal[m] + (long long)sb * ms.m[m].n_out;
             eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
-            eo.mticket = bd.tickets + BATCH_MAX_PROPS * FRMC_MAX_MODELS + sb;
-            eo.ptotal = bd.ptotal + sb;
-            eo.var2 = bd.var2;
-            epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + sb * FRMC_MAX_MODELS, nullptr, eo);
+            eo.terms = ((bd.defer_mask >> m) & 1u) ? bd.bterm[m] + (long long)sb * ms.m[m].n_out : nullptr;
+            eo.warm = warm ? 1 : 0;
+            long long *est = (stamps && blockIdx.x == 1 && rounds <= 64) ? stamps + BATCH_STAMP_SLOTS + (rounds - 1) * 128 : nullptr;
+            if (est && tid == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); est[120] = (long long)gt_; est[121] = (long long)t_round; }
+            epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + sb * FRMC_MAX_MODELS, est, eo);
+            warm = true;
         }
         BATCH_STAMP(4 + 5 * (rounds - 1) + 0);           // CTA 0's own epilogue done
         grid_arrive(bars);
@@ -1584,8 +1677,47 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         grid_wait(bars, bar_target);
         BATCH_STAMP(4 + 5 * (rounds - 1) + 1);           // every epilogue of the round done
         // decisions: every CTA walks the same numbers down the tree to the same conclusion
-        if (tid < ns) bs.s_pt[tid] = __ldcg(bd.ptotal + par * BATCH_MAX_GROUPS + tid);
-        if (tid >= 32 && tid < 32 + BATCH_MAX_GROUPS) bs.s_rand[tid - 32] = __ldcg(bd.rand + ri + tid - 32);
+        {
+            // chi2 of every slot: models in defer_mask left their terms (all slab CTAs wrote a slice) and one warp per
+            // (slot, model) sums them in numpy's pairwise order, straight from L2; the other models left their chi2
+            const int n_def = __popc(bd.defer_mask);
+            const int n_tasks = ns * n_def;
+            if (tid >= EPI_THREADS - 32 && lane < BATCH_MAX_GROUPS) bs.s_rand[lane] = __ldcg(bd.rand + ri + lane);
+            if (tid >= EPI_THREADS - 64 && tid < EPI_THREADS - 32) {
+                for (int e = lane; e < ns * ms.n; e += 32) {
+                    const int sl = e / ms.n, mm = e - sl * ms.n;
+                    if (!((bd.defer_mask >> mm) & 1u)) bs.s_chi[sl][mm] = __ldcg(bd.res + (par * BATCH_MAX_GROUPS + sl) * 2 * FRMC_MAX_MODELS + mm);
+                }
+            }
+            for (int task = wrp; task < n_tasks; task += EPI_THREADS / 32) {
+                const int sl = task / n_def;
+                int mm = 0;
+                for (int c = task - sl * n_def, x = 0; x < ms.n; ++x)
+                    if ((bd.defer_mask >> x) & 1u) { if (c == 0) { mm = x; break; } --c; }
+                if (!((valid >> sl) & 1u)) continue;                      // nobody evaluated this slot (warp-uniform)
+                const float chi = warp_pairwise_sum(bd.bterm[mm] + (long long)(par * BATCH_MAX_GROUPS + sl) * ms.m[mm].n_out, bs.sched[mm],
+                                                    ms.m[mm].pw_leaves, bs.pw_scratch[wrp]);
+                if (lane == 0) bs.s_chi[sl][mm] = chi;
+            }
+            __syncthreads();
+            // the engine's total standard error of a slot: np.sum of the float32 list [chi2_m / varianceSquared_m]
+            // (Engine.py:3024-3029; sequential for fewer than 8 terms, numpy's 8-accumulator tree for exactly 8)
+            if (tid < ns) {
+                float term[FRMC_MAX_MODELS];
+#pragma unroll
+                for (int i = 0; i < FRMC_MAX_MODELS; ++i) term[i] = (i < ms.n) ? __fdiv_rn(bs.s_chi[tid][i], bd.var2[i]) : 0.0f;
+                float tot;
+                if (ms.n == 8) {
+                    tot = __fadd_rn(__fadd_rn(__fadd_rn(term[0], term[1]), __fadd_rn(term[2], term[3])),
+                                    __fadd_rn(__fadd_rn(term[4], term[5]), __fadd_rn(term[6], term[7])));
+                } else {
+                    tot = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < FRMC_MAX_MODELS; ++i) if (i < ms.n) tot = __fadd_rn(tot, term[i]);
+                }
+                bs.s_pt[tid] = tot;
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             int sl = 0, k = cur, used = 0, last = -1, n_path = 0;
@@ -1597,9 +1729,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
                 bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
                 if (dec) { A |= 1u << k; tl = nt; last = sl; }
-                sl = bs.slot_child[sl][dec ? 1 : 0];
+                sl = bs.shape_child[sl][dec ? 1 : 0];
                 ++k;
-                if (sl < 0) break;
+                if (sl < 0 || !((valid >> sl) & 1u)) break;
             }
             // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
             const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
@@ -1612,8 +1744,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             for (int e = tid; e < n_path * per; e += blockDim.x) {
                 const int i = e / per, mm = e - i * per;
                 if (mm == ms.n) bd.out_dec[in.out_base + cur + i] = bs.path_dec[i];
-                else bd.out_chi2[(long long)(in.out_base + cur + i) * ms.n + mm] =
-                         __ldcg(bd.res + (par * BATCH_MAX_GROUPS + bs.path_slot[i]) * 2 * FRMC_MAX_MODELS + mm);
+                else bd.out_chi2[(long long)(in.out_base + cur + i) * ms.n + mm] = bs.s_chi[bs.path_slot[i]][mm];
             }
         }
         const unsigned int Aset = bs.s_acc;
@@ -1666,8 +1797,8 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 for (int x = 0; x < n_aj; ++x)
                     for (int t = in.first[acc_j[x]] + tid; t < in.first[acc_j[x] + 1]; t += blockDim.x) atoms[bs.sPos[t]] = bs.sNew[t];
                 if (tid < ms.n) {
-                    bd.run->cchi2[tid] = __ldcg(bd.res + lb * 2 * FRMC_MAX_MODELS + tid);
-                    bd.run->csf[tid] = __ldcg(bd.res + lb * 2 * FRMC_MAX_MODELS + FRMC_MAX_MODELS + tid);
+                    bd.run->cchi2[tid] = bs.s_chi[last][tid];
+                    bd.run->csf[tid] = ms.m[tid].scale;        // no refit schedule inside a batch
                 }
             }
             // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
@@ -1793,6 +1924,7 @@ struct frmc_store {
     // runs of proposals resolved on the device (batch_kernel)
     bool batch_ok = false;           // checked in sync_models: resident S(Q) slabs, no refit schedule, co-residency
     bool batch_ready = false;        // buffers below match the current grids and models
+    unsigned int batch_defer_mask = 0u;   // sync_models: models whose chi2 is summed after the grid barrier
     BatchDev bdev;
     std::vector<void *> batch_owned;
     unsigned long long *d_bbars = nullptr;
@@ -1992,6 +2124,14 @@ static int sync_models(frmc_store *s)
         if (m.adjust_freq > 0) s->batch_ok = false;
     }
     if (s->batch_ok) {
+        // S(Q) models without prior/window leave chi2 terms and every CTA sums them after the grid barrier
+        s->batch_defer_mask = 0u;
+        for (size_t mi = 0; mi < s->models.size(); ++mi) {
+            const ModelDev &d = s->models[mi].dev;
+            const bool is_sq = (d.kind == FRMC_KIND_SQ || d.kind == FRMC_KIND_RSQ);
+            if (!is_sq || d.prior || d.window || d.pw_leaves > BATCH_DEFER_MAX_LEAVES || getenv("FRMC_BATCH_NO_DEFER")) continue;
+            s->batch_defer_mask |= 1u << mi;
+        }
         int per_sm = 0;
 #define BATCH_ATTR(M) do { \
             if (cudaFuncSetAttribute(batch_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)) != cudaSuccess) s->batch_ok = false; \
@@ -2383,6 +2523,7 @@ static int batch_prepare(frmc_store *s)
     }
     for (size_t m = 0; m < s->models.size(); ++m) {
         if ((rc = alloc((void **)&bd.btotal[m], sizeof(float) * (size_t)BATCH_MAX_PROPS * s->models[m].dev.n_out))) return rc;
+        if ((rc = alloc((void **)&bd.bterm[m], sizeof(float) * (size_t)BATCH_MAX_PROPS * s->models[m].dev.n_out))) return rc;
         bd.total_committed[m] = s->models[m].total_committed;
     }
     if ((rc = alloc((void **)&bd.res, sizeof(float) * BATCH_MAX_PROPS * 2 * FRMC_MAX_MODELS))) return rc;
@@ -2398,6 +2539,7 @@ static int batch_prepare(frmc_store *s)
     if (!s->bev0) { FRMC_CUDA(cudaEventCreate(&s->bev0)); FRMC_CUDA(cudaEventCreate(&s->bev1)); }
     bd.n_groups = std::max(1, std::min(BATCH_MAX_GROUPS, s->ctx->sm_count / std::max(1, s->epi_map.n)));
     if (const char *e = getenv("FRMC_BATCH_GROUPS")) bd.n_groups = std::max(1, std::min(bd.n_groups, atoi(e)));
+    bd.defer_mask = s->batch_defer_mask;
     s->batch_ready = true;
     return FRMC_OK;
 }
@@ -2413,9 +2555,9 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in)
     int npad = (int)s->npad, nEl = s->nEl;
     unsigned long long *ovf = s->d_overflow;
     if (!s->d_bstamps && getenv("FRMC_BATCH_STAMPS")) {
-        FRMC_CUDA(cudaMalloc(&s->d_bstamps, sizeof(long long) * BATCH_STAMP_SLOTS));
+        FRMC_CUDA(cudaMalloc(&s->d_bstamps, sizeof(long long) * BATCH_STAMP_TOTAL));
     }
-    if (s->d_bstamps) FRMC_CUDA(cudaMemsetAsync(s->d_bstamps, 0, sizeof(long long) * BATCH_STAMP_SLOTS, s->stream));
+    if (s->d_bstamps) FRMC_CUDA(cudaMemsetAsync(s->d_bstamps, 0, sizeof(long long) * BATCH_STAMP_TOTAL, s->stream));
     // sub-block culling of the delta pass against the widest d^2 window of the grids (frmc_set_block_culling(0): off)
     GridParams gw;
     memset(&gw, 0, sizeof(gw));
@@ -3105,7 +3247,7 @@ int frmc_store_batch_stats(frmc_store *s, uint64_t *launches, uint64_t *rounds, 
 
 int frmc_store_batch_stamps(frmc_store *s, int64_t *out, int n)
 {
-    FRMC_REQUIRE(s && out && n >= 1 && n <= BATCH_STAMP_SLOTS, FRMC_EINVAL, "bad arguments");
+    FRMC_REQUIRE(s && out && n >= 1 && n <= BATCH_STAMP_TOTAL, FRMC_EINVAL, "bad arguments");
     FRMC_REQUIRE(s->d_bstamps, FRMC_ESTATE, "no batch timeline recorded (set FRMC_BATCH_STAMPS=1 before the first run)");
     FRMC_CUDA(cudaSetDevice(s->dev));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));

@@ -37,7 +37,7 @@ m = n - 200
 launches, rounds, props = store.batch_stats()
 print("%s: %d proposals, %d accepted, device %.2f us/eval, wall %.2f us/eval, %d launches, %d rounds (all runs)" % (
     which, m, int((out["decisions"] > 0).sum()), 1e3 * out["device_ms"] / m, 1e6 * wall / m, launches, rounds))
-st = np.zeros(4 + 5 * 64, np.int64)
+st = np.zeros(4 + 5 * 64 + 64 * 128, np.int64)
 L.check(store._lib.frmc_store_batch_stamps(store._handle, st.ctypes.data_as(L.c_i64p), st.shape[0]), "stamps")
 print("last launch: clear %.2f us, delta pass %.2f us, rounds+end %.2f us, total %.2f us" % (
     (st[1] - st[0]) / 1e3, (st[2] - st[1]) / 1e3, (st[3] - st[2]) / 1e3, (st[3] - st[0]) / 1e3))
@@ -57,4 +57,15 @@ print("rounds in last launch: %d (with commit: %d)" % (len(acc["round"]), len(ac
 for k, v in acc.items():
     if v:
         print("  %-15s mean %.2f us  min %.2f  max %.2f" % (k, np.mean(v) / 1e3, np.min(v) / 1e3, np.max(v) / 1e3))
+# CTA 1 (first S(Q) slab of group 0): where its evaluation spends the round
+sq = {"plan": [], "tables": [], "G(r)": [], "S(Q) rows": [], "fence+barrier": []}
+for r in range(len(acc["round"])):
+    e = st[4 + 5 * 64 + 128 * r: 4 + 5 * 64 + 128 * (r + 1)]
+    if e[120] == 0 or e[75] == 0:
+        continue
+    sq["plan"].append(e[120] - e[121]); sq["tables"].append(e[73] - e[120]); sq["G(r)"].append(e[74] - e[73])
+    sq["S(Q) rows"].append(e[75] - e[74]); sq["fence+barrier"].append(st[4 + 5 * r + 1] - e[75])
+for k, v in sq.items():
+    if v:
+        print("  S(Q) CTA %-14s mean %.2f us  min %.2f  max %.2f" % (k, np.mean(v) / 1e3, np.min(v) / 1e3, np.max(v) / 1e3))
 store.close()
