@@ -561,10 +561,12 @@ __device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem
 // Where a BATCH evaluation (batch_kernel: several proposals in flight) reads its counts and leaves its results:
 // the counts are the COMMITTED symmetrised totals plus the proposal's own symmetrised delta, the model total and
 // chi^2 go to per-proposal buffers, and nothing is published to the host (the kernel decides itself).
+static const int EPI_MAX_ADDS = 8;
 struct EpiOut {
-    const int *add;          // [nsym][hs] the proposal's symmetrised delta on this model's grid
-    const int *add2[3];      // deltas of earlier proposals this evaluation ASSUMES accepted (speculation), or null
-    unsigned int amask, amask2[3];   // bit s: row s of the delta can be non-zero (rows of untouched element pairs are not read)
+    const int *base;         // [nsym][hs] symmetrised totals the evaluation starts from (a fully visible copy)
+    const int *adds[EPI_MAX_ADDS];   // [nsym][hs] symmetrised deltas on this model's grid: the proposal's own, then those
+    unsigned int amask[EPI_MAX_ADDS];// of the proposals assumed accepted and of the acceptances not yet folded into base;
+    int n_adds;              // amask bit s: row s can be non-zero (rows of untouched element pairs are not read)
     float *total;            // [n_out]    model total of this evaluation
     float *res;              // [2*FRMC_MAX_MODELS] chi2 per model, then the scale factor each evaluation used
     float *terms;            // S(Q) models: [n_out] weighted squared residuals; when set the slab CTAs stop there and
@@ -623,8 +625,72 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
 
     // ---- 1. r-space function: EPI_BINS bins per thread per round, every load issued before any arithmetic
     {
-        const int *__restrict__ stot = BATCH ? gs.grid[M.grid].tot : gs.grid[M.grid].stot;
+        const int *__restrict__ stot = BATCH ? eo.base : gs.grid[M.grid].stot;
         constexpr int EPI_BINS = 2, PB = 16;
+        const bool defer = !is_sq && (M.refit || M.prior || M.window);   // scale, prior, window applied in stage 1b
+        // bin r from the sum over the pair terms (acc): /shellVolumes, prefactor, shape, scale
+        auto finish_bin = [&](int r, float accv, float svr, float prf, float shp) {
+            float a = __fdiv_rn(accv, svr);
+            float out;
+            if (M.kind == FRMC_KIND_PCF) {
+                out = a;
+                if (M.shape) out = __fsub_rn(out, shp);
+                if (!defer && M.scale != 1.0f) {
+                    float Gr = __fmul_rn(prf, __fsub_rn(out, 1.0f));
+                    Gr = __fmul_rn(Gr, M.scale);
+                    out = __fadd_rn(1.0f, __fdiv_rn(Gr, prf));
+                }
+            } else {
+                out = __fmul_rn(prf, __fsub_rn(a, 1.0f));
+                if (M.kind == FRMC_KIND_PDF) {
+                    if (M.shape) out = __fsub_rn(out, shp);
+                    if (!defer && M.scale != 1.0f) out = __fmul_rn(out, M.scale);
+                }
+            }
+            sG[r] = out;
+            if (slab == 0 && !defer) {
+                if (!BATCH) M.rfun[r] = out;
+                if (!is_sq) total[r] = out;
+            }
+        };
+        if (BATCH && (hs & 1) == 0) {
+            // batch, even histogram size: two consecutive bins per thread through 8-byte loads (half the load and
+            // address instructions of the scalar loop; rows start on 8-byte boundaries because hs is even)
+            for (int r0 = 2 * tid; r0 < hs; r0 += 2 * EPI_THREADS) {
+                float acc0 = 0.0f, acc1 = 0.0f;
+                const float2 svr = *reinterpret_cast<const float2 *>(M.sv + r0), prf = *reinterpret_cast<const float2 *>(M.pref + r0);
+                const float2 shp = M.shape ? *reinterpret_cast<const float2 *>(M.shape + r0) : make_float2(0.f, 0.f);
+                for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_pad); p0 += PB) {
+                    int2 c[PB];
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) c[u] = __ldcg(reinterpret_cast<const int2 *>(stot + s_psym[p0 + u] * hs + r0));
+                    for (int x = 0; x < eo.n_adds; ++x) {       // block-uniform
+                        const int *ap = eo.adds[x];
+                        const unsigned int mk = eo.amask[x];
+                        int2 e[PB];
+#pragma unroll
+                        for (int u = 0; u < PB; ++u)
+                            e[u] = ((mk >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(reinterpret_cast<const int2 *>(ap + s_psym[p0 + u] * hs + r0))
+                                                                        : make_int2(0, 0);
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) { c[u].x += e[u].x; c[u].y += e[u].y; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) {
+                        const float w = s_w[p0 + u], D = s_D[p0 + u], rD = s_rD[p0 + u];
+                        if (rD == rD) {                       // block-uniform: proven 3-op exact division
+                            acc0 = __fadd_rn(acc0, div_by_const(__fmul_rn(w, (float)c[u].x), D, rD));
+                            acc1 = __fadd_rn(acc1, div_by_const(__fmul_rn(w, (float)c[u].y), D, rD));
+                        } else {
+                            acc0 = __fadd_rn(acc0, __fdiv_rn(__fmul_rn(w, (float)c[u].x), D));
+                            acc1 = __fadd_rn(acc1, __fdiv_rn(__fmul_rn(w, (float)c[u].y), D));
+                        }
+                    }
+                }
+                finish_bin(r0, acc0, svr.x, prf.x, shp.x);
+                finish_bin(r0 + 1, acc1, svr.y, prf.y, shp.y);
+            }
+        } else
         for (int rb = tid; rb < hs; rb += EPI_BINS * EPI_THREADS) {
             float acc[EPI_BINS], svr[EPI_BINS], prf[EPI_BINS], shp[EPI_BINS];
 #pragma unroll
@@ -641,21 +707,15 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
 #pragma unroll
                     for (int u = 0; u < PB; ++u) c[j][u] = __ldcg(stot + (long long)s_psym[p0 + u] * hs + r);
                     if (BATCH) {
-                        int e[PB];
+                        for (int x = 0; x < eo.n_adds; ++x) {       // block-uniform
+                            const int *ap = eo.adds[x];
+                            const unsigned int mk = eo.amask[x];
+                            int e[PB];
 #pragma unroll
-                        for (int u = 0; u < PB; ++u)
-                            e[u] = ((eo.amask >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(eo.add + (long long)s_psym[p0 + u] * hs + r) : 0;
+                            for (int u = 0; u < PB; ++u)
+                                e[u] = ((mk >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(ap + (long long)s_psym[p0 + u] * hs + r) : 0;
 #pragma unroll
-                        for (int u = 0; u < PB; ++u) c[j][u] += e[u];
-#pragma unroll
-                        for (int x = 0; x < 3; ++x) {
-                            if (eo.add2[x]) {             // block-uniform
-#pragma unroll
-                                for (int u = 0; u < PB; ++u)
-                                    e[u] = ((eo.amask2[x] >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(eo.add2[x] + (long long)s_psym[p0 + u] * hs + r) : 0;
-#pragma unroll
-                                for (int u = 0; u < PB; ++u) c[j][u] += e[u];
-                            }
+                            for (int u = 0; u < PB; ++u) c[j][u] += e[u];
                         }
                     }
                 }
@@ -677,29 +737,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
             for (int j = 0; j < EPI_BINS; ++j) {
                 const int r = rb + j * EPI_THREADS;
                 if (r >= hs) continue;
-                float a = __fdiv_rn(acc[j], svr[j]);
-                float out;
-                const bool defer = !is_sq && (M.refit || M.prior || M.window);   // scale, prior, window applied in stage 1b
-                if (M.kind == FRMC_KIND_PCF) {
-                    out = a;
-                    if (M.shape) out = __fsub_rn(out, shp[j]);
-                    if (!defer && M.scale != 1.0f) {
-                        float Gr = __fmul_rn(prf[j], __fsub_rn(out, 1.0f));
-                        Gr = __fmul_rn(Gr, M.scale);
-                        out = __fadd_rn(1.0f, __fdiv_rn(Gr, prf[j]));
-                    }
-                } else {
-                    out = __fmul_rn(prf[j], __fsub_rn(a, 1.0f));
-                    if (M.kind == FRMC_KIND_PDF) {
-                        if (M.shape) out = __fsub_rn(out, shp[j]);
-                        if (!defer && M.scale != 1.0f) out = __fmul_rn(out, M.scale);
-                    }
-                }
-                sG[r] = out;
-                if (slab == 0 && !defer) {
-                    if (!BATCH) M.rfun[r] = out;
-                    if (!is_sq) total[r] = out;
-                }
+                finish_bin(r, acc[j], svr[j], prf[j], shp[j]);
             }
         }
     }
@@ -1651,16 +1689,14 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             EpiOut eo;
             const GridDev &Gd = gs.grid[ms.m[m].grid];
             const long long per = (long long)Gd.nsym * Gd.g.hs;
-            eo.add = bd.bsym[ms.m[m].grid] + (long long)k * per;
-            eo.amask = bs.symmask[k];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                eo.add2[x] = nullptr; eo.amask2[x] = 0u;
-                if (A) {
-                    const int a = __ffs(A) - 1;
-                    eo.add2[x] = bd.bsym[ms.m[m].grid] + (long long)a * per; eo.amask2[x] = bs.symmask[a];
-                    A &= A - 1u;
-                }
+            eo.base = Gd.tot;
+            eo.adds[0] = bd.bsym[ms.m[m].grid] + (long long)k * per;
+            eo.amask[0] = bs.symmask[k];
+            eo.n_adds = 1;
+            for (; A; A &= A - 1u) {
+                const int a = __ffs(A) - 1;
+                eo.adds[eo.n_adds] = bd.bsym[ms.m[m].grid] + (long long)a * per; eo.amask[eo.n_adds] = bs.symmask[a];
+                ++eo.n_adds;
             }
             eo.total = bd.btotal[m] + (long long)sb * ms.m[m].n_out;
             eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
