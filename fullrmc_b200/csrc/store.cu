@@ -1657,6 +1657,14 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     bool stopped = false;
     const int lane = tid & 31, wrp = tid >> 5;
     bool warm = false;                                   // this CTA's epilogue tables are staged
+    // Lazy commit of the symmetrised totals.  They exist twice (GridDev::tot / ::stot, equal between launches): buffer
+    // `vis` is complete and visible to every CTA; the acceptances of a round are folded into the OTHER buffer without
+    // a barrier, while the next round already evaluates on buffer vis + the deltas of those acceptances (pend).  The
+    // barrier that ends that round's evaluations makes the other buffer the visible one.  A barrier right after the
+    // commit is only needed when an accepted proposal pairs with an atom of an unresolved one (its delta is corrected).
+    int vis = 0;
+    unsigned int pend = 0u;
+    bool inflight = false, other_stale = false;
     while (cur < np && !stopped) {
         ++rounds;
         unsigned long long t_round = 0;
@@ -1689,11 +1697,11 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             EpiOut eo;
             const GridDev &Gd = gs.grid[ms.m[m].grid];
             const long long per = (long long)Gd.nsym * Gd.g.hs;
-            eo.base = Gd.tot;
+            eo.base = vis ? Gd.stot : Gd.tot;
             eo.adds[0] = bd.bsym[ms.m[m].grid] + (long long)k * per;
             eo.amask[0] = bs.symmask[k];
             eo.n_adds = 1;
-            for (; A; A &= A - 1u) {
+            for (A |= pend; A; A &= A - 1u) {                // assumed acceptances and those not yet in the visible buffer
                 const int a = __ffs(A) - 1;
                 eo.adds[eo.n_adds] = bd.bsym[ms.m[m].grid] + (long long)a * per; eo.amask[eo.n_adds] = bs.symmask[a];
                 ++eo.n_adds;
@@ -1712,6 +1720,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         bar_target += gridDim.x;
         grid_wait(bars, bar_target);
         BATCH_STAMP(4 + 5 * (rounds - 1) + 1);           // every epilogue of the round done
+        if (inflight) { vis ^= 1; pend = 0u; inflight = false; other_stale = true; }   // the last commit is visible now
         // decisions: every CTA walks the same numbers down the tree to the same conclusion
         {
             // chi2 of every slot: models in defer_mask left their terms (all slab CTAs wrote a slice) and one warp per
@@ -1794,6 +1803,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             n_acc += __popc(Aset);
             int acc_j[BATCH_MAX_SPEC + 1], n_aj = 0;
             for (unsigned int a = Aset; a; a &= a - 1u) acc_j[n_aj++] = __ffs(a) - 1;
+            const bool last_round = (cur >= np) || stopped;
+            // does an accepted proposal pair with an atom of an unresolved one?  (every warp finds the same answer)
+            const bool need_bar = __ballot_sync(0xFFFFFFFFu, lane >= cur && lane < np && (bs.near[lane] & Aset)) != 0u;
             const long long stride = (long long)gridDim.x * blockDim.x;
             const long long gt = (long long)blockIdx.x * blockDim.x + tid;
             const int lb = par * BATCH_MAX_GROUPS + last;    // the evaluation that saw all of them
@@ -1809,11 +1821,13 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                     const GridDev &Gd = gs.grid[gi];
                     const long long ns_ = (long long)Gd.nsym * Gd.g.hs;
                     if (c < ns_) {
-                        const int t0 = __ldcg(Gd.tot + c);
+                        int *bv = vis ? Gd.stot : Gd.tot, *bo = vis ? Gd.tot : Gd.stot;
+                        const int t0 = __ldcg(bv + c);
                         int v = 0;
 #pragma unroll
                         for (int x = 0; x <= BATCH_MAX_SPEC; ++x) if (x < n_aj) v += __ldcg(bd.bsym[gi] + (long long)acc_j[x] * ns_ + c);
-                        if (v) { Gd.tot[c] = t0 + v; Gd.stot[c] = t0 + v; }
+                        bo[c] = t0 + v;                                  // every cell: the other buffer may be one commit behind
+                        if (last_round && v) bv[c] = t0 + v;             // the launch ends with both buffers equal
                         done = true;
                     } else if ((c -= ns_) < 2 * Gd.cells) {
                         const unsigned long long c0 = __ldcg(Gd.counts + c);
@@ -1839,37 +1853,56 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             }
             // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
             // Proposals resolved in this round need none: their nodes had no such pair (bs.near).
-            const int later0 = in.first[cur];                // atoms are listed in proposal order
-            for (int x = 0; x < n_aj; ++x) {
-                const int a0 = in.first[acc_j[x]], a1 = in.first[acc_j[x] + 1];
-                const long long n_items = (long long)(na - later0) * (a1 - a0);
-                for (long long it = gt; it < n_items; it += stride) {
-                    const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
-                    const int j2 = bs.sProp[t];
-                    if (!((bs.near[j2] >> acc_j[x]) & 1u)) continue;         // no pair in range (the common case)
-                    const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
-                    const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
-                    const int same = (mt >> 8) == (mu >> 8);
-                    const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
-                    const int slab_ = et * nEl + eu;
-                    const int sym = sym_index(et, eu, nEl);
-                    const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
-                    const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
-                    const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
-                    const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
-                    unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
-                    if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
-                    if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                    if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
-                    if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                    if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+            if (need_bar) {
+                const int later0 = in.first[cur];                // atoms are listed in proposal order
+                for (int x = 0; x < n_aj; ++x) {
+                    const int a0 = in.first[acc_j[x]], a1 = in.first[acc_j[x] + 1];
+                    const long long n_items = (long long)(na - later0) * (a1 - a0);
+                    for (long long it = gt; it < n_items; it += stride) {
+                        const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
+                        const int j2 = bs.sProp[t];
+                        if (!((bs.near[j2] >> acc_j[x]) & 1u)) continue;         // no pair in range (the common case)
+                        const float4 ot = bs.sOld[t], nt = bs.sNew[t], ou = bs.sOld[u], nu = bs.sNew[u];
+                        const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
+                        const int same = (mt >> 8) == (mu >> 8);
+                        const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+                        const int slab_ = et * nEl + eu;
+                        const int sym = sym_index(et, eu, nEl);
+                        const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
+                        const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
+                        const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
+                        const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
+                        unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
+                        if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
+                        if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                        if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
+                        if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
+                        if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+                    }
                 }
             }
             BATCH_STAMP(4 + 5 * (rounds - 1) + 3);       // CTA 0's share of the commit done
-            grid_arrive(bars);
-            bar_target += gridDim.x;
-            grid_wait(bars, bar_target);
-            BATCH_STAMP(4 + 5 * (rounds - 1) + 4);       // commit visible to everyone
+            if (last_round) {
+                other_stale = false;                     // both buffers were written
+            } else if (need_bar) {
+                grid_arrive(bars);
+                bar_target += gridDim.x;
+                grid_wait(bars, bar_target);
+                vis ^= 1; other_stale = true;            // the commit and the corrections are visible to everyone
+            } else {
+                pend = Aset; inflight = true;            // folded into the other buffer, visible after the next barrier
+            }
+            BATCH_STAMP(4 + 5 * (rounds - 1) + 4);
+        }
+    }
+    if (other_stale) {
+        // the launch ended on a round without acceptance while the other buffer was one commit behind
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (int gi = 0; gi < gs.n; ++gi) {
+            const GridDev &Gd = gs.grid[gi];
+            const int *bv = vis ? Gd.stot : Gd.tot;
+            int *bo = vis ? Gd.tot : Gd.stot;
+            for (long long c = (long long)blockIdx.x * blockDim.x + tid; c < (long long)Gd.nsym * Gd.g.hs; c += stride) bo[c] = __ldcg(bv + c);
         }
     }
     BATCH_STAMP(3);
