@@ -165,6 +165,9 @@ def smooth_target(n, seed, center):
 
 
 # ----------------------------------------------------------------------------- per-move leg
+NO_PERSISTENT = False     # --no-persistent
+
+
 def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
     from fullrmc_b200 import _lib
     from fullrmc_b200.store import DeviceStore
@@ -215,12 +218,15 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
     # (1) one cooperative launch per proposal
     wall_launch, accepted_launch, launches_launch, box, chi_end = metropolis_run()
     # (2) the same sequence from the same start through the persistent kernel
-    store.set_coords(system.boxCoords, system.basis)
-    store.compute_data()
-    store.set_persistent(True)
-    wall, accepted, launches, box2, chi_end2 = metropolis_run()
-    started, served = store.persistent_stats()
-    store.set_persistent(False)
+    if NO_PERSISTENT:                                     # under ncu: a replayed kernel cannot follow the host's command stream
+        wall, accepted, launches, box2, chi_end2, started, served = wall_launch, accepted_launch, launches_launch, box, chi_end, 0, 0
+    else:
+        store.set_coords(system.boxCoords, system.basis)
+        store.compute_data()
+        store.set_persistent(True)
+        wall, accepted, launches, box2, chi_end2 = metropolis_run()
+        started, served = store.persistent_stats()
+        store.set_persistent(False)
     same_trajectory = bool(accepted == accepted_launch and chi_end == chi_end2 and np.array_equal(box, box2))
     # device-only time of the propose pipeline: the same CUDA graph launched back to back, CUDA events
     i = idx_all[:1]
@@ -725,7 +731,11 @@ def main():
     ap.add_argument("--no-permove", action="store_true")
     ap.add_argument("--no-brute", action="store_true", help="skip the culling-off leg of the full histogram")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-persistent", action="store_true", help="skip the persistent-kernel leg (profilers replay kernels; "
+                    "a resident kernel that follows the host's command stream cannot be replayed)")
     args = ap.parse_args()
+    global NO_PERSISTENT
+    NO_PERSISTENT = bool(args.no_persistent)
     if args.impl == "reference":
         run_reference(args)
     else:
