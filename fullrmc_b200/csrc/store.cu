@@ -1288,15 +1288,17 @@ struct BatchShared {
     int sProp[FRMC_MAX_GROUP];
     float4 fOld[FRMC_MAX_GROUP];               // the same positions as one-point boxes for blocks_far:
     float4 fNew[FRMC_MAX_GROUP];               // periodically reduced coordinates, w = rounding margin
-    float s_pt[BATCH_MAX_GROUPS], s_rand[BATCH_MAX_GROUPS];
+    float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
-    // the launch's speculation tree (built once): slot s evaluates proposal cur + depth[s] on the committed state plus
-    // the proposals {cur + d : bit d of pat[s]}; child = slot of the next proposal after a rejection [0] / an
-    // acceptance [1] (-1: none); anc = its ancestors' slots
-    int shape_depth[BATCH_MAX_GROUPS];
-    unsigned int shape_pat[BATCH_MAX_GROUPS], shape_anc[BATCH_MAX_GROUPS];
-    int shape_child[BATCH_MAX_GROUPS][2];
-    int shape_n;
+    // the round's plan (rebuilt after every walk by thread 0): slot s evaluates proposal slot_k[s] on the committed
+    // state plus the proposals of slot_A[s]; child = slot of the next proposal after a rejection [0] / an acceptance
+    // [1], or -1
+    int slot_k[BATCH_MAX_GROUPS];
+    unsigned int slot_A[BATCH_MAX_GROUPS];
+    int slot_child[BATCH_MAX_GROUPS][2];
+    int n_slots;
+    float est[BATCH_MAX_PROPS];                // predicted change of the total standard error by proposal j (has_est bit j)
+    unsigned int has_est;
     int sched[FRMC_MAX_MODELS][4 * BATCH_DEFER_MAX_LEAVES];   // pairwise-summation schedules of the models in defer_mask
     unsigned int symmask[BATCH_MAX_PROPS];     // rows of the symmetrised delta proposal j can touch (all ones when unknown)
     float s_chi[BATCH_MAX_GROUPS][FRMC_MAX_MODELS];                // chi2 per slot and model of the round
@@ -1455,45 +1457,6 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     for (int mm = 0; mm < ms.n; ++mm)
         if ((bd.defer_mask >> mm) & 1u)
             for (int i = tid; i < 4 * ms.m[mm].pw_leaves; i += blockDim.x) bs.sched[mm][i] = ms.m[mm].pw_sched[i];
-    // ---- the speculation tree: the G most probable nodes below the root (depth 0, nothing assumed), a rejection
-    // weighted 1 - pa and an acceptance pa (the acceptance ratio of this call so far), at most BATCH_MAX_SPEC
-    // assumed acceptances per node.  Same integers, same tree in every CTA.
-    if (tid < 32) {
-        const unsigned FULL = 0xFFFFFFFFu;
-        const int lane = tid;
-        float pa = __fdiv_rn((float)(__ldcg(&bd.run->n_accepted) + 1), (float)(in.out_base + 2));
-        pa = fminf(fmaxf(pa, 0.02f), 0.98f);
-        int cd = (lane == 0) ? 0 : -1, cpar = -1, cacc = 0;
-        unsigned int cP = 0u, cAnc = 0u;
-        float cp = (lane == 0) ? 1.0f : 0.0f;
-        int n_sl = 0;
-        for (int sl = 0; sl < G; ++sl) {
-            const unsigned key = __float_as_uint(cp);                    // cp >= 0: ordered like the floats
-            const unsigned best = __reduce_max_sync(FULL, key);
-            if (best == 0u) break;
-            const int w = __ffs(__ballot_sync(FULL, key == best)) - 1;
-            const int d = __shfl_sync(FULL, cd, w), par = __shfl_sync(FULL, cpar, w), isacc = __shfl_sync(FULL, cacc, w);
-            const unsigned int P = __shfl_sync(FULL, cP, w), anc = __shfl_sync(FULL, cAnc, w);
-            const float pr = __shfl_sync(FULL, cp, w);
-            if (lane == 0) {
-                bs.shape_depth[sl] = d; bs.shape_pat[sl] = P; bs.shape_anc[sl] = anc;
-                bs.shape_child[sl][0] = -1; bs.shape_child[sl][1] = -1;
-                if (par >= 0) bs.shape_child[par][isacc] = sl;
-            }
-            const bool deeper = d + 1 < BATCH_MAX_PROPS;
-            const unsigned int P2 = P | (1u << d);
-            const bool acc_ok = deeper && __popc(P2) <= BATCH_MAX_SPEC;
-            const int e = __ffs(__ballot_sync(FULL, cp == 0.0f) & ~(1u << w)) - 1;   // a free lane: at most G+1 are live
-            if (lane == w) {
-                if (deeper) { cd = d + 1; cp = __fmul_rn(pr, __fsub_rn(1.0f, pa)); cpar = sl; cacc = 0; cAnc = anc | (1u << sl); }
-                else { cd = -1; cp = 0.0f; }
-            }
-            if (lane == e && acc_ok) { cd = d + 1; cP = P2; cp = __fmul_rn(pr, pa); cpar = sl; cacc = 1; cAnc = anc | (1u << sl); }
-            n_sl = sl + 1;
-            __syncwarp();
-        }
-        if (lane == 0) bs.shape_n = n_sl;
-    }
     __syncthreads();
     {
         // rows [el_t, *] of the symmetrised delta are the only ones proposal j can touch -- unless there are more than
@@ -1665,34 +1628,69 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     int vis = 0;
     unsigned int pend = 0u;
     bool inflight = false, other_stale = false;
+    // ---- the plan of a round (thread 0).  Which G nodes are worth evaluating is a PREDICTION; whatever it is, a
+    // decision is only ever taken on a node whose assumed set equals the set the walk has accepted, so the outcome is
+    // exact.  Two proposals change the total standard error almost additively (the cross term is second order in
+    // 1/N), so the change a proposal made on one state (est) predicts its fate on the states that follow:
+    //   1. a chain along the predictions from proposal c on, the assumed set growing with every predicted acceptance
+    //      (at most BATCH_MAX_SPEC); a node needs that no assumed proposal shares an atom (in.share) or an in-range
+    //      pair (bs.near) with its proposal -- then the proposal's delta needs no correction;
+    //   2. the first proposal without a prediction on the chain's state, and the proposals behind it on the committed
+    //      state: they are the next rounds' predictions, and while nothing is assumed yet they extend the chain
+    //      (the "all rejected so far" chain of a run without predictions).
+    auto build_plan = [&](int c, unsigned int accm, int ri_off) {
+        int n = 0, k = c, used = 0, prev = -1, prev_dec = 0;
+        unsigned int A = 0u;
+        const unsigned int he = bs.has_est;
+        bool open = true;                                // the chain can still be extended by the next node
+        while (n < G && k < np && ((he >> k) & 1u)) {
+            if ((in.share[k] & (accm | A)) || (bs.near[k] & A)) { open = false; break; }
+            bs.slot_k[n] = k; bs.slot_A[n] = A; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
+            if (prev >= 0) bs.slot_child[prev][prev_dec] = n;
+            int dec = 1;
+            if (bs.est[k] > 0.0f) { const float u = bs.s_rand[ri_off + used]; ++used; dec = (u > bd.tol) ? 0 : 1; }
+            prev = n; prev_dec = dec; ++n;
+            if (dec) {
+                if (__popc(A) >= BATCH_MAX_SPEC) { open = false; ++k; break; }
+                A |= 1u << k;
+            }
+            ++k;
+        }
+        if (open && n < G && k < np && !((in.share[k] & (accm | A)) || (bs.near[k] & A))) {
+            // the first proposal without a prediction, on the chain's state
+            bs.slot_k[n] = k; bs.slot_A[n] = A; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
+            if (prev >= 0) bs.slot_child[prev][prev_dec] = n;
+            prev = n; ++n; ++k;
+            // behind it: on the committed state; linked as "all rejected" while nothing is assumed
+            for (; n < G && k < np; ++k) {
+                if (in.share[k] & accm) break;
+                if ((he >> k) & 1u) continue;            // already predicted
+                bs.slot_k[n] = k; bs.slot_A[n] = 0u; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
+                if (A == 0u && bs.slot_k[prev] == k - 1) { bs.slot_child[prev][0] = n; prev = n; }
+                ++n;
+            }
+        } else {
+            // the chain ended on a conflict or on the limit of assumed acceptances: predictions for what follows
+            for (; n < G && k < np; ++k) {
+                if (in.share[k] & accm) break;
+                if ((he >> k) & 1u) continue;
+                bs.slot_k[n] = k; bs.slot_A[n] = 0u; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
+                ++n;
+            }
+        }
+        bs.n_slots = n;
+    };
+    if (tid == 0) { bs.has_est = 0u; build_plan(0, 0u, 0); }
+    __syncthreads();
     while (cur < np && !stopped) {
         ++rounds;
         unsigned long long t_round = 0;
         if (stamps && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_round));
-        // ---- the round's nodes: slot s is proposal cur + depth[s] on the committed state + the proposals of its
-        // pattern.  A node is evaluated only if, for it and all its ancestors, no assumed proposal shares an atom with
-        // the node's proposal (in.share) or pairs with one of its atoms (bs.near): then the proposal's delta needs no
-        // correction and the counts are exactly the sequential path's.  Every warp finds the same mask.
-        const int ns = bs.shape_n;
-        unsigned int valid;
-        {
-            bool self = false;
-            unsigned int anc = 0u;
-            if (lane < ns) {
-                const int k = cur + bs.shape_depth[lane];
-                if (k < np) {
-                    const unsigned int A = bs.shape_pat[lane] << cur;
-                    self = !((in.share[k] & (acc_mask | A)) || (bs.near[k] & A));
-                }
-                anc = bs.shape_anc[lane];
-            }
-            const unsigned int vs = __ballot_sync(0xFFFFFFFFu, self);
-            valid = __ballot_sync(0xFFFFFFFFu, self && ((vs & anc) == anc));
-        }
+        const int ns = bs.n_slots;
         const int par = rounds & 1;                          // slot buffers alternate: a CTA may still read round r-1's
-        if (epi && ((valid >> group) & 1u)) {
-            const int k = cur + bs.shape_depth[group];
-            unsigned int A = bs.shape_pat[group] << cur;
+        if (epi && group < ns) {
+            const int k = bs.slot_k[group];
+            unsigned int A = bs.slot_A[group];
             const int sb = par * BATCH_MAX_GROUPS + group;
             EpiOut eo;
             const GridDev &Gd = gs.grid[ms.m[m].grid];
@@ -1727,7 +1725,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             // (slot, model) sums them in numpy's pairwise order, straight from L2; the other models left their chi2
             const int n_def = __popc(bd.defer_mask);
             const int n_tasks = ns * n_def;
-            if (tid >= EPI_THREADS - 32 && lane < BATCH_MAX_GROUPS) bs.s_rand[lane] = __ldcg(bd.rand + ri + lane);
+            if (tid >= EPI_THREADS - 32) bs.s_rand[lane] = __ldcg(bd.rand + ri + lane);
             if (tid >= EPI_THREADS - 64 && tid < EPI_THREADS - 32) {
                 for (int e = lane; e < ns * ms.n; e += 32) {
                     const int sl = e / ms.n, mm = e - sl * ms.n;
@@ -1739,7 +1737,6 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 int mm = 0;
                 for (int c = task - sl * n_def, x = 0; x < ms.n; ++x)
                     if ((bd.defer_mask >> x) & 1u) { if (c == 0) { mm = x; break; } --c; }
-                if (!((valid >> sl) & 1u)) continue;                      // nobody evaluated this slot (warp-uniform)
                 const float chi = warp_pairwise_sum(bd.bterm[mm] + (long long)(par * BATCH_MAX_GROUPS + sl) * ms.m[mm].n_out, bs.sched[mm],
                                                     ms.m[mm].pw_leaves, bs.pw_scratch[wrp]);
                 if (lane == 0) bs.s_chi[sl][mm] = chi;
@@ -1761,6 +1758,8 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                     for (int i = 0; i < FRMC_MAX_MODELS; ++i) if (i < ms.n) tot = __fadd_rn(tot, term[i]);
                 }
                 bs.s_pt[tid] = tot;
+                // a node on the committed state predicts its proposal's fate in the rounds to come
+                if (bs.slot_A[tid] == 0u) { bs.est[bs.slot_k[tid]] = __fsub_rn(tot, total); atomicOr(&bs.has_est, 1u << bs.slot_k[tid]); }
             }
         }
         __syncthreads();
@@ -1774,13 +1773,21 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
                 bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
                 if (dec) { A |= 1u << k; tl = nt; last = sl; }
-                sl = bs.shape_child[sl][dec ? 1 : 0];
+                sl = bs.slot_child[sl][dec ? 1 : 0];
                 ++k;
-                if (sl < 0 || !((valid >> sl) & 1u)) break;
+                if (sl < 0) break;
             }
             // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
             const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
             bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
+            if (k < np && !stop) {
+                // the deltas of unresolved proposals next to an accepted one are about to be corrected: their
+                // predictions go; then the next round's plan
+                unsigned int he = bs.has_est;
+                for (int j2 = k; j2 < np; ++j2) if (bs.near[j2] & A) he &= ~(1u << j2);
+                bs.has_est = he;
+                build_plan(k, acc_mask | A, used);
+            }
         }
         __syncthreads();
         if (blockIdx.x == 0) {
@@ -3213,10 +3220,10 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], plo[c]); s->hi[c] = std::max(s->hi[c], phi[c]); }
     const int mode = current_mode(s, nullptr, nullptr);
     // call-wide device arrays
-    if (s->brand_cap < (size_t)n + BATCH_MAX_GROUPS) {
+    if (s->brand_cap < (size_t)n + 2 * BATCH_MAX_GROUPS) {
         cudaFree(s->d_brand); s->d_brand = nullptr; s->brand_cap = 0;
-        FRMC_CUDA(cudaMalloc(&s->d_brand, sizeof(float) * ((size_t)n + BATCH_MAX_GROUPS)));
-        s->brand_cap = (size_t)n + BATCH_MAX_GROUPS;
+        FRMC_CUDA(cudaMalloc(&s->d_brand, sizeof(float) * ((size_t)n + 2 * BATCH_MAX_GROUPS)));
+        s->brand_cap = (size_t)n + 2 * BATCH_MAX_GROUPS;
     }
     if (s->bout_cap < (size_t)n) {
         cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec); s->d_bout_chi2 = nullptr; s->d_bout_dec = nullptr; s->bout_cap = 0;
@@ -3224,7 +3231,7 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
         FRMC_CUDA(cudaMalloc(&s->d_bout_dec, sizeof(int) * (size_t)n));
         s->bout_cap = (size_t)n;
     }
-    FRMC_CUDA(cudaMemsetAsync(s->d_brand, 0, sizeof(float) * ((size_t)n + BATCH_MAX_GROUPS), s->stream));
+    FRMC_CUDA(cudaMemsetAsync(s->d_brand, 0, sizeof(float) * ((size_t)n + 2 * BATCH_MAX_GROUPS), s->stream));
     FRMC_CUDA(cudaMemcpyAsync(s->d_brand, rand, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
     BatchDev &bd = s->bdev;
     bd.rand = s->d_brand; bd.out_chi2 = s->d_bout_chi2; bd.out_dec = s->d_bout_dec;
