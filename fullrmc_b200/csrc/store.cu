@@ -1638,49 +1638,79 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
     //   2. the first proposal without a prediction on the chain's state, and the proposals behind it on the committed
     //      state: they are the next rounds' predictions, and while nothing is assumed yet they extend the chain
     //      (the "all rejected so far" chain of a run without predictions).
+    // Built by warp 0, lane j = proposal j (a launch has at most 32): everything is a vote or a prefix count.
     auto build_plan = [&](int c, unsigned int accm, int ri_off) {
-        int n = 0, k = c, used = 0, prev = -1, prev_dec = 0;
-        unsigned int A = 0u;
+        const unsigned int FULL = 0xFFFFFFFFu;
+        const int j = lane;
+        const unsigned int below = (1u << j) - 1u, from_c = ~((1u << c) - 1u);
         const unsigned int he = bs.has_est;
-        bool open = true;                                // the chain can still be extended by the next node
-        while (n < G && k < np && ((he >> k) & 1u)) {
-            if ((in.share[k] & (accm | A)) || (bs.near[k] & A)) { open = false; break; }
-            bs.slot_k[n] = k; bs.slot_A[n] = A; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
-            if (prev >= 0) bs.slot_child[prev][prev_dec] = n;
-            int dec = 1;
-            if (bs.est[k] > 0.0f) { const float u = bs.s_rand[ri_off + used]; ++used; dec = (u > bd.tol) ? 0 : 1; }
-            prev = n; prev_dec = dec; ++n;
-            if (dec) {
-                if (__popc(A) >= BATCH_MAX_SPEC) { open = false; ++k; break; }
-                A |= 1u << k;
-            }
-            ++k;
+        const bool in_rng = j >= c && j < np;
+        const bool has = in_rng && ((he >> j) & 1u);
+        const unsigned int has_m = __ballot_sync(FULL, has), rng_m = __ballot_sync(FULL, in_rng);
+        const unsigned int noest = rng_m & ~has_m;
+        const int f = noest ? __ffs(noest) - 1 : np;                 // first proposal without a prediction
+        const bool lead = in_rng && j < f;                           // the leading run of predicted proposals
+        const bool worse = lead && bs.est[j] > 0.0f;
+        const unsigned int worse_m = __ballot_sync(FULL, worse);
+        int dec = 1;
+        if (worse) { const float u = bs.s_rand[ri_off + __popc(worse_m & below)]; dec = (u > bd.tol) ? 0 : 1; }
+        const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
+        const unsigned int A_j = acc_pred & below & from_c;         // predicted acceptances in front of j
+        const unsigned int sh_j = in_rng ? in.share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;
+        const bool fits = !((sh_j & (accm | A_j)) || (nr_j & A_j)) && __popc(A_j) <= BATCH_MAX_SPEC;
+        const unsigned int bad = __ballot_sync(FULL, lead && !fits);
+        int chain_end = bad ? __ffs(bad) - 1 : f;
+        if (chain_end - c > G) chain_end = c + G;
+        const int L = chain_end - c;
+        // 1. the chain along the predictions
+        if (in_rng && j < chain_end) {
+            const int sl = j - c;
+            bs.slot_k[sl] = j; bs.slot_A[sl] = A_j;
+            bs.slot_child[sl][dec ^ 1] = -1;
+            bs.slot_child[sl][dec] = (j + 1 < chain_end) ? sl + 1 : -1;
         }
-        if (open && n < G && k < np && !((in.share[k] & (accm | A)) || (bs.near[k] & A))) {
-            // the first proposal without a prediction, on the chain's state
-            bs.slot_k[n] = k; bs.slot_A[n] = A; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
-            if (prev >= 0) bs.slot_child[prev][prev_dec] = n;
-            prev = n; ++n; ++k;
-            // behind it: on the committed state; linked as "all rejected" while nothing is assumed
-            for (; n < G && k < np; ++k) {
-                if (in.share[k] & accm) break;
-                if ((he >> k) & 1u) continue;            // already predicted
-                bs.slot_k[n] = k; bs.slot_A[n] = 0u; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
-                if (A == 0u && bs.slot_k[prev] == k - 1) { bs.slot_child[prev][0] = n; prev = n; }
-                ++n;
+        __syncwarp();
+        int n = L;
+        // 2. the first proposal without a prediction, on the chain's state
+        const unsigned int A_f = acc_pred & from_c & ((f < 32) ? ((1u << f) - 1u) : FULL);
+        const unsigned int sh_f = __shfl_sync(FULL, sh_j, f & 31), nr_f = __shfl_sync(FULL, nr_j, f & 31);
+        const bool open = (chain_end == f) && (f < np) && (L < G) &&
+                          !((sh_f & (accm | A_f)) || (nr_f & A_f)) && __popc(A_f) <= BATCH_MAX_SPEC;
+        const int dec_last = __shfl_sync(FULL, dec, (f - 1) & 31);   // predicted decision of the chain's last proposal
+        int est_from = chain_end;
+        if (open) {
+            if (j == 0) {
+                bs.slot_k[n] = f; bs.slot_A[n] = A_f; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
+                if (L > 0) bs.slot_child[n - 1][dec_last] = n;
             }
-        } else {
-            // the chain ended on a conflict or on the limit of assumed acceptances: predictions for what follows
-            for (; n < G && k < np; ++k) {
-                if (in.share[k] & accm) break;
-                if ((he >> k) & 1u) continue;
-                bs.slot_k[n] = k; bs.slot_A[n] = 0u; bs.slot_child[n][0] = -1; bs.slot_child[n][1] = -1;
-                ++n;
-            }
+            ++n;
+            est_from = f + 1;
         }
-        bs.n_slots = n;
+        // 3. behind it, on the committed state: the next rounds' predictions.  While nothing is assumed they also
+        //    extend the chain ("all rejected so far").
+        const unsigned int conflict = __ballot_sync(FULL, in_rng && j >= est_from && (sh_j & accm));
+        const int stop_at = conflict ? __ffs(conflict) - 1 : np;
+        const bool cand = in_rng && j >= est_from && j < stop_at && !has;
+        const unsigned int cand_m = __ballot_sync(FULL, cand);
+        const int sl = n + __popc(cand_m & below);
+        __syncwarp();
+        if (cand && sl < G) {
+            bs.slot_k[sl] = j; bs.slot_A[sl] = 0u; bs.slot_child[sl][0] = -1; bs.slot_child[sl][1] = -1;
+        }
+        __syncwarp();
+        if (open && A_f == 0u) {
+            // proposals f+1, f+2, ... as long as they are consecutive candidates: rejection children of one another
+            const unsigned int after_f = (f + 1 < 32) ? ~((1u << (f + 1)) - 1u) : 0u;
+            const unsigned int gap = ~cand_m & after_f;
+            const int run_end = gap ? __ffs(gap) - 1 : 32;             // exclusive
+            if (cand && j < run_end && sl < G) bs.slot_child[sl - 1][0] = sl;
+        }
+        if (j == 0) bs.n_slots = min(G, n + __popc(cand_m));
+        __syncwarp();
     };
-    if (tid == 0) { bs.has_est = 0u; build_plan(0, 0u, 0); }
+    if (tid == 0) bs.has_est = 0u;
+    __syncthreads();
+    if (wrp == 0) build_plan(0, 0u, 0);
     __syncthreads();
     while (cur < np && !stopped) {
         ++rounds;
@@ -1763,30 +1793,36 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int sl = 0, k = cur, used = 0, last = -1, n_path = 0;
-            unsigned int A = 0u;
-            float tl = total;
-            for (;;) {
-                const float nt = bs.s_pt[sl];
-                int dec = 1;
-                if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
-                bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
-                if (dec) { A |= 1u << k; tl = nt; last = sl; }
-                sl = bs.slot_child[sl][dec ? 1 : 0];
-                ++k;
-                if (sl < 0) break;
+        if (wrp == 0) {
+            if (lane == 0) {
+                int sl = 0, k = cur, used = 0, last = -1, n_path = 0;
+                unsigned int A = 0u;
+                float tl = total;
+                for (;;) {
+                    const float nt = bs.s_pt[sl];
+                    int dec = 1;
+                    if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
+                    bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
+                    if (dec) { A |= 1u << k; tl = nt; last = sl; }
+                    sl = bs.slot_child[sl][dec ? 1 : 0];
+                    ++k;
+                    // a decision is only taken on a node that is exactly the walk's state (whatever the plan predicted)
+                    if (sl < 0 || bs.slot_k[sl] != k || bs.slot_A[sl] != A) break;
+                }
+                // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
+                const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
+                bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
             }
-            // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
-            const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
-            bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
-            if (k < np && !stop) {
+            __syncwarp();
+            const int k = bs.s_cur;
+            const unsigned int A = bs.s_acc;
+            if (k < np && !bs.s_stopped) {
                 // the deltas of unresolved proposals next to an accepted one are about to be corrected: their
                 // predictions go; then the next round's plan
-                unsigned int he = bs.has_est;
-                for (int j2 = k; j2 < np; ++j2) if (bs.near[j2] & A) he &= ~(1u << j2);
-                bs.has_est = he;
-                build_plan(k, acc_mask | A, used);
+                const unsigned int gone = __ballot_sync(0xFFFFFFFFu, lane >= k && lane < np && (bs.near[lane] & A));
+                if (lane == 0) bs.has_est &= ~gone;
+                __syncwarp();
+                build_plan(k, acc_mask | A, bs.s_ri - ri);
             }
         }
         __syncthreads();
