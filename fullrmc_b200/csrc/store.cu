@@ -1278,6 +1278,7 @@ struct BatchDev {                     // by value: the batch's device buffers
     int *out_dec;                     // call-wide [n]: 0 rejected, 1 accepted, 2 accepted within the tolerance
     float var2[FRMC_MAX_MODELS];
     float tol;
+    float box_eps;                    // rounding margin of a sub-block box: 1e-6 (1 + largest |coordinate| of the store and the proposals)
     int n_groups;                     // G
 };
 
@@ -1286,8 +1287,8 @@ struct BatchShared {
     float4 sNew[FRMC_MAX_GROUP];
     int sPos[FRMC_MAX_GROUP];
     int sProp[FRMC_MAX_GROUP];
-    float4 fOld[FRMC_MAX_GROUP];               // the same positions as one-point boxes for blocks_far:
-    float4 fNew[FRMC_MAX_GROUP];               // periodically reduced coordinates, w = rounding margin
+    float4 fOld[FRMC_MAX_GROUP];               // low / high corner of the box spanned by a moved atom's old and new position
+    float4 fNew[FRMC_MAX_GROUP];               // (blocks_far's conventions: periodically reduced coordinates, lo.w = rounding margin)
     float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
     // the round's plan (rebuilt after every walk by thread 0): slot s evaluates proposal slot_k[s] on the committed
@@ -1384,6 +1385,17 @@ __device__ __forceinline__ void batch_hit(float d2, int sign, int same, int slab
     }
 }
 
+// order-preserving map float -> unsigned (and back): min / max of floats through integer REDUX
+__device__ __forceinline__ unsigned int float_order(float f)
+{
+    const unsigned int b = __float_as_uint(f);
+    return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float order_float(unsigned int k)
+{
+    return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
 // a position as a one-point box for blocks_far (block_bbox_kernel's conventions: fractional part under PBC,
 // w = margin for the rounding of fl(xi - xj) on the raw coordinates)
 __device__ __forceinline__ float4 point_box(float x, float y, float z, int pbc)
@@ -1447,8 +1459,11 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         bs.sOld[t] = o;
         bs.sNew[t] = make_float4(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], o.w);
         bs.sPos[t] = p;
-        bs.fOld[t] = point_box(o.x, o.y, o.z, cp.pbc);
-        bs.fNew[t] = point_box(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], cp.pbc);
+        {
+            const float4 fo = point_box(o.x, o.y, o.z, cp.pbc), fn = point_box(in.moved[3 * t], in.moved[3 * t + 1], in.moved[3 * t + 2], cp.pbc);
+            bs.fOld[t] = make_float4(fminf(fo.x, fn.x), fminf(fo.y, fn.y), fminf(fo.z, fn.z), fmaxf(fo.w, fn.w));
+            bs.fNew[t] = make_float4(fmaxf(fo.x, fn.x), fmaxf(fo.y, fn.y), fmaxf(fo.z, fn.z), 0.f);
+        }
         int j = 0;
         while (j + 1 < np && in.first[j + 1] <= t) ++j;
         bs.sProp[t] = j;
@@ -1520,36 +1535,25 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 // from below, common.cuh)
                 unsigned long long near_mask;
                 if (cp.enabled) {
+                    // min / max over the warp as one REDUX each, on the order-preserving integer image of the floats
                     const float v[3] = {a[u].x, a[u].y, a[u].z};
-                    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, amax = 0.f;
-                    if (mj != PAD_META && isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2])) {
+                    const bool fin = mj != PAD_META && isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
+                    float lo[3], hi[3];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            amax = fmaxf(amax, fabsf(v[c]));
-                            const float f = cp.pbc ? (v[c] - floorf(v[c])) : v[c];
-                            lo[c] = f; hi[c] = f;
-                        }
+                    for (int c = 0; c < 3; ++c) {
+                        const float f = cp.pbc ? (v[c] - floorf(v[c])) : v[c];
+                        const unsigned int kmin = __reduce_min_sync(0xffffffffu, fin ? float_order(f) : 0xFFFFFFFFu);
+                        const unsigned int kmax = __reduce_max_sync(0xffffffffu, fin ? float_order(f) : 0u);
+                        lo[c] = order_float(kmin); hi[c] = order_float(kmax);
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
-                            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
-                        }
-                        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-                    }
-                    const float4 loJ = make_float4(lo[0], lo[1], lo[2], 1e-6f * (1.0f + amax));
+                    // (w of the low corner: the rounding margin of fl(xi - xj), here from the store-wide coordinate bound)
+                    const float4 loJ = make_float4(lo[0], lo[1], lo[2], bd.box_eps);
                     const float4 hiJ = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? 0.f : 1.f);
                     near_mask = 0ull;
                     for (int t0 = 0; t0 < na; t0 += 32) {
                         const int t = t0 + (tid & 31);
-                        bool reach = false;
-                        if (t < na) {
-                            const float4 fo = bs.fOld[t], fn = bs.fNew[t];
-                            reach = !blocks_far(fo, make_float4(fo.x, fo.y, fo.z, 0.f), loJ, hiJ, cp) ||
-                                    !blocks_far(fn, make_float4(fn.x, fn.y, fn.z, 0.f), loJ, hiJ, cp);
-                        }
+                        // the moved atom's own box spans its old and its new position (one test for both)
+                        const bool reach = (t < na) && !blocks_far(bs.fOld[t], bs.fNew[t], loJ, hiJ, cp);
                         near_mask |= (unsigned long long)__ballot_sync(0xffffffffu, reach) << t0;
                     }
                 } else {
@@ -2671,6 +2675,11 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in)
     }
     if (s->d_bstamps) FRMC_CUDA(cudaMemsetAsync(s->d_bstamps, 0, sizeof(long long) * BATCH_STAMP_TOTAL, s->stream));
     // sub-block culling of the delta pass against the widest d^2 window of the grids (frmc_set_block_culling(0): off)
+    {
+        float amax = 0.f;
+        for (int c = 0; c < 3; ++c) amax = std::max(amax, std::max(fabsf(s->lo[c]), fabsf(s->hi[c])));
+        s->bdev.box_eps = 1e-6f * (1.0f + amax);
+    }
     GridParams gw;
     memset(&gw, 0, sizeof(gw));
     gw.t2max = gs.t2hi;
