@@ -1298,6 +1298,8 @@ struct BatchShared {
     unsigned int slot_A[BATCH_MAX_GROUPS];
     int slot_child[BATCH_MAX_GROUPS][2];
     int n_slots;
+    int path_len;                              // slots 0 .. path_len-1 are linked one after the other ...
+    unsigned int path_exp;                     // ... by these expected decisions (bit s: slot s accepted)
     float est[BATCH_MAX_PROPS];                // predicted change of the total standard error by proposal j (has_est bit j)
     unsigned int has_est;
     int sched[FRMC_MAX_MODELS][4 * BATCH_DEFER_MAX_LEAVES];   // pairwise-summation schedules of the models in defer_mask
@@ -1709,7 +1711,21 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             const int run_end = gap ? __ffs(gap) - 1 : 32;             // exclusive
             if (cand && j < run_end && sl < G) bs.slot_child[sl - 1][0] = sl;
         }
-        if (j == 0) bs.n_slots = min(G, n + __popc(cand_m));
+        if (j == 0) {
+            bs.n_slots = min(G, n + __popc(cand_m));
+            int P = L;
+            if (open) {
+                P = L + 1;
+                if (A_f == 0u) {
+                    const unsigned int after_f = (f + 1 < 32) ? ~((1u << (f + 1)) - 1u) : 0u;
+                    const unsigned int gap = ~cand_m & after_f;
+                    const unsigned int run = cand_m & after_f & (gap ? ((1u << (__ffs(gap) - 1)) - 1u) : 0xFFFFFFFFu);
+                    P += min(__popc(run), G - P);
+                }
+            }
+            bs.path_len = P;
+            bs.path_exp = (L > 0) ? ((acc_pred >> c) & ((L < 32) ? ((1u << L) - 1u) : 0xFFFFFFFFu)) : 0u;
+        }
         __syncwarp();
     };
     if (tid == 0) bs.has_est = 0u;
@@ -1798,24 +1814,43 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         }
         __syncthreads();
         if (wrp == 0) {
-            if (lane == 0) {
-                int sl = 0, k = cur, used = 0, last = -1, n_path = 0;
-                unsigned int A = 0u;
-                float tl = total;
-                for (;;) {
-                    const float nt = bs.s_pt[sl];
-                    int dec = 1;
-                    if (nt > tl) { const float u = bs.s_rand[used++]; dec = (u > bd.tol) ? 0 : 2; }
-                    bs.path_slot[n_path] = sl; bs.path_dec[n_path] = dec; ++n_path;
-                    if (dec) { A |= 1u << k; tl = nt; last = sl; }
-                    sl = bs.slot_child[sl][dec ? 1 : 0];
-                    ++k;
-                    // a decision is only taken on a node that is exactly the walk's state (whatever the plan predicted)
-                    if (sl < 0 || bs.slot_k[sl] != k || bs.slot_A[sl] != A) break;
+            {
+                // lane s = slot s of the linked path.  Each lane decides its proposal as if every slot in front of it
+                // had gone the expected way; the walk ends at the first slot that did not (its own decision stands: its
+                // node is still the true state).  A slot that is not exactly the expected state cuts the path.
+                const unsigned int FULL = 0xFFFFFFFFu, below = (1u << lane) - 1u;
+                const unsigned int pexp = bs.path_exp;
+                int P = bs.path_len;
+                const bool on = lane < P;
+                const bool exact = on && bs.slot_k[lane] == cur + lane && bs.slot_A[lane] == ((pexp & below) << cur);
+                const unsigned int inexact = __ballot_sync(FULL, on && !exact);
+                if (inexact) P = __ffs(inexact) - 1;                       // (slot 0 is (cur, nothing) by construction)
+                if (P < 1) __trap();                                       // never spin without progress
+                const float nt = (lane < P) ? bs.s_pt[lane] : 0.0f;
+                const unsigned int acc_before = pexp & below;
+                const float nt_prev = __shfl_sync(FULL, nt, acc_before ? 31 - __clz(acc_before) : 0);
+                const float tl_s = acc_before ? nt_prev : total;
+                const bool worse = lane < P && nt > tl_s;
+                const unsigned int worse_m = __ballot_sync(FULL, worse);
+                int dec = 1;
+                if (worse) { const float u = bs.s_rand[__popc(worse_m & below)]; dec = (u > bd.tol) ? 0 : 2; }
+                const bool surprise = lane < P - 1 && ((dec != 0) != (((pexp >> lane) & 1u) != 0u));
+                const unsigned int sur = __ballot_sync(FULL, surprise);
+                const int s_end = sur ? __ffs(sur) - 1 : P - 1;            // last slot the walk resolves
+                const bool res = lane <= s_end;
+                const unsigned int acc_slots = __ballot_sync(FULL, res && dec != 0);
+                if (res) { bs.path_slot[lane] = lane; bs.path_dec[lane] = dec; }
+                const int last = acc_slots ? 31 - __clz(acc_slots) : -1;
+                const float tl = __shfl_sync(FULL, nt, last < 0 ? 0 : last);
+                if (lane == 0) {
+                    const int k = cur + s_end + 1;
+                    const unsigned int A = acc_slots << cur;
+                    const int used = __popc(worse_m & ((s_end < 31) ? ((2u << s_end) - 1u) : FULL));
+                    // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
+                    const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
+                    bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0;
+                    bs.s_total = last < 0 ? total : tl;
                 }
-                // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
-                const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
-                bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0; bs.s_total = tl;
             }
             __syncwarp();
             const int k = bs.s_cur;
