@@ -1856,11 +1856,8 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             const int k = bs.s_cur;
             const unsigned int A = bs.s_acc;
             if (k < np && !bs.s_stopped) {
-                // the deltas of unresolved proposals next to an accepted one are about to be corrected: their
-                // predictions go; then the next round's plan
-                const unsigned int gone = __ballot_sync(0xFFFFFFFFu, lane >= k && lane < np && (bs.near[lane] & A));
-                if (lane == 0) bs.has_est &= ~gone;
-                __syncwarp();
+                // the next round's plan.  (The deltas of unresolved proposals next to an accepted one are about to be
+                // corrected by a few pair events; their predictions stay, they only steer the plan.)
                 build_plan(k, acc_mask | A, bs.s_ri - ri);
             }
         }
