@@ -561,7 +561,7 @@ __device__ __forceinline__ void epilogue_prefetch(EpiShared &es, float *epi_smem
 // Where a BATCH evaluation (batch_kernel: several proposals in flight) reads its counts and leaves its results:
 // the counts are the COMMITTED symmetrised totals plus the proposal's own symmetrised delta, the model total and
 // chi^2 go to per-proposal buffers, and nothing is published to the host (the kernel decides itself).
-static const int EPI_MAX_ADDS = 10;
+static const int EPI_MAX_ADDS = 12;
 struct EpiOut {
     const int *base;         // [nsym][hs] symmetrised totals the evaluation starts from (a fully visible copy)
     const int *adds[EPI_MAX_ADDS];   // [nsym][hs] symmetrised deltas on this model's grid: the proposal's own, then those
@@ -1234,7 +1234,7 @@ propose_loop_kernel(float4 *__restrict__ atoms, int npad, HostCmd *hcmd, DevCmd 
 // totals the sequential path would have staged.
 static const int BATCH_MAX_PROPS = 32;
 static const int BATCH_MAX_GROUPS = 16;
-static const int BATCH_MAX_SPEC = 4;
+static const int BATCH_MAX_SPEC = 5;
 static const int BATCH_DEFER_MAX_LEAVES = 32;   // longest pairwise schedule a warp sums (n_out up to ~4000)   // accepted-but-uncommitted proposals an evaluation may assume (EpiOut::add2)
 static const int BATCH_STAMP_SLOTS = 4 + 5 * 64;   // start, cleared, delta pass done, end; 5 per round
 static const int BATCH_STAMP_TOTAL = BATCH_STAMP_SLOTS + 64 * 128;   // + per round the EPI_STAMP block of CTA 1 (see tools/probe_batch.py)
