@@ -199,6 +199,36 @@ def test_batch_on_large_sparse_systems(kind, orc):
         r[0].close()
 
 
+@pytest.mark.parametrize("tol", [1.0, 0.0])
+def test_batch_deep_chains(tol, orc):
+    """single-atom proposals far apart in a large sparse system: nothing interacts, so the rounds' chains of predicted
+    outcomes run as deep as the plan allows.  tolerance 1 accepts every proposal (every node of a chain assumes all the
+    proposals before it, the limit of assumed acceptances and the pending commits are always at their maximum);
+    tolerance 0 is the benchmark's rule.  Bit-exact against the sequential device path."""
+    case = TS._large_sparse_case("ortho")
+    rng = np.random.default_rng(123)
+    n = 96
+    atoms = rng.choice(case["boxCoords"].shape[0], n, replace=False).astype(np.int32)
+    props = [(atoms[j:j + 1], (case["boxCoords"][atoms[j:j + 1]] + rng.normal(0, 0.003, (1, 3)).astype(F32)).astype(F32)) for j in range(n)]
+    rand = rng.random(n).astype(F32)
+    idx, moved, sizes = flatten(props)
+    var2 = np.array([1.0, 0.8], F32)
+    seq, _ = TS._build(case, ["PDF", "SQ"], np.random.default_rng(11))
+    bat, _ = TS._build(case, ["PDF", "SQ"], np.random.default_rng(11))
+    total0 = host_total(seq.compute_data(), var2)
+    bat.compute_data()
+    chis, decs, total, used = sequential_run(seq, props, total0, rand, tol, var2)
+    out = bat.run_batch(idx, moved, total0, rand, tolerance=tol, group_sizes=sizes, variance_squared=var2)
+    assert np.array_equal(out["decisions"], decs) and np.array_equal(out["chi2"], chis)
+    assert F32(out["total"]) == F32(total) and out["rand_used"] == used
+    if tol == 1.0:
+        assert int((decs > 0).sum()) == n
+    compare_stores(seq, bat, 2)
+    launches, rounds, resolved = bat.batch_stats()
+    assert resolved == n and rounds <= n // 2, "the chains resolved fewer than two proposals per round (%d rounds)" % rounds
+    seq.close(); bat.close()
+
+
 def test_batch_two_grids(orc):
     """PDF and S(Q) on different r-grids (the NiTi arrangement): both grids' deltas come from the same pass"""
     from fullrmc_b200.model import ModelSpec
