@@ -1659,7 +1659,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         const bool worse = lead && bs.est[j] > 0.0f;
         const unsigned int worse_m = __ballot_sync(FULL, worse);
         int dec = 1;
-        if (worse) { const float u = bs.s_rand[ri_off + __popc(worse_m & below)]; dec = (u > bd.tol) ? 0 : 1; }
+        if (worse) {                                                 // (lanes beyond the round's G nodes are never used)
+            const float u = bs.s_rand[min(ri_off + __popc(worse_m & below), 2 * BATCH_MAX_GROUPS - 1)];
+            dec = (u > bd.tol) ? 0 : 1;
+        }
         const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
         const unsigned int A_j = acc_pred & below & from_c;         // predicted acceptances in front of j
         const unsigned int sh_j = in_rng ? in.share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;

@@ -39,5 +39,14 @@ for mode in (False, True):
         prev = it % 2 == 0
     (st.accept if prev else st.reject)()
     print("persistent", mode, chi)
+# runs of proposals resolved on the device (batch_kernel): single atoms, a repeated atom, neighbours
+st.set_persistent(False)
+n = 80
+idx = rng.integers(0, 20000, n).astype(np.int32)
+idx[10] = idx[9]; idx[30] = idx[2]
+moved = (s.boxCoords[idx] + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
+total = np.float32(np.sum(st.committed_chi2()[:2], dtype=np.float32))
+out = st.run_batch(idx, moved, total, rng.random(n).astype(np.float32), tolerance=0.3)
+print("batch", int((out["decisions"] > 0).sum()), "accepted of", n, "in", st.batch_stats()[1], "rounds")
 st.close()
 print("done")
