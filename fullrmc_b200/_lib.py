@@ -62,6 +62,8 @@ SIGNATURES = {
                                                    c_i32p, c_f32p, c_i32p, c_f32p]),
     "frmc_full_atomic_distances_coords": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, c_f32p, c_f32p, _I,
                                                c_i32p, c_f32p, c_i32p, c_f32p]),
+    "frmc_coordination_counts": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_f32p, _I64, _I64, c_i32p, c_i32p, c_i32p, c_f32p, c_f32p,
+                                      _I64, c_i64p, c_i32p, _I64, c_i32p]),
     "frmc_debug_work_items": (_I, [_I64, c_i32p, _I, _I, _I, _I, c_i64p, c_i64p]),
     "frmc_debug_layout": (_I, [_I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,

@@ -13,7 +13,7 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
        -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -fno-fast-math)
 if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
 OBJS=()
-for f in common stateless fullhist store atomdist; do
+for f in common stateless fullhist store atomdist coordnum; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   OBJS+=("$OUT/$f.o")
 done

@@ -161,6 +161,21 @@ int frmc_full_atomic_distances_coords(int dev, const float *coords, int64_t n, c
                                       const float *upperLimit, int flags, int32_t *nintra, float *dintra,
                                       int32_t *ninter, float *dinter);
 
+/* ---- coordination-number counts (Extensions/atomic_coordination.pyx) ----------
+ * One call = a flat list of tasks; task t counts the atoms j of list task_list[t] whose distance to atom
+ * task_core[t] satisfies task_lower[t] <= d <= task_upper[t] (both ends inclusive, the float32 distance of
+ * pairs_distances_to_point; atomic_coordination.pyx:31-48, :89-108) and adds the count to counts[task_out[t]].
+ * Lists are given as offsets [nlists+1] into list_indexes.  This is what single_atom_single_shell_coords (:89),
+ * single_atom_multi_shells_coords (:139), single_atom_coord_number_coords (:207), multi_atoms_coord_number_coords
+ * (:280) and all_atoms_coord_number_coords (:349) reduce to; the *_totdists forms (:71, :116, :171, :249, :317)
+ * pass `distances` [nrows, n] instead of coords (coords NULL) and task_core[t] is then the ROW of the matrix.
+ * counts [nout] is overwritten (int32; the reference accumulates the same integers as float32). */
+int frmc_coordination_counts(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
+                             const float *distances, int64_t nrows, int64_t ntasks, const int32_t *task_core,
+                             const int32_t *task_list, const int32_t *task_out, const float *task_lower,
+                             const float *task_upper, int64_t nlists, const int64_t *list_offsets,
+                             const int32_t *list_indexes, int64_t nout, int32_t *counts);
+
 /* ------------------------------------------------------------------------------------
  * Stateful fast path: device-resident coordinate store + running histograms.
  * Replaces compute_data / compute_before_move / compute_after_move / accept_move /

@@ -33,7 +33,8 @@ MODULES = ("pairs_distances", "pairs_histograms", "reciprocal_space")
 # only needed to IMPORT the reference's Engine/constraint classes (golden-vector generation); not on the path
 EXTRA_MODULES = ("boundary_conditions_collection",)
 # the distance-constraint kernels (atomic_distances.pyx imports pairs_distances)
-NEXT_MODULES = ("atomic_distances",)
+# the coordination-number loops (atomic_coordination.pyx imports pairs_distances too)
+NEXT_MODULES = ("atomic_distances", "atomic_coordination")
 
 
 def is_built():
@@ -41,7 +42,7 @@ def is_built():
     if not os.path.isdir(core):
         return False
     names = os.listdir(core)
-    return all(any(n.startswith(m + ".") and n.endswith(".so") for n in names) for m in MODULES)
+    return all(any(n.startswith(m + ".") and n.endswith(".so") for n in names) for m in MODULES + NEXT_MODULES)
 
 
 def build(force=False):

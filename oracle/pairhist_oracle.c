@@ -324,6 +324,38 @@ void orc_multiple_atomic_distances_coords(const int32_t *indexes, int64_t k, con
     }
 }
 
+/* ---------------------------------------------------------------- coordination numbers
+ * Extensions/atomic_coordination.pyx:89-108 (single_atom_single_shell_coords): distances from the core atom to
+ * boxCoords[shellIndexes] by pairs_distances_to_point, then the counting loop :31-48 -- a float32 counter that
+ * gains 1.0 for every distance with lower <= d <= upper (both ends inclusive; the core atom itself is not
+ * skipped when it is in the list).  Negative indexes wrap as numpy fancy indexing does. */
+float orc_single_atom_single_shell_coords(int32_t coreIndex, const int32_t *shellIndexes, int64_t ns, const float *coords,
+                                          int64_t n, const float *basis, int isPBC, float lowerShell, float upperShell)
+{
+    const int64_t a = coreIndex < 0 ? coreIndex + n : coreIndex;
+    const float px = coords[3 * a], py = coords[3 * a + 1], pz = coords[3 * a + 2];
+    float coordNumber = 0.0f;
+    for (int64_t i = 0; i < ns; ++i) {
+        const int64_t j = shellIndexes[i] < 0 ? shellIndexes[i] + n : shellIndexes[i];
+        const float d = isPBC ? orc_dist_pbc(px, py, pz, coords + 3 * j, basis) : orc_dist_ibc(px, py, pz, coords + 3 * j);
+        if (lowerShell <= d && d <= upperShell) coordNumber += 1.0f;
+    }
+    return coordNumber;
+}
+
+/* atomic_coordination.pyx:71-85 (single_atom_single_shell_totdists; shellIndexes NULL = :55-67 subdists) */
+float orc_single_atom_single_shell_dists(const float *distances, int64_t n, const int32_t *shellIndexes, int64_t ns,
+                                         float lowerShell, float upperShell)
+{
+    float coordNumber = 0.0f;
+    for (int64_t i = 0; i < ns; ++i) {
+        const int64_t j = shellIndexes ? (shellIndexes[i] < 0 ? shellIndexes[i] + n : shellIndexes[i]) : i;
+        const float d = distances[j];
+        if (lowerShell <= d && d <= upperShell) coordNumber += 1.0f;
+    }
+    return coordNumber;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -1,0 +1,140 @@
+"""Coordination-number counts (Extensions/atomic_coordination.pyx).
+
+CPU: the oracle restatement (oracle/coordination.py + orc_single_atom_single_shell_* in oracle/pairhist_oracle.c)
+against the golden outputs of the reference's own compiled module (tests/gen_golden_atomic_coordination.py).
+GPU: fullrmc_b200.Core.atomic_coordination against the same golden vectors, against the oracle on larger systems, and
+through the before/after bookkeeping of AtomicCoordinationNumberConstraint (AtomicCoordinationConstraints.py:519-577).
+All comparisons are exact: the outputs are integer counts held as float32.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from gen_golden_atomic_coordination import definitions, run_all, unpack_lists
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "atomic_coordination.npz"))
+
+
+@pytest.fixture(scope="module")
+def orc_pd():
+    from oracle import pairhist
+    return pairhist
+
+
+def _system(g, name):
+    defs = (unpack_lists(g, name + "/cores"), unpack_lists(g, name + "/shells"), [np.float32(x) for x in g[name + "/lowerShells"]],
+            [np.float32(x) for x in g[name + "/upperShells"]], unpack_lists(g, name + "/asCore", True), unpack_lists(g, name + "/inShell", True))
+    return g[name + "/boxCoords"], g[name + "/basis"], bool(g[name + "/isPBC"]), defs, g[name + "/indexes"]
+
+
+def _compare(module, pd, g):
+    names = [str(x) for x in g["names"]]
+    assert len(names) == 4
+    for name in names:
+        box, basis, pbc, defs, idx = _system(g, name)
+        before = box.copy()
+        res = run_all(module, pd, box, basis, pbc, defs, idx)
+        assert np.array_equal(box, before)                       # inputs are borrowed, never modified
+        keys = sorted(k[len(name) + 5:] for k in g.files if k.startswith(name + "/out/"))
+        assert keys == sorted(res.keys())
+        for key in keys:
+            ref = g["%s/out/%s" % (name, key)]
+            got = np.asarray(res[key])
+            assert got.dtype == ref.dtype and got.shape == ref.shape, (name, key)
+            assert np.array_equal(got, ref), (name, key, got, ref)
+        assert bool(g[name + "/out/all_totdists_raises_TypeError"])
+        assert g[name + "/out/all_coords"].sum() > 100           # the fixture is not vacuous
+
+
+def test_oracle_matches_reference_golden(golden, orc_pd):
+    from oracle import coordination
+    _compare(coordination, orc_pd, golden)
+
+
+@pytest.mark.gpu
+def test_device_matches_reference_golden(golden):
+    from fullrmc_b200.Core import atomic_coordination, pairs_distances
+    _compare(atomic_coordination, pairs_distances, golden)
+
+
+def _random_system(n, nT, pbc, ndef, seed):
+    rng = np.random.default_rng(seed)
+    basis = np.array([[40, 0, 0], [5, 38, 0], [-3, 6, 36]], np.float32) if pbc else np.eye(3, dtype=np.float32)
+    box = (rng.random((n, 3)) * 1.6 - 0.3).astype(np.float32)     # partly outside [0,1): the general wrap is exercised
+    if not pbc:
+        box = (box * 36.0).astype(np.float32)
+    el = rng.integers(0, nT, n).astype(np.int32)
+    return rng, box, basis, definitions(rng, n, el, nT, ndef)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nT,pbc", [(6000, 3, True), (5000, 2, False)])
+def test_device_matches_oracle_on_larger_systems(n, nT, pbc):
+    """lists longer than one work item (2048 entries), thousands of tasks in one launch"""
+    from fullrmc_b200.Core import atomic_coordination as dev
+    from oracle import coordination as orc
+    rng, box, basis, defs = _random_system(n, nT, pbc, 4, 77 + n)
+    cores, shells, lowers, uppers, as_core, in_shell = defs
+    kw = dict(boxCoords=box, basis=basis, isPBC=pbc, coresIndexes=cores, shellsIndexes=shells, lowerShells=lowers, upperShells=uppers,
+              asCoreDefIdxs=as_core, inShellDefIdxs=in_shell)
+    got, ref = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    dev.all_atoms_coord_number_coords(coordNumData=got, **kw)
+    orc.all_atoms_coord_number_coords(coordNumData=ref, **kw)
+    assert np.array_equal(got, ref) and ref.sum() > 1000
+    idx = rng.integers(0, n, 13).astype(np.int32)                 # a molecule-sized group
+    got, ref = np.ones(4, np.float32), np.ones(4, np.float32)
+    dev.multi_atoms_coord_number_coords(indexes=idx, coordNumData=got, **kw)
+    orc.multi_atoms_coord_number_coords(indexes=idx, coordNumData=ref, **kw)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_device_before_after_bookkeeping_equals_recount():
+    """compute_before_move / compute_after_move of AtomicCoordinationNumberConstraint (AtomicCoordinationConstraints.py:519-577):
+    the constraint halves the whole-system count (every core-shell pair is met from both of its ends, :505) and then
+    data - before + after over a run of accepted moves equals the halved count from scratch of the final configuration"""
+    from fullrmc_b200.Core import atomic_coordination as dev
+    rng, box, basis, defs = _random_system(3000, 2, True, 3, 5)
+    cores, shells, lowers, uppers, as_core, in_shell = defs
+    kw = dict(basis=basis, isPBC=True, coresIndexes=cores, shellsIndexes=shells, lowerShells=lowers, upperShells=uppers,
+              asCoreDefIdxs=as_core, inShellDefIdxs=in_shell)
+    data = np.zeros(3, np.float32)
+    dev.all_atoms_coord_number_coords(boxCoords=box, coordNumData=data, **kw)
+    data /= np.float32(2.)
+    for _ in range(12):
+        idx = rng.integers(0, len(box), 1).astype(np.int32)      # single-atom moves: pairs inside a moved group would count once
+        before, after = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        dev.multi_atoms_coord_number_coords(indexes=idx, boxCoords=box, coordNumData=before, **kw)
+        box[idx] += (rng.normal(0, 0.02, (1, 3))).astype(np.float32)
+        dev.multi_atoms_coord_number_coords(indexes=idx, boxCoords=box, coordNumData=after, **kw)
+        data = data - before + after
+    recount = np.zeros(3, np.float32)
+    dev.all_atoms_coord_number_coords(boxCoords=box, coordNumData=recount, **kw)
+    assert np.array_equal(data, recount / np.float32(2.)) and recount.sum() > 1000
+
+
+@pytest.mark.gpu
+def test_device_edge_cases():
+    from fullrmc_b200.Core import atomic_coordination as dev
+    box = np.array([[0.1, 0.1, 0.1], [0.2, 0.1, 0.1], [0.95, 0.1, 0.1]], np.float32)
+    basis = (np.eye(3) * 10).astype(np.float32)
+    empty = np.zeros(0, np.int32)
+    assert dev.single_atom_single_shell_coords(0, empty, box, basis, True, 0.0, 5.0) == 0.0
+    allidx = np.arange(3, dtype=np.int32)
+    # the core atom itself is counted when lower <= 0 (the reference does not skip it); both shell ends are inclusive
+    assert dev.single_atom_single_shell_coords(0, allidx, box, basis, True, 0.0, 5.0) == 3.0
+    d01 = float(dev.single_atom_single_shell_totdists(np.array([0.5, 1.0, 1.5], np.float32), allidx, 1.0, 1.5))
+    assert d01 == 2.0
+    assert dev.single_atom_single_shell_coords(0, allidx, box, basis, False, 0.05, 0.2) == 1.0     # no images: only atom 1
+    data = np.zeros(1, np.float32)
+    dev.multi_atoms_coord_number_coords(indexes=empty, boxCoords=box, basis=basis, isPBC=True, coresIndexes=[allidx], shellsIndexes=[allidx],
+                                        lowerShells=[0.5], upperShells=[2.0], asCoreDefIdxs=[[0]] * 3, inShellDefIdxs=[[0]] * 3, coordNumData=data)
+    assert data[0] == 0.0
+    with pytest.raises(ValueError):
+        dev.single_atom_single_shell_coords(0, np.array([7], np.int32), box, basis, True, 0.0, 5.0)
+    with pytest.raises(TypeError):
+        dev.all_atoms_coord_number_totdists(np.zeros((3, 3), np.float32), [allidx], [allidx], [0.5], [2.0], [[0]] * 3, [[0]] * 3, data)
