@@ -483,6 +483,63 @@ def distance_leg(system, no_cpu):
     return out
 
 
+def coordination_leg(system, no_cpu):
+    """all_atoms_coord_number_coords (Extensions/atomic_coordination.pyx:349-376) of cfg4 through the stateless host call:
+    three definitions (core element, shell element, shell [1.5, 3.5] A) laid out as AtomicCoordinationNumberConstraint does
+    (AtomicCoordinationConstraints.py:376-400); the compiled reference timed on sampled atoms beside it"""
+    from fullrmc_b200 import _lib
+    from fullrmc_b200.Core import atomic_coordination as ac
+    lib = _lib.load_library()
+    n, el = system.numberOfAtoms, system.elementIndex
+    pairs = [(0, 1), (2, 2), (3, 4)]
+    cores = [np.nonzero(el == a)[0].astype(np.int32) for a, _ in pairs]
+    shells = [np.nonzero(el == b)[0].astype(np.int32) for _, b in pairs]
+    as_core, in_shell = [[] for _ in range(n)], [[] for _ in range(n)]
+    for d in range(len(pairs)):
+        for i in cores[d]:
+            as_core[i].append(d)
+        for i in shells[d]:
+            in_shell[i].append(d)
+    kw = dict(basis=system.basis, isPBC=system.isPBC, coresIndexes=cores, shellsIndexes=shells, lowerShells=[np.float32(1.5)] * 3,
+              upperShells=[np.float32(3.5)] * 3, asCoreDefIdxs=as_core, inShellDefIdxs=in_shell)
+    tests = float(sum(len(c) * len(s_) * 2 for c, s_ in zip(cores, shells)))       # distance tests of one whole-system call
+    data = np.zeros(3, np.float32)
+    ac.all_atoms_coord_number_coords(boxCoords=system.boxCoords, coordNumData=data, **kw)      # warm
+    l0 = int(lib.frmc_launch_count())
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        data = np.zeros(3, np.float32)
+        ac.all_atoms_coord_number_coords(boxCoords=system.boxCoords, coordNumData=data, **kw)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"metric": "all_atoms_coord_number_coords G distance tests/s", "workload": "cfg4: %d atoms, 3 definitions, shell [1.5, 3.5] A, "
+           "%.3g distance tests per call" % (n, tests), "e2e": {"value": tests / dt / 1e9, "unit": "G tests/s", "ms_per_call": 1e3 * dt,
+           "h2d_bytes_per_step": 12 * n + 24 * sum(len(a) + len(b) for a, b in zip(as_core, in_shell)), "d2h_bytes_per_step": 12,
+           "api": "fullrmc_b200.Core.atomic_coordination.all_atoms_coord_number_coords"},
+           "coordination_numbers": [float(x) for x in data / 2], "gpu_launches": (int(lib.frmc_launch_count()) - l0) // reps,
+           "roofline": None, "note": "stateless first version of this row: one launch over (atom, definition) tasks cut into 2048-entry "
+           "items; the call is dominated by flattening the Python lists on the host"}
+    # a per-move call (one atom, as compute_before_move makes it): latency of the host-buffer call
+    idx = np.array([n // 2], np.int32)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ac.multi_atoms_coord_number_coords(indexes=idx, boxCoords=system.boxCoords, coordNumData=np.zeros(3, np.float32), **kw)
+    out["per_move_call_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+    if not no_cpu:
+        from oracle import build_ref
+        import importlib
+        if build_ref.load() is not None:
+            ref = importlib.import_module("fullrmc.Core.atomic_coordination")
+            atoms = np.linspace(0, n - 1, 300).astype(np.int32)
+            sample = float(sum(len(shells[d]) for a in atoms for d in as_core[a]) + sum(len(cores[d]) for a in atoms for d in in_shell[a]))
+            t0 = time.perf_counter()
+            ref.multi_atoms_coord_number_coords(indexes=atoms, boxCoords=system.boxCoords, coordNumData=np.zeros(3, np.float32), ncores=1, **kw)
+            dtc = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": sample / dtc / 1e9, "unit": "G tests/s", "cores": 1, "kind": "reference",
+                                   "sample": "300 uniformly spaced atoms (multi_atoms_coord_number_coords)"}
+    return out
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -705,6 +762,7 @@ def run_b200(args):
         line["per_move"] = pm
         line["per_move_cfg4"] = pm4
         line["distance_constraint_cfg4"] = distance_leg(s4, args.no_cpu)
+        line["coordination_cfg4"] = coordination_leg(s4, args.no_cpu)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         scale = max(1, n // 1000000)                                           # ~10 s of CPU work per leg at 1 M atoms

@@ -12,6 +12,8 @@ accepted and ignored.
 The reference's ``single_atom_coord_number_totdists`` (:171-198) walks ``asCoreDefIdxs`` in BOTH of its loops (the
 coordinates form :207-240 walks ``inShellDefIdxs`` in the second); the mirror reproduces that as it is.
 """
+from itertools import chain
+
 import numpy as np
 
 from .. import _lib as L
@@ -50,15 +52,15 @@ class _Lists(object):
 
 
 def _count(what, tasks, lists, nout, boxCoords=None, basis=None, isPBC=False, distances=None):
-    """tasks: list of (core atom or distance row, list slot, output slot, lower, upper) -> int32 counts [nout]"""
+    """tasks: (core atom or distance row, list slot, output slot, lower, upper) as five equally long columns, or a
+    list of such 5-tuples -> int32 counts [nout]"""
     lib = L.load_library()
     counts = np.zeros(nout, _I32)
-    nt = len(tasks)
-    core = np.fromiter((t[0] for t in tasks), _I32, nt)
-    lst = np.fromiter((t[1] for t in tasks), _I32, nt)
-    out = np.fromiter((t[2] for t in tasks), _I32, nt)
-    lower = np.fromiter((t[3] for t in tasks), _F32, nt)
-    upper = np.fromiter((t[4] for t in tasks), _F32, nt)
+    if isinstance(tasks, list):
+        tasks = tuple(zip(*tasks)) if tasks else ((), (), (), (), ())
+    core, lst, out = (np.ascontiguousarray(c, dtype=_I32) for c in tasks[:3])
+    lower, upper = (np.ascontiguousarray(c, dtype=_F32) for c in tasks[3:])
+    nt = core.shape[0]
     off, idx = lists.flat()
     if distances is None:
         coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
@@ -128,13 +130,27 @@ def single_atom_multi_shells_coords(coreIndex, shellsIndexes, boxCoords, basis, 
 
 # ---------------------------------------------------------------- coordination-number definitions
 def _definition_tasks(atoms, rows, coresIndexes, shellsIndexes, lowerShells, upperShells, asCoreDefIdxs, secondDefIdxs, lists):
-    tasks = []
-    for a, row in zip(atoms, rows):
-        for defIdx in asCoreDefIdxs[a]:          # a is a core atom of the definition: count its shell atoms
-            tasks.append((row, lists.add(shellsIndexes[defIdx]), defIdx, lowerShells[defIdx], upperShells[defIdx]))
-        for defIdx in secondDefIdxs[a]:          # a is in the shell of the definition: count the core atoms around it
-            tasks.append((row, lists.add(coresIndexes[defIdx]), defIdx, lowerShells[defIdx], upperShells[defIdx]))
-    return tasks
+    """the (atom, definition) visits of single_atom_coord_number_* for every atom of `atoms`, as task columns: an atom
+    that is a core of a definition counts the definition's shell atoms, an atom named by `secondDefIdxs` counts its
+    core atoms.  The order of the tasks is free (integer counts), so they are gathered per role, not per atom."""
+    ndef = len(lowerShells)
+    slot_shell = np.array([lists.add(shellsIndexes[d]) for d in range(ndef)], _I32)
+    slot_core = np.array([lists.add(coresIndexes[d]) for d in range(ndef)], _I32)
+    lower = np.array([lowerShells[d] for d in range(ndef)], _F32)
+    upper = np.array([upperShells[d] for d in range(ndef)], _F32)
+    rows = np.asarray(rows, _I32)
+    core, lst, defs = [], [], []
+    for defIdxs, slots in ((asCoreDefIdxs, slot_shell), (secondDefIdxs, slot_core)):
+        per_atom = [defIdxs[a] for a in atoms]
+        lens = np.fromiter(map(len, per_atom), _I64, len(per_atom))
+        d = np.fromiter(chain.from_iterable(per_atom), _I32, int(lens.sum()))
+        if d.size and (d.min() < 0 or d.max() >= ndef):
+            raise IndexError("list index out of range")              # what lowerShells[defIdx] raises in the reference
+        core.append(np.repeat(rows, lens))
+        lst.append(slots[d])
+        defs.append(d)
+    d = np.concatenate(defs)
+    return np.concatenate(core), np.concatenate(lst), d, lower[d], upper[d]
 
 
 def _accumulate(coordNumData, counts):
@@ -146,7 +162,7 @@ def _accumulate(coordNumData, counts):
 def multi_atoms_coord_number_coords(indexes, boxCoords, basis, isPBC, coresIndexes, shellsIndexes, lowerShells, upperShells,
                                     asCoreDefIdxs, inShellDefIdxs, coordNumData, ncores=1):
     """atomic_coordination.pyx:280-313 (through :207-240): adds to coordNumData in place"""
-    atoms = [int(i) for i in np.asarray(indexes).ravel()]
+    atoms = np.asarray(indexes).ravel().tolist()
     lists = _Lists()
     tasks = _definition_tasks(atoms, atoms, coresIndexes, shellsIndexes, lowerShells, upperShells, asCoreDefIdxs, inShellDefIdxs, lists)
     counts = _count("multi_atoms_coord_number_coords", tasks, lists, len(coordNumData), boxCoords=boxCoords, basis=basis, isPBC=isPBC)
@@ -171,14 +187,14 @@ def all_atoms_coord_number_coords(boxCoords, basis, isPBC, coresIndexes, shellsI
 def multi_atoms_coord_number_totdists(indexes, distances, coresIndexes, shellsIndexes, lowerShells, upperShells, asCoreDefIdxs,
                                       inShellDefIdxs, coordNumData, ncores=1):
     """atomic_coordination.pyx:249-276 (through :171-198): distances[i] is the row of atom indexes[i]"""
-    atoms = [int(i) for i in np.asarray(indexes).ravel()]
+    atoms = np.asarray(indexes).ravel().tolist()
     rows = [L.as_array(distances[i], "distances", _F32, 1) for i in range(len(atoms))]
     if not atoms:
         return
     d = np.ascontiguousarray(np.stack(rows))
     lists = _Lists()
     # the reference walks asCoreDefIdxs twice here (:185, :192); see the module docstring
-    tasks = _definition_tasks(atoms, range(len(atoms)), coresIndexes, shellsIndexes, lowerShells, upperShells, asCoreDefIdxs, asCoreDefIdxs, lists)
+    tasks = _definition_tasks(atoms, np.arange(len(atoms)), coresIndexes, shellsIndexes, lowerShells, upperShells, asCoreDefIdxs, asCoreDefIdxs, lists)
     _accumulate(coordNumData, _count("multi_atoms_coord_number_totdists", tasks, lists, len(coordNumData), distances=d))
 
 

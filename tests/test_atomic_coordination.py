@@ -138,3 +138,24 @@ def test_device_edge_cases():
         dev.single_atom_single_shell_coords(0, np.array([7], np.int32), box, basis, True, 0.0, 5.0)
     with pytest.raises(TypeError):
         dev.all_atoms_coord_number_totdists(np.zeros((3, 3), np.float32), [allidx], [allidx], [0.5], [2.0], [[0]] * 3, [[0]] * 3, data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pbc", [True, False])
+def test_device_shell_bounds_that_are_distances_of_the_system(pbc, orc_pd):
+    """both ends inclusive when the bounds ARE distances that occur (the device compares d^2 against thresholds found by
+    exact fp32 search, csrc/coordnum.cu), and non-finite bounds fall back to the comparison on the rounded distance"""
+    from fullrmc_b200.Core import atomic_coordination as dev
+    from oracle import coordination as orc
+    rng, box, basis, _ = _random_system(4000, 2, pbc, 2, 91)
+    allidx = np.arange(len(box), dtype=np.int32)
+    for core in (3, 1777):
+        row = np.sort(orc_pd.pairs_distances_to_indexcoords(core, box, basis, pbc))
+        for lo, up in ((row[40], row[400]), (row[0], row[1]), (row[7], row[7]), (np.float32(0), row[-1]), (row[100], row[99]),
+                       (np.nextafter(row[40], np.float32(np.inf)), np.nextafter(row[400], np.float32(-np.inf))),
+                       (np.float32(-1.0), np.float32(np.inf)), (np.float32(np.nan), row[50]), (row[5], np.float32(np.nan)),
+                       (np.float32(-np.inf), row[9]), (np.float32(0), np.float32(0))):
+            got = dev.single_atom_single_shell_coords(core, allidx, box, basis, pbc, lo, up)
+            ref = orc.single_atom_single_shell_coords(core, allidx, box, basis, pbc, lo, up)
+            assert got == ref, (core, lo, up, got, ref)
+    assert orc.single_atom_single_shell_coords(3, allidx, box, basis, pbc, row[40], row[400]) >= 300

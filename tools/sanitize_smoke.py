@@ -5,7 +5,7 @@ import os
 import sys, numpy as np
 sys.path.insert(0, "/root/repo")
 from fullrmc_b200 import synthetic
-from fullrmc_b200.Core import pairs_histograms as ph, atomic_distances as ad
+from fullrmc_b200.Core import pairs_histograms as ph, atomic_distances as ad, atomic_coordination as ac
 from fullrmc_b200.store import DeviceStore
 from fullrmc_b200.model import ModelSpec
 # small but multi-block systems through every new kernel
@@ -17,6 +17,12 @@ for n, basis, pbc in ((9000, np.diag([70.0, 66.0, 72.0]).astype(np.float32), Tru
     lo = np.zeros((3, 3, 1), np.float32); up = np.full((3, 3, 1), 2.0, np.float32)
     r = ad.full_atomic_distances_coords(s.boxCoords, s.basis, pbc, s.moleculeIndex, s.elementIndex, 3, lo, up, intraMolecular=False)
     print("atomdist", int(r[2].sum()))
+    cores = [np.nonzero(s.elementIndex == 0)[0].astype(np.int32), np.nonzero(s.elementIndex == 1)[0].astype(np.int32)]
+    shells = [np.nonzero(s.elementIndex == 2)[0].astype(np.int32), cores[1]]
+    as_core = [[int(e)] if e < 2 else [] for e in s.elementIndex]; in_shell = [[0] if e == 2 else ([1] if e == 1 else []) for e in s.elementIndex]
+    cn = np.zeros(2, np.float32)
+    ac.multi_atoms_coord_number_coords(np.arange(0, n, 7, dtype=np.int32), s.boxCoords, s.basis, pbc, cores, shells, [0.5, 1.0], [3.0, 4.0], as_core, in_shell, cn)
+    print("coordination", cn)
 if os.environ.get("SAN_SKIP_STORE"):
     print("done (stateless kernels only)"); sys.exit(0)
 s = synthetic.random_system(20000, 5, np.diag([60.0, 60.0, 60.0]).astype(np.float32), n_elements=2)
