@@ -159,3 +159,35 @@ def test_device_shell_bounds_that_are_distances_of_the_system(pbc, orc_pd):
             ref = orc.single_atom_single_shell_coords(core, allidx, box, basis, pbc, lo, up)
             assert got == ref, (core, lo, up, got, ref)
     assert orc.single_atom_single_shell_coords(3, allidx, box, basis, pbc, row[40], row[400]) >= 300
+
+
+def test_host_flattening_lists_the_reference_visits():
+    """CPU: the task table the mirror builds (vectorised, grouped by role) holds exactly the (atom, list, definition,
+    bounds) visits of single_atom_coord_number_coords (:207-240) for every listed atom, lists deduplicated by identity"""
+    from fullrmc_b200.Core import atomic_coordination as dev
+    rng = np.random.default_rng(3)
+    n, nT, ndef = 300, 3, 5
+    el = rng.integers(0, nT, n).astype(np.int32)
+    cores, shells, lowers, uppers, as_core, in_shell = definitions(rng, n, el, nT, ndef)
+    shells[1] = cores[0]                                            # one array used twice: stored once
+    in_shell = [[] for _ in range(n)]
+    for d in range(ndef):
+        for i in shells[d]:
+            in_shell[int(i)].append(d)
+    atoms = rng.integers(0, n, 40).tolist() + [-1]                  # a repeated and a negative index are legal
+    lists = dev._Lists()
+    core, lst, out, lo, up = dev._definition_tasks(atoms, atoms, cores, shells, lowers, uppers, as_core, in_shell, lists)
+    off, idx = lists.flat()
+    assert len(off) - 1 == 2 * ndef - 1 and off[-1] == idx.shape[0]
+    got = sorted((int(a), tuple(idx[off[s]:off[s + 1]].tolist()), int(d), float(x), float(y)) for a, s, d, x, y in zip(core, lst, out, lo, up))
+    want = []
+    for a in atoms:
+        for d in as_core[a]:
+            want.append((a, tuple(shells[d].tolist()), d, float(lowers[d]), float(uppers[d])))
+        for d in in_shell[a]:
+            want.append((a, tuple(cores[d].tolist()), d, float(lowers[d]), float(uppers[d])))
+    assert got == sorted(want) and len(got) > 40
+    with pytest.raises(IndexError):
+        dev._definition_tasks([0], [0], cores, shells, lowers, uppers, [[ndef]] * n, in_shell, dev._Lists())
+    with pytest.raises(ValueError):
+        dev._Lists().add(np.zeros(3, np.int64))                     # Cython would refuse the int64 buffer
