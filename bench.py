@@ -159,9 +159,8 @@ def build_models(store, system, grid, exp_g, exp_s, q):
 
 
 def smooth_target(n, seed, center):
-    """experimental stand-in: smooth noise around the ideal-gas value (mixed accept/reject)"""
-    rng = np.random.default_rng(seed)
-    return (center + 0.02 * np.convolve(rng.standard_normal(n + 20), np.ones(21) / 21.0, "valid")).astype(np.float32)
+    from fullrmc_b200 import synthetic
+    return synthetic.smooth_target(n, seed, center)
 
 
 # ----------------------------------------------------------------------------- per-move leg

@@ -188,7 +188,7 @@ __device__ __forceinline__ void diff3(float px, float py, float pz, float cx, fl
 __device__ __forceinline__ bool blocks_far(const float4 loI, const float4 hiI, const float4 loJ, const float4 hiJ,
                                            const CullParams &cp)
 {
-    if (hiI.w != 0.f || hiJ.w != 0.f) return true;          // no finite atom on one side: nothing can be in range
+    if (hiI.w == 1.f || hiJ.w == 1.f) return true;          // no finite atom on one side: nothing can be in range
     const float eps = loI.w + loJ.w;
     const float li[3] = {loI.x, loI.y, loI.z}, ui[3] = {hiI.x, hiI.y, hiI.z};
     const float lj[3] = {loJ.x, loJ.y, loJ.z}, uj[3] = {hiJ.x, hiJ.y, hiJ.z};

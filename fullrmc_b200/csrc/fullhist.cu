@@ -3,16 +3,21 @@
 //
 // Pipeline of one launch (full_hist_launch):
 //   block_bbox_kernel    one bounding box per 256-record block and per 32-record sub-block
-//   pair_list_kernel x2  + scan2_kernel: the (I tile, J block) pairs whose boxes are within maxDistance,
-//                        cut into items of <= 8 surviving blocks (exact: a skipped pair cannot hold a hit)
-//   full_hist_kernel     persistent CTAs take items from an atomic counter; sweep with the reference's fp32
-//                        operation order, hits queued per lane and binned by the whole warp, counts in
-//                        CTA-private shared memory, flushed with 64-bit atomics per element pair
+//   pair_list_kernel x2  + scan2_kernel: the (I block, J block) pairs whose boxes are within maxDistance,
+//                        cut into items of <= 4 surviving blocks (exact: a skipped pair cannot hold a hit)
+//   bin_table_kernel     the d^2 thresholds of every bin edge, found by exact search on the reference's own
+//                        fp32 expression (int)((sqrt(d2) - rmin) / bin)
+//   full_hist_warp_kernel  WARPS take (item, I sub-block) tasks from a per-element-pair atomic counter.  A warp
+//                        holds 32 I atoms in registers, tests its own sub-block box against every 32-record J
+//                        sub-block of the item, streams the survivors through a private two-stage shared-memory
+//                        ring filled by TMA bulk copies (cp.async.bulk + mbarrier: no CTA barrier anywhere in the
+//                        sweep), evaluates 32 x 32 distances per unit with the reference's fp32 operation order,
+//                        queues (d2, j) of the hits per lane and bins them per sub-block into CTA-private
+//                        shared-memory counters, flushed with 64-bit atomics when the CTA leaves an element pair
 //
-// Bound: FP32 instruction issue on the pairs that cannot be excluded (19 exact operations per distance on the
-// orthorhombic fast path), plus the bin pass of the in-range pairs.  Not HBM (one pass over 20 B/atom) and
-// not tensor cores: the minimum image needs exact fp32 wrap/compare sequences that have no GEMM form.
-// DESIGN.md section 4.1 and profiles/r1_fullhist_ncu_summary.md have the instruction budget and the ncu numbers.
+// Bound: FP32 instruction issue on the distance evaluations that cannot be excluded, plus the bin pass of the
+// in-range pairs.  Not HBM (one pass over 20 B/atom) and not tensor cores: the minimum image needs exact fp32
+// wrap/compare sequences that have no GEMM form.  DESIGN.md section 4.1 has the instruction budget.
 #include "common.cuh"
 #include "layout.h"
 
@@ -267,8 +272,60 @@ void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vecto
     }
 }
 
-// ------------------------------------------------------------------ the kernel
-static const int JS = 512;   // J atoms staged per shared-memory sub-tile
+// ------------------------------------------------------------------ the sweep
+// Work unit of the sweep: 32 I records (one per lane of a warp) x one 32-record J sub-block.
+static const int V2_THREADS = 256;        // 8 warps per CTA share one set of counters
+static const int V2_WARPS = V2_THREADS / 32;
+static const int V2_ITEM_BLOCKS = 4;      // surviving J blocks per item: 8 tasks (one per I sub-block) of <= 32 units each
+static const int V2_CAP = 24;             // hit-queue entries per lane (8 bytes each); drained after every unit
+static const int V2_TASK_LIMIT = 65536;   // tasks a CTA bins into its 32-bit counters between two flushes (32768 hits each at most)
+// per-warp shared memory: queue [V2_CAP][32] uint2, J ring [2][32] float4, J original indexes [2][32] u32, 2 mbarriers
+static const int V2_Q_BYTES = V2_CAP * 32 * 8;
+static const int V2_WARP_BYTES = V2_Q_BYTES + 2 * 32 * 16 + 2 * 32 * 4 + 32;
+
+__device__ __forceinline__ unsigned fh_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fh_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(fh_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fh_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fh_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void fh_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(fh_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(fh_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fh_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0, spins = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(fh_smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > 100000000u) __trap();     // never hang the GPU on a lost transaction
+    } while (!ok);
+}
+
+// squared distance with the reference's operation order; NOWRAP drops the minimum-image step for units whose
+// boxes prove |fl(xi - xj)| < 0.5 - 2^-25 on every axis: there round() is 0 and d - round(d) = d exactly
+// (pairs_distances.pyx:31-32, 372-386), so the sequence of rounded operations is unchanged.
+template <int MODE, bool NOWRAP>
+__device__ __forceinline__ float dist2_unit(float xi, float yi, float zi, float xj, float yj, float zj, const Lattice &L)
+{
+    if (!NOWRAP || MODE == MODE_IBC) return dist2<MODE>(xi, yi, zi, xj, yj, zj, L);
+    const float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj), dz = __fsub_rn(zi, zj);
+    float rx, ry, rz;
+    if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
+        rx = __fmul_rn(dx, L.b[0]); ry = __fmul_rn(dy, L.b[4]); rz = __fmul_rn(dz, L.b[8]);
+    } else {
+        rx = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[0]), __fmul_rn(dy, L.b[3])), __fmul_rn(dz, L.b[6]));
+        ry = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[1]), __fmul_rn(dy, L.b[4])), __fmul_rn(dz, L.b[7]));
+        rz = __fadd_rn(__fadd_rn(__fmul_rn(dx, L.b[2]), __fmul_rn(dy, L.b[5])), __fmul_rn(dz, L.b[8]));
+    }
+    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+}
 
 // where an overflowing event goes when the reference's unchecked write is reproduced: straight to the
 // global ordered histogram (rare: a pair within an ulp of maxDistance)
@@ -278,122 +335,102 @@ struct SpillTarget {
     int slab_ab, slab_ba;
 };
 
-// Lane-private hit queues, warp-balanced binning.  In-range pairs are 0.3 % (plain sweep of a sparse box)
-// to 50 % (maxDistance near half the box) of the pairs swept.  Binning a pair where it is found runs
-// sqrt/div/atomic with a lane or two alive and, inlined per register atom and unroll step, bloats the loop
-// past the instruction cache (ncu: "no instruction" was the top stall).  So the sweep only RECORDS a hit --
-// a predicated 4-byte store of (i << 8 | q) into the lane's own column of a shared-memory array and a
-// predicated pointer bump: no branch, no vote -- and when a column is nearly full or the staged block ends
-// the warp bins ALL its columns together, entry f of the concatenated columns going to lane f % 32 (the
-// owner column is found by a 5-step search over the scanned column lengths).  The I tile is kept in shared
-// memory as well so that any lane can bin any entry.  The bin pass recomputes d2 from the same operands
-// with the same instruction sequence, so it sees the identical value; integer counts make the order of
-// binning irrelevant.
-template <int R> struct SweepShape {
-    static const int U = (R == 1) ? 4 : 2;          // J records per drain check
-    static const int CAP = (R == 1) ? 20 : 16;      // queue entries per lane; [slot][thread] layout: own bank
+// Bin index of an in-range d2 without sqrt and divide: tab[b] = (T[b], T[b+1]), T[b] the smallest fp32 d2 whose
+// reference bin (int)((sqrt(d2) - rmin) / bin) is >= b (bin_table_kernel: exact search on that very expression,
+// which is monotone in d2).  An approximate sqrt gives a guess at most one bin off; the thresholds decide.
+__device__ __forceinline__ int bin_from_table(float d2, const float2 *__restrict__ tab, float inv_bin, float c0, int hs)
+{
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2));
+    int b = __float2int_rz(__fmaf_rn(s, inv_bin, c0));
+    b = max(0, min(b, hs));
+    float2 t = tab[b];
+    while (d2 < t.x) t = tab[--b];
+    while (d2 >= t.y) t = tab[++b];
+    return b;
+}
+
+struct WarpCtx {                  // what the bin pass needs, all warp-uniform or lane-private registers
+    const float4 *sJ;             // [2][32] staged J records
+    const uint32_t *sO;           // [2][32] their original indexes
+    const uint2 *lq;              // this lane's queue column (stride 32 entries)
+    uint32_t w0;                  // shared-window address of lq
+    uint32_t mi, oi;              // the lane's own I record: meta, original index
+    bool cross;                   // different elements: the ordered slot depends on the original order
 };
 
-template <int MODE, int R>
-__device__ __forceinline__ void bin_warp_queues(const uint32_t *__restrict__ lq0 /* column of lane 0 of this warp */,
-                                                int n, const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO,
-                                                const float4 *__restrict__ sI, const uint32_t *__restrict__ sIO,
-                                                int i0, int jbase, bool tri, bool cross, const Lattice &L,
-                                                const GridParams &g, unsigned int *__restrict__ sh,
-                                                unsigned long long &ov, const SpillTarget &sp)
+// every lane bins its own queue (d2 kept from the sweep: nothing is recomputed)
+template <bool TABLE>
+__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, const GridParams &g, const float2 *__restrict__ tab,
+                                            float inv_bin, float c0, unsigned int *__restrict__ sh, unsigned long long &ov,
+                                            const SpillTarget &sp)
 {
+    const int n = (int)((wp - W.w0) >> 8);
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
     const int lane = threadIdx.x & 31;
-    int incl = n;                                  // inclusive scan of the column lengths
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - n;
-    for (int f0 = 0; f0 < total; f0 += 32) {
-        const int f = f0 + lane;
-        int l = 0;                                 // owner column = number of columns that end at or before f
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
-            if (v <= f) l += step;
-        }
-        const int first = __shfl_sync(0xffffffffu, excl, l & 31);
-        if (f < total) {
-            const uint32_t e = lq0[(f - first) * 256 + l];
-            const int q = (int)(e & 0xFFu), i = (int)(e >> 8);
-            if (!tri || (i0 + i < jbase + q)) {    // diagonal tile: only p < q counts
-                const float4 a = sI[i], c = sJ[q];
-                const float d2 = dist2<MODE>(a.x, a.y, a.z, c.x, c.y, c.z, L);
-                const int b = bin_index(d2, g);
-                const uint32_t mi = __float_as_uint(a.w), mj = __float_as_uint(c.w);
-                // slot bit 1: inter-molecular, bit 0: the J atom comes first in original order
-                const int slot = (((mi >> 8) == (mj >> 8)) ? 0 : 2) | ((cross && (sIO[i] > sO[q])) ? 1 : 0);
-                if (b < g.hs) {
+    for (int k = 0; k < nmax; ++k) {
+        if (k < n) {
+            const uint2 e = W.lq[k * 32];
+            const float d2 = __uint_as_float(e.x);
+            const int q = (int)(e.y & 63u);                    // stage * 32 + record
+            if (!(e.y & 0x80u) || lane < (q & 31)) {           // unit on the diagonal of its block: only p < q counts
+                const uint32_t mj = __float_as_uint(W.sJ[q].w);
+                int slot = ((W.mi >> 8) == (mj >> 8)) ? 0 : 2;  // bit 1: inter-molecular
+                if (W.cross && W.oi > W.sO[q]) slot |= 1;       // bit 0: the J atom comes first in original order
+                int b = TABLE ? bin_from_table(d2, tab, inv_bin, c0, g.hs) : bin_index(d2, g);
+                if ((unsigned)b < (unsigned)g.hs) {
                     atomicAdd(&sh[slot * g.hs + b], 1u);
                 } else {
                     ++ov;
+                    if (TABLE) b = bin_index(d2, g);            // the table stops at histSize; the spill needs the real index
                     const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-                    if (g.spill && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+                    if (g.spill && b >= 0 && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
                 }
             }
         }
     }
+    wp = W.w0;
     __syncwarp();
 }
 
-// one staged block of SEG_PAD J records against the thread's R register atoms
-template <int MODE, int R>
-__device__ __forceinline__ void sweep_block(const float4 *__restrict__ sJ, const uint32_t *__restrict__ sO, int jbase,
-                                            const float (&xi)[R], const float (&yi)[R], const float (&zi)[R],
-                                            const float4 *__restrict__ sI, const uint32_t *__restrict__ sIO, int i0,
-                                            bool tri, bool cross, const Lattice &Lc, const GridParams &g, unsigned submask,
-                                            uint32_t *__restrict__ lq, unsigned int *__restrict__ sh,
-                                            unsigned long long &ov, const SpillTarget &sp)
+// one staged J sub-block (32 records) against the lane's I atom; hits are pushed as (d2, tag + q): a predicated
+// 8-byte store into the lane's own queue column and a predicated pointer bump -- no branch, no vote
+template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE>
+__device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float xi, float yi, float zi, const Lattice &Lc,
+                                           float t2min, float t2max, uint32_t tag, uint32_t &wp, const WarpCtx &W,
+                                           const GridParams &g, const float2 *__restrict__ tab, float inv_bin, float c0,
+                                           unsigned int *__restrict__ sh, unsigned long long &ov, const SpillTarget &sp)
 {
-    const int U = SweepShape<R>::U, CAP = SweepShape<R>::CAP;
-    // lattice in plain registers: from the constant bank the compiler re-reads it (LDCU) every iteration
-    Lattice L = Lc;
+    Lattice L = Lc;               // lattice in plain registers: from the constant bank the compiler re-reads it every iteration
     if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
         asm volatile("" : "+f"(L.b[0]), "+f"(L.b[4]), "+f"(L.b[8]));
     }
-    float t2min = g.t2min, t2max = g.t2max;
     asm volatile("" : "+f"(t2min), "+f"(t2max));
-    // 32-bit shared-window addresses: the push is STS + IADD under the hit predicate
-    const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(lq);
-    const uint32_t wfull = w0 + (uint32_t)(CAP - U * R) * 1024u;
-    uint32_t wp = w0;                            // next free slot of this lane's queue (stride 256 words)
-    const uint32_t *lq0 = lq - (threadIdx.x & 31);
-    uint32_t tid8 = threadIdx.x << 8;            // opaque, or the compiler rebuilds it under every hit predicate
-    asm volatile("" : "+r"(tid8));
-    // 32-record sub-blocks whose box is out of reach of every I block are not in submask (CTA-uniform)
-    for (unsigned sm = submask; sm; sm &= sm - 1u) {
-        const int qb = (__ffs(sm) - 1) * 32;
 #pragma unroll 1
-        for (int q = qb; q < qb + 32; q += U) {
-            const uint32_t ev = tid8 + (uint32_t)q;          // entry = (r * SEG_PAD + tid) << 8 | (q + u)
+    for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float4 a = sJ[q + u];
+        for (int c = 0; c < 2; ++c) {
+            // eight records in flight: loads first, then eight independent distance chains, then the pushes
+            float4 a[8];
+            float d2[8];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float d2 = dist2<MODE>(xi[r], yi[r], zi[r], a.x, a.y, a.z, L);
-                    if ((d2 >= t2min) && (d2 < t2max)) {
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"(ev + (uint32_t)(((r * SEG_PAD) << 8) + u)) : "memory");
-                        wp += 1024u;
-                    }
+            for (int u = 0; u < 8; ++u) a[u] = sJu[half * 16 + c * 8 + u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])),
+                                 "r"(tag + (uint32_t)(half * 16 + c * 8 + u)) : "memory");
+                    wp += 256u;
                 }
             }
-            if (__any_sync(0xffffffffu, wp > wfull)) {
-                __syncwarp();
-                bin_warp_queues<MODE, R>(lq0, (int)((wp - w0) >> 10), sJ, sO, sI, sIO, i0, jbase, tri, cross, Lc, g, sh, ov, sp);
-                wp = w0;
-            }
         }
+        // the queue holds 24 entries per lane: after the first 16 records it is emptied only if a lane has more than 8
+        if (half == 0 && !__any_sync(0xffffffffu, wp > W.w0 + 8u * 256u)) continue;
+        __syncwarp();
+        drain_queue<TABLE>(wp, W, g, tab, inv_bin, c0, sh, ov, sp);
     }
-    __syncwarp();
-    bin_warp_queues<MODE, R>(lq0, (int)((wp - w0) >> 10), sJ, sO, sI, sIO, i0, jbase, tri, cross, Lc, g, sh, ov, sp);
 }
 
 // ------------------------------------------------------------------ block bounding boxes + culling
@@ -429,10 +466,15 @@ __global__ void block_bbox_kernel(const float4 *__restrict__ atoms, int nblocks,
             }
             amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         }
+        // hi.w: 1 = no finite atom, 2 = every atom has all three coordinates in [0, 1) (raw = reduced: the sweep may
+        // then prove from the boxes that no pair of two such sub-blocks needs the minimum-image step), 0 = otherwise
+        const bool in_unit = !(isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) ||
+                             (a.x >= 0.f && a.x < 1.f && a.y >= 0.f && a.y < 1.f && a.z >= 0.f && a.z < 1.f);
+        const bool all_unit = __all_sync(0xffffffffu, in_unit);
         if (lane == 0) {
             const size_t at = 2 * ((size_t)blk * (SEG_PAD / 32) + sb);
             sbox[at + 0] = make_float4(lo[0], lo[1], lo[2], 1e-6f * (1.0f + amax));
-            sbox[at + 1] = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? 0.f : 1.f);
+            sbox[at + 1] = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? (all_unit ? 2.f : 0.f) : 1.f);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) { blo[c] = fminf(blo[c], lo[c]); bhi[c] = fmaxf(bhi[c], hi[c]); }
@@ -479,16 +521,14 @@ CullParams make_cull(const Lattice &L, int mode, const GridParams &g)
 // ------------------------------------------------------------------ surviving block pairs, built on the device
 // A ROW (host, layout.h:WorkItem) is one I tile against the whole J range of one element pair.  One warp
 // per row tests the row's J blocks 32 at a time against the tile's boxes and writes the survivors; rows are
-// then cut into ITEMS of at most PAIR_ITEM_BLOCKS surviving blocks, the units the sweep kernel's atomic
-// counter hands out.  Items therefore cost about the same and none is empty: no CTA walks culled work, and
+// then cut into ITEMS of at most PairLists::item_blocks surviving blocks, the units the sweep kernels' atomic
+// counters hand out.  Items therefore cost about the same and none is empty: no CTA walks culled work, and
 // the tail of a launch is one item long (what limited the 8-GPU efficiency of the chunked list).
 // Two passes (count, exclusive scan, fill) size the lists exactly; the host reads the two totals back.
-static const int PAIR_ITEM_BLOCKS = 8;
-
 __global__ void pair_list_kernel(const WorkItem *__restrict__ rows, int n_rows, const float4 *__restrict__ bbox, CullParams cp,
                                  int *__restrict__ row_cnt, int *__restrict__ row_items, const int *__restrict__ row_start,
                                  const int *__restrict__ row_item_start, uint32_t *__restrict__ entries, int4 *__restrict__ items,
-                                 int fill)
+                                 int fill, int PAIR_ITEM_BLOCKS)
 {
     const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (r >= n_rows) return;
@@ -543,126 +583,201 @@ __global__ void __launch_bounds__(1024) scan2_kernel(const int *__restrict__ a, 
     if (t == 1023) { totals[0] = pa[t]; totals[1] = pb[t]; }
 }
 
+// d^2 thresholds of the bin edges: T[b] = smallest fp32 d2 in [t2min, t2max) whose reference bin index
+// (int)((sqrt(d2) - rmin) / bin) -- evaluated with the very IEEE operations of bin_index() -- is >= b, +inf when there
+// is none; the expression is monotone in d2 (sqrt, subtraction, division by a positive bin and truncation all are),
+// so a bisection over the ordered bit patterns of the positive floats finds it exactly.  tab[b] = (T[b], T[b+1]),
+// b = 0..hs, with T[0] = -inf and T[hs+1] = +inf: bin_from_table() returns hs for the edge-overflow events.
+__global__ void bin_table_kernel(GridParams g, float2 *__restrict__ tab)
+{
+    const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (b > g.hs) return;
+    float edge[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int want = b + k;
+        if (want == 0) { edge[k] = -INFINITY; continue; }
+        if (want > g.hs) { edge[k] = INFINITY; continue; }
+        unsigned lo = __float_as_uint(g.t2min), hi = __float_as_uint(g.t2max);      // search [lo, hi)
+        const unsigned end = hi;
+        while (lo < hi) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            if (bin_index(__uint_as_float(mid), g) >= want) hi = mid; else lo = mid + 1;
+        }
+        edge[k] = (lo < end) ? __uint_as_float(lo) : INFINITY;
+    }
+    tab[b] = make_float2(edge[0], edge[1]);
+}
+
+// everything one launch of the sweep needs, by value
+struct SweepArgs {
+    const float4 *atoms; const uint32_t *orig; const float4 *bbox;
+    const WorkItem *rows; const int *pair_first_row; const int *row_item_start;
+    const uint32_t *entries; const int4 *items; int *pair_next;
+    const float2 *tab;
+    unsigned long long *counts; unsigned long long *stats;
+    int n_rows, n_pairs, n_items, nblocks, nEl;
+    Lattice L; GridParams g; CullParams cp;
+};
+
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
-// stats[0] += edge overflow events, stats[1] += (SEG_PAD I records x 32 J records) units actually swept.
-template <int MODE, int R>
-__global__ void __launch_bounds__(256, (R == 1) ? 4 : 3)
-full_hist_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, const float4 *__restrict__ bbox,
-                 const WorkItem *__restrict__ rows, const uint32_t *__restrict__ entries, const int4 *__restrict__ items,
-                 int n_items, int *__restrict__ next_item, Lattice L, GridParams g, CullParams cp, int nblocks, int nEl,
-                 unsigned long long *__restrict__ counts, unsigned long long *__restrict__ stats)
+// stats[0] += edge overflow events, stats[1] += (32 I records x 32 J records) units actually swept.
+template <int MODE, bool HASMIN, bool TABLE>
+__global__ void __launch_bounds__(V2_THREADS, 3) full_hist_warp_kernel(const SweepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *sJ = reinterpret_cast<float4 *>(smem_raw);
-    uint32_t *sO = reinterpret_cast<uint32_t *>(smem_raw + sizeof(float4) * JS);
-    unsigned char *cur = smem_raw + (sizeof(float4) + sizeof(uint32_t)) * JS;
-    float4 *sI = reinterpret_cast<float4 *>(cur);                       cur += sizeof(float4) * SEG_PAD * R;
-    uint32_t *sIO = reinterpret_cast<uint32_t *>(cur);                  cur += sizeof(uint32_t) * SEG_PAD * R;
-    uint32_t *lq = reinterpret_cast<uint32_t *>(cur) + threadIdx.x;     cur += sizeof(uint32_t) * SweepShape<R>::CAP * 256;
-    unsigned int *sh = reinterpret_cast<unsigned int *>(cur);
-    __shared__ int s_item;
-
-    const int tid = threadIdx.x, lane = threadIdx.x & 31;
+    const GridParams &g = A.g;
+    const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nsh = 4 * g.hs;
-    for (int c = tid; c < nsh; c += 256) sh[c] = 0u;
-    unsigned long long ov = 0, swept = 0;
-    const long long cells = (long long)nEl * nEl * g.hs;
-    int cur_slab = -1;                        // element pair the shared counters currently hold
-    unsigned int since_flush = 0;             // block pairs swept into the counters since the last flush
-    SpillTarget sp;
-    sp.counts = counts; sp.cells = cells; sp.slab_ab = 0; sp.slab_ba = 0;
+    unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw);                      // 4 x hs counters of the CTA's element pair
+    size_t off = ((size_t)nsh * 4 + 15) & ~(size_t)15;
+    float2 *tab = reinterpret_cast<float2 *>(smem_raw + off);
+    if (TABLE) off += (((size_t)g.hs + 1) * 8 + 15) & ~(size_t)15;
+    unsigned char *wbase = smem_raw + off + (size_t)warp * V2_WARP_BYTES;
+    float4 *sJ = reinterpret_cast<float4 *>(wbase + V2_Q_BYTES);
+    uint32_t *sO = reinterpret_cast<uint32_t *>(wbase + V2_Q_BYTES + 2 * 32 * 16);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_Q_BYTES + 2 * 32 * 16 + 2 * 32 * 4);
+    __shared__ int s_tasks, s_again, s_p0;
 
-    while (true) {
-        __syncthreads();                      // s_item consumed, previous item's sweeps done
-        if (tid == 0) s_item = atomicAdd(next_item, 1);
-        __syncthreads();
-        const int it = s_item;
-        WorkItem w;
-        w.ea = -1; w.eb = -1;
-        int4 item = make_int4(0, 0, 0, 0);    // {row, first entry, surviving J blocks (<= PAIR_ITEM_BLOCKS), -}
-        if (it < n_items) { item = items[it]; w = rows[item.x]; }
-        const int slab = (it < n_items) ? w.ea * nEl + w.eb : -2;
-        // The counters belong to one element pair at a time; the item list is ordered by pair, so this
-        // flush happens a handful of times per CTA (32-bit counters: also before 2^31 pairs pile up).
-        if (slab != cur_slab || since_flush >= 32768u - 64u) {
-            __syncthreads();                  // every warp has binned its queues (sweep_block ends with that)
-            if (cur_slab >= 0) {
-                for (int c = tid; c < nsh; c += 256) {
-                    const unsigned int v = sh[c];
-                    if (v) {
+    for (int c = tid; c < nsh; c += V2_THREADS) sh[c] = 0u;
+    if (TABLE) for (int c = tid; c <= g.hs; c += V2_THREADS) tab[c] = A.tab[c];
+    if (lane == 0) {
+        fh_mbar_init(&mbar[0], 1); fh_mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        s_tasks = 0; s_again = 0;
+        // CTAs start on the element pair that holds their share of the items, so that a CTA stays on one pair
+        // (one flush of its counters) for most of the launch; pairs are then visited cyclically
+        const long long target = ((2ll * blockIdx.x + 1) * A.n_items) / (2ll * gridDim.x);
+        int p0 = 0;
+        for (int p = 0; p < A.n_pairs; ++p) {
+            const int r = A.pair_first_row[p];
+            if ((r < A.n_rows ? A.row_item_start[r] : A.n_items) <= target) p0 = p;
+        }
+        s_p0 = p0;
+    }
+    __syncthreads();
+    const int p0 = s_p0;
+
+    WarpCtx W;
+    W.sJ = sJ; W.sO = sO;
+    W.lq = reinterpret_cast<const uint2 *>(wbase) + lane;
+    W.w0 = fh_smem_u32(W.lq);
+    uint32_t wp = W.w0;
+    const float inv_bin = TABLE ? __frcp_rn(g.bin) : 0.f, c0 = TABLE ? -g.rmin * inv_bin : 0.f;
+    unsigned long long ov = 0, swept = 0;
+    const long long cells = (long long)A.nEl * A.nEl * g.hs;
+    SpillTarget sp;
+    sp.counts = A.counts; sp.cells = cells; sp.slab_ab = 0; sp.slab_ba = 0;
+    unsigned seq = 0;                             // J sub-blocks this warp has streamed: stage = seq & 1, parity = (seq >> 1) & 1
+    const float T = __int_as_float(0x3EFFFFFF);   // 0.5 - 2^-25: below it round() is 0 (common.cuh:wrap_fast)
+
+    for (int v = 0; v < A.n_pairs; ++v) {
+        const int p = (p0 + v) % A.n_pairs;
+        const int r0 = A.pair_first_row[p], r1 = A.pair_first_row[p + 1];
+        const int is = (r0 < A.n_rows) ? A.row_item_start[r0] : A.n_items;
+        const int ie = (r1 < A.n_rows) ? A.row_item_start[r1] : A.n_items;
+        const int ntasks = (ie - is) * (SEG_PAD / 32);
+        if (ntasks <= 0) continue;
+        const WorkItem w0row = A.rows[r0];
+        const bool cross = (w0row.ea != w0row.eb);
+        sp.slab_ab = w0row.ea * A.nEl + w0row.eb; sp.slab_ba = w0row.eb * A.nEl + w0row.ea;
+        W.cross = cross;
+        bool again = true;
+        while (again) {
+            // ---- this warp's tasks of the pair
+            while (true) {
+                if (*(volatile int *)&s_tasks >= V2_TASK_LIMIT) { if (lane == 0) s_again = 1; break; }
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&A.pair_next[p], 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= ntasks) break;
+                if (lane == 0) atomicAdd(&s_tasks, 1);
+                const int4 item = A.items[is + (t >> 3)];     // {row, first entry, surviving J blocks (<= V2_ITEM_BLOCKS), -}
+                const int s = t & 7;                          // the I sub-block of the row's block this warp takes
+                const WorkItem w = A.rows[item.x];
+                const int bi = w.i0 / SEG_PAD;
+                const size_t atI = 2 * ((size_t)A.nblocks + (size_t)bi * (SEG_PAD / 32) + s);
+                const float4 loI = A.bbox[atI], hiI = A.bbox[atI + 1];
+                if (A.cp.enabled && hiI.w == 1.f) continue;   // padding only
+                const int pI = w.i0 + s * 32 + lane;
+                const float4 ai = A.atoms[pI];
+                W.mi = __float_as_uint(ai.w); W.oi = A.orig[pI];
+                // which of the item's 32-record J sub-blocks can hold a hit for THIS warp's 32 atoms: lane = (entry, sub-block)
+                const int e = lane >> 3, sb = lane & 7;
+                int jb = 0;
+                bool near = false, nowrap = false, tri = false;
+                if (e < item.z) {
+                    jb = (int)A.entries[item.y + e];
+                    near = true;
+                    if (!cross && jb == bi) { near = (sb >= s); tri = (sb == s); }     // inside the I block: only p < q counts
+                    if (near && A.cp.enabled) {
+                        const size_t atJ = 2 * ((size_t)A.nblocks + (size_t)jb * (SEG_PAD / 32) + sb);
+                        const float4 loJ = A.bbox[atJ], hiJ = A.bbox[atJ + 1];
+                        near = !blocks_far(loI, hiI, loJ, hiJ, A.cp);
+                        nowrap = (hiI.w == 2.f) && (hiJ.w == 2.f) &&
+                                 (__fsub_rn(hiI.x, loJ.x) < T) && (__fsub_rn(hiJ.x, loI.x) < T) &&
+                                 (__fsub_rn(hiI.y, loJ.y) < T) && (__fsub_rn(hiJ.y, loI.y) < T) &&
+                                 (__fsub_rn(hiI.z, loJ.z) < T) && (__fsub_rn(hiJ.z, loI.z) < T);
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, near);
+                const unsigned m_nowrap = __ballot_sync(0xffffffffu, near && nowrap);
+                const unsigned m_tri = __ballot_sync(0xffffffffu, near && tri);
+                if (!m) continue;
+                swept += (unsigned)__popc(m);
+                // stream the surviving sub-blocks: unit n+1 is in flight (TMA) while unit n is swept
+                auto issue = [&](int bit, unsigned sq) {
+                    const int jbb = __shfl_sync(0xffffffffu, jb, bit & ~7);
+                    if (lane == 0) {
+                        const int st = (int)(sq & 1u);
+                        const size_t pj = (size_t)jbb * SEG_PAD + (size_t)(bit & 7) * 32;
+                        fh_mbar_expect_tx(&mbar[st], 32 * 16 + 32 * 4);
+                        fh_bulk_g2s(sJ + st * 32, A.atoms + pj, 32 * 16, &mbar[st]);
+                        fh_bulk_g2s(sO + st * 32, A.orig + pj, 32 * 4, &mbar[st]);
+                    }
+                };
+                issue(__ffs(m) - 1, seq);
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1u;
+                    if (m) issue(__ffs(m) - 1, seq + 1u);      // its stage was drained at the end of the previous unit
+                    const int st = (int)(seq & 1u);
+                    fh_mbar_wait(&mbar[st], (seq >> 1) & 1u);
+                    const uint32_t tag = (uint32_t)(st * 32) | (((m_tri >> bit) & 1u) ? 0x80u : 0u);
+                    if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
+                        sweep_unit<MODE, true, HASMIN, TABLE>(sJ + st * 32, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, tag, wp, W, g, tab,
+                                                              inv_bin, c0, sh, ov, sp);
+                    else
+                        sweep_unit<MODE, false, HASMIN, TABLE>(sJ + st * 32, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, tag, wp, W, g, tab,
+                                                               inv_bin, c0, sh, ov, sp);
+                    ++seq;
+                }
+            }
+            // ---- the CTA leaves the pair (or its 32-bit counters are due): counters -> global ordered histogram
+            __syncthreads();
+            const bool dirty = s_tasks > 0;
+            again = s_again != 0;
+            if (dirty) {
+                for (int c = tid; c < nsh; c += V2_THREADS) {
+                    const unsigned int cnt = sh[c];
+                    if (cnt) {
                         sh[c] = 0u;
                         const int slot = c / g.hs, b = c - slot * g.hs;
                         const long long at = ((slot >> 1) ? cells : 0) + (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-                        atomicAdd(&counts[at], (unsigned long long)v);
+                        atomicAdd(&A.counts[at], (unsigned long long)cnt);
                     }
                 }
             }
-            cur_slab = slab;
-            since_flush = 0;
-            sp.slab_ab = w.ea * nEl + w.eb; sp.slab_ba = w.eb * nEl + w.ea;
             __syncthreads();
-        }
-        if (it >= n_items) break;
-
-        // the I tile: coordinates in registers for the sweep, the full records in shared memory for the
-        // bin pass (made visible by the staging barrier below; the loop-top barrier protects the rewrite)
-        float xi[R], yi[R], zi[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float4 a = make_float4(__int_as_float(0x7FC00000), __int_as_float(0x7FC00000), __int_as_float(0x7FC00000),
-                                   __uint_as_float(PAD_META));     // NaN: never in range
-            uint32_t o = 0xFFFFFFFFu;
-            if (r < w.ni) {
-                const int p = w.i0 + r * SEG_PAD + tid;
-                a = atoms[p]; o = orig[p];
-            }
-            xi[r] = a.x; yi[r] = a.y; zi[r] = a.z;
-            sI[r * SEG_PAD + tid] = a; sIO[r * SEG_PAD + tid] = o;
-        }
-        const bool cross = (w.ea != w.eb);
-        const int bi = w.i0 / SEG_PAD;
-
-        // the item's surviving J blocks, staged two at a time
-        const bool same_el = (w.ea == w.eb);
-        for (int e = 0; e < item.z; e += 2) {
-            const int nb = (e + 1 < item.z) ? 2 : 1;
-            const int jb0 = (int)entries[item.y + e] * SEG_PAD;
-            const int jb1 = (nb == 2) ? (int)entries[item.y + e + 1] * SEG_PAD : jb0;
-            __syncthreads();                  // previous staged blocks fully consumed
-            sJ[tid] = atoms[jb0 + tid]; sO[tid] = orig[jb0 + tid];
-            if (nb == 2) { sJ[SEG_PAD + tid] = atoms[jb1 + tid]; sO[SEG_PAD + tid] = orig[jb1 + tid]; }
+            if (tid == 0) { s_tasks = 0; s_again = 0; }
             __syncthreads();
-            // second level: lanes 0-7 / 8-15 test the 32-record sub-blocks of the two staged blocks (every warp
-            // computes the same mask, so the CTA stays in step without exchanging it)
-            unsigned sub = 0xFFFFu;
-            if (cp.enabled) {
-                const int which = lane >> 3, sb = lane & 7;
-                bool nr = false;
-                if (which < nb) {
-                    const size_t at = 2 * ((size_t)nblocks + (size_t)((which ? jb1 : jb0) / SEG_PAD) * (SEG_PAD / 32) + sb);
-                    const float4 loJ = bbox[at], hiJ = bbox[at + 1];
-                    bool far = true;
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (r < w.ni) far = far && blocks_far(bbox[2 * (bi + r)], bbox[2 * (bi + r) + 1], loJ, hiJ, cp);
-                    nr = !far;
-                }
-                sub = __ballot_sync(0xffffffffu, nr);
-            }
-            if (nb == 1) sub &= 0xFFu;
-#pragma unroll 1
-            for (int b = 0; b < nb; ++b) {
-                const int jbb = b ? jb1 : jb0;
-                const bool tri = same_el && jbb < w.i0 + w.ni * SEG_PAD;      // J block inside the I tile: only p < q counts
-                sweep_block<MODE, R>(sJ + b * SEG_PAD, sO + b * SEG_PAD, jbb, xi, yi, zi, sI, sIO, w.i0, tri, cross, L, g,
-                                     (sub >> (8 * b)) & 0xFFu, lq, sh, ov, sp);
-            }
-            since_flush += (unsigned)(nb * w.ni);
-            swept += (unsigned)(__popc(sub & 0xFFFFu) * w.ni);
         }
     }
-    if (ov) atomicAdd(&stats[0], ov);
-    if (tid == 0 && swept) atomicAdd(&stats[1], swept);
+    if (ov) atomicAdd(&A.stats[0], ov);
+    if (lane == 0 && swept) atomicAdd(&A.stats[1], swept);
 }
 
 // counts (64-bit, SIGNED: the reference's running ordered arrays data-before+after may hold
@@ -675,29 +790,27 @@ __global__ void counts64_to_float_kernel(const unsigned long long *__restrict__ 
     if (c < cells2) out[c] = (float)(long long)counts[c];
 }
 
-size_t full_hist_smem_bytes(int hs, int R)
+static size_t full_hist_smem_bytes(int hs, bool table)
 {
-    const size_t cap = (R == 1) ? SweepShape<1>::CAP : SweepShape<4>::CAP;
-    return (sizeof(float4) + sizeof(uint32_t)) * (JS + (size_t)SEG_PAD * R) + sizeof(uint32_t) * cap * 256 +
-           sizeof(unsigned int) * 4 * (size_t)hs;
+    size_t s = (((size_t)4 * hs * 4 + 15) & ~(size_t)15) + (size_t)V2_WARPS * V2_WARP_BYTES;
+    if (table) s += (((size_t)hs + 1) * 8 + 15) & ~(size_t)15;
+    return s;
 }
 
-template <int MODE, int R>
-static int launch_full_t(cudaStream_t stream, int sm_count, const float4 *atoms, const uint32_t *orig, const float4 *bbox,
-                         const WorkItem *rows, const uint32_t *entries, const int4 *items, int n_items, int *next_item,
-                         const Lattice &L, const GridParams &g, const CullParams &cp, int nblocks, int nEl,
-                         unsigned long long *counts, unsigned long long *stats)
+template <int MODE, bool HASMIN, bool TABLE>
+static int launch_full_t(cudaStream_t stream, int sm_count, const SweepArgs &A)
 {
-    size_t smem = full_hist_smem_bytes(g.hs, R);
-    FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "histSize %d needs %zu B of shared memory per CTA (limit 200 KiB)", g.hs, smem);
-    auto kern = full_hist_kernel<MODE, R>;
+    const size_t smem = full_hist_smem_bytes(A.g.hs, TABLE);
+    FRMC_REQUIRE(smem <= 200 * 1024, FRMC_ELIMIT, "histSize %d needs %zu B of shared memory per CTA (limit 200 KiB)", A.g.hs, smem);
+    auto kern = full_hist_warp_kernel<MODE, HASMIN, TABLE>;
     FRMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    FRMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    FRMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, V2_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    int grid = std::min(n_items, sm_count * per_sm);
+    const long long tasks = (long long)A.n_items * (SEG_PAD / 32);
+    const int grid = (int)std::min<long long>((tasks + V2_WARPS - 1) / V2_WARPS, (long long)sm_count * per_sm);
     if (grid < 1) return FRMC_OK;
-    kern<<<grid, 256, smem, stream>>>(atoms, orig, bbox, rows, entries, items, n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
+    kern<<<grid, V2_THREADS, smem, stream>>>(A);
     FRMC_LAUNCH_CHECK();
     return FRMC_OK;
 }
@@ -716,8 +829,9 @@ static int ensure_capacity(T **buf, size_t *cap, size_t need, cudaStream_t strea
 
 void PairLists::release()
 {
-    cudaFree(row_ints); cudaFree(entries); cudaFree(items);
-    row_ints = nullptr; entries = nullptr; items = nullptr; row_cap = entries_cap = items_cap = 0;
+    cudaFree(row_ints); cudaFree(entries); cudaFree(items); cudaFree(pair_next); cudaFree(bin_table);
+    row_ints = nullptr; entries = nullptr; items = nullptr; pair_next = nullptr; bin_table = nullptr;
+    row_cap = entries_cap = items_cap = bin_cap = 0;
 }
 
 // Box pass and surviving-pair lists for `rows` under the culling parameters cp (bbox: 18 float4 per SEG_PAD
@@ -728,18 +842,17 @@ int build_pair_lists(cudaStream_t stream, const float4 *atoms, int64_t npad, flo
 {
     const int nblocks = (int)(npad / SEG_PAD);
     lists.n_entries = lists.n_items = 0;
+    lists.n_rows = n_rows;
     if (n_rows <= 0 || nblocks <= 0) return FRMC_OK;
-    if (cp.enabled) {
-        block_bbox_kernel<<<(nblocks * 32 + 255) / 256, 256, 0, stream>>>(atoms, nblocks, cp.pbc, bbox);
-        FRMC_LAUNCH_CHECK();
-    }
+    block_bbox_kernel<<<(nblocks * 32 + 255) / 256, 256, 0, stream>>>(atoms, nblocks, cp.pbc, bbox);
+    FRMC_LAUNCH_CHECK();
     // row scratch: cnt, items, start, item_start [n_rows each] + 2 totals
     int rc = ensure_capacity(&lists.row_ints, &lists.row_cap, (size_t)4 * n_rows + 2, stream);
     if (rc) return rc;
     int *row_cnt = lists.row_ints, *row_items = row_cnt + n_rows, *row_start = row_items + n_rows,
         *row_item_start = row_start + n_rows, *totals = row_item_start + n_rows;
     const int list_grid = (int)(((long long)n_rows * 32 + 255) / 256);
-    pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, nullptr, nullptr, nullptr, nullptr, 0);
+    pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, nullptr, nullptr, nullptr, nullptr, 0, lists.item_blocks);
     FRMC_LAUNCH_CHECK();
     scan2_kernel<<<1, 1024, 0, stream>>>(row_cnt, row_items, n_rows, row_start, row_item_start, totals);
     FRMC_LAUNCH_CHECK();
@@ -754,29 +867,66 @@ int build_pair_lists(cudaStream_t stream, const float4 *atoms, int64_t npad, flo
     rc = ensure_capacity(&lists.items, &lists.items_cap, (size_t)h_tot[1], stream);
     if (rc) return rc;
     pair_list_kernel<<<list_grid, 256, 0, stream>>>(rows, n_rows, bbox, cp, row_cnt, row_items, row_start, row_item_start,
-                                                    lists.entries, lists.items, 1);
+                                                    lists.entries, lists.items, 1, lists.item_blocks);
     FRMC_LAUNCH_CHECK();
     return FRMC_OK;
 }
 
-// Box pass, surviving-pair lists, then the sweep, on prepared device arrays.  next_item must be zeroed by the
-// caller (stream-ordered) before every launch; stats[0] accumulates edge-overflow events, stats[1] swept
-// (256 x 32) units.
-int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
+// Rows of one shard + the index of the first row of every element pair (rows are ordered by pair), packed into one
+// blob for the device: [n_rows WorkItem][n_pairs + 1 int, the last = n_rows].
+void pack_rows(const std::vector<WorkItem> &rows, std::vector<unsigned char> &blob, int &n_pairs)
+{
+    std::vector<int> first;
+    for (size_t r = 0; r < rows.size(); ++r)
+        if (r == 0 || rows[r].ea != rows[r - 1].ea || rows[r].eb != rows[r - 1].eb) first.push_back((int)r);
+    n_pairs = (int)first.size();
+    first.push_back((int)rows.size());
+    blob.resize(rows.size() * sizeof(WorkItem) + first.size() * sizeof(int));
+    if (!rows.empty()) memcpy(blob.data(), rows.data(), rows.size() * sizeof(WorkItem));
+    memcpy(blob.data() + rows.size() * sizeof(WorkItem), first.data(), first.size() * sizeof(int));
+}
+
+// Box pass, surviving-pair lists, bin-edge table, then the sweep, on prepared device arrays.  `rows` is the device
+// copy of a pack_rows() blob.  stats[0] accumulates edge-overflow events, stats[1] swept (32 x 32) units.
+int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *atoms, const uint32_t *orig,
+                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, int n_pairs, PairLists &lists,
                      const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
     CullParams cp = make_cull(L, mode, g);
     if (g_no_cull) cp.enabled = 0;
     const int nblocks = (int)(npad / SEG_PAD);
     if (n_rows <= 0 || nblocks <= 0) return FRMC_OK;
+    lists.item_blocks = V2_ITEM_BLOCKS;
     int rc = build_pair_lists(stream, atoms, npad, bbox, rows, n_rows, cp, lists);
     if (rc) return rc;
     if (lists.n_items == 0) return FRMC_OK;
+    const int max_pairs = FRMC_MAX_ELEMENTS * (FRMC_MAX_ELEMENTS + 1) / 2;
+    FRMC_REQUIRE(n_pairs >= 1 && n_pairs <= max_pairs, FRMC_EINVAL, "bad element-pair count %d", n_pairs);
+    if (!lists.pair_next) FRMC_CUDA(cudaMalloc((void **)&lists.pair_next, sizeof(int) * (max_pairs + 8)));
+    FRMC_CUDA(cudaMemsetAsync(lists.pair_next, 0, sizeof(int) * (max_pairs + 8), stream));
+    // the table replaces sqrt + divide in the bin pass when the grid is sane and it fits beside the counters
+    const bool table = (g.bin > 0.f) && std::isfinite(g.bin) && std::isfinite(g.rmin) && g.hs <= 4096;
+    if (table) {
+        if (lists.bin_cap < (size_t)g.hs + 1) {
+            if (lists.bin_table) { FRMC_CUDA(cudaStreamSynchronize(stream)); cudaFree(lists.bin_table); lists.bin_table = nullptr; }
+            FRMC_CUDA(cudaMalloc((void **)&lists.bin_table, sizeof(float2) * ((size_t)g.hs + 1)));
+            lists.bin_cap = (size_t)g.hs + 1;
+        }
+        bin_table_kernel<<<(g.hs + 1 + 127) / 128, 128, 0, stream>>>(g, lists.bin_table);
+        FRMC_LAUNCH_CHECK();
+    }
+    SweepArgs A;
+    A.atoms = atoms; A.orig = orig; A.bbox = bbox;
+    A.rows = rows; A.pair_first_row = reinterpret_cast<const int *>(rows + n_rows); A.row_item_start = lists.row_ints + 3 * (size_t)n_rows;
+    A.entries = lists.entries; A.items = lists.items; A.pair_next = lists.pair_next;
+    A.tab = lists.bin_table; A.counts = counts; A.stats = stats;
+    A.n_rows = n_rows; A.n_pairs = n_pairs; A.n_items = lists.n_items; A.nblocks = nblocks; A.nEl = nEl;
+    A.L = L; A.g = g; A.cp = cp;
+    const bool hasmin = g.t2min > 0.f;      // rmin <= 0: every non-NaN d2 passes the lower test
 #define FH_CASE(M)                                                                                         \
     case M:                                                                                                \
-        return (R == 4) ? launch_full_t<M, 4>(stream, sm_count, atoms, orig, bbox, rows, lists.entries, lists.items, lists.n_items, next_item, L, g, cp, nblocks, nEl, counts, stats) \
-                        : launch_full_t<M, 1>(stream, sm_count, atoms, orig, bbox, rows, lists.entries, lists.items, lists.n_items, next_item, L, g, cp, nblocks, nEl, counts, stats);
+        if (table) return hasmin ? launch_full_t<M, true, true>(stream, sm_count, A) : launch_full_t<M, false, true>(stream, sm_count, A); \
+        return hasmin ? launch_full_t<M, true, false>(stream, sm_count, A) : launch_full_t<M, false, false>(stream, sm_count, A);
     switch (mode) {
         FH_CASE(MODE_IBC)
         FH_CASE(MODE_ORTHO_FAST)
@@ -787,36 +937,6 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const f
 #undef FH_CASE
     set_error("unknown geometry mode %d", mode);
     return FRMC_EINVAL;
-}
-
-// Does block culling remove most of the sweep?  Estimated from the reach (maxDistance + one block
-// extent, both ways) against the cell heights / coordinate spans; decides the register tiling below.
-bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g)
-{
-    if (g_no_cull || n <= 0) return false;
-    const CullParams cp = make_cull(L, mode, g);
-    if (!cp.enabled) return false;
-    double span[3], vol = 1.0;
-    for (int c = 0; c < 3; ++c) {
-        span[c] = (mode == MODE_IBC) ? (double)hi[c] - (double)lo[c] : (double)cp.h[c];
-        if (!(span[c] > 0.0) || !std::isfinite(span[c])) return false;
-        vol *= span[c];
-    }
-    const double per_el = std::max(1.0, (double)n / std::max(1, nEl));
-    const double extent = cbrt(vol * (double)SEG_PAD / per_el);
-    const double reach = 2.0 * ((double)g.rmax + extent);
-    double frac = 1.0;
-    for (int c = 0; c < 3; ++c) frac *= std::min(1.0, reach / span[c]);
-    return frac < 0.5;
-}
-
-// Tile-shape heuristic: returns R, the register atoms per thread (I-tile = 256*R).  R = 4 amortises the shared-
-// memory load of a J record over four pairs (23.4 issue slots per pair instead of 26) and is right when
-// every block pair has to be swept; when culling bites, R = 1 keeps the culled unit at one 256-atom block
-// (about 2.5x fewer pairs swept than with a 1024-atom I-tile).
-int choose_tiling(int64_t npad, bool sparse)
-{
-    return (npad >= 32768 && !sparse) ? 4 : 1;
 }
 
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2)
@@ -868,9 +988,8 @@ extern "C" int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int 
     int rc = build_layout(coords.data(), n, mol.data(), el, nEl, 1, lay);
     if (rc) return rc;
     (void)sm_count;
-    const int R = choose_tiling(lay.npad, false);
     std::vector<WorkItem> items;
-    build_rows(lay, R, shard, nshards, items);
+    build_rows(lay, 1, shard, nshards, items);
     auto real_in = [&](int e, int64_t a, int64_t b) -> int64_t {   // real atoms of segment e inside positions [a, b)
         const int64_t end = lay.seg_start[e] + lay.seg_count[e];
         return std::max<int64_t>(0, std::min(b, end) - std::max(a, lay.seg_start[e]));
@@ -926,29 +1045,30 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     GridParams g = make_grid(rmin, rmax, bin, hs);
     int mode = choose_mode_from_bounds(L.b, isPBC, lay.lo, lay.hi);
-    const int R = choose_tiling(lay.npad, culling_pays(L, mode, lay.lo, lay.hi, lay.n, nEl, g));
     std::vector<WorkItem> items;
-    build_rows(lay, R, shard, nshards, items);
+    build_rows(lay, 1, shard, nshards, items);
+    std::vector<unsigned char> blob;
+    int n_pairs = 0;
+    pack_rows(items, blob, n_pairs);
 
     float4 *d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float) * 4 * (size_t)lay.npad);
     uint32_t *d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);
-    WorkItem *d_items = (WorkItem *)ctx_buffer(c, 2, sizeof(WorkItem) * items.size());
+    WorkItem *d_items = (WorkItem *)ctx_buffer(c, 2, blob.size());
     unsigned long long *d_counts = (unsigned long long *)ctx_buffer(c, 4, sizeof(unsigned long long) * (2 * cells + 3));
     float4 *d_bbox = (float4 *)ctx_buffer(c, 3, sizeof(float4) * 18 * (size_t)(lay.npad / SEG_PAD + 1));
     float *d_out = (float *)ctx_buffer(c, 5, sizeof(float) * 2 * cells);
     if (!d_atoms || !d_orig || !d_items || !d_counts || !d_out || !d_bbox) return FRMC_ENOMEM;
     unsigned long long *d_ov = d_counts + 2 * cells;
-    int *d_next = (int *)(d_counts + 2 * cells + 2);
     FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (2 * cells + 3), c->stream));
     if (lay.npad > 0) {
         FRMC_CUDA(cudaMemcpyAsync(d_atoms, lay.rec.data(), sizeof(float) * 4 * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
         FRMC_CUDA(cudaMemcpyAsync(d_orig, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
     }
     if (!items.empty()) {
-        FRMC_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
+        FRMC_CUDA(cudaMemcpyAsync(d_items, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
         static PairLists stateless_lists[64];          // per device, grow-only, like the context's scratch buffers
-        rc = full_hist_launch(c->stream, c->sm_count, mode, R, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(),
-                              stateless_lists[c->dev & 63], d_next, L, g, nEl, d_counts, d_ov);
+        rc = full_hist_launch(c->stream, c->sm_count, mode, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), n_pairs,
+                              stateless_lists[c->dev & 63], L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);

@@ -66,6 +66,11 @@ struct PairLists {
     int4 *items = nullptr;          // {row, first entry, blocks, -}
     size_t row_cap = 0, entries_cap = 0, items_cap = 0;
     int n_entries = 0, n_items = 0; // of the last launch
+    int n_rows = 0;                 // rows of the last launch (row_ints + 3 * n_rows = first item of every row)
+    int item_blocks = 8;            // surviving blocks per item
+    int *pair_next = nullptr;       // full histogram: one task counter per element pair (+ scratch), zeroed per launch
+    float2 *bin_table = nullptr;    // full histogram: (T[b], T[b+1]) d^2 thresholds of the bin edges
+    size_t bin_cap = 0;
     void release();
 };
 

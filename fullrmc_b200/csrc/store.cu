@@ -26,11 +26,10 @@
 namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
-int full_hist_launch(cudaStream_t stream, int sm_count, int mode, int R, const float4 *atoms, const uint32_t *orig,
-                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, PairLists &lists, int *next_item,
+int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *atoms, const uint32_t *orig,
+                     int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, int n_pairs, PairLists &lists,
                      const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
-int choose_tiling(int64_t npad, bool sparse);
-bool culling_pays(const Lattice &L, int mode, const float lo[3], const float hi[3], int64_t n, int nEl, const GridParams &g);
+void pack_rows(const std::vector<WorkItem> &rows, std::vector<unsigned char> &blob, int &n_pairs);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
 
 // ------------------------------------------------------------------ device-side descriptors
@@ -2031,7 +2030,8 @@ struct frmc_store {
     WorkItem *d_items = nullptr;     // rows of the pair list (I tile x J range of an element pair)
     PairLists lists;                 // device-built surviving block pairs, cut into items
     int n_items = 0, R = 1;
-    int items_shard = -1, items_nshards = -1, items_sparse = -1;   // which slice / tiling of the work list d_items holds
+    int items_shard = -1, items_nshards = -1;   // which slice of the row list d_items holds
+    int n_pairs = 0;                            // element pairs present in that slice
     HostLayout lay;                  // rec freed after upload; segments + inverse permutation kept
     int *d_next = nullptr;
     unsigned long long *d_overflow = nullptr;   // [0] edge-overflow events, [1] block pairs swept by the last compute_data
@@ -2169,18 +2169,17 @@ static int upload_layout(frmc_store *s, const float *coords)
     return FRMC_OK;
 }
 
-static int upload_items(frmc_store *s, int shard, int nshards, bool sparse)
+static int upload_items(frmc_store *s, int shard, int nshards)
 {
-    if (s->d_items && s->items_shard == shard && s->items_nshards == nshards && s->items_sparse == (int)sparse) return FRMC_OK;
+    if (s->d_items && s->items_shard == shard && s->items_nshards == nshards) return FRMC_OK;
     std::vector<WorkItem> items;
-    s->items_sparse = (int)sparse;
-    s->R = choose_tiling(s->npad, sparse);
-    build_rows(s->lay, s->R, shard, nshards, items);
+    build_rows(s->lay, 1, shard, nshards, items);
+    std::vector<unsigned char> blob;
+    pack_rows(items, blob, s->n_pairs);
     if (s->d_items) { cudaFree(s->d_items); s->d_items = nullptr; }
     s->n_items = (int)items.size();
-    FRMC_CUDA(cudaMalloc(&s->d_items, sizeof(WorkItem) * std::max<size_t>(items.size(), 1)));
-    if (!items.empty())
-        FRMC_CUDA(cudaMemcpyAsync(s->d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaMalloc(&s->d_items, std::max<size_t>(blob.size(), 16)));
+    FRMC_CUDA(cudaMemcpyAsync(s->d_items, blob.data(), blob.size(), cudaMemcpyHostToDevice, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     s->items_shard = shard; s->items_nshards = nshards;
     return FRMC_OK;
@@ -2777,7 +2776,7 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     };
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create");
     if (upload_layout(s, coords)) return fail("layout upload");
-    if (upload_items(s, 0, 1, false)) return fail("work list upload");
+    if (upload_items(s, 0, 1)) return fail("work list upload");
     if (cudaMalloc(&s->d_next, sizeof(int) * 4) != cudaSuccess) return fail("alloc");
     if (cudaMalloc(&s->d_overflow, 2 * sizeof(unsigned long long)) != cudaSuccess) return fail("alloc");
     cudaMemset(s->d_overflow, 0, 2 * sizeof(unsigned long long));
@@ -3098,9 +3097,7 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
     int rc = flush_pending(s);
     if (rc) return rc;
     const int mode = current_mode(s, nullptr, nullptr);
-    bool sparse = !s->grids.empty();          // R = 1 tiling only when culling pays for every grid
-    for (auto &g : s->grids) sparse = sparse && culling_pays(s->L, mode, s->lo, s->hi, s->n, s->nEl, g.dev.g);
-    rc = upload_items(s, shard, nshards, sparse);
+    rc = upload_items(s, shard, nshards);
     if (rc) return rc;
     for (auto &g : s->grids) {
         FRMC_CUDA(cudaMemsetAsync(g.dev.counts, 0, sizeof(unsigned long long) * 2 * g.dev.cells, s->stream));
@@ -3109,8 +3106,8 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
         if (s->n_items > 0) {
             cudaEvent_t t0 = timing_begin(s);
             FRMC_CUDA(cudaMemsetAsync(s->d_overflow + 1, 0, sizeof(unsigned long long), s->stream));
-            rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->R, s->d_atoms, s->d_orig, s->npad, s->d_bbox, s->d_items,
-                                  s->n_items, s->lists, s->d_next, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
+            rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->d_atoms, s->d_orig, s->npad, s->d_bbox, s->d_items,
+                                  s->n_items, s->n_pairs, s->lists, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
             if (rc) return rc;
             timing_end(s, TIME_FULL, t0);
         }
@@ -3532,7 +3529,7 @@ uint64_t frmc_store_swept_pairs(frmc_store *s)
     cudaSetDevice(s->dev);
     cudaMemcpyAsync(&blocks, s->d_overflow + 1, sizeof(blocks), cudaMemcpyDeviceToHost, s->stream);
     cudaStreamSynchronize(s->stream);
-    return blocks * (unsigned long long)SEG_PAD * 32ull;
+    return blocks * 1024ull;
 }
 
 }  // extern "C"

@@ -83,6 +83,13 @@ def q_values(qmin=0.5, qmax=20.0, nq=400):
     return np.linspace(qmin, qmax, nq).astype(FLOAT_TYPE)
 
 
+def smooth_target(n, seed, center):
+    """experimental stand-in for the synthetic configs: smooth noise around the ideal-gas value
+    (0 for G(r), 1 for S(Q)), so that Metropolis acceptance is mixed rather than degenerate"""
+    rng = np.random.default_rng(seed)
+    return (center + 0.02 * np.convolve(rng.standard_normal(n + 20), np.ones(21) / 21.0, "valid")).astype(np.float32)
+
+
 def translation_proposals(system, n_moves, seed, sigma=0.1):
     """Single-atom Gaussian translations (sigma in Angstrom) expressed in box coordinates:
     (atom index, movedBox[1,3]) pairs, generated up front so GPU and CPU arms see the same moves.

@@ -92,15 +92,20 @@ def fit_total(c, kind, E):
 ONLY = set(sys.argv[1:])        # optional case names on the command line: regenerate just those
 
 
-def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sigma, out_dir):
+def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sigma, out_dir, recipe=None):
+    """recipe: (generator name, n, seed) of fullrmc_b200.synthetic for systems too large to store; the fixture then
+    holds the recipe instead of the per-atom arrays and the tests regenerate them (tests/test_golden_large.py)"""
     if ONLY and name not in ONLY:
         return
     box, basis, isPBC, mol, el, elements = arrays
     E = H.fake_engine(fullrmc, box, basis, isPBC, mol, el, elements)
     constraints = make_constraints(E)
-    out = dict(boxCoords=box.copy(), basis=basis, isPBC=np.bool_(isPBC), moleculeIndex=mol, elementIndex=el,
-               elements=np.array(elements), volume=np.float32(E.volume), numberDensity=np.float32(E.numberDensity),
-               n_constraints=np.int32(len(constraints)))
+    out = dict(basis=basis, isPBC=np.bool_(isPBC), elements=np.array(elements), volume=np.float32(E.volume),
+               numberDensity=np.float32(E.numberDensity), n_constraints=np.int32(len(constraints)))
+    if recipe is None:
+        out.update(boxCoords=box.copy(), moleculeIndex=mol, elementIndex=el)
+    else:
+        out.update(recipe_name=np.array(recipe[0]), recipe_n=np.int64(recipe[1]), recipe_seed=np.int64(recipe[2]))
     for ci, (c, kind) in enumerate(constraints):
         H.attach(E, c)
         for k, v in describe(c, kind).items():
@@ -170,7 +175,8 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
     for ci in shaped:
         out["c%d/shape_steps" % ci] = np.array([t for t, _ in shape_log[ci]], np.int32)
         out["c%d/shape_arrays" % ci] = np.array([a for _, a in shape_log[ci]], np.float32)
-    out["final_boxCoords"] = np.asarray(E.boxCoordinates, np.float32).copy()
+    if recipe is None:
+        out["final_boxCoords"] = np.asarray(E.boxCoordinates, np.float32).copy()
     path = os.path.join(out_dir, "constraints_%s.npz" % name)
     np.savez_compressed(path, **out)
     print("%-10s %5d atoms, %d constraints, %d steps (%d accepted), start chi2 %s -> %s   [%d KiB]" % (

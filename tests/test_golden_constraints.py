@@ -27,8 +27,31 @@ NAMES = ["niti", "thf", "siox", "synth", "niti_sf", "synth_sf", "siox_shape"]   
 Z = {"o": 8.0, "si": 14.0, "ti": 22.0, "ni": 28.0, "zr": 40.0, "c": 6.0, "h": 1.0}
 
 
+class _Golden(dict):
+    """the fixture as a dict with the NpzFile's ``files`` attribute"""
+
+    @property
+    def files(self):
+        return list(self.keys())
+
+
 def _load(golden_dir, name):
-    return np.load(os.path.join(golden_dir, "constraints_%s.npz" % name))
+    """A trajectory fixture.  Fixtures of the large synthetic systems (tests/gen_golden_large.py) hold the recipe of
+    fullrmc_b200.synthetic instead of the per-atom arrays; those, and the final coordinates, are rebuilt here."""
+    z = np.load(os.path.join(golden_dir, "constraints_%s.npz" % name))
+    g = _Golden((k, z[k]) for k in z.files)
+    if "recipe_name" in g:
+        from fullrmc_b200 import synthetic
+        system = getattr(synthetic, str(g["recipe_name"]))(int(g["recipe_n"]), int(g["recipe_seed"]))
+        assert np.array_equal(system.basis, g["basis"])
+        g["boxCoords"], g["moleculeIndex"], g["elementIndex"] = system.boxCoords, system.moleculeIndex, system.elementIndex
+        final = system.boxCoords.copy()
+        for s in range(g["steps/idx"].shape[0]):
+            if bool(g["steps/accepted"][s]):
+                k = int(g["steps/k"][s])
+                final[g["steps/idx"][s, :k]] = g["steps/moved"][s, :k]          # Engine.py:3337-3338
+        g["final_boxCoords"] = final
+    return g
 
 
 def _constraint_desc(g, ci):
