@@ -274,7 +274,7 @@ void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vecto
 
 // ------------------------------------------------------------------ the sweep
 // Work unit of the sweep: 32 I records (one per lane of a warp) x one 32-record J sub-block.
-static const int V2_THREADS = 256;        // 8 warps per CTA share one set of counters
+static const int V2_THREADS = 384;        // 12 warps per CTA share one set of counters (2 CTAs per SM at histSize 1000)
 static const int V2_WARPS = V2_THREADS / 32;
 static const int V2_ITEM_BLOCKS = 4;      // surviving J blocks per item: 8 tasks (one per I sub-block) of <= 32 units each
 static const int V2_CAP = 24;             // hit-queue entries per lane (8 bytes each); drained after every unit
@@ -335,56 +335,110 @@ struct SpillTarget {
     int slab_ab, slab_ba;
 };
 
-// Bin index of an in-range d2 without sqrt and divide: tab[b] = (T[b], T[b+1]), T[b] the smallest fp32 d2 whose
-// reference bin (int)((sqrt(d2) - rmin) / bin) is >= b (bin_table_kernel: exact search on that very expression,
-// which is monotone in d2).  An approximate sqrt gives a guess at most one bin off; the thresholds decide.
-__device__ __forceinline__ int bin_from_table(float d2, const float2 *__restrict__ tab, float inv_bin, float c0, int hs)
+// 32-bit shared-window accesses: the bin pass addresses the queue, the staged J records and the bin-edge table with
+// plain registers (the compiler otherwise rebuilds the generic->shared base in the uniform datapath at every use)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    float s;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2));
-    int b = __float2int_rz(__fmaf_rn(s, inv_bin, c0));
-    b = max(0, min(b, hs));
-    float2 t = tab[b];
-    while (d2 < t.x) t = tab[--b];
-    while (d2 >= t.y) t = tab[++b];
-    return b;
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f64(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
 }
 
-struct WarpCtx {                  // what the bin pass needs, all warp-uniform or lane-private registers
-    const float4 *sJ;             // [2][32] staged J records
-    const uint32_t *sO;           // [2][32] their original indexes
-    const uint2 *lq;              // this lane's queue column (stride 32 entries)
-    uint32_t w0;                  // shared-window address of lq
+struct WarpCtx {                  // what the bin pass needs: warp-uniform or lane-private registers
+    uint32_t w0;                  // shared address of this lane's queue column (entries 256 bytes apart)
+    uint32_t o_off;               // shared address of a J record's original index = (tag >> 2) + o_off
+    uint32_t tag0;                // tag of staged record 0 (what a dead queue slot is read as)
+    uint32_t sh_addr, tab_addr;   // shared addresses of the counters and of the bin-edge table
     uint32_t mi, oi;              // the lane's own I record: meta, original index
+    uint32_t off_inter, off_swap; // byte offsets of the inter-molecular / J-first counter slabs (2 hs, hs counters)
     bool cross;                   // different elements: the ordered slot depends on the original order
 };
 
-// every lane bins its own queue (d2 kept from the sweep: nothing is recomputed)
+// the rare events of the bin pass, kept out of line (the exact sqrt and divide are long): an edge overflow
+// (bin index == histSize because of fp32 rounding, or a grid whose maxDistance lies beyond rmin + hs * bin)
+__device__ __noinline__ void bin_overflow(float d2, int swap, int inter, GridParams g, SpillTarget sp)
+{
+    const int b = bin_index(d2, g);
+    const long long flat = (long long)(swap ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+    if (g.spill && b >= 0 && flat < sp.cells) atomicAdd(&sp.counts[(inter ? sp.cells : 0) + flat], 1ull);
+}
+
+// Bin index of an in-range d2 without sqrt and divide: tab[b] = (T[b], T[b+1]), T[b] the smallest fp32 d2 whose
+// reference bin (int)((sqrt(d2) - rmin) / bin) is >= b (bin_table_kernel: exact search on that very expression,
+// which is monotone in d2).  An approximate sqrt gives a guess, the thresholds decide: one +-1 step covers every
+// regular grid, and the corrected bin is verified against its own edges (walking on if a degenerate grid needs it).
+__device__ __noinline__ int bin_walk(float d2, int b, uint32_t tab_addr)
+{
+    float2 t = lds_f64(tab_addr + 8u * (uint32_t)b);
+    while (d2 < t.x) t = lds_f64(tab_addr + 8u * (uint32_t)(--b));
+    while (d2 >= t.y) t = lds_f64(tab_addr + 8u * (uint32_t)(++b));
+    return b;
+}
+
+// every lane bins its own queue (d2 kept from the sweep: nothing is recomputed), four entries per trip: the
+// shared-memory loads of the four first (queue, J meta / index, bin edges), then the four counter updates
 template <bool TABLE>
-__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, const GridParams &g, const float2 *__restrict__ tab,
-                                            float inv_bin, float c0, unsigned int *__restrict__ sh, unsigned long long &ov,
-                                            const SpillTarget &sp)
+__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, const GridParams &g, float inv_bin, float c0,
+                                            unsigned long long &ov, const SpillTarget &sp)
 {
     const int n = (int)((wp - W.w0) >> 8);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < nmax; ++k) {
-        if (k < n) {
-            const uint2 e = W.lq[k * 32];
-            const float d2 = __uint_as_float(e.x);
-            const int q = (int)(e.y & 63u);                    // stage * 32 + record
-            if (!(e.y & 0x80u) || lane < (q & 31)) {           // unit on the diagonal of its block: only p < q counts
-                const uint32_t mj = __float_as_uint(W.sJ[q].w);
-                int slot = ((W.mi >> 8) == (mj >> 8)) ? 0 : 2;  // bit 1: inter-molecular
-                if (W.cross && W.oi > W.sO[q]) slot |= 1;       // bit 0: the J atom comes first in original order
-                int b = TABLE ? bin_from_table(d2, tab, inv_bin, c0, g.hs) : bin_index(d2, g);
-                if ((unsigned)b < (unsigned)g.hs) {
-                    atomicAdd(&sh[slot * g.hs + b], 1u);
+    const int hs = g.hs;
+    for (int k = 0; k < nmax; k += 4) {
+        float d2[4];
+        uint32_t tag[4], off[4];
+        int b[4];
+        bool live[4], inter[4], swp[4];
+        float2 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            live[j] = (k + j < n);
+            uint2 e = make_uint2(0u, W.tag0);                      // a dead slot reads a valid J record
+            if (live[j]) e = lds_u64(W.w0 + (uint32_t)(k + j) * 256u);
+            d2[j] = __uint_as_float(e.x);
+            tag[j] = e.y;                                          // shared address of the J record's meta word
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t mj = lds_u32(tag[j]);
+            inter[j] = ((W.mi ^ mj) >= 256u);                      // molecule ranks differ
+            swp[j] = W.cross && W.oi > lds_u32((tag[j] >> 2) + W.o_off);                     // the J atom comes first in original order
+            off[j] = (inter[j] ? W.off_inter : 0u) + (swp[j] ? W.off_swap : 0u);
+            if (TABLE) {
+                float s;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2[j]));
+                b[j] = max(0, min(__float2int_rz(__fmaf_rn(s, inv_bin, c0)), hs));
+                t[j] = lds_f64(W.tab_addr + 8u * (uint32_t)b[j]);
+            } else {
+                b[j] = live[j] ? bin_index(d2[j], g) : 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int bb = b[j];
+            if (TABLE) {
+                bb += (d2[j] >= t[j].y) ? 1 : 0;
+                bb -= (d2[j] < t[j].x) ? 1 : 0;
+                if (live[j] && bb != b[j]) bb = bin_walk(d2[j], bb, W.tab_addr);        // a few percent of the hits
+            }
+            if (live[j]) {
+                if ((unsigned)bb < (unsigned)hs) {
+                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(W.sh_addr + off[j] + 4u * (uint32_t)bb) : "memory");
                 } else {
                     ++ov;
-                    if (TABLE) b = bin_index(d2, g);            // the table stops at histSize; the spill needs the real index
-                    const long long flat = (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-                    if (g.spill && b >= 0 && flat < sp.cells) atomicAdd(&sp.counts[((slot & 2) ? sp.cells : 0) + flat], 1ull);
+                    bin_overflow(d2[j], swp[j], inter[j], g, sp);
                 }
             }
         }
@@ -393,19 +447,34 @@ __device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, cons
     __syncwarp();
 }
 
-// one staged J sub-block (32 records) against the lane's I atom; hits are pushed as (d2, tag + q): a predicated
-// 8-byte store into the lane's own queue column and a predicated pointer bump -- no branch, no vote
-template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE>
-__device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float xi, float yi, float zi, const Lattice &Lc,
-                                           float t2min, float t2max, uint32_t tag, uint32_t &wp, const WarpCtx &W,
-                                           const GridParams &g, const float2 *__restrict__ tab, float inv_bin, float c0,
-                                           unsigned int *__restrict__ sh, unsigned long long &ov, const SpillTarget &sp)
+// one staged J sub-block (32 records) against the lane's I atom; hits are pushed as (d2, shared address of the J
+// record's meta word): a predicated 8-byte store into the lane's own queue column and a predicated pointer bump --
+// no branch, no vote.  TRI (the unit on the diagonal of the I block): only p < q counts, i.e. lane < record.
+template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE, bool TRI>
+__device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, uint32_t tag, float xi, float yi, float zi,
+                                           const Lattice &Lc, float t2min, float t2max, uint32_t &wp, const WarpCtx &W,
+                                           const GridParams &g, float inv_bin, float c0, unsigned long long &ov, const SpillTarget &sp)
 {
     Lattice L = Lc;               // lattice in plain registers: from the constant bank the compiler re-reads it every iteration
     if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
         asm volatile("" : "+f"(L.b[0]), "+f"(L.b[4]), "+f"(L.b[8]));
     }
     asm volatile("" : "+f"(t2min), "+f"(t2max));
+    if constexpr (TRI) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll 1
+        for (int q = 1; q < 32; ++q) {
+            const float4 a = sJu[q];
+            const float d2 = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a.x, a.y, a.z, L);
+            if ((!HASMIN || d2 >= t2min) && (d2 < t2max) && lane < q) {
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2)), "r"(tag + 16u * (uint32_t)q) : "memory");
+                wp += 256u;
+            }
+            if (q == 15) { __syncwarp(); drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp); }
+        }
+        __syncwarp();
+        drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp);
+    } else {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -421,7 +490,7 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float
             for (int u = 0; u < 8; ++u) {
                 if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
                     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])),
-                                 "r"(tag + (uint32_t)(half * 16 + c * 8 + u)) : "memory");
+                                 "r"(tag + 16u * (uint32_t)(half * 16 + c * 8 + u)) : "memory");
                     wp += 256u;
                 }
             }
@@ -429,7 +498,8 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float
         // the queue holds 24 entries per lane: after the first 16 records it is emptied only if a lane has more than 8
         if (half == 0 && !__any_sync(0xffffffffu, wp > W.w0 + 8u * 256u)) continue;
         __syncwarp();
-        drain_queue<TABLE>(wp, W, g, tab, inv_bin, c0, sh, ov, sp);
+        drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp);
+    }
     }
 }
 
@@ -587,7 +657,7 @@ __global__ void __launch_bounds__(1024) scan2_kernel(const int *__restrict__ a, 
 // (int)((sqrt(d2) - rmin) / bin) -- evaluated with the very IEEE operations of bin_index() -- is >= b, +inf when there
 // is none; the expression is monotone in d2 (sqrt, subtraction, division by a positive bin and truncation all are),
 // so a bisection over the ordered bit patterns of the positive floats finds it exactly.  tab[b] = (T[b], T[b+1]),
-// b = 0..hs, with T[0] = -inf and T[hs+1] = +inf: bin_from_table() returns hs for the edge-overflow events.
+// b = 0..hs, with T[0] = -inf and T[hs+1] = +inf: the bin pass arrives at hs for the edge-overflow events.
 __global__ void bin_table_kernel(GridParams g, float2 *__restrict__ tab)
 {
     const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -623,7 +693,7 @@ struct SweepArgs {
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
 // stats[0] += edge overflow events, stats[1] += (32 I records x 32 J records) units actually swept.
 template <int MODE, bool HASMIN, bool TABLE>
-__global__ void __launch_bounds__(V2_THREADS, 3) full_hist_warp_kernel(const SweepArgs A)
+__global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const SweepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridParams &g = A.g;
@@ -662,9 +732,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3) full_hist_warp_kernel(const Swe
     const int p0 = s_p0;
 
     WarpCtx W;
-    W.sJ = sJ; W.sO = sO;
-    W.lq = reinterpret_cast<const uint2 *>(wbase) + lane;
-    W.w0 = fh_smem_u32(W.lq);
+    W.w0 = fh_smem_u32(wbase) + 8u * (uint32_t)lane;
+    const uint32_t sJ_addr = fh_smem_u32(sJ);
+    W.o_off = fh_smem_u32(sO) - ((sJ_addr + 12u) >> 2);
+    W.tag0 = sJ_addr + 12u;
+    W.sh_addr = fh_smem_u32(sh); W.tab_addr = fh_smem_u32(tab);
+    W.off_inter = 8u * (uint32_t)g.hs; W.off_swap = 4u * (uint32_t)g.hs;
+    W.mi = 0u; W.oi = 0u; W.cross = false;
     uint32_t wp = W.w0;
     const float inv_bin = TABLE ? __frcp_rn(g.bin) : 0.f, c0 = TABLE ? -g.rmin * inv_bin : 0.f;
     unsigned long long ov = 0, swept = 0;
@@ -746,13 +820,18 @@ __global__ void __launch_bounds__(V2_THREADS, 3) full_hist_warp_kernel(const Swe
                     if (m) issue(__ffs(m) - 1, seq + 1u);      // its stage was drained at the end of the previous unit
                     const int st = (int)(seq & 1u);
                     fh_mbar_wait(&mbar[st], (seq >> 1) & 1u);
-                    const uint32_t tag = (uint32_t)(st * 32) | (((m_tri >> bit) & 1u) ? 0x80u : 0u);
-                    if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
-                        sweep_unit<MODE, true, HASMIN, TABLE>(sJ + st * 32, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, tag, wp, W, g, tab,
-                                                              inv_bin, c0, sh, ov, sp);
-                    else
-                        sweep_unit<MODE, false, HASMIN, TABLE>(sJ + st * 32, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, tag, wp, W, g, tab,
-                                                               inv_bin, c0, sh, ov, sp);
+                    const uint32_t tag = sJ_addr + 12u + (uint32_t)st * 512u;      // shared address of record 0's meta word
+                    const float4 *sJu = sJ + st * 32;
+                    if ((m_tri >> bit) & 1u) {
+                        if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
+                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                        else
+                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                    } else if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u)) {
+                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                    } else {
+                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                    }
                     ++seq;
                 }
             }

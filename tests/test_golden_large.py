@@ -51,7 +51,7 @@ def test_fixture_rows_match_the_oracle(name, golden_dir, orc):
 @pytest.mark.parametrize("name", NAMES)
 def test_full_histogram_at_benchmark_size(name, golden_dir):
     """culled, un-culled, 8-shard sum, the rows entry point and the store path against the fixture"""
-    import fullrmc_b200
+    from fullrmc_b200 import _lib as fullrmc_b200
     from fullrmc_b200.Core import pairs_histograms as ph
     from fullrmc_b200.store import DeviceStore
     if not _have(golden_dir, "full_%s.npz" % name):
