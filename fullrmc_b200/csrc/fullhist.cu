@@ -122,6 +122,19 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
             rank[i] = (int32_t)(std::lower_bound(keys.begin(), keys.end(), mol[i]) - keys.begin());
     }
 
+    {
+        // largest spread of a molecule in original indexes: the sweep treats pairs farther apart than this as
+        // inter-molecular without looking at their molecule indexes
+        int32_t max_id = -1;
+        for (int64_t i = 0; i < n; ++i) { const int32_t id = direct ? mol[i] : rank[i]; if (id > max_id) max_id = id; }
+        std::vector<int32_t> first((size_t)max_id + 1, -1);
+        int64_t span = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t &f = first[(size_t)(direct ? mol[i] : rank[i])];
+            if (f < 0) f = (int32_t)i; else span = std::max<int64_t>(span, i - f);
+        }
+        out.mol_span = (uint32_t)span;
+    }
     lap("count+mol");
     out.rec.resize((size_t)out.npad * 4);
     out.orig.resize((size_t)out.npad);
@@ -277,11 +290,11 @@ void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vecto
 static const int V2_THREADS = 384;        // 12 warps per CTA share one set of counters (2 CTAs per SM at histSize 1000)
 static const int V2_WARPS = V2_THREADS / 32;
 static const int V2_ITEM_BLOCKS = 4;      // surviving J blocks per item: 8 tasks (one per I sub-block) of <= 32 units each
-static const int V2_CAP = 24;             // hit-queue entries per lane (8 bytes each); drained after every unit
+static const int V2_CAP = 24;             // hit-queue entries per lane (8 bytes each); emptied when a lane holds more than CAP - 16
 static const int V2_TASK_LIMIT = 65536;   // tasks a CTA bins into its 32-bit counters between two flushes (32768 hits each at most)
-// per-warp shared memory: queue [V2_CAP][32] uint2, J ring [2][32] float4, J original indexes [2][32] u32, 2 mbarriers
+// per-warp shared memory: queue [V2_CAP][32] uint2, J ring [2][32] float4, 2 mbarriers
 static const int V2_Q_BYTES = V2_CAP * 32 * 8;
-static const int V2_WARP_BYTES = V2_Q_BYTES + 2 * 32 * 16 + 2 * 32 * 4 + 32;
+static const int V2_WARP_BYTES = V2_Q_BYTES + 2 * 32 * 16 + 32;
 
 __device__ __forceinline__ unsigned fh_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fh_mbar_init(unsigned long long *bar, unsigned count)
@@ -327,22 +340,25 @@ __device__ __forceinline__ float dist2_unit(float xi, float yi, float zi, float 
     return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
 }
 
-// where an overflowing event goes when the reference's unchecked write is reproduced: straight to the
-// global ordered histogram (rare: a pair within an ulp of maxDistance)
-struct SpillTarget {
-    unsigned long long *counts;   // [2][nEl*nEl][hs]
-    long long cells;
-    int slab_ab, slab_ba;
-};
-
-// 32-bit shared-window accesses: the bin pass addresses the queue, the staged J records and the bin-edge table with
-// plain registers (the compiler otherwise rebuilds the generic->shared base in the uniform datapath at every use)
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+// The sweep reads SWEEP RECORDS {x, y, z, original index} (sweep_records_kernel: the store's records with the
+// original index in place of the meta word).  A hit is queued as (d2, original index of the J atom) -- both already
+// sit in registers, the d2 just computed and the last word of the J record -- so the push is a predicated 8-byte
+// store and a predicated pointer bump, and the bin pass needs nothing else from the J side:
+//   * ordered slot of a cross-element pair: original index of I against that of J;
+//   * intra / inter: atoms of one molecule lie within `mol_span` original indexes of each other (the largest spread
+//     of a molecule, found on the host), so a pair farther apart than that is inter-molecular without looking anything
+//     up; the few candidates go through the exact comparison of the molecule indexes (slow path).
+__global__ void sweep_records_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, long long npad,
+                                     float4 *__restrict__ out)
 {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npad) return;
+    float4 a = atoms[p];
+    a.w = __uint_as_float(orig[p]);
+    out[p] = a;
 }
+
+// 32-bit shared-window accesses: the bin pass addresses the queue and the bin-edge table with plain registers
 __device__ __forceinline__ uint2 lds_u64(uint32_t addr)
 {
     uint2 v;
@@ -356,110 +372,115 @@ __device__ __forceinline__ float2 lds_f64(uint32_t addr)
     return v;
 }
 
-struct WarpCtx {                  // what the bin pass needs: warp-uniform or lane-private registers
-    uint32_t w0;                  // shared address of this lane's queue column (entries 256 bytes apart)
-    uint32_t o_off;               // shared address of a J record's original index = (tag >> 2) + o_off
-    uint32_t tag0;                // tag of staged record 0 (what a dead queue slot is read as)
-    uint32_t sh_addr, tab_addr;   // shared addresses of the counters and of the bin-edge table
-    uint32_t mi, oi;              // the lane's own I record: meta, original index
-    uint32_t off_inter, off_swap; // byte offsets of the inter-molecular / J-first counter slabs (2 hs, hs counters)
-    bool cross;                   // different elements: the ordered slot depends on the original order
+// what the rare events of the bin pass need; one copy per CTA in shared memory (the slab indexes change with the pair)
+struct SlowCtx {
+    GridParams g;
+    unsigned long long *counts;      // [2][nEl*nEl][hs] global ordered histogram (edge spill)
+    const int32_t *mol;              // molecule index by ORIGINAL atom index
+    long long cells;
+    int slab_ab, slab_ba;
+    uint32_t sh_addr;                // shared address of the counters
+    int cross;
 };
 
-// the rare events of the bin pass, kept out of line (the exact sqrt and divide are long): an edge overflow
-// (bin index == histSize because of fp32 rounding, or a grid whose maxDistance lies beyond rmin + hs * bin)
-__device__ __noinline__ void bin_overflow(float d2, int swap, int inter, GridParams g, SpillTarget sp)
+struct WarpCtx {                  // what the bin pass needs: warp-uniform or lane-private registers
+    uint32_t w0;                  // shared address of this lane's queue column (entries 256 bytes apart)
+    uint32_t sh_inter;            // shared address of the inter-molecular counters of the [a,b] slab
+    uint32_t tab_addr;            // shared address of the bin-edge table
+    uint32_t off_swap;            // byte offset from an [a,b] slab to its [b,a] slab (hs counters); 0 inside one element
+    uint32_t oi;                  // original index of the lane's I atom
+    uint32_t span, span2;         // molecule spread in original indexes, and twice it
+    const SlowCtx *slow;          // shared memory
+};
+
+// The rare events, out of line: a pair that may be intra-molecular (exact molecule comparison), a bin guess the
+// table did not confirm (exact fp32 sqrt and divide, the reference's own expression), an edge overflow (bin index ==
+// histSize through fp32 rounding, or a grid whose maxDistance lies beyond rmin + hs * bin: counted, and written where
+// the reference's unchecked store lands when spill emulation is on).
+__device__ __noinline__ void bin_slow(float d2, uint32_t oi, uint32_t oj, const SlowCtx *S, unsigned long long *ov)
 {
+    const GridParams g = S->g;
+    const bool inter = S->mol[oi] != S->mol[oj];
+    const bool swp = S->cross && oi > oj;
     const int b = bin_index(d2, g);
-    const long long flat = (long long)(swap ? sp.slab_ba : sp.slab_ab) * g.hs + b;
-    if (g.spill && b >= 0 && flat < sp.cells) atomicAdd(&sp.counts[(inter ? sp.cells : 0) + flat], 1ull);
+    if ((unsigned)b < (unsigned)g.hs) {
+        const uint32_t addr = S->sh_addr + 4u * (uint32_t)(((inter ? 2 : 0) + (swp ? 1 : 0)) * g.hs + b);
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    } else {
+        ++*ov;
+        const long long flat = (long long)(swp ? S->slab_ba : S->slab_ab) * g.hs + b;
+        if (g.spill && b >= 0 && flat < S->cells) atomicAdd(&S->counts[(inter ? S->cells : 0) + flat], 1ull);
+    }
 }
 
-// Bin index of an in-range d2 without sqrt and divide: tab[b] = (T[b], T[b+1]), T[b] the smallest fp32 d2 whose
-// reference bin (int)((sqrt(d2) - rmin) / bin) is >= b (bin_table_kernel: exact search on that very expression,
-// which is monotone in d2).  An approximate sqrt gives a guess, the thresholds decide: one +-1 step covers every
-// regular grid, and the corrected bin is verified against its own edges (walking on if a degenerate grid needs it).
-__device__ __noinline__ int bin_walk(float d2, int b, uint32_t tab_addr)
-{
-    float2 t = lds_f64(tab_addr + 8u * (uint32_t)b);
-    while (d2 < t.x) t = lds_f64(tab_addr + 8u * (uint32_t)(--b));
-    while (d2 >= t.y) t = lds_f64(tab_addr + 8u * (uint32_t)(++b));
-    return b;
-}
-
-// every lane bins its own queue (d2 kept from the sweep: nothing is recomputed), four entries per trip: the
-// shared-memory loads of the four first (queue, J meta / index, bin edges), then the four counter updates
+// every lane bins its own queue, four entries per trip: the shared-memory loads of the four first (queue, bin
+// edges), then the four counter updates.  Fast path per entry: approximate sqrt -> bin guess -> the two d^2 edges of
+// that bin confirm it (bin_table_kernel) -> one shared-memory increment.  Anything else is flagged and redone by
+// bin_slow() after the loop.
 template <bool TABLE>
-__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, const GridParams &g, float inv_bin, float c0,
-                                            unsigned long long &ov, const SpillTarget &sp)
+__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, int hs, float inv_bin, float c0, unsigned long long &ov)
 {
     const int n = (int)((wp - W.w0) >> 8);
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    const int hs = g.hs;
+    uint32_t slow = 0u;                                            // bit k: entry k of this lane needs bin_slow()
     for (int k = 0; k < nmax; k += 4) {
         float d2[4];
-        uint32_t tag[4], off[4];
-        int b[4];
-        bool live[4], inter[4], swp[4];
+        uint32_t oj[4];
         float2 t[4];
+        int b[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            live[j] = (k + j < n);
-            uint2 e = make_uint2(0u, W.tag0);                      // a dead slot reads a valid J record
-            if (live[j]) e = lds_u64(W.w0 + (uint32_t)(k + j) * 256u);
-            d2[j] = __uint_as_float(e.x);
-            tag[j] = e.y;                                          // shared address of the J record's meta word
+            uint2 e = make_uint2(0u, 0u);
+            if (k + j < n) e = lds_u64(W.w0 + (uint32_t)(k + j) * 256u);
+            d2[j] = __uint_as_float(e.x); oj[j] = e.y;
         }
+        if (TABLE) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t mj = lds_u32(tag[j]);
-            inter[j] = ((W.mi ^ mj) >= 256u);                      // molecule ranks differ
-            swp[j] = W.cross && W.oi > lds_u32((tag[j] >> 2) + W.o_off);                     // the J atom comes first in original order
-            off[j] = (inter[j] ? W.off_inter : 0u) + (swp[j] ? W.off_swap : 0u);
-            if (TABLE) {
+            for (int j = 0; j < 4; ++j) {
                 float s;
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2[j]));
-                b[j] = max(0, min(__float2int_rz(__fmaf_rn(s, inv_bin, c0)), hs));
+                b[j] = max(0, min(__float2int_rz(__fmaf_rn(s, inv_bin, c0)), hs - 1));
                 t[j] = lds_f64(W.tab_addr + 8u * (uint32_t)b[j]);
-            } else {
-                b[j] = live[j] ? bin_index(d2[j], g) : 0;
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int bb = b[j];
-            if (TABLE) {
-                bb += (d2[j] >= t[j].y) ? 1 : 0;
-                bb -= (d2[j] < t[j].x) ? 1 : 0;
-                if (live[j] && bb != b[j]) bb = bin_walk(d2[j], bb, W.tab_addr);        // a few percent of the hits
+            const bool live = (k + j < n);
+            const bool maybe_intra = (oj[j] - W.oi + W.span) <= W.span2;          // |oj - oi| <= span (unsigned wrap-around trick)
+            const bool sure = TABLE && (d2[j] >= t[j].x) && (d2[j] < t[j].y) && !maybe_intra;
+            if (live && sure) {
+                const uint32_t addr = W.sh_inter + ((W.oi > oj[j]) ? W.off_swap : 0u) + 4u * (uint32_t)b[j];
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+            } else if (live) {
+                slow |= 1u << (k + j);
             }
-            if (live[j]) {
-                if ((unsigned)bb < (unsigned)hs) {
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(W.sh_addr + off[j] + 4u * (uint32_t)bb) : "memory");
-                } else {
-                    ++ov;
-                    bin_overflow(d2[j], swp[j], inter[j], g, sp);
-                }
-            }
+        }
+    }
+    if (__any_sync(0xffffffffu, slow != 0u)) {
+        while (slow) {
+            const int k = __ffs(slow) - 1;
+            slow &= slow - 1u;
+            const uint2 e = lds_u64(W.w0 + (uint32_t)k * 256u);
+            bin_slow(__uint_as_float(e.x), W.oi, e.y, W.slow, &ov);
         }
     }
     wp = W.w0;
     __syncwarp();
 }
 
-// one staged J sub-block (32 records) against the lane's I atom; hits are pushed as (d2, shared address of the J
-// record's meta word): a predicated 8-byte store into the lane's own queue column and a predicated pointer bump --
-// no branch, no vote.  TRI (the unit on the diagonal of the I block): only p < q counts, i.e. lane < record.
+// one staged J sub-block (32 sweep records) against the lane's I atom.  TRI (the unit on the diagonal of the I block):
+// only p < q counts, i.e. lane < record.  The queue (24 entries per lane) is emptied when a lane holds more than 8.
 template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE, bool TRI>
-__device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, uint32_t tag, float xi, float yi, float zi,
-                                           const Lattice &Lc, float t2min, float t2max, uint32_t &wp, const WarpCtx &W,
-                                           const GridParams &g, float inv_bin, float c0, unsigned long long &ov, const SpillTarget &sp)
+__device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float xi, float yi, float zi, const Lattice &Lc,
+                                           float t2min, float t2max, uint32_t &wp, const WarpCtx &W, int hs, float inv_bin,
+                                           float c0, unsigned long long &ov)
 {
     Lattice L = Lc;               // lattice in plain registers: from the constant bank the compiler re-reads it every iteration
     if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
         asm volatile("" : "+f"(L.b[0]), "+f"(L.b[4]), "+f"(L.b[8]));
     }
     asm volatile("" : "+f"(t2min), "+f"(t2max));
+    const uint32_t wfull = W.w0 + (uint32_t)(V2_CAP - 16) * 256u;
     if constexpr (TRI) {
         const int lane = threadIdx.x & 31;
 #pragma unroll 1
@@ -467,39 +488,33 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, uint3
             const float4 a = sJu[q];
             const float d2 = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a.x, a.y, a.z, L);
             if ((!HASMIN || d2 >= t2min) && (d2 < t2max) && lane < q) {
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2)), "r"(tag + 16u * (uint32_t)q) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2)), "r"(__float_as_uint(a.w)) : "memory");
                 wp += 256u;
             }
-            if (q == 15) { __syncwarp(); drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp); }
+            if ((q & 15) == 15 && __any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); drain_queue<TABLE>(wp, W, hs, inv_bin, c0, ov); }
         }
-        __syncwarp();
-        drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp);
     } else {
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            // eight records in flight: loads first, then eight independent distance chains, then the pushes
-            float4 a[8];
-            float d2[8];
+            for (int c = 0; c < 2; ++c) {
+                // eight records in flight: loads first, then eight independent distance chains, then the pushes
+                float4 a[8];
+                float d2[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = sJu[half * 16 + c * 8 + u];
+                for (int u = 0; u < 8; ++u) a[u] = sJu[half * 16 + c * 8 + u];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
+                for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])),
-                                 "r"(tag + 16u * (uint32_t)(half * 16 + c * 8 + u)) : "memory");
-                    wp += 256u;
+                for (int u = 0; u < 8; ++u) {
+                    if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])), "r"(__float_as_uint(a[u].w)) : "memory");
+                        wp += 256u;
+                    }
                 }
             }
+            if (__any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); drain_queue<TABLE>(wp, W, hs, inv_bin, c0, ov); }
         }
-        // the queue holds 24 entries per lane: after the first 16 records it is emptied only if a lane has more than 8
-        if (half == 0 && !__any_sync(0xffffffffu, wp > W.w0 + 8u * 256u)) continue;
-        __syncwarp();
-        drain_queue<TABLE>(wp, W, g, inv_bin, c0, ov, sp);
-    }
     }
 }
 
@@ -681,7 +696,10 @@ __global__ void bin_table_kernel(GridParams g, float2 *__restrict__ tab)
 
 // everything one launch of the sweep needs, by value
 struct SweepArgs {
-    const float4 *atoms; const uint32_t *orig; const float4 *bbox;
+    const float4 *recs;              // sweep records {x, y, z, original index}
+    const int32_t *mol;              // molecule index by original atom index (read only when mol_span > 0 ... or for candidates)
+    const float4 *bbox;
+    uint32_t mol_span;               // largest spread of a molecule in original indexes
     const WorkItem *rows; const int *pair_first_row; const int *row_item_start;
     const uint32_t *entries; const int4 *items; int *pair_next;
     const float2 *tab;
@@ -705,9 +723,9 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     if (TABLE) off += (((size_t)g.hs + 1) * 8 + 15) & ~(size_t)15;
     unsigned char *wbase = smem_raw + off + (size_t)warp * V2_WARP_BYTES;
     float4 *sJ = reinterpret_cast<float4 *>(wbase + V2_Q_BYTES);
-    uint32_t *sO = reinterpret_cast<uint32_t *>(wbase + V2_Q_BYTES + 2 * 32 * 16);
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_Q_BYTES + 2 * 32 * 16 + 2 * 32 * 4);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_Q_BYTES + 2 * 32 * 16);
     __shared__ int s_tasks, s_again, s_p0;
+    __shared__ SlowCtx s_slow;
 
     for (int c = tid; c < nsh; c += V2_THREADS) sh[c] = 0u;
     if (TABLE) for (int c = tid; c <= g.hs; c += V2_THREADS) tab[c] = A.tab[c];
@@ -716,8 +734,11 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
+    const long long cells = (long long)A.nEl * A.nEl * g.hs;
     if (tid == 0) {
         s_tasks = 0; s_again = 0;
+        s_slow.g = g; s_slow.counts = A.counts; s_slow.mol = A.mol; s_slow.cells = cells;
+        s_slow.slab_ab = 0; s_slow.slab_ba = 0; s_slow.sh_addr = fh_smem_u32(sh); s_slow.cross = 0;
         // CTAs start on the element pair that holds their share of the items, so that a CTA stays on one pair
         // (one flush of its counters) for most of the launch; pairs are then visited cyclically
         const long long target = ((2ll * blockIdx.x + 1) * A.n_items) / (2ll * gridDim.x);
@@ -733,18 +754,16 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
 
     WarpCtx W;
     W.w0 = fh_smem_u32(wbase) + 8u * (uint32_t)lane;
-    const uint32_t sJ_addr = fh_smem_u32(sJ);
-    W.o_off = fh_smem_u32(sO) - ((sJ_addr + 12u) >> 2);
-    W.tag0 = sJ_addr + 12u;
-    W.sh_addr = fh_smem_u32(sh); W.tab_addr = fh_smem_u32(tab);
-    W.off_inter = 8u * (uint32_t)g.hs; W.off_swap = 4u * (uint32_t)g.hs;
-    W.mi = 0u; W.oi = 0u; W.cross = false;
+    W.sh_inter = fh_smem_u32(sh) + 8u * (uint32_t)g.hs;
+    W.tab_addr = fh_smem_u32(tab);
+    W.off_swap = 0u; W.oi = 0u;
+    W.span = (A.mol_span >= 0x40000000u) ? 0x7FFFFFFFu : A.mol_span;
+    W.span2 = 2u * W.span;
+    W.slow = &s_slow;
     uint32_t wp = W.w0;
     const float inv_bin = TABLE ? __frcp_rn(g.bin) : 0.f, c0 = TABLE ? -g.rmin * inv_bin : 0.f;
     unsigned long long ov = 0, swept = 0;
-    const long long cells = (long long)A.nEl * A.nEl * g.hs;
-    SpillTarget sp;
-    sp.counts = A.counts; sp.cells = cells; sp.slab_ab = 0; sp.slab_ba = 0;
+    int slab_ab = 0, slab_ba = 0;
     unsigned seq = 0;                             // J sub-blocks this warp has streamed: stage = seq & 1, parity = (seq >> 1) & 1
     const float T = __int_as_float(0x3EFFFFFF);   // 0.5 - 2^-25: below it round() is 0 (common.cuh:wrap_fast)
 
@@ -757,8 +776,10 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
         if (ntasks <= 0) continue;
         const WorkItem w0row = A.rows[r0];
         const bool cross = (w0row.ea != w0row.eb);
-        sp.slab_ab = w0row.ea * A.nEl + w0row.eb; sp.slab_ba = w0row.eb * A.nEl + w0row.ea;
-        W.cross = cross;
+        slab_ab = w0row.ea * A.nEl + w0row.eb; slab_ba = w0row.eb * A.nEl + w0row.ea;
+        W.off_swap = cross ? 4u * (uint32_t)g.hs : 0u;
+        if (tid == 0) { s_slow.slab_ab = slab_ab; s_slow.slab_ba = slab_ba; s_slow.cross = cross ? 1 : 0; }
+        __syncthreads();                          // the slow path's view of the pair; the previous pair's flush is behind us
         bool again = true;
         while (again) {
             // ---- this warp's tasks of the pair
@@ -776,9 +797,8 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                 const size_t atI = 2 * ((size_t)A.nblocks + (size_t)bi * (SEG_PAD / 32) + s);
                 const float4 loI = A.bbox[atI], hiI = A.bbox[atI + 1];
                 if (A.cp.enabled && hiI.w == 1.f) continue;   // padding only
-                const int pI = w.i0 + s * 32 + lane;
-                const float4 ai = A.atoms[pI];
-                W.mi = __float_as_uint(ai.w); W.oi = A.orig[pI];
+                const float4 ai = A.recs[w.i0 + s * 32 + lane];
+                W.oi = __float_as_uint(ai.w);
                 // which of the item's 32-record J sub-blocks can hold a hit for THIS warp's 32 atoms: lane = (entry, sub-block)
                 const int e = lane >> 3, sb = lane & 7;
                 int jb = 0;
@@ -802,38 +822,39 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                 const unsigned m_tri = __ballot_sync(0xffffffffu, near && tri);
                 if (!m) continue;
                 swept += (unsigned)__popc(m);
-                // stream the surviving sub-blocks: unit n+1 is in flight (TMA) while unit n is swept
+                // stream the surviving sub-blocks: unit n+1 is in flight (TMA) while unit n is swept.  A stage is
+                // free as soon as its sweep has ended: queued hits carry everything the bin pass needs.
                 auto issue = [&](int bit, unsigned sq) {
                     const int jbb = __shfl_sync(0xffffffffu, jb, bit & ~7);
                     if (lane == 0) {
                         const int st = (int)(sq & 1u);
-                        const size_t pj = (size_t)jbb * SEG_PAD + (size_t)(bit & 7) * 32;
-                        fh_mbar_expect_tx(&mbar[st], 32 * 16 + 32 * 4);
-                        fh_bulk_g2s(sJ + st * 32, A.atoms + pj, 32 * 16, &mbar[st]);
-                        fh_bulk_g2s(sO + st * 32, A.orig + pj, 32 * 4, &mbar[st]);
+                        fh_mbar_expect_tx(&mbar[st], 32 * 16);
+                        fh_bulk_g2s(sJ + st * 32, A.recs + ((size_t)jbb * SEG_PAD + (size_t)(bit & 7) * 32), 32 * 16, &mbar[st]);
                     }
                 };
                 issue(__ffs(m) - 1, seq);
                 while (m) {
                     const int bit = __ffs(m) - 1;
                     m &= m - 1u;
-                    if (m) issue(__ffs(m) - 1, seq + 1u);      // its stage was drained at the end of the previous unit
+                    __syncwarp();                              // every lane has read the stage the next copy overwrites
+                    if (m) issue(__ffs(m) - 1, seq + 1u);
                     const int st = (int)(seq & 1u);
                     fh_mbar_wait(&mbar[st], (seq >> 1) & 1u);
-                    const uint32_t tag = sJ_addr + 12u + (uint32_t)st * 512u;      // shared address of record 0's meta word
                     const float4 *sJu = sJ + st * 32;
                     if ((m_tri >> bit) & 1u) {
                         if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
-                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
                         else
-                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
                     } else if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u)) {
-                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
                     } else {
-                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, tag, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g, inv_bin, c0, ov, sp);
+                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
                     }
                     ++seq;
                 }
+                __syncwarp();
+                drain_queue<TABLE>(wp, W, g.hs, inv_bin, c0, ov);          // the queue belongs to this task's I atoms
             }
             // ---- the CTA leaves the pair (or its 32-bit counters are due): counters -> global ordered histogram
             __syncthreads();
@@ -845,7 +866,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                     if (cnt) {
                         sh[c] = 0u;
                         const int slot = c / g.hs, b = c - slot * g.hs;
-                        const long long at = ((slot >> 1) ? cells : 0) + (long long)((slot & 1) ? sp.slab_ba : sp.slab_ab) * g.hs + b;
+                        const long long at = ((slot >> 1) ? cells : 0) + (long long)((slot & 1) ? slab_ba : slab_ab) * g.hs + b;
                         atomicAdd(&A.counts[at], (unsigned long long)cnt);
                     }
                 }
@@ -908,9 +929,9 @@ static int ensure_capacity(T **buf, size_t *cap, size_t need, cudaStream_t strea
 
 void PairLists::release()
 {
-    cudaFree(row_ints); cudaFree(entries); cudaFree(items); cudaFree(pair_next); cudaFree(bin_table);
-    row_ints = nullptr; entries = nullptr; items = nullptr; pair_next = nullptr; bin_table = nullptr;
-    row_cap = entries_cap = items_cap = bin_cap = 0;
+    cudaFree(row_ints); cudaFree(entries); cudaFree(items); cudaFree(pair_next); cudaFree(bin_table); cudaFree(recs);
+    row_ints = nullptr; entries = nullptr; items = nullptr; pair_next = nullptr; bin_table = nullptr; recs = nullptr;
+    row_cap = entries_cap = items_cap = bin_cap = recs_cap = 0;
 }
 
 // Box pass and surviving-pair lists for `rows` under the culling parameters cp (bbox: 18 float4 per SEG_PAD
@@ -966,9 +987,12 @@ void pack_rows(const std::vector<WorkItem> &rows, std::vector<unsigned char> &bl
 }
 
 // Box pass, surviving-pair lists, bin-edge table, then the sweep, on prepared device arrays.  `rows` is the device
-// copy of a pack_rows() blob.  stats[0] accumulates edge-overflow events, stats[1] swept (32 x 32) units.
+// copy of a pack_rows() blob; mol_by_orig (device, molecule index by original atom index) is read only for pairs
+// within mol_span original indexes of each other (HostLayout::mol_span).  stats[0] accumulates edge-overflow events,
+// stats[1] swept (32 x 32) units.
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *atoms, const uint32_t *orig,
                      int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, int n_pairs, PairLists &lists,
+                     const int32_t *mol_by_orig, uint32_t mol_span,
                      const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats)
 {
     CullParams cp = make_cull(L, mode, g);
@@ -994,8 +1018,16 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *
         bin_table_kernel<<<(g.hs + 1 + 127) / 128, 128, 0, stream>>>(g, lists.bin_table);
         FRMC_LAUNCH_CHECK();
     }
+    // sweep records {x, y, z, original index} of the current coordinates
+    if (lists.recs_cap < (size_t)npad) {
+        if (lists.recs) { FRMC_CUDA(cudaStreamSynchronize(stream)); cudaFree(lists.recs); lists.recs = nullptr; }
+        FRMC_CUDA(cudaMalloc((void **)&lists.recs, sizeof(float4) * (size_t)npad));
+        lists.recs_cap = (size_t)npad;
+    }
+    sweep_records_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(atoms, orig, (long long)npad, lists.recs);
+    FRMC_LAUNCH_CHECK();
     SweepArgs A;
-    A.atoms = atoms; A.orig = orig; A.bbox = bbox;
+    A.recs = lists.recs; A.mol = mol_by_orig; A.mol_span = mol_span; A.bbox = bbox;
     A.rows = rows; A.pair_first_row = reinterpret_cast<const int *>(rows + n_rows); A.row_item_start = lists.row_ints + 3 * (size_t)n_rows;
     A.entries = lists.entries; A.items = lists.items; A.pair_next = lists.pair_next;
     A.tab = lists.bin_table; A.counts = counts; A.stats = stats;
@@ -1145,9 +1177,15 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     }
     if (!items.empty()) {
         FRMC_CUDA(cudaMemcpyAsync(d_items, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+        int32_t *d_mol = nullptr;                      // only molecular systems ever read it
+        if (lay.mol_span > 0) {
+            d_mol = (int32_t *)ctx_buffer(c, 6, sizeof(int32_t) * (size_t)n);
+            if (!d_mol) return FRMC_ENOMEM;
+            FRMC_CUDA(cudaMemcpyAsync(d_mol, mol, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        }
         static PairLists stateless_lists[64];          // per device, grow-only, like the context's scratch buffers
         rc = full_hist_launch(c->stream, c->sm_count, mode, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), n_pairs,
-                              stateless_lists[c->dev & 63], L, g, nEl, d_counts, d_ov);
+                              stateless_lists[c->dev & 63], d_mol, lay.mol_span, L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);

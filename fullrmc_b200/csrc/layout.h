@@ -41,6 +41,7 @@ struct HostLayout {
     std::vector<float> kd;            // scratch of the k-d ordering (4 floats per atom), kept to reuse its pages
     float lo[3], hi[3];               // coordinate bounds (mode selection)
     bool finite = true;
+    uint32_t mol_span = 0;            // largest |i - j| (original indexes) over pairs of atoms of one molecule
 };
 
 // Builds the sorted layout.  Returns 0 or a negative FRMC_E* code (error string set).
@@ -71,6 +72,8 @@ struct PairLists {
     int *pair_next = nullptr;       // full histogram: one task counter per element pair (+ scratch), zeroed per launch
     float2 *bin_table = nullptr;    // full histogram: (T[b], T[b+1]) d^2 thresholds of the bin edges
     size_t bin_cap = 0;
+    float4 *recs = nullptr;         // full histogram: sweep records {x, y, z, original index}
+    size_t recs_cap = 0;
     void release();
 };
 

@@ -28,6 +28,7 @@ namespace frmc {
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *atoms, const uint32_t *orig,
                      int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, int n_pairs, PairLists &lists,
+                     const int32_t *mol_by_orig, uint32_t mol_span,
                      const Lattice &L, const GridParams &g, int nEl, unsigned long long *counts, unsigned long long *stats);
 void pack_rows(const std::vector<WorkItem> &rows, std::vector<unsigned char> &blob, int &n_pairs);
 int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *counts, float *out, long long cells2);
@@ -2025,6 +2026,8 @@ struct frmc_store {
     Lattice L;
     float lo[3], hi[3];
     std::vector<int32_t> h_mol, h_el;
+    int32_t *d_mol = nullptr;                   // molecule index by original atom index (full histogram: exact intra/inter test)
+    uint32_t mol_span = 0;                      // HostLayout::mol_span
     float4 *d_atoms = nullptr;
     uint32_t *d_orig = nullptr;
     WorkItem *d_items = nullptr;     // rows of the pair list (I tile x J range of an element pair)
@@ -2153,6 +2156,11 @@ static int upload_layout(frmc_store *s, const float *coords)
     int rc = build_layout(coords, s->n, s->h_mol.data(), s->h_el.data(), s->nEl, s->isPBC, s->lay);
     if (rc) return rc;
     s->npad = s->lay.npad;
+    s->mol_span = s->lay.mol_span;
+    if (!s->d_mol && s->n > 0) {
+        FRMC_CUDA(cudaMalloc(&s->d_mol, sizeof(int32_t) * (size_t)s->n));
+        FRMC_CUDA(cudaMemcpyAsync(s->d_mol, s->h_mol.data(), sizeof(int32_t) * (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
+    }
     for (int c = 0; c < 3; ++c) { s->lo[c] = s->lay.lo[c]; s->hi[c] = s->lay.hi[c]; }
     if (!s->d_atoms) {
         FRMC_CUDA(cudaMalloc(&s->d_atoms, sizeof(float4) * std::max<int64_t>(s->npad, 1)));
@@ -2816,7 +2824,7 @@ void frmc_store_destroy(frmc_store *s)
         for (void *p : m.owned) cudaFree(p);
     }
     for (auto &g : s->grids) { cudaFree(g.dev.counts); cudaFree(g.dev.delta); cudaFree(g.dev.tot); cudaFree(g.dev.stot); }
-    cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next);
+    cudaFree(s->d_atoms); cudaFree(s->d_orig); cudaFree(s->d_items); cudaFree(s->d_next); cudaFree(s->d_mol);
     s->lists.release();
     cudaFree(s->d_overflow); cudaFree(s->d_bbox); cudaFree(s->d_prop); cudaFree(s->d_seq); cudaFree(s->d_stamps); cudaFree(s->d_bars);
     for (auto &p : s->ev_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -3107,7 +3115,7 @@ int frmc_compute_data_shard(frmc_store *s, int shard, int nshards)
             cudaEvent_t t0 = timing_begin(s);
             FRMC_CUDA(cudaMemsetAsync(s->d_overflow + 1, 0, sizeof(unsigned long long), s->stream));
             rc = full_hist_launch(s->stream, s->ctx->sm_count, mode, s->d_atoms, s->d_orig, s->npad, s->d_bbox, s->d_items,
-                                  s->n_items, s->n_pairs, s->lists, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
+                                  s->n_items, s->n_pairs, s->lists, s->d_mol, s->mol_span, s->L, g.dev.g, s->nEl, g.dev.counts, s->d_overflow);
             if (rc) return rc;
             timing_end(s, TIME_FULL, t0);
         }
