@@ -400,7 +400,7 @@ struct WarpCtx {                  // what the bin pass needs: warp-uniform or la
 __device__ __noinline__ void bin_slow(float d2, uint32_t oi, uint32_t oj, const SlowCtx *S, unsigned long long *ov)
 {
     const GridParams g = S->g;
-    const bool inter = S->mol[oi] != S->mol[oj];
+    const bool inter = (S->mol == nullptr) || S->mol[oi] != S->mol[oj];     // no array: every atom is its own molecule (mol_span == 0)
     const bool swp = S->cross && oi > oj;
     const int b = bin_index(d2, g);
     if ((unsigned)b < (unsigned)g.hs) {

@@ -93,6 +93,47 @@ def build(force=False):
     return is_built()
 
 
+PKG = os.path.join(OUT, "pkg")                     # the staged reference package: oracle/_ref/pkg/fullrmc
+EXAMPLES = os.path.join(OUT, "Examples")          # the shipped inputs of BASELINE.json configs 1-3
+EXAMPLE_FILES = {"atomicNiTi": ("system.pdb", "experimental.gr", "experimental.fq"),
+                 "molecularTHF": ("thf.pdb", "thf_pdf.exp"),
+                 "SiOxNanosphere": ("SiOx.pdb", "SiOx.gr")}
+PY_DIRS = ("", "Core", "Constraints", "Generators", "Selectors")
+
+
+def is_staged():
+    return (os.path.exists(os.path.join(PKG, "fullrmc", "Engine.py")) and
+            all(os.path.exists(os.path.join(EXAMPLES, d, f)) for d, fs in EXAMPLE_FILES.items() for f in fs))
+
+
+def stage_package(force=False):
+    """Stage the reference's pure-Python package (Engine, constraint classes, generators, selectors) next to its
+    compiled kernels, plus the example inputs of configs 1-3, under the git-ignored oracle/_ref/ -- so that the
+    UNMODIFIED reference classes and Engine.run can be driven on the GPU box, where /root/reference does not
+    exist (tests/ref_harness.py; tests/test_dropin.py swaps fullrmc.Core.<extension> for fullrmc_b200.Core.<name>
+    underneath them).  Binaries and inputs only travel; nothing here is tracked by git.  Returns True when usable."""
+    if is_staged() and not force:
+        return True
+    if not os.path.isdir(REF) or not build():
+        return False
+    dst_pkg = os.path.join(PKG, "fullrmc")
+    for sub in PY_DIRS:
+        src_dir, dst_dir = os.path.join(REF, sub), os.path.join(dst_pkg, sub)
+        os.makedirs(dst_dir, exist_ok=True)
+        for name in os.listdir(src_dir):
+            if name.endswith(".py") and name != "setup.py":
+                shutil.copyfile(os.path.join(src_dir, name), os.path.join(dst_dir, name))
+    so_dir = os.path.join(OUT, "fullrmc", "Core")
+    for name in os.listdir(so_dir):
+        if name.endswith(".so"):
+            shutil.copyfile(os.path.join(so_dir, name), os.path.join(dst_pkg, "Core", name))
+    for d, files in EXAMPLE_FILES.items():
+        os.makedirs(os.path.join(EXAMPLES, d), exist_ok=True)
+        for f in files:
+            shutil.copyfile(os.path.join(REF, "Examples", d, f), os.path.join(EXAMPLES, d, f))
+    return is_staged()
+
+
 def load():
     """Import the compiled reference modules; returns (pairs_distances, pairs_histograms,
     reciprocal_space) or None when oracle/_ref has not been built."""
@@ -107,4 +148,6 @@ def load():
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     print("oracle/_ref built:", ok)
+    staged = stage_package(force="--force" in sys.argv)
+    print("reference package + example inputs staged under oracle/_ref:", staged)
     sys.exit(0 if ok else 1)

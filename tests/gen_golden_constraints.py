@@ -22,7 +22,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, HERE)
 import ref_harness as H  # noqa: E402
 
-EX = os.path.join(H.REF, "Examples")
+EX = H.examples_dir()
 
 
 def read_pdb(path):
@@ -89,7 +89,15 @@ def fit_total(c, kind, E):
     return np.asarray(getattr(c, fn)(c.data, rho0=E.numberDensity), np.float32)
 
 
-ONLY = set(sys.argv[1:])        # optional case names on the command line: regenerate just those
+# command line: [--dropin] [--out DIR] [case names: regenerate just those]
+#   --dropin   the same unmodified reference classes, but with fullrmc.Core.<extension> replaced by the CUDA drop-in
+#              modules fullrmc_b200.Core.<name> (tests/ref_harness.load_reference(dropin=True)); needs a GPU.
+#              tests/test_dropin.py runs this into a scratch directory and requires the files it writes to equal the
+#              committed fixtures array for array: the literal drop-in demonstration.
+_ARGS = sys.argv[1:]
+DROPIN = "--dropin" in _ARGS
+OUT_DIR = _ARGS[_ARGS.index("--out") + 1] if "--out" in _ARGS else None
+ONLY = set(a for i, a in enumerate(_ARGS) if not a.startswith("--") and (i == 0 or _ARGS[i - 1] != "--out"))
 
 
 def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sigma, out_dir, recipe=None):
@@ -185,14 +193,17 @@ def run_case(name, fullrmc, arrays, make_constraints, groups, n_steps, seed, sig
 
 
 def main():
-    fullrmc = H.load_reference()
-    assert fullrmc is not None, "needs /root/reference"
+    fullrmc = H.load_reference(dropin=DROPIN)
+    assert fullrmc is not None, "needs /root/reference (or the package staged by oracle/build_ref.py)"
+    if DROPIN:
+        import fullrmc_b200
+        fullrmc_b200.set_edge_spill(True)        # the reference's unchecked write at bin == histSize
     from fullrmc.Globals import FLOAT_TYPE
     from fullrmc.Core.Collection import rebin, convert_Gr_to_gr
     from fullrmc.Constraints.PairDistributionConstraints import PairDistributionConstraint
     from fullrmc.Constraints.PairCorrelationConstraints import PairCorrelationConstraint
     from fullrmc.Constraints.StructureFactorConstraints import StructureFactorConstraint, ReducedStructureFactorConstraint
-    out_dir = os.path.join(ROOT, "tests", "golden")
+    out_dir = OUT_DIR or os.path.join(ROOT, "tests", "golden")
 
     # ---- config 1: Examples/atomicNiTi as shipped (run.py:41-49): PDF + reduced S(Q), atomic groups
     d = os.path.join(EX, "atomicNiTi")

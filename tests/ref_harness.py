@@ -2,40 +2,53 @@
 classes + Engine) under the third-party stubs of tests/ref_stubs, with the reference's own
 compiled kernels (oracle/_ref) in place of fullrmc.Core.<extension>.
 
-Used only by tests/gen_golden_constraints.py in the build container; nothing is copied into the
-repository: the package tree is a directory of symlinks under a temporary directory.
+Used by the golden-vector generators in the build container and by tests/test_dropin.py on the GPU box; nothing
+of the reference is tracked by git: oracle/build_ref.stage_package copies the package and the example inputs into
+the git-ignored oracle/_ref/, which travels to the GPU box like the built binaries.
 """
 import os
 import sys
-import tempfile
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 REF = os.environ.get("FULLRMC_REFERENCE", "/root/reference")
 
 
-def load_reference():
-    if not os.path.isdir(REF):
-        return None
+def examples_dir():
+    """the shipped example inputs: /root/reference/Examples here, the staged copies on the GPU box"""
+    from oracle import build_ref
+    return os.path.join(REF, "Examples") if os.path.isdir(REF) else build_ref.EXAMPLES
+
+
+DROPIN_MODULES = ("pairs_distances", "pairs_histograms", "reciprocal_space", "atomic_distances", "atomic_coordination")
+
+
+def load_reference(dropin=False):
+    """Import the unmodified reference package (staged by oracle/build_ref.stage_package under oracle/_ref/pkg, with
+    the reference's own compiled kernels in fullrmc/Core) under the third-party stubs.
+
+    dropin=True installs the CUDA backend the way SURVEY.md section 8b (ii) describes: ``sys.modules`` is pre-seeded
+    with ``fullrmc_b200.Core.<name>`` under the names ``fullrmc.Core.<name>`` BEFORE anything imports
+    ``fullrmc.Constraints.*``, so that the constraint modules' ``from ..Core.pairs_histograms import ...`` lines bind
+    the CUDA functions.  No reference source is touched.  Must be the first import of fullrmc in the process."""
     sys.path.insert(0, ROOT)
     from oracle import build_ref
-    assert build_ref.build(), "cannot build oracle/_ref"
-    tmp = tempfile.mkdtemp(prefix="frmc_refpkg_")
-    pkg = os.path.join(tmp, "fullrmc")
-    os.makedirs(os.path.join(pkg, "Core"))
-    for name in os.listdir(REF):
-        if name != "Core":
-            os.symlink(os.path.join(REF, name), os.path.join(pkg, name))
-    for name in os.listdir(os.path.join(REF, "Core")):
-        os.symlink(os.path.join(REF, "Core", name), os.path.join(pkg, "Core", name))
-    so_dir = os.path.join(build_ref.OUT, "fullrmc", "Core")
-    for name in os.listdir(so_dir):
-        if name.endswith(".so"):
-            os.symlink(os.path.join(so_dir, name), os.path.join(pkg, "Core", name))
-    sys.path.insert(0, tmp)
+    if not build_ref.stage_package():
+        return None
+    assert "fullrmc" not in sys.modules, "load_reference must run before anything imports fullrmc"
+    sys.path.insert(0, build_ref.PKG)
     sys.path.insert(0, os.path.join(ROOT, "tests", "ref_stubs"))
+    if dropin:
+        import importlib
+        for name in DROPIN_MODULES:
+            sys.modules["fullrmc.Core." + name] = importlib.import_module("fullrmc_b200.Core." + name)
     import fullrmc  # noqa: F401
+    if dropin:
+        import fullrmc.Constraints.PairDistributionConstraints as pdm
+        assert pdm.full_pairs_histograms_coords.__module__ == "fullrmc_b200.Core.pairs_histograms"
     return fullrmc
 
 
@@ -65,7 +78,10 @@ def fake_engine(fullrmc, boxCoordinates, basisVectors, isPBC, moleculesIndex, el
                 elementsIndex=np.ascontiguousarray(elementsIndex, dtype=np.int32), allElements=allElements,
                 elements=list(elements), numberOfAtomsPerElement={elements[i]: int(counts[i]) for i in range(len(elements))},
                 volume=volume, numberDensity=FLOAT_TYPE(n) / FLOAT_TYPE(volume), accepted=0, generated=0, tried=0,
-                numberOfAtoms=n, numberOfElements=len(elements))
+                numberOfAtoms=n, numberOfElements=len(elements),
+                # what Engine.run / set_groups / set_group_selector touch beyond the constraints' needs (Engine.py:256-300)
+                groups=[], groupSelector=None, tolerance=0., saveGroupsFlag=False, tolerated=0, removed=[0., 0., 0.],
+                totalStandardError=None, lastSelectedGroupIndex=None, path=None, timeout=10, id="fake", pdb=None)
     for k, v in priv.items():
         object.__setattr__(E, "_Engine__" + k, v)
     object.__setattr__(E, "_runtime_ncores", np.int32(1))
