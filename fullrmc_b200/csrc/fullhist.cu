@@ -290,11 +290,13 @@ void build_rows(const HostLayout &lay, int R, int shard, int nshards, std::vecto
 static const int V2_THREADS = 384;        // 12 warps per CTA share one set of counters (2 CTAs per SM at histSize 1000)
 static const int V2_WARPS = V2_THREADS / 32;
 static const int V2_ITEM_BLOCKS = 4;      // surviving J blocks per item: 8 tasks (one per I sub-block) of <= 32 units each
-static const int V2_CAP = 24;             // hit-queue entries per lane (8 bytes each); emptied when a lane holds more than CAP - 16
+static const int V2_CAP = 23;             // hit-queue entries per lane (8 bytes each); emptied when a lane holds more than CAP - 8
 static const int V2_TASK_LIMIT = 65536;   // tasks a CTA bins into its 32-bit counters between two flushes (32768 hits each at most)
-// per-warp shared memory: queue [V2_CAP][32] uint2, J ring [2][32] float4, 2 mbarriers
+// per-warp shared memory: queue [V2_CAP][32] uint2, J ring [2][32] float4, bin-pass scratch [32] uint4, 2 mbarriers
 static const int V2_Q_BYTES = V2_CAP * 32 * 8;
-static const int V2_WARP_BYTES = V2_Q_BYTES + 2 * 32 * 16 + 32;
+static const int V2_SCRATCH_OFF = V2_Q_BYTES + 2 * 32 * 16;
+static const int V2_MBAR_OFF = V2_SCRATCH_OFF + 32 * 16;
+static const int V2_WARP_BYTES = V2_MBAR_OFF + 32;
 
 __device__ __forceinline__ unsigned fh_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fh_mbar_init(unsigned long long *bar, unsigned count)
@@ -381,15 +383,28 @@ struct SlowCtx {
     int slab_ab, slab_ba;
     uint32_t sh_addr;                // shared address of the counters
     int cross;
+    unsigned long long ov;           // edge-overflow events seen by this CTA
 };
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct WarpCtx {                  // what the bin pass needs: warp-uniform or lane-private registers
-    uint32_t w0;                  // shared address of this lane's queue column (entries 256 bytes apart)
+    uint32_t wq;                  // shared address of the warp's queue ([V2_CAP][32] entries of 8 bytes; lane l owns column l)
+    uint32_t w0;                  // wq + 8 * lane: this lane's column
     uint32_t sh_inter;            // shared address of the inter-molecular counters of the [a,b] slab
     uint32_t tab_addr;            // shared address of the bin-edge table
     uint32_t off_swap;            // byte offset from an [a,b] slab to its [b,a] slab (hs counters); 0 inside one element
     uint32_t oi;                  // original index of the lane's I atom
-    uint32_t span, span2;         // molecule spread in original indexes, and twice it
+    uint32_t span;                // molecule spread in original indexes
     const SlowCtx *slow;          // shared memory
 };
 
@@ -397,7 +412,7 @@ struct WarpCtx {                  // what the bin pass needs: warp-uniform or la
 // table did not confirm (exact fp32 sqrt and divide, the reference's own expression), an edge overflow (bin index ==
 // histSize through fp32 rounding, or a grid whose maxDistance lies beyond rmin + hs * bin: counted, and written where
 // the reference's unchecked store lands when spill emulation is on).
-__device__ __noinline__ void bin_slow(float d2, uint32_t oi, uint32_t oj, const SlowCtx *S, unsigned long long *ov)
+__device__ __noinline__ void bin_slow(float d2, uint32_t oi, uint32_t oj, SlowCtx *S)
 {
     const GridParams g = S->g;
     const bool inter = (S->mol == nullptr) || S->mol[oi] != S->mol[oj];     // no array: every atom is its own molecule (mol_span == 0)
@@ -407,80 +422,119 @@ __device__ __noinline__ void bin_slow(float d2, uint32_t oi, uint32_t oj, const 
         const uint32_t addr = S->sh_addr + 4u * (uint32_t)(((inter ? 2 : 0) + (swp ? 1 : 0)) * g.hs + b);
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
     } else {
-        ++*ov;
+        atomicAdd(&S->ov, 1ull);
         const long long flat = (long long)(swp ? S->slab_ba : S->slab_ab) * g.hs + b;
         if (g.spill && b >= 0 && flat < S->cells) atomicAdd(&S->counts[(inter ? S->cells : 0) + flat], 1ull);
     }
 }
 
-// every lane bins its own queue, four entries per trip: the shared-memory loads of the four first (queue, bin
-// edges), then the four counter updates.  Fast path per entry: approximate sqrt -> bin guess -> the two d^2 edges of
-// that bin confirm it (bin_table_kernel) -> one shared-memory increment.  Anything else is flagged and redone by
-// bin_slow() after the loop.
+// The bin pass: the warp empties all 32 queue columns TOGETHER.  Hit counts differ a lot from lane to lane (an I atom
+// on the near side of its sub-block sees several times the hits of one on the far side), so the concatenation of the
+// columns is cut into 32 equal runs: lane l bins entries [l*c, (l+1)*c), c = ceil(total / 32), walking from its first
+// (column, row) -- found by a 5-step search in the scanned column lengths -- across column ends.  What an entry needs
+// from its I atom (the original index) comes from the column owner's slot in the scratch words.  Two entries per
+// trip: the shared-memory loads of both (queue, bin edges) before the two counter updates.
+// Fast path per entry: approximate sqrt -> bin guess -> the two d^2 edges of that bin confirm it (bin_table_kernel)
+// -> one shared-memory increment.  Anything else goes through bin_slow().
 template <bool TABLE>
-__device__ __forceinline__ void drain_queue(uint32_t &wp, const WarpCtx &W, int hs, float inv_bin, float c0, unsigned long long &ov)
+__device__ __noinline__ uint32_t drain_queue(uint32_t wp, uint32_t wq, uint32_t oi, uint32_t off_swap, uint32_t sh_inter,
+                                             uint32_t tab_addr, uint32_t span, int hs, float inv_bin, float c0, SlowCtx *S)
 {
-    const int n = (int)((wp - W.w0) >> 8);
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
-    uint32_t slow = 0u;                                            // bit k: entry k of this lane needs bin_slow()
-    for (int k = 0; k < nmax; k += 4) {
-        float d2[4];
-        uint32_t oj[4];
-        float2 t[4];
-        int b[4];
+    const int lane = threadIdx.x & 31;
+    const uint32_t w0 = wq + 8u * (uint32_t)lane;
+    // scratch, one 16-byte record per NON-EMPTY column in lane order: {entries, original index of its I atom,
+    // entries of all columns before it, shared address of the column}
+    const uint32_t ws = wq + (uint32_t)V2_SCRATCH_OFF;
+    const int n = (int)((wp - w0) >> 8);
+    int incl = n;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return w0;
+    const unsigned occupied = __ballot_sync(0xffffffffu, n > 0);
+    const int n_cols = __popc(occupied);
+    if (n > 0) {
+        const uint32_t at = ws + 16u * (uint32_t)__popc(occupied & ((1u << lane) - 1u));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"((uint32_t)n), "r"(oi), "r"((uint32_t)(incl - n)), "r"(w0) : "memory");
+    }
+    __syncwarp();
+    const int c = (total + 31) >> 5;
+    const int f = lane * c;
+    const int cnt = min(c, total - f);                            // <= 0: nothing left for this lane
+    // the column holding entry f: the last record whose start (entries before it) is <= f
+    int col = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int probe = col + step;
+        if (probe < n_cols && (int)lds_u32(ws + 16u * (uint32_t)probe + 8u) <= f) col = probe;
+    }
+    uint4 rec;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(ws + 16u * (uint32_t)col));
+    int left = (int)rec.x - (f - (int)rec.z);                     // entries of this column from the lane's first one on
+    uint32_t src = rec.w + 256u * (uint32_t)(f - (int)rec.z);     // shared address of the lane's next entry
+    uint32_t oi_o = rec.y;
+    const uint32_t span2 = 2u * span;
+    for (int j = 0; j < c; j += 2) {
+        float d2[2];
+        uint32_t oj[2], oio[2];
+        float2 t[2];
+        int b[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            // every record holds at least one entry, so one step reaches the next entry (no loop, no branch)
+            if (left == 0 && j + u < cnt) {
+                ++col;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(ws + 16u * (uint32_t)col));
+                left = (int)rec.x; src = rec.w; oi_o = rec.y;
+            }
             uint2 e = make_uint2(0u, 0u);
-            if (k + j < n) e = lds_u64(W.w0 + (uint32_t)(k + j) * 256u);
-            d2[j] = __uint_as_float(e.x); oj[j] = e.y;
+            if (j + u < cnt) e = lds_u64(src);
+            src += 256u; --left;
+            d2[u] = __uint_as_float(e.x); oj[u] = e.y; oio[u] = oi_o;
         }
         if (TABLE) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int u = 0; u < 2; ++u) {
                 float s;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2[j]));
-                b[j] = max(0, min(__float2int_rz(__fmaf_rn(s, inv_bin, c0)), hs - 1));
-                t[j] = lds_f64(W.tab_addr + 8u * (uint32_t)b[j]);
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(d2[u]));
+                b[u] = max(0, min(__float2int_rz(__fmaf_rn(s, inv_bin, c0)), hs - 1));
+                t[u] = lds_f64(tab_addr + 8u * (uint32_t)b[u]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool live = (k + j < n);
-            const bool maybe_intra = (oj[j] - W.oi + W.span) <= W.span2;          // |oj - oi| <= span (unsigned wrap-around trick)
-            const bool sure = TABLE && (d2[j] >= t[j].x) && (d2[j] < t[j].y) && !maybe_intra;
-            if (live && sure) {
-                const uint32_t addr = W.sh_inter + ((W.oi > oj[j]) ? W.off_swap : 0u) + 4u * (uint32_t)b[j];
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-            } else if (live) {
-                slow |= 1u << (k + j);
+        for (int u = 0; u < 2; ++u) {
+            const bool maybe_intra = (oj[u] - oio[u] + span) <= span2;            // |oj - oi| <= span (unsigned wrap-around)
+            const bool sure = TABLE && (d2[u] >= t[u].x) && (d2[u] < t[u].y) && !maybe_intra;
+            if (j + u < cnt) {
+                if (sure) {
+                    const uint32_t addr = sh_inter + ((oio[u] > oj[u]) ? off_swap : 0u) + 4u * (uint32_t)b[u];
+                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                } else {
+                    bin_slow(d2[u], oio[u], oj[u], S);
+                }
             }
         }
     }
-    if (__any_sync(0xffffffffu, slow != 0u)) {
-        while (slow) {
-            const int k = __ffs(slow) - 1;
-            slow &= slow - 1u;
-            const uint2 e = lds_u64(W.w0 + (uint32_t)k * 256u);
-            bin_slow(__uint_as_float(e.x), W.oi, e.y, W.slow, &ov);
-        }
-    }
-    wp = W.w0;
     __syncwarp();
+    return w0;
 }
 
 // one staged J sub-block (32 sweep records) against the lane's I atom.  TRI (the unit on the diagonal of the I block):
-// only p < q counts, i.e. lane < record.  The queue (24 entries per lane) is emptied when a lane holds more than 8.
+// only p < q counts, i.e. lane < record.
 template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE, bool TRI>
 __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float xi, float yi, float zi, const Lattice &Lc,
                                            float t2min, float t2max, uint32_t &wp, const WarpCtx &W, int hs, float inv_bin,
-                                           float c0, unsigned long long &ov)
+                                           float c0)
 {
     Lattice L = Lc;               // lattice in plain registers: from the constant bank the compiler re-reads it every iteration
     if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
         asm volatile("" : "+f"(L.b[0]), "+f"(L.b[4]), "+f"(L.b[8]));
     }
     asm volatile("" : "+f"(t2min), "+f"(t2max));
-    const uint32_t wfull = W.w0 + (uint32_t)(V2_CAP - 16) * 256u;
+    const uint32_t wfull = W.w0 + (uint32_t)(V2_CAP - 8) * 256u;
     if constexpr (TRI) {
         const int lane = threadIdx.x & 31;
 #pragma unroll 1
@@ -491,29 +545,27 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float
                 asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2)), "r"(__float_as_uint(a.w)) : "memory");
                 wp += 256u;
             }
-            if ((q & 15) == 15 && __any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); drain_queue<TABLE>(wp, W, hs, inv_bin, c0, ov); }
+            if ((q & 7) == 7 && __any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); wp = drain_queue<TABLE>(wp, W.wq, W.oi, W.off_swap, W.sh_inter, W.tab_addr, W.span, hs, inv_bin, c0, (SlowCtx *)W.slow); }
         }
     } else {
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int c = 0; c < 4; ++c) {
+            // eight records in flight: loads first, then eight independent distance chains, then the pushes
+            float4 a[8];
+            float d2[8];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                // eight records in flight: loads first, then eight independent distance chains, then the pushes
-                float4 a[8];
-                float d2[8];
+            for (int u = 0; u < 8; ++u) a[u] = sJu[c * 8 + u];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = sJu[half * 16 + c * 8 + u];
+            for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])), "r"(__float_as_uint(a[u].w)) : "memory");
-                        wp += 256u;
-                    }
+            for (int u = 0; u < 8; ++u) {
+                if ((!HASMIN || d2[u] >= t2min) && (d2[u] < t2max)) {
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wp), "r"(__float_as_uint(d2[u])), "r"(__float_as_uint(a[u].w)) : "memory");
+                    wp += 256u;
                 }
             }
-            if (__any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); drain_queue<TABLE>(wp, W, hs, inv_bin, c0, ov); }
+            // the queue holds V2_CAP entries per lane: it is emptied when a lane could not take eight more
+            if (__any_sync(0xffffffffu, wp > wfull)) { __syncwarp(); wp = drain_queue<TABLE>(wp, W.wq, W.oi, W.off_swap, W.sh_inter, W.tab_addr, W.span, hs, inv_bin, c0, (SlowCtx *)W.slow); }
         }
     }
 }
@@ -723,7 +775,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     if (TABLE) off += (((size_t)g.hs + 1) * 8 + 15) & ~(size_t)15;
     unsigned char *wbase = smem_raw + off + (size_t)warp * V2_WARP_BYTES;
     float4 *sJ = reinterpret_cast<float4 *>(wbase + V2_Q_BYTES);
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_Q_BYTES + 2 * 32 * 16);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_MBAR_OFF);
     __shared__ int s_tasks, s_again, s_p0;
     __shared__ SlowCtx s_slow;
 
@@ -738,7 +790,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     if (tid == 0) {
         s_tasks = 0; s_again = 0;
         s_slow.g = g; s_slow.counts = A.counts; s_slow.mol = A.mol; s_slow.cells = cells;
-        s_slow.slab_ab = 0; s_slow.slab_ba = 0; s_slow.sh_addr = fh_smem_u32(sh); s_slow.cross = 0;
+        s_slow.slab_ab = 0; s_slow.slab_ba = 0; s_slow.sh_addr = fh_smem_u32(sh); s_slow.cross = 0; s_slow.ov = 0ull;
         // CTAs start on the element pair that holds their share of the items, so that a CTA stays on one pair
         // (one flush of its counters) for most of the launch; pairs are then visited cyclically
         const long long target = ((2ll * blockIdx.x + 1) * A.n_items) / (2ll * gridDim.x);
@@ -753,16 +805,16 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     const int p0 = s_p0;
 
     WarpCtx W;
-    W.w0 = fh_smem_u32(wbase) + 8u * (uint32_t)lane;
+    W.wq = fh_smem_u32(wbase);
+    W.w0 = W.wq + 8u * (uint32_t)lane;
     W.sh_inter = fh_smem_u32(sh) + 8u * (uint32_t)g.hs;
     W.tab_addr = fh_smem_u32(tab);
     W.off_swap = 0u; W.oi = 0u;
     W.span = (A.mol_span >= 0x40000000u) ? 0x7FFFFFFFu : A.mol_span;
-    W.span2 = 2u * W.span;
     W.slow = &s_slow;
     uint32_t wp = W.w0;
     const float inv_bin = TABLE ? __frcp_rn(g.bin) : 0.f, c0 = TABLE ? -g.rmin * inv_bin : 0.f;
-    unsigned long long ov = 0, swept = 0;
+    unsigned long long swept = 0;
     int slab_ab = 0, slab_ba = 0;
     unsigned seq = 0;                             // J sub-blocks this warp has streamed: stage = seq & 1, parity = (seq >> 1) & 1
     const float T = __int_as_float(0x3EFFFFFF);   // 0.5 - 2^-25: below it round() is 0 (common.cuh:wrap_fast)
@@ -843,18 +895,18 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                     const float4 *sJu = sJ + st * 32;
                     if ((m_tri >> bit) & 1u) {
                         if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
-                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
+                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
                         else
-                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
+                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
                     } else if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u)) {
-                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
+                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
                     } else {
-                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, ov);
+                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
                     }
                     ++seq;
                 }
                 __syncwarp();
-                drain_queue<TABLE>(wp, W, g.hs, inv_bin, c0, ov);          // the queue belongs to this task's I atoms
+                wp = drain_queue<TABLE>(wp, W.wq, W.oi, W.off_swap, W.sh_inter, W.tab_addr, W.span, g.hs, inv_bin, c0, &s_slow);   // the queue belongs to this task's I atoms
             }
             // ---- the CTA leaves the pair (or its 32-bit counters are due): counters -> global ordered histogram
             __syncthreads();
@@ -876,7 +928,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
             __syncthreads();
         }
     }
-    if (ov) atomicAdd(&A.stats[0], ov);
+    if (tid == 0 && s_slow.ov) atomicAdd(&A.stats[0], s_slow.ov);      // the last flush's barriers are behind every bin pass
     if (lane == 0 && swept) atomicAdd(&A.stats[1], swept);
 }
 
