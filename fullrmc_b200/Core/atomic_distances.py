@@ -32,10 +32,10 @@ def _limits(lowerLimit, upperLimit, nT):
 
 
 def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements,
-                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, reduceDistance=False,
-                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, countWithinLimits=True,
+                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, countWithinLimits=True,
+                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, reduceDistance=False,
                                      allAtoms=True, ncores=1):
-    """atomic_distances.pyx:326-417"""
+    """atomic_distances.pyx:326-417 (same positional order of the optional flags as the reference, :335-342)"""
     lib = L.load_library()
     idx = L.as_array(indexes, "indexes", _I32, 1)
     coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
@@ -59,9 +59,9 @@ def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeI
 
 
 def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, lowerLimit, upperLimit,
-                                 interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=False,
-                                 reduceDistanceToLower=False, countWithinLimits=True, ncores=1):
-    """atomic_distances.pyx:500-567 -- in within-limits mode the device sweeps only the block pairs of the k-d ordered
+                                 interMolecular=True, intraMolecular=True, reduceDistanceToUpper=False, reduceDistanceToLower=False,
+                                 reduceDistance=False, countWithinLimits=True, ncores=1):
+    """atomic_distances.pyx:500-567 (optional flags in the reference's positional order, :508-514) -- in within-limits mode the device sweeps only the block pairs of the k-d ordered
     store that can reach the largest upper limit (csrc/atomdist.cu: full_culled)"""
     lib = L.load_library()
     coords = L.as_array(boxCoords, "boxCoords", _F32, 2)

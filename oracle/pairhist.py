@@ -185,8 +185,8 @@ def _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUp
 
 
 def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements,
-                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, reduceDistance=False,
-                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, countWithinLimits=True,
+                                     lowerLimit, upperLimit, interMolecular=True, intraMolecular=True, countWithinLimits=True,
+                                     reduceDistanceToUpper=False, reduceDistanceToLower=False, reduceDistance=False,
                                      allAtoms=True, ncores=1):
     """atomic_distances.pyx:326-417; returns (nintra, dintra, ninter, dinter), each [nT, nT, 1]"""
     indexes, coords, basis = _i32(indexes), _f32(boxCoords), _f32(basis)
@@ -206,11 +206,12 @@ def multiple_atomic_distances_coords(indexes, boxCoords, basis, isPBC, moleculeI
 
 
 def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements, lowerLimit, upperLimit,
-                                 interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=False,
-                                 reduceDistanceToLower=False, countWithinLimits=True, ncores=1):
+                                 interMolecular=True, intraMolecular=True, reduceDistanceToUpper=False, reduceDistanceToLower=False,
+                                 reduceDistance=False, countWithinLimits=True, ncores=1):
     """atomic_distances.pyx:500-567"""
     coords = _f32(boxCoords)
     return multiple_atomic_distances_coords(np.arange(coords.shape[0], dtype=np.int32), coords, basis, isPBC, moleculeIndex,
-                                            elementIndex, numberOfElements, lowerLimit, upperLimit, interMolecular, intraMolecular,
-                                            reduceDistance, reduceDistanceToUpper, reduceDistanceToLower, countWithinLimits,
-                                            allAtoms=False, ncores=ncores)
+                                            elementIndex, numberOfElements, lowerLimit, upperLimit, interMolecular=interMolecular,
+                                            intraMolecular=intraMolecular, countWithinLimits=countWithinLimits,
+                                            reduceDistanceToUpper=reduceDistanceToUpper, reduceDistanceToLower=reduceDistanceToLower,
+                                            reduceDistance=reduceDistance, allAtoms=False, ncores=ncores)

@@ -81,7 +81,8 @@ def fake_engine(fullrmc, boxCoordinates, basisVectors, isPBC, moleculesIndex, el
                 numberOfAtoms=n, numberOfElements=len(elements),
                 # what Engine.run / set_groups / set_group_selector touch beyond the constraints' needs (Engine.py:256-300)
                 groups=[], groupSelector=None, tolerance=0., saveGroupsFlag=False, tolerated=0, removed=[0., 0., 0.],
-                totalStandardError=None, lastSelectedGroupIndex=None, path=None, timeout=10, id="fake", pdb=None)
+                totalStandardError=None, lastSelectedGroupIndex=None, path=None, timeout=10, id="fake",
+                pdb=type("PdbStandIn", (object,), {"numberOfAtoms": n})())     # add_group only asks it for numberOfAtoms
     for k, v in priv.items():
         object.__setattr__(E, "_Engine__" + k, v)
     object.__setattr__(E, "_runtime_ncores", np.int32(1))

@@ -92,3 +92,57 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "pairhist_oracle" not in text, f
+
+
+# positional order of every drop-in function = the reference's (Extensions/*.pyx); a positional caller must bind the
+# same arguments (round-1 advice: atomic_distances had its optional flags in a different order)
+SIGNATURES = {
+    "pairs_histograms": {
+        "single_pairs_histograms": "atomIndex distances moleculeIndex elementIndex hintra hinter minDistance maxDistance bin allAtoms ncores",
+        "multiple_pairs_histograms_coords": "indexes boxCoords basis isPBC moleculeIndex elementIndex numberOfElements minDistance maxDistance bin histSize allAtoms ncores",
+        "multiple_pairs_histograms_dists": "indexes distances moleculeIndex elementIndex numberOfElements minDistance maxDistance bin histSize allAtoms ncores",
+        "full_pairs_histograms_coords": "boxCoords basis isPBC moleculeIndex elementIndex numberOfElements minDistance maxDistance bin histSize ncores",
+        "full_pairs_histograms_dists": "distances moleculeIndex elementIndex numberOfElements minDistance maxDistance bin histSize ncores",
+    },
+    "pairs_distances": {
+        "pairs_distances_to_indexcoords": "atomIndex coords basis isPBC allAtoms ncores",
+        "pairs_distances_to_point": "point coords basis isPBC ncores",
+    },
+    "reciprocal_space": {
+        "gr_to_sq": "distances gr qrange rho",
+        "Gr_to_sq": "distances Gr qrange",
+    },
+    "atomic_distances": {
+        "multiple_atomic_distances_coords": "indexes boxCoords basis isPBC moleculeIndex elementIndex numberOfElements lowerLimit upperLimit "
+                                            "interMolecular intraMolecular countWithinLimits reduceDistanceToUpper reduceDistanceToLower "
+                                            "reduceDistance allAtoms ncores",
+        "full_atomic_distances_coords": "boxCoords basis isPBC moleculeIndex elementIndex numberOfElements lowerLimit upperLimit interMolecular "
+                                        "intraMolecular reduceDistanceToUpper reduceDistanceToLower reduceDistance countWithinLimits ncores",
+    },
+}
+
+
+def _pyx_signature(text, name):
+    """parameter names of `def name(...)` in a .pyx file, in order"""
+    import re
+    m = re.search(r"^def\s+%s\s*\((.*?)\)\s*:" % re.escape(name), text, re.S | re.M)
+    assert m, name
+    names = []
+    for part in re.sub(r"\[[^]]*\]", "", m.group(1)).split(","):     # typed-buffer brackets hold commas of their own
+        part = part.split("=")[0].replace("not None", "").strip()
+        names.append(part.split()[-1])
+    return names
+
+
+@pytest.mark.parametrize("module", sorted(SIGNATURES))
+def test_positional_order_equals_the_reference(module):
+    import importlib
+    import inspect
+    mod = importlib.import_module("fullrmc_b200.Core." + module)
+    pyx = os.path.join(os.environ.get("FULLRMC_REFERENCE", "/root/reference"), "Extensions", module + ".pyx")
+    text = open(pyx).read() if os.path.exists(pyx) else None
+    for name, want in SIGNATURES[module].items():
+        got = [p for p in inspect.signature(getattr(mod, name)).parameters if not p.startswith("_")]
+        assert got == want.split(), "%s.%s: %s" % (module, name, got)
+        if text is not None:                                  # in the build container: the table above IS the reference's
+            assert _pyx_signature(text, name) == want.split(), "%s.%s table differs from the .pyx" % (module, name)
