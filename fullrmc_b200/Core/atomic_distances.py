@@ -82,3 +82,33 @@ def full_atomic_distances_coords(boxCoords, basis, isPBC, moleculeIndex, element
         L.ptr(nintra, L.c_i32p), L.ptr(dintra, L.c_f32p), L.ptr(ninter, L.c_i32p), L.ptr(dinter, L.c_f32p))
     L.check(rc, "full_atomic_distances_coords")
     return nintra, dintra, ninter, dinter
+
+
+def pair_elements_stats(elementIndex, moleculeIndex, numberOfElements):
+    """atomic_distances.pyx:632-672 -- number of ordered pairs (i < j) per (element of i, element of j), split into
+    same-molecule and different-molecule pairs; no distances are involved.  The reference walks all N(N-1)/2 pairs;
+    the counts only depend on how many atoms of each element precede an atom (overall, and inside its molecule), so
+    they are formed here from prefix counts in O(N * numberOfElements) on the host -- set-up work of
+    ``set_type_definition`` (DistanceConstraints.py:525-541), not part of a Monte-Carlo step.  Accumulated in int64
+    and returned as int32 like the reference's arrays (the same wrap-around for systems beyond 2^31 pairs of a kind)."""
+    el = L.as_array(elementIndex, "elementIndex", _I32, 1)
+    mol = L.as_array(moleculeIndex, "moleculeIndex", _I32, 1)
+    nT = int(numberOfElements)
+    n = el.shape[0]
+    if mol.shape[0] != n:
+        raise ValueError("moleculeIndex length must equal the number of atoms (%d)" % n)
+    total = np.zeros((nT, nT), np.int64)
+    intra = np.zeros((nT, nT), np.int64)
+    if n > 1:
+        onehot = (el[:, None] == np.arange(nT, dtype=_I32)[None, :])            # [n, nT]
+        before = np.cumsum(onehot, axis=0, dtype=np.int64) - onehot             # atoms of each element strictly before j
+        total = before.T @ onehot.astype(np.int64)                              # [a, b] = sum_j [el_j = b] * #(i < j, el_i = a)
+        order = np.argsort(mol, kind="stable")                                  # molecule by molecule, original order inside
+        oh = onehot[order]
+        cs = np.cumsum(oh, axis=0, dtype=np.int64) - oh
+        first = np.r_[True, mol[order][1:] != mol[order][:-1]]                  # first atom of each molecule in the sorted list
+        base = cs[first][np.cumsum(first) - 1]                                  # prefix counts at the start of the atom's molecule
+        intra = (cs - base).T @ oh.astype(np.int64)
+    inter = total - intra
+    return (np.ascontiguousarray(intra.astype(_I32).reshape(nT, nT, 1)),
+            np.ascontiguousarray(inter.astype(_I32).reshape(nT, nT, 1)))

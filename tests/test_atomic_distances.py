@@ -102,3 +102,20 @@ def test_argument_checks_like_the_reference():
         ad.full_atomic_distances_coords(box, basis, True, mol, el, nT, np.zeros((3, 3, 1), np.float32), lim)
     r = ad.full_atomic_distances_coords(box, basis, True, mol, el, nT, lim, lim + 1)     # all atoms coincide: d = 0 in [0, 1)
     assert int(r[0].sum()) == n * (n - 1) // 2 and float(r[1].sum()) == 0.0
+
+
+def test_pair_elements_stats_equals_the_compiled_reference(ref_modules):
+    """host-side prefix-count form of atomic_distances.pyx:632-672 against the reference's O(N^2) loop (no GPU involved)"""
+    import importlib
+    if ref_modules is None:
+        pytest.skip("oracle/_ref not built")
+    ref = importlib.import_module("fullrmc.Core.atomic_distances")
+    from fullrmc_b200.Core import atomic_distances as ad
+    rng = np.random.default_rng(0)
+    for n, nT, msize in ((1, 2, 1), (2, 2, 1), (500, 3, 13), (777, 4, 1), (600, 2, 600), (900, 5, 7)):
+        el = rng.integers(0, nT, n).astype(np.int32)
+        mol = (rng.permutation(n) // msize).astype(np.int32)              # molecules scattered over the index range
+        want = ref.pair_elements_stats(elementIndex=el, moleculeIndex=mol, numberOfElements=nT)
+        got = ad.pair_elements_stats(elementIndex=el, moleculeIndex=mol, numberOfElements=nT)
+        assert np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
+        assert got[0].dtype == np.int32 and got[0].shape == (nT, nT, 1)
