@@ -51,6 +51,7 @@ SIGNATURES = {
     "frmc_device_count": (_I, []),
     "frmc_set_edge_spill": (_I, [_I]),
     "frmc_set_block_culling": (_I, [_I]),
+    "frmc_set_device_layout": (_I, [_I]),
     "frmc_launch_count": (ctypes.c_uint64, []),
     "frmc_points_to_coords": (_I, [_I, c_f32p, c_i32p, c_i64p, _I64, c_f32p, _I64, c_f32p, _I, _I, _I, c_f32p]),
     "frmc_from_to_points_differences": (_I, [_I, c_f32p, c_f32p, _I64, c_f32p, _I, c_f32p]),
@@ -66,6 +67,7 @@ SIGNATURES = {
                                       _I64, c_i64p, c_i32p, _I64, c_i32p]),
     "frmc_debug_work_items": (_I, [_I64, c_i32p, _I, _I, _I, _I, c_i64p, c_i64p]),
     "frmc_debug_layout": (_I, [_I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
+    "frmc_debug_device_layout": (_I, [_I, _I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,
                                                   _I, c_f32p, c_f32p, c_u64p]),
     "frmc_single_pairs_histograms": (_I, [_I, ctypes.c_int32, c_f32p, _I64, _I64, c_i32p, c_i32p, _I, _I, c_f32p,
@@ -168,6 +170,12 @@ def set_edge_spill(on):
 def set_block_culling(on):
     """Full-histogram block culling (default on; results are identical either way).  Returns the previous setting."""
     return bool(load_library().frmc_set_block_culling(int(bool(on))))
+
+
+def set_device_layout(on):
+    """Stateless full histogram: order the caller's atoms on the device (default) or on the host cores.  Identical
+    histograms either way.  Returns the previous setting."""
+    return bool(load_library().frmc_set_device_layout(int(bool(on))))
 
 
 def device_index():

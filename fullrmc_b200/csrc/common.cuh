@@ -235,7 +235,7 @@ __device__ __forceinline__ bool bin_of_distance(float d, const GridParams &g, in
 struct DeviceCtx {
     int dev = -1;
     cudaStream_t stream = nullptr;
-    static const int NBUF = 12;
+    static const int NBUF = 24;
     void *buf[NBUF] = {nullptr};
     size_t cap[NBUF] = {0};
     void *pinned = nullptr;

@@ -33,6 +33,7 @@ namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int g_no_cull = 0;
+int g_device_layout = 1;      // stateless full histogram: order the caller's atoms on the device (devlayout.cu)
 
 // ------------------------------------------------------------------ host: layout + row list
 // k-d ordering of one element's atoms: split the longest box axis at a record count that is a multiple
@@ -1116,6 +1117,13 @@ using namespace frmc;
 // Host-only inspection of the multi-GPU decomposition (no device needed): number of work items and
 // of atom pairs covered by shard `shard` of `nshards` for a system with the given element indexes.
 // Summed over the shards the pair count is n(n-1)/2; used by the CPU tests of the sharding logic.
+extern "C" int frmc_set_device_layout(int on)
+{
+    int old = g_device_layout;
+    g_device_layout = on ? 1 : 0;
+    return old;
+}
+
 extern "C" int frmc_set_block_culling(int on)
 {
     int old = !g_no_cull;
@@ -1135,6 +1143,26 @@ extern "C" int frmc_debug_layout(int64_t n, const float *coords, const int32_t *
     if (rc) return rc;
     FRMC_REQUIRE(capacity >= lay.npad, FRMC_EINVAL, "orig_out holds %lld records, the layout has %lld", (long long)capacity, (long long)lay.npad);
     for (int64_t p = 0; p < lay.npad; ++p) orig_out[p] = lay.orig[(size_t)p];
+    for (int e = 0; e <= nEl; ++e) seg_start_out[e] = lay.seg_start[(size_t)e];
+    *npad_out = lay.npad;
+    return FRMC_OK;
+}
+
+// The same inspection for the layout built on the device (devlayout.cu); needs a device.
+extern "C" int frmc_debug_device_layout(int dev, int64_t n, const float *coords, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
+                                        int64_t capacity, uint32_t *orig_out, int64_t *npad_out, int64_t *seg_start_out)
+{
+    FRMC_REQUIRE(n >= 0 && coords && mol && el && orig_out && npad_out && seg_start_out, FRMC_EINVAL, "bad arguments");
+    DeviceCtx *c = get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    HostLayout lay;
+    float4 *d_atoms = nullptr;
+    uint32_t *d_orig = nullptr;
+    int rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig);
+    if (rc) return rc;
+    FRMC_REQUIRE(capacity >= lay.npad, FRMC_EINVAL, "orig_out holds %lld records, the layout has %lld", (long long)capacity, (long long)lay.npad);
+    if (lay.npad > 0) FRMC_CUDA(cudaMemcpyAsync(orig_out, d_orig, sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyDeviceToHost, c->stream));
+    FRMC_CUDA(cudaStreamSynchronize(c->stream));
     for (int e = 0; e <= nEl; ++e) seg_start_out[e] = lay.seg_start[(size_t)e];
     *npad_out = lay.npad;
     return FRMC_OK;
@@ -1186,24 +1214,26 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     const int64_t cells = (int64_t)nEl * nEl * hs;
     DeviceCtx *c = get_ctx(dev);
     if (!c) return FRMC_ECUDA;
-    // the layout scratch lives for the thread: repeated calls (an Engine calling compute_data) reuse its pages, and
-    // the two arrays that travel to the device are page-locked once per growth so the H2D copies run at link speed
+    // the store layout of the caller's arrays: built on the device (devlayout.cu: raw arrays up, one small read-back);
+    // frmc_set_device_layout(0) keeps the host k-d ordering of build_layout() instead (same histogram either way)
     static thread_local HostLayout lay;
-    static thread_local void *pinned_rec = nullptr, *pinned_orig = nullptr;
-    {
-        const size_t need = (size_t)n + (size_t)SEG_PAD * nEl;
-        auto pin = [](auto &vec, size_t need_elems, void *&reg) {
-            if (vec.capacity() >= need_elems && reg == (void *)vec.data()) return;
-            if (reg) { cudaHostUnregister(reg); reg = nullptr; }
-            if (vec.capacity() < need_elems) vec.reserve(need_elems + need_elems / 4);
-            if (cudaHostRegister(vec.data(), vec.capacity() * sizeof(vec[0]), cudaHostRegisterPortable) == cudaSuccess) reg = vec.data();
-            else cudaGetLastError();            // pageable copies still work
-        };
-        pin(lay.rec, need * 4, pinned_rec);
-        pin(lay.orig, need, pinned_orig);
+    float4 *d_atoms = nullptr;
+    uint32_t *d_orig = nullptr;
+    int rc;
+    if (g_device_layout) {
+        rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig);
+        if (rc) return rc;
+    } else {
+        rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
+        if (rc) return rc;
+        d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float) * 4 * (size_t)lay.npad);
+        d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);
+        if (!d_atoms || !d_orig) return FRMC_ENOMEM;
+        if (lay.npad > 0) {
+            FRMC_CUDA(cudaMemcpyAsync(d_atoms, lay.rec.data(), sizeof(float) * 4 * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
+            FRMC_CUDA(cudaMemcpyAsync(d_orig, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
+        }
     }
-    int rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
-    if (rc) return rc;
     Lattice L;
     for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     GridParams g = make_grid(rmin, rmax, bin, hs);
@@ -1214,19 +1244,13 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     int n_pairs = 0;
     pack_rows(items, blob, n_pairs);
 
-    float4 *d_atoms = (float4 *)ctx_buffer(c, 0, sizeof(float) * 4 * (size_t)lay.npad);
-    uint32_t *d_orig = (uint32_t *)ctx_buffer(c, 1, sizeof(uint32_t) * (size_t)lay.npad);
     WorkItem *d_items = (WorkItem *)ctx_buffer(c, 2, blob.size());
     unsigned long long *d_counts = (unsigned long long *)ctx_buffer(c, 4, sizeof(unsigned long long) * (2 * cells + 3));
     float4 *d_bbox = (float4 *)ctx_buffer(c, 3, sizeof(float4) * 18 * (size_t)(lay.npad / SEG_PAD + 1));
     float *d_out = (float *)ctx_buffer(c, 5, sizeof(float) * 2 * cells);
-    if (!d_atoms || !d_orig || !d_items || !d_counts || !d_out || !d_bbox) return FRMC_ENOMEM;
+    if (!d_items || !d_counts || !d_out || !d_bbox) return FRMC_ENOMEM;
     unsigned long long *d_ov = d_counts + 2 * cells;
     FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (2 * cells + 3), c->stream));
-    if (lay.npad > 0) {
-        FRMC_CUDA(cudaMemcpyAsync(d_atoms, lay.rec.data(), sizeof(float) * 4 * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
-        FRMC_CUDA(cudaMemcpyAsync(d_orig, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c->stream));
-    }
     if (!items.empty()) {
         FRMC_CUDA(cudaMemcpyAsync(d_items, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
         int32_t *d_mol = nullptr;                      // only molecular systems ever read it

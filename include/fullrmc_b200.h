@@ -55,11 +55,15 @@ const char *frmc_version(void);
  * dropped; on=1: the in-array spill is reproduced so trajectories stay bit-identical to the
  * reference's.  Either way they are counted in edge_overflow.  Returns the previous setting. */
 int frmc_set_edge_spill(int on);
-/* Block culling of the full-histogram kernels (default on): atoms are stored in Morton order, each
- * 256-atom block carries a bounding box, and block pairs provably farther apart than maxDistance are
- * not swept.  The result is identical either way (tests sweep both); on=0 forces the reference's plain
- * O(N^2) sweep, for measurement.  Returns the previous setting. */
+/* Block culling of the full-histogram kernels (default on): atoms are stored element by element in k-d order,
+ * each 256-atom block and each 32-atom sub-block carries a bounding box, and block pairs provably farther apart
+ * than maxDistance are not swept.  The result is identical either way (tests sweep both); on=0 forces the
+ * reference's plain O(N^2) sweep, for measurement.  Returns the previous setting. */
 int frmc_set_block_culling(int on);
+/* Where the stateless full histogram orders the caller's atoms (default on = on the device, csrc/devlayout.cu:
+ * raw arrays are uploaded as they are; off = k-d ordering on the host cores before the upload).  The histogram is
+ * identical either way.  Returns the previous setting. */
+int frmc_set_device_layout(int on);
 /* number of visible CUDA devices, or a negative error code (no CPU fallback exists) */
 int frmc_device_count(void);
 
@@ -111,6 +115,9 @@ int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, c
  * every element (nEl + 1 values).  orig_out must hold n + 256 * nEl records. */
 int frmc_debug_layout(int64_t n, const float *coords, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
                       int64_t capacity, uint32_t *orig_out, int64_t *npad_out, int64_t *seg_start_out);
+/* The same inspection of the layout the DEVICE builds for the stateless full histogram (csrc/devlayout.cu). */
+int frmc_debug_device_layout(int dev, int64_t n, const float *coords, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
+                             int64_t capacity, uint32_t *orig_out, int64_t *npad_out, int64_t *seg_start_out);
 /* Host-only view of the multi-GPU decomposition of the full histogram (runs without a device):
  * work items and atom pairs assigned to `shard` of `nshards`; over all shards the pairs sum to n(n-1)/2. */
 int frmc_debug_work_items(int64_t n, const int32_t *el, int nEl, int shard, int nshards, int sm_count,

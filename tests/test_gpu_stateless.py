@@ -351,3 +351,18 @@ def test_reciprocal_space_functions(golden, orc):
     want = np.array([(2 / np.pi) * np.sum(q.astype(np.float64) * (golden["recip/Gr_to_sq"].astype(np.float64) - 1) *
                                           np.sin(q.astype(np.float64) * float(rr)) * dq) for rr in r[:50]])
     assert np.max(np.abs(Gr - want)) <= 5e-5 * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_device_and_host_layout_give_the_same_histogram(case, ph, orc):
+    """the stateless full histogram orders the atoms on the device by default (csrc/devlayout.cu); the host k-d ordering
+    (frmc_set_device_layout(0)) and the oracle must give the identical arrays"""
+    from fullrmc_b200 import _lib
+    want = orc.full_pairs_histograms_coords(boxCoords=case["boxCoords"], ncores=orc.max_threads(), **_kw(case))
+    for on in (True, False):
+        previous = _lib.set_device_layout(on)
+        try:
+            got = ph.full_pairs_histograms_coords(boxCoords=case["boxCoords"], **_kw(case))
+        finally:
+            _lib.set_device_layout(previous)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), "device layout %s" % on

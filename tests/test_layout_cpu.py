@@ -11,7 +11,7 @@ from fullrmc_b200 import _lib as L
 PAD = 0xFFFFFFFF
 
 
-def _layout(coords, el, nEl, isPBC=True, mol=None):
+def _layout(coords, el, nEl, isPBC=True, mol=None, device=False):
     lib = L.load_library()
     n = coords.shape[0]
     coords = np.ascontiguousarray(coords, dtype=np.float32)
@@ -21,21 +21,36 @@ def _layout(coords, el, nEl, isPBC=True, mol=None):
     orig = np.empty(cap, dtype=np.uint32)
     npad = ctypes.c_int64(0)
     seg = np.zeros(nEl + 1, dtype=np.int64)
-    L.check(lib.frmc_debug_layout(n, L.ptr(coords, L.c_f32p), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p), nEl, int(isPBC), cap,
-                                  orig.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(npad),
-                                  L.ptr(seg, L.c_i64p)), "debug_layout")
+    args = (n, L.ptr(coords, L.c_f32p), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p), nEl, int(isPBC), cap,
+            orig.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(npad), L.ptr(seg, L.c_i64p))
+    if device:                                                   # the layout the device builds (csrc/devlayout.cu)
+        L.check(lib.frmc_debug_device_layout(L.device_index(), *args), "debug_device_layout")
+    else:
+        L.check(lib.frmc_debug_layout(*args), "debug_layout")
     return orig[:npad.value], seg
 
 
-@pytest.mark.parametrize("n,nEl,pbc,spread", [(1, 1, True, 0.0), (300, 3, True, 0.0), (5000, 2, False, 0.0), (70000, 5, True, 0.0),
-                                              (40000, 4, True, 2.5)])
+SHAPES = [(1, 1, True, 0.0), (300, 3, True, 0.0), (5000, 2, False, 0.0), (70000, 5, True, 0.0), (40000, 4, True, 2.5)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nEl,pbc,spread", SHAPES + [(1025, 1, True, 0.0), (200000, 1, True, 0.0), (33, 16, False, 0.0)])
+def test_device_layout_is_an_element_sorted_permutation(n, nEl, pbc, spread):
+    _check_permutation(n, nEl, pbc, spread, device=True)
+
+
+@pytest.mark.parametrize("n,nEl,pbc,spread", SHAPES)
 def test_layout_is_an_element_sorted_permutation(n, nEl, pbc, spread):
+    _check_permutation(n, nEl, pbc, spread, device=False)
+
+
+def _check_permutation(n, nEl, pbc, spread, device):
     rng = np.random.default_rng(n + nEl)
     coords = (rng.random((n, 3)) * (1 + 2 * spread) - spread).astype(np.float32)
     if not pbc:
         coords = (coords * 80.0 - 13.0).astype(np.float32)
     el = rng.integers(0, nEl, n).astype(np.int32)
-    orig, seg = _layout(coords, el, nEl, pbc)
+    orig, seg = _layout(coords, el, nEl, pbc, device=device)
     assert orig.shape[0] == seg[-1] and orig.shape[0] % 256 == 0
     real = orig[orig != PAD]
     assert np.array_equal(np.sort(real), np.arange(n, dtype=np.uint32))          # every atom exactly once
@@ -46,18 +61,27 @@ def test_layout_is_an_element_sorted_permutation(n, nEl, pbc, spread):
         assert np.all(block[:cnt] != PAD) and np.all(block[cnt:] == PAD)          # padding only at the end of a segment
         assert np.all(el[block[:cnt]] == e)
     # deterministic
-    orig2, _ = _layout(coords, el, nEl, pbc)
+    orig2, _ = _layout(coords, el, nEl, pbc, device=device)
     assert np.array_equal(orig, orig2)
+
+
+@pytest.mark.gpu
+def test_device_kd_order_makes_compact_blocks():
+    _check_compact(device=True)
 
 
 def test_kd_order_makes_compact_blocks():
     """uniform points: aligned runs of 256 (and 32) records must be boxes of about the ideal volume; a random order
     of the same points would give boxes spanning the whole cell"""
+    _check_compact(device=False)
+
+
+def _check_compact(device):
     rng = np.random.default_rng(5)
     n = 120000
     coords = rng.random((n, 3)).astype(np.float32)
     el = rng.integers(0, 2, n).astype(np.int32)
-    orig, seg = _layout(coords, el, 2, True)
+    orig, seg = _layout(coords, el, 2, True, device=device)
     for blk, slack in ((256, 2.0), (32, 3.0)):
         vols = []
         for e in range(2):
