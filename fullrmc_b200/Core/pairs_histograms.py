@@ -118,10 +118,11 @@ def multiple_pairs_histograms_dists(indexes, distances, moleculeIndex, elementIn
 
 
 def full_pairs_histograms_coords(boxCoords, basis, isPBC, moleculeIndex, elementIndex, numberOfElements,
-                                 minDistance, maxDistance, bin, histSize, ncores=1, _shard=0, _nshards=1):
+                                 minDistance, maxDistance, bin, histSize, ncores=1, _shard=0, _nshards=1, _devices=None):
     """pairs_histograms.pyx:289-335 -- ordered upper triangle [el[i], el[j]], i<j, over the
-    whole system (tiled CUDA kernel).  ``_shard/_nshards`` (not part of the reference
-    signature) select one slice of the tile work list for one-process-per-GPU runs."""
+    whole system (CUDA sweep).  Not part of the reference signature: ``_shard/_nshards`` select one slice
+    of the row list for one-process-per-GPU runs; ``_devices`` (default: $FULLRMC_B200_DEVICES) spreads ONE call
+    over several GPUs of the box, the integer counts combined by an NCCL all-reduce inside the library."""
     lib = L.load_library()
     coords = L.as_array(boxCoords, "boxCoords", _F32, 2)
     basis = L.as_array(basis, "basis", _F32, 2)
@@ -135,7 +136,17 @@ def full_pairs_histograms_coords(boxCoords, basis, isPBC, moleculeIndex, element
     hintra = np.empty((nEl, nEl, hs), dtype=_F32)
     hinter = np.empty((nEl, nEl, hs), dtype=_F32)
     ov = ctypes.c_uint64(0)
-    rc = lib.frmc_full_pairs_histograms_coords(L.device_index(), L.ptr(coords, L.c_f32p), n, L.ptr(basis, L.c_f32p),
+    devices = L.device_list() if _devices is None else [int(d) for d in _devices]
+    if len(devices) > 1 and int(_nshards) == 1:
+        devs = (ctypes.c_int * len(devices))(*devices)
+        rc = lib.frmc_full_pairs_histograms_coords_multi(len(devices), devs, L.ptr(coords, L.c_f32p), n, L.ptr(basis, L.c_f32p),
+                                                         int(bool(isPBC)), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p), nEl,
+                                                         float(_F32(minDistance)), float(_F32(maxDistance)), float(_F32(bin)), hs,
+                                                         L.ptr(hintra, L.c_f32p), L.ptr(hinter, L.c_f32p), ctypes.byref(ov))
+        L.check(rc, "full_pairs_histograms_coords (%d devices)" % len(devices))
+        _set_overflow(ov.value)
+        return hintra, hinter
+    rc = lib.frmc_full_pairs_histograms_coords(devices[0] if _devices is not None else L.device_index(), L.ptr(coords, L.c_f32p), n, L.ptr(basis, L.c_f32p),
                                                int(bool(isPBC)), L.ptr(mol, L.c_i32p), L.ptr(el, L.c_i32p), nEl,
                                                float(_F32(minDistance)), float(_F32(maxDistance)), float(_F32(bin)),
                                                hs, int(_shard), int(_nshards), L.ptr(hintra, L.c_f32p),

@@ -66,6 +66,9 @@ SIGNATURES = {
     "frmc_coordination_counts": (_I, [_I, c_f32p, _I64, c_f32p, _I, c_f32p, _I64, _I64, c_i32p, c_i32p, c_i32p, c_f32p, c_f32p,
                                       _I64, c_i64p, c_i32p, _I64, c_i32p]),
     "frmc_debug_work_items": (_I, [_I64, c_i32p, _I, _I, _I, _I, c_i64p, c_i64p]),
+    "frmc_full_pairs_histograms_coords_multi": (_I, [_I, ctypes.POINTER(ctypes.c_int), c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, _F, _F, _F, _I,
+                                                     c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64)]),
+    "frmc_multi_reduce_path": (ctypes.c_char_p, []),
     "frmc_debug_layout": (_I, [_I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_debug_device_layout": (_I, [_I, _I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,
@@ -185,6 +188,17 @@ def device_index():
         if v is not None and v != "":
             return int(v)
     return 0
+
+
+def device_list():
+    """Devices the stateless full histogram spreads over: $FULLRMC_B200_DEVICES = "0,1,2,3" or "all" (one Python
+    process, several GPUs: frmc_full_pairs_histograms_coords_multi); unset = the single device of device_index()."""
+    v = os.environ.get("FULLRMC_B200_DEVICES", "").strip()
+    if not v:
+        return [device_index()]
+    if v.lower() == "all":
+        return list(range(int(load_library().frmc_device_count())))
+    return [int(x) for x in v.split(",") if x.strip() != ""]
 
 
 # ---------------------------------------------------------------- argument validation

@@ -14,7 +14,7 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
 if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
 OBJS=()
 PIDS=()
-for f in common stateless fullhist devlayout store atomdist coordnum; do
+for f in common stateless fullhist devlayout multigpu store atomdist coordnum; do
   rm -f "$OUT/$f.o"                     # a failed compile must never leave a stale object for the link step
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   PIDS+=("$!")
@@ -23,5 +23,5 @@ done
 for pid in "${PIDS[@]}"; do
   wait "$pid" || { echo "nvcc failed (pid $pid)" >&2; exit 1; }
 done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libfullrmc_b200.so" "${OBJS[@]}" -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libfullrmc_b200.so" "${OBJS[@]}" -lcudart -ldl
 echo "built $OUT/libfullrmc_b200.so"

@@ -16,6 +16,7 @@ namespace frmc {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char *fmt, ...);
+const char *last_error();                  // of the calling thread
 extern unsigned long long g_launch_count;   // kernels launched by this library
 
 #define FRMC_CUDA(call)                                                                      \

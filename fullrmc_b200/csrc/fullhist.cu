@@ -1114,6 +1114,15 @@ int launch_counts64_to_float(cudaStream_t stream, const unsigned long long *coun
 
 using namespace frmc;
 
+namespace frmc {
+// per device, grow-only, like the context's scratch buffers
+PairLists &stateless_lists_for(int dev)
+{
+    static PairLists lists[64];
+    return lists[dev & 63];
+}
+}  // namespace frmc
+
 // Host-only inspection of the multi-GPU decomposition (no device needed): number of work items and
 // of atom pairs covered by shard `shard` of `nshards` for a system with the given element indexes.
 // Summed over the shards the pair count is n(n-1)/2; used by the CPU tests of the sharding logic.
@@ -1259,9 +1268,8 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
             if (!d_mol) return FRMC_ENOMEM;
             FRMC_CUDA(cudaMemcpyAsync(d_mol, mol, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
         }
-        static PairLists stateless_lists[64];          // per device, grow-only, like the context's scratch buffers
         rc = full_hist_launch(c->stream, c->sm_count, mode, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), n_pairs,
-                              stateless_lists[c->dev & 63], d_mol, lay.mol_span, L, g, nEl, d_counts, d_ov);
+                              stateless_lists_for(c->dev), d_mol, lay.mol_span, L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);

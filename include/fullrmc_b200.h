@@ -110,6 +110,19 @@ int frmc_full_pairs_histograms_coords(int dev, const float *coords, int64_t n, c
                                       float rmax, float bin, int hs, int shard, int nshards,
                                       float *hintra, float *hinter, uint64_t *edge_overflow);
 
+/* The same histogram over `ndev` GPUs of one box from ONE call of one process ("shards + NCCL
+ * inside"; what an unmodified Engine's compute_data reaches through fullrmc_b200.Core.pairs_histograms when
+ * $FULLRMC_B200_DEVICES lists several devices): devs[0] orders the atoms and copies the store to the others over
+ * NVLink, every device sweeps its share of the triangular row list, one ncclAllReduce(sum) of the 64-bit counts
+ * (in-process communicator, ncclCommInitAll once per device set; libnccl.so.2 is loaded at run time,
+ * $FULLRMC_B200_NCCL overrides its path), devs[0] returns the arrays.  Identical to the one-device result. */
+int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs, const float *coords, int64_t n, const float *basis,
+                                            int isPBC, const int32_t *mol, const int32_t *el, int nEl, float rmin,
+                                            float rmax, float bin, int hs, float *hintra, float *hinter,
+                                            uint64_t *edge_overflow);
+/* how the last multi-device call combined the devices' counts: "nccl <version> x<ndev>" or "single device" */
+const char *frmc_multi_reduce_path(void);
+
 /* Host-only inspection of the store layout (no device needed): original index of every record of the
  * element-sorted, k-d ordered store (0xFFFFFFFF = padding), padded record count, padded segment start of
  * every element (nEl + 1 values).  orig_out must hold n + 256 * nEl records. */
