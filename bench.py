@@ -33,6 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 HS, BIN, NQ = 1000, 0.02, 400
+HBM_GBS = 6650.0            # replaced by MEASURED_PEAKS.json:hbm_gbs in run_b200
 METRIC = "RMC move evals/s (PDF+S(Q)); full pair-histogram Gpairs/s at 1/2/4/8 B200"
 
 
@@ -462,11 +463,21 @@ def distance_leg(system, no_cpu):
     for _ in range(reps):
         nintra, dintra, ninter, dinter = ad.full_atomic_distances_coords(**kw)
     dt = (time.perf_counter() - t0) / reps
+    launches = (int(lib.frmc_launch_count()) - l0) // reps
+    _, ms_kernel = _lib.kernel_ms_of(lambda: ad.full_atomic_distances_coords(**kw))
+    # the block sweep reads every 16-byte record of a surviving (256 x 256) block pair once per I block from L2 / shared
+    # memory; its algorithmic HBM traffic is one pass over the store (20 B/atom): an issue-bound kernel like the
+    # histogram sweep.  Reported against the same fp32-issue ceiling (general basis: 37 slots per evaluation).
     out = {"metric": "full_atomic_distances_coords Gpairs/s", "workload": "cfg4: %d atoms, %d types, window [0, 1.5 A), inter-molecular, "
            "reduced to upper" % (n, nT), "e2e": {"value": n_pairs(n) / dt / 1e9, "unit": "Gpairs/s", "ms_per_call": 1e3 * dt,
            "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 16 * nT * nT, "api": "fullrmc_b200.Core.atomic_distances.full_atomic_distances_coords"},
-           "pairs_counted": int(ninter.sum()), "gpu_launches": (int(lib.frmc_launch_count()) - l0) // reps,
-           "roofline": None, "note": "stateless version of this row: k-d ordered store + block culling against the largest upper "
+           "pairs_counted": int(ninter.sum()), "gpu_launches": launches, "kernel_ms": ms_kernel,
+           "value": n_pairs(n) / (ms_kernel * 1e-3) / 1e9, "unit": "Gpairs/s (device time of the block sweep)",
+           "roofline": {"bound": "hbm", "achieved": 20.0 * n / (ms_kernel * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s",
+                        "frac": 20.0 * n / (ms_kernel * 1e-3) / 1e9 / HBM_GBS, "traffic": None,
+                        "note": "algorithmic bytes = one pass over the 20 B/atom store; the sweep itself is issue-bound on the block pairs "
+                                "within the largest upper limit, so the fraction is small by construction"},
+           "note": "stateless version of this row: k-d ordered store + block culling against the largest upper "
            "limit, hits sorted and summed in the reference's order; the call is dominated by host ordering, copies and syncs"}
     if not no_cpu:
         from oracle import build_ref
@@ -511,12 +522,21 @@ def coordination_leg(system, no_cpu):
         data = np.zeros(3, np.float32)
         ac.all_atoms_coord_number_coords(boxCoords=system.boxCoords, coordNumData=data, **kw)
     dt = (time.perf_counter() - t0) / reps
+    launches = (int(lib.frmc_launch_count()) - l0) // reps
+    _, ms_kernel = _lib.kernel_ms_of(lambda: ac.all_atoms_coord_number_coords(boxCoords=system.boxCoords, coordNumData=np.zeros(3, np.float32), **kw))
+    # every distance test gathers one 16-byte position + one 4-byte list index: L2-resident
+    gathered = 20.0 * tests
     out = {"metric": "all_atoms_coord_number_coords G distance tests/s", "workload": "cfg4: %d atoms, 3 definitions, shell [1.5, 3.5] A, "
            "%.3g distance tests per call" % (n, tests), "e2e": {"value": tests / dt / 1e9, "unit": "G tests/s", "ms_per_call": 1e3 * dt,
            "h2d_bytes_per_step": 12 * n + 24 * sum(len(a) + len(b) for a, b in zip(as_core, in_shell)), "d2h_bytes_per_step": 12,
            "api": "fullrmc_b200.Core.atomic_coordination.all_atoms_coord_number_coords"},
-           "coordination_numbers": [float(x) for x in data / 2], "gpu_launches": (int(lib.frmc_launch_count()) - l0) // reps,
-           "roofline": None, "note": "stateless first version of this row: one launch over (atom, definition) tasks cut into 2048-entry "
+           "coordination_numbers": [float(x) for x in data / 2], "gpu_launches": launches, "kernel_ms": ms_kernel,
+           "value": tests / (ms_kernel * 1e-3) / 1e9, "unit": "G tests/s (device time of the counting kernel)",
+           "roofline": {"bound": "hbm", "achieved": gathered / (ms_kernel * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s (gathered bytes, L2 resident)",
+                        "frac": gathered / (ms_kernel * 1e-3) / 1e9 / HBM_GBS, "traffic": None,
+                        "note": "algorithmic bytes = 20 B gathered per distance test (16 B position + 4 B list index); the lists are L2 "
+                                "resident, so a figure above the HBM peak means L2 reuse, not DRAM traffic"},
+           "note": "stateless first version of this row: one launch over (atom, definition) tasks cut into 2048-entry "
            "items; the call is dominated by flattening the Python lists on the host"}
     # a per-move call (one atom, as compute_before_move makes it): latency of the host-buffer call
     idx = np.array([n // 2], np.int32)
@@ -539,6 +559,316 @@ def coordination_leg(system, no_cpu):
     return out
 
 
+
+# ----------------------------------------------------------------------------- parity against the committed fixtures
+def golden(name):
+    path = os.path.join(ROOT, "tests", "golden", name)
+    return np.load(path) if os.path.exists(path) else None
+
+
+def full_histogram_parity(tag, intra, inter, overflow=None):
+    """the arrays of a timed step against tests/golden/full_<tag>.npz (compiled reference for cfg4; the pinned C
+    restatement, cross-checked against the compiled reference on 64 rows, for cfg5).  None when there is no fixture."""
+    z = golden("full_%s.npz" % tag)
+    if z is None:
+        return None
+    ok = bool(np.array_equal(intra, z["intra"]) and np.array_equal(inter, z["inter"]))
+    if overflow is not None:
+        ok = ok and int(overflow) == int(z["edge_overflow"])
+    return ok
+
+
+def counts_to_arrays(counts_host, n_el, hs):
+    cells = n_el * n_el * hs
+    return (counts_host[:cells].reshape(n_el, n_el, hs).astype(np.float32),
+            counts_host[cells:2 * cells].reshape(n_el, n_el, hs).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- BASELINE.json configs 1-3 (shipped inputs)
+EXAMPLES = {   # fixture, label, what moves, sigma of the rigid translation in Angstrom, scale-factor refit as shipped
+    "cfg1_niti": ("constraints_niti.npz", "Examples/atomicNiTi: 6750 atoms, PDF hs 1999 + reduced S(Q) 112 x 417, refit (10, 0.8, 1.2), k = 1", "atoms", 0.1,
+                  (10, 0.8, 1.2)),
+    "cfg2_thf": ("constraints_thf.npz", "Examples/molecularTHF: 9490 atoms, g(r) hs 2000 with data weights, molecule moves k = 13", "molecules", 0.2, None),
+    "cfg3_siox": ("constraints_siox_shape.npz", "Examples/SiOxNanosphere: 3410 atoms, non-periodic PDF hs 1243 + shape function, k = 1", "atoms", 0.2, None),
+}
+
+
+def _fixture_constraints(g):
+    F32 = np.float32
+    elements = [str(e) for e in g["elements"]]
+    counts = np.bincount(g["elementIndex"], minlength=len(elements))
+    n_per = {elements[i]: int(counts[i]) for i in range(len(elements))}
+    descs = []
+    for ci in range(int(g["n_constraints"])):
+        d = {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("c%d/" % ci)}
+        d["kind"] = str(d["kind"])
+        d["weighting"] = {str(p): F32(w) for p, w in zip(d["pairs"], d["pair_w"])}
+        d["dataWeights"] = None if d["dataWeights"].shape[0] == 0 else d["dataWeights"]
+        descs.append(d)
+    return elements, n_per, descs
+
+
+def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
+    """RMC move evaluations/s on the shipped inputs of configs 1-3, as an Engine would drive them:
+    (a) the five-method protocol of the device constraint mirrors (compute_before_move / compute_after_move /
+        accept_move / reject_move per constraint, host Metropolis in the reference's order) -- one launch per move;
+    (b) the same proposal sequence through frmc_run_batch (the engine's rule on the device);
+    (c) the reference sequence (2 x multiple + 2 x full-subset histograms, totals, chi^2 per constraint) on one host
+        core with the reference's compiled kernels (oracle/_ref), beside it."""
+    import fullrmc_b200
+    from fullrmc_b200.constraints import DeviceBackend, make_device_constraint
+    F32 = np.float32
+    fixture, label, what, sigma, adjust = EXAMPLES[key]
+    g = golden(fixture)
+    if g is None:
+        return {"workload": label, "error": "fixture %s missing" % fixture}
+    elements, n_per, descs = _fixture_constraints(g)
+    box0, basis, pbc = g["boxCoords"], g["basis"], bool(g["isPBC"])
+    mol, el = g["moleculeIndex"], g["elementIndex"]
+    n = box0.shape[0]
+    previous = fullrmc_b200.set_edge_spill(True)          # trajectories as the reference's own unchecked write gives them
+    try:
+        def build():
+            backend = DeviceBackend(box0, basis, pbc, mol, el, elements, n_per, g["volume"], g["numberDensity"], device=dev)
+            cons = []
+            for d in descs:
+                kw = dict(dataWeights=d["dataWeights"], scaleFactor=float(d["scaleFactor"]),
+                          qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None)
+                if adjust is not None:
+                    kw["adjustScaleFactor"] = adjust
+                if "shapeFuncParams" in d:
+                    sp = d["shapeFuncParams"]
+                    kw["shapeFuncParams"] = dict(rmin=sp[0], rmax=None if np.isnan(sp[1]) else sp[1], dr=sp[2], qmin=sp[3], qmax=sp[4],
+                                                 dq=sp[5], updateFreq=1000)          # Examples/SiOxNanosphere/run.py:46
+                    kw["shapeWeighting"] = None
+                cons.append(make_device_constraint(backend, d["kind"], d["experimental"], d["minDistance"], d["maxDistance"], d["bin"],
+                                                   int(d["histSize"]), d["shellCenters"], d["shellVolumes"], d["weighting"], **kw))
+            for c in cons:
+                c.compute_data()
+                if c._shapeFuncParams is not None:
+                    c.runtime_initialize()
+            return backend, cons
+        rng = np.random.default_rng(17)
+        if what == "molecules":
+            groups = [np.flatnonzero(mol == m).astype(np.int32) for m in range(int(mol.max()) + 1)]
+        else:
+            groups = None
+        inv = np.linalg.inv(basis.astype(np.float64)) if pbc else np.eye(3)
+        total = n_evals + warm
+        pick = rng.integers(0, len(groups) if groups is not None else n, total)
+        shifts = (rng.normal(0.0, sigma, (total, 3)) @ inv).astype(F32)
+
+        # (a) the five-method protocol, host Metropolis (tolerance 0)
+        backend, cons = build()
+        box = box0.copy()
+        err_old = sum(float(c.standardError) for c in cons)
+        accepted = 0
+        t0 = None
+        for it in range(total):
+            if it == warm:
+                backend.store.get_coords(); t0 = time.perf_counter()
+            idx = groups[pick[it]] if groups is not None else np.array([pick[it]], np.int32)
+            moved = (box[idx] + shifts[it]).astype(F32)
+            for c in cons:
+                if c._shapeFuncParams is not None:
+                    c.runtime_on_step()
+            for c in cons:
+                c.compute_before_move(idx, idx)
+                c.compute_after_move(idx, idx, moved)
+            err_new = sum(float(c.afterMoveStandardError) for c in cons)
+            if err_new <= err_old:
+                for c in cons:
+                    c.accept_move(idx, idx)
+                box[idx] = moved; err_old = err_new
+                accepted += int(it >= warm)
+            else:
+                for c in cons:
+                    c.reject_move(idx, idx)
+        backend.store.get_coords()
+        wall = time.perf_counter() - t0
+        coords_a = backend.store.get_coords()
+        backend.close()
+        out = {"workload": label, "evals": n_evals, "accepted": accepted,
+               "five_method_protocol": {"value": n_evals / wall, "unit": "evals/s", "us_per_eval": 1e6 * wall / n_evals,
+                                        "api": "Device*Constraint.compute_before_move / compute_after_move / accept_move / reject_move, host Metropolis"}}
+        # (b) the same sequence resolved on the device
+        try:
+            backend, cons = build()
+            moved_all, idx_all, sizes = [], [], []
+            boxb = box0.copy()
+            # the run entry point takes proposals relative to the configuration at the time they are tried: drive it
+            # in launches of at most 256 proposals, re-basing on the accepted coordinates in between
+            err0 = np.sum([F32(c.standardError) for c in cons], dtype=F32)
+            rand = np.ones(total, F32)
+            done, acc_b, dev_ms, timed_from = 0, 0, 0.0, 0
+            t0 = None
+            tot = err0
+            while done < total:
+                if done >= warm and t0 is None:
+                    t0 = time.perf_counter(); dev_ms = 0.0; acc_b = 0; timed_from = done
+                m = min(64, total - done)
+                ids = [groups[pick[j]] if groups is not None else np.array([pick[j]], np.int32) for j in range(done, done + m)]
+                # proposals of one launch must not depend on each other's outcome: keep distinct groups only
+                seen, keep = set(), []
+                for j, a in enumerate(ids):
+                    key_ = int(pick[done + j])
+                    if key_ in seen:
+                        break
+                    seen.add(key_); keep.append(j)
+                m = len(keep)
+                ids = ids[:m]
+                mv = np.concatenate([(boxb[a] + shifts[done + j]).astype(F32) for j, a in enumerate(ids)])
+                res = backend.store.run_batch(np.concatenate(ids), mv, tot, rand[done:done + m], tolerance=0.0,
+                                              group_sizes=np.array([a.shape[0] for a in ids], np.int32))
+                tot = res["total"]; dev_ms += res["device_ms"]
+                for j, a in enumerate(ids):
+                    if res["decisions"][j] > 0:
+                        boxb[a] = (boxb[a] + shifts[done + j]).astype(F32); acc_b += 1
+                done += m
+            wall_b = time.perf_counter() - t0
+            nb = total - timed_from
+            out["run_batch"] = {"value": nb / (dev_ms * 1e-3) if dev_ms > 0 else None, "unit": "evals/s (device time)",
+                                "e2e_evals_s": nb / wall_b, "us_per_eval_e2e": 1e6 * wall_b / nb, "evals": nb, "accepted": acc_b,
+                                "batch_launches": backend.store.batch_stats()[0],
+                                "same_final_coordinates_as_protocol": bool(np.array_equal(backend.store.get_coords(), coords_a)),
+                                "api": "DeviceStore.run_batch (frmc_run_batch), launches of <= 64 distinct groups"}
+            backend.close()
+        except Exception as err:
+            out["run_batch"] = {"error": "%s: %s" % (type(err).__name__, err)}
+        # (c) the reference sequence on one host core
+        if not no_cpu:
+            out["cpu_baseline"] = example_cpu_baseline(g, elements, n_per, descs, groups, pick, shifts, ref_evals)
+    finally:
+        fullrmc_b200.set_edge_spill(previous)
+    return out
+
+
+def example_cpu_baseline(g, elements, n_per, descs, groups, pick, shifts, n_evals):
+    """PairDistributionConstraints.py:1044-1129 (and the PCF / S(Q) twins) with the reference's compiled kernels"""
+    from oracle import build_ref, pairhist as orc, epilogue as ep
+    F32 = np.float32
+    mods = build_ref.load()
+    if mods is not None:
+        fns, kind = (mods[1].multiple_pairs_histograms_coords, mods[1].full_pairs_histograms_coords), "reference"
+    else:
+        fns, kind = (orc.multiple_pairs_histograms_coords, orc.full_pairs_histograms_coords), "port"
+    box = g["boxCoords"].copy()
+    basis, pbc, mol, el = g["basis"], bool(g["isPBC"]), g["moleculeIndex"], g["elementIndex"]
+    volume, rho0 = F32(g["volume"]), F32(g["numberDensity"])
+    data = [[d["start_intra"].copy(), d["start_inter"].copy()] for d in descs]
+    mats = [ep.gr2sq_matrix(d["qValues"], d["shellCenters"]) if d["kind"] in ("SQ", "RSQ") else None for d in descs]
+    t0 = time.perf_counter()
+    for it in range(n_evals):
+        idx = groups[pick[it]] if groups is not None else np.array([pick[it]], np.int32)
+        tmp = box.copy(); tmp[idx] = (box[idx] + shifts[it]).astype(F32)
+        for ci, d in enumerate(descs):
+            args = (basis, pbc, mol, el, len(elements), d["minDistance"], d["maxDistance"], d["bin"], int(d["histSize"]))
+            bi, be = ep.move_delta(fns, idx, box, *args)
+            ai, ae = ep.move_delta(fns, idx, tmp, *args)
+            ni, ne = data[ci][0] - bi + ai, data[ci][1] - be + ae
+            common = dict(elements=elements, n_per_element=n_per, weighting=d["weighting"], volume=volume, rho0=rho0,
+                          shell_centers=d["shellCenters"], shell_volumes=d["shellVolumes"])
+            if d["kind"] == "PDF":
+                tot = ep.total_Gr(ni, ne, scale_factor=float(d["scaleFactor"]), **common)
+            elif d["kind"] == "PCF":
+                tot = ep.total_gr(ni, ne, scale_factor=float(d["scaleFactor"]), **common)
+            else:
+                tot = ep.total_Sq(ni, ne, gr2sq=mats[ci], scale_factor=float(d["scaleFactor"]), reduced=(d["kind"] == "RSQ"), **common)
+            ep.standard_error(d["experimental"], tot, d["dataWeights"])
+    wall = time.perf_counter() - t0
+    return {"value": n_evals / wall, "unit": "evals/s", "cores": 1, "kind": kind,
+            "sample": "%d evaluations of the reference sequence per constraint (2 x multiple + 2 x full-subset histograms, total, chi2), ncores=1" % n_evals}
+
+
+# ----------------------------------------------------------------------------- cfg4 full histogram
+def cfg4_full_leg(dev, sm_mhz, n_sm):
+    """the 100 000-atom triclinic box: device time through the store, wall time through the stateless host-buffer call,
+    both checked against tests/golden/full_cfg4.npz (the compiled reference)"""
+    from fullrmc_b200 import _lib, synthetic
+    from fullrmc_b200.Core import pairs_histograms as ph
+    from fullrmc_b200.store import DeviceStore
+    s4 = synthetic.cfg4()
+    grid = synthetic.RGrid(0.0, BIN, HS)
+    kw = dict(s4.hist_kwargs(), **grid.kwargs())
+    n = s4.numberOfAtoms
+    with DeviceStore(s4.boxCoords, s4.basis, True, s4.moleculeIndex, s4.elementIndex, 5, device=dev) as st:
+        gid = st.add_grid(grid.minDistance, grid.maxDistance, grid.bin, grid.hs)
+        for _ in range(3):
+            st.compute_data_shard(0, 1)
+        st.set_timing(True)
+        for _ in range(10):
+            st.compute_data_shard(0, 1)
+        ms, cnt = st.get_timing("full")
+        st.set_timing(False)
+        swept = st.swept_pairs
+        hi, he = st.export_data(gid)
+    ms_kernel = ms / max(cnt, 1)
+    ph.full_pairs_histograms_coords(boxCoords=s4.boxCoords, **kw)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ei, ee = ph.full_pairs_histograms_coords(boxCoords=s4.boxCoords, **kw)
+    e2e = (time.perf_counter() - t0) / 5
+    parity = full_histogram_parity("cfg4", hi, he)
+    parity_e2e = full_histogram_parity("cfg4", ei, ee, ph.LAST_EDGE_OVERFLOW)
+    # general-basis minimum image: 3 sub, 3 x (compare + add + sign select), 9 mul + 6 add, 3 mul + 2 add, 2 compares
+    # = 37 issue slots per evaluation (SURVEY.md section 8d); units the boxes prove wrap-free run at 26
+    peak = n_sm * 128 * sm_mhz * 1e6 / 37.0 / 1e9
+    ach = swept / (ms_kernel * 1e-3) / 1e9
+    return {"workload": "cfg4: synthetic %d-atom 5-element triclinic box, full pair histogram, rmin 0, bin %.2f, hs %d" % (n, BIN, HS),
+            "value": n_pairs(n) / (ms_kernel * 1e-3) / 1e9, "unit": "Gpairs/s", "ms_per_step": ms_kernel,
+            "pairs_per_step": n_pairs(n), "pairs_swept_per_step": swept, "swept_fraction": swept / float(n_pairs(n)),
+            "e2e": {"value": n_pairs(n) / e2e / 1e9, "unit": "Gpairs/s", "ms_per_step": 1e3 * e2e, "h2d_bytes_per_step": 20 * n,
+                    "d2h_bytes_per_step": int(2 * 4 * 25 * HS), "api": "fullrmc_b200.Core.pairs_histograms.full_pairs_histograms_coords"},
+            "parity_checked": bool(parity and parity_e2e), "parity_reference": "tests/golden/full_cfg4.npz (compiled reference)",
+            "roofline": {"bound": "fp32-issue", "achieved": ach, "peak": peak, "unit": "G distance evaluations/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": "%d SMs x 128 lanes x %.0f MHz / 37 fp32 issue slots per general-basis evaluation" % (n_sm, sm_mhz)}}
+
+
+# ----------------------------------------------------------------------------- fixture trajectories inside the bench
+def per_move_fixture_replay(tag, dev):
+    """the 200 recorded moves of the unmodified reference classes (tests/golden/constraints_<tag>.npz) through
+    DeviceStore.step before anything is timed: every chi^2 bit-exact, or the per-move numbers are not reported as checked"""
+    import fullrmc_b200
+    from fullrmc_b200 import synthetic
+    from fullrmc_b200.constraints import DeviceBackend, make_device_constraint
+    z = golden("constraints_%s.npz" % tag)
+    if z is None:
+        return None
+    g = {k: z[k] for k in z.files}
+    system = getattr(synthetic, str(g["recipe_name"]))(int(g["recipe_n"]), int(g["recipe_seed"]))
+    g["boxCoords"], g["moleculeIndex"], g["elementIndex"] = system.boxCoords, system.moleculeIndex, system.elementIndex
+    class G(dict):
+        files = property(lambda self: list(self.keys()))
+    elements, n_per, descs = _fixture_constraints(G(g))
+    previous = fullrmc_b200.set_edge_spill(True)
+    try:
+        backend = DeviceBackend(system.boxCoords, g["basis"], True, system.moleculeIndex, system.elementIndex, elements, n_per,
+                                g["volume"], g["numberDensity"], device=dev)
+        cons = [make_device_constraint(backend, d["kind"], d["experimental"], d["minDistance"], d["maxDistance"], d["bin"], int(d["histSize"]),
+                                       d["shellCenters"], d["shellVolumes"], d["weighting"], dataWeights=d["dataWeights"],
+                                       scaleFactor=float(d["scaleFactor"]), qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None)
+                for d in descs]
+        ok = True
+        for ci, c in enumerate(cons):
+            _, err = c.compute_data()
+            ok = ok and np.float32(err) == np.float32(g["start_stdErr"][ci])
+        prev = None
+        steps = g["steps/idx"].shape[0]
+        for s_ in range(steps):
+            k = int(g["steps/k"][s_])
+            chi = backend.store.step(prev, g["steps/idx"][s_, :k].astype(np.int32), np.ascontiguousarray(g["steps/moved"][s_, :k]))
+            ok = ok and bool(np.array_equal(chi[:len(cons)].astype(np.float32), g["steps/chi2_after"][s_, :len(cons)].astype(np.float32)))
+            prev = bool(g["steps/accepted"][s_])
+        (backend.store.accept if prev else backend.store.reject)()
+        for ci, (d, c) in enumerate(zip(descs, cons)):
+            hi, he = backend.store.export_data(c._grid)
+            ok = ok and bool(np.array_equal(hi, d["final_intra"]) and np.array_equal(he, d["final_inter"]))
+        backend.close()
+        return bool(ok)
+    finally:
+        fullrmc_b200.set_edge_spill(previous)
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -558,8 +888,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gpairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(busy_all)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg5: synthetic %d-atom cubic box, 5 elements, full pair histogram, rmin 0, bin %.2f, hs %d"
-                               % (n, BIN, HS), "sampled": True},
+        "config": {"workload": "cfg5: synthetic %d-atom cubic box, 5 elements, full pair histogram, rmin 0, bin %.2f, hs %d" % (n, BIN, HS)},
         "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -574,6 +903,7 @@ def run_b200(args):
     from fullrmc_b200 import _lib, parallel, synthetic
     from fullrmc_b200.Core import pairs_histograms as ph
     from fullrmc_b200.store import DeviceStore
+    global HBM_GBS
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -582,6 +912,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: fullrmc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     os.environ["FULLRMC_B200_DEVICE"] = str(local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL announces its version on stdout when the communicator comes up; the contract is ONE JSON
@@ -593,12 +924,14 @@ def run_b200(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
             torch.cuda.synchronize()
+            cpu_group = dist.new_group(backend="gloo")      # host-side waits that keep the GPUs free (e2e leg)
         finally:
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     lib = _lib.load_library()
     hbm_gbs, peak_src, sm_max_mhz = measured_peaks()
+    HBM_GBS = hbm_gbs
 
     n = args.natoms
     system = synthetic.cfg5(n, 5)
@@ -616,16 +949,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ar_events = []
+
     def step():
         # this rank's tile shard -> NCCL all-reduce(sum) of the int64 counts over NVLink (issued on the
         # store's stream) -> device epilogue
-        return parallel.compute_data_sharded(store, rank, world, tensors=[counts])
+        return parallel.compute_data_sharded(store, rank, world, tensors=[counts], events=ar_events if world > 1 else None)
 
     sampler = ClockSampler(local)
     with torch.cuda.stream(ext):
         for _ in range(args.warmup):
             chi2 = step()
         barrier()
+        del ar_events[:]
         store.set_timing(True)
         launches0 = int(lib.frmc_launch_count())
         sampler.start()
@@ -640,10 +976,11 @@ def run_b200(args):
         ms = e0.elapsed_time(e1)
         ms_kernel, n_kernel = store.get_timing("full")
         store.set_timing(False)
-    t = torch.tensor([ms, ms_kernel / max(n_kernel, 1)], dtype=torch.float64, device="cuda:%d" % local)
+    ms_allreduce = float(np.mean([a.elapsed_time(b_) for a, b_ in ar_events])) if ar_events else 0.0
+    t = torch.tensor([ms, ms_kernel / max(n_kernel, 1), ms_allreduce], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_kernel_launch = float(t[0]), float(t[1])
+    ms_total, ms_kernel_launch, ms_allreduce = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = ms_total / args.steps
     P = n_pairs(n)
     value = P / (ms_per_step * 1e-3) / 1e9
@@ -654,6 +991,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tsw)
     swept_total = int(tsw[0])
+    # ---- parity of the timed step: the (all-reduced) counts against the committed reference fixture
+    tag = "cfg5" if n == 1000000 else None
+    ti, te = counts_to_arrays(counts_host, 5, HS)
+    parity_step = full_histogram_parity(tag, ti, te, store.edge_overflow if world == 1 else None) if tag else None
 
     # ---- the same histogram with culling switched off: the reference's own O(N^2) sweep, every pair evaluated
     #      (2 steps at N=1; the result must be the identical integer histogram)
@@ -662,7 +1003,7 @@ def run_b200(args):
         _lib.set_block_culling(False)
         try:
             with torch.cuda.stream(ext):
-                step()                                               # rebuilds the row list for the R=4 tiling
+                step()
                 store.set_timing(True)
                 b0 = torch.cuda.Event(enable_timing=True); b1 = torch.cuda.Event(enable_timing=True)
                 b0.record(ext)
@@ -675,30 +1016,54 @@ def run_b200(args):
             same = bool(np.array_equal(counts.cpu().numpy(), counts_host) and np.array_equal(chi2_b, chi2))
             brute = {"ms_per_step": ms_b, "value": P / (ms_b * 1e-3) / 1e9, "unit": "Gpairs/s", "pairs_swept": store.swept_pairs,
                      "identical_histogram_and_chi2": same,
-                     "note": "culling off (frmc_set_block_culling(0)): all N(N-1)/2 pairs evaluated, R=4 register tiling"}
+                     "note": "culling off (frmc_set_block_culling(0)): all N(N-1)/2 pairs evaluated by the same kernel"}
         finally:
             _lib.set_block_culling(True)
 
-    # ---- e2e: the reference-facing stateless call with HOST buffers (host sort + H2D + kernel + D2H)
+    # ---- e2e: ONE call of the reference-facing function with HOST buffers (raw arrays up, ordering on the device,
+    #      sweep, histograms back).  N > 1: rank 0's single process drives all N GPUs through the in-library path
+    #      (frmc_full_pairs_histograms_coords_multi: NVLink copy of the store, shards, ncclAllReduce inside the library),
+    #      the way an unmodified Engine's compute_data would; the other ranks wait on a host-side barrier.
     kw = dict(system.hist_kwargs(), **grid.kwargs())
-    e2e_steps = max(1, min(args.steps, 3))
-    hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _shard=rank, _nshards=world, **kw)   # warm
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _shard=rank, _nshards=world, **kw)
+    e2e_steps = max(1, min(args.steps, 5))
+    in_library = world == 1 or torch.cuda.device_count() >= world
+    e2e_s, e2e_parity, e2e_path = None, None, None
+    if in_library:
+        if rank == 0:
+            devs = list(range(world))
+            saved_fd = None
+            if world > 1:                                   # ncclCommInitAll prints its banner on stdout too
+                sys.stdout.flush(); saved_fd = os.dup(1); os.dup2(2, 1)
+            try:
+                hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _devices=devs, **kw)   # warm (communicator, buffers)
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _devices=devs, **kw)
+                e2e_s = (time.perf_counter() - t0) / e2e_steps
+            finally:
+                if saved_fd is not None:
+                    sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
+            e2e_parity = full_histogram_parity(tag, hi, he, ph.LAST_EDGE_OVERFLOW) if tag else None
+            e2e_path = lib.frmc_multi_reduce_path().decode() if world > 1 else "single device"
+            agree = bool(int(hi.sum(dtype=np.float64) + he.sum(dtype=np.float64)) == in_range_pairs)
         if world > 1:
+            dist.barrier(group=cpu_group)
+    else:                                                   # one GPU visible per rank: sharded calls + all-reduce of the arrays
+        hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _shard=rank, _nshards=world, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hi, he = ph.full_pairs_histograms_coords(boxCoords=system.boxCoords, _shard=rank, _nshards=world, **kw)
             both = torch.from_numpy(np.stack([hi, he])).to("cuda:%d" % local)
             dist.all_reduce(both)
             both = both.cpu().numpy(); hi, he = both[0], both[1]
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda:%d" % local)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0])
-    # the stateless path and the store path agree with each other (cheap self-check, not the parity test)
-    agree = bool(int(hi.sum(dtype=np.float64) + he.sum(dtype=np.float64)) == in_range_pairs)
+        barrier()
+        te_ = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda:%d" % local)
+        dist.all_reduce(te_, op=dist.ReduceOp.MAX)
+        e2e_s = float(te_[0])
+        e2e_parity = full_histogram_parity(tag, hi, he) if tag else None
+        e2e_path = "one stateless call per rank + all-reduce of the float arrays"
+        agree = bool(int(hi.sum(dtype=np.float64) + he.sum(dtype=np.float64)) == in_range_pairs)
     npad = int(((np.bincount(system.elementIndex, minlength=5) + 255) // 256 * 256).sum())
 
     store.close()
@@ -723,22 +1088,30 @@ def run_b200(args):
                 traffic = json.load(fh).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    parity_checked = bool(parity_step) and bool(e2e_parity)
     line = {
         "metric": METRIC, "value": value, "unit": "Gpairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg5: synthetic %d-atom cubic box (L=%.2f A), 5 elements, full pair histogram, rmin 0, "
-                               "bin %.2f, hs %d, + G(r), S(Q) (nQ=%d), chi2 epilogue" % (n, float(system.basis[0, 0]), BIN, HS, NQ),
+        "config": {"workload": "cfg5: synthetic %d-atom cubic box, 5 elements, full pair histogram, rmin 0, bin %.2f, hs %d" % (n, BIN, HS),
+                   "box_edge_A": float(system.basis[0, 0]), "epilogue": "G(r), S(Q) (nQ=%d), chi2 on the device after the all-reduce" % NQ,
                    "pairs_per_step": P, "pairs_swept_per_step": swept_total, "swept_fraction": swept_total / float(P),
-                   "in_range_pairs": in_range_pairs, "brute_force_sweep": brute, "parallelism": "tile-list shards x%d + NCCL allreduce(int64)" % world,
-                   "value_counts": "all N(N-1)/2 pairs the reference evaluates; pairs in blocks whose bounding boxes are "
+                   "in_range_pairs": in_range_pairs, "brute_force_sweep": brute,
+                   "parallelism": "row-list shards x%d + NCCL allreduce(int64)" % world,
+                   "allreduce_ms_per_step": ms_allreduce,
+                   "value_counts": "all N(N-1)/2 pairs the reference evaluates; pairs in (32 x 32)-atom units whose bounding boxes are "
                                    "farther apart than maxDistance are skipped, the histogram is bit-identical",
                    "l2_policy": "inputs (16 B/atom = %.1f MB) are L2-resident by design; the kernel is issue-bound, not HBM-bound" % (16e-6 * npad),
                    "chi2": [float(c) for c in chi2]},
+        "parity_checked": parity_checked,
+        "parity": {"timed_step_equals_fixture": parity_step, "e2e_call_equals_fixture": e2e_parity,
+                   "fixture": "tests/golden/full_cfg5.npz: oracle/pairhist_oracle.c (pinned bit-for-bit to the compiled reference) over all "
+                              "5e11 pairs, 64 rows cross-checked against the compiled reference (tests/gen_golden_large.py)" if tag else None},
         "clocks": clocks,
-        "e2e": {"value": P / e2e_s / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": 20 * npad,
-                "d2h_bytes_per_step": int(2 * 4 * 25 * HS), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
-                "api": "fullrmc_b200.Core.pairs_histograms.full_pairs_histograms_coords (host numpy in/out)",
+        "e2e": {"value": (P / e2e_s / 1e9) if e2e_s else None, "unit": "Gpairs/s", "h2d_bytes_per_step": 20 * n,
+                "d2h_bytes_per_step": int(2 * 4 * 25 * HS), "ms_per_step": 1e3 * e2e_s if e2e_s else None, "steps": e2e_steps,
+                "api": "fullrmc_b200.Core.pairs_histograms.full_pairs_histograms_coords (host numpy in/out; raw arrays up, atoms ordered on "
+                       "the device)", "devices_in_one_call": world, "reduce": e2e_path,
                 "consistent_with_store_path": agree},
         "gpu_launches": launches,
         "roofline": {"bound": "fp32-issue (neither hbm nor tensor: exact fp32 minimum-image arithmetic on shared-memory/"
@@ -750,6 +1123,8 @@ def run_b200(args):
                                     % (n_sm, sm_mhz)},
     }
     if world == 1 and not args.no_permove:
+        replay5 = per_move_fixture_replay("cfg5", local) if n == 1000000 else None
+        replay4 = per_move_fixture_replay("cfg4", local)
         pm = per_move_leg(system, grid, q, args.permove_evals, args.permove_warm, "cfg5: %d-atom cubic box, k=1 translations, hs %d, nQ %d"
                           % (n, HS, NQ), hbm_gbs, peak_src, local)
         s4 = synthetic.cfg4()
@@ -758,10 +1133,44 @@ def run_b200(args):
         if not args.no_cpu:
             pm["cpu_baseline"] = per_move_cpu_baseline(system, grid, q, 300)      # ~10 s of CPU work
             pm4["cpu_baseline"] = per_move_cpu_baseline(s4, grid, q, 2500)        # ~10 s
+        pm["reference_trajectory_replayed"] = replay5
+        pm4["reference_trajectory_replayed"] = replay4
         line["per_move"] = pm
         line["per_move_cfg4"] = pm4
-        line["distance_constraint_cfg4"] = distance_leg(s4, args.no_cpu)
-        line["coordination_cfg4"] = coordination_leg(s4, args.no_cpu)
+        # the driver keeps top-level scalars: the per-move half of the metric, both ways of driving it
+        for suffix, leg in (("", pm), ("_cfg4", pm4)):
+            single = leg.get("single_proposal", leg)
+            line["per_move%s_evals_s" % suffix] = leg.get("value")
+            line["per_move%s_e2e_evals_s" % suffix] = (leg.get("e2e") or {}).get("value")
+            line["per_move%s_roofline_frac" % suffix] = (leg.get("roofline") or {}).get("frac")
+            line["per_move%s_host_accept_evals_s" % suffix] = (single.get("e2e") or {}).get("value")
+            line["per_move%s_host_accept_device_evals_s" % suffix] = single.get("value")
+            line["per_move%s_host_accept_frac" % suffix] = (single.get("roofline") or {}).get("e2e_frac")
+            line["per_move%s_parity_checked" % suffix] = bool(leg.get("reference_trajectory_replayed")) and \
+                bool(leg.get("identical_to_sequential_path", True))
+            cb = leg.get("cpu_baseline") or {}
+            line["per_move%s_reference_evals_s" % suffix] = cb.get("value")
+        full4 = cfg4_full_leg(local, sm_mhz, n_sm)
+        line["full_histogram_cfg4"] = full4
+        line["full_histogram_cfg4_gpairs_s"] = full4["value"]
+        line["full_histogram_cfg4_e2e_gpairs_s"] = full4["e2e"]["value"]
+        line["full_histogram_cfg4_roofline_frac"] = full4["roofline"]["frac"]
+        line["full_histogram_cfg4_parity_checked"] = full4["parity_checked"]
+        for key in ("cfg1_niti", "cfg2_thf", "cfg3_siox"):
+            try:
+                leg = example_leg(key, args.example_evals, 50, local, args.no_cpu, {"cfg1_niti": 2000, "cfg2_thf": 300, "cfg3_siox": 3000}[key])
+            except Exception as err:
+                leg = {"error": "%s: %s" % (type(err).__name__, err)}
+            line[key] = leg
+            line[key + "_evals_s"] = (leg.get("five_method_protocol") or {}).get("value")
+            line[key + "_batch_evals_s"] = (leg.get("run_batch") or {}).get("e2e_evals_s")
+            line[key + "_reference_evals_s"] = (leg.get("cpu_baseline") or {}).get("value")
+        dleg = distance_leg(s4, args.no_cpu)
+        cleg = coordination_leg(s4, args.no_cpu)
+        line["distance_constraint_cfg4"] = dleg
+        line["coordination_cfg4"] = cleg
+        line["distance_constraint_cfg4_roofline_frac"] = (dleg.get("roofline") or {}).get("frac")
+        line["coordination_cfg4_roofline_frac"] = (cleg.get("roofline") or {}).get("frac")
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         scale = max(1, n // 1000000)                                           # ~10 s of CPU work per leg at 1 M atoms
@@ -784,6 +1193,7 @@ def main():
     ap.add_argument("--natoms", type=int, default=1000000)
     ap.add_argument("--permove-evals", type=int, default=3000)
     ap.add_argument("--permove-warm", type=int, default=200)
+    ap.add_argument("--example-evals", type=int, default=1500, help="move evaluations per shipped-example leg (configs 1-3)")
     ap.add_argument("--ref-rows", type=int, default=1600, help="sampled rows per reference step")
     ap.add_argument("--no-permove", action="store_true")
     ap.add_argument("--no-brute", action="store_true", help="skip the culling-off leg of the full histogram")

@@ -51,6 +51,8 @@ SIGNATURES = {
     "frmc_device_count": (_I, []),
     "frmc_set_edge_spill": (_I, [_I]),
     "frmc_set_block_culling": (_I, [_I]),
+    "frmc_ctx_set_timing": (_I, [_I, _I]),
+    "frmc_ctx_kernel_ms": (_I, [_I, ctypes.POINTER(ctypes.c_double)]),
     "frmc_set_device_layout": (_I, [_I]),
     "frmc_launch_count": (ctypes.c_uint64, []),
     "frmc_points_to_coords": (_I, [_I, c_f32p, c_i32p, c_i64p, _I64, c_f32p, _I64, c_f32p, _I, _I, _I, c_f32p]),
@@ -173,6 +175,21 @@ def set_edge_spill(on):
 def set_block_culling(on):
     """Full-histogram block culling (default on; results are identical either way).  Returns the previous setting."""
     return bool(load_library().frmc_set_block_culling(int(bool(on))))
+
+
+def kernel_ms_of(call, device=None):
+    """Run ``call()`` (a stateless drop-in function) with the library's kernel timer on; returns (result, device ms of
+    the call's dominant kernel)."""
+    lib = load_library()
+    dev = device_index() if device is None else int(device)
+    check(lib.frmc_ctx_set_timing(dev, 1), "ctx_set_timing")
+    try:
+        out = call()
+        ms = ctypes.c_double(0.0)
+        check(lib.frmc_ctx_kernel_ms(dev, ctypes.byref(ms)), "ctx_kernel_ms")
+    finally:
+        lib.frmc_ctx_set_timing(dev, 0)
+    return out, float(ms.value)
 
 
 def set_device_layout(on):

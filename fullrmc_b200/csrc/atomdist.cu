@@ -362,6 +362,7 @@ static int full_culled(int dev, const float *coords, int64_t n, const float *bas
     for (int attempt = 0; attempt < 2; ++attempt) {
         FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * 2 * cells + 16, c->stream));
         if (pl.n_items > 0) {
+            CtxTimer timer(c);                       // frmc_ctx_kernel_ms: the block sweep
             const int grid = std::min(pl.n_items, c->sm_count * 8);
 #define LAUNCH_ADB(M) atomdist_block_kernel<M><<<grid, 256, 0, c->stream>>>(d_atoms, d_orig, d_rows, pl.entries, pl.items, pl.n_items, L, d_lim, \
                                                                             nT, flags, d_counts, d_nhits, (unsigned long long)sc.cap, sc.keys, sc.vals)

@@ -165,6 +165,35 @@ int frmc_device_count(void)
 
 uint64_t frmc_launch_count(void) { return frmc::g_launch_count; }
 
+int frmc_ctx_set_timing(int dev, int on)
+{
+    frmc::DeviceCtx *c = frmc::get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    if (on && !c->t0) {
+        if (cudaEventCreate(&c->t0) != cudaSuccess || cudaEventCreate(&c->t1) != cudaSuccess) {
+            frmc::set_error("cudaEventCreate failed");
+            return FRMC_ECUDA;
+        }
+    }
+    c->timing = on ? 1 : 0;
+    c->timed = 0;
+    return FRMC_OK;
+}
+
+int frmc_ctx_kernel_ms(int dev, double *ms)
+{
+    frmc::DeviceCtx *c = frmc::get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    if (!ms || !c->timed) { frmc::set_error("no timed kernel on device %d (frmc_ctx_set_timing first)", dev); return FRMC_ESTATE; }
+    float f = 0.f;
+    if (cudaEventSynchronize(c->t1) != cudaSuccess || cudaEventElapsedTime(&f, c->t0, c->t1) != cudaSuccess) {
+        frmc::set_error("cudaEventElapsedTime failed");
+        return FRMC_ECUDA;
+    }
+    *ms = (double)f;
+    return FRMC_OK;
+}
+
 int frmc_set_edge_spill(int on)
 {
     int old = frmc::g_edge_spill;

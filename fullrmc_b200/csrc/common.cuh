@@ -242,6 +242,17 @@ struct DeviceCtx {
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     int sm_count = 0;
+    // optional device timing of the stateless entry points' dominant kernel (frmc_ctx_set_timing): events around the
+    // launch, on the context's stream; read back with frmc_ctx_kernel_ms after the call
+    int timing = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int timed = 0;
+};
+
+struct CtxTimer {                 // RAII bracket: records t0 now and t1 when it goes out of scope
+    DeviceCtx *c;
+    explicit CtxTimer(DeviceCtx *ctx) : c(ctx) { if (c->timing && c->t0) { cudaEventRecord(c->t0, c->stream); } }
+    ~CtxTimer() { if (c->timing && c->t1) { cudaEventRecord(c->t1, c->stream); c->timed = 1; } }
 };
 
 // returns nullptr (and sets the error string) on failure

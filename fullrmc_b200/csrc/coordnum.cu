@@ -226,6 +226,8 @@ extern "C" int frmc_coordination_counts(int dev, const float *coords, int64_t n,
     FRMC_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, c->stream));
     FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)nout, c->stream));
     const int grid = (int)std::min<long long>(n_items, (long long)c->sm_count * 8);
+    {
+    CtxTimer timer(c);                               // frmc_ctx_kernel_ms: the counting kernel
 #define LAUNCH_CN(M, D) coordnum_kernel<M, D><<<grid, CN_THREADS, 0, c->stream>>>(use_d ? nullptr : (const float4 *)d_in, use_d ? d_in : nullptr, (long long)n, chunk_len, \
                                   d_tasks, (int)ntasks, d_item_off, n_items, d_list_off, d_idx, L, d_counts)
     if (use_d) {
@@ -241,6 +243,7 @@ extern "C" int frmc_coordination_counts(int dev, const float *coords, int64_t n,
         }
     }
 #undef LAUNCH_CN
+    }
     FRMC_LAUNCH_CHECK();
     FRMC_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(int) * (size_t)nout, cudaMemcpyDeviceToHost, c->stream));
     FRMC_CUDA(cudaStreamSynchronize(c->stream));

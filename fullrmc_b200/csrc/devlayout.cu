@@ -28,6 +28,9 @@
 #include "layout.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -39,6 +42,9 @@ struct DlStats {                 // device -> host after the counting pass
     int count[FRMC_MAX_ELEMENTS];
     int lo[3], hi[3];            // order-preserving integer images of the coordinate bounds
     int not_finite, bad_element;
+    int mol_not_direct;          // a molecule index outside [0, 2^24 - 1): the host ranks them
+    int mol_decreasing;          // moleculeIndex is not non-decreasing: molecules may be scattered over the index range
+    int mol_repeats;             // two consecutive atoms share a molecule: molecules of more than one atom exist
 };
 
 struct DlTask {                  // one tree node (host-built: the shape depends only on the element counts)
@@ -66,7 +72,8 @@ static float dl_ordered_to_float(int i)
     return f;
 }
 
-__global__ void __launch_bounds__(256) dl_count_kernel(const float *__restrict__ coords, const int32_t *__restrict__ el, long long n, int nEl,
+__global__ void __launch_bounds__(256) dl_count_kernel(const float *__restrict__ coords, const int32_t *__restrict__ el,
+                                                       const int32_t *__restrict__ mol, long long n, int nEl,
                                                        int *__restrict__ chunk_cnt, DlStats *__restrict__ stats)
 {
     __shared__ int s_cnt[FRMC_MAX_ELEMENTS];
@@ -78,12 +85,19 @@ __global__ void __launch_bounds__(256) dl_count_kernel(const float *__restrict__
     __syncthreads();
     const long long base = (long long)blockIdx.x * DL_CHUNK;
     int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
-    int nf = 0, bad = 0;
+    int nf = 0, bad = 0, mflags = 0;
     for (int r = 0; r < DL_CHUNK / 256; ++r) {
         const long long i = base + r * 256 + tid;
         if (i < n) {
             const int e = el[i];
             if (e < 0 || e >= nEl) bad = 1; else atomicAdd(&s_cnt[e], 1);
+            const int m = mol[i];
+            if (m < 0 || m >= 0x00FFFFFF) mflags |= 1;
+            if (i > 0) {
+                const int mp = mol[i - 1];
+                if (m < mp) mflags |= 2;
+                if (m == mp) mflags |= 4;
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float v = coords[3 * i + c];
@@ -99,6 +113,12 @@ __global__ void __launch_bounds__(256) dl_count_kernel(const float *__restrict__
         hi[c] = __reduce_max_sync(0xffffffffu, hi[c]);
     }
     nf = __any_sync(0xffffffffu, nf); bad = __any_sync(0xffffffffu, bad);
+    mflags = __reduce_or_sync(0xffffffffu, mflags);
+    if ((tid & 31) == 0 && mflags) {
+        if (mflags & 1) stats->mol_not_direct = 1;
+        if (mflags & 2) stats->mol_decreasing = 1;
+        if (mflags & 4) stats->mol_repeats = 1;
+    }
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { atomicMin(&s_lo[c], lo[c]); atomicMax(&s_hi[c], hi[c]); }
@@ -438,13 +458,23 @@ static void dl_walk(DlTree &tree, std::vector<std::vector<DlTask>> &levels, int 
 
 // Builds the store records of `coords` on device `c` into the context's scratch slots 0 (records) and 1 (original
 // indexes), returned through d_atoms_out / d_orig_out.  lay receives what the host keeps: n, npad, nEl, seg_start,
-// seg_count, bounds, finiteness, mol_span (rec / orig / inv stay empty).  One stream synchronisation (element counts).
+// seg_count, bounds, finiteness, mol_span (rec / orig / inv stay empty); *d_mol_out = the device copy of the molecule
+// keys by original index (what the sweep's exact intra/inter test reads).  One stream synchronisation (element counts).
 int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
-                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out)
+                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out, int32_t **d_mol_out)
 {
     FRMC_REQUIRE(n >= 0 && n < (1ll << 31) - 4096, FRMC_ELIMIT, "atom count %lld outside 0..2^31", (long long)n);
     FRMC_REQUIRE(nEl >= 1 && nEl <= FRMC_MAX_ELEMENTS, FRMC_ELIMIT, "numberOfElements %d outside 1..%d", nEl, FRMC_MAX_ELEMENTS);
     cudaStream_t st = c->stream;
+    const bool timing = getenv("FRMC_LAYOUT_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what, bool sync) {
+        if (!timing) return;
+        if (sync) cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[device layout] %-14s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     lay.n = n; lay.nEl = nEl;
     lay.seg_count.assign((size_t)nEl, 0);
     lay.seg_start.assign((size_t)nEl + 1, 0);
@@ -452,10 +482,6 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
     std::vector<int32_t> rank;
     const int32_t *keys = mol;
     lay.mol_span = 0;
-    if (n > 0) {
-        int rc = molecule_keys(mol, n, rank, &keys, &lay.mol_span);
-        if (rc) return rc;
-    }
     const int n_chunks = (int)((n + DL_CHUNK - 1) / DL_CHUNK);
     // device scratch (slots 7..12 of the context): raw arrays, chunk counts + stats, two point buffers, tasks + boxes
     float *d_coords = (float *)ctx_buffer(c, 7, sizeof(float) * 3 * (size_t)std::max<int64_t>(n, 1));
@@ -471,15 +497,27 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
     if (n > 0) {
         FRMC_CUDA(cudaMemcpyAsync(d_coords, coords, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
         FRMC_CUDA(cudaMemcpyAsync(d_el, el, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        FRMC_CUDA(cudaMemcpyAsync(d_key, keys, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        dl_count_kernel<<<n_chunks, 256, 0, st>>>(d_coords, d_el, (long long)n, nEl, d_cnt, d_stats);
+        FRMC_CUDA(cudaMemcpyAsync(d_key, mol, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        dl_count_kernel<<<n_chunks, 256, 0, st>>>(d_coords, d_el, d_key, (long long)n, nEl, d_cnt, d_stats);
         FRMC_LAUNCH_CHECK();
         dl_scan_kernel<<<1, 1024, 0, st>>>(d_cnt, n_chunks, nEl, d_stats);
         FRMC_LAUNCH_CHECK();
     }
     FRMC_CUDA(cudaMemcpyAsync(&h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     FRMC_CUDA(cudaStreamSynchronize(st));
+    lap("upload+count", false);
     FRMC_REQUIRE(!h_stats.bad_element, FRMC_EINVAL, "an elementIndex entry lies outside 0..%d", nEl - 1);
+    // molecule keys of the meta word and the spread of a molecule: nothing to do on the host for the usual atomic
+    // system (every atom its own molecule, ids in range: the device saw no two neighbours sharing one and the ids
+    // never decreasing, so no molecule has two atoms); otherwise one pass over the ids (and a ranking when they do
+    // not fit 24 bits), with the ranked keys replacing the raw ids on the device
+    if (n > 0 && (h_stats.mol_not_direct || h_stats.mol_decreasing || h_stats.mol_repeats)) {
+        int rc = molecule_keys(mol, n, rank, &keys, &lay.mol_span);
+        if (rc) return rc;
+        if (keys != mol) FRMC_CUDA(cudaMemcpyAsync(d_key, keys, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    *d_mol_out = d_key;
+    lap("molecule keys", false);
     DlElemBase eb;
     DlShift sh;
     DlPad pad;
@@ -542,6 +580,7 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
     all.insert(all.end(), tree.leaf.begin(), tree.leaf.end());
     FRMC_CUDA(cudaMemcpyAsync(d_tasks, all.data(), sizeof(DlTask) * n_tasks, cudaMemcpyHostToDevice, st));
     FRMC_CUDA(cudaMemcpyAsync(d_boxes, h_boxes.data(), sizeof(DlBox) * h_boxes.size(), cudaMemcpyHostToDevice, st));
+    lap("tree+tasks", false);
     dl_gather_kernel<<<n_chunks, 256, 0, st>>>(d_coords, d_el, (long long)n, nEl, isPBC ? 1 : 0, d_cnt, eb, buf0);
     FRMC_LAUNCH_CHECK();
     for (size_t d = 0; d + 1 < tree.level_start.size(); ++d) {
@@ -551,10 +590,12 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
             FRMC_LAUNCH_CHECK();
         }
     }
+    lap("gather+splits", true);
     dl_leaf_kernel<<<(unsigned)tree.leaf.size(), DL_LEAF, 0, st>>>(d_tasks + tree.split.size(), buf0, buf1, d_boxes, d_coords, d_key, sh, d_atoms, d_orig);
     FRMC_LAUNCH_CHECK();
     dl_pad_kernel<<<nEl, 256, 0, st>>>(pad, d_atoms, d_orig);
     FRMC_LAUNCH_CHECK();
+    lap("leaves+pad", true);
     return FRMC_OK;
 }
 

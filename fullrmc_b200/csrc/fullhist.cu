@@ -1167,7 +1167,8 @@ extern "C" int frmc_debug_device_layout(int dev, int64_t n, const float *coords,
     HostLayout lay;
     float4 *d_atoms = nullptr;
     uint32_t *d_orig = nullptr;
-    int rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig);
+    int32_t *d_keys = nullptr;
+    int rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig, &d_keys);
     if (rc) return rc;
     FRMC_REQUIRE(capacity >= lay.npad, FRMC_EINVAL, "orig_out holds %lld records, the layout has %lld", (long long)capacity, (long long)lay.npad);
     if (lay.npad > 0) FRMC_CUDA(cudaMemcpyAsync(orig_out, d_orig, sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyDeviceToHost, c->stream));
@@ -1228,9 +1229,10 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     static thread_local HostLayout lay;
     float4 *d_atoms = nullptr;
     uint32_t *d_orig = nullptr;
+    int32_t *d_mol_dev = nullptr;
     int rc;
     if (g_device_layout) {
-        rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig);
+        rc = device_layout(c, coords, n, mol, el, nEl, isPBC, lay, &d_atoms, &d_orig, &d_mol_dev);
         if (rc) return rc;
     } else {
         rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
@@ -1262,15 +1264,23 @@ extern "C" int frmc_full_pairs_histograms_coords(int dev, const float *coords, i
     FRMC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (2 * cells + 3), c->stream));
     if (!items.empty()) {
         FRMC_CUDA(cudaMemcpyAsync(d_items, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
-        int32_t *d_mol = nullptr;                      // only molecular systems ever read it
-        if (lay.mol_span > 0) {
+        int32_t *d_mol = d_mol_dev;                    // only molecular systems ever read it
+        if (lay.mol_span > 0 && !d_mol) {
             d_mol = (int32_t *)ctx_buffer(c, 6, sizeof(int32_t) * (size_t)n);
             if (!d_mol) return FRMC_ENOMEM;
             FRMC_CUDA(cudaMemcpyAsync(d_mol, mol, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
         }
+        CtxTimer timer(c);                             // frmc_ctx_kernel_ms: box pass + lists + sweep
         rc = full_hist_launch(c->stream, c->sm_count, mode, d_atoms, d_orig, lay.npad, d_bbox, d_items, (int)items.size(), n_pairs,
                               stateless_lists_for(c->dev), d_mol, lay.mol_span, L, g, nEl, d_counts, d_ov);
         if (rc) return rc;
+    }
+    if (getenv("FRMC_LAYOUT_TIMING")) {
+        static thread_local auto t_prev = std::chrono::steady_clock::now();
+        cudaStreamSynchronize(c->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[full histogram] lists+sweep done %.3f ms after the previous mark\n", std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
     }
     rc = launch_counts64_to_float(c->stream, d_counts, d_out, 2 * cells);
     if (rc) return rc;

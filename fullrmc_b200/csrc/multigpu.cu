@@ -139,9 +139,10 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
     HostLayout &lay = lay_tls;
     float4 *d_atoms0 = nullptr;
     uint32_t *d_orig0 = nullptr;
+    int32_t *d_keys0 = nullptr;
     int rc;
     if (g_device_layout) {
-        rc = device_layout(c0, coords, n, mol, el, nEl, isPBC, lay, &d_atoms0, &d_orig0);
+        rc = device_layout(c0, coords, n, mol, el, nEl, isPBC, lay, &d_atoms0, &d_orig0, &d_keys0);
         if (rc) return rc;
     } else {
         rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);

@@ -40,19 +40,32 @@ def counts_tensor(store, grid):
     return torch.as_tensor(_DevArray(ptr, n), device="cuda:%d" % store.device)
 
 
-def compute_data_sharded(store, rank=None, world=None, tensors=None):
+def compute_data_sharded(store, rank=None, world=None, tensors=None, events=None):
     """compute_data over all ranks: this rank's tile shard, all-reduce of every grid's counts on the
-    store's stream, then the epilogue.  Returns chi^2 per model (identical on every rank)."""
+    store's stream, then the epilogue.  Returns chi^2 per model (identical on every rank).
+    events: optional list that receives one (start, end) pair of CUDA events around the all-reduce
+    (recorded on the store's stream; the caller reads them after a synchronisation)."""
     import torch
+    import torch.distributed as dist
     r, w, _ = rank_world()
     rank = r if rank is None else rank
     world = w if world is None else world
+    if world > 1 and not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == world):
+        # a partial histogram must never reach the epilogue: chi^2 would be plausible and wrong
+        raise RuntimeError("compute_data_sharded(world=%d) needs an initialised process group of that size "
+                           "(torch.distributed.init_process_group)" % world)
     store.compute_data_shard(rank, world)
     if world > 1:
         ext = torch.cuda.ExternalStream(store.stream, device=store.device)
         with torch.cuda.stream(ext):
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
             for g in range(len(store._grids)):
                 allreduce_sum_(tensors[g] if tensors is not None else counts_tensor(store, g))
+            if events is not None:
+                e1.record(ext)
+                events.append((e0, e1))
     return store.finalize_data()
 
 

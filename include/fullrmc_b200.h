@@ -64,6 +64,11 @@ int frmc_set_block_culling(int on);
  * raw arrays are uploaded as they are; off = k-d ordering on the host cores before the upload).  The histogram is
  * identical either way.  Returns the previous setting. */
 int frmc_set_device_layout(int on);
+/* Device time of the dominant kernel of the stateless entry points (full histogram: box pass + lists + sweep; distance
+ * windows: the block sweep; coordination numbers: the counting kernel): CUDA events around it on the library's stream
+ * when switched on; frmc_ctx_kernel_ms returns the last call's figure (for bench.py's rooflines). */
+int frmc_ctx_set_timing(int dev, int on);
+int frmc_ctx_kernel_ms(int dev, double *ms);
 /* number of visible CUDA devices, or a negative error code (no CPU fallback exists) */
 int frmc_device_count(void);
 
