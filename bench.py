@@ -737,7 +737,7 @@ def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
             out["run_batch"] = {"error": "%s: %s" % (type(err).__name__, err)}
         # (c) the reference sequence on one host core
         if not no_cpu:
-            out["cpu_baseline"] = example_cpu_baseline(g, elements, n_per, descs, groups, pick, shifts, ref_evals)
+            out["cpu_baseline"] = example_cpu_baseline(g, elements, n_per, descs, groups, pick, shifts, min(ref_evals, total))
     finally:
         fullrmc_b200.set_edge_spill(previous)
     return out
