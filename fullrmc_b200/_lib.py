@@ -71,6 +71,8 @@ SIGNATURES = {
     "frmc_full_pairs_histograms_coords_multi": (_I, [_I, ctypes.POINTER(ctypes.c_int), c_f32p, _I64, c_f32p, _I, c_i32p, c_i32p, _I, _F, _F, _F, _I,
                                                      c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64)]),
     "frmc_multi_reduce_path": (ctypes.c_char_p, []),
+    "frmc_shape_function": (_I, [_I, c_f32p, c_f32p, _I, _I, _I, c_i32p, c_i32p, ctypes.POINTER(ctypes.c_double), c_f32p, c_f32p,
+                                 ctypes.c_double, c_f32p, _I, c_f32p, _I, c_f32p]),
     "frmc_debug_layout": (_I, [_I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_debug_device_layout": (_I, [_I, _I64, c_f32p, c_i32p, c_i32p, _I, _I, _I64, ctypes.POINTER(ctypes.c_uint32), c_i64p, c_i64p]),
     "frmc_multiple_pairs_histograms_dists": (_I, [_I, c_i32p, _I64, c_f32p, _I64, c_i32p, c_i32p, _I, _F, _F, _F, _I,

@@ -200,7 +200,7 @@ class _DeviceExperimentalConstraint(object):
         coords = b.store.get_coords()
         rmax = p["rmax"]
         if rmax is None:
-            rmax = shape.auto_rmax(b.isPBC, b.basisVectors, coords)        # IBC: box coordinates are the real ones
+            rmax = shape.default_rmax(b.isPBC, b.basisVectors, coords)     # IBC: box coordinates are the real ones
         arr = shape.get_Gr_shape_function(self.shellCenters, coords, b.basisVectors, b.isPBC, b.moleculesIndex, b.elementsIndex,
                                           b.elements, b.numberOfAtomsPerElement, b.volume, self._shapeWeighting,
                                           qmin=p["qmin"], qmax=p["qmax"], dq=p["dq"], rmin=p["rmin"], rmax=rmax, dr=p["dr"])
@@ -297,18 +297,34 @@ class DevicePairCorrelationConstraint(DevicePairDistributionConstraint):
 
 
 class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
-    """S(Q) constraint: experimentalData is (m,2) [Q, S(Q)]; the r-grid is the reference's
-    (StructureFactorConstraints.py:330-350: edges = arange(rmin, rmax, dr))."""
+    """S(Q) constraint: experimentalData is (m,2) [Q, S(Q)].  The r-grid follows the reference's defaults
+    (StructureFactorConstraints.py): rmin=None -> 2 pi / Qmax (:511-512); dr=None -> 2 pi / Qmax rounded DOWN to one
+    decimal (:560-565); rmax given -> edges = arange(rmin, rmax + dr, dr) (:341), rmax=None -> edges = arange(rmin,
+    half the shortest basis vector, dr) (:337-339; the reference uses 2 pi / dQ only while no engine is attached)."""
     KIND = "SQ"
 
-    def __init__(self, backend, experimentalData, weighting, rmin, rmax, dr, dataWeights=None, scaleFactor=1.0,
+    def __init__(self, backend, experimentalData, weighting, rmin=None, rmax=None, dr=None, dataWeights=None, scaleFactor=1.0,
                  adjustScaleFactor=(0, 0.8, 1.2)):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
-        edges = np.arange(rmin, rmax, dr).astype(FLOAT_TYPE)                   # :337-341
+        qmax = exp[-1, 0]
+        minimumDistance = FLOAT_TYPE(2. * PI / qmax) if rmin is None else FLOAT_TYPE(rmin)
+        if dr is None:
+            b = 2. * PI / qmax
+            rb = round(b, 1)
+            if rb > b:
+                rb -= 0.1
+            b = FLOAT_TYPE(rb)
+        else:
+            b = FLOAT_TYPE(dr)
+        if rmax is None:
+            half = np.min([np.linalg.norm(v) / 2. for v in backend.basisVectors])
+            edges = np.arange(minimumDistance, half, b).astype(FLOAT_TYPE)
+        else:
+            edges = np.arange(minimumDistance, FLOAT_TYPE(rmax) + b, b).astype(FLOAT_TYPE)
         centers = (edges[0:-1] + edges[1:]) / FLOAT_TYPE(2.)                   # :346
         hs = len(edges) - 1
         super(DeviceStructureFactorConstraint, self).__init__(
-            backend, exp[:, 1], edges[0], edges[-1], FLOAT_TYPE(dr), hs, centers, shell_volumes_from_edges(edges),
+            backend, exp[:, 1], edges[0], edges[-1], b, hs, centers, shell_volumes_from_edges(edges),
             weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0], adjustScaleFactor=adjustScaleFactor)
 
 

@@ -181,6 +181,55 @@ __global__ void q_to_r_kernel(const float *__restrict__ q, const float *__restri
     Gr[ri] = (float)((2.0 / 3.14159265358979323846) * (double)acc);
 }
 
+// Shape function of a finite system (ShapeFunction, Constraints/Collection.py:20-125; refreshed by
+// PairDistributionConstraint._update_shape_array, PairDistributionConstraints.py:316-343): from the ordered pair
+// histograms of the whole system on the shape function's own coarse r-grid to G_shape(r) on the constraint's r values,
+//     g(b)   = sum_pairs w_ij * (n_ij(b) / V_shell(b)) / D_ij          D_ij = N_ij / volume
+//     G(b)   = 4 pi r_b rho0 (g(b) - 1)
+//     S(q)-1 = sum_b G(b) * dr * sin(q r_b) / q                        (StructureFactorConstraints.py:302-312, 772-773)
+//     G_s(r) = (2/pi) * dq * sum_q q (S(q)-1) sin(q r)                 (Collection.py:83-91)
+// three small kernels, every sum in double (the reference's numpy float32 sums are within 1e-6 of it norm-wise;
+// tests/test_golden_constraints.py holds the SiOx refreshes to that bar).
+__global__ void shape_gr_kernel(const float *__restrict__ hintra, const float *__restrict__ hinter, int nEl, int hs, int n_pairs,
+                                const int *__restrict__ pair_a, const int *__restrict__ pair_b, const double *__restrict__ pair_coef,
+                                const float *__restrict__ shell_volumes, const float *__restrict__ shell_centers, double rho0,
+                                double *__restrict__ G)
+{
+    const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= hs) return;
+    double g = 0.0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int ea = pair_a[p], eb = pair_b[p];
+        const size_t ab = ((size_t)ea * nEl + eb) * hs + b, ba = ((size_t)eb * nEl + ea) * hs + b;
+        double nij = (double)hintra[ab] + (double)hinter[ab];
+        if (ea != eb) nij += (double)hintra[ba] + (double)hinter[ba];
+        g += pair_coef[p] * nij / (double)shell_volumes[b];
+    }
+    G[b] = 4.0 * 3.14159265358979323846 * (double)shell_centers[b] * rho0 * (g - 1.0);
+}
+
+__global__ void shape_sq_kernel(const double *__restrict__ G, const float *__restrict__ shell_centers, int hs,
+                                const float *__restrict__ q, int nq, double *__restrict__ S1)
+{
+    const int m = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (m >= nq) return;
+    const double dr = (double)shell_centers[1] - (double)shell_centers[0], qq = (double)q[m];
+    double acc = 0.0;
+    for (int b = 0; b < hs; ++b) acc += G[b] * dr * sin(qq * (double)shell_centers[b]) / qq;
+    S1[m] = acc;
+}
+
+__global__ void shape_back_kernel(const double *__restrict__ S1, const float *__restrict__ q, int nq, const float *__restrict__ r,
+                                  int nr, float *__restrict__ out)
+{
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= nr) return;
+    const double dq = (double)q[1] - (double)q[0], rr = (double)r[k];
+    double acc = 0.0;
+    for (int m = 0; m < nq; ++m) acc += (double)q[m] * S1[m] * dq * sin((double)q[m] * rr);
+    out[k] = (float)((2.0 / 3.14159265358979323846) * acc);
+}
+
 // ------------------------------------------------------------------ host helpers
 static inline Lattice make_lattice(const float *basis)
 {
@@ -456,6 +505,43 @@ static int reciprocal_common(int dev, int which, const float *a, const float *b,
     FRMC_LAUNCH_CHECK();
     FRMC_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, c->stream));
     FRMC_CUDA(cudaStreamSynchronize(c->stream));
+    return FRMC_OK;
+}
+
+int frmc_shape_function(int dev, const float *hintra, const float *hinter, int nEl, int hs, int n_pairs, const int32_t *pair_a,
+                        const int32_t *pair_b, const double *pair_coef, const float *shell_volumes, const float *shell_centers,
+                        double rho0, const float *q, int nq, const float *r, int nr, float *out)
+{
+    FRMC_REQUIRE(hintra && hinter && pair_a && pair_b && pair_coef && shell_volumes && shell_centers && q && r && out, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(nEl >= 1 && nEl <= FRMC_MAX_ELEMENTS && hs >= 2 && nq >= 2 && nr >= 1 && n_pairs >= 1, FRMC_EINVAL, "bad sizes");
+    DeviceCtx *c = get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    const size_t cells = (size_t)nEl * nEl * hs;
+    float *d_h = (float *)ctx_buffer(c, 0, sizeof(float) * 2 * cells);
+    float *d_f = (float *)ctx_buffer(c, 1, sizeof(float) * ((size_t)2 * hs + nq + 2 * (size_t)nr));
+    double *d_d = (double *)ctx_buffer(c, 2, sizeof(double) * ((size_t)n_pairs + hs + nq) + sizeof(int) * 2 * (size_t)n_pairs);
+    if (!d_h || !d_f || !d_d) return FRMC_ENOMEM;
+    float *d_vol = d_f, *d_cen = d_f + hs, *d_q = d_f + 2 * hs, *d_r = d_q + nq, *d_out = d_r + nr;
+    double *d_coef = d_d, *d_G = d_d + n_pairs, *d_S1 = d_G + hs;
+    int *d_pa = reinterpret_cast<int *>(d_S1 + nq), *d_pb = d_pa + n_pairs;
+    cudaStream_t st = c->stream;
+    FRMC_CUDA(cudaMemcpyAsync(d_h, hintra, sizeof(float) * cells, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_h + cells, hinter, sizeof(float) * cells, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_vol, shell_volumes, sizeof(float) * hs, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_cen, shell_centers, sizeof(float) * hs, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_q, q, sizeof(float) * nq, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_r, r, sizeof(float) * nr, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_coef, pair_coef, sizeof(double) * n_pairs, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_pa, pair_a, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, st));
+    FRMC_CUDA(cudaMemcpyAsync(d_pb, pair_b, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, st));
+    shape_gr_kernel<<<(hs + 127) / 128, 128, 0, st>>>(d_h, d_h + cells, nEl, hs, n_pairs, d_pa, d_pb, d_coef, d_vol, d_cen, rho0, d_G);
+    FRMC_LAUNCH_CHECK();
+    shape_sq_kernel<<<(nq + 63) / 64, 64, 0, st>>>(d_G, d_cen, hs, d_q, nq, d_S1);
+    FRMC_LAUNCH_CHECK();
+    shape_back_kernel<<<(nr + 63) / 64, 64, 0, st>>>(d_S1, d_q, nq, d_r, nr, d_out);
+    FRMC_LAUNCH_CHECK();
+    FRMC_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * nr, cudaMemcpyDeviceToHost, st));
+    FRMC_CUDA(cudaStreamSynchronize(st));
     return FRMC_OK;
 }
 

@@ -1,105 +1,67 @@
-"""Shape function of a finite (nano-particle) system, the reference's ``ShapeFunction``
-(Constraints/Collection.py:20-125) as used by ``PairDistributionConstraint._update_shape_array``
+"""Shape function of a finite (nano-particle) system on the device: what the reference's ``ShapeFunction``
+(Constraints/Collection.py:20-125) hands ``PairDistributionConstraint._update_shape_array``
 (Constraints/PairDistributionConstraints.py:316-343).
 
-The expensive step -- the full pair histogram of the whole system on the shape function's own coarse
-r-grid -- runs on the device (``Core.pairs_histograms.full_pairs_histograms_coords``); the rest is a few
-hundred float32 numbers and follows the reference's numpy expressions one for one on the host:
-
-* the r-grid and Q values of the private StructureFactorConstraint (StructureFactorConstraints.py:330-350),
-* its *plotting-path* total ``get_constraint_value()["total"]`` (StructureFactorConstraints.py:836-896; note the
-  operation order differs from the fitting path ``__get_total_Sq``),
-* the sine back-transform ``G(r) = 2/pi * sum_q q (S(q)-1) sin(q r) dq`` (Collection.py:83-91).
+Both steps run on the GPU: the full pair histogram of the current configuration on the shape function's own coarse
+r-grid (``Core.pairs_histograms.full_pairs_histograms_coords``) and the chain histogram -> G(r) -> S(q) - 1 -> sine
+back-transform onto the constraint's r values (``frmc_shape_function``, csrc/stateless.cu).  This module only lays
+out the inputs: the r-grid and q values the reference's private StructureFactorConstraint would build from
+(rmin, rmax, dr) and (qmin, qmax, dq), and one coefficient per element pair.
 """
+import ctypes
+import itertools
+
 import numpy as np
 
-from .model import FLOAT_TYPE, PI, elements_pairs, gr2sq_matrix, shell_volumes_from_edges
+from . import _lib as L
+from .model import FLOAT_TYPE, shell_volumes_from_edges
 
 
-def auto_rmax(isPBC, basisVectors, realCoordinates):
-    """rmax when the parameters leave it open (PairDistributionConstraints.py:323-334)"""
+def default_rmax(isPBC, basisVectors, coordinates):
+    """the histogram's reach when the parameters leave rmax open: ten Angstrom beyond the longest cell edge of a
+    periodic box, beyond the diameter about the centroid of a finite one (PairDistributionConstraints.py:323-334)"""
     if isPBC:
-        lengths = [np.linalg.norm(v) for v in np.asarray(basisVectors)]        # boundaryConditions.get_a/b/c
-        return FLOAT_TYPE(np.max(lengths) + 10)
-    real = np.asarray(realCoordinates)
-    coordsCenter = np.sum(real, axis=0) / real.shape[0]
-    coordinates = real - coordsCenter
-    distances = np.sqrt(np.sum(coordinates ** 2, axis=1))
-    maxDistance = 2. * np.max(distances)
-    return FLOAT_TYPE(maxDistance + 10)
-
-
-def shape_grid(rmin, rmax, dr):
-    """edges, centres, volumes of the private StructureFactorConstraint (rmax given: :340-350)"""
-    rmin, rmax, dr = FLOAT_TYPE(rmin), FLOAT_TYPE(rmax), FLOAT_TYPE(dr)
-    edges = np.arange(rmin, rmax + dr, dr).astype(FLOAT_TYPE)
-    centers = (edges[0:-1] + edges[1:]) / FLOAT_TYPE(2.)
-    return edges, centers, shell_volumes_from_edges(edges)
-
-
-def plotting_total_Sq(intra, inter, elements, n_per_element, weighting, volume, numberOfAtoms, shell_centers,
-                      shell_volumes, gr2sq):
-    """StructureFactorConstraint._get_constraint_value(...)["total"] with scale factor 1, no window (:836-896)"""
-    volume = FLOAT_TYPE(volume)
-    gr = np.zeros(shell_centers.shape[0], dtype=FLOAT_TYPE)
-    for pair in elements_pairs(elements):
-        wij = weighting.get(pair[0] + "-" + pair[1], None)
-        if wij is None:
-            wij = weighting[pair[1] + "-" + pair[0]]
-        ni, nj = n_per_element[pair[0]], n_per_element[pair[1]]
-        idi, idj = elements.index(pair[0]), elements.index(pair[1])
-        sf_intra = np.zeros(shell_centers.shape[0], dtype=FLOAT_TYPE)
-        sf_inter = np.zeros(shell_centers.shape[0], dtype=FLOAT_TYPE)
-        if idi == idj:
-            Nij = ni * (ni - 1) / 2.0
-            sf_intra += intra[idi, idj, :]
-            sf_inter += inter[idi, idj, :]
-        else:
-            Nij = ni * nj
-            sf_intra += intra[idi, idj, :] + intra[idj, idi, :]
-            sf_inter += inter[idi, idj, :] + inter[idj, idi, :]
-        nij = sf_intra + sf_inter
-        dij = nij / shell_volumes
-        Dij = Nij / volume
-        gr += wij * dij / Dij
-    rho0 = FLOAT_TYPE(numberOfAtoms / volume)
-    Gr = (FLOAT_TYPE(4.) * PI * shell_centers * rho0) * (gr - 1)
-    return np.sum(Gr.reshape((-1, 1)) * gr2sq, axis=0) + 1
-
-
-def Gr_from_Sq(qValues, rValues, Sq):
-    """ShapeFunction.__get_Gr_from_Sq (Collection.py:83-91)"""
-    Gr = np.zeros(len(rValues), dtype=FLOAT_TYPE)
-    sq_1 = Sq - 1
-    qsq_1 = qValues * sq_1
-    dq = qValues[1] - qValues[0]
-    for ridx, r in enumerate(rValues):
-        sinqr_dq = dq * np.sin(qValues * r)
-        Gr[ridx] = (2. / PI) * np.sum(qsq_1 * sinqr_dq)
-    return Gr
+        return FLOAT_TYPE(max(float(np.linalg.norm(v)) for v in np.asarray(basisVectors)) + 10)
+    xyz = np.asarray(coordinates)
+    radius = np.sqrt(((xyz - xyz.sum(axis=0) / xyz.shape[0]) ** 2).sum(axis=1)).max()
+    return FLOAT_TYPE(2. * radius + 10)
 
 
 def get_Gr_shape_function(rValues, boxCoordinates, basisVectors, isPBC, moleculesIndex, elementsIndex, elements,
-                          numberOfAtomsPerElement, volume, weighting, qmin=0.001, qmax=1, dq=0.005, rmin=0.00, rmax=100, dr=1,
-                          full_histogram=None):
-    """ShapeFunction(engine, ...).get_Gr_shape_function(rValues) for the given engine arrays.
-
-    ``weighting`` is the private constraint's weighting scheme ("A-B" -> float32), i.e. what
-    ``get_normalized_weighting`` returns for the "atomicNumber" property; ``full_histogram`` defaults to the
-    CUDA ``full_pairs_histograms_coords`` (tests pass the oracle's to pin the host arithmetic on the CPU)."""
-    if full_histogram is None:
-        from .Core.pairs_histograms import full_pairs_histograms_coords as full_histogram
+                          numberOfAtomsPerElement, volume, weighting, qmin=0.001, qmax=1, dq=0.005, rmin=0.00, rmax=100, dr=1):
+    """G_shape(r) on ``rValues`` for the given engine arrays (ShapeFunction(engine, ...).get_Gr_shape_function).
+    ``weighting`` is the weighting scheme of the private constraint ("A-B" -> float32: what
+    ``get_normalized_weighting`` returns for the "atomicNumber" property)."""
+    from .Core.pairs_histograms import full_pairs_histograms_coords
+    lib = L.load_library()
     elements = list(elements)
-    Q = np.arange(FLOAT_TYPE(qmin), FLOAT_TYPE(qmax), FLOAT_TYPE(dq))
-    qValues = np.transpose([Q, np.zeros(len(Q))]).astype(FLOAT_TYPE)[:, 0]
-    edges, centers, volumes = shape_grid(rmin, rmax, dr)
-    hs = len(edges) - 1
-    intra, inter = full_histogram(boxCoords=np.ascontiguousarray(boxCoordinates, dtype=FLOAT_TYPE),
-                                  basis=np.ascontiguousarray(basisVectors, dtype=FLOAT_TYPE), isPBC=bool(isPBC),
-                                  moleculeIndex=np.ascontiguousarray(moleculesIndex, dtype=np.int32),
-                                  elementIndex=np.ascontiguousarray(elementsIndex, dtype=np.int32),
-                                  numberOfElements=len(elements), minDistance=edges[0], maxDistance=edges[-1],
-                                  bin=FLOAT_TYPE(dr), histSize=hs)
-    Sq = plotting_total_Sq(intra, inter, elements, numberOfAtomsPerElement, weighting, volume, len(elementsIndex), centers,
-                           volumes, gr2sq_matrix(qValues, centers))
-    return Gr_from_Sq(qValues, np.asarray(rValues, dtype=FLOAT_TYPE), Sq)
+    nEl = len(elements)
+    q = np.ascontiguousarray(np.arange(FLOAT_TYPE(qmin), FLOAT_TYPE(qmax), FLOAT_TYPE(dq)), dtype=FLOAT_TYPE)
+    step = FLOAT_TYPE(dr)
+    edges = np.arange(FLOAT_TYPE(rmin), FLOAT_TYPE(rmax) + step, step).astype(FLOAT_TYPE)      # StructureFactorConstraints.py:341
+    centers = np.ascontiguousarray((edges[:-1] + edges[1:]) / FLOAT_TYPE(2.), dtype=FLOAT_TYPE)
+    volumes = np.ascontiguousarray(shell_volumes_from_edges(edges), dtype=FLOAT_TYPE)
+    hs = centers.shape[0]
+    intra, inter = full_pairs_histograms_coords(boxCoords=np.ascontiguousarray(boxCoordinates, dtype=FLOAT_TYPE),
+                                                basis=np.ascontiguousarray(basisVectors, dtype=FLOAT_TYPE), isPBC=bool(isPBC),
+                                                moleculeIndex=np.ascontiguousarray(moleculesIndex, dtype=np.int32),
+                                                elementIndex=np.ascontiguousarray(elementsIndex, dtype=np.int32),
+                                                numberOfElements=nEl, minDistance=edges[0], maxDistance=edges[-1], bin=step, histSize=hs)
+    pairs = sorted(itertools.combinations_with_replacement(elements, 2))
+    pa = np.array([elements.index(a) for a, _ in pairs], np.int32)
+    pb = np.array([elements.index(b) for _, b in pairs], np.int32)
+    coef = np.empty(len(pairs), np.float64)                       # w_ij / D_ij, D_ij = (pairs of the kind) / volume
+    for k, (a, b) in enumerate(pairs):
+        w = weighting.get(a + "-" + b, weighting.get(b + "-" + a))
+        na, nb = numberOfAtomsPerElement[a], numberOfAtomsPerElement[b]
+        kinds = na * (na - 1) / 2.0 if a == b else float(na) * nb
+        coef[k] = float(w) * float(volume) / kinds if kinds > 0 else 0.0
+    r = np.ascontiguousarray(rValues, dtype=FLOAT_TYPE)
+    out = np.empty(r.shape[0], FLOAT_TYPE)
+    rho0 = float(len(elementsIndex)) / float(volume)
+    rc = lib.frmc_shape_function(L.device_index(), L.ptr(intra, L.c_f32p), L.ptr(inter, L.c_f32p), nEl, hs, len(pairs), L.ptr(pa, L.c_i32p),
+                                 L.ptr(pb, L.c_i32p), coef.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), L.ptr(volumes, L.c_f32p),
+                                 L.ptr(centers, L.c_f32p), rho0, L.ptr(q, L.c_f32p), q.shape[0], L.ptr(r, L.c_f32p), r.shape[0],
+                                 L.ptr(out, L.c_f32p))
+    L.check(rc, "shape_function")
+    return out

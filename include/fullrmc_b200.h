@@ -165,6 +165,16 @@ int frmc_gr_to_sq(int dev, const float *distances, const float *gr, int64_t n, c
 int frmc_sq_to_Gr(int dev, const float *qvalues, const float *rvalues, const float *sq, int64_t m, int64_t n,
                   float *Gr);
 
+/* Shape function of a finite system on the device (ShapeFunction.get_Gr_shape_function,
+ * Constraints/Collection.py:83-110, and the private StructureFactorConstraint's total behind it): from the ordered
+ * histograms hintra / hinter [nEl,nEl,hs] of the whole system on the shape grid (shell volumes / centres [hs]) to
+ * G_shape on the r values r[nr], through S(q)-1 on q[nq].  pair_a / pair_b / pair_coef [n_pairs]: the unordered
+ * element pairs and w_ij / D_ij of each (weighting scheme over N_ij / volume).  Double-precision sums; within 1e-6
+ * (norm-wise) of the reference's float32 numpy path. */
+int frmc_shape_function(int dev, const float *hintra, const float *hinter, int nEl, int hs, int n_pairs, const int32_t *pair_a,
+                        const int32_t *pair_b, const double *pair_coef, const float *shell_volumes, const float *shell_centers,
+                        double rho0, const float *q, int nq, const float *r, int nr, float *out);
+
 /* ---- distance-constraint kernels (Extensions/atomic_distances.pyx) --------------
  * multiple_atomic_distances_coords (:326-417) / full_atomic_distances_coords (:500-567): counts and float32 sums
  * of the (optionally reduced) distances of the pairs inside -- or, without FRMC_AD_WITHIN, outside -- the
