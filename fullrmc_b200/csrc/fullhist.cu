@@ -813,6 +813,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     W.off_swap = 0u; W.oi = 0u;
     W.span = (A.mol_span >= 0x40000000u) ? 0x7FFFFFFFu : A.mol_span;
     W.slow = &s_slow;
+    const uint32_t sJ_addr = fh_smem_u32(sJ), mbar_addr = fh_smem_u32(mbar);
     uint32_t wp = W.w0;
     const float inv_bin = TABLE ? __frcp_rn(g.bin) : 0.f, c0 = TABLE ? -g.rmin * inv_bin : 0.f;
     unsigned long long swept = 0;
@@ -880,9 +881,12 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                 auto issue = [&](int bit, unsigned sq) {
                     const int jbb = __shfl_sync(0xffffffffu, jb, bit & ~7);
                     if (lane == 0) {
-                        const int st = (int)(sq & 1u);
-                        fh_mbar_expect_tx(&mbar[st], 32 * 16);
-                        fh_bulk_g2s(sJ + st * 32, A.recs + ((size_t)jbb * SEG_PAD + (size_t)(bit & 7) * 32), 32 * 16, &mbar[st]);
+                        // plain 32-bit shared-window addresses kept in registers: no generic->shared conversion per copy
+                        const uint32_t st = sq & 1u, bar = mbar_addr + 8u * st, dst = sJ_addr + 512u * st;
+                        const float4 *src = A.recs + ((size_t)jbb * SEG_PAD + (size_t)(bit & 7) * 32);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(512u) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                     ::"r"(dst), "l"(src), "r"(512u), "r"(bar) : "memory");
                     }
                 };
                 issue(__ffs(m) - 1, seq);
@@ -892,7 +896,15 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                     __syncwarp();                              // every lane has read the stage the next copy overwrites
                     if (m) issue(__ffs(m) - 1, seq + 1u);
                     const int st = (int)(seq & 1u);
-                    fh_mbar_wait(&mbar[st], (seq >> 1) & 1u);
+                    {
+                        unsigned ok = 0, spins = 0;
+                        const uint32_t bar = mbar_addr + 8u * (uint32_t)st, parity = (seq >> 1) & 1u;
+                        do {
+                            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                            if (!ok && ++spins > 100000000u) __trap();     // never hang the GPU on a lost transaction
+                        } while (!ok);
+                    }
                     const float4 *sJu = sJ + st * 32;
                     if ((m_tri >> bit) & 1u) {
                         if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))

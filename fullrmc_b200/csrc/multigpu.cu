@@ -185,6 +185,24 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
         if (!d.atoms || !d.orig || !d.rows || !d.bbox || !d.counts || (lay.mol_span > 0 && !d.mol)) return FRMC_ENOMEM;
         d.rc = FRMC_OK;
     }
+    // direct NVLink copies device 0 -> device k (without peer access cudaMemcpyPeerAsync stages through the host)
+    {
+        static std::mutex mu;
+        static bool enabled[64][64];
+        std::lock_guard<std::mutex> lock(mu);
+        for (int k = 1; k < ndev; ++k) {
+            const int a = c0->dev, b = ctx[(size_t)k]->dev;
+            if (a >= 64 || b >= 64 || enabled[a][b]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                cudaSetDevice(a);
+                if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();      // already enabled by the host program
+                cudaSetDevice(b);
+                if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
+            }
+            enabled[a][b] = true;
+        }
+    }
     FRMC_CUDA(cudaSetDevice(c0->dev));
     cudaEvent_t ready;
     FRMC_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
