@@ -7,13 +7,12 @@
 // Parity contract: counts are integers; the distance SUMS are float32 `+=` in the reference's loop order (listed
 // atom, then i ascending), which a parallel reduction cannot reproduce.  So the sweep (same exact fp32 distance
 // arithmetic and d^2 thresholds as the histogram kernels) only EMITS the hits -- key (row, i), payload (slot,
-// value) -- into a device list; the list is radix-sorted by key (cub) and one thread per output cell adds its
+// value) -- into a device list; the list is radix-sorted by key (rs_* kernels below) and one thread per output cell adds its
 // entries in that order.  Hits are the exception by construction (the constraint exists to keep atoms apart);
 // the list grows on demand and the call fails loudly beyond FRMC_ATOMDIST_MAX_HITS.
 #include "common.cuh"
 #include "layout.h"
 
-#include <cub/device/device_radix_sort.cuh>
 
 #include <cstring>
 #include <vector>
@@ -89,6 +88,82 @@ atomdist_hits_kernel(const float *__restrict__ coords, const int *__restrict__ m
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort of (key, value) pairs
+// 8 bits per pass, three kernels per pass: digit counts per 4096-key block, exclusive scan of the [digit][block] table,
+// stable scatter (rounds of 256 keys in order; inside a round __match_any_sync ranks the lanes of a warp that share a
+// digit, per-warp counts order the warps).  Passes over digits every key shares (the bits above log2 N of either half
+// of the (row, other) key) are skipped by the caller.
+static const int RS_THREADS = 256, RS_ROUNDS = 16, RS_BLOCK = RS_THREADS * RS_ROUNDS;
+
+__global__ void __launch_bounds__(RS_THREADS) rs_count_kernel(const unsigned long long *__restrict__ keys, unsigned long long n, int shift,
+                                                              unsigned int *__restrict__ table, int n_blocks)
+{
+    __shared__ unsigned int cnt[256];
+    cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long base = (unsigned long long)blockIdx.x * RS_BLOCK;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const unsigned long long i = base + (unsigned long long)r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&cnt[(unsigned)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    table[(size_t)threadIdx.x * n_blocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// exclusive scan of the digit-major table [256][n_blocks] by one CTA
+__global__ void __launch_bounds__(1024) rs_scan_kernel(unsigned int *__restrict__ table, long long len)
+{
+    __shared__ unsigned int part[1024];
+    const int t = threadIdx.x;
+    const long long per = (len + 1023) / 1024, a = min(len, t * per), b = min(len, a + per);
+    unsigned int sum = 0;
+    for (long long i = a; i < b; ++i) sum += table[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned int v = (t >= o) ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned int run = part[t] - sum;
+    for (long long i = a; i < b; ++i) { const unsigned int v = table[i]; table[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vals,
+                                                                unsigned long long n, int shift, const unsigned int *__restrict__ table, int n_blocks,
+                                                                unsigned long long *__restrict__ keys_out, unsigned long long *__restrict__ vals_out)
+{
+    __shared__ unsigned int run[256];                  // next output position of every digit for this block
+    __shared__ unsigned int wcnt[RS_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    run[tid] = table[(size_t)tid * n_blocks + blockIdx.x];
+    const unsigned long long base = (unsigned long long)blockIdx.x * RS_BLOCK;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        for (int w = 0; w < RS_THREADS / 32; ++w) wcnt[w][tid] = 0u;
+        __syncthreads();
+        const unsigned long long i = base + (unsigned long long)r * RS_THREADS + tid;
+        const bool live = i < n;
+        unsigned long long k = 0, v = 0;
+        unsigned d = 256u + (unsigned)lane;            // dead lanes match nobody
+        if (live) { k = keys[i]; v = vals[i]; d = (unsigned)(k >> shift) & 255u; }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (live && rank == 0) wcnt[warp][d] = (unsigned)__popc(peers);
+        __syncthreads();
+        if (live) {
+            unsigned before = run[d];
+            for (int w = 0; w < warp; ++w) before += wcnt[w][d];
+            keys_out[before + rank] = k; vals_out[before + rank] = v;
+        }
+        __syncthreads();
+        unsigned add = 0;
+        for (int w = 0; w < RS_THREADS / 32; ++w) add += wcnt[w][tid];
+        run[tid] += add;
+        __syncthreads();
     }
 }
 
@@ -179,11 +254,11 @@ atomdist_block_kernel(const float4 *__restrict__ atoms, const uint32_t *__restri
 
 using namespace frmc;
 
-// grow-only hit-list scratch per device (keys, values and their sorted copies, cub temp storage)
+// grow-only hit-list scratch per device (keys, values, their ping-pong copies, the sort's digit table)
 struct AdScratch {
     unsigned long long *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
-    void *temp = nullptr;
-    size_t cap = 0, temp_bytes = 0;
+    unsigned int *table = nullptr;
+    size_t cap = 0;
 };
 static AdScratch g_ad[64];
 
@@ -191,32 +266,58 @@ static int ad_reserve(AdScratch &sc, size_t cap, cudaStream_t stream)
 {
     if (sc.cap >= cap) return FRMC_OK;
     FRMC_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(sc.keys); cudaFree(sc.vals); cudaFree(sc.keys2); cudaFree(sc.vals2); cudaFree(sc.temp);
+    cudaFree(sc.keys); cudaFree(sc.vals); cudaFree(sc.keys2); cudaFree(sc.vals2); cudaFree(sc.table);
     sc = AdScratch();
     FRMC_CUDA(cudaMalloc((void **)&sc.keys, sizeof(unsigned long long) * cap));
     FRMC_CUDA(cudaMalloc((void **)&sc.vals, sizeof(unsigned long long) * cap));
     FRMC_CUDA(cudaMalloc((void **)&sc.keys2, sizeof(unsigned long long) * cap));
     FRMC_CUDA(cudaMalloc((void **)&sc.vals2, sizeof(unsigned long long) * cap));
-    size_t bytes = 0;
-    FRMC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)std::min<size_t>(cap, 1u << 30), 0, 64, stream));
-    FRMC_CUDA(cudaMalloc(&sc.temp, bytes));
-    sc.temp_bytes = bytes;
+    FRMC_CUDA(cudaMalloc((void **)&sc.table, sizeof(unsigned int) * 256 * ((cap + RS_BLOCK - 1) / RS_BLOCK + 1)));
     sc.cap = cap;
     return FRMC_OK;
 }
 
 // sort the hits by (listed atom, other atom), add them per output cell in that order, hand the arrays back
-static int ad_finish(DeviceCtx *c, AdScratch &sc, unsigned long long hits, int cells, const int *d_counts, float *d_sums,
+// sort `hits` (key, value) pairs by key; index_bits = bits either 32-bit half of a key can use.  Returns the buffer
+// that holds the sorted values.
+static int index_bits_of(int64_t n)
+{
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) < n) ++bits;
+    return bits;
+}
+
+static int ad_sort(cudaStream_t stream, AdScratch &sc, unsigned long long hits, int index_bits, const unsigned long long **sorted_vals)
+{
+    unsigned long long *ka = sc.keys, *va = sc.vals, *kb = sc.keys2, *vb = sc.vals2;
+    const int n_blocks = (int)((hits + RS_BLOCK - 1) / RS_BLOCK);
+    const int passes_half = (index_bits + 7) / 8;
+    for (int half = 0; half < 2; ++half)
+        for (int p = 0; p < passes_half; ++p) {
+            const int shift = 32 * half + 8 * p;
+            rs_count_kernel<<<n_blocks, RS_THREADS, 0, stream>>>(ka, hits, shift, sc.table, n_blocks);
+            FRMC_LAUNCH_CHECK();
+            rs_scan_kernel<<<1, 1024, 0, stream>>>(sc.table, 256ll * n_blocks);
+            FRMC_LAUNCH_CHECK();
+            rs_scatter_kernel<<<n_blocks, RS_THREADS, 0, stream>>>(ka, va, hits, shift, sc.table, n_blocks, kb, vb);
+            FRMC_LAUNCH_CHECK();
+            std::swap(ka, kb); std::swap(va, vb);
+        }
+    *sorted_vals = va;
+    return FRMC_OK;
+}
+
+static int ad_finish(DeviceCtx *c, AdScratch &sc, unsigned long long hits, int index_bits, int cells, const int *d_counts, float *d_sums,
                      int32_t *nintra, float *dintra, int32_t *ninter, float *dinter)
 {
     std::vector<int> h_counts((size_t)2 * cells);
     std::vector<float> h_sums((size_t)2 * cells, 0.0f);
     FRMC_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
     if (hits > 0) {
-        size_t bytes = sc.temp_bytes;
-        FRMC_CUDA(cub::DeviceRadixSort::SortPairs(sc.temp, bytes, sc.keys, sc.keys2, sc.vals, sc.vals2, (int)hits, 0, 64, c->stream));
-        ++g_launch_count;
-        atomdist_sum_kernel<<<(2 * cells + 63) / 64, 64, 0, c->stream>>>(sc.vals2, hits, 2 * cells, d_sums);
+        const unsigned long long *sorted = nullptr;
+        int rc = ad_sort(c->stream, sc, hits, index_bits, &sorted);
+        if (rc) return rc;
+        atomdist_sum_kernel<<<(2 * cells + 63) / 64, 64, 0, c->stream>>>(sorted, hits, 2 * cells, d_sums);
         FRMC_LAUNCH_CHECK();
         FRMC_CUDA(cudaMemcpyAsync(h_sums.data(), d_sums, sizeof(float) * 2 * cells, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -301,7 +402,7 @@ extern "C" int frmc_multiple_atomic_distances_coords(int dev, const int32_t *ind
         rc = ad_reserve(sc, (size_t)(hits + hits / 8), c->stream);      // second pass with room for all of them
         if (rc) return rc;
     }
-    return ad_finish(c, sc, hits, cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
+    return ad_finish(c, sc, hits, index_bits_of(std::max<int64_t>(n, k)), cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
 }
 
 // the full pass on the k-d ordered store with block culling (within-limits mode only: there the hits are the pairs
@@ -384,7 +485,7 @@ static int full_culled(int dev, const float *coords, int64_t n, const float *bas
         rc = ad_reserve(sc, (size_t)(hits + hits / 8), c->stream);
         if (rc) return rc;
     }
-    return ad_finish(c, sc, hits, cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
+    return ad_finish(c, sc, hits, index_bits_of(n), cells, d_counts, d_sums, nintra, dintra, ninter, dinter);
 }
 
 extern "C" int frmc_full_atomic_distances_coords(int dev, const float *coords, int64_t n, const float *basis, int isPBC,
