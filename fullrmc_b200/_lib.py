@@ -43,6 +43,11 @@ class ModelDesc(ctypes.Structure):
     ]
 
 
+class AmputationDesc(ctypes.Structure):
+    """Mirror of ``struct frmc_amputation_desc`` (include/fullrmc_b200.h)."""
+    _fields_ = [("pair_w", c_f32p), ("pair_D", c_f32p), ("prefactor", c_f32p)]
+
+
 # every symbol include/fullrmc_b200.h declares: name -> (restype, argtypes)
 _I, _I64, _F, _VP = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 SIGNATURES = {
@@ -108,6 +113,12 @@ SIGNATURES = {
     # array arguments as plain addresses: the tight loop passes arr.__array_interface__["data"][0] (1 us) instead of
     # building a typed ctypes pointer per call (4 us each)
     "frmc_step": (_I, [_VP, _I, _VP, _I, _VP, c_f32p]),
+    "frmc_propose_amputation": (_I, [_VP, ctypes.c_int32, ctypes.POINTER(AmputationDesc), _I, c_f32p]),
+    "frmc_accept_amputation": (_I, [_VP]),
+    "frmc_reject_amputation": (_I, [_VP]),
+    "frmc_model_set_constants": (_I, [_VP, _I, c_f32p, c_f32p, c_f32p]),
+    "frmc_store_n_atoms": (_I64, [_VP]),
+    "frmc_import_data": (_I, [_VP, _I, c_f32p, c_f32p]),
     "frmc_run_batch": (_I, [_VP, _I, c_i32p, c_i32p, c_f32p, c_f32p, _F, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p,
                             ctypes.POINTER(ctypes.c_double)]),
     "frmc_store_batch_stats": (_I, [_VP, c_u64p, c_u64p, c_u64p]),

@@ -22,7 +22,7 @@ writes to put them behind the real constraint classes.
 """
 import numpy as np
 
-from .model import FLOAT_TYPE, PI, ModelSpec, shell_volumes_from_edges
+from .model import FLOAT_TYPE, PI, ModelSpec, shell_volumes_from_edges, faber_ziman_weights
 from .store import DeviceStore
 
 
@@ -51,6 +51,8 @@ class DeviceBackend(object):
         self._chi2 = None            # chi^2 per model of the staged proposal
         self._resolved = True
         self._dirty = True           # committed data need a compute_data pass
+        self.allowFittingScaleFactor = False   # engine._RT_moveGenerator.allowFittingScaleFactor of a remove generator
+        self._amputation = None      # (relative index, chi^2 per model) of the removal being tried
 
     # -------------------------------------------------------------- registration
     def _grid(self, minDistance, maxDistance, bin, histSize):
@@ -114,6 +116,63 @@ class DeviceBackend(object):
             self._move = None
             self._chi2 = None
 
+    # -------------------------------------------------------------- atom removal (Engine.py:3231-3276, :758-797)
+    @property
+    def numberOfAtoms(self):
+        return self.store.numberOfAtoms
+
+    def _amputate(self, relativeIndex):
+        """compute_as_if_amputated of every registered constraint in one device evaluation"""
+        rel = int(relativeIndex)
+        if self._amputation is not None and self._amputation[0] == rel:
+            return self._amputation[1]
+        if not self._resolved or self._amputation is not None:
+            raise RuntimeError("previous move was neither accepted nor rejected")
+        self._compute_data()
+        element = self.elements[int(self.elementsIndex[rel])]
+        counts = dict(self.numberOfAtomsPerElement)
+        counts[element] -= 1
+        if counts[element] < 1:
+            raise ValueError("Collecting last atom of any element type is not allowed")          # Engine.py:776
+        rho0 = FLOAT_TYPE((self.numberOfAtoms - 1) / self.volume)                                 # PairDistributionConstraints.py:1198
+        specs = [None] * self.store.n_models
+        for c in self.constraints:
+            c._amputationWeighting = c._weighting_for(counts)
+            specs[c._model] = c._spec_with(counts, c._amputationWeighting, rho0)
+        chi2 = self.store.propose_amputation(rel, specs, allow_fit=self.allowFittingScaleFactor).copy()
+        self._amputation = (rel, chi2, counts)
+        return chi2
+
+    def _resolve_amputation(self, accept):
+        if self._amputation is None:
+            return
+        rel, chi2, counts = self._amputation
+        if accept:
+            self.store.accept_amputation()
+            self._committed = chi2.copy()
+            self.accepted += 1
+            self._pending_collect = (rel, counts)
+        else:
+            self.store.reject_amputation()
+        self._amputation = None
+
+    def _on_collector_collect_atom(self, relativeIndex=None):
+        """Engine._on_collector_collect_atom (Engine.py:758-797) for the engine state this backend mirrors: the per-atom
+        arrays lose the row, numberOfAtomsPerElement the atom, the number density follows in periodic systems only
+        (:795-796); every model then gets the constants of that state (its weighting scheme is the one its
+        accept_amputation adopted)."""
+        rel, counts = self._pending_collect
+        if relativeIndex is not None and int(relativeIndex) != rel:
+            raise ValueError("collected atom %d is not the amputated one (%d)" % (int(relativeIndex), rel))
+        self._pending_collect = None
+        self.moleculesIndex = np.delete(self.moleculesIndex, rel, axis=0)
+        self.elementsIndex = np.delete(self.elementsIndex, rel, axis=0)
+        self.numberOfAtomsPerElement = counts
+        if self.isPBC:
+            self.numberDensity = FLOAT_TYPE(self.numberOfAtoms) / FLOAT_TYPE(self.volume)
+        for c in self.constraints:
+            self.store.set_model_constants(c._model, c._spec_with(counts, c.weighting, self.numberDensity))
+
     def close(self):
         self.store.close()
 
@@ -124,8 +183,11 @@ class _DeviceExperimentalConstraint(object):
 
     def __init__(self, backend, experimentalData, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
                  weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None, adjustScaleFactor=(0, 0.8, 1.2),
-                 shapeFuncParams=None, shapeWeighting=None):
+                 shapeFuncParams=None, shapeWeighting=None, elementsWeight=None):
         self.backend = backend
+        self.weighting = dict(weighting)                 # the constraint's weightingScheme ("A-B" -> float32)
+        self.elementsWeight = None if elementsWeight is None else dict(elementsWeight)   # _elementsWeight (:486): only removals need it
+        self.amputationStandardError = None
         self.experimentalData = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         self.minimumDistance = FLOAT_TYPE(minDistance)
         self.maximumDistance = FLOAT_TYPE(maxDistance)
@@ -140,6 +202,7 @@ class _DeviceExperimentalConstraint(object):
         spec = ModelSpec(self.KIND, backend.elements, backend.numberOfAtomsPerElement, weighting, backend.volume,
                          backend.numberDensity, self.shellCenters, self.shellVolumes, self.experimentalData,
                          data_weights=dataWeights, shape_array=shapeArray, scale_factor=scaleFactor, q_values=qValues)
+        self._spec = spec
         backend._register(self, (self.minimumDistance, self.maximumDistance, self.bin, self.histogramSize), spec)
         # shape function refreshed from the running configuration (set_shape_function_parameters with a dict,
         # PairDistributionConstraints.py:502-567): defaults and types as there
@@ -239,6 +302,51 @@ class _DeviceExperimentalConstraint(object):
         self.backend._compute_data()
         return self.backend.store.export_total(self._model, staged=staged)
 
+    # -- atom removal (PairDistributionConstraints.py:1168-1238; PairCorrelationConstraints.py:394-462;
+    #    StructureFactorConstraints.py:1098-1166)
+    def _weighting_for(self, numberOfAtomsPerElement):
+        """get_normalized_weighting(numbers, weights=self._elementsWeight) cast to FLOAT_TYPE (:1190-1192)"""
+        if self.elementsWeight is None:
+            raise ValueError("removing atoms needs the constraint's elementsWeight (element -> weight)")
+        return faber_ziman_weights(numberOfAtomsPerElement, self.elementsWeight)
+
+    def _spec_with(self, numberOfAtomsPerElement, weighting, rho0):
+        """this constraint's model constants for another composition / number density"""
+        o = self._spec
+        return ModelSpec(o.kind, o.elements, numberOfAtomsPerElement, weighting, o.volume, rho0, o.shell_centers, o.shell_volumes,
+                         o.experimental, data_weights=o.data_weights, shape_array=o.shape_array, scale_factor=o.scale_factor,
+                         gr2sq=o.gr2sq, sq_exact=o.sq_exact)
+
+    def compute_as_if_amputated(self, realIndex, relativeIndex):
+        chi2 = self.backend._amputate(np.asarray(relativeIndex).ravel()[0])
+        self.amputationStandardError = FLOAT_TYPE(chi2[self._model])
+
+    def accept_amputation(self, realIndex, relativeIndex):
+        self.backend._resolve_amputation(True)
+        self.weighting = self._amputationWeighting
+        self.standardError = self.amputationStandardError
+        self.amputationStandardError = None
+
+    def reject_amputation(self, realIndex, relativeIndex):
+        self.backend._resolve_amputation(False)
+        self.amputationStandardError = None
+
+    def _on_collector_collect_atom(self, realIndex):
+        pass                                             # like the reference's: the engine-level hook does the work
+
+    def set_data(self, data):
+        """resume from saved data["intra"] / data["inter"] (Constraint.set_data; what the repository holds of this
+        constraint, Core/Constraint.py:275-288) instead of a compute_data pass"""
+        b = self.backend
+        b.store.import_data(self._grid, data["intra"], data["inter"])
+        b._imported = getattr(b, "_imported", set()) | {self._grid}
+        if b._imported >= set(b._grids.values()):          # every grid of the store has its counts: totals and chi^2
+            b._committed = b.store.finalize_data()
+            b._dirty = False
+            b._imported = set()
+            for c in b.constraints:
+                c.standardError = FLOAT_TYPE(b._committed[c._model])
+
     # -- the five methods (Core/Constraint.py:732-748)
     def compute_data(self, update=True):
         if update:
@@ -277,7 +385,7 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
     KIND = "PDF"
 
     def __init__(self, backend, experimentalData, weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0,
-                 adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None):
+                 adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None, elementsWeight=None):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         r = exp[:, 0]
         b = FLOAT_TYPE(r[1] - r[0])                                            # :726
@@ -288,7 +396,7 @@ class DevicePairDistributionConstraint(_DeviceExperimentalConstraint):
         super(DevicePairDistributionConstraint, self).__init__(
             backend, exp[:, 1], rmin, rmax, b, hs, np.array(r, dtype=FLOAT_TYPE), shell_volumes_from_edges(edges),
             weighting, dataWeights, shapeArray, scaleFactor, adjustScaleFactor=adjustScaleFactor,
-            shapeFuncParams=shapeFuncParams, shapeWeighting=shapeWeighting)
+            shapeFuncParams=shapeFuncParams, shapeWeighting=shapeWeighting, elementsWeight=elementsWeight)
 
 
 class DevicePairCorrelationConstraint(DevicePairDistributionConstraint):
@@ -304,7 +412,7 @@ class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
     KIND = "SQ"
 
     def __init__(self, backend, experimentalData, weighting, rmin=None, rmax=None, dr=None, dataWeights=None, scaleFactor=1.0,
-                 adjustScaleFactor=(0, 0.8, 1.2)):
+                 adjustScaleFactor=(0, 0.8, 1.2), elementsWeight=None):
         exp = np.ascontiguousarray(experimentalData, dtype=FLOAT_TYPE)
         qmax = exp[-1, 0]
         minimumDistance = FLOAT_TYPE(2. * PI / qmax) if rmin is None else FLOAT_TYPE(rmin)
@@ -325,7 +433,8 @@ class DeviceStructureFactorConstraint(_DeviceExperimentalConstraint):
         hs = len(edges) - 1
         super(DeviceStructureFactorConstraint, self).__init__(
             backend, exp[:, 1], edges[0], edges[-1], b, hs, centers, shell_volumes_from_edges(edges),
-            weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0], adjustScaleFactor=adjustScaleFactor)
+            weighting, dataWeights, None, scaleFactor, qValues=exp[:, 0], adjustScaleFactor=adjustScaleFactor,
+            elementsWeight=elementsWeight)
 
 
 class DeviceReducedStructureFactorConstraint(DeviceStructureFactorConstraint):
@@ -338,7 +447,7 @@ _KIND_CLASS = {}
 
 def make_device_constraint(backend, kind, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
                            weighting, dataWeights=None, shapeArray=None, scaleFactor=1.0, qValues=None,
-                           adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None):
+                           adjustScaleFactor=(0, 0.8, 1.2), shapeFuncParams=None, shapeWeighting=None, elementsWeight=None):
     """Build a device constraint from the quantities a reference constraint has already derived
     (limits, bin, histogram size, shell arrays, weighting scheme) -- what the subclass recipe of
     INTEGRATION.md hands over."""
@@ -347,4 +456,4 @@ def make_device_constraint(backend, kind, experimental, minDistance, maxDistance
             _KIND_CLASS[name] = type("Device%sConstraint" % name, (_DeviceExperimentalConstraint,), {"KIND": name})
     return _KIND_CLASS[kind](backend, experimental, minDistance, maxDistance, bin, histSize, shellCenters, shellVolumes,
                              weighting, dataWeights, shapeArray, scaleFactor, qValues, adjustScaleFactor, shapeFuncParams,
-                             shapeWeighting)
+                             shapeWeighting, elementsWeight)

@@ -2009,6 +2009,7 @@ struct ModelHost {
     float *total_committed = nullptr;
     int adjust_freq = 0;             // scale-factor refit every `freq` accepted moves (0: never)
     float sf_staged = 1.0f;          // scale factor the last evaluation used
+    float *amp_w = nullptr, *amp_D = nullptr, *amp_rD = nullptr, *amp_pref = nullptr;   // constants of the one-atom-fewer evaluation
     std::vector<void *> owned;
 };
 
@@ -2021,7 +2022,10 @@ struct frmc_store {
     DeviceCtx *ctx = nullptr;
     cudaStream_t stream = nullptr;
     int dev = 0;
-    int64_t n = 0, npad = 0;
+    int64_t n = 0, npad = 0;         // n: atoms the store holds NOW (the engine's relative numbering runs over them)
+    int64_t n0 = 0;                  // atoms the layout was built for (the "real" numbering: lay.inv, d_orig, d_mol, h_mol, h_el)
+    std::vector<int32_t> rel2real;   // relative -> real index once atoms have been removed (empty: identity)
+    int amp_rel = -1;                // relative index of the atom of the staged amputation
     int nEl = 0, isPBC = 0;
     Lattice L;
     float lo[3], hi[3];
@@ -2100,6 +2104,13 @@ struct frmc_store {
 };
 
 enum { TIME_DELTA = 0, TIME_FULL = 1, TIME_EPILOGUE = 2, TIME_COMMIT = 3 };
+
+// position in the sorted store of the atom the engine calls `idx` (its RELATIVE index: after atoms were removed
+// the engine's arrays are np.delete'd, Engine.py:781-788, and every later atom moves down by one)
+static inline int pos_of(const frmc_store *s, int idx)
+{
+    return s->lay.inv[s->rel2real.empty() ? idx : s->rel2real[idx]];
+}
 
 static cudaEvent_t timing_begin(frmc_store *s)
 {
@@ -2314,21 +2325,29 @@ static ModelDev launch_model(const frmc_store *s, const ModelHost &mh)
 }
 
 // totals + chi^2 of every model from the staged totals; results land in s->h_chi2 once h_seq == seq_expected
+static int launch_epilogue_ms(frmc_store *s, const ModelSet &ms);
+
 static int launch_epilogue(frmc_store *s)
 {
     const int nm = (int)s->models.size();
     if (nm == 0) return FRMC_OK;
     int rc = sync_models(s);
     if (rc) return rc;
-    GridSet gs = make_gridset(s);
     ModelSet ms;
     memset(&ms, 0, sizeof(ms));
     ms.n = nm;
+    for (int i = 0; i < nm; ++i) ms.m[i] = launch_model(s, s->models[i]);
+    return launch_epilogue_ms(s, ms);
+}
+
+// the same launch with the model descriptors the caller prepared (the one-atom-fewer evaluation swaps constants)
+static int launch_epilogue_ms(frmc_store *s, const ModelSet &ms)
+{
+    const int nm = ms.n;
+    GridSet gs = make_gridset(s);
     int max_q = 1;
-    for (int i = 0; i < nm; ++i) {
-        ms.m[i] = launch_model(s, s->models[i]);
+    for (int i = 0; i < nm; ++i)
         if (ms.m[i].kind == FRMC_KIND_SQ || ms.m[i].kind == FRMC_KIND_RSQ) max_q = std::max(max_q, ms.m[i].n_out);
-    }
     cudaEvent_t t0 = timing_begin(s);
     dim3 grid((unsigned)((max_q + 31) / 32), (unsigned)nm);
     epilogue_kernel<<<grid, EPI_THREADS, s->epi_smem, s->stream>>>(ms, gs, s->h_chi2, s->d_seq, s->h_seq,
@@ -2409,6 +2428,32 @@ static int dev_copy(ModelHost &mh, const T *src, size_t count, const T **dst)
     mh.owned.push_back(p);
     FRMC_CUDA(cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice));
     *dst = (const T *)p;
+    return FRMC_OK;
+}
+
+// rD[p] = RN(1/D[p]) when div_by_const is proven equal to the IEEE division for pair p over the whole count range
+// (validate_fastdiv_kernel on the device arrays d_w / d_D), NaN otherwise (the epilogue then divides)
+static int validated_reciprocals(frmc_store *s, int n_pairs, const float *d_w, const float *d_D, const float *h_D, std::vector<float> &rD)
+{
+    int *d_ok = nullptr;
+    float *d_rD = nullptr;
+    std::vector<int> ok((size_t)n_pairs, 1);
+    rD.assign((size_t)n_pairs, 0.f);
+    FRMC_CUDA(cudaMalloc(&d_ok, sizeof(int) * n_pairs));
+    FRMC_CUDA(cudaMalloc(&d_rD, sizeof(float) * n_pairs));
+    FRMC_CUDA(cudaMemcpy(d_ok, ok.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice));
+    validate_fastdiv_kernel<<<dim3(64, (unsigned)n_pairs), 256, 0, s->stream>>>(d_w, d_D, n_pairs, d_ok, d_rD);
+    ++g_launch_count;
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(ok.data(), d_ok, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(rD.data(), d_rD, sizeof(float) * n_pairs, cudaMemcpyDeviceToHost);
+    cudaFree(d_ok); cudaFree(d_rD);
+    if (e != cudaSuccess) { set_error("fast-division validation failed: %s", cudaGetErrorString(e)); return FRMC_ECUDA; }
+    for (int p = 0; p < n_pairs; ++p) {
+        const float Dp = h_D[p];
+        const bool sane = (Dp == Dp) && !isinf(Dp) && fabsf(Dp) > 1e-30f && fabsf(Dp) < 1e30f && (rD[p] == rD[p]);
+        if (!(ok[p] && sane)) rD[p] = __builtin_nanf("");
+    }
     return FRMC_OK;
 }
 
@@ -2595,6 +2640,8 @@ static int propose_persistent(frmc_store *s, int mode)
 // the per-move pipeline.  Fused path: ONE cooperative launch (resolve previous + delta pass +
 // epilogue).  Fallback (timing mode, FRMC_NO_FUSED=1, too many epilogue CTAs): delta pass
 // (proposal by value) + fused epilogue, two launches, after the pending resolution.
+static int launch_delta(frmc_store *s, int mode);
+
 static int launch_propose(frmc_store *s, int mode)
 {
     int rc = FRMC_OK;
@@ -2613,6 +2660,13 @@ static int launch_propose(frmc_store *s, int mode)
         }
     }
     if ((rc = flush_pending(s))) return rc;
+    if ((rc = launch_delta(s, mode))) return rc;
+    return launch_epilogue(s);
+}
+
+// the stand-alone delta pass of the staged proposal (s->prop_in)
+static int launch_delta(frmc_store *s, int mode)
+{
     GridSet gs = make_gridset(s);
     long long want = (s->npad + 256 * DELTA_UNROLL - 1) / (256 * DELTA_UNROLL);
     long long cap = (long long)s->ctx->sm_count * 8;
@@ -2629,7 +2683,7 @@ static int launch_propose(frmc_store *s, int mode)
 #undef LAUNCH_DELTA
     FRMC_LAUNCH_CHECK();
     timing_end(s, TIME_DELTA, t0);
-    return launch_epilogue(s);
+    return FRMC_OK;
 }
 
 static int stage_proposal(frmc_store *s, const int32_t *indexes, int k, const float *moved)
@@ -2645,7 +2699,7 @@ static int stage_proposal(frmc_store *s, const int32_t *indexes, int k, const fl
     bool finite = true;
     for (int t = 0; t < k; ++t) {
         FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", indexes[t], (long long)s->n - 1);
-        h.pos[t] = s->lay.inv[indexes[t]];
+        h.pos[t] = pos_of(s, indexes[t]);
         for (int c = 0; c < 3; ++c) {
             float v = moved[3 * t + c];
             h.moved[3 * t + c] = v;
@@ -2770,7 +2824,7 @@ frmc_store *frmc_store_create(int dev, int64_t n, const float *coords, const flo
     DeviceCtx *c = get_ctx(dev);
     if (!c) return nullptr;
     frmc_store *s = new frmc_store();
-    s->ctx = c; s->dev = dev; s->n = n; s->nEl = nEl; s->isPBC = isPBC ? 1 : 0;
+    s->ctx = c; s->dev = dev; s->n = n; s->n0 = n; s->nEl = nEl; s->isPBC = isPBC ? 1 : 0;
     for (int i = 0; i < 9; ++i) s->L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     s->h_mol.assign(mol, mol + n);
     s->h_el.assign(el, el + n);
@@ -2850,6 +2904,16 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
     FRMC_CUDA(cudaSetDevice(s->dev));
     { int frc = flush_pending(s); if (frc) return frc; }
     if (basis) for (int i = 0; i < 9; ++i) s->L.b[i] = basis[i];
+    if (!s->rel2real.empty()) {
+        // atoms were removed since the layout was built: the caller's array has one row per remaining atom, so the
+        // per-atom tables are compacted and the store starts a new "real" numbering
+        std::vector<int32_t> mol((size_t)s->n), el((size_t)s->n);
+        for (int64_t i = 0; i < s->n; ++i) { mol[i] = s->h_mol[s->rel2real[i]]; el[i] = s->h_el[s->rel2real[i]]; }
+        s->h_mol.swap(mol); s->h_el.swap(el);
+        s->rel2real.clear();
+        s->n0 = s->n;
+        cudaFree(s->d_mol); s->d_mol = nullptr;
+    }
     int rc = upload_layout(s, coords);
     if (rc) return rc;
     s->items_shard = s->items_nshards = -1;
@@ -2869,7 +2933,7 @@ int frmc_store_get_coords(frmc_store *s, float *coords_out)
     FRMC_CUDA(cudaMemcpyAsync(rec.data(), s->d_atoms, sizeof(float4) * s->npad, cudaMemcpyDeviceToHost, s->stream));
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     for (int64_t i = 0; i < s->n; ++i) {
-        int64_t p = s->lay.inv[i];
+        int64_t p = pos_of(s, (int)i);
         coords_out[3 * i] = rec[4 * p]; coords_out[3 * i + 1] = rec[4 * p + 1]; coords_out[3 * i + 2] = rec[4 * p + 2];
     }
     return FRMC_OK;
@@ -2933,25 +2997,8 @@ int frmc_model_add(frmc_store *s, int grid, const frmc_model_desc *d)
     if ((rc = dev_copy(mh, d->pair_w, (size_t)d->n_pairs, &mh.dev.w))) return rc;
     if ((rc = dev_copy(mh, d->pair_D, (size_t)d->n_pairs, &mh.dev.D))) return rc;
     {   // reciprocal table for the 3-op exact division, each pair validated on the device
-        int *d_ok = nullptr;
-        float *d_rD = nullptr;
-        std::vector<int> ok((size_t)d->n_pairs, 1);
-        std::vector<float> rD((size_t)d->n_pairs, 0.f);
-        FRMC_CUDA(cudaMalloc(&d_ok, sizeof(int) * d->n_pairs));
-        FRMC_CUDA(cudaMalloc(&d_rD, sizeof(float) * d->n_pairs));
-        FRMC_CUDA(cudaMemcpy(d_ok, ok.data(), sizeof(int) * d->n_pairs, cudaMemcpyHostToDevice));
-        validate_fastdiv_kernel<<<dim3(64, (unsigned)d->n_pairs), 256, 0, s->stream>>>(mh.dev.w, mh.dev.D, d->n_pairs, d_ok, d_rD);
-        ++g_launch_count;
-        cudaError_t e = cudaStreamSynchronize(s->stream);
-        if (e == cudaSuccess) e = cudaMemcpy(ok.data(), d_ok, sizeof(int) * d->n_pairs, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(rD.data(), d_rD, sizeof(float) * d->n_pairs, cudaMemcpyDeviceToHost);
-        cudaFree(d_ok); cudaFree(d_rD);
-        if (e != cudaSuccess) { set_error("fast-division validation failed: %s", cudaGetErrorString(e)); return FRMC_ECUDA; }
-        for (int p = 0; p < d->n_pairs; ++p) {
-            const float Dp = d->pair_D[p];
-            const bool sane = (Dp == Dp) && !isinf(Dp) && fabsf(Dp) > 1e-30f && fabsf(Dp) < 1e30f && (rD[p] == rD[p]);
-            if (!(ok[p] && sane)) rD[p] = __builtin_nanf("");
-        }
+        std::vector<float> rD;
+        if ((rc = validated_reciprocals(s, d->n_pairs, mh.dev.w, mh.dev.D, d->pair_D, rD))) return rc;
         if ((rc = dev_copy(mh, (const float *)rD.data(), rD.size(), &mh.dev.rD))) return rc;
         if (d->n_pairs <= EPI_INLINE_PAIRS)
             for (int p = 0; p < d->n_pairs; ++p) {
@@ -3138,6 +3185,7 @@ int frmc_finalize_data(frmc_store *s, float *chi2)
     FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
     FRMC_CUDA(cudaSetDevice(s->dev));
     { int frc = flush_pending(s); if (frc) return frc; }
+    FRMC_CUDA(cudaMemsetAsync(s->d_next + 2, 0, sizeof(int), s->stream));      // the too-big flag of symmetrise_kernel
     for (auto &g : s->grids) {
         const long long ns = (long long)g.dev.nsym * g.dev.g.hs;
         int grid = (int)std::max<long long>(1, std::min<long long>((ns + 255) / 256, (long long)s->ctx->sm_count * 2));
@@ -3238,6 +3286,179 @@ int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const 
         if (rc) return rc;
     }
     return frmc_propose(s, indexes, k, moved, chi2_after);
+}
+
+// ---- dynamic N and persisted state ---------------------------------------------------
+int64_t frmc_store_n_atoms(frmc_store *s) { return s ? s->n : -1; }
+
+int frmc_model_set_constants(frmc_store *s, int model, const float *pair_w, const float *pair_D, const float *prefactor)
+{
+    FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }          // also ends a persistent run (descriptors travel by value)
+    ModelHost &mh = s->models[model];
+    const int np = mh.dev.n_pairs;
+    if (pair_w) FRMC_CUDA(cudaMemcpyAsync((void *)mh.dev.w, pair_w, sizeof(float) * np, cudaMemcpyHostToDevice, s->stream));
+    if (pair_D) FRMC_CUDA(cudaMemcpyAsync((void *)mh.dev.D, pair_D, sizeof(float) * np, cudaMemcpyHostToDevice, s->stream));
+    if (prefactor) FRMC_CUDA(cudaMemcpyAsync((void *)mh.dev.pref, prefactor, sizeof(float) * mh.dev.hs, cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    if (pair_w || pair_D) {
+        std::vector<float> hD((size_t)np), hw((size_t)np), rD;
+        FRMC_CUDA(cudaMemcpy(hD.data(), mh.dev.D, sizeof(float) * np, cudaMemcpyDeviceToHost));
+        FRMC_CUDA(cudaMemcpy(hw.data(), mh.dev.w, sizeof(float) * np, cudaMemcpyDeviceToHost));
+        int rc = validated_reciprocals(s, np, mh.dev.w, mh.dev.D, hD.data(), rD);
+        if (rc) return rc;
+        FRMC_CUDA(cudaMemcpy((void *)mh.dev.rD, rD.data(), sizeof(float) * np, cudaMemcpyHostToDevice));
+        if (np <= EPI_INLINE_PAIRS)
+            for (int p = 0; p < np; ++p) { mh.dev.i_w[p] = hw[p]; mh.dev.i_D[p] = hD[p]; mh.dev.i_rD[p] = rD[p]; }
+    }
+    s->models_dirty = true;
+    return FRMC_OK;
+}
+
+int frmc_propose_amputation(frmc_store *s, int32_t index, const frmc_amputation_desc *descs, int allow_fit, float *chi2_out)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_REQUIRE(!s->grids.empty(), FRMC_ESTATE, "no grid registered");
+    for (auto &g : s->grids) FRMC_REQUIRE(g.valid, FRMC_ESTATE, "call frmc_compute_data before removing atoms");
+    FRMC_REQUIRE(index >= 0 && index < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", index, (long long)s->n - 1);
+    FRMC_REQUIRE(s->n >= 2, FRMC_ELIMIT, "cannot remove the last atom");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    int rc = flush_pending(s);
+    if (rc) return rc;
+    if ((rc = sync_models(s))) return rc;
+    // the atom's row leaves the histograms: a proposal whose "moved" position pairs with nothing (NaN fails every
+    // range test), i.e. data - compute_before_move's activeAtomsDataBeforeMove (PairDistributionConstraints.py:1181-1184)
+    ProposalIn &h = s->prop_in;
+    h.k = 1;
+    h.pos[0] = pos_of(s, index);
+    h.moved[0] = h.moved[1] = h.moved[2] = __builtin_nanf("");
+    for (int c = 0; c < 3; ++c) { s->prop_lo[c] = s->lo[c]; s->prop_hi[c] = s->hi[c]; }
+    const int mode = current_mode(s, nullptr, nullptr);
+    ++s->seq_expected;
+    if ((rc = launch_delta(s, mode))) return rc;
+    const int nm = (int)s->models.size();
+    ModelSet ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = nm;
+    for (int i = 0; i < nm; ++i) {
+        ModelHost &mh = s->models[i];
+        ModelDev d = launch_model(s, mh);
+        if (!allow_fit) d.refit = 0;             // _set_adjust_scale_factor_frequency(0) around the evaluation (:1195-1197)
+        const frmc_amputation_desc *a = descs ? descs + i : nullptr;
+        if (a && (a->pair_w || a->pair_D)) {
+            FRMC_REQUIRE(a->pair_w && a->pair_D, FRMC_EINVAL, "model %d: pair_w and pair_D come together", i);
+            if (!mh.amp_w) {
+                void *p = nullptr;
+                FRMC_CUDA(cudaMalloc(&p, sizeof(float) * 3 * d.n_pairs)); mh.owned.push_back(p);
+                mh.amp_w = (float *)p; mh.amp_D = mh.amp_w + d.n_pairs; mh.amp_rD = mh.amp_D + d.n_pairs;
+            }
+            std::vector<float> nan((size_t)d.n_pairs, __builtin_nanf(""));     // IEEE division for this one evaluation
+            FRMC_CUDA(cudaMemcpyAsync(mh.amp_w, a->pair_w, sizeof(float) * d.n_pairs, cudaMemcpyHostToDevice, s->stream));
+            FRMC_CUDA(cudaMemcpyAsync(mh.amp_D, a->pair_D, sizeof(float) * d.n_pairs, cudaMemcpyHostToDevice, s->stream));
+            FRMC_CUDA(cudaMemcpyAsync(mh.amp_rD, nan.data(), sizeof(float) * d.n_pairs, cudaMemcpyHostToDevice, s->stream));
+            d.w = mh.amp_w; d.D = mh.amp_D; d.rD = mh.amp_rD;
+            if (d.n_pairs <= EPI_INLINE_PAIRS)
+                for (int p = 0; p < d.n_pairs; ++p) { d.i_w[p] = a->pair_w[p]; d.i_D[p] = a->pair_D[p]; d.i_rD[p] = nan[p]; }
+        }
+        if (a && a->prefactor) {
+            if (!mh.amp_pref) {
+                void *p = nullptr;
+                FRMC_CUDA(cudaMalloc(&p, sizeof(float) * d.hs)); mh.owned.push_back(p);
+                mh.amp_pref = (float *)p;
+            }
+            FRMC_CUDA(cudaMemcpyAsync(mh.amp_pref, a->prefactor, sizeof(float) * d.hs, cudaMemcpyHostToDevice, s->stream));
+            d.pref = mh.amp_pref;
+        }
+        ms.m[i] = d;
+    }
+    if (nm) {
+        if ((rc = launch_epilogue_ms(s, ms))) return rc;
+        if ((rc = wait_epilogue(s))) return rc;
+    } else {
+        FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    for (int i = 0; i < nm; ++i) {
+        s->chi2_staged[i] = s->h_chi2[i];
+        s->models[i].sf_staged = s->h_chi2[2 * FRMC_MAX_MODELS + i];
+        if (chi2_out) chi2_out[i] = s->h_chi2[i];
+    }
+    s->amp_rel = index;
+    s->state = 2;
+    return FRMC_OK;
+}
+
+int frmc_accept_amputation(frmc_store *s)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_REQUIRE(s->state == 2, FRMC_ESTATE, "no staged amputation to accept");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    s->pending = 1;
+    int rc = flush_pending(s);                 // counts += delta, totals, model totals
+    if (rc) return rc;
+    // the record becomes padding: NaN coordinates pair with nothing, PAD_META keeps it out of every sweep
+    const int pos = s->prop_in.pos[0];
+    const float nanv = __builtin_nanf("");
+    float rec[4] = {nanv, nanv, nanv, 0.f};
+    const uint32_t pad = PAD_META, none = 0xFFFFFFFFu;
+    memcpy(&rec[3], &pad, 4);
+    FRMC_CUDA(cudaMemcpyAsync(s->d_atoms + pos, rec, sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaMemcpyAsync(s->d_orig + pos, &none, sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->rel2real.empty()) {
+        s->rel2real.resize((size_t)s->n);
+        for (int64_t i = 0; i < s->n; ++i) s->rel2real[i] = (int32_t)i;
+    }
+    s->rel2real.erase(s->rel2real.begin() + s->amp_rel);
+    --s->n;
+    for (size_t i = 0; i < s->models.size(); ++i) {
+        s->chi2_committed[i] = s->chi2_staged[i];
+        s->models[i].dev.scale = s->models[i].sf_staged;      // accept_amputation: _set_fitted_scale_factor_value (:1227)
+    }
+    s->models_dirty = true;
+    ++s->accepted;                              // Engine.__on_runtime_step_try_remove counts it as accepted (Engine.py:3259)
+    s->amp_rel = -1;
+    s->state = 0;
+    return FRMC_OK;
+}
+
+int frmc_reject_amputation(frmc_store *s)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_REQUIRE(s->state == 2, FRMC_ESTATE, "no staged amputation to reject");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    s->pending = 2;
+    s->amp_rel = -1;
+    s->state = 0;
+    return flush_pending(s);
+}
+
+int frmc_import_data(frmc_store *s, int grid, const float *hintra, const float *hinter)
+{
+    FRMC_REQUIRE(s && hintra && hinter, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(grid >= 0 && grid < (int)s->grids.size(), FRMC_EINVAL, "unknown grid %d", grid);
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    GridDev &G = s->grids[grid].dev;
+    std::vector<long long> cnt((size_t)(2 * G.cells));
+    for (int part = 0; part < 2; ++part) {
+        const float *src = part ? hinter : hintra;
+        for (long long c = 0; c < G.cells; ++c) {
+            const float v = src[c];
+            const long long iv = (long long)v;
+            FRMC_REQUIRE(v == v && fabsf(v) < 9.0e18f && (float)iv == v, FRMC_EINVAL,
+                         "saved histogram cell %lld of %s is not an integer count (%g)", c, part ? "inter" : "intra", (double)v);
+            cnt[(size_t)part * G.cells + c] = iv;
+        }
+    }
+    FRMC_CUDA(cudaMemcpyAsync(G.counts, cnt.data(), sizeof(long long) * cnt.size(), cudaMemcpyHostToDevice, s->stream));
+    FRMC_CUDA(cudaMemsetAsync(G.delta, 0, sizeof(int) * 2 * G.cells, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    s->grids[grid].valid = true;
+    return FRMC_OK;
 }
 
 int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32_t *indexes, const float *moved,
@@ -3343,7 +3564,7 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
                 in.first[np] = na;
                 unsigned int share = 0u;
                 for (int t = first[j]; t < first[j + 1]; ++t) {
-                    const int pos = s->lay.inv[indexes[t]];
+                    const int pos = pos_of(s, indexes[t]);
                     for (int v = 0; v < na; ++v)
                         if (in.pos[v] == pos) {
                             int jp = 0;
@@ -3352,7 +3573,7 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
                         }
                 }
                 for (int t = first[j]; t < first[j + 1]; ++t, ++na) {
-                    in.pos[na] = s->lay.inv[indexes[t]];
+                    in.pos[na] = pos_of(s, indexes[t]);
                     in.moved[3 * na] = moved[3 * (size_t)t]; in.moved[3 * na + 1] = moved[3 * (size_t)t + 1]; in.moved[3 * na + 2] = moved[3 * (size_t)t + 2];
                 }
                 in.share[np] = share;

@@ -271,6 +271,60 @@ class DeviceStore(object):
     def reject(self):
         L.check(self._lib.frmc_reject(self._handle), "reject")
 
+    # ------------------------------------------------------------------ atom removal, persisted state
+    def _constants(self, spec):
+        pa, pb, pw, pD = spec.pair_table()
+        return pw, pD, spec.prefactor()
+
+    def propose_amputation(self, index, specs=None, allow_fit=False):
+        """compute_as_if_amputated for every model (include/fullrmc_b200.h: frmc_propose_amputation): chi^2 per model of
+        the system without atom `index`.  specs: one ModelSpec per model holding the constants of that system (weighting
+        scheme, numberOfAtomsPerElement and number density with the atom gone), or None to keep the models' own."""
+        descs, keep = None, []
+        if specs is not None:
+            if len(specs) != self.n_models:
+                raise ValueError("one ModelSpec per model")
+            descs = (L.AmputationDesc * self.n_models)()
+            for i, spec in enumerate(specs):
+                if spec is None:
+                    continue
+                pw, pD, pref = self._constants(spec)
+                keep += [pw, pD, pref]
+                descs[i].pair_w = L.ptr(pw, L.c_f32p); descs[i].pair_D = L.ptr(pD, L.c_f32p); descs[i].prefactor = L.ptr(pref, L.c_f32p)
+        L.check(self._lib.frmc_propose_amputation(self._handle, int(index), descs, int(bool(allow_fit)), L.ptr(self._chi2, L.c_f32p)),
+                "propose_amputation")
+        return self._chi2[:self.n_models].copy()
+
+    def accept_amputation(self, specs=None):
+        """accept_amputation + Engine._on_collector_collect_atom: the atom leaves the store; specs (one ModelSpec per model
+        or None) are the constants the models use from now on."""
+        L.check(self._lib.frmc_accept_amputation(self._handle), "accept_amputation")
+        self.numberOfAtoms = int(self._lib.frmc_store_n_atoms(self._handle))
+        if specs is not None:
+            for i, spec in enumerate(specs):
+                if spec is not None:
+                    self.set_model_constants(i, spec)
+
+    def reject_amputation(self):
+        L.check(self._lib.frmc_reject_amputation(self._handle), "reject_amputation")
+
+    def set_model_constants(self, model, spec):
+        """replace a model's weighting scheme / D_ij / 4 pi r rho0 by those of `spec`"""
+        pw, pD, pref = self._constants(spec)
+        L.check(self._lib.frmc_model_set_constants(self._handle, int(model), L.ptr(pw, L.c_f32p), L.ptr(pD, L.c_f32p),
+                                                   L.ptr(pref, L.c_f32p)), "set_model_constants")
+        self._models[model] = spec
+
+    def import_data(self, grid, hintra, hinter):
+        """Resume from saved data["intra"] / data["inter"] (float32 (nEl,nEl,hs)) instead of a full-histogram pass;
+        follow with finalize_data()."""
+        a = np.ascontiguousarray(hintra, dtype=_F32)
+        b = np.ascontiguousarray(hinter, dtype=_F32)
+        hs = self._grids[grid][3]
+        if a.shape != (self.numberOfElements, self.numberOfElements, hs) or b.shape != a.shape:
+            raise ValueError("saved histograms must be (nEl, nEl, histSize)")
+        L.check(self._lib.frmc_import_data(self._handle, int(grid), L.ptr(a, L.c_f32p), L.ptr(b, L.c_f32p)), "import_data")
+
     # ------------------------------------------------------------------ export
     def export_data(self, grid=0):
         """The reference's data["intra"], data["inter"]: float32 (nEl,nEl,hs) arrays."""

@@ -306,6 +306,44 @@ int frmc_reject(frmc_store *s);
 /* One host call per Metropolis step: resolve the staged proposal (previous = 1 accept, 0 reject;
  * ignored when nothing is staged) and evaluate the next one. */
 int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const float *moved, float *chi2_after);
+/* ---- dynamic N and persisted state -------------------------------------------------
+ * Atom removal (Engine.__on_runtime_step_try_remove, Engine.py:3231-3276; compute_as_if_amputated / accept_amputation /
+ * reject_amputation of the three constraints, PairDistributionConstraints.py:1168-1238,
+ * PairCorrelationConstraints.py:394-462, StructureFactorConstraints.py:1098-1166; Engine._on_collector_collect_atom,
+ * Engine.py:758-797) without rebuilding the store: the atom's row is subtracted from the running counts by one pass
+ * over the store, the constraint-level constants of the system with one atom fewer are swapped in for the evaluation,
+ * and on acceptance the record becomes padding.  Afterwards every `indexes` argument of this ABI is the engine's
+ * RELATIVE index (its arrays are np.delete'd: atoms behind the removed one move down by one); frmc_store_get_coords
+ * returns one row per remaining atom.
+ *
+ * frmc_amputation_desc: the constants one model uses while the atom is tried as removed, prepared by the host with the
+ * reference's numpy expressions: pair_w [n_pairs] = the weighting scheme for numberOfAtomsPerElement[el] - 1
+ * (:1190-1192), pair_D [n_pairs] = D_ij of those counts (:867-874), prefactor [histSize] = 4 pi r rho0 with
+ * rho0 = (N - 1) / volume (:1198).  NULL members keep the model's own. */
+typedef struct frmc_amputation_desc {
+    const float *pair_w;
+    const float *pair_D;
+    const float *prefactor;
+} frmc_amputation_desc;
+/* compute_as_if_amputated for every model at once: chi2_out [n_models] = amputationStandardError.  descs: one per
+ * model or NULL.  allow_fit = engine._RT_moveGenerator.allowFittingScaleFactor (0: no scale-factor refit in this
+ * evaluation whatever the schedule says, :1195-1197).  The amputation stays staged until accepted or rejected. */
+int frmc_propose_amputation(frmc_store *s, int32_t index, const frmc_amputation_desc *descs, int allow_fit, float *chi2_out);
+/* accept_amputation + _on_collector_collect_atom: data = data - row, standardError = amputationStandardError, the
+ * scale factor the evaluation used becomes the model's, the atom leaves the store (n drops by one).  The models keep
+ * their OWN constants: follow with frmc_model_set_constants for what the engine's new state implies. */
+int frmc_accept_amputation(frmc_store *s);
+int frmc_reject_amputation(frmc_store *s);
+/* replace a model's pair weights / D_ij / prefactor (NULL keeps one); the 3-op division is re-validated */
+int frmc_model_set_constants(frmc_store *s, int model, const float *pair_w, const float *pair_D, const float *prefactor);
+/* atoms the store holds now */
+int64_t frmc_store_n_atoms(frmc_store *s);
+/* Resume from persisted state (Constraint._dump_to_repository / the engine's runtime save, Core/Constraint.py:275-288,
+ * Engine.py:1188-1202, store data["intra"] / data["inter"]): the saved float32 arrays [nEl,nEl,histSize] become the
+ * grid's committed counts (every cell must hold an integer) instead of a full-histogram pass; follow with
+ * frmc_finalize_data for totals and chi^2.  The inverse of frmc_export_data. */
+int frmc_import_data(frmc_store *s, int grid, const float *hintra, const float *hinter);
+
 /* A RUN of n proposals tried in sequence with the engine's own acceptance rule, resolved on the device
  * (replaces n rounds of Engine.__on_runtime_step_try_move, Engine.py:3302-3338, for the histogram constraints):
  *   total_new = sum_m chi2_m / variance_sq[m]           (Engine.compute_total_standard_error, Engine.py:3024-3029)
