@@ -119,6 +119,12 @@ SIGNATURES = {
     "frmc_model_set_constants": (_I, [_VP, _I, c_f32p, c_f32p, c_f32p]),
     "frmc_store_n_atoms": (_I64, [_VP]),
     "frmc_import_data": (_I, [_VP, _I, c_f32p, c_f32p]),
+    "frmc_transform_coordinates": (_I, [_I, c_f32p, c_f32p, _I64, c_f32p]),
+    "frmc_store_set_real_coords": (_I, [_VP, c_f32p, c_f32p]),
+    "frmc_store_get_real_coords": (_I, [_VP, c_f32p]),
+    "frmc_store_set_groups": (_I, [_VP, _I, c_i32p, c_i32p]),
+    "frmc_run_generated": (_I, [_VP, _I, ctypes.c_uint64, ctypes.c_uint64, _F, _F, c_f32p, _F, c_f32p, c_f32p, c_i32p, c_i32p, c_f32p,
+                                ctypes.POINTER(ctypes.c_double)]),
     "frmc_run_batch": (_I, [_VP, _I, c_i32p, c_i32p, c_f32p, c_f32p, _F, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p,
                             ctypes.POINTER(ctypes.c_double)]),
     "frmc_store_batch_stats": (_I, [_VP, c_u64p, c_u64p, c_u64p]),

@@ -2,6 +2,7 @@
 // (Extensions/pairs_distances.pyx, pairs_histograms.pyx, reciprocal_space.pyx).
 // Host buffers in, host buffers out; the kernels run on the per-device context stream.
 #include "common.cuh"
+#include "rng.cuh"
 #include "layout.h"
 
 #include <cstring>
@@ -272,6 +273,21 @@ static int check_elements(const int32_t *el, int64_t n, int nEl)
 
 using namespace frmc;
 
+// Extensions/boundary_conditions_collection.pyx:88-110 transform_coordinates: out[i] = coords[i] . transMatrix, every
+// product and sum rounded to float32 in the reference's order (what Engine.py:3223 turns moved real coordinates into
+// box coordinates with)
+__global__ void transform_coordinates_kernel(const float *__restrict__ coords, int64_t n, const float *__restrict__ m, float *__restrict__ out)
+{
+    __shared__ float sm[9];
+    if (threadIdx.x < 9) sm[threadIdx.x] = m[threadIdx.x];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ox, oy, oz;
+    transform_point(sm, coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], ox, oy, oz);
+    out[3 * i] = ox; out[3 * i + 1] = oy; out[3 * i + 2] = oz;
+}
+
 extern "C" {
 
 int frmc_points_to_coords(int dev, const float *points, const int32_t *from_index, const int64_t *start, int64_t k,
@@ -336,6 +352,26 @@ int frmc_from_to_points_differences(int dev, const float *points_from, const flo
     unsigned grid = (unsigned)((n + 255) / 256);
     if (isPBC) from_to_kernel<true><<<grid, 256, 0, c->stream>>>(d_from, d_to, n, L, d_out);
     else from_to_kernel<false><<<grid, 256, 0, c->stream>>>(d_from, d_to, n, L, d_out);
+    FRMC_LAUNCH_CHECK();
+    FRMC_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    FRMC_CUDA(cudaStreamSynchronize(c->stream));
+    return FRMC_OK;
+}
+
+int frmc_transform_coordinates(int dev, const float *trans_matrix, const float *coords, int64_t n, float *out)
+{
+    FRMC_REQUIRE(n >= 0, FRMC_EINVAL, "negative size");
+    if (n == 0) return FRMC_OK;
+    FRMC_REQUIRE(trans_matrix && coords && out, FRMC_EINVAL, "NULL argument");
+    DeviceCtx *c = get_ctx(dev);
+    if (!c) return FRMC_ECUDA;
+    float *d_in = (float *)ctx_buffer(c, 0, sizeof(float) * 3 * n);
+    float *d_m = (float *)ctx_buffer(c, 1, sizeof(float) * 9);
+    float *d_out = (float *)ctx_buffer(c, 3, sizeof(float) * 3 * n);
+    if (!d_in || !d_m || !d_out) return FRMC_ENOMEM;
+    FRMC_CUDA(cudaMemcpyAsync(d_in, coords, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    FRMC_CUDA(cudaMemcpyAsync(d_m, trans_matrix, sizeof(float) * 9, cudaMemcpyHostToDevice, c->stream));
+    transform_coordinates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_in, n, d_m, d_out);
     FRMC_LAUNCH_CHECK();
     FRMC_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     FRMC_CUDA(cudaStreamSynchronize(c->stream));

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "layout.h"
 #include "store_view.h"
+#include "rng.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -1256,7 +1257,9 @@ struct BatchRun {                     // device memory, carried from launch to l
     int n_done;                       // proposals resolved (call-wide index)
     int n_accepted;
     int rounds;                       // evaluation rounds (statistics)
-    int pad[2];
+    int gen_state;                    // device-generated runs: 0 running, 1 every proposal of the call is resolved, 3 a generated
+                                      // coordinate left the window the geometry mode was chosen for (the host re-plans)
+    int pad;
     float cchi2[FRMC_MAX_MODELS];     // chi2 per model of the committed state
     float csf[FRMC_MAX_MODELS];
 };
@@ -1280,6 +1283,29 @@ struct BatchDev {                     // by value: the batch's device buffers
     float tol;
     float box_eps;                    // rounding margin of a sub-block box: 1e-6 (1 + largest |coordinate| of the store and the proposals)
     int n_groups;                     // G
+    int rand_per_proposal;            // 1: rand[i] belongs to proposal i of the call (counter-based contract, fullrmc_b200/rng.py);
+                                      // 0: consumed in order, one per worse proposal (the reference's generate_random_float stream)
+};
+
+// ---- device-generated runs: a launch's proposals are drawn on the device
+struct GenOut {                       // device memory: what the generator leaves for the commit besides the BatchIn
+    int ridx[FRMC_MAX_GROUP];         // real index of every moved atom
+    float mreal[3 * FRMC_MAX_GROUP];  // moved REAL coordinates (engine.realCoordinates of an accepted move, Engine.py:3337)
+};
+
+struct GenParams {                    // by value
+    unsigned long long seed, first_counter;
+    int n_total;                      // proposals of the call
+    int n_groups;
+    const int *goff, *gidx;           // groups: atoms gidx[goff[g] .. goff[g+1]) (real indexes)
+    const int *inv;                   // real index -> position in the sorted store
+    const float4 *real;               // real coordinates by real index (periodic systems)
+    float rb[9];                      // reciprocalBasisVectors (transform_coordinates' transMatrix)
+    int pbc;
+    float amp_min, amp_max;
+    float win_lo[3], win_hi[3];       // box coordinates must stay inside (the geometry mode and culling margin assume it)
+    float *rand_out;                  // call-wide: acceptance number of every proposal
+    int *group_out;                   // call-wide: selected group of every proposal (may be NULL)
 };
 
 struct BatchShared {
@@ -1290,6 +1316,7 @@ struct BatchShared {
     float4 fOld[FRMC_MAX_GROUP];               // low / high corner of the box spanned by a moved atom's old and new position
     float4 fNew[FRMC_MAX_GROUP];               // (blocks_far's conventions: periodically reduced coordinates, lo.w = rounding margin)
     float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
+    float s_prand[BATCH_MAX_PROPS];            // rand_per_proposal: the acceptance number of proposal j of this launch
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
     // the round's plan (rebuilt after every walk by thread 0): slot s evaluates proposal slot_k[s] on the committed
     // state plus the proposals of slot_A[s]; child = slot of the next proposal after a rejection [0] / an acceptance
@@ -1416,16 +1443,100 @@ __device__ __forceinline__ void zero_ints(int *p, long long n)
         q[i] = make_int4(0, 0, 0, 0);
 }
 
+// One launch's proposals drawn on the device (one warp; lane j = proposal n_done + j of the call): group from the
+// step's first word, translation vector, moved real coordinates = current real coordinates + vector, moved box
+// coordinates = transform_coordinates(reciprocal basis, moved real) -- Engine.__on_runtime_step_select_group,
+// Engine.py:3166-3228, for translation generators -- with the counter-based numbers of rng.cuh.  The current
+// coordinates are read AFTER every earlier launch has committed (stream order), and a proposal that moves an atom an
+// accepted proposal of its own launch moved ends that launch (batch_kernel), so it is generated again from the
+// new position: the run equals the sequential one.
+__global__ void generate_batch_kernel(const GenParams gp, BatchRun *__restrict__ run, BatchIn *__restrict__ din, GenOut *__restrict__ gen,
+                                      const float4 *__restrict__ atoms)
+{
+    __shared__ int s_k[BATCH_MAX_PROPS], s_first[BATCH_MAX_PROPS + 1], s_g[BATCH_MAX_PROPS];
+    __shared__ int s_pos[FRMC_MAX_GROUP];
+    __shared__ int s_np, s_bad;
+    const int j = threadIdx.x;
+    const int base = run->n_done;
+    if (j == 0) s_bad = 0;
+    if (base >= gp.n_total || run->gen_state == 3) {
+        if (j == 0) { din->n_prop = 0; din->n_atoms = 0; din->out_base = base; if (base >= gp.n_total) run->gen_state = 1; }
+        return;
+    }
+    const bool active = base + j < gp.n_total;
+    const StepRandom sr = step_random(gp.seed, gp.first_counter + (unsigned long long)(base + j), gp.amp_min, gp.amp_max);
+    const int g = (int)(((unsigned long long)sr.group_word * (unsigned long long)gp.n_groups) >> 32);
+    const int k = active ? gp.goff[g + 1] - gp.goff[g] : 0;
+    s_k[j] = k; s_g[j] = g;
+    __syncwarp();
+    if (j == 0) {
+        int na = 0, np = 0;
+        while (np < BATCH_MAX_PROPS && s_k[np] > 0 && na + s_k[np] <= FRMC_MAX_GROUP) { s_first[np] = na; na += s_k[np]; ++np; }
+        s_first[np] = na;
+        s_np = np;
+        din->n_prop = np; din->n_atoms = na; din->out_base = base;
+        for (int i = 0; i <= np; ++i) din->first[i] = s_first[i];
+    }
+    __syncwarp();
+    const int np = s_np;
+    if (j < np) {
+        bool bad = false;
+        for (int t = 0; t < k; ++t) {
+            const int r = gp.gidx[gp.goff[g] + t];
+            const int pos = gp.inv[r];
+            float x, y, z;
+            if (gp.pbc) { const float4 rc = gp.real[r]; x = rc.x; y = rc.y; z = rc.z; }
+            else { const float4 rc = atoms[pos]; x = rc.x; y = rc.y; z = rc.z; }      // non-periodic: box coordinates ARE the real ones
+            const float mx = __fadd_rn(x, sr.vx), my = __fadd_rn(y, sr.vy), mz = __fadd_rn(z, sr.vz);
+            float bx = mx, by = my, bz = mz;
+            if (gp.pbc) transform_point(gp.rb, mx, my, mz, bx, by, bz);
+            const int a = s_first[j] + t;
+            s_pos[a] = pos;
+            din->pos[a] = pos;
+            din->moved[3 * a] = bx; din->moved[3 * a + 1] = by; din->moved[3 * a + 2] = bz;
+            gen->ridx[a] = r;
+            gen->mreal[3 * a] = mx; gen->mreal[3 * a + 1] = my; gen->mreal[3 * a + 2] = mz;
+            bad = bad || !(bx >= gp.win_lo[0] && bx <= gp.win_hi[0] && by >= gp.win_lo[1] && by <= gp.win_hi[1] &&
+                           bz >= gp.win_lo[2] && bz <= gp.win_hi[2]);
+        }
+        if (bad) atomicExch(&s_bad, 1);
+        gp.rand_out[base + j] = sr.accept;
+        if (gp.group_out) gp.group_out[base + j] = g;
+    }
+    __syncwarp();
+    if (j < np) {
+        unsigned int share = 0u;                 // earlier proposals of the launch that move one of this proposal's atoms
+        for (int t = s_first[j]; t < s_first[j + 1]; ++t)
+            for (int v = 0; v < s_first[j]; ++v)
+                if (s_pos[v] == s_pos[t]) {
+                    int jp = 0;
+                    while (s_first[jp + 1] <= v) ++jp;
+                    share |= 1u << jp;
+                }
+        din->share[j] = share;
+    }
+    __syncwarp();
+    if (j == 0) {
+        if (s_bad) { din->n_prop = 0; din->n_atoms = 0; run->gen_state = 3; }
+        run->stopped = 0;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
-batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, GridSet gs, int nEl, const ModelSet ms, const EpiMap em,
-             const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars, unsigned long long *__restrict__ overflow,
-             long long *__restrict__ stamps)
+batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ BatchIn in_host, Lattice L, GridSet gs, int nEl, const ModelSet ms,
+             const EpiMap em, const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars,
+             unsigned long long *__restrict__ overflow, long long *__restrict__ stamps, const BatchIn *__restrict__ in_dev,
+             const GenOut *__restrict__ gen, float4 *__restrict__ real)
 {
     extern __shared__ __align__(128) float epi_smem[];
     __shared__ __align__(16) EpiShared es;
     __shared__ BatchShared bs;
     const int tid = threadIdx.x;
+    // the launch's proposals: handed over by the host in the kernel parameters, or drawn on the device by
+    // generate_batch_kernel (in_dev; gen / real then carry the real coordinates to commit)
+    const BatchIn &in = in_dev ? *in_dev : in_host;
+    if (in_dev && in.n_prop == 0) return;            // nothing generated: the call is finished or must be re-planned (uniform)
     // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST launch
 #define BATCH_STAMP(i) do { if (stamps && blockIdx.x == 0 && tid == 0 && (i) < BATCH_STAMP_SLOTS) { \
         unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[(i)] = (long long)gt_; } } while (0)
@@ -1470,7 +1581,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         while (j + 1 < np && in.first[j + 1] <= t) ++j;
         bs.sProp[t] = j;
     }
-    if (tid < BATCH_MAX_PROPS) { bs.near[tid] = 0u; bs.symmask[tid] = 0u; }
+    if (tid < BATCH_MAX_PROPS) {
+        bs.near[tid] = 0u; bs.symmask[tid] = 0u;
+        bs.s_prand[tid] = (bd.rand_per_proposal && tid < np) ? __ldcg(bd.rand + in.out_base + tid) : 0.0f;
+    }
     for (int mm = 0; mm < ms.n; ++mm)
         if ((bd.defer_mask >> mm) & 1u)
             for (int i = tid; i < 4 * ms.m[mm].pw_leaves; i += blockDim.x) bs.sched[mm][i] = ms.m[mm].pw_sched[i];
@@ -1660,7 +1774,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
         const unsigned int worse_m = __ballot_sync(FULL, worse);
         int dec = 1;
         if (worse) {                                                 // (lanes beyond the round's G nodes are never used)
-            const float u = bs.s_rand[min(ri_off + __popc(worse_m & below), 2 * BATCH_MAX_GROUPS - 1)];
+            const float u = bd.rand_per_proposal ? bs.s_prand[j] : bs.s_rand[min(ri_off + __popc(worse_m & below), 2 * BATCH_MAX_GROUPS - 1)];
             dec = (u > bd.tol) ? 0 : 1;
         }
         const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
@@ -1836,7 +1950,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
                 const bool worse = lane < P && nt > tl_s;
                 const unsigned int worse_m = __ballot_sync(FULL, worse);
                 int dec = 1;
-                if (worse) { const float u = bs.s_rand[__popc(worse_m & below)]; dec = (u > bd.tol) ? 0 : 2; }
+                if (worse) {
+                    const float u = bd.rand_per_proposal ? bs.s_prand[min(cur + lane, BATCH_MAX_PROPS - 1)] : bs.s_rand[__popc(worse_m & below)];
+                    dec = (u > bd.tol) ? 0 : 2;
+                }
                 const bool surprise = lane < P - 1 && ((dec != 0) != (((pexp >> lane) & 1u) != 0u));
                 const unsigned int sur = __ballot_sync(FULL, surprise);
                 const int s_end = sur ? __ffs(sur) - 1 : P - 1;            // last slot the walk resolves
@@ -1927,7 +2044,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn in, Lattice L, 
             }
             if (blockIdx.x == 0) {
                 for (int x = 0; x < n_aj; ++x)
-                    for (int t = in.first[acc_j[x]] + tid; t < in.first[acc_j[x] + 1]; t += blockDim.x) atoms[bs.sPos[t]] = bs.sNew[t];
+                    for (int t = in.first[acc_j[x]] + tid; t < in.first[acc_j[x] + 1]; t += blockDim.x) {
+                        atoms[bs.sPos[t]] = bs.sNew[t];
+                        if (gen && real) real[gen->ridx[t]] = make_float4(gen->mreal[3 * t], gen->mreal[3 * t + 1], gen->mreal[3 * t + 2], 0.f);
+                    }
                 if (tid < ms.n) {
                     bd.run->cchi2[tid] = bs.s_chi[last][tid];
                     bd.run->csf[tid] = ms.m[tid].scale;        // no refit schedule inside a batch
@@ -2092,6 +2212,19 @@ struct frmc_store {
     long long *d_bstamps = nullptr;  // debug timeline of the last batch launch (FRMC_BATCH_STAMPS=1)
     cudaEvent_t bev0 = nullptr, bev1 = nullptr;
     unsigned long long batch_launches = 0, batch_rounds = 0, batch_proposals = 0;
+    // device-generated runs (generate_batch_kernel)
+    float4 *d_real = nullptr;        // engine.realCoordinates by real index (periodic systems); valid while real_valid
+    bool real_valid = false;         // every move accepted since frmc_store_set_real_coords went through a generated run
+    float rbasis[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // engine.reciprocalBasisVectors
+    int *d_inv = nullptr;            // real index -> position in the sorted store
+    int *d_goff = nullptr, *d_gidx = nullptr;        // groups
+    int n_groups = 0;
+    BatchIn *d_bin = nullptr;        // the generated launch
+    GenOut *d_gen = nullptr;
+    int *d_gout = nullptr; size_t gout_cap = 0;      // selected group of every proposal of a call
+    bool force_general = false;      // a generated coordinate left the fast-wrap window once: general minimum image from then on
+    int gen_win_kind = 0;            // 0: no window yet, 1: fast-wrap window, 2: wide window (general minimum image / non-periodic)
+    float gen_win_lo[3] = {0, 0, 0}, gen_win_hi[3] = {0, 0, 0};
     unsigned long long accepted = 0;  // the engine's count of accepted moves (refit schedule, Core/Constraint.py:1418-1422)
     float chi2_committed[FRMC_MAX_MODELS];
     // optional per-kernel timing (CUDA events on the store's stream; bench.py's roofline leg)
@@ -2464,6 +2597,7 @@ static int current_mode(frmc_store *s, const float *extra_lo, const float *extra
         lo[c] = extra_lo ? std::min(s->lo[c], extra_lo[c]) : s->lo[c];
         hi[c] = extra_hi ? std::max(s->hi[c], extra_hi[c]) : s->hi[c];
     }
+    if (s->force_general) hi[0] = INFINITY;
     return choose_mode_from_bounds(s->L.b, s->isPBC, lo, hi);
 }
 
@@ -2757,7 +2891,7 @@ static int batch_prepare(frmc_store *s)
 }
 
 template <int MODE>
-static int launch_batch_t(frmc_store *s, const BatchIn &in)
+static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
 {
     GridSet gs = make_gridset(s);
     ModelSet ms;
@@ -2781,7 +2915,11 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in)
     gw.t2max = gs.t2hi;
     CullParams cp = make_cull(s->L, MODE, gw);
     if (g_no_cull) cp.enabled = 0;
-    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps};
+    const BatchIn *in_dev = generated ? s->d_bin : nullptr;
+    const GenOut *gen = generated ? s->d_gen : nullptr;
+    float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
+    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
+                    &in_dev, &gen, &real};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)batch_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
                                                 args, s->epi_smem, s->stream);
     if (e != cudaSuccess) {
@@ -2793,14 +2931,14 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in)
     return FRMC_OK;
 }
 
-static int launch_batch(frmc_store *s, int mode, const BatchIn &in)
+static int launch_batch(frmc_store *s, int mode, const BatchIn &in, bool generated = false)
 {
     switch (mode) {
-        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in);
-        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in);
-        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in);
-        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in);
-        default: return launch_batch_t<MODE_TRI_GEN>(s, in);
+        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in, generated);
+        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in, generated);
+        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in, generated);
+        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in, generated);
+        default: return launch_batch_t<MODE_TRI_GEN>(s, in, generated);
     }
 }
 
@@ -2888,6 +3026,7 @@ void frmc_store_destroy(frmc_store *s)
     cudaFree(s->d_cmd); cudaFree(s->d_pbars);
     for (void *p : s->batch_owned) cudaFree(p);
     cudaFree(s->d_bstamps);
+    cudaFree(s->d_real); cudaFree(s->d_inv); cudaFree(s->d_goff); cudaFree(s->d_gidx); cudaFree(s->d_bin); cudaFree(s->d_gen); cudaFree(s->d_gout);
     cudaFree(s->d_bbars); cudaFree(s->d_brand); cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec);
     if (s->h_brun) cudaFreeHost(s->h_brun);
     if (s->bev0) cudaEventDestroy(s->bev0);
@@ -2916,6 +3055,8 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
     }
     int rc = upload_layout(s, coords);
     if (rc) return rc;
+    cudaFree(s->d_inv); s->d_inv = nullptr;              // generated runs: new layout, new window, real coordinates again
+    s->real_valid = false; s->force_general = false; s->gen_win_kind = 0;
     s->items_shard = s->items_nshards = -1;
     for (auto &g : s->grids) g.valid = false;
     s->state = 0;
@@ -3254,6 +3395,7 @@ int frmc_accept(frmc_store *s)
     // the device-side commit is deferred: the next fused proposal resolves it in its first phase,
     // anything else that looks at the device state calls flush_pending() first
     s->pending = 1;
+    s->real_valid = false;
     for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], s->prop_lo[c]); s->hi[c] = std::max(s->hi[c], s->prop_hi[c]); }
     for (size_t i = 0; i < s->models.size(); ++i) {
         s->chi2_committed[i] = s->chi2_staged[i];
@@ -3543,6 +3685,8 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     bd.rand = s->d_brand; bd.out_chi2 = s->d_bout_chi2; bd.out_dec = s->d_bout_dec;
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.var2[i] = var2[i];
     bd.tol = tolerance;
+    bd.rand_per_proposal = 0;
+    s->real_valid = false;                      // accepted moves of this run bypass the real-coordinate array
     BatchRun run0;
     memset(&run0, 0, sizeof(run0));
     run0.total = *total_io;
@@ -3611,6 +3755,195 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     const BatchRun &r = *s->h_brun;
     *total_io = r.total;
     if (n_rand_used) *n_rand_used = r.n_rand;
+    if (r.n_accepted > 0) for (int m = 0; m < nm; ++m) { s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m]; }
+    s->accepted += (unsigned long long)r.n_accepted;
+    s->batch_rounds += (unsigned long long)r.rounds;
+    s->batch_proposals += (unsigned long long)n;
+    return FRMC_OK;
+}
+
+// ---- device-generated runs of moves ---------------------------------------------------
+int frmc_store_set_real_coords(frmc_store *s, const float *real, const float *rbasis)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_REQUIRE(s->rel2real.empty(), FRMC_ESTATE, "atoms were removed from this store: re-create it before generated runs");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    if (!s->d_inv) {
+        FRMC_CUDA(cudaMalloc(&s->d_inv, sizeof(int) * (size_t)s->n0));
+        FRMC_CUDA(cudaMemcpyAsync(s->d_inv, s->lay.inv.data(), sizeof(int) * (size_t)s->n0, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (s->isPBC) {
+        FRMC_REQUIRE(real && rbasis, FRMC_EINVAL, "a periodic store needs realCoordinates and reciprocalBasisVectors");
+        for (int i = 0; i < 9; ++i) s->rbasis[i] = rbasis[i];
+        std::vector<float> r4((size_t)s->n0 * 4, 0.f);
+        for (int64_t i = 0; i < s->n0; ++i) { r4[4 * i] = real[3 * i]; r4[4 * i + 1] = real[3 * i + 1]; r4[4 * i + 2] = real[3 * i + 2]; }
+        if (!s->d_real) FRMC_CUDA(cudaMalloc(&s->d_real, sizeof(float4) * (size_t)s->n0));
+        FRMC_CUDA(cudaMemcpyAsync(s->d_real, r4.data(), sizeof(float4) * (size_t)s->n0, cudaMemcpyHostToDevice, s->stream));
+    }
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    s->real_valid = true;
+    return FRMC_OK;
+}
+
+int frmc_store_get_real_coords(frmc_store *s, float *real_out)
+{
+    FRMC_REQUIRE(s && real_out, FRMC_EINVAL, "NULL argument");
+    if (!s->isPBC) return frmc_store_get_coords(s, real_out);       // engine.realCoordinates is engine.boxCoordinates (Engine.py:2253)
+    FRMC_REQUIRE(s->real_valid && s->d_real, FRMC_ESTATE, "no valid real coordinates (frmc_store_set_real_coords, then generated runs only)");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    std::vector<float> r4((size_t)s->n0 * 4);
+    FRMC_CUDA(cudaMemcpyAsync(r4.data(), s->d_real, sizeof(float4) * (size_t)s->n0, cudaMemcpyDeviceToHost, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < s->n0; ++i) { real_out[3 * i] = r4[4 * i]; real_out[3 * i + 1] = r4[4 * i + 1]; real_out[3 * i + 2] = r4[4 * i + 2]; }
+    return FRMC_OK;
+}
+
+int frmc_store_set_groups(frmc_store *s, int n_groups, const int32_t *offsets, const int32_t *indexes)
+{
+    FRMC_REQUIRE(s && offsets && indexes, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(n_groups >= 1, FRMC_EINVAL, "need at least one group");
+    FRMC_REQUIRE(offsets[0] == 0, FRMC_EINVAL, "offsets must start at 0");
+    for (int g = 0; g < n_groups; ++g) {
+        const int k = offsets[g + 1] - offsets[g];
+        FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group %d has %d atoms (1..%d)", g, k, FRMC_MAX_GROUP);
+        for (int t = offsets[g]; t < offsets[g + 1]; ++t)
+            FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n0, FRMC_EINVAL, "group %d: atom index %d outside 0..%lld", g, indexes[t], (long long)s->n0 - 1);
+    }
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    cudaFree(s->d_goff); cudaFree(s->d_gidx); s->d_goff = s->d_gidx = nullptr;
+    FRMC_CUDA(cudaMalloc(&s->d_goff, sizeof(int) * (size_t)(n_groups + 1)));
+    FRMC_CUDA(cudaMalloc(&s->d_gidx, sizeof(int) * (size_t)offsets[n_groups]));
+    FRMC_CUDA(cudaMemcpy(s->d_goff, offsets, sizeof(int) * (size_t)(n_groups + 1), cudaMemcpyHostToDevice));
+    FRMC_CUDA(cudaMemcpy(s->d_gidx, indexes, sizeof(int) * (size_t)offsets[n_groups], cudaMemcpyHostToDevice));
+    s->n_groups = n_groups;
+    return FRMC_OK;
+}
+
+int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_counter, float amp_min, float amp_max,
+                       const float *variance_sq, float tolerance, float *total_io, float *chi2_out, int32_t *decisions,
+                       int32_t *groups_out, float *rand_out, double *device_ms)
+{
+    FRMC_REQUIRE(s && total_io, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(n >= 1, FRMC_EINVAL, "need at least one proposal");
+    FRMC_REQUIRE(amp_min >= 0.f && amp_max > amp_min, FRMC_EINVAL, "bad amplitude range [%g, %g)", (double)amp_min, (double)amp_max);
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_REQUIRE(!s->grids.empty() && !s->models.empty(), FRMC_ESTATE, "a run of proposals needs at least one grid and one model");
+    for (auto &g : s->grids) FRMC_REQUIRE(g.valid, FRMC_ESTATE, "call frmc_compute_data before proposing moves");
+    FRMC_REQUIRE(s->n_groups > 0, FRMC_ESTATE, "no groups (frmc_store_set_groups)");
+    FRMC_REQUIRE(s->real_valid, FRMC_ESTATE, "no valid real coordinates (frmc_store_set_real_coords)");
+    FRMC_REQUIRE(s->rel2real.empty(), FRMC_ESTATE, "atoms were removed from this store: re-create it before generated runs");
+    const int nm = (int)s->models.size();
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    int rc = flush_pending(s);
+    if (rc) return rc;
+    if ((rc = sync_models(s))) return rc;
+    FRMC_REQUIRE(s->batch_ok && !s->timing, FRMC_ESTATE,
+                 "generated runs go through the batch kernel: resident S(Q) slabs, no scale-factor refit schedule, timing off");
+    if ((rc = batch_prepare(s))) return rc;
+    if (!s->d_bin) {
+        FRMC_CUDA(cudaMalloc(&s->d_bin, sizeof(BatchIn)));
+        FRMC_CUDA(cudaMalloc(&s->d_gen, sizeof(GenOut)));
+    }
+    if (s->brand_cap < (size_t)n + 2 * BATCH_MAX_GROUPS) {
+        cudaFree(s->d_brand); s->d_brand = nullptr; s->brand_cap = 0;
+        FRMC_CUDA(cudaMalloc(&s->d_brand, sizeof(float) * ((size_t)n + 2 * BATCH_MAX_GROUPS)));
+        s->brand_cap = (size_t)n + 2 * BATCH_MAX_GROUPS;
+    }
+    if (s->bout_cap < (size_t)n) {
+        cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec); s->d_bout_chi2 = nullptr; s->d_bout_dec = nullptr; s->bout_cap = 0;
+        FRMC_CUDA(cudaMalloc(&s->d_bout_chi2, sizeof(float) * (size_t)n * FRMC_MAX_MODELS));
+        FRMC_CUDA(cudaMalloc(&s->d_bout_dec, sizeof(int) * (size_t)n));
+        s->bout_cap = (size_t)n;
+    }
+    if (s->gout_cap < (size_t)n) {
+        cudaFree(s->d_gout); s->d_gout = nullptr; s->gout_cap = 0;
+        FRMC_CUDA(cudaMalloc(&s->d_gout, sizeof(int) * (size_t)n));
+        s->gout_cap = (size_t)n;
+    }
+    FRMC_CUDA(cudaMemsetAsync(s->d_brand, 0, sizeof(float) * ((size_t)n + 2 * BATCH_MAX_GROUPS), s->stream));
+    BatchDev &bd = s->bdev;
+    bd.rand = s->d_brand; bd.out_chi2 = s->d_bout_chi2; bd.out_dec = s->d_bout_dec;
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.var2[i] = (variance_sq && i < nm) ? variance_sq[i] : 1.0f;
+    bd.tol = tolerance;
+    bd.rand_per_proposal = 1;
+    BatchRun run0;
+    memset(&run0, 0, sizeof(run0));
+    run0.total = *total_io;
+    for (int m = 0; m < nm; ++m) { run0.cchi2[m] = s->chi2_committed[m]; run0.csf[m] = s->models[m].dev.scale; }
+    *s->h_brun = run0;
+    FRMC_CUDA(cudaMemcpyAsync(bd.run, s->h_brun, sizeof(BatchRun), cudaMemcpyHostToDevice, s->stream));
+    if (device_ms) FRMC_CUDA(cudaEventRecord(s->bev0, s->stream));
+    GenParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.seed = seed; gp.first_counter = first_counter; gp.n_total = n; gp.n_groups = s->n_groups;
+    gp.goff = s->d_goff; gp.gidx = s->d_gidx; gp.inv = s->d_inv; gp.real = s->d_real;
+    for (int i = 0; i < 9; ++i) gp.rb[i] = s->rbasis[i];
+    gp.pbc = s->isPBC; gp.amp_min = amp_min; gp.amp_max = amp_max;
+    gp.rand_out = s->d_brand; gp.group_out = s->d_gout;
+    BatchIn none;
+    memset(&none, 0, sizeof(none));
+    int done = 0, replans = 0;
+    while (done < n) {
+        // The window the generated box coordinates must stay in: the geometry mode (the fast minimum image needs every
+        // coordinate difference below 1.5) and the rounding margin of the culling boxes are chosen for it.  It is fixed
+        // once per layout (and once more if a coordinate ever leaves the fast window); the store's bounds become the
+        // window, since an accepted position may be anywhere inside.
+        if (s->gen_win_kind == 0 || (s->gen_win_kind == 1 && s->force_general)) {
+            float mid[3], half[3];
+            for (int c = 0; c < 3; ++c) { mid[c] = 0.5f * (s->lo[c] + s->hi[c]); half[c] = 0.5f * (s->hi[c] - s->lo[c]); }
+            const bool fast = s->isPBC && !s->force_general && half[0] <= 0.7449f && half[1] <= 0.7449f && half[2] <= 0.7449f;
+            for (int c = 0; c < 3; ++c) {
+                const float w = !s->isPBC ? half[c] + std::max(16.0f, 2.0f * half[c]) : (fast ? 0.7449f : std::max(8.0f, half[c] + 4.0f));
+                s->gen_win_lo[c] = mid[c] - w; s->gen_win_hi[c] = mid[c] + w;
+            }
+            s->gen_win_kind = fast ? 1 : 2;
+            if (s->isPBC && !fast) s->force_general = true;
+        }
+        const bool fast = s->gen_win_kind == 1;
+        for (int c = 0; c < 3; ++c) {
+            gp.win_lo[c] = s->gen_win_lo[c]; gp.win_hi[c] = s->gen_win_hi[c];
+            s->lo[c] = std::min(s->lo[c], gp.win_lo[c]); s->hi[c] = std::max(s->hi[c], gp.win_hi[c]);
+        }
+        const int mode = current_mode(s, nullptr, nullptr);
+        const int launches = std::min(64, (n - done + BATCH_MAX_PROPS - 1) / BATCH_MAX_PROPS + 1);
+        for (int l = 0; l < launches; ++l) {
+            generate_batch_kernel<<<1, 32, 0, s->stream>>>(gp, bd.run, s->d_bin, s->d_gen, s->d_atoms);
+            FRMC_LAUNCH_CHECK();
+            if ((rc = launch_batch(s, mode, none, true))) return rc;
+        }
+        FRMC_CUDA(cudaMemcpyAsync(s->h_brun, bd.run, sizeof(BatchRun), cudaMemcpyDeviceToHost, s->stream));
+        FRMC_CUDA(cudaStreamSynchronize(s->stream));
+        const BatchRun &r = *s->h_brun;
+        FRMC_REQUIRE(r.n_done >= done && r.n_done <= n, FRMC_ECUDA, "generated run went backwards (done %d -> %d of %d)", done, r.n_done, n);
+        if (r.gen_state == 3) {
+            // a generated coordinate left the window: general minimum image from now on (exact for any coordinate)
+            FRMC_REQUIRE(fast && ++replans <= 2, FRMC_ELIMIT,
+                         "generated coordinates drifted out of the store's coordinate window; re-wrap them (frmc_store_set_coords)");
+            s->force_general = true;
+            s->h_brun->gen_state = 0;
+            FRMC_CUDA(cudaMemcpyAsync(bd.run, s->h_brun, sizeof(BatchRun), cudaMemcpyHostToDevice, s->stream));
+        } else {
+            FRMC_REQUIRE(r.n_done > done, FRMC_ECUDA, "generated run made no progress (done %d of %d)", done, n);
+        }
+        done = r.n_done;
+    }
+    if (device_ms) {
+        FRMC_CUDA(cudaEventRecord(s->bev1, s->stream));
+        FRMC_CUDA(cudaEventSynchronize(s->bev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->bev0, s->bev1);
+        *device_ms = ms;
+    }
+    if (chi2_out) FRMC_CUDA(cudaMemcpyAsync(chi2_out, s->d_bout_chi2, sizeof(float) * (size_t)n * nm, cudaMemcpyDeviceToHost, s->stream));
+    if (decisions) FRMC_CUDA(cudaMemcpyAsync(decisions, s->d_bout_dec, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (groups_out) FRMC_CUDA(cudaMemcpyAsync(groups_out, s->d_gout, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (rand_out) FRMC_CUDA(cudaMemcpyAsync(rand_out, s->d_brand, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    const BatchRun &r = *s->h_brun;
+    *total_io = r.total;
     if (r.n_accepted > 0) for (int m = 0; m < nm; ++m) { s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m]; }
     s->accepted += (unsigned long long)r.n_accepted;
     s->batch_rounds += (unsigned long long)r.rounds;

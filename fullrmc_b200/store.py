@@ -271,6 +271,50 @@ class DeviceStore(object):
     def reject(self):
         L.check(self._lib.frmc_reject(self._handle), "reject")
 
+    # ------------------------------------------------------------------ device-generated runs of moves
+    def set_real_coords(self, realCoordinates=None, reciprocalBasisVectors=None):
+        """engine.realCoordinates and engine.reciprocalBasisVectors (both None for a non-periodic store)"""
+        if not self.isPBC:
+            L.check(self._lib.frmc_store_set_real_coords(self._handle, None, None), "set_real_coords")
+            return
+        real = L.as_array(realCoordinates, "realCoordinates", _F32, 2)
+        rb = L.as_array(reciprocalBasisVectors, "reciprocalBasisVectors", _F32, 2)
+        if real.shape != (self.numberOfAtoms, 3) or rb.shape != (3, 3):
+            raise ValueError("realCoordinates must be (N,3) and reciprocalBasisVectors (3,3)")
+        L.check(self._lib.frmc_store_set_real_coords(self._handle, L.ptr(real, L.c_f32p), L.ptr(rb, L.c_f32p)), "set_real_coords")
+
+    def get_real_coords(self):
+        out = np.empty((self.numberOfAtoms, 3), dtype=_F32)
+        L.check(self._lib.frmc_store_get_real_coords(self._handle, L.ptr(out, L.c_f32p)), "get_real_coords")
+        return out
+
+    def set_groups(self, groups):
+        """the engine's groups: a list of atom-index lists (engine.groups[g].indexes)"""
+        sizes = [len(g) for g in groups]
+        off = np.zeros(len(groups) + 1, dtype=_I32)
+        off[1:] = np.cumsum(sizes)
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=_I32).ravel() for g in groups]), dtype=_I32)
+        L.check(self._lib.frmc_store_set_groups(self._handle, len(groups), L.ptr(off, L.c_i32p), L.ptr(idx, L.c_i32p)), "set_groups")
+
+    def run_generated(self, n, seed, first_counter, amplitude, total, tolerance=0.0, variance_squared=None):
+        """n Metropolis steps generated, evaluated, decided and applied on the device (include/fullrmc_b200.h:
+        frmc_run_generated; the random-number contract is fullrmc_b200/rng.py).  amplitude: number or (min, max) like
+        TranslationGenerator.  Returns dict with chi2 (n, n_models), decisions (n,), groups (n,), rand (n,) the
+        acceptance numbers, total (float32), device_ms."""
+        amp = (0.0, float(amplitude)) if np.isscalar(amplitude) else (float(amplitude[0]), float(amplitude[1]))
+        var = None if variance_squared is None else np.ascontiguousarray(variance_squared, dtype=_F32).ravel()
+        chi2 = np.zeros((n, self.n_models), dtype=_F32)
+        dec = np.zeros(n, dtype=_I32)
+        grp = np.zeros(n, dtype=_I32)
+        rnd = np.zeros(n, dtype=_F32)
+        tot = ctypes.c_float(float(_F32(total)))
+        ms = ctypes.c_double(0.0)
+        L.check(self._lib.frmc_run_generated(self._handle, int(n), int(seed), int(first_counter), float(_F32(amp[0])), float(_F32(amp[1])),
+                                             L.ptr(var, L.c_f32p), float(_F32(tolerance)), ctypes.byref(tot), L.ptr(chi2, L.c_f32p),
+                                             L.ptr(dec, L.c_i32p), L.ptr(grp, L.c_i32p), L.ptr(rnd, L.c_f32p), ctypes.byref(ms)),
+                "run_generated")
+        return {"chi2": chi2, "decisions": dec, "groups": grp, "rand": rnd, "total": _F32(tot.value), "device_ms": float(ms.value)}
+
     # ------------------------------------------------------------------ atom removal, persisted state
     def _constants(self, spec):
         pa, pb, pw, pD = spec.pair_table()

@@ -98,6 +98,11 @@ int frmc_points_to_coords(int dev, const float *points, const int32_t *from_inde
 int frmc_from_to_points_differences(int dev, const float *points_from, const float *points_to, int64_t n,
                                     const float *basis, int isPBC, float *out);
 
+/* Extensions/boundary_conditions_collection.pyx:88-110 transform_coordinates: out [n,3] = coords [n,3] . transMatrix [3,3]
+ * (row vectors; every product and sum rounded to float32 in the reference's order).  Engine.py:3223 maps moved real
+ * coordinates to box coordinates with it (transMatrix = reciprocalBasisVectors). */
+int frmc_transform_coordinates(int dev, const float *trans_matrix, const float *coords, int64_t n, float *out);
+
 /* Extensions/pairs_histograms.pyx:150-217 multiple_pairs_histograms_coords.
  * hintra/hinter: [nEl,nEl,hs] fp32, overwritten (the reference returns fresh np.zeros arrays). */
 int frmc_multiple_pairs_histograms_coords(int dev, const int32_t *indexes, int64_t k, const float *coords,
@@ -361,6 +366,31 @@ int frmc_import_data(frmc_store *s, int grid, const float *hintra, const float *
 int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32_t *indexes, const float *moved,
                    const float *variance_sq, float tolerance, const float *rand, float *total_io,
                    float *chi2_out, int32_t *decisions, int32_t *n_rand_used, double *device_ms);
+/* ---- device-generated runs of moves (move generation, transform_coordinates and move
+ * application on the device, so that a run of steps needs no per-step host<->device traffic at all) --------------
+ * What Engine.run does per step for groups moved by a TranslationGenerator under a RandomSelector -- select a group
+ * (Engine.py:3168), translate its atoms' real coordinates by a random vector (Generators/Translations.py:171-187,
+ * Core/Collection.py:674-701), transform_coordinates to box coordinates (Engine.py:3222-3223), evaluate, decide
+ * (Engine.py:3302-3338), and on acceptance update realCoordinates and boxCoordinates (:3337-3338) -- for a whole RUN of
+ * steps on the device.  The random numbers are COUNTER BASED (fullrmc_b200/rng.py states the contract: Philox4x32-10,
+ * key = seed, counter = step number; group index, direction, amplitude and the acceptance number of step c are pure
+ * functions of (seed, c)): the reference's own Mersenne-Twister streams are consumed in an order that depends on every
+ * earlier decision, so they cannot be drawn ahead.  A reference Engine equipped with the selector / generator plug-ins
+ * of fullrmc_b200/engine_plugins.py draws the same numbers and walks the same trajectory, bit for bit
+ * (tests/test_generated_runs.py).
+ *   frmc_store_set_real_coords  engine.realCoordinates [n,3] and engine.reciprocalBasisVectors [3,3] (both NULL for a
+ *                               non-periodic store, whose box coordinates are the real ones)
+ *   frmc_store_set_groups       the engine's groups: atoms indexes[offsets[g] .. offsets[g+1]) of group g
+ *   frmc_run_generated          n steps numbered first_counter ..; amplitude range [amp_min, amp_max) as
+ *                               TranslationGenerator.amplitude; the other arguments as frmc_run_batch.  groups_out [n]
+ *                               and rand_out [n] (the acceptance numbers) may be NULL.
+ * Moves accepted through any other entry point invalidate the real coordinates (set them again). */
+int frmc_store_set_real_coords(frmc_store *s, const float *real, const float *rbasis);
+int frmc_store_get_real_coords(frmc_store *s, float *real_out);
+int frmc_store_set_groups(frmc_store *s, int n_groups, const int32_t *offsets, const int32_t *indexes);
+int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_counter, float amp_min, float amp_max,
+                       const float *variance_sq, float tolerance, float *total_io, float *chi2_out, int32_t *decisions,
+                       int32_t *groups_out, float *rand_out, double *device_ms);
 /* batch launches, evaluation rounds inside them and proposals they resolved so far */
 int frmc_store_batch_stats(frmc_store *s, uint64_t *launches, uint64_t *rounds, uint64_t *proposals);
 /* Debug (FRMC_BATCH_STAMPS=1 in the environment before the first run): globaltimer ns of CTA 0 at the phase
