@@ -247,6 +247,10 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
         batched = batched_leg(store, system, idx_all, disp, warm, n_evals, hbm_gbs, peak_src, lib)
     except Exception as err:                              # never lose the whole line to the newest path
         batched = {"error": "%s: %s" % (type(err).__name__, err)}
+    try:
+        generated = generated_leg(store, system, warm, n_evals, hbm_gbs, peak_src, lib)
+    except Exception as err:
+        generated = {"error": "%s: %s" % (type(err).__name__, err)}
     store.close()
     npad = ((np.bincount(system.elementIndex, minlength=system.numberOfElements) + 255) // 256 * 256).sum()
     evals_s = n_evals / wall
@@ -278,12 +282,14 @@ def per_move_leg(system, grid, q, n_evals, warm, label, hbm_gbs, peak_src, dev):
     }
     if not batched.get("identical_to_sequential_path"):
         single["batched"] = batched
+        single["generated"] = generated
         return single
     # headline = the run-of-proposals entry point (same metric, same rule, verified identical to the one-proposal-per-
     # launch path on this very sequence); the one-proposal numbers stay beside it
     out = {"metric": single["metric"], "workload": label}
     out.update(batched)
     out["single_proposal"] = {k: v for k, v in single.items() if k not in ("metric", "workload")}
+    out["generated"] = generated
     return out
 
 
@@ -360,6 +366,85 @@ def batched_leg(store, system, idx_all, disp, warm, n_evals, hbm_gbs, peak_src, 
                      "e2e_frac": evals_s * bytes_eval / 1e9 / hbm_gbs,
                      "note": "algorithmic bytes stay 16 B/atom per evaluated proposal (SURVEY 8d); the batch pass reads each record "
                              "once for up to 32 proposals, so the achieved figure counts reuse, not DRAM traffic"},
+    }
+
+
+def generated_leg(store, system, warm, n_evals, hbm_gbs, peak_src, lib):
+    """The same metric with NOTHING crossing the bus per step: DeviceStore.run_generated (frmc_run_generated) selects the
+    atom, draws the translation (counter-based contract of fullrmc_b200/rng.py), applies transform_coordinates, evaluates,
+    decides and moves the atom on the device.  Checked on this very run: the same steps regenerated on the host from the
+    contract (numpy) and driven one by one through DeviceStore.step with the rule on the host must give the same
+    decisions, chi2 and final coordinates."""
+    from fullrmc_b200 import rng as frng
+    F32 = np.float32
+    n = system.numberOfAtoms
+    basis64 = system.basis.astype(np.float64)
+    rb = np.linalg.inv(basis64).astype(F32)
+    seed, amp = 20261017, 0.17                         # mean displacement close to the N(0, 0.1 A)^3 proposals of the other legs
+
+    def restart():
+        store.set_coords(system.boxCoords, system.basis)
+        c = store.compute_data()
+        real = (system.boxCoords.astype(np.float64) @ basis64).astype(F32)
+        store.set_groups(None)
+        store.set_real_coords(real, rb)
+        return np.sum([F32(x) for x in c], dtype=F32), real
+
+    total0, real0 = restart()
+    w = store.run_generated(warm, seed, 0, amp, total0)
+    launches0 = int(lib.frmc_launch_count())
+    stats0 = store.batch_stats()
+    t0 = time.perf_counter()
+    out = store.run_generated(n_evals, seed, warm, amp, w["total"])
+    wall = time.perf_counter() - t0
+    launches = int(lib.frmc_launch_count()) - launches0
+    stats1 = store.batch_stats()
+    final_gen = (store.get_coords(), store.get_real_coords(), store.committed_chi2())
+    # the same steps from the numpy statement of the contract, one DeviceStore.step each, rule on the host
+    total0b, real = restart()
+    box = system.boxCoords.copy()
+    tot = total0b
+    off = np.arange(n + 1, dtype=np.int32); gi = np.arange(n, dtype=np.int32)
+    decs = np.zeros(warm + n_evals, np.int32)
+    chis = np.zeros((warm + n_evals, 2), F32)
+    prev = None
+    for it in range(warm + n_evals):
+        g_, idx, mreal, mbox, u = frng.generate_step(seed, it, off, gi, real, rb, 0.0, amp)
+        chi = store.step(prev, idx, mbox)
+        chis[it] = chi[:2]
+        nt = np.sum([F32(chi[0]), F32(chi[1])], dtype=F32)
+        prev = True
+        if nt > tot:
+            prev = not (float(u) > 0.0)
+        decs[it] = 1 if prev else 0
+        if prev:
+            tot = nt; real[idx] = mreal; box[idx] = mbox
+    (store.accept if prev else store.reject)()
+    same = bool(np.array_equal(np.concatenate([w["decisions"], out["decisions"]]) > 0, decs > 0) and
+                np.array_equal(np.concatenate([w["chi2"], out["chi2"]]), chis) and
+                np.array_equal(final_gen[0], store.get_coords()) and np.array_equal(final_gen[0], box) and
+                np.array_equal(final_gen[1], real) and np.array_equal(final_gen[2], store.committed_chi2()) and
+                F32(out["total"]) == F32(tot))
+    bytes_eval = 16.0 * n
+    dev_evals_s = n_evals / (out["device_ms"] * 1e-3)
+    evals_s = n_evals / wall
+    return {
+        "value": dev_evals_s, "unit": "evals/s",
+        "value_definition": "device time (CUDA events around all launches of one frmc_run_generated call) of %d steps generated, "
+                            "evaluated, decided and applied on the device" % n_evals,
+        "us_per_eval_device": 1e3 * out["device_ms"] / n_evals,
+        "e2e": {"value": evals_s, "unit": "evals/s", "us_per_eval": 1e6 * wall / n_evals,
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 + 4 + 4 + 4,
+                "api": "DeviceStore.run_generated (frmc_run_generated): seed and step counter in; chi2, decision, selected group "
+                       "and acceptance number of every step out; wall clock of the call"},
+        "evals": n_evals, "accepted": int((out["decisions"] > 0).sum()), "gpu_launches": launches,
+        "evaluation_rounds": stats1[1] - stats0[1],
+        "identical_to_sequential_path": same,
+        "rng_contract": "fullrmc_b200/rng.py (Philox4x32-10, key = seed, counter = step); reference-side plug-ins: fullrmc_b200/engine_plugins.py",
+        "roofline": {"bound": "hbm", "achieved": dev_evals_s * bytes_eval / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": dev_evals_s * bytes_eval / 1e9 / hbm_gbs, "traffic": None,
+                     "algorithmic_bytes_per_eval": bytes_eval, "peak_source": peak_src,
+                     "e2e_frac": evals_s * bytes_eval / 1e9 / hbm_gbs},
     }
 
 
@@ -608,6 +693,16 @@ def _fixture_constraints(g):
     return elements, n_per, descs
 
 
+def shape_budget(backend, cons):
+    """accepted moves that may still happen before a constraint refreshes its shape array (a run of proposals resolved on
+    the device must end there: Engine.run refreshes between steps, PairDistributionConstraints.py:362-374)"""
+    left = 1 << 30
+    for c in cons:
+        if c._shapeFuncParams is not None and c._shapeUpdateFreq:
+            left = min(left, c._shapeUpdateFreq - (backend.accepted % c._shapeUpdateFreq))
+    return left
+
+
 def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
     """RMC move evaluations/s on the shipped inputs of configs 1-3, as an Engine would drive them:
     (a) the five-method protocol of the device constraint mirrors (compute_before_move / compute_after_move /
@@ -706,7 +801,11 @@ def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
             while done < total:
                 if done >= warm and t0 is None:
                     t0 = time.perf_counter(); dev_ms = 0.0; acc_b = 0; timed_from = done
-                m = min(64, total - done)
+                # Engine.run: _runtime_on_step before every move (shape-function refresh every updateFreq accepted moves);
+                # a launch must end where the next refresh is due
+                if any([c.runtime_on_step() for c in cons if c._shapeFuncParams is not None]):
+                    tot = np.sum([F32(c.standardError) for c in cons], dtype=F32)
+                m = min(64, total - done, shape_budget(backend, cons))
                 ids = [groups[pick[j]] if groups is not None else np.array([pick[j]], np.int32) for j in range(done, done + m)]
                 # proposals of one launch must not depend on each other's outcome: keep distinct groups only
                 seen, keep = set(), []
@@ -724,6 +823,7 @@ def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
                 for j, a in enumerate(ids):
                     if res["decisions"][j] > 0:
                         boxb[a] = (boxb[a] + shifts[done + j]).astype(F32); acc_b += 1
+                backend.accepted += int((res["decisions"] > 0).sum())
                 done += m
             wall_b = time.perf_counter() - t0
             nb = total - timed_from
@@ -735,6 +835,43 @@ def example_leg(key, n_evals, warm, dev, no_cpu, ref_evals):
             backend.close()
         except Exception as err:
             out["run_batch"] = {"error": "%s: %s" % (type(err).__name__, err)}
+        # (d) steps generated on the device (frmc_run_generated): the engine's groups and real coordinates handed over
+        #     once, then nothing but the seed crosses the bus; TranslationGenerator amplitude 0.2 A (its default)
+        try:
+            backend, cons = build()
+            st = backend.store
+            st.set_groups(groups)
+            if pbc:
+                real0 = (box0.astype(np.float64) @ basis.astype(np.float64)).astype(F32)
+                st.set_real_coords(real0, np.linalg.inv(basis.astype(np.float64)).astype(F32))
+            else:
+                st.set_real_coords()
+            tot = np.sum([F32(c.standardError) for c in cons], dtype=F32)
+            done, acc_g, dev_ms, t0, timed_from = 0, 0, 0.0, None, 0
+            while done < total:
+                if done >= warm and t0 is None:
+                    t0 = time.perf_counter(); dev_ms = 0.0; acc_g = 0; timed_from = done
+                if any([c.runtime_on_step() for c in cons if c._shapeFuncParams is not None]):
+                    tot = np.sum([F32(c.standardError) for c in cons], dtype=F32)
+                    if pbc:
+                        raise RuntimeError("shape refresh of a periodic system is not wired into this leg")
+                    st.set_real_coords()
+                m = min(total - done, shape_budget(backend, cons), (warm - done) if done < warm else total)
+                res = st.run_generated(m, 4242, done, 0.2, tot)
+                tot = res["total"]; dev_ms += res["device_ms"]
+                na = int((res["decisions"] > 0).sum())
+                acc_g += na; backend.accepted += na
+                done += m
+            wall_g = time.perf_counter() - t0
+            ng = total - timed_from
+            out["run_generated"] = {"value": ng / (dev_ms * 1e-3) if dev_ms > 0 else None, "unit": "evals/s (device time)",
+                                    "e2e_evals_s": ng / wall_g, "us_per_eval_e2e": 1e6 * wall_g / ng, "evals": ng, "accepted": acc_g,
+                                    "h2d_bytes_per_step": 0, "batch_launches": st.batch_stats()[0],
+                                    "api": "DeviceStore.run_generated (frmc_run_generated): selection, translation (amplitude 0.2 A), "
+                                           "transform_coordinates, evaluation, decision and move application on the device"}
+            backend.close()
+        except Exception as err:
+            out["run_generated"] = {"error": "%s: %s" % (type(err).__name__, err)}
         # (c) the reference sequence on one host core
         if not no_cpu:
             out["cpu_baseline"] = example_cpu_baseline(g, elements, n_per, descs, groups, pick, shifts, min(ref_evals, total))
@@ -1146,6 +1283,11 @@ def run_b200(args):
             line["per_move%s_host_accept_evals_s" % suffix] = (single.get("e2e") or {}).get("value")
             line["per_move%s_host_accept_device_evals_s" % suffix] = single.get("value")
             line["per_move%s_host_accept_frac" % suffix] = (single.get("roofline") or {}).get("e2e_frac")
+            gen = leg.get("generated") or {}
+            line["per_move%s_generated_evals_s" % suffix] = gen.get("value")
+            line["per_move%s_generated_e2e_evals_s" % suffix] = (gen.get("e2e") or {}).get("value")
+            line["per_move%s_generated_roofline_frac" % suffix] = (gen.get("roofline") or {}).get("e2e_frac")
+            line["per_move%s_generated_parity_checked" % suffix] = bool(gen.get("identical_to_sequential_path"))
             line["per_move%s_parity_checked" % suffix] = bool(leg.get("reference_trajectory_replayed")) and \
                 bool(leg.get("identical_to_sequential_path", True))
             cb = leg.get("cpu_baseline") or {}
@@ -1164,6 +1306,7 @@ def run_b200(args):
             line[key] = leg
             line[key + "_evals_s"] = (leg.get("five_method_protocol") or {}).get("value")
             line[key + "_batch_evals_s"] = (leg.get("run_batch") or {}).get("e2e_evals_s")
+            line[key + "_generated_evals_s"] = (leg.get("run_generated") or {}).get("e2e_evals_s")
             line[key + "_reference_evals_s"] = (leg.get("cpu_baseline") or {}).get("value")
         dleg = distance_leg(s4, args.no_cpu)
         cleg = coordination_leg(s4, args.no_cpu)

@@ -573,6 +573,8 @@ struct EpiOut {
     float *terms;            // S(Q) models: [n_out] weighted squared residuals; when set the slab CTAs stop there and
                              // every CTA forms chi2 itself after the grid barrier (no ticket, no last-CTA stage)
     int warm;                // this CTA has run this (model, slab) before in this launch: tables and schedule are staged
+    int refit;               // this evaluation refits the scale factor (the engine's accepted count AT THIS NODE % frequency == 0)
+    float scale;             // the model's committed scale factor at this node (acceptances inside the launch may have changed it)
 };
 
 // part 2: r-space function, chi^2 / S(Q) slice, ticket, publish (steps 1-4 above)
@@ -584,6 +586,8 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
 {
     const ModelDev &M = ms.m[m];
     float *const total = BATCH ? eo.total : M.total;
+    const int mrefit = BATCH ? eo.refit : M.refit;           // per launch on the one-proposal paths, per node in a batch
+    const float mscale = BATCH ? eo.scale : M.scale;
     const bool is_sq = (M.kind == FRMC_KIND_SQ || M.kind == FRMC_KIND_RSQ);
     const int hs = M.hs, nq = M.n_out;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -628,7 +632,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     {
         const int *__restrict__ stot = BATCH ? eo.base : gs.grid[M.grid].stot;
         constexpr int EPI_BINS = 2, PB = 16;
-        const bool defer = !is_sq && (M.refit || M.prior || M.window);   // scale, prior, window applied in stage 1b
+        const bool defer = !is_sq && (mrefit || M.prior || M.window);   // scale, prior, window applied in stage 1b
         // bin r from the sum over the pair terms (acc): /shellVolumes, prefactor, shape, scale
         auto finish_bin = [&](int r, float accv, float svr, float prf, float shp) {
             float a = __fdiv_rn(accv, svr);
@@ -636,16 +640,16 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
             if (M.kind == FRMC_KIND_PCF) {
                 out = a;
                 if (M.shape) out = __fsub_rn(out, shp);
-                if (!defer && M.scale != 1.0f) {
+                if (!defer && mscale != 1.0f) {
                     float Gr = __fmul_rn(prf, __fsub_rn(out, 1.0f));
-                    Gr = __fmul_rn(Gr, M.scale);
+                    Gr = __fmul_rn(Gr, mscale);
                     out = __fadd_rn(1.0f, __fdiv_rn(Gr, prf));
                 }
             } else {
                 out = __fmul_rn(prf, __fsub_rn(a, 1.0f));
                 if (M.kind == FRMC_KIND_PDF) {
                     if (M.shape) out = __fsub_rn(out, shp);
-                    if (!defer && M.scale != 1.0f) out = __fmul_rn(out, M.scale);
+                    if (!defer && mscale != 1.0f) out = __fmul_rn(out, mscale);
                 }
             }
             sG[r] = out;
@@ -754,14 +758,14 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     EPI_STAMP(2);
 
     float chi2 = 0.f;
-    if (tid == 0) es.s_sf = M.scale;
+    if (tid == 0) es.s_sf = mscale;
     if (!is_sq) {
-        if (M.refit || M.prior || M.window) {
+        if (mrefit || M.prior || M.window) {
             // ---- 1b. scale-factor refit on the unscaled function (PairDistributionConstraints.py:886-888;
             //          PairCorrelationConstraints.py:171-184 fits on G(r) = 4 pi r rho0 (g - 1)), then scale,
             //          multiframe prior (:890) and window convolution (:892-893)
-            float sf = M.scale;
-            if (M.refit) {
+            float sf = mscale;
+            if (mrefit) {
                 if (M.kind == FRMC_KIND_PCF)
                     fit_scale_factor(es, sT, M, hs, [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(sG[i], 1.0f)); },
                                      [&](int i) { return __fmul_rn(M.pref[i], __fsub_rn(M.expv[i], 1.0f)); });
@@ -869,9 +873,9 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 float sv = acc;
                 if (M.kind == FRMC_KIND_SQ) {
                     sv = __fadd_rn(sv, 1.0f);
-                    if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fadd_rn(__fmul_rn(M.scale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
+                    if (!(mrefit || M.prior || M.window) && mscale != 1.0f) sv = __fadd_rn(__fmul_rn(mscale, __fsub_rn(sv, 1.0f)), 1.0f);   // scale*(Sq-1)+1 (:775-778)
                 } else {
-                    if (!(M.refit || M.prior || M.window) && M.scale != 1.0f) sv = __fmul_rn(M.scale, sv);                            // (:1258-1260)
+                    if (!(mrefit || M.prior || M.window) && mscale != 1.0f) sv = __fmul_rn(mscale, sv);                            // (:1258-1260)
                 }
                 total[q0 + lane] = sv;
                 if (with_terms) {
@@ -896,11 +900,11 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         EPI_STAMP(4);
         if (!s_last) return;
         __threadfence();
-        if (M.refit || M.prior || M.window) {
+        if (mrefit || M.prior || M.window) {
             // ---- 3b. refit on S(Q)-1 against experimental-1 (StructureFactorConstraints.py:824-834, inherited by
             //          the reduced constraint), then scale the slices the other CTAs left unscaled, prior, window
-            float sf = M.scale;
-            if (M.refit) {
+            float sf = mscale;
+            if (mrefit) {
                 fit_scale_factor(es, sT, M, nq, [&](int i) { return __fsub_rn(__ldcg(total + i), 1.0f); },
                                  [&](int i) { return __fsub_rn(M.expv[i], 1.0f); });
                 sf = es.s_sf;
@@ -1283,6 +1287,8 @@ struct BatchDev {                     // by value: the batch's device buffers
     float tol;
     float box_eps;                    // rounding margin of a sub-block box: 1e-6 (1 + largest |coordinate| of the store and the proposals)
     int n_groups;                     // G
+    int freq[FRMC_MAX_MODELS];        // scale-factor refit schedule per model (0: none): an evaluation refits when the engine's
+    unsigned long long accepted_base; // accepted count at its node (accepted_base + acceptances of this call so far) % freq == 0
     int rand_per_proposal;            // 1: rand[i] belongs to proposal i of the call (counter-based contract, fullrmc_b200/rng.py);
                                       // 0: consumed in order, one per worse proposal (the reference's generate_random_float stream)
 };
@@ -1316,6 +1322,7 @@ struct BatchShared {
     float4 fOld[FRMC_MAX_GROUP];               // low / high corner of the box spanned by a moved atom's old and new position
     float4 fNew[FRMC_MAX_GROUP];               // (blocks_far's conventions: periodically reduced coordinates, lo.w = rounding margin)
     float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
+    float s_csf[FRMC_MAX_MODELS];              // committed scale factor per model as the launch proceeds (refit schedules)
     float s_prand[BATCH_MAX_PROPS];            // rand_per_proposal: the acceptance number of proposal j of this launch
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
     // the round's plan (rebuilt after every walk by thread 0): slot s evaluates proposal slot_k[s] on the committed
@@ -1584,6 +1591,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     if (tid < BATCH_MAX_PROPS) {
         bs.near[tid] = 0u; bs.symmask[tid] = 0u;
         bs.s_prand[tid] = (bd.rand_per_proposal && tid < np) ? __ldcg(bd.rand + in.out_base + tid) : 0.0f;
+        if (tid < FRMC_MAX_MODELS) bs.s_csf[tid] = (tid < ms.n) ? __ldcg(&bd.run->csf[tid]) : 1.0f;
     }
     for (int mm = 0; mm < ms.n; ++mm)
         if ((bd.defer_mask >> mm) & 1u)
@@ -1759,8 +1767,23 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     //      state: they are the next rounds' predictions, and while nothing is assumed yet they extend the chain
     //      (the "all rejected so far" chain of a run without predictions).
     // Built by warp 0, lane j = proposal j (a launch has at most 32): everything is a vote or a prefix count.
+    // Refit schedules: an evaluation made at accepted count n refits when n % frequency == 0, and an accepted refit
+    // changes the model's scale factor for everything behind it.  A node may therefore only assume acceptances whose
+    // own evaluations do not refit: counts base .. base + |A| - 1 must not hit a multiple of any frequency.
+    auto spec_limit = [&](unsigned int accm) {
+        int lim = BATCH_MAX_SPEC;
+        const unsigned long long base = bd.accepted_base + (unsigned long long)acc_before + (unsigned long long)__popc(accm);
+        for (int mm = 0; mm < ms.n; ++mm)
+            if (bd.freq[mm] > 0) {
+                const int f = bd.freq[mm];
+                const int t = (int)((f - (int)(base % (unsigned long long)f)) % f);
+                lim = min(lim, t);
+            }
+        return lim;
+    };
     auto build_plan = [&](int c, unsigned int accm, int ri_off) {
         const unsigned int FULL = 0xFFFFFFFFu;
+        const int max_spec = spec_limit(accm);
         const int j = lane;
         const unsigned int below = (1u << j) - 1u, from_c = ~((1u << c) - 1u);
         const unsigned int he = bs.has_est;
@@ -1780,7 +1803,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
         const unsigned int A_j = acc_pred & below & from_c;         // predicted acceptances in front of j
         const unsigned int sh_j = in_rng ? in.share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;
-        const bool fits = !((sh_j & (accm | A_j)) || (nr_j & A_j)) && __popc(A_j) <= BATCH_MAX_SPEC;
+        const bool fits = !((sh_j & (accm | A_j)) || (nr_j & A_j)) && __popc(A_j) <= max_spec;
         const unsigned int bad = __ballot_sync(FULL, lead && !fits);
         int chain_end = bad ? __ffs(bad) - 1 : f;
         if (chain_end - c > G) chain_end = c + G;
@@ -1798,7 +1821,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const unsigned int A_f = acc_pred & from_c & ((f < 32) ? ((1u << f) - 1u) : FULL);
         const unsigned int sh_f = __shfl_sync(FULL, sh_j, f & 31), nr_f = __shfl_sync(FULL, nr_j, f & 31);
         const bool open = (chain_end == f) && (f < np) && (L < G) &&
-                          !((sh_f & (accm | A_f)) || (nr_f & A_f)) && __popc(A_f) <= BATCH_MAX_SPEC;
+                          !((sh_f & (accm | A_f)) || (nr_f & A_f)) && __popc(A_f) <= max_spec;
         const int dec_last = __shfl_sync(FULL, dec, (f - 1) & 31);   // predicted decision of the chain's last proposal
         int est_from = chain_end;
         if (open) {
@@ -1875,6 +1898,12 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
             eo.terms = ((bd.defer_mask >> m) & 1u) ? bd.bterm[m] + (long long)sb * ms.m[m].n_out : nullptr;
             eo.warm = warm ? 1 : 0;
+            {
+                const unsigned long long cnt = bd.accepted_base + (unsigned long long)acc_before + (unsigned long long)__popc(acc_mask) +
+                                               (unsigned long long)__popc(bs.slot_A[group]);
+                eo.refit = (bd.freq[m] > 0 && cnt % (unsigned long long)bd.freq[m] == 0ull) ? 1 : 0;
+                eo.scale = bs.s_csf[m];
+            }
             long long *est = (stamps && blockIdx.x == 1 && rounds <= 64) ? stamps + BATCH_STAMP_SLOTS + (rounds - 1) * 128 : nullptr;
             if (est && tid == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); est[120] = (long long)gt_; est[121] = (long long)t_round; }
             epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + sb * FRMC_MAX_MODELS, est, eo);
@@ -1994,6 +2023,8 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const unsigned int Aset = bs.s_acc;
         const int last = bs.s_last;
         cur = bs.s_cur; ri = bs.s_ri; stopped = bs.s_stopped != 0; total = bs.s_total;
+        if (Aset && tid < ms.n && bd.freq[tid] > 0)     // accept_move keeps the scale factor the accepted evaluation used
+            bs.s_csf[tid] = __ldcg(bd.res + (par * BATCH_MAX_GROUPS + last) * 2 * FRMC_MAX_MODELS + FRMC_MAX_MODELS + tid);
         __syncthreads();
         BATCH_STAMP(4 + 5 * (rounds - 1) + 2);           // decisions made
         if (Aset) {
@@ -2050,7 +2081,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                     }
                 if (tid < ms.n) {
                     bd.run->cchi2[tid] = bs.s_chi[last][tid];
-                    bd.run->csf[tid] = ms.m[tid].scale;        // no refit schedule inside a batch
+                    bd.run->csf[tid] = bs.s_csf[tid];
                 }
             }
             // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
@@ -2423,7 +2454,6 @@ static int sync_models(frmc_store *s)
     for (auto &m : s->models) {
         const bool is_sq = (m.dev.kind == FRMC_KIND_SQ || m.dev.kind == FRMC_KIND_RSQ);
         if (is_sq && (m.dev.hs + SQ_ROWS - 1) / SQ_ROWS > m.dev.n_stages) s->batch_ok = false;
-        if (m.adjust_freq > 0) s->batch_ok = false;
     }
     if (s->batch_ok) {
         // S(Q) models without prior/window leave chi2 terms and every CTA sums them after the grid barrier
@@ -2432,6 +2462,7 @@ static int sync_models(frmc_store *s)
             const ModelDev &d = s->models[mi].dev;
             const bool is_sq = (d.kind == FRMC_KIND_SQ || d.kind == FRMC_KIND_RSQ);
             if (!is_sq || d.prior || d.window || d.pw_leaves > BATCH_DEFER_MAX_LEAVES || getenv("FRMC_BATCH_NO_DEFER")) continue;
+            if (s->models[mi].adjust_freq > 0) continue;          // the refit is the last slab CTA's job (ticket path)
             s->batch_defer_mask |= 1u << mi;
         }
         int per_sm = 0;
@@ -3247,6 +3278,7 @@ int frmc_model_set_adjust(frmc_store *s, int model, int frequency, float sf_min,
 {
     FRMC_REQUIRE(s && model >= 0 && model < (int)s->models.size(), FRMC_EINVAL, "unknown model %d", model);
     FRMC_REQUIRE(frequency >= 0, FRMC_EINVAL, "negative frequency");
+    if ((s->models[model].adjust_freq > 0) != (frequency > 0)) s->models_dirty = true;   // which kernels take the model depends on it
     s->models[model].adjust_freq = frequency;
     s->models[model].dev.sf_min = sf_min;
     s->models[model].dev.sf_max = sf_max;
@@ -3686,6 +3718,8 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.var2[i] = var2[i];
     bd.tol = tolerance;
     bd.rand_per_proposal = 0;
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.freq[i] = (i < nm) ? s->models[i].adjust_freq : 0;
+    bd.accepted_base = s->accepted;
     s->real_valid = false;                      // accepted moves of this run bypass the real-coordinate array
     BatchRun run0;
     memset(&run0, 0, sizeof(run0));
@@ -3755,7 +3789,11 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     const BatchRun &r = *s->h_brun;
     *total_io = r.total;
     if (n_rand_used) *n_rand_used = r.n_rand;
-    if (r.n_accepted > 0) for (int m = 0; m < nm; ++m) { s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m]; }
+    if (r.n_accepted > 0)
+        for (int m = 0; m < nm; ++m) {
+            s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m];
+            if (s->models[m].adjust_freq > 0) { s->models[m].dev.scale = r.csf[m]; s->models[m].sf_staged = r.csf[m]; }
+        }
     s->accepted += (unsigned long long)r.n_accepted;
     s->batch_rounds += (unsigned long long)r.rounds;
     s->batch_proposals += (unsigned long long)n;
@@ -3869,6 +3907,8 @@ int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_count
     for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.var2[i] = (variance_sq && i < nm) ? variance_sq[i] : 1.0f;
     bd.tol = tolerance;
     bd.rand_per_proposal = 1;
+    for (int i = 0; i < FRMC_MAX_MODELS; ++i) bd.freq[i] = (i < nm) ? s->models[i].adjust_freq : 0;
+    bd.accepted_base = s->accepted;
     BatchRun run0;
     memset(&run0, 0, sizeof(run0));
     run0.total = *total_io;
@@ -3944,7 +3984,11 @@ int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_count
     FRMC_CUDA(cudaStreamSynchronize(s->stream));
     const BatchRun &r = *s->h_brun;
     *total_io = r.total;
-    if (r.n_accepted > 0) for (int m = 0; m < nm; ++m) { s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m]; }
+    if (r.n_accepted > 0)
+        for (int m = 0; m < nm; ++m) {
+            s->chi2_committed[m] = r.cchi2[m]; s->chi2_staged[m] = r.cchi2[m];
+            if (s->models[m].adjust_freq > 0) { s->models[m].dev.scale = r.csf[m]; s->models[m].sf_staged = r.csf[m]; }
+        }
     s->accepted += (unsigned long long)r.n_accepted;
     s->batch_rounds += (unsigned long long)r.rounds;
     s->batch_proposals += (unsigned long long)n;

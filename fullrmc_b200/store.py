@@ -288,13 +288,20 @@ class DeviceStore(object):
         L.check(self._lib.frmc_store_get_real_coords(self._handle, L.ptr(out, L.c_f32p)), "get_real_coords")
         return out
 
-    def set_groups(self, groups):
-        """the engine's groups: a list of atom-index lists (engine.groups[g].indexes)"""
-        sizes = [len(g) for g in groups]
-        off = np.zeros(len(groups) + 1, dtype=_I32)
-        off[1:] = np.cumsum(sizes)
-        idx = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=_I32).ravel() for g in groups]), dtype=_I32)
-        L.check(self._lib.frmc_store_set_groups(self._handle, len(groups), L.ptr(off, L.c_i32p), L.ptr(idx, L.c_i32p)), "set_groups")
+    def set_groups(self, groups=None, offsets=None, indexes=None):
+        """the engine's groups: a list of atom-index lists (engine.groups[g].indexes), None for one group per atom
+        (Engine.set_groups(None)), or the flat form offsets (G+1,) / indexes"""
+        if offsets is not None:
+            off = np.ascontiguousarray(offsets, dtype=_I32)
+            idx = np.ascontiguousarray(indexes, dtype=_I32)
+        elif groups is None:
+            off = np.arange(self.numberOfAtoms + 1, dtype=_I32)
+            idx = np.arange(self.numberOfAtoms, dtype=_I32)
+        else:
+            off = np.zeros(len(groups) + 1, dtype=_I32)
+            off[1:] = np.cumsum([len(g) for g in groups])
+            idx = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=_I32).ravel() for g in groups]), dtype=_I32)
+        L.check(self._lib.frmc_store_set_groups(self._handle, off.shape[0] - 1, L.ptr(off, L.c_i32p), L.ptr(idx, L.c_i32p)), "set_groups")
 
     def run_generated(self, n, seed, first_counter, amplitude, total, tolerance=0.0, variance_squared=None):
         """n Metropolis steps generated, evaluated, decided and applied on the device (include/fullrmc_b200.h:

@@ -55,6 +55,7 @@ def run_case(name, fullrmc, G, E_maker, arrays, build, groups, n_steps, seed, fi
     for ci, (c, kind) in enumerate(constraints):
         out["c%d/final_stdErr" % ci] = np.float32(c.standardError)
         out["c%d/final_intra" % ci], out["c%d/final_inter" % ci] = c.data["intra"].copy(), c.data["inter"].copy()
+        out["c%d/final_scaleFactor" % ci] = np.float32(c.scaleFactor)
     path = os.path.join(out_dir, "generated_%s.npz" % name)
     np.savez_compressed(path, **out)
     print("%-8s %d steps: tried %d accepted %d  total standard error %.6f  [%d KiB]" % (
@@ -84,6 +85,14 @@ def main():
         rsf = ReducedStructureFactorConstraint(experimentalData=Sq, weighting="atomicNumber")
         return [(pdf, "PDF"), (rsf, "RSQ")]
     run_case("niti", fullrmc, G, R.make_engine, arrays, niti, None, 400, 0x1234ABCD5678EF01, 1000, 0.3, out_dir)
+
+    # the same as shipped (Examples/atomicNiTi/run.py:102-103): both constraints refit their scale factor every 10 accepted moves
+    def niti_sf(E):
+        cons = niti(E)
+        for c, _ in cons:
+            c.set_adjust_scale_factor((10, 0.8, 1.2))
+        return cons
+    run_case("niti_sf", fullrmc, G, R.make_engine, arrays, niti_sf, None, 400, 2024, 0, 0.3, out_dir)
 
     # periodic, molecule groups (k = 13): Examples/molecularTHF, g(r) with data weights
     d2 = os.path.join(EX, "molecularTHF")

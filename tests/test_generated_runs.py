@@ -20,7 +20,7 @@ from fullrmc_b200 import rng
 from test_golden_constraints import _Golden, _constraint_desc, _oracle_total, _system
 
 F32 = np.float32
-NAMES = ["niti", "thf", "siox", "synth"]
+NAMES = ["niti", "niti_sf", "thf", "siox", "synth"]
 
 
 def _load(golden_dir, name):
@@ -137,7 +137,8 @@ def _device_store(g):
         cons.append((d, make_device_constraint(backend, d["kind"], d["experimental"], d["minDistance"], d["maxDistance"], d["bin"],
                                                int(d["histSize"]), d["shellCenters"], d["shellVolumes"], d["weighting"],
                                                dataWeights=d["dataWeights"], shapeArray=d["shapeArray"], scaleFactor=float(d["scaleFactor"]),
-                                               qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None)))
+                                               qValues=d.get("qValues") if d["kind"] in ("SQ", "RSQ") else None,
+                                               adjustScaleFactor=d["adjust"])))
     st = backend.store
     off = g["group_offsets"]
     st.set_groups([g["group_indexes"][off[i]:off[i + 1]] for i in range(off.shape[0] - 1)])
@@ -186,6 +187,7 @@ def test_device_generated_run_reproduces_the_reference_engine(name, chunks, gold
             data = c.data
             assert np.array_equal(data["intra"], d["final_intra"]) and np.array_equal(data["inter"], d["final_inter"])
             assert F32(chi[ci]) == F32(d["final_stdErr"])
+            assert F32(st.get_scale(c._model)[0]) == F32(d["final_scaleFactor"])
         backend.close()
     finally:
         fullrmc_b200.set_edge_spill(previous)
