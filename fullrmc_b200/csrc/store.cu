@@ -1323,6 +1323,9 @@ struct BatchShared {
     float4 fNew[FRMC_MAX_GROUP];               // (blocks_far's conventions: periodically reduced coordinates, lo.w = rounding margin)
     float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
     float s_csf[FRMC_MAX_MODELS];              // committed scale factor per model as the launch proceeds (refit schedules)
+    unsigned int s_cnt_mod[FRMC_MAX_MODELS];   // (accepted count at the start of the launch) % refit frequency, per model
+    int in_first[BATCH_MAX_PROPS + 1];         // the launch's BatchIn fields the rounds read (first, share): staged once, so the
+    unsigned int in_share[BATCH_MAX_PROPS];    // plan and the walk never wait for a parameter / global load
     float s_prand[BATCH_MAX_PROPS];            // rand_per_proposal: the acceptance number of proposal j of this launch
     unsigned int near[BATCH_MAX_PROPS];        // bit i of near[j]: a pair (atom of j, atom of earlier proposal i) is in range
     // the round's plan (rebuilt after every walk by thread 0): slot s evaluates proposal slot_k[s] on the committed
@@ -1529,7 +1532,7 @@ __global__ void generate_batch_kernel(const GenParams gp, BatchRun *__restrict__
     }
 }
 
-template <int MODE>
+template <int MODE, bool GEN>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
 batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ BatchIn in_host, Lattice L, GridSet gs, int nEl, const ModelSet ms,
              const EpiMap em, const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars,
@@ -1542,8 +1545,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     const int tid = threadIdx.x;
     // the launch's proposals: handed over by the host in the kernel parameters, or drawn on the device by
     // generate_batch_kernel (in_dev; gen / real then carry the real coordinates to commit)
-    const BatchIn &in = in_dev ? *in_dev : in_host;
-    if (in_dev && in.n_prop == 0) return;            // nothing generated: the call is finished or must be re-planned (uniform)
+    // (GEN is a template parameter so that the host-proposal variant keeps reading its proposals from the constant bank)
+    const BatchIn &in = GEN ? *in_dev : in_host;
+    if (GEN && in.n_prop == 0) return;               // nothing generated: the call is finished or must be re-planned (uniform)
     // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST launch
 #define BATCH_STAMP(i) do { if (stamps && blockIdx.x == 0 && tid == 0 && (i) < BATCH_STAMP_SLOTS) { \
         unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[(i)] = (long long)gt_; } } while (0)
@@ -1591,7 +1595,14 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     if (tid < BATCH_MAX_PROPS) {
         bs.near[tid] = 0u; bs.symmask[tid] = 0u;
         bs.s_prand[tid] = (bd.rand_per_proposal && tid < np) ? __ldcg(bd.rand + in.out_base + tid) : 0.0f;
-        if (tid < FRMC_MAX_MODELS) bs.s_csf[tid] = (tid < ms.n) ? __ldcg(&bd.run->csf[tid]) : 1.0f;
+        if (tid < FRMC_MAX_MODELS) {
+            bs.s_csf[tid] = (tid < ms.n) ? __ldcg(&bd.run->csf[tid]) : 1.0f;
+            bs.s_cnt_mod[tid] = (tid < ms.n && bd.freq[tid] > 0)
+                ? (unsigned int)((bd.accepted_base + (unsigned long long)__ldcg(&bd.run->n_accepted)) % (unsigned long long)bd.freq[tid]) : 0u;
+        }
+        bs.in_share[tid] = (tid < np) ? in.share[tid] : 0u;
+        bs.in_first[tid] = in.first[min(tid, np)];
+        if (tid == 0) bs.in_first[BATCH_MAX_PROPS] = in.first[min(BATCH_MAX_PROPS, np)];
     }
     for (int mm = 0; mm < ms.n; ++mm)
         if ((bd.defer_mask >> mm) & 1u)
@@ -1694,7 +1705,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                     if (moved_here) {
                         // a proposal never pairs its atoms with the stored copy of its own atoms (handled below)
                         bool own = false;
-                        for (int v = in.first[j]; v < in.first[j + 1]; ++v) own |= (bs.sPos[v] == p);
+                        for (int v = bs.in_first[j]; v < bs.in_first[j + 1]; ++v) own |= (bs.sPos[v] == p);
                         if (own) continue;
                     }
                     const float4 o = bs.sOld[t], nw = bs.sNew[t];
@@ -1770,14 +1781,17 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     // Refit schedules: an evaluation made at accepted count n refits when n % frequency == 0, and an accepted refit
     // changes the model's scale factor for everything behind it.  A node may therefore only assume acceptances whose
     // own evaluations do not refit: counts base .. base + |A| - 1 must not hit a multiple of any frequency.
+    bool any_freq = false;
+    for (int mm = 0; mm < FRMC_MAX_MODELS; ++mm) any_freq = any_freq || bd.freq[mm] > 0;
     auto spec_limit = [&](unsigned int accm) {
         int lim = BATCH_MAX_SPEC;
-        const unsigned long long base = bd.accepted_base + (unsigned long long)acc_before + (unsigned long long)__popc(accm);
+        if (!any_freq) return lim;
+        const unsigned int acc = (unsigned int)__popc(accm);
         for (int mm = 0; mm < ms.n; ++mm)
             if (bd.freq[mm] > 0) {
-                const int f = bd.freq[mm];
-                const int t = (int)((f - (int)(base % (unsigned long long)f)) % f);
-                lim = min(lim, t);
+                const unsigned int f = (unsigned int)bd.freq[mm];
+                const unsigned int t = (f - (bs.s_cnt_mod[mm] + acc) % f) % f;
+                lim = min(lim, (int)t);
             }
         return lim;
     };
@@ -1802,7 +1816,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         }
         const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
         const unsigned int A_j = acc_pred & below & from_c;         // predicted acceptances in front of j
-        const unsigned int sh_j = in_rng ? in.share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;
+        const unsigned int sh_j = in_rng ? bs.in_share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;
         const bool fits = !((sh_j & (accm | A_j)) || (nr_j & A_j)) && __popc(A_j) <= max_spec;
         const unsigned int bad = __ballot_sync(FULL, lead && !fits);
         int chain_end = bad ? __ffs(bad) - 1 : f;
@@ -1898,12 +1912,12 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
             eo.terms = ((bd.defer_mask >> m) & 1u) ? bd.bterm[m] + (long long)sb * ms.m[m].n_out : nullptr;
             eo.warm = warm ? 1 : 0;
-            {
-                const unsigned long long cnt = bd.accepted_base + (unsigned long long)acc_before + (unsigned long long)__popc(acc_mask) +
-                                               (unsigned long long)__popc(bs.slot_A[group]);
-                eo.refit = (bd.freq[m] > 0 && cnt % (unsigned long long)bd.freq[m] == 0ull) ? 1 : 0;
-                eo.scale = bs.s_csf[m];
+            eo.refit = 0;
+            if (bd.freq[m] > 0) {
+                const unsigned int f = (unsigned int)bd.freq[m];
+                eo.refit = ((bs.s_cnt_mod[m] + (unsigned int)__popc(acc_mask) + (unsigned int)__popc(bs.slot_A[group])) % f == 0u) ? 1 : 0;
             }
+            eo.scale = bs.s_csf[m];
             long long *est = (stamps && blockIdx.x == 1 && rounds <= 64) ? stamps + BATCH_STAMP_SLOTS + (rounds - 1) * 128 : nullptr;
             if (est && tid == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); est[120] = (long long)gt_; est[121] = (long long)t_round; }
             epilogue_run<true>(es, epi_smem, ms, gs, m, slab, nullptr, nullptr, nullptr, bd.tickets + sb * FRMC_MAX_MODELS, est, eo);
@@ -1996,7 +2010,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                     const unsigned int A = acc_slots << cur;
                     const int used = __popc(worse_m & ((s_end < 31) ? ((2u << s_end) - 1u) : FULL));
                     // a proposal that moves an atom an accepted proposal of this launch has moved ends the launch
-                    const bool stop = (k < np) && (in.share[k] & (acc_mask | A));
+                    const bool stop = (k < np) && (bs.in_share[k] & (acc_mask | A));
                     bs.s_acc = A; bs.s_last = last; bs.s_cur = k; bs.s_ri = ri + used; bs.s_stopped = stop ? 1 : 0;
                     bs.s_total = last < 0 ? total : tl;
                 }
@@ -2075,9 +2089,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             }
             if (blockIdx.x == 0) {
                 for (int x = 0; x < n_aj; ++x)
-                    for (int t = in.first[acc_j[x]] + tid; t < in.first[acc_j[x] + 1]; t += blockDim.x) {
+                    for (int t = bs.in_first[acc_j[x]] + tid; t < bs.in_first[acc_j[x] + 1]; t += blockDim.x) {
                         atoms[bs.sPos[t]] = bs.sNew[t];
-                        if (gen && real) real[gen->ridx[t]] = make_float4(gen->mreal[3 * t], gen->mreal[3 * t + 1], gen->mreal[3 * t + 2], 0.f);
+                        if (GEN && real) real[gen->ridx[t]] = make_float4(gen->mreal[3 * t], gen->mreal[3 * t + 1], gen->mreal[3 * t + 2], 0.f);
                     }
                 if (tid < ms.n) {
                     bd.run->cchi2[tid] = bs.s_chi[last][tid];
@@ -2087,9 +2101,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
             // Proposals resolved in this round need none: their nodes had no such pair (bs.near).
             if (need_bar) {
-                const int later0 = in.first[cur];                // atoms are listed in proposal order
+                const int later0 = bs.in_first[cur];                // atoms are listed in proposal order
                 for (int x = 0; x < n_aj; ++x) {
-                    const int a0 = in.first[acc_j[x]], a1 = in.first[acc_j[x] + 1];
+                    const int a0 = bs.in_first[acc_j[x]], a1 = bs.in_first[acc_j[x] + 1];
                     const long long n_items = (long long)(na - later0) * (a1 - a0);
                     for (long long it = gt; it < n_items; it += stride) {
                         const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
@@ -2466,12 +2480,14 @@ static int sync_models(frmc_store *s)
             s->batch_defer_mask |= 1u << mi;
         }
         int per_sm = 0;
-#define BATCH_ATTR(M) do { \
-            if (cudaFuncSetAttribute(batch_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)) != cudaSuccess) s->batch_ok = false; \
-            cudaFuncSetAttribute(batch_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batch_kernel<M>, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->batch_ok = false; \
+#define BATCH_ATTR1(K) do { \
+            if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)) != cudaSuccess) s->batch_ok = false; \
+            cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->batch_ok = false; \
         } while (0)
+#define BATCH_ATTR(M) do { auto k0 = batch_kernel<M, false>; auto k1 = batch_kernel<M, true>; BATCH_ATTR1(k0); BATCH_ATTR1(k1); } while (0)
         BATCH_ATTR(MODE_IBC); BATCH_ATTR(MODE_ORTHO_FAST); BATCH_ATTR(MODE_TRI_FAST); BATCH_ATTR(MODE_ORTHO_GEN); BATCH_ATTR(MODE_TRI_GEN);
+#undef BATCH_ATTR1
 #undef BATCH_ATTR
         cudaGetLastError();
     }
@@ -2951,8 +2967,8 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
     float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
     void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
                     &in_dev, &gen, &real};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)batch_kernel<MODE>, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS),
-                                                args, s->epi_smem, s->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(generated ? (const void *)batch_kernel<MODE, true> : (const void *)batch_kernel<MODE, false>,
+                                                dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS), args, s->epi_smem, s->stream);
     if (e != cudaSuccess) {
         set_error("cooperative launch of the batch kernel failed: %s", cudaGetErrorString(e));
         return FRMC_ECUDA;
