@@ -18,6 +18,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -132,6 +135,14 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
     }
     DeviceCtx *c0 = ctx[0];
     FRMC_CUDA(cudaSetDevice(c0->dev));
+    const bool timing = getenv("FRMC_MULTI_TIMING") != nullptr;     // debug: host wall clock at the phase boundaries (stderr)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_start = now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(c0->stream);
+        fprintf(stderr, "[multi x%d] %-28s %8.3f ms\n", ndev, what, std::chrono::duration<double, std::milli>(now() - t_start).count());
+    };
 
     // 1. the store layout on device 0 (the scratch is per calling thread; the worker threads below must see THIS
     //    thread's instance, hence the reference)
@@ -155,6 +166,7 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
             FRMC_CUDA(cudaMemcpyAsync(d_orig0, lay.orig.data(), sizeof(uint32_t) * (size_t)lay.npad, cudaMemcpyHostToDevice, c0->stream));
         }
     }
+    lap("layout on device 0");
     Lattice L;
     for (int i = 0; i < 9; ++i) L.b[i] = basis ? basis[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
     const GridParams g = make_grid(rmin, rmax, bin, hs);
@@ -212,6 +224,7 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
             FRMC_CUDA(cudaMemcpyPeerAsync(D[(size_t)k].orig, ctx[(size_t)k]->dev, d_orig0, c0->dev, sizeof(uint32_t) * (size_t)lay.npad, c0->stream));
         }
     FRMC_CUDA(cudaEventRecord(ready, c0->stream));
+    lap("rows + peer copies");
 
     // 3. every device lists and sweeps its rows (one host thread each: the list builder synchronises its stream)
     auto work = [&](int k) {
@@ -243,6 +256,7 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
     for (int k = 0; k < ndev; ++k)
         if (D[(size_t)k].rc) { set_error("device %d: %s", ctx[(size_t)k]->dev, D[(size_t)k].err.c_str()); cudaEventDestroy(ready); return D[(size_t)k].rc; }
 
+    lap("sweeps issued (threads joined)");
     // 4. one all-reduce of the 64-bit counts (+ the overflow and swept counters behind them)
     if (ndev > 1) {
         CommSet *cs = nullptr;
@@ -266,6 +280,7 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
         snprintf(g_reduce_path, sizeof(g_reduce_path), "single device");
     }
 
+    lap("all-reduce issued");
     // 5. device 0 returns the result; the other devices only have to finish
     FRMC_CUDA(cudaSetDevice(c0->dev));
     float *d_out = (float *)ctx_buffer(c0, 5, sizeof(float) * 2 * (size_t)cells);
@@ -281,6 +296,7 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
         FRMC_CUDA(cudaStreamSynchronize(ctx[(size_t)k]->stream));
     }
     FRMC_CUDA(cudaSetDevice(c0->dev));
+    lap("all devices done, result home");
     cudaEventDestroy(ready);
     if (edge_overflow) *edge_overflow = ov;
     return FRMC_OK;
