@@ -214,7 +214,7 @@ def main():
         rsf = ReducedStructureFactorConstraint(experimentalData=Sq, weighting="atomicNumber")
         return [(pdf, "PDF"), (rsf, "RSQ")]
     n = arrays[0].shape[0]
-    run_case("niti", fullrmc, arrays, niti, [[i] for i in range(n)], 40, 1, 0.15, out_dir)
+    run_case("niti", fullrmc, arrays, niti, [[i] for i in range(n)], 160, 1, 0.15, out_dir)
 
     # ---- config 2: Examples/molecularTHF as shipped (run.py:52-57): g(r) with data weights, molecule moves
     d = os.path.join(EX, "molecularTHF")
@@ -225,7 +225,7 @@ def main():
         return [(PairCorrelationConstraint(experimentalData=gr.astype(FLOAT_TYPE), weighting="atomicNumber", dataWeights=dw), "PCF")]
     mol = arrays[3]
     groups = [np.flatnonzero(mol == m).tolist() for m in range(int(mol.max()) + 1)]
-    run_case("thf", fullrmc, arrays, thf, groups, 24, 2, 0.2, out_dir)
+    run_case("thf", fullrmc, arrays, thf, groups, 72, 2, 0.2, out_dir)
 
     # ---- config 3: Examples/SiOxNanosphere (run.py:41): non-periodic PDF (shape function left to a later round)
     d = os.path.join(EX, "SiOxNanosphere")
@@ -235,7 +235,7 @@ def main():
         object.__setattr__(E, "_Engine__volume", FLOAT_TYPE(E.numberOfAtoms / 0.0125))
         return [(PairDistributionConstraint(experimentalData=os.path.join(d, "SiOx.gr"), weighting="atomicNumber"), "PDF")]
     n = arrays[0].shape[0]
-    run_case("siox", fullrmc, arrays, siox, [[i] for i in range(n)], 40, 3, 0.2, out_dir)
+    run_case("siox", fullrmc, arrays, siox, [[i] for i in range(n)], 160, 3, 0.2, out_dir)
 
     # ---- synthetic triclinic, 4 elements: G(r) + full S(Q) with a scale factor and data weights
     rng = np.random.default_rng(44)
@@ -254,7 +254,7 @@ def main():
                                        weighting="atomicNumber", scaleFactor=1.05)
         return [(pdf, "PDF"), (sf, "SQ")]
     groups = [[3 * m, 3 * m + 1, 3 * m + 2] for m in range(n // 3)]
-    run_case("synth", fullrmc, arrays, synth, groups, 30, 4, 0.25, out_dir)
+    run_case("synth", fullrmc, arrays, synth, groups, 120, 4, 0.25, out_dir)
 
     # ---- scale-factor refit (Core/Constraint.py:1363-1423).  NiTi as shipped switches it on for both constraints
     #      (Examples/atomicNiTi/run.py:102-103); a short frequency makes 40 steps cross several refit windows.
@@ -266,7 +266,7 @@ def main():
             c.set_adjust_scale_factor((4, 0.8, 1.2))
         return cons
     nn = arrays_niti[0].shape[0]
-    run_case("niti_sf", fullrmc, arrays_niti, niti_sf, [[i] for i in range(nn)], 40, 11, 0.15, out_dir)
+    run_case("niti_sf", fullrmc, arrays_niti, niti_sf, [[i] for i in range(nn)], 160, 11, 0.15, out_dir)
 
     # ---- config 3 with its shape function (Examples/SiOxNanosphere/run.py:41-47; Constraints/Collection.py:20-125),
     #      refreshed every 4 accepted moves instead of every 1000
@@ -280,7 +280,7 @@ def main():
                                            'updateFreq': 4})
         return [(pdf, "PDF")]
     ns = arrays_siox[0].shape[0]
-    run_case("siox_shape", fullrmc, arrays_siox, siox_shape, [[i] for i in range(ns)], 24, 13, 0.2, out_dir)
+    run_case("siox_shape", fullrmc, arrays_siox, siox_shape, [[i] for i in range(ns)], 96, 13, 0.2, out_dir)
 
     # synthetic: g(r) with data weights + full S(Q), refit every 3 accepted moves with a tight clip range
     rng2 = np.random.default_rng(45)
@@ -293,7 +293,7 @@ def main():
         sf = StructureFactorConstraint(experimentalData=np.stack([q, 1 + rng2.normal(0, 0.1, 150).astype(np.float32)], 1).astype(np.float32),
                                        weighting="atomicNumber", scaleFactor=1.05, adjustScaleFactor=(3, 0.7, 1.3))
         return [(pcf, "PCF"), (sf, "SQ")]
-    run_case("synth_sf", fullrmc, arrays, synth_sf, groups, 30, 5, 0.25, out_dir)
+    run_case("synth_sf", fullrmc, arrays, synth_sf, groups, 120, 5, 0.25, out_dir)
 
 
 if __name__ == "__main__":
