@@ -125,6 +125,10 @@ SIGNATURES = {
     "frmc_store_set_groups": (_I, [_VP, _I, c_i32p, c_i32p]),
     "frmc_run_generated": (_I, [_VP, _I, ctypes.c_uint64, ctypes.c_uint64, _F, _F, c_f32p, _F, c_f32p, c_f32p, c_i32p, c_i32p, c_f32p,
                                 ctypes.POINTER(ctypes.c_double)]),
+    "frmc_store_distance_add": (_I, [_VP, c_i32p, _I, c_f32p, c_f32p, _I]),
+    # array arguments as plain addresses (see frmc_step)
+    "frmc_store_distance_move": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),
+    "frmc_store_move_atoms": (_I, [_VP, c_i32p, _I, c_f32p]),
     "frmc_run_batch": (_I, [_VP, _I, c_i32p, c_i32p, c_f32p, c_f32p, _F, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p,
                             ctypes.POINTER(ctypes.c_double)]),
     "frmc_store_batch_stats": (_I, [_VP, c_u64p, c_u64p, c_u64p]),

@@ -11,8 +11,13 @@ Reference classes: ``InterMolecularDistanceConstraint`` / ``IntraMolecularDistan
 * a rigid (non-flexible) constraint rejects a step when any cell's count grows (:361-383).
 
 The two kernels are ``fullrmc_b200.Core.atomic_distances`` (CUDA, bit-identical to the reference's Cython, sums
-included); this first version is stateless -- the coordinates travel with every call -- like the reference's
-own functions.  Sharing the device store's per-move sweep is the next step.
+included).  Two modes:
+
+* stateless (``store=None``): the coordinates travel with every call, like the reference's own functions;
+* on the device store (``store=DeviceStore``): the constraint is registered once on the store
+  whose atoms the histogram constraints move, and a move's four quantities (M and F, before and after) come from ONE
+  pass over the resident records (``DeviceStore.distance_move``, csrc/storedist.cu) -- no coordinate upload; the
+  engine's boxCoordinates array is not read at all in the Monte-Carlo loop.
 """
 import numpy as np
 
@@ -31,10 +36,12 @@ class DeviceMolecularDistanceConstraint(object):
     """
 
     def __init__(self, boxCoordinates, basisVectors, isPBC, moleculesIndex, typesIndex, numberOfTypes, lowerLimitArray,
-                 upperLimitArray, typePairsIndex, interMolecular=True, flexible=True, kernels=None):
+                 upperLimitArray, typePairsIndex, interMolecular=True, flexible=True, kernels=None, store=None):
         if kernels is None:
             from .Core import atomic_distances as kernels
         self._kernels = kernels
+        self._store = store
+        self._pending = None                 # store mode: the group of the move being evaluated
         self.boxCoordinates = boxCoordinates
         self.basisVectors = np.ascontiguousarray(basisVectors, dtype=FLOAT_TYPE)
         self.isPBC = bool(isPBC)
@@ -57,6 +64,9 @@ class DeviceMolecularDistanceConstraint(object):
         self.activeAtomsDataAfterMove = None
         self.tried = 0
         self.accepted = 0
+        if store is not None:
+            self._sd = store.distance_add(self.typesIndex, self.numberOfTypes, self.lowerLimitArray, self.upperLimitArray,
+                                          **{k: v for k, v in self._flags.items()})
 
     # ---------------------------------------------------------------- helpers
     def _pick(self, result):
@@ -92,8 +102,13 @@ class DeviceMolecularDistanceConstraint(object):
         return FLOAT_TYPE(np.sum(distances))
 
     # ---------------------------------------------------------------- the five methods
+    def _coords(self):
+        if self._store is not None:
+            return self._store.get_coords()                       # the store owns the coordinates
+        return np.ascontiguousarray(self.boxCoordinates, dtype=FLOAT_TYPE)
+
     def compute_data(self, update=True):
-        coords = np.ascontiguousarray(self.boxCoordinates, dtype=FLOAT_TYPE)
+        coords = self._coords()
         number, distanceSum = self._pick(self._kernels.full_atomic_distances_coords(
             moleculeIndex=self.moleculesIndex, elementIndex=self.typesIndex, **self._system(coords), **self._flags))
         data = {"number": number, "distanceSum": distanceSum}
@@ -105,14 +120,28 @@ class DeviceMolecularDistanceConstraint(object):
         return data, stdError
 
     def compute_before_move(self, realIndexes, relativeIndexes):
+        if self._store is not None:
+            # before and after come from one pass over the store once the moved coordinates are known
+            self._pending = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+            self.activeAtomsDataBeforeMove = self.activeAtomsDataAfterMove = None
+            return
         coords = np.ascontiguousarray(self.boxCoordinates, dtype=FLOAT_TYPE)
         self.activeAtomsDataBeforeMove = self._move_contribution(coords, relativeIndexes)
         self.activeAtomsDataAfterMove = None
 
     def compute_after_move(self, realIndexes, relativeIndexes, movedBoxCoordinates):
-        coords = np.array(self.boxCoordinates, dtype=FLOAT_TYPE)                       # a copy: the engine's array stays as it is
-        coords[relativeIndexes] = movedBoxCoordinates
-        self.activeAtomsDataAfterMove = self._move_contribution(coords, relativeIndexes)
+        if self._store is not None:
+            idx = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+            counts, sums = self._store.distance_move(self._sd, idx, movedBoxCoordinates)
+            part = 1 if self._interMolecular else 0
+            # multiple(all N) - full(group alone), before and after (:606-737)
+            self.activeAtomsDataBeforeMove = {"number": counts[0, part] - counts[1, part], "distanceSum": sums[0, part] - sums[1, part]}
+            self.activeAtomsDataAfterMove = {"number": counts[2, part] - counts[3, part], "distanceSum": sums[2, part] - sums[3, part]}
+            self._moved = (idx, np.ascontiguousarray(movedBoxCoordinates, dtype=FLOAT_TYPE))
+        else:
+            coords = np.array(self.boxCoordinates, dtype=FLOAT_TYPE)                   # a copy: the engine's array stays as it is
+            coords[relativeIndexes] = movedBoxCoordinates
+            self.activeAtomsDataAfterMove = self._move_contribution(coords, relativeIndexes)
         number = self.data["number"] - self.activeAtomsDataBeforeMove["number"] + self.activeAtomsDataAfterMove["number"]
         distanceSum = self.data["distanceSum"] - self.activeAtomsDataBeforeMove["distanceSum"] + self.activeAtomsDataAfterMove["distanceSum"]
         self.afterMoveStandardError = self._compute_standard_error(self._get_constraint_value({"number": number, "distanceSum": distanceSum}))
@@ -132,6 +161,8 @@ class DeviceMolecularDistanceConstraint(object):
         self.standardError = self.afterMoveStandardError
         self.afterMoveStandardError = None
         self.accepted += 1
+        if self._store is not None and self._store.n_models == 0:
+            self._store.move_atoms(*self._moved)                  # nobody else commits the move on a store without models
 
     def reject_move(self, realIndexes, relativeIndexes):
         self.activeAtomsDataBeforeMove = self.activeAtomsDataAfterMove = None

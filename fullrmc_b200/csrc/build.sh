@@ -14,7 +14,7 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
 if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
 OBJS=()
 PIDS=()
-for f in common stateless fullhist devlayout multigpu store atomdist coordnum; do
+for f in common stateless fullhist devlayout multigpu store atomdist coordnum storedist; do
   rm -f "$OUT/$f.o"                     # a failed compile must never leave a stale object for the link step
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   PIDS+=("$!")

@@ -2749,10 +2749,18 @@ int store_view(frmc_store *s, StoreView *out)
     if (rc) return rc;
     out->dev = s->dev; out->stream = s->stream; out->sm_count = s->ctx->sm_count; out->ctx = s->ctx;
     out->atoms = s->d_atoms; out->orig = s->d_orig; out->n = s->n; out->npad = s->npad; out->inv = s->lay.inv.data();
+    out->n0 = s->n0; out->rel2real = s->rel2real.empty() ? nullptr : s->rel2real.data();
     out->L = s->L; out->isPBC = s->isPBC;
     for (int c = 0; c < 3; ++c) { out->lo[c] = s->lo[c]; out->hi[c] = s->hi[c]; }
     out->pending = s->pending; out->prop = s->d_prop;
     return FRMC_OK;
+}
+
+int store_flush(frmc_store *s)
+{
+    FRMC_REQUIRE(s, FRMC_EINVAL, "NULL store");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    return flush_pending(s);
 }
 }  // namespace frmc
 
@@ -3057,6 +3065,7 @@ void frmc_store_destroy(frmc_store *s)
                 s->t_launch / s->n_calls, s->t_wait / s->n_calls);
     if (!s) return;
     cudaSetDevice(s->dev);
+    storedist_release(s);
     if (s->h_cmd) stop_persistent(s);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &m : s->models) {
@@ -3109,6 +3118,32 @@ int frmc_store_set_coords(frmc_store *s, const float *coords, const float *basis
     s->state = 0;
     GridSet gs = make_gridset(s);
     if (gs.n) { clear_delta_kernel<<<launch_cells_grid(s), 256, 0, s->stream>>>(gs); FRMC_LAUNCH_CHECK(); }
+    return FRMC_OK;
+}
+
+int frmc_store_move_atoms(frmc_store *s, const int32_t *indexes, int k, const float *moved)
+{
+    FRMC_REQUIRE(s && indexes && moved, FRMC_EINVAL, "NULL argument");
+    FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group size %d outside 1..%d", k, FRMC_MAX_GROUP);
+    FRMC_REQUIRE(s->state == 0, FRMC_ESTATE, "a proposal is staged; accept or reject it first");
+    FRMC_CUDA(cudaSetDevice(s->dev));
+    { int frc = flush_pending(s); if (frc) return frc; }
+    for (int t = 0; t < k; ++t) {
+        FRMC_REQUIRE(indexes[t] >= 0 && indexes[t] < s->n, FRMC_EINVAL, "atom index %d outside 0..%lld", indexes[t], (long long)s->n - 1);
+        for (int c = 0; c < 3; ++c) {
+            const float v = moved[3 * t + c];
+            FRMC_REQUIRE(v == v && !isinf(v), FRMC_EINVAL, "moved coordinates contain NaN or Inf");
+        }
+    }
+    for (int t = 0; t < k; ++t) {
+        // coordinates only: the record keeps its meta word (12-byte copy into the 16-byte record)
+        FRMC_CUDA(cudaMemcpyAsync(reinterpret_cast<float *>(s->d_atoms + pos_of(s, indexes[t])), moved + 3 * t, sizeof(float) * 3,
+                                  cudaMemcpyHostToDevice, s->stream));
+        for (int c = 0; c < 3; ++c) { s->lo[c] = std::min(s->lo[c], moved[3 * t + c]); s->hi[c] = std::max(s->hi[c], moved[3 * t + c]); }
+    }
+    FRMC_CUDA(cudaStreamSynchronize(s->stream));
+    s->real_valid = false;
+    for (auto &g : s->grids) g.valid = false;          // running histograms (if any) no longer describe the coordinates
     return FRMC_OK;
 }
 

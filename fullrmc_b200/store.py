@@ -271,6 +271,50 @@ class DeviceStore(object):
     def reject(self):
         L.check(self._lib.frmc_reject(self._handle), "reject")
 
+    # ------------------------------------------------------------------ distance-constraint pre-filter on the store
+    def distance_add(self, typesIndex, numberOfTypes, lowerLimit, upperLimit, interMolecular=True, intraMolecular=True,
+                     countWithinLimits=True, reduceDistanceToUpper=False, reduceDistanceToLower=False, reduceDistance=False):
+        """register a molecular distance constraint on this store (include/fullrmc_b200.h: frmc_store_distance_add);
+        the limit arrays are the reference's [nT,nT,1] arrays indexed [type_i, type_a]; returns its id"""
+        from .Core.atomic_distances import _flags
+        t = np.ascontiguousarray(typesIndex, dtype=_I32)
+        nT = int(numberOfTypes)
+        lo = np.ascontiguousarray(lowerLimit, dtype=_F32).reshape(-1)
+        up = np.ascontiguousarray(upperLimit, dtype=_F32).reshape(-1)
+        if t.shape[0] != self.numberOfAtoms or lo.shape[0] != nT * nT or up.shape[0] != nT * nT:
+            raise ValueError("typesIndex must have one entry per atom and the limits numberOfTypes^2 entries")
+        flags = _flags(interMolecular, intraMolecular, countWithinLimits, reduceDistanceToUpper, reduceDistanceToLower, reduceDistance)
+        cid = L.check(self._lib.frmc_store_distance_add(self._handle, L.ptr(t, L.c_i32p), nT, L.ptr(lo, L.c_f32p), L.ptr(up, L.c_f32p),
+                                                        flags), "distance_add")
+        self._dist = getattr(self, "_dist", {})
+        counts, sums = np.zeros((4, 2, nT, nT, 1), dtype=_I32), np.zeros((4, 2, nT, nT, 1), dtype=_F32)
+        self._dist[cid] = (counts, sums, counts.__array_interface__["data"][0], sums.__array_interface__["data"][0])
+        return cid
+
+    def distance_move(self, cid, indexes, movedBoxCoordinates):
+        """One pass over the resident atoms for a move of a registered distance constraint: returns (counts, sums), each
+        (4, 2, nT, nT, 1) = (M before, F before, M after, F after) x (intra, inter): M = multiple_atomic_distances_coords of
+        the group against all atoms, F = full_atomic_distances_coords of the group alone.  Views of reused buffers."""
+        idx, moved = indexes, movedBoxCoordinates
+        if not (type(idx) is np.ndarray and idx.dtype == _I32 and idx.flags.c_contiguous):
+            idx = np.ascontiguousarray(idx, dtype=_I32)
+        if not (type(moved) is np.ndarray and moved.dtype == _F32 and moved.flags.c_contiguous):
+            moved = np.ascontiguousarray(moved, dtype=_F32)
+        if moved.size != 3 * idx.shape[0]:
+            raise ValueError("movedBoxCoordinates must be (k,3)")
+        counts, sums, pc, ps = self._dist[cid]
+        rc = self._lib.frmc_store_distance_move(self._handle, cid, idx.__array_interface__["data"][0], idx.shape[0],
+                                                moved.__array_interface__["data"][0], pc, ps)
+        if rc < 0:
+            L.check(rc, "distance_move")
+        return counts, sums
+
+    def move_atoms(self, indexes, movedBoxCoordinates):
+        """apply an accepted move on a store without histogram models (with models, accept() does it)"""
+        idx = np.ascontiguousarray(indexes, dtype=_I32)
+        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
+        L.check(self._lib.frmc_store_move_atoms(self._handle, L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(moved, L.c_f32p)), "move_atoms")
+
     # ------------------------------------------------------------------ device-generated runs of moves
     def set_real_coords(self, realCoordinates=None, reciprocalBasisVectors=None):
         """engine.realCoordinates and engine.reciprocalBasisVectors (both None for a non-periodic store)"""

@@ -311,6 +311,23 @@ int frmc_reject(frmc_store *s);
 /* One host call per Metropolis step: resolve the staged proposal (previous = 1 accept, 0 reject;
  * ignored when nothing is staged) and evaluate the next one. */
 int frmc_step(frmc_store *s, int previous, const int32_t *indexes, int k, const float *moved, float *chi2_after);
+/* ---- the distance-constraint pre-filter on the device store (the per-move pass shares the
+ * store) -----------------------------------------------------------------------------------------------------------
+ * InterMolecularDistanceConstraint / IntraMolecularDistanceConstraint evaluate, for the k atoms of a move,
+ * M = multiple_atomic_distances_coords(indexes, all atoms) and F = full_atomic_distances_coords(the group alone) before
+ * and after the move (Constraints/DistanceConstraints.py:606-737), and Engine.py:3281-3290 does so BEFORE the
+ * experimental constraints on every step.  frmc_store_distance_add registers the constraint once on the store whose
+ * atoms the histogram constraints move (type [n] = typesIndex by atom; lowerLimit / upperLimit [nT*nT] indexed
+ * [type_i, type_a]; flags = FRMC_AD_*); frmc_store_distance_move evaluates all four quantities of one move in one pass
+ * over the resident records -- no coordinate upload.  counts_out / sums_out: [4][2][nT*nT] = (M before, F before,
+ * M after, F after) x (intra, inter) x [type_a, type_i]; the float32 sums are accumulated in the reference's loop
+ * order (bit-identical).  frmc_store_move_atoms applies an accepted move on a store without histogram models (with
+ * models, frmc_accept does). */
+int frmc_store_distance_add(frmc_store *s, const int32_t *type, int nT, const float *lowerLimit, const float *upperLimit, int flags);
+int frmc_store_distance_move(frmc_store *s, int id, const int32_t *indexes, int k, const float *moved, int32_t *counts_out,
+                             float *sums_out);
+int frmc_store_move_atoms(frmc_store *s, const int32_t *indexes, int k, const float *moved);
+
 /* ---- dynamic N and persisted state -------------------------------------------------
  * Atom removal (Engine.__on_runtime_step_try_remove, Engine.py:3231-3276; compute_as_if_amputated / accept_amputation /
  * reject_amputation of the three constraints, PairDistributionConstraints.py:1168-1238,
