@@ -564,6 +564,37 @@ def distance_leg(system, no_cpu):
                                 "within the largest upper limit, so the fraction is small by construction"},
            "note": "stateless version of this row: k-d ordered store + block culling against the largest upper "
            "limit, hits sorted and summed in the reference's order; the call is dominated by host ordering, copies and syncs"}
+    # the per-move evaluation (what Engine.py:3281-3290 runs before the experimental constraints on every step): the
+    # stateless call with the coordinates uploaded each time, and the pass over the device store's resident records
+    try:
+        from fullrmc_b200.store import DeviceStore
+        rng = np.random.default_rng(23)
+        m = 220
+        idx = rng.integers(0, n, m).astype(np.int32)
+        moved = (system.boxCoords[idx] + rng.normal(0, 0.001, (m, 3))).astype(np.float32)
+        mkw = dict(kw, allAtoms=True)
+        for it in range(3):
+            ad.multiple_atomic_distances_coords(indexes=idx[it:it + 1], **mkw)
+        t0 = time.perf_counter()
+        for it in range(3, 23):
+            before = ad.multiple_atomic_distances_coords(indexes=idx[it:it + 1], **mkw)
+        us_stateless = 1e6 * (time.perf_counter() - t0) / 20
+        with DeviceStore(system.boxCoords, system.basis, system.isPBC, system.moleculeIndex, system.elementIndex, nT) as st:
+            cid = st.distance_add(system.elementIndex, nT, lo, up, interMolecular=True, intraMolecular=False, reduceDistanceToUpper=True)
+            for it in range(20):
+                counts, sums = st.distance_move(cid, idx[it:it + 1], moved[it:it + 1])
+            same = bool(np.array_equal(counts[0, 1], ad.multiple_atomic_distances_coords(indexes=idx[19:20], **mkw)[2]) and
+                        np.array_equal(sums[0, 1], ad.multiple_atomic_distances_coords(indexes=idx[19:20], **mkw)[3]))
+            t0 = time.perf_counter()
+            for it in range(20, m):
+                st.distance_move(cid, idx[it:it + 1], moved[it:it + 1])
+            us_store = 1e6 * (time.perf_counter() - t0) / (m - 20)
+        out["per_move"] = {"stateless_call_us": us_stateless, "store_pass_us": us_store, "identical": same,
+                           "h2d_bytes_per_step_stateless": 20 * n, "h2d_bytes_per_step_store": 16,
+                           "api": "DeviceStore.distance_move (frmc_store_distance_move): before and after of one move, group vs all "
+                                  "atoms and group alone, in one pass over the resident records"}
+    except Exception as err:
+        out["per_move"] = {"error": "%s: %s" % (type(err).__name__, err)}
     if not no_cpu:
         from oracle import build_ref
         import importlib
@@ -1313,6 +1344,8 @@ def run_b200(args):
         line["distance_constraint_cfg4"] = dleg
         line["coordination_cfg4"] = cleg
         line["distance_constraint_cfg4_roofline_frac"] = (dleg.get("roofline") or {}).get("frac")
+        line["distance_constraint_cfg4_per_move_store_us"] = (dleg.get("per_move") or {}).get("store_pass_us")
+        line["distance_constraint_cfg4_per_move_stateless_us"] = (dleg.get("per_move") or {}).get("stateless_call_us")
         line["coordination_cfg4_roofline_frac"] = (cleg.get("roofline") or {}).get("frac")
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
