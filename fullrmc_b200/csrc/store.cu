@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <type_traits>
 #include <immintrin.h>
 #include <chrono>
 #include <cstdio>
@@ -573,6 +574,9 @@ struct EpiOut {
     float *terms;            // S(Q) models: [n_out] weighted squared residuals; when set the slab CTAs stop there and
                              // every CTA forms chi2 itself after the grid barrier (no ticket, no last-CTA stage)
     int warm;                // this CTA has run this (model, slab) before in this launch: tables and schedule are staged
+    const unsigned int *ev;  // on-the-fly pair corrections of this node on this model's grid: (row << 16 | bin), bit 31 = minus one
+    const unsigned int *ev_bits;   // 1024-bit filter on (bin & 1023): a thread scans the list only when one of its bins is marked
+    int n_ev;
     int refit;               // this evaluation refits the scale factor (the engine's accepted count AT THIS NODE % frequency == 0)
     float scale;             // the model's committed scale factor at this node (acceptances inside the launch may have changed it)
 };
@@ -631,7 +635,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
     // ---- 1. r-space function: EPI_BINS bins per thread per round, every load issued before any arithmetic
     {
         const int *__restrict__ stot = BATCH ? eo.base : gs.grid[M.grid].stot;
-        constexpr int EPI_BINS = 2, PB = 16;
+        constexpr int EPI_BINS = 2;
         const bool defer = !is_sq && (mrefit || M.prior || M.window);   // scale, prior, window applied in stage 1b
         // bin r from the sum over the pair terms (acc): /shellVolumes, prefactor, shape, scale
         auto finish_bin = [&](int r, float accv, float svr, float prf, float shp) {
@@ -658,6 +662,11 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 if (!is_sq) total[r] = out;
             }
         };
+        // the pair loop is unrolled PB pairs at a time; models with few element pairs (two elements: three pairs) take
+        // the narrow variant instead of loading twelve padding rows per bin
+        auto bins = [&](auto pb_tag) {
+        constexpr int PB = decltype(pb_tag)::value;
+        const int np_padx = (np + PB - 1) / PB * PB;
         if (BATCH && (hs & 1) == 0) {
             // batch, even histogram size: two consecutive bins per thread through 8-byte loads (half the load and
             // address instructions of the scalar loop; rows start on 8-byte boundaries because hs is even)
@@ -665,7 +674,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 float acc0 = 0.0f, acc1 = 0.0f;
                 const float2 svr = *reinterpret_cast<const float2 *>(M.sv + r0), prf = *reinterpret_cast<const float2 *>(M.pref + r0);
                 const float2 shp = M.shape ? *reinterpret_cast<const float2 *>(M.shape + r0) : make_float2(0.f, 0.f);
-                for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_pad); p0 += PB) {
+                for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_padx); p0 += PB) {
                     int2 c[PB];
 #pragma unroll
                     for (int u = 0; u < PB; ++u) c[u] = __ldcg(reinterpret_cast<const int2 *>(stot + s_psym[p0 + u] * hs + r0));
@@ -679,6 +688,17 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                                                                         : make_int2(0, 0);
 #pragma unroll
                         for (int u = 0; u < PB; ++u) { c[u].x += e[u].x; c[u].y += e[u].y; }
+                    }
+                    // on-the-fly pair corrections (CorrEv): the few events of this node, filtered by bin
+                    if (eo.n_ev && (((eo.ev_bits[(r0 & 1023) >> 5] >> (r0 & 31)) | (eo.ev_bits[((r0 + 1) & 1023) >> 5] >> ((r0 + 1) & 31))) & 1u)) {
+                        for (int x = 0; x < eo.n_ev; ++x) {
+                            const unsigned int evx = eo.ev[x];
+                            const int eb = (int)(evx & 0xFFFFu), erow = (int)((evx >> 16) & 0x7FFFu), es_ = (evx >> 31) ? -1 : 1;
+                            if ((eb & ~1) != r0) continue;
+#pragma unroll
+                            for (int u = 0; u < PB; ++u)
+                                if (s_psym[p0 + u] == erow && s_w[p0 + u] != 0.0f) { if (eb & 1) c[u].y += es_; else c[u].x += es_; }
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < PB; ++u) {
@@ -704,7 +724,7 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 acc[j] = 0.0f;
                 svr[j] = M.sv[r]; prf[j] = M.pref[r]; shp[j] = M.shape ? M.shape[r] : 0.0f;
             }
-            for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_pad); p0 += PB) {
+            for (int p0 = 0; p0 < ((M.sq_exact & 4) ? 0 : np_padx); p0 += PB) {
                 int c[EPI_BINS][PB];
 #pragma unroll
                 for (int j = 0; j < EPI_BINS; ++j) {
@@ -721,6 +741,16 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                                 e[u] = ((mk >> (s_psym[p0 + u] & 31)) & 1u) ? __ldcg(ap + (long long)s_psym[p0 + u] * hs + r) : 0;
 #pragma unroll
                             for (int u = 0; u < PB; ++u) c[j][u] += e[u];
+                        }
+                        if (eo.n_ev && ((eo.ev_bits[(r & 1023) >> 5] >> (r & 31)) & 1u)) {      // on-the-fly pair corrections
+                            for (int x = 0; x < eo.n_ev; ++x) {
+                                const unsigned int evx = eo.ev[x];
+                                const int eb = (int)(evx & 0xFFFFu), erow = (int)((evx >> 16) & 0x7FFFu), es_ = (evx >> 31) ? -1 : 1;
+                                if (eb != r) continue;
+#pragma unroll
+                                for (int u = 0; u < PB; ++u)
+                                    if (s_psym[p0 + u] == erow && s_w[p0 + u] != 0.0f) c[j][u] += es_;
+                            }
                         }
                     }
                 }
@@ -745,6 +775,10 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
                 finish_bin(r, acc[j], svr[j], prf[j], shp[j]);
             }
         }
+        };
+        if (np <= 4) bins(std::integral_constant<int, 4>{});
+        else if (np <= 8) bins(std::integral_constant<int, 8>{});
+        else bins(std::integral_constant<int, 16>{});
     }
     {   // chi^2 summation schedule (needed at the very end): fetched here, its latency hides behind the barrier
         const int nl = M.pw_leaves;
@@ -1268,6 +1302,22 @@ struct BatchRun {                     // device memory, carried from launch to l
     float csf[FRMC_MAX_MODELS];
 };
 
+// Pair corrections applied ON THE FLY (launches of single-atom proposals).  The delta of proposal x was formed against
+// the positions at the start of the launch; if an earlier proposal y of the launch is accepted and their atoms are in
+// range, x's true delta differs by the four events +h(x_old,y_old) -h(x_old,y_new) -h(x_new,y_old) +h(x_new,y_new).
+// The head writes them per (x, y, grid) into a table; a node that ASSUMES y accepted adds them to the counts it loads
+// (so a chain of predicted acceptances may run through atoms that see each other: in a small dense system, where every
+// pair of atoms is in range, that is the difference between one and five proposals per round), and the commit of
+// several acceptances of one round adds them to the totals.  Acceptances already committed are handled as before: the
+// deltas of the proposals behind them are corrected in place.
+struct CorrEv {
+    int sym;                          // (symmetrised row << 16) | bin, or -1: the event changes no histogram cell
+    int ord;                          // ((ordered cell index) << 3) | overflow code << 1 | (sign > 0); overflow code: 0 none,
+};                                    // 1 counts +1, 2 counts -1 towards the proposal's edge-overflow events
+static const int CORR_PER_PAIR = FRMC_MAX_GRIDS * 4;
+static const int CORR_NODE_MAX = 64;              // events one node applies (<= 15 pairs x 4 on its model's grid)
+static const int CORR_COMMIT_MAX = 240;           // events one commit applies (<= 15 pairs x 4 x grids)
+
 struct BatchDev {                     // by value: the batch's device buffers
     int *bsym[FRMC_MAX_GRIDS];        // [BATCH_MAX_PROPS][nsym*hs]  symmetrised delta per proposal
     int *bdelta[FRMC_MAX_GRIDS];      // [BATCH_MAX_PROPS][2*cells]  ordered delta per proposal
@@ -1289,6 +1339,7 @@ struct BatchDev {                     // by value: the batch's device buffers
     int n_groups;                     // G
     int freq[FRMC_MAX_MODELS];        // scale-factor refit schedule per model (0: none): an evaluation refits when the engine's
     unsigned long long accepted_base; // accepted count at its node (accepted_base + acceptances of this call so far) % freq == 0
+    CorrEv *corr;                     // [BATCH_MAX_PROPS * (BATCH_MAX_PROPS - 1) / 2][FRMC_MAX_GRIDS][4], pair (x, y < x) at x (x - 1) / 2 + y
     int rand_per_proposal;            // 1: rand[i] belongs to proposal i of the call (counter-based contract, fullrmc_b200/rng.py);
                                       // 0: consumed in order, one per worse proposal (the reference's generate_random_float stream)
 };
@@ -1322,6 +1373,9 @@ struct BatchShared {
     float4 fOld[FRMC_MAX_GROUP];               // low / high corner of the box spanned by a moved atom's old and new position
     float4 fNew[FRMC_MAX_GROUP];               // (blocks_far's conventions: periodically reduced coordinates, lo.w = rounding margin)
     float s_pt[BATCH_MAX_GROUPS], s_rand[2 * BATCH_MAX_GROUPS];   // random numbers from the round's first: the walk's, then the plan's
+    unsigned int ev[CORR_NODE_MAX];            // the node's on-the-fly pair corrections (EpiOut::ev)
+    unsigned int ev_bits[32];                  // filter of the node's list, then of the commit's list
+    int n_ev, n_cev;
     float s_csf[FRMC_MAX_MODELS];              // committed scale factor per model as the launch proceeds (refit schedules)
     unsigned int s_cnt_mod[FRMC_MAX_MODELS];   // (accepted count at the start of the launch) % refit frequency, per model
     int in_first[BATCH_MAX_PROPS + 1];         // the launch's BatchIn fields the rounds read (first, share): staged once, so the
@@ -1422,6 +1476,28 @@ __device__ __forceinline__ void batch_hit(float d2, int sign, int same, int slab
             }
         }
     }
+}
+
+// the histogram event of one distance on grid G as batch_hit would register it, as a CorrEv (sign folded in later)
+__device__ __forceinline__ CorrEv corr_event(float d2, int same, int slab, int sym, const GridDev &G, int nEl)
+{
+    CorrEv ev;
+    ev.sym = -1; ev.ord = 0;
+    if (!in_range(d2, G.g)) return ev;
+    const int b = bin_index(d2, G.g);
+    if (b < G.g.hs) {
+        ev.sym = (sym << 16) | b;
+        ev.ord = (int)(((same ? 0 : G.cells) + (long long)slab * G.g.hs + b) << 3);
+        return ev;
+    }
+    ev.ord = 2;                                   // an edge-overflow event (code 1; the caller flips it for "undone" pairs)
+    const long long flat = (long long)slab * G.g.hs + b;
+    if (G.g.spill && flat < G.cells) {            // the reference's unchecked write lands in the next slab
+        const int s2 = (int)(flat / G.g.hs), b2 = (int)(flat - (long long)s2 * G.g.hs);
+        ev.sym = (sym_index(s2 / nEl, s2 % nEl, nEl) << 16) | b2;
+        ev.ord |= (int)(((same ? 0 : G.cells) + flat) << 3);
+    }
+    return ev;
 }
 
 // order-preserving map float -> unsigned (and back): min / max of floats through integer REDUX
@@ -1567,6 +1643,8 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     __syncthreads();
     unsigned long long bar_target = bs.s_bar;
     const int np = in.n_prop, na = in.n_atoms;
+    // every proposal moves one atom: pair corrections between proposals of the launch are applied on the fly (CorrEv)
+    const bool fly = (na == np) && np > 1 && bd.corr != nullptr;
     // ---- (1) clear the per-proposal buffers, load the moved atoms
     for (int gi = 0; gi < gs.n; ++gi) {
         const GridDev &Gd = gs.grid[gi];
@@ -1636,6 +1714,29 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const bool hit = ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) || ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) ||
                          ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) || ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi));
         if (hit) atomicOr(&bs.near[jt], 1u << ju);
+        if (hit && fly && blockIdx.x == 0) {
+            // the four events of the pair per grid (x = the later proposal's atom, y = the earlier one's): +oo -on -no +nn;
+            // overflow events count towards x's total with +1 for the re-done pairs (on, nn) and -1 for the undone (oo, no)
+            const uint32_t mt = __float_as_uint(ot.w), mu = __float_as_uint(ou.w);
+            const int same = (mt >> 8) == (mu >> 8);
+            const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
+            const int slab_ = et * nEl + eu, sym = sym_index(et, eu, nEl);
+            const float d4[4] = {d_oo, d_on, d_no, d_nn};
+            CorrEv *dst = bd.corr + (size_t)(jt * (jt - 1) / 2 + ju) * CORR_PER_PAIR;
+            for (int gi = 0; gi < FRMC_MAX_GRIDS; ++gi)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    CorrEv ev;
+                    ev.sym = -1; ev.ord = 0;
+                    if (gi < gs.n) {
+                        ev = corr_event(d4[c4], same, slab_, sym, gs.grid[gi], nEl);
+                        const bool plus = (c4 == 0 || c4 == 3), redone = (c4 == 1 || c4 == 3);
+                        if (ev.ord & 2) ev.ord = (ev.ord & ~6) | (redone ? 2 : 4);
+                        if (plus) ev.ord |= 1;
+                    }
+                    dst[gi * 4 + c4] = ev;
+                }
+        }
     }
     grid_arrive(bars);
     bar_target += gridDim.x;
@@ -1785,6 +1886,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     for (int mm = 0; mm < FRMC_MAX_MODELS; ++mm) any_freq = any_freq || bd.freq[mm] > 0;
     auto spec_limit = [&](unsigned int accm) {
         int lim = BATCH_MAX_SPEC;
+        if (fly && gs.n >= 3) lim = (gs.n == 3) ? 4 : 3;     // the commit's event list: pairs x 4 x grids <= CORR_COMMIT_MAX
         if (!any_freq) return lim;
         const unsigned int acc = (unsigned int)__popc(accm);
         for (int mm = 0; mm < ms.n; ++mm)
@@ -1817,7 +1919,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const unsigned int acc_pred = __ballot_sync(FULL, lead && dec);
         const unsigned int A_j = acc_pred & below & from_c;         // predicted acceptances in front of j
         const unsigned int sh_j = in_rng ? bs.in_share[j] : 0u, nr_j = in_rng ? bs.near[j] : 0u;
-        const bool fits = !((sh_j & (accm | A_j)) || (nr_j & A_j)) && __popc(A_j) <= max_spec;
+        const bool fits = !((sh_j & (accm | A_j)) || (!fly && (nr_j & A_j))) && __popc(A_j) <= max_spec;
         const unsigned int bad = __ballot_sync(FULL, lead && !fits);
         int chain_end = bad ? __ffs(bad) - 1 : f;
         if (chain_end - c > G) chain_end = c + G;
@@ -1835,7 +1937,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         const unsigned int A_f = acc_pred & from_c & ((f < 32) ? ((1u << f) - 1u) : FULL);
         const unsigned int sh_f = __shfl_sync(FULL, sh_j, f & 31), nr_f = __shfl_sync(FULL, nr_j, f & 31);
         const bool open = (chain_end == f) && (f < np) && (L < G) &&
-                          !((sh_f & (accm | A_f)) || (nr_f & A_f)) && __popc(A_f) <= max_spec;
+                          !((sh_f & (accm | A_f)) || (!fly && (nr_f & A_f))) && __popc(A_f) <= max_spec;
         const int dec_last = __shfl_sync(FULL, dec, (f - 1) & 31);   // predicted decision of the chain's last proposal
         int est_from = chain_end;
         if (open) {
@@ -1912,6 +2014,46 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             eo.res = bd.res + sb * 2 * FRMC_MAX_MODELS;
             eo.terms = ((bd.defer_mask >> m) & 1u) ? bd.bterm[m] + (long long)sb * ms.m[m].n_out : nullptr;
             eo.warm = warm ? 1 : 0;
+            // on-the-fly pair corrections: every pair (x, y) with x in A + {k}, y in A, y < x, atoms in range
+            eo.ev = bs.ev; eo.ev_bits = bs.ev_bits; eo.n_ev = 0;
+            {
+                const unsigned int Aas = bs.slot_A[group];
+                bool any_pair = false;                        // (uniform) does any member of A + {k} see an earlier member of A?
+                if (fly && Aas) {
+                    for (unsigned int xm = Aas | (1u << k); xm; xm &= xm - 1u) {
+                        const int x = __ffs(xm) - 1;
+                        any_pair = any_pair || (bs.near[x] & Aas & ((1u << x) - 1u)) != 0u;
+                    }
+                }
+                if (any_pair) {
+                    __syncthreads();                          // the previous use of the list (this CTA's last node / commit) is over
+                    if (tid < 32) bs.ev_bits[tid] = 0u;
+                    if (tid == 0) bs.n_ev = 0;
+                    __syncthreads();
+                    const int gi = ms.m[m].grid;
+                    // thread = (x slot, y, combo): x runs over the members of A and k itself
+                    const unsigned int X = Aas | (1u << k);
+                    const int nx = __popc(X);
+                    for (int e = tid; e < nx * 32 * 4; e += blockDim.x) {
+                        const int xi = e >> 7, y = (e >> 2) & 31, c4 = e & 3;
+                        int x = 0;
+                        { unsigned int xm = X; for (int q = 0; q < xi; ++q) xm &= xm - 1u; x = __ffs(xm) - 1; }
+                        if (y >= x || !((Aas >> y) & 1u) || !((bs.near[x] >> y) & 1u)) continue;
+                        const int2 raw = __ldcg(reinterpret_cast<const int2 *>(bd.corr + ((size_t)(x * (x - 1) / 2 + y) * CORR_PER_PAIR + gi * 4 + c4)));
+                        CorrEv cv;
+                        cv.sym = raw.x; cv.ord = raw.y;
+                        if (cv.sym < 0) continue;
+                        const int at = atomicAdd(&bs.n_ev, 1);
+                        if (at < CORR_NODE_MAX) {
+                            bs.ev[at] = (unsigned int)cv.sym | ((cv.ord & 1) ? 0u : 0x80000000u);
+                            atomicOr(&bs.ev_bits[((cv.sym & 0xFFFF) & 1023) >> 5], 1u << (cv.sym & 31));
+                        }
+                    }
+                    __syncthreads();
+                    if (bs.n_ev > CORR_NODE_MAX) __trap();   // cannot happen: <= 15 pairs x 4 events
+                    eo.n_ev = bs.n_ev;
+                }
+            }
             eo.refit = 0;
             if (bd.freq[m] > 0) {
                 const unsigned int f = (unsigned int)bd.freq[m];
@@ -2049,7 +2191,43 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             for (unsigned int a = Aset; a; a &= a - 1u) acc_j[n_aj++] = __ffs(a) - 1;
             const bool last_round = (cur >= np) || stopped;
             // does an accepted proposal pair with an atom of an unresolved one?  (every warp finds the same answer)
-            const bool need_bar = __ballot_sync(0xFFFFFFFFu, lane >= cur && lane < np && (bs.near[lane] & Aset)) != 0u;
+            bool need_bar = __ballot_sync(0xFFFFFFFFu, lane >= cur && lane < np && (bs.near[lane] & Aset)) != 0u;
+            // on-the-fly mode: several acceptances of this round may pair with EACH OTHER (their nodes saw the events of
+            // those pairs from the table); the commit adds the same events to the totals and the ordered counts.  Every
+            // CTA gathers the list; entries: sym = grid << 24 | row << 16 | bin, ord = grid << 28 | cell << 3 | codes.
+            CorrEv *clist = reinterpret_cast<CorrEv *>(&bs.pw_scratch[0][0]);      // idle outside the decision phase
+            int n_cev = 0;
+            bool acc_pairs = false;                           // (uniform) do two acceptances of this round see each other?
+            if (fly && (Aset & (Aset - 1u)))
+                for (int x = 0; x < n_aj; ++x) acc_pairs = acc_pairs || (bs.near[acc_j[x]] & Aset & ((1u << acc_j[x]) - 1u)) != 0u;
+            if (acc_pairs) {
+                if (tid < 32) bs.ev_bits[tid] = 0u;
+                if (tid == 0) bs.n_cev = 0;
+                __syncthreads();
+                const int per_x = 32 * gs.n * 4;
+                for (int e = tid; e < n_aj * per_x; e += blockDim.x) {
+                    const int x = acc_j[e / per_x], rem = e % per_x, y = rem / (gs.n * 4), g4 = rem % (gs.n * 4), gi = g4 >> 2;
+                    if (y >= x || !((Aset >> y) & 1u) || !((bs.near[x] >> y) & 1u)) continue;
+                    const int2 raw = __ldcg(reinterpret_cast<const int2 *>(bd.corr + ((size_t)(x * (x - 1) / 2 + y) * CORR_PER_PAIR + g4)));
+                    if (blockIdx.x == 0 && (raw.y & 6))          // edge-overflow events follow the pair they belong to
+                        atomicAdd(&bd.bov[x], (raw.y & 2) ? 1ull : ~0ull);
+                    if (raw.x < 0) continue;
+                    const int at = atomicAdd(&bs.n_cev, 1);
+                    if (at < CORR_COMMIT_MAX) {
+                        clist[at].sym = raw.x | (gi << 24);
+                        clist[at].ord = raw.y | (gi << 28);
+                        const int hs_g = gs.grid[gi].g.hs;
+                        const int csym = ((raw.x >> 16) & 0xFF) * hs_g + (raw.x & 0xFFFF);
+                        atomicOr(&bs.ev_bits[((csym + 977 * gi) & 1023) >> 5], 1u << ((csym + 977 * gi) & 31));
+                        const int cord = (raw.y >> 3) & 0x1FFFFFF;
+                        atomicOr(&bs.ev_bits[((cord + 331 + 977 * gi) & 1023) >> 5], 1u << ((cord + 331 + 977 * gi) & 31));
+                    }
+                }
+                __syncthreads();
+                n_cev = bs.n_cev;
+                if (n_cev > CORR_COMMIT_MAX) __trap();       // spec_limit keeps pairs x 4 x grids within the list
+                if (n_cev > 0) need_bar = true;               // the lazy commit's "pending" set assumes non-interacting acceptances
+            }
             const long long stride = (long long)gridDim.x * blockDim.x;
             const long long gt = (long long)blockIdx.x * blockDim.x + tid;
             const int lb = par * BATCH_MAX_GROUPS + last;    // the evaluation that saw all of them
@@ -2070,6 +2248,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                         int v = 0;
 #pragma unroll
                         for (int x = 0; x <= BATCH_MAX_SPEC; ++x) if (x < n_aj) v += __ldcg(bd.bsym[gi] + (long long)acc_j[x] * ns_ + c);
+                        if (n_cev && ((bs.ev_bits[(((int)c + 977 * gi) & 1023) >> 5] >> (((int)c + 977 * gi) & 31)) & 1u)) {
+                            const int key = (gi << 24) | ((int)(c / Gd.g.hs) << 16) | (int)(c % Gd.g.hs);
+                            for (int e = 0; e < n_cev; ++e) if (clist[e].sym == key) v += (clist[e].ord & 1) ? 1 : -1;
+                        }
                         bo[c] = t0 + v;                                  // every cell: the other buffer may be one commit behind
                         if (last_round && v) bv[c] = t0 + v;             // the launch ends with both buffers equal
                         done = true;
@@ -2078,6 +2260,10 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                         int d = 0;
 #pragma unroll
                         for (int x = 0; x <= BATCH_MAX_SPEC; ++x) if (x < n_aj) d += __ldcg(bd.bdelta[gi] + (long long)acc_j[x] * 2 * Gd.cells + c);
+                        if (n_cev && ((bs.ev_bits[(((int)c + 331 + 977 * gi) & 1023) >> 5] >> (((int)c + 331 + 977 * gi) & 31)) & 1u)) {
+                            for (int e = 0; e < n_cev; ++e)
+                                if (((clist[e].ord >> 3) & 0x1FFFFFF) == (int)c && ((clist[e].ord >> 28) & 3) == gi) d += (clist[e].ord & 1) ? 1 : -1;
+                        }
                         if (d) Gd.counts[c] = (unsigned long long)((long long)c0 + d);
                         done = true;
                     } else c -= 2 * Gd.cells;
@@ -2932,6 +3118,8 @@ static int batch_prepare(frmc_store *s)
     if ((rc = alloc((void **)&bd.tickets, sizeof(unsigned int) * BATCH_MAX_PROPS * (FRMC_MAX_MODELS + 1)))) return rc;
     if ((rc = alloc((void **)&bd.bov, sizeof(unsigned long long) * BATCH_MAX_PROPS))) return rc;
     if ((rc = alloc((void **)&bd.run, sizeof(BatchRun)))) return rc;
+    if (!getenv("FRMC_BATCH_NO_FLY") &&
+        (rc = alloc((void **)&bd.corr, sizeof(CorrEv) * (size_t)(BATCH_MAX_PROPS * (BATCH_MAX_PROPS - 1) / 2) * CORR_PER_PAIR))) return rc;
     if (!s->d_bbars) {
         FRMC_CUDA(cudaMalloc(&s->d_bbars, sizeof(unsigned long long) * 2));
         FRMC_CUDA(cudaMemsetAsync(s->d_bbars, 0, sizeof(unsigned long long) * 2, s->stream));
