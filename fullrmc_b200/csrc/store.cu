@@ -1340,6 +1340,7 @@ struct BatchDev {                     // by value: the batch's device buffers
     int freq[FRMC_MAX_MODELS];        // scale-factor refit schedule per model (0: none): an evaluation refits when the engine's
     unsigned long long accepted_base; // accepted count at its node (accepted_base + acceptances of this call so far) % freq == 0
     CorrEv *corr;                     // [BATCH_MAX_PROPS * (BATCH_MAX_PROPS - 1) / 2][FRMC_MAX_GRIDS][4], pair (x, y < x) at x (x - 1) / 2 + y
+    int debug;                        // FRMC_BATCH_DEBUG: timing experiments only (results are wrong when set)
     int rand_per_proposal;            // 1: rand[i] belongs to proposal i of the call (counter-based contract, fullrmc_b200/rng.py);
                                       // 0: consumed in order, one per worse proposal (the reference's generate_random_float stream)
 };
@@ -1746,13 +1747,26 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     {
         const int T = gridDim.x * blockDim.x;
         const float4 padrec = make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+        // A small store leaves most of the grid idle while each busy thread walks all the moved atoms one after the other
+        // (10^4 records against 64 moved atoms: 2 warps per CTA, 64 distance pairs each).  When the records fill less than
+        // half of the grid, S copies of the pass run side by side, copy s taking the moved atoms t with t % S == s.
+        const int span = (npad + 31) & ~31;
+        const int fit = T / span;
+        const int S = (fit >= 64) ? 64 : (fit >= 32) ? 32 : (fit >= 16) ? 16 : (fit >= 8) ? 8 : (fit >= 4) ? 4 : (fit >= 2) ? 2 : 1;
+        const int gid = blockIdx.x * blockDim.x + tid;
+        const int sub = (S > 1) ? gid / span : 0;
+        const int pbase = (S > 1) ? ((sub < S) ? gid - sub * span : npad) : gid;
+        const unsigned long long every = (S == 1) ? ~0ull : (S == 2) ? 0x5555555555555555ull : (S == 4) ? 0x1111111111111111ull :
+                                         (S == 8) ? 0x0101010101010101ull : (S == 16) ? 0x0001000100010001ull :
+                                         (S == 32) ? 0x0000000100000001ull : 1ull;
+        const unsigned long long sub_mask = every << (sub & (S - 1));
         float4 nxt[DELTA_UNROLL];
         {
-            const int p0 = blockIdx.x * blockDim.x + tid;
+            const int p0 = pbase;
 #pragma unroll
             for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
         }
-        for (int p0 = blockIdx.x * blockDim.x + tid; p0 < npad; p0 += DELTA_UNROLL * T) {
+        for (int p0 = pbase; p0 < npad; p0 += DELTA_UNROLL * T) {
             float4 a[DELTA_UNROLL];
 #pragma unroll
             for (int u = 0; u < DELTA_UNROLL; ++u) a[u] = nxt[u];
@@ -1799,6 +1813,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                 bool moved_here = false;                 // this record is one of the batch's moved atoms (rare; its
                                                          // own old position lies in the box, so it is in near_mask)
                 for (unsigned long long mk = near_mask; mk; mk &= mk - 1ull) moved_here |= (bs.sPos[__ffsll((long long)mk) - 1] == p);
+                near_mask &= sub_mask;                   // this copy's share of the moved atoms
                 const int ej = mj & 0xFF;
                 for (unsigned long long mk = near_mask; mk; mk &= mk - 1ull) {
                     const int t = __ffsll((long long)mk) - 1;
@@ -2200,7 +2215,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             bool acc_pairs = false;                           // (uniform) do two acceptances of this round see each other?
             if (fly && (Aset & (Aset - 1u)))
                 for (int x = 0; x < n_aj; ++x) acc_pairs = acc_pairs || (bs.near[acc_j[x]] & Aset & ((1u << acc_j[x]) - 1u)) != 0u;
-            if (acc_pairs) {
+            if (acc_pairs && !(bd.debug & 2)) {
                 if (tid < 32) bs.ev_bits[tid] = 0u;
                 if (tid == 0) bs.n_cev = 0;
                 __syncthreads();
@@ -2236,7 +2251,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             long long n_items_c = 0;
             for (int gi = 0; gi < gs.n; ++gi) n_items_c += (long long)gs.grid[gi].nsym * gs.grid[gi].g.hs + 2 * gs.grid[gi].cells;
             for (int mm = 0; mm < ms.n; ++mm) n_items_c += ms.m[mm].n_out;
-            for (long long it0 = gt; it0 < n_items_c; it0 += stride) {
+            for (long long it0 = gt; it0 < ((bd.debug & 4) ? 0 : n_items_c); it0 += stride) {
                 long long c = it0;
                 bool done = false;
                 for (int gi = 0; gi < gs.n && !done; ++gi) {
@@ -2286,12 +2301,21 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             }
             // pair (t of an unresolved proposal, u of an accepted one): the delta pass paired t with u's OLD position.
             // Proposals resolved in this round need none: their nodes had no such pair (bs.near).
-            if (need_bar) {
+            if (need_bar && !(bd.debug & 1)) {
+                // One unit of work = (accepted atom u, unresolved atom t, one of the four old/new combinations).  The units
+                // are dealt to lane 0 of consecutive WARPS of the whole grid (unit w -> warp w): a few hundred units finish in
+                // the time of one (they used to sit in the first lanes of CTA 0, one after the other).
                 const int later0 = bs.in_first[cur];                // atoms are listed in proposal order
+                const int n_later = na - later0;
+                const long long gw = gt >> 5, n_warps = stride >> 5;
+                long long base_u = 0;
                 for (int x = 0; x < n_aj; ++x) {
                     const int a0 = bs.in_first[acc_j[x]], a1 = bs.in_first[acc_j[x] + 1];
-                    const long long n_items = (long long)(na - later0) * (a1 - a0);
-                    for (long long it = gt; it < n_items; it += stride) {
+                    const long long n_units = (long long)n_later * (a1 - a0) * 4;
+                    if (lane == 0)
+                    for (long long w = gw - base_u % n_warps + ((gw < base_u % n_warps) ? n_warps : 0); w < n_units; w += n_warps) {
+                        const int c4 = (int)(w & 3);
+                        const long long it = w >> 2;
                         const int t = later0 + (int)(it / (a1 - a0)), u = a0 + (int)(it % (a1 - a0));
                         const int j2 = bs.sProp[t];
                         if (!((bs.near[j2] >> acc_j[x]) & 1u)) continue;         // no pair in range (the common case)
@@ -2301,17 +2325,15 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
                         const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
                         const int slab_ = et * nEl + eu;
                         const int sym = sym_index(et, eu, nEl);
-                        const float d_oo = dist2<MODE>(ot.x, ot.y, ot.z, ou.x, ou.y, ou.z, L);
-                        const float d_on = dist2<MODE>(ot.x, ot.y, ot.z, nu.x, nu.y, nu.z, L);
-                        const float d_no = dist2<MODE>(nt.x, nt.y, nt.z, ou.x, ou.y, ou.z, L);
-                        const float d_nn = dist2<MODE>(nt.x, nt.y, nt.z, nu.x, nu.y, nu.z, L);
-                        unsigned long long ov_undone = 0, ov_redone = 0;   // edge-overflow events follow the pairs they belong to
-                        if ((d_oo >= gs.t2lo) && (d_oo < gs.t2hi)) batch_hit(d_oo, +1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo -1 at (old, old)
-                        if ((d_on >= gs.t2lo) && (d_on < gs.t2hi)) batch_hit(d_on, -1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                        if ((d_no >= gs.t2lo) && (d_no < gs.t2hi)) batch_hit(d_no, -1, same, slab_, sym, j2, gs, bd, nEl, ov_undone);   // undo +1 at (new, old)
-                        if ((d_nn >= gs.t2lo) && (d_nn < gs.t2hi)) batch_hit(d_nn, +1, same, slab_, sym, j2, gs, bd, nEl, ov_redone);
-                        if (ov_redone != ov_undone) atomicAdd(&bd.bov[j2], ov_redone - ov_undone);   // modulo 2^64: the sum stays the true count
+                        // c4: 0 (old, old) undo -1 | 1 (old, new) redo -1 | 2 (new, old) undo +1 | 3 (new, new) redo +1
+                        const float4 pt = (c4 & 2) ? nt : ot, pu = (c4 & 1) ? nu : ou;
+                        const float d2 = dist2<MODE>(pt.x, pt.y, pt.z, pu.x, pu.y, pu.z, L);
+                        if (!((d2 >= gs.t2lo) && (d2 < gs.t2hi))) continue;
+                        unsigned long long ov = 0;                     // edge-overflow events follow the pairs they belong to
+                        batch_hit(d2, (c4 == 0 || c4 == 3) ? +1 : -1, same, slab_, sym, j2, gs, bd, nEl, ov);
+                        if (ov) atomicAdd(&bd.bov[j2], (c4 & 1) ? ov : (0ull - ov));   // re-done pairs count, undone ones are taken back (modulo 2^64)
                     }
+                    base_u += n_units;
                 }
             }
             BATCH_STAMP(4 + 5 * (rounds - 1) + 3);       // CTA 0's share of the commit done
@@ -3129,6 +3151,7 @@ static int batch_prepare(frmc_store *s)
     bd.n_groups = std::max(1, std::min(BATCH_MAX_GROUPS, s->ctx->sm_count / std::max(1, s->epi_map.n)));
     if (const char *e = getenv("FRMC_BATCH_GROUPS")) bd.n_groups = std::max(1, std::min(bd.n_groups, atoi(e)));
     bd.defer_mask = s->batch_defer_mask;
+    bd.debug = getenv("FRMC_BATCH_DEBUG") ? atoi(getenv("FRMC_BATCH_DEBUG")) : 0;
     s->batch_ready = true;
     return FRMC_OK;
 }
