@@ -12,6 +12,8 @@ FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
        -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
        -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -fno-fast-math)
 if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi
+if [ -n "${FRMC_EXTRA_FLAGS:-}" ]; then FLAGS+=(${FRMC_EXTRA_FLAGS}); fi   # experiments (e.g. -DFRMC_X=1)
+OUT="${FRMC_OUT_DIR:-$OUT}"; mkdir -p "$OUT"
 OBJS=()
 PIDS=()
 for f in common stateless fullhist devlayout multigpu store atomdist coordnum storedist; do

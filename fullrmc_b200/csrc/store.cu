@@ -211,6 +211,17 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
     float4 *sOld = sh.sOld, *sNew = sh.sNew;
     int *sPos = sh.sPos;
     const int k = in.k;
+    unsigned long long ov = 0;
+    const int T = gridDim.x * blockDim.x;
+    // double-buffered: the DELTA_UNROLL loads of the next batch are in flight while this batch is processed.  The first
+    // batch is requested BEFORE the moved atoms are staged: the two L2 round trips overlap.
+    const float4 padrec = make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
+    float4 nxt[DELTA_UNROLL];
+    {
+        const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
+    }
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const int p = in.pos[t];
         const float4 o = __ldcg(atoms + p);
@@ -220,16 +231,6 @@ __device__ __forceinline__ void delta_body(DeltaShared &sh, const float4 *__rest
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) prop->k = k;
     __syncthreads();
-    unsigned long long ov = 0;
-    const int T = gridDim.x * blockDim.x;
-    // double-buffered: the DELTA_UNROLL loads of the next batch are in flight while this batch is processed
-    const float4 padrec = make_float4(0.f, 0.f, 0.f, __uint_as_float(PAD_META));
-    float4 nxt[DELTA_UNROLL];
-    {
-        const int p0 = blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-        for (int u = 0; u < DELTA_UNROLL; ++u) { const int p = p0 + u * T; nxt[u] = (p < npad) ? __ldcg(atoms + p) : padrec; }
-    }
     for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < npad; p0 += DELTA_UNROLL * T) {
         float4 a[DELTA_UNROLL];
 #pragma unroll
@@ -777,7 +778,6 @@ __device__ __forceinline__ void epilogue_run(EpiShared &es, float *epi_smem, con
         }
         };
         if (np <= 4) bins(std::integral_constant<int, 4>{});
-        else if (np <= 8) bins(std::integral_constant<int, 8>{});
         else bins(std::integral_constant<int, 16>{});
     }
     {   // chi^2 summation schedule (needed at the very end): fetched here, its latency hides behind the barrier
@@ -1609,7 +1609,7 @@ __global__ void generate_batch_kernel(const GenParams gp, BatchRun *__restrict__
     }
 }
 
-template <int MODE, bool GEN>
+template <int MODE, bool GEN, bool FLYT>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
 batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ BatchIn in_host, Lattice L, GridSet gs, int nEl, const ModelSet ms,
              const EpiMap em, const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars,
@@ -1645,7 +1645,9 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     unsigned long long bar_target = bs.s_bar;
     const int np = in.n_prop, na = in.n_atoms;
     // every proposal moves one atom: pair corrections between proposals of the launch are applied on the fly (CorrEv)
-    const bool fly = (na == np) && np > 1 && bd.corr != nullptr;
+    // (FLYT is a template parameter: the host leaves the machinery out for large sparse systems, where two proposals of
+    // a launch hardly ever see each other and the leaner kernel is a few percent faster)
+    const bool fly = FLYT && (na == np) && np > 1 && bd.corr != nullptr;
     // ---- (1) clear the per-proposal buffers, load the moved atoms
     for (int gi = 0; gi < gs.n; ++gi) {
         const GridDev &Gd = gs.grid[gi];
@@ -1722,10 +1724,11 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
             const int same = (mt >> 8) == (mu >> 8);
             const int et = (int)(mt & 0xFF), eu = (int)(mu & 0xFF);
             const int slab_ = et * nEl + eu, sym = sym_index(et, eu, nEl);
-            const float d4[4] = {d_oo, d_on, d_no, d_nn};
+            const float d4[4] = {d_oo, d_on, d_no, d_nn};       // (rolled loops below: this is cold code, keep it small)
             CorrEv *dst = bd.corr + (size_t)(jt * (jt - 1) / 2 + ju) * CORR_PER_PAIR;
+#pragma unroll 1
             for (int gi = 0; gi < FRMC_MAX_GRIDS; ++gi)
-#pragma unroll
+#pragma unroll 1
                 for (int c4 = 0; c4 < 4; ++c4) {
                     CorrEv ev;
                     ev.sym = -1; ev.ord = 0;
@@ -2455,6 +2458,7 @@ struct frmc_store {
     // runs of proposals resolved on the device (batch_kernel)
     bool batch_ok = false;           // checked in sync_models: resident S(Q) slabs, no refit schedule, co-residency
     bool batch_ready = false;        // buffers below match the current grids and models
+    bool batch_fly = true;           // launches use the on-the-fly pair corrections (batch_prepare: dense enough to pay)
     unsigned int batch_defer_mask = 0u;   // sync_models: models whose chi2 is summed after the grid barrier
     BatchDev bdev;
     std::vector<void *> batch_owned;
@@ -2693,7 +2697,8 @@ static int sync_models(frmc_store *s)
             cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->batch_ok = false; \
         } while (0)
-#define BATCH_ATTR(M) do { auto k0 = batch_kernel<M, false>; auto k1 = batch_kernel<M, true>; BATCH_ATTR1(k0); BATCH_ATTR1(k1); } while (0)
+#define BATCH_ATTR(M) do { auto k0 = batch_kernel<M, false, false>; auto k1 = batch_kernel<M, true, false>; BATCH_ATTR1(k0); BATCH_ATTR1(k1); \
+                           auto k2 = batch_kernel<M, false, true>; auto k3 = batch_kernel<M, true, true>; BATCH_ATTR1(k2); BATCH_ATTR1(k3); } while (0)
         BATCH_ATTR(MODE_IBC); BATCH_ATTR(MODE_ORTHO_FAST); BATCH_ATTR(MODE_TRI_FAST); BATCH_ATTR(MODE_ORTHO_GEN); BATCH_ATTR(MODE_TRI_GEN);
 #undef BATCH_ATTR1
 #undef BATCH_ATTR
@@ -3152,6 +3157,25 @@ static int batch_prepare(frmc_store *s)
     if (const char *e = getenv("FRMC_BATCH_GROUPS")) bd.n_groups = std::max(1, std::min(bd.n_groups, atoi(e)));
     bd.defer_mask = s->batch_defer_mask;
     bd.debug = getenv("FRMC_BATCH_DEBUG") ? atoi(getenv("FRMC_BATCH_DEBUG")) : 0;
+    {
+        // On-the-fly pair corrections pay when proposals of one launch see each other: expected number of in-range pairs
+        // among 32 atoms placed at random = 496 x (sphere of the widest window) / (volume of the system).
+        double rmax2 = 0.0;
+        for (auto &g : s->grids) rmax2 = std::max(rmax2, (double)g.dev.g.t2max);
+        const double r = sqrt(std::max(rmax2, 0.0));
+        double vol;
+        if (s->isPBC) {
+            const float *b = s->L.b;
+            vol = fabs((double)b[0] * ((double)b[4] * b[8] - (double)b[5] * b[7]) - (double)b[1] * ((double)b[3] * b[8] - (double)b[5] * b[6]) +
+                       (double)b[2] * ((double)b[3] * b[7] - (double)b[4] * b[6]));
+        } else {
+            vol = 1.0;
+            for (int c = 0; c < 3; ++c) vol *= std::max(1e-3, (double)s->hi[c] - (double)s->lo[c]);
+        }
+        const double expected = 496.0 * (4.0 / 3.0) * 3.14159265358979 * r * r * r / std::max(vol, 1e-30);
+        s->batch_fly = bd.corr != nullptr && !(expected < 4.0);
+        if (const char *e = getenv("FRMC_BATCH_FLY")) s->batch_fly = bd.corr != nullptr && atoi(e) != 0;
+    }
     s->batch_ready = true;
     return FRMC_OK;
 }
@@ -3186,8 +3210,9 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
     float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
     void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
                     &in_dev, &gen, &real};
-    cudaError_t e = cudaLaunchCooperativeKernel(generated ? (const void *)batch_kernel<MODE, true> : (const void *)batch_kernel<MODE, false>,
-                                                dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS), args, s->epi_smem, s->stream);
+    const void *kern = generated ? (s->batch_fly ? (const void *)batch_kernel<MODE, true, true> : (const void *)batch_kernel<MODE, true, false>)
+                                 : (s->batch_fly ? (const void *)batch_kernel<MODE, false, true> : (const void *)batch_kernel<MODE, false, false>);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS), args, s->epi_smem, s->stream);
     if (e != cudaSuccess) {
         set_error("cooperative launch of the batch kernel failed: %s", cudaGetErrorString(e));
         return FRMC_ECUDA;
