@@ -1,134 +1,141 @@
-"""Device-backed mirror of ``AtomicCoordinationNumberConstraint``'s five methods.
+"""Coordination-number constraint on the CUDA counting kernels.
 
-Reference class: Constraints/AtomicCoordinationConstraints.py.  State, method names and arithmetic follow it:
+What the reference's ``AtomicCoordinationNumberConstraint`` (Constraints/AtomicCoordinationConstraints.py) keeps and
+computes, expressed for this backend:
 
-* data = float32 [number of definitions]: per definition the number of (core, shell) neighbour pairs inside the shell,
-  i.e. the whole-system count of ``all_atoms_coord_number_coords`` halved, because every pair is met from both of its
-  ends (:491-505);
-* a move's contribution is ``multi_atoms_coord_number_coords`` of the moved atoms before and after (:519-577), and the
-  data after the move is ``data - before + after`` (:575);
-* standardError = sum over the definitions of ``weight * (min - CN)`` or ``weight * (CN - max)`` where the mean
-  coordination number ``CN = data / number of core atoms`` lies outside ``[min, max]`` (:404-461);
-* accept_move / reject_move commit or drop the staged data (:580-612).
+* ``data`` -- float32, one entry per shell definition: the number of (core, shell) neighbour pairs of the whole system.
+  The whole-system count meets every pair from both ends, hence the halving (:491-505).
+* a move changes ``data`` by the counts of the moved atoms after the move minus their counts before it (:519-577).
+* the standard error penalises the MEAN coordination number ``data / number of core atoms`` of a definition for lying
+  outside ``[minAtoms, maxAtoms]``, linearly and weighted, summed over the definitions in order in float32 (:404-461).
 
-The counting functions are ``fullrmc_b200.Core.atomic_coordination`` (CUDA, bit-identical to the reference's Cython);
-this first version is stateless -- the coordinates travel with every call -- like the reference's own functions.
+The engine-facing protocol (``compute_data`` / ``compute_before_move`` / ``compute_after_move`` / ``accept_move`` /
+``reject_move``; Core/Constraint.py:732-748) is kept, with one staged move at a time.  The counts come from
+``fullrmc_b200.Core.atomic_coordination`` (one launch per call over a flat task table, bit-identical to the reference's
+Cython loops); coordinates travel with every call, like the reference's own functions.
 """
+import collections
+
 import numpy as np
 
 FLOAT_TYPE = np.float32
 INT_TYPE = np.int32
 
+_StagedMove = collections.namedtuple("_StagedMove", "indexes before after data error")
+
+
+def _membership(lists, n_atoms):
+    """per atom the definitions whose list names it, in definition order (what the counting kernels' task builder wants)"""
+    out = [[] for _ in range(n_atoms)]
+    for d, atoms in enumerate(lists):
+        for a in atoms:
+            out[a].append(d)
+    return out
+
 
 class DeviceAtomicCoordinationNumberConstraint(object):
     """:Parameters:
-        #. boxCoordinates, basisVectors, isPBC: the engine arrays (boxCoordinates is read at every call; compute_after_move
-           writes the moved coordinates into it and restores them, as the reference does, :555-572).
-        #. coresIndexes, shellsIndexes, lowerShells, upperShells, minAtoms, maxAtoms, weights: what the reference derives
-           in set_coordination_number_definition (:242-420): per definition the sorted int32 core and shell atom lists,
-           the shell bounds, the allowed range of the mean coordination number and the weight.
+        #. boxCoordinates, basisVectors, isPBC: the engine arrays.  boxCoordinates is read at every call and never
+           written: the after-move counts are taken on a patched copy.
+        #. coresIndexes, shellsIndexes, lowerShells, upperShells, minAtoms, maxAtoms, weights: per definition the sorted
+           int32 core and shell atom lists, the shell bounds, the allowed range of the mean coordination number and
+           the weight -- what set_coordination_number_definition derives (:242-420).
     """
 
     def __init__(self, boxCoordinates, basisVectors, isPBC, coresIndexes, shellsIndexes, lowerShells, upperShells, minAtoms,
                  maxAtoms, weights=None, kernels=None):
         if kernels is None:
             from .Core import atomic_coordination as kernels
-        self._kernels = kernels
+        self._count = kernels
         self.boxCoordinates = boxCoordinates
         self.basisVectors = np.ascontiguousarray(basisVectors, dtype=FLOAT_TYPE)
         self.isPBC = bool(isPBC)
-        self.coresIndexes = [np.ascontiguousarray(c, dtype=INT_TYPE) for c in coresIndexes]
-        self.shellsIndexes = [np.ascontiguousarray(s, dtype=INT_TYPE) for s in shellsIndexes]
-        ndef = len(self.coresIndexes)
-        self.lowerShells = [FLOAT_TYPE(x) for x in lowerShells]
-        self.upperShells = [FLOAT_TYPE(x) for x in upperShells]
-        self.minAtoms = [FLOAT_TYPE(x) for x in minAtoms]
-        self.maxAtoms = [FLOAT_TYPE(x) for x in maxAtoms]
-        self.weights = np.ones(ndef, FLOAT_TYPE) if weights is None else np.array(weights, dtype=FLOAT_TYPE)
-        assert len(self.shellsIndexes) == ndef and len(self.lowerShells) == ndef and len(self.upperShells) == ndef
-        assert len(self.minAtoms) == ndef and len(self.maxAtoms) == ndef and self.weights.shape == (ndef,)
-        # per atom: the definitions it is a core of / in the shell of (:385-400)
-        n = boxCoordinates.shape[0]
-        self.asCoreDefIdxs = [[] for _ in range(n)]
-        self.inShellDefIdxs = [[] for _ in range(n)]
-        for defIdx in range(ndef):
-            for atIdx in self.coresIndexes[defIdx]:
-                self.asCoreDefIdxs[atIdx].append(defIdx)
-            for atIdx in self.shellsIndexes[defIdx]:
-                self.inShellDefIdxs[atIdx].append(defIdx)
-        self.numberOfCores = np.array([len(c) for c in self.coresIndexes], dtype=FLOAT_TYPE)
+        as_lists = lambda seq: [np.ascontiguousarray(x, dtype=INT_TYPE) for x in seq]
+        as_f32 = lambda seq: np.array([FLOAT_TYPE(x) for x in seq], dtype=FLOAT_TYPE)
+        self.coresIndexes, self.shellsIndexes = as_lists(coresIndexes), as_lists(shellsIndexes)
+        n_def = len(self.coresIndexes)
+        self.lowerShells, self.upperShells = list(as_f32(lowerShells)), list(as_f32(upperShells))
+        self.minAtoms, self.maxAtoms = as_f32(minAtoms), as_f32(maxAtoms)
+        self.weights = np.ones(n_def, FLOAT_TYPE) if weights is None else as_f32(weights)
+        sizes = {len(self.shellsIndexes), len(self.lowerShells), len(self.upperShells), self.minAtoms.shape[0],
+                 self.maxAtoms.shape[0], self.weights.shape[0]}
+        if sizes != {n_def}:
+            raise ValueError("every per-definition argument needs one entry per shell definition (%d)" % n_def)
+        n_atoms = boxCoordinates.shape[0]
+        self.asCoreDefIdxs = _membership(self.coresIndexes, n_atoms)
+        self.inShellDefIdxs = _membership(self.shellsIndexes, n_atoms)
+        self.numberOfCores = np.array([c.shape[0] for c in self.coresIndexes], dtype=FLOAT_TYPE)
         self.data = None
         self.standardError = None
-        self.afterMoveStandardError = None
-        self.activeAtomsDataBeforeMove = None
-        self.activeAtomsDataAfterMove = None
-        self._dataAfterMove = None
+        self._staged = None
         self.tried = 0
         self.accepted = 0
 
-    def _lists(self):
+    # ---------------------------------------------------------------- counting
+    def _definitions(self):
         return dict(basis=self.basisVectors, isPBC=self.isPBC, coresIndexes=self.coresIndexes, shellsIndexes=self.shellsIndexes,
                     lowerShells=self.lowerShells, upperShells=self.upperShells, asCoreDefIdxs=self.asCoreDefIdxs,
                     inShellDefIdxs=self.inShellDefIdxs, ncores=1)
 
-    def compute_standard_error(self, data):
-        """:404-461, term by term (numpy float32 scalars, so the sum runs in float32 as the reference's does)"""
-        coordNum = data / self.numberOfCores
-        StdErr = 0.
-        for idx, cn in enumerate(coordNum):
-            if cn < self.minAtoms[idx]:
-                StdErr += self.weights[idx] * (self.minAtoms[idx] - cn)
-            elif cn > self.maxAtoms[idx]:
-                StdErr += self.weights[idx] * (cn - self.maxAtoms[idx])
-        return StdErr
+    def _counts_of(self, indexes, coordinates):
+        """neighbour pairs the listed atoms take part in, per definition"""
+        out = np.zeros(len(self.coresIndexes), dtype=FLOAT_TYPE)
+        self._count.multi_atoms_coord_number_coords(indexes=indexes, boxCoords=coordinates, coordNumData=out, **self._definitions())
+        return out
 
+    def compute_standard_error(self, data):
+        """weighted linear penalty of the mean coordination numbers outside their ranges; terms added in definition order
+        in float32 (a definition inside its range adds an exact zero), which is the order of the reference's loop"""
+        mean = (np.asarray(data, dtype=FLOAT_TYPE) / self.numberOfCores).astype(FLOAT_TYPE)
+        below, above = mean < self.minAtoms, mean > self.maxAtoms
+        terms = np.zeros(mean.shape[0], dtype=FLOAT_TYPE)
+        terms[below] = (self.weights * (self.minAtoms - mean))[below]
+        only_above = above & ~below
+        terms[only_above] = (self.weights * (mean - self.maxAtoms))[only_above]
+        return FLOAT_TYPE(np.add.accumulate(terms, dtype=FLOAT_TYPE)[-1]) if terms.shape[0] else FLOAT_TYPE(0.0)
+
+    # ---------------------------------------------------------------- the engine-facing protocol
     def compute_data(self, update=True):
-        """:473-517"""
-        coordNumData = np.zeros(len(self.coresIndexes), dtype=FLOAT_TYPE)
-        self._kernels.all_atoms_coord_number_coords(boxCoords=self.boxCoordinates, coordNumData=coordNumData, **self._lists())
-        coordNumData /= FLOAT_TYPE(2.)
-        stdError = self.compute_standard_error(data=coordNumData)
+        pairs = np.zeros(len(self.coresIndexes), dtype=FLOAT_TYPE)
+        self._count.all_atoms_coord_number_coords(boxCoords=self.boxCoordinates, coordNumData=pairs, **self._definitions())
+        pairs /= FLOAT_TYPE(2.)                              # every neighbour pair was met from both of its atoms
+        error = self.compute_standard_error(pairs)
         if update:
-            self.data = coordNumData
-            self.activeAtomsDataBeforeMove = None
-            self.activeAtomsDataAfterMove = None
-            self.standardError = stdError
-        return coordNumData, stdError
+            self.data, self.standardError, self._staged = pairs, error, None
+        return pairs, error
 
     def compute_before_move(self, realIndexes, relativeIndexes):
-        """:519-543"""
-        beforeMoveData = np.zeros(self.data.shape, dtype=self.data.dtype)
-        self._kernels.multi_atoms_coord_number_coords(indexes=np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE),
-                                                      boxCoords=self.boxCoordinates, coordNumData=beforeMoveData, **self._lists())
-        self.activeAtomsDataBeforeMove = beforeMoveData
-        self.activeAtomsDataAfterMove = None
+        idx = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+        self._staged = _StagedMove(idx, self._counts_of(idx, self.boxCoordinates), None, None, None)
 
     def compute_after_move(self, realIndexes, relativeIndexes, movedBoxCoordinates):
-        """:545-578"""
-        boxData = np.array(self.boxCoordinates[relativeIndexes], dtype=FLOAT_TYPE)
-        self.boxCoordinates[relativeIndexes] = movedBoxCoordinates
-        afterMoveData = np.zeros(self.data.shape, dtype=self.data.dtype)
-        try:
-            self._kernels.multi_atoms_coord_number_coords(indexes=np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE),
-                                                          boxCoords=self.boxCoordinates, coordNumData=afterMoveData, **self._lists())
-        finally:
-            self.boxCoordinates[relativeIndexes] = boxData
-        self.activeAtomsDataAfterMove = afterMoveData
-        self._dataAfterMove = self.data - self.activeAtomsDataBeforeMove + self.activeAtomsDataAfterMove
-        self.afterMoveStandardError = self.compute_standard_error(data=self._dataAfterMove)
+        idx = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+        if self._staged is None or not np.array_equal(self._staged.indexes, idx):
+            self.compute_before_move(realIndexes, relativeIndexes)
+        patched = np.array(self.boxCoordinates, dtype=FLOAT_TYPE)
+        patched[idx] = movedBoxCoordinates
+        after = self._counts_of(idx, patched)
+        data = self.data - self._staged.before + after
+        self._staged = self._staged._replace(after=after, data=data, error=self.compute_standard_error(data))
         self.tried += 1
 
     def accept_move(self, realIndexes, relativeIndexes):
-        """:580-598"""
-        self.data = self._dataAfterMove
-        self.activeAtomsDataBeforeMove = None
-        self.activeAtomsDataAfterMove = None
-        self.standardError = self.afterMoveStandardError
-        self.afterMoveStandardError = None
+        self.data, self.standardError = self._staged.data, self._staged.error
+        self._staged = None
         self.accepted += 1
 
     def reject_move(self, realIndexes, relativeIndexes):
-        """:600-612"""
-        self.activeAtomsDataBeforeMove = None
-        self.activeAtomsDataAfterMove = None
-        self.afterMoveStandardError = None
+        self._staged = None
+
+    # ---------------------------------------------------------------- the reference's attribute names for the staged move
+    @property
+    def afterMoveStandardError(self):
+        return None if self._staged is None else self._staged.error
+
+    @property
+    def activeAtomsDataBeforeMove(self):
+        return None if self._staged is None else self._staged.before
+
+    @property
+    def activeAtomsDataAfterMove(self):
+        return None if self._staged is None else self._staged.after

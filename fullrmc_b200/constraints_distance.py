@@ -89,14 +89,13 @@ class DeviceMolecularDistanceConstraint(object):
         return {"number": numberM - numberF, "distanceSum": sumM - sumF}
 
     def _get_constraint_value(self, data=None):
-        """:415-428"""
+        """per type pair the mean reduced distance of the counted pairs: both orderings of the pair summed, then
+        sum / count where anything was counted (:415-428)"""
         data = self.data if data is None else data
-        idi, idj = self.typePairsIndex[:, 0], self.typePairsIndex[:, 1]
-        numbers = (data["number"][idi, idj] + data["number"][idj, idi]).reshape(-1)
-        distances = (data["distanceSum"][idi, idj] + data["distanceSum"][idj, idi]).reshape(-1)
-        nonZero = np.where(numbers)
-        distances[nonZero] /= numbers[nonZero]
-        return distances
+        first, second = self.typePairsIndex[:, 0], self.typePairsIndex[:, 1]
+        both = lambda a: (a[first, second] + a[second, first]).reshape(-1)
+        counts, sums = both(data["number"]), both(data["distanceSum"])
+        return np.divide(sums, counts, out=sums.copy(), where=counts != 0)
 
     def _compute_standard_error(self, distances):
         return FLOAT_TYPE(np.sum(distances))

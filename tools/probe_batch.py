@@ -1,7 +1,8 @@
 """Debug probe: phase timeline of the batch kernel (globaltimer stamps of CTA 0, last launch of a run).
 usage: FRMC_BATCH_STAMPS=1 python tools/probe_batch.py [cfg4|cfg5] [n_proposals] [tolerance]"""
 import os, sys, time
-os.environ.setdefault("FRMC_BATCH_STAMPS", "1")
+if not os.environ.get("FRMC_NO_STAMPS"):
+    os.environ.setdefault("FRMC_BATCH_STAMPS", "1")
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fullrmc_b200 import synthetic, _lib as L
@@ -37,6 +38,8 @@ m = n - 200
 launches, rounds, props = store.batch_stats()
 print("%s: %d proposals, %d accepted, device %.2f us/eval, wall %.2f us/eval, %d launches, %d rounds (all runs)" % (
     which, m, int((out["decisions"] > 0).sum()), 1e3 * out["device_ms"] / m, 1e6 * wall / m, launches, rounds))
+if os.environ.get("FRMC_NO_STAMPS"):
+    store.close(); sys.exit(0)
 st = np.zeros(4 + 5 * 64 + 64 * 128, np.int64)
 L.check(store._lib.frmc_store_batch_stamps(store._handle, st.ctypes.data_as(L.c_i64p), st.shape[0]), "stamps")
 print("last launch: clear %.2f us, delta pass %.2f us, rounds+end %.2f us, total %.2f us" % (

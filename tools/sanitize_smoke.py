@@ -54,5 +54,23 @@ moved = (s.boxCoords[idx] + rng.normal(0, 0.01, (n, 3))).astype(np.float32)
 total = np.float32(np.sum(st.committed_chi2()[:2], dtype=np.float32))
 out = st.run_batch(idx, moved, total, rng.random(n).astype(np.float32), tolerance=0.3)
 print("batch", int((out["decisions"] > 0).sum()), "accepted of", n, "in", st.batch_stats()[1], "rounds")
+# steps generated on the device (generate_batch_kernel + batch_kernel<GEN>), on-the-fly pair corrections (dense launch)
+b64 = s.basis.astype(np.float64)
+st.set_groups(None)
+st.set_real_coords((st.get_coords().astype(np.float64) @ b64).astype(np.float32), np.linalg.inv(b64).astype(np.float32))
+total = np.float32(np.sum(st.committed_chi2()[:2], dtype=np.float32))
+out = st.run_generated(96, 5, 0, 0.3, total)
+print("generated", int((out["decisions"] > 0).sum()), "accepted of 96")
+# atom removal (amputation evaluation, accept, constants), the distance pass on the store
+chi = st.propose_amputation(17)
+st.accept_amputation()
+chi = st.propose_amputation(40); st.reject_amputation()
+print("amputation", chi, st.numberOfAtoms)
 st.close()
+s2 = synthetic.random_system(9000, 3, np.diag([70.0, 66.0, 72.0]).astype(np.float32), n_elements=3, molecule_size=4)
+with DeviceStore(s2.boxCoords, s2.basis, True, s2.moleculeIndex, s2.elementIndex, 3) as st2:
+    cid = st2.distance_add(s2.elementIndex, 3, np.zeros((3, 3, 1), np.float32), np.full((3, 3, 1), 2.5, np.float32), reduceDistanceToUpper=True)
+    idx = np.arange(8, 12, dtype=np.int32)
+    counts, sums = st2.distance_move(cid, idx, (s2.boxCoords[idx] + np.float32(0.01)).astype(np.float32))
+    print("store distance pass", int(counts.sum()))
 print("done")
