@@ -8,7 +8,7 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../lib"
 mkdir -p "$OUT"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -split-compile 0
+FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
        -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
        -Xcompiler -fPIC -Xcompiler -O2 -Xcompiler -fno-fast-math)
 if [ "${FRMC_PTXAS_V:-0}" = "1" ]; then FLAGS+=(-Xptxas -v); fi

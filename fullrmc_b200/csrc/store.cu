@@ -2697,7 +2697,7 @@ static int sync_models(frmc_store *s)
             cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, EPI_THREADS, smem) != cudaSuccess || per_sm < 1) s->batch_ok = false; \
         } while (0)
-#define BATCH_ATTR(M) do { auto k0 = batch_kernel<M, false, false>; auto k1 = batch_kernel<M, true, false>; BATCH_ATTR1(k0); BATCH_ATTR1(k1); \
+#define BATCH_ATTR(M) do { auto k0 = batch_kernel<M, false, false>; BATCH_ATTR1(k0); \
                            auto k2 = batch_kernel<M, false, true>; auto k3 = batch_kernel<M, true, true>; BATCH_ATTR1(k2); BATCH_ATTR1(k3); } while (0)
         BATCH_ATTR(MODE_IBC); BATCH_ATTR(MODE_ORTHO_FAST); BATCH_ATTR(MODE_TRI_FAST); BATCH_ATTR(MODE_ORTHO_GEN); BATCH_ATTR(MODE_TRI_GEN);
 #undef BATCH_ATTR1
@@ -3210,7 +3210,8 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
     float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
     void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
                     &in_dev, &gen, &real};
-    const void *kern = generated ? (s->batch_fly ? (const void *)batch_kernel<MODE, true, true> : (const void *)batch_kernel<MODE, true, false>)
+    // (three variants per geometry mode, not four: generated runs always take the kernel with the on-the-fly corrections)
+    const void *kern = generated ? (const void *)batch_kernel<MODE, true, true>
                                  : (s->batch_fly ? (const void *)batch_kernel<MODE, false, true> : (const void *)batch_kernel<MODE, false, false>);
     cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)s->ctx->sm_count), dim3(EPI_THREADS), args, s->epi_smem, s->stream);
     if (e != cudaSuccess) {

@@ -154,3 +154,45 @@ def test_store_pass_latency_at_cfg4_size():
         us = 1e6 * (time.perf_counter() - t0) / 280
         print("store distance pass at cfg4: %.1f us per move" % us)
         assert us < 200.0
+
+
+@pytest.mark.gpu
+def test_store_pass_after_atoms_were_removed():
+    """after removals the engine's relative indexes address the remaining atoms and the removed records pair with
+    nothing: the store pass equals the stateless kernels on the engine's np.delete'd arrays"""
+    from fullrmc_b200 import synthetic
+    from fullrmc_b200.Core import atomic_distances as ad
+    from fullrmc_b200.model import ModelSpec
+    from fullrmc_b200.store import DeviceStore
+    basis = np.array([[40, 0, 0], [6, 39, 0], [-4, 8, 38]], dtype=F32)
+    s = synthetic.random_system(6000, 3, basis, n_elements=3, molecule_size=2)
+    grid = synthetic.RGrid(0.0, 0.05, 160)
+    nT = 3
+    lower = np.zeros((nT, nT, 1), F32)
+    upper = np.full((nT, nT, 1), 2.0, F32)
+    flags = dict(interMolecular=True, intraMolecular=True, reduceDistance=False, reduceDistanceToUpper=True,
+                 reduceDistanceToLower=False, countWithinLimits=True)
+    common = dict(elements=s.elements, n_per_element=s.numberOfAtomsPerElement, weighting=s.weighting, volume=s.volume,
+                  rho0=s.numberDensity, shell_centers=grid.shellCenters, shell_volumes=grid.shellVolumes)
+    rng = np.random.default_rng(9)
+    with DeviceStore(s.boxCoords, s.basis, True, s.moleculeIndex, s.elementIndex, 3) as store:
+        gi = store.add_grid(grid.minDistance, grid.maxDistance, grid.bin, grid.hs)
+        store.add_model(gi, ModelSpec("PDF", experimental=np.zeros(grid.hs, F32), **common))
+        store.compute_data()
+        cid = store.distance_add(s.elementIndex, nT, lower, upper, **flags)
+        box, mol, el = s.boxCoords.copy(), s.moleculeIndex.copy(), s.elementIndex.copy()
+        for victim in (4000, 17, 2999, 17):
+            store.propose_amputation(victim); store.accept_amputation()
+            box, mol, el = np.delete(box, victim, axis=0), np.delete(mol, victim), np.delete(el, victim)
+        assert store.numberOfAtoms == box.shape[0] and np.array_equal(store.get_coords(), box)
+        kw = dict(basis=s.basis, isPBC=True, numberOfElements=nT, lowerLimit=lower, upperLimit=upper, **flags)
+        for step in range(12):
+            idx = np.sort(rng.choice(box.shape[0], 3, replace=False)).astype(np.int32)
+            moved = (box[idx] + rng.normal(0, 0.02, (3, 3))).astype(F32)
+            counts, sums = store.distance_move(cid, idx, moved)
+            after = box.copy(); after[idx] = moved
+            for which, coords in ((0, box), (2, after)):
+                ni, di, ne, de = ad.multiple_atomic_distances_coords(indexes=idx, boxCoords=coords, moleculeIndex=mol, elementIndex=el,
+                                                                     allAtoms=True, **kw)
+                assert np.array_equal(counts[which, 0], ni) and np.array_equal(counts[which, 1], ne), "step %d" % step
+                assert np.array_equal(sums[which, 0], di) and np.array_equal(sums[which, 1], de), "step %d" % step
