@@ -642,16 +642,20 @@ def coordination_leg(system, no_cpu):
     _, ms_kernel = _lib.kernel_ms_of(lambda: ac.all_atoms_coord_number_coords(boxCoords=system.boxCoords, coordNumData=np.zeros(3, np.float32), **kw))
     # every distance test gathers one 16-byte position + one 4-byte list index: L2-resident
     gathered = 20.0 * tests
+    issue_peak = 148 * 128 * 1.965 / 37.0
     out = {"metric": "all_atoms_coord_number_coords G distance tests/s", "workload": "cfg4: %d atoms, 3 definitions, shell [1.5, 3.5] A, "
            "%.3g distance tests per call" % (n, tests), "e2e": {"value": tests / dt / 1e9, "unit": "G tests/s", "ms_per_call": 1e3 * dt,
            "h2d_bytes_per_step": 12 * n + 24 * sum(len(a) + len(b) for a, b in zip(as_core, in_shell)), "d2h_bytes_per_step": 12,
            "api": "fullrmc_b200.Core.atomic_coordination.all_atoms_coord_number_coords"},
            "coordination_numbers": [float(x) for x in data / 2], "gpu_launches": launches, "kernel_ms": ms_kernel,
            "value": tests / (ms_kernel * 1e-3) / 1e9, "unit": "G tests/s (device time of the counting kernel)",
-           "roofline": {"bound": "hbm", "achieved": gathered / (ms_kernel * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s (gathered bytes, L2 resident)",
-                        "frac": gathered / (ms_kernel * 1e-3) / 1e9 / HBM_GBS, "traffic": None,
-                        "note": "algorithmic bytes = 20 B gathered per distance test (16 B position + 4 B list index); the lists are L2 "
-                                "resident, so a figure above the HBM peak means L2 reuse, not DRAM traffic"},
+           "roofline": {"bound": "fp32-issue", "achieved": tests / (ms_kernel * 1e-3) / 1e9, "peak": issue_peak, "unit": "G distance tests/s",
+                        "frac": tests / (ms_kernel * 1e-3) / 1e9 / issue_peak, "traffic": None,
+                        "peak_source": "148 SMs x 128 lanes x 1965 MHz / 37 fp32 issue slots per general-basis distance test (the "
+                                       "full histogram's count for the same arithmetic)",
+                        "gathered_gbs": gathered / (ms_kernel * 1e-3) / 1e9,
+                        "note": "every test also gathers 20 B (16 B position + 4 B list index) from L1/L2: the lists are L2 resident, "
+                                "DRAM traffic is about one pass over the inputs, so HBM does not bound this kernel"},
            "note": "stateless first version of this row: one launch over (atom, definition) tasks cut into 2048-entry "
            "items; the call is dominated by flattening the Python lists on the host"}
     # a per-move call (one atom, as compute_before_move makes it): latency of the host-buffer call
@@ -660,6 +664,31 @@ def coordination_leg(system, no_cpu):
     for _ in range(20):
         ac.multi_atoms_coord_number_coords(indexes=idx, boxCoords=system.boxCoords, coordNumData=np.zeros(3, np.float32), **kw)
     out["per_move_call_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+    # the same evaluation on the device store (csrc/storecoord.cu): definitions registered once, before and after of a move
+    # from one launch over the resident records
+    try:
+        from fullrmc_b200.store import DeviceStore
+        rng = np.random.default_rng(29)
+        m = 220
+        midx = rng.integers(0, n, m).astype(np.int32)
+        moved = (system.boxCoords[midx] + rng.normal(0, 0.001, (m, 3))).astype(np.float32)
+        with DeviceStore(system.boxCoords, system.basis, system.isPBC, system.moleculeIndex, system.elementIndex, 5) as st:
+            cid = st.coordination_add(cores, shells, [np.float32(1.5)] * 3, [np.float32(3.5)] * 3)
+            for it in range(20):
+                counts = st.coordination_move(cid, midx[it:it + 1], moved[it:it + 1])
+            want = np.zeros(3, np.float32)
+            ac.multi_atoms_coord_number_coords(indexes=midx[19:20], boxCoords=system.boxCoords, coordNumData=want, **kw)
+            same = bool(np.array_equal(counts[0].astype(np.float32), want))
+            t0 = time.perf_counter()
+            for it in range(20, m):
+                st.coordination_move(cid, midx[it:it + 1], moved[it:it + 1])
+            us_store = 1e6 * (time.perf_counter() - t0) / (m - 20)
+        out["per_move"] = {"stateless_call_us": 1e3 * out["per_move_call_ms"], "store_pass_us": us_store, "identical": same,
+                           "h2d_bytes_per_step_store": 16, "gpu_launches_per_move": 1,
+                           "api": "DeviceStore.coordination_move (frmc_store_coordination_move): before and after counts of one move "
+                                  "in one launch over the resident records"}
+    except Exception as err:
+        out["per_move"] = {"error": "%s: %s" % (type(err).__name__, err)}
     if not no_cpu:
         from oracle import build_ref
         import importlib
@@ -1347,6 +1376,8 @@ def run_b200(args):
         line["distance_constraint_cfg4_per_move_store_us"] = (dleg.get("per_move") or {}).get("store_pass_us")
         line["distance_constraint_cfg4_per_move_stateless_us"] = (dleg.get("per_move") or {}).get("stateless_call_us")
         line["coordination_cfg4_roofline_frac"] = (cleg.get("roofline") or {}).get("frac")
+        line["coordination_cfg4_per_move_store_us"] = (cleg.get("per_move") or {}).get("store_pass_us")
+        line["coordination_cfg4_per_move_stateless_us"] = (cleg.get("per_move") or {}).get("stateless_call_us")
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         scale = max(1, n // 1000000)                                           # ~10 s of CPU work per leg at 1 M atoms

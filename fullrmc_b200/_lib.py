@@ -129,6 +129,8 @@ SIGNATURES = {
     # array arguments as plain addresses (see frmc_step)
     "frmc_store_distance_move": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP]),
     "frmc_store_move_atoms": (_I, [_VP, c_i32p, _I, c_f32p]),
+    "frmc_store_coordination_add": (_I, [_VP, _I, c_i64p, c_i32p, c_i64p, c_i32p, c_f32p, c_f32p]),
+    "frmc_store_coordination_move": (_I, [_VP, _I, _VP, _I, _VP, _VP]),
     "frmc_run_batch": (_I, [_VP, _I, c_i32p, c_i32p, c_f32p, c_f32p, _F, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p,
                             ctypes.POINTER(ctypes.c_double)]),
     "frmc_store_batch_stats": (_I, [_VP, c_u64p, c_u64p, c_u64p]),

@@ -12,7 +12,13 @@ computes, expressed for this backend:
 The engine-facing protocol (``compute_data`` / ``compute_before_move`` / ``compute_after_move`` / ``accept_move`` /
 ``reject_move``; Core/Constraint.py:732-748) is kept, with one staged move at a time.  The counts come from
 ``fullrmc_b200.Core.atomic_coordination`` (one launch per call over a flat task table, bit-identical to the reference's
-Cython loops); coordinates travel with every call, like the reference's own functions.
+Cython loops).  Two ways to run:
+
+* stateless (``store=None``): coordinates and lists travel with every call, like the reference's own functions;
+* on the device store (``store=DeviceStore``): the definitions are registered once on the store whose atoms the histogram
+  constraints move, and the before / after counts of a move come from ONE launch over the resident records
+  (``DeviceStore.coordination_move``, csrc/storecoord.cu) -- no coordinate or list upload; the store owns the
+  coordinates (``boxCoordinates`` is only read by ``compute_data`` when no store is given).
 """
 import collections
 
@@ -43,7 +49,8 @@ class DeviceAtomicCoordinationNumberConstraint(object):
     """
 
     def __init__(self, boxCoordinates, basisVectors, isPBC, coresIndexes, shellsIndexes, lowerShells, upperShells, minAtoms,
-                 maxAtoms, weights=None, kernels=None):
+                 maxAtoms, weights=None, kernels=None, store=None):
+        self._store = store
         if kernels is None:
             from .Core import atomic_coordination as kernels
         self._count = kernels
@@ -70,6 +77,9 @@ class DeviceAtomicCoordinationNumberConstraint(object):
         self._staged = None
         self.tried = 0
         self.accepted = 0
+        self._sc = None
+        if store is not None:
+            self._sc = store.coordination_add(self.coresIndexes, self.shellsIndexes, self.lowerShells, self.upperShells)
 
     # ---------------------------------------------------------------- counting
     def _definitions(self):
@@ -97,7 +107,8 @@ class DeviceAtomicCoordinationNumberConstraint(object):
     # ---------------------------------------------------------------- the engine-facing protocol
     def compute_data(self, update=True):
         pairs = np.zeros(len(self.coresIndexes), dtype=FLOAT_TYPE)
-        self._count.all_atoms_coord_number_coords(boxCoords=self.boxCoordinates, coordNumData=pairs, **self._definitions())
+        coords = self.boxCoordinates if self._store is None else self._store.get_coords()
+        self._count.all_atoms_coord_number_coords(boxCoords=coords, coordNumData=pairs, **self._definitions())
         pairs /= FLOAT_TYPE(2.)                              # every neighbour pair was met from both of its atoms
         error = self.compute_standard_error(pairs)
         if update:
@@ -106,10 +117,21 @@ class DeviceAtomicCoordinationNumberConstraint(object):
 
     def compute_before_move(self, realIndexes, relativeIndexes):
         idx = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+        if self._store is not None:
+            # before and after come from one launch over the store once the moved coordinates are known
+            self._staged = _StagedMove(idx, None, None, None, None)
+            return
         self._staged = _StagedMove(idx, self._counts_of(idx, self.boxCoordinates), None, None, None)
 
     def compute_after_move(self, realIndexes, relativeIndexes, movedBoxCoordinates):
         idx = np.ascontiguousarray(relativeIndexes, dtype=INT_TYPE)
+        if self._store is not None:
+            counts = self._store.coordination_move(self._sc, idx, movedBoxCoordinates).astype(FLOAT_TYPE)
+            data = self.data - counts[0] + counts[1]
+            self._staged = _StagedMove(idx, counts[0], counts[1], data, self.compute_standard_error(data))
+            self._moved = (idx, np.ascontiguousarray(movedBoxCoordinates, dtype=FLOAT_TYPE))
+            self.tried += 1
+            return
         if self._staged is None or not np.array_equal(self._staged.indexes, idx):
             self.compute_before_move(realIndexes, relativeIndexes)
         patched = np.array(self.boxCoordinates, dtype=FLOAT_TYPE)
@@ -123,6 +145,8 @@ class DeviceAtomicCoordinationNumberConstraint(object):
         self.data, self.standardError = self._staged.data, self._staged.error
         self._staged = None
         self.accepted += 1
+        if self._store is not None and self._store.n_models == 0:
+            self._store.move_atoms(*self._moved)                  # nobody else commits the move on a store without models
 
     def reject_move(self, realIndexes, relativeIndexes):
         self._staged = None

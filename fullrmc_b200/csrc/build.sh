@@ -16,7 +16,7 @@ if [ -n "${FRMC_EXTRA_FLAGS:-}" ]; then FLAGS+=(${FRMC_EXTRA_FLAGS}); fi   # exp
 OUT="${FRMC_OUT_DIR:-$OUT}"; mkdir -p "$OUT"
 OBJS=()
 PIDS=()
-for f in common stateless fullhist devlayout multigpu store atomdist coordnum storedist; do
+for f in common stateless fullhist devlayout multigpu store atomdist coordnum storedist storecoord; do
   rm -f "$OUT/$f.o"                     # a failed compile must never leave a stale object for the link step
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   PIDS+=("$!")

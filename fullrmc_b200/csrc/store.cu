@@ -2400,6 +2400,7 @@ struct frmc_store {
     int dev = 0;
     int64_t n = 0, npad = 0;         // n: atoms the store holds NOW (the engine's relative numbering runs over them)
     int64_t n0 = 0;                  // atoms the layout was built for (the "real" numbering: lay.inv, d_orig, d_mol, h_mol, h_el)
+    uint64_t layout_gen = 0;         // counts the layouts of this store: per-position tables of other translation units follow it
     std::vector<int32_t> rel2real;   // relative -> real index once atoms have been removed (empty: identity)
     int amp_rel = -1;                // relative index of the atom of the staged amputation
     int nEl = 0, isPBC = 0;
@@ -2558,6 +2559,7 @@ static int upload_layout(frmc_store *s, const float *coords)
     if (rc) return rc;
     s->npad = s->lay.npad;
     s->mol_span = s->lay.mol_span;
+    ++s->layout_gen;
     if (!s->d_mol && s->n > 0) {
         FRMC_CUDA(cudaMalloc(&s->d_mol, sizeof(int32_t) * (size_t)s->n));
         FRMC_CUDA(cudaMemcpyAsync(s->d_mol, s->h_mol.data(), sizeof(int32_t) * (size_t)s->n, cudaMemcpyHostToDevice, s->stream));
@@ -2962,7 +2964,7 @@ int store_view(frmc_store *s, StoreView *out)
     if (rc) return rc;
     out->dev = s->dev; out->stream = s->stream; out->sm_count = s->ctx->sm_count; out->ctx = s->ctx;
     out->atoms = s->d_atoms; out->orig = s->d_orig; out->n = s->n; out->npad = s->npad; out->inv = s->lay.inv.data();
-    out->n0 = s->n0; out->rel2real = s->rel2real.empty() ? nullptr : s->rel2real.data();
+    out->n0 = s->n0; out->layout_gen = s->layout_gen; out->rel2real = s->rel2real.empty() ? nullptr : s->rel2real.data();
     out->L = s->L; out->isPBC = s->isPBC;
     for (int c = 0; c < 3; ++c) { out->lo[c] = s->lo[c]; out->hi[c] = s->hi[c]; }
     out->pending = s->pending; out->prop = s->d_prop;
@@ -3303,6 +3305,7 @@ void frmc_store_destroy(frmc_store *s)
     if (!s) return;
     cudaSetDevice(s->dev);
     storedist_release(s);
+    storecoord_release(s);
     if (s->h_cmd) stop_persistent(s);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &m : s->models) {

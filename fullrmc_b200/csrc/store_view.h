@@ -34,6 +34,7 @@ struct StoreView {
     const uint32_t *orig;
     int64_t n, npad;                 // n: atoms the store holds now
     int64_t n0;                      // atoms of the layout (the numbering of inv / orig)
+    uint64_t layout_gen;             // changes whenever the store is laid out again (positions of the records change)
     const int32_t *rel2real;         // host: the engine's relative index -> original index once atoms were removed (NULL: identity)
     const int32_t *inv;              // host: original index -> position
     Lattice L;
@@ -47,5 +48,6 @@ struct StoreView {
 int store_view(frmc_store *s, StoreView *out);   // store.cu; ends a persistent run (its kernel owns the GPU)
 int store_flush(frmc_store *s);                  // store.cu; applies a deferred accept / reject to the device state
 void storedist_release(frmc_store *s);           // storedist.cu; frees the distance constraints registered on a store
+void storecoord_release(frmc_store *s);          // storecoord.cu; frees the coordination-number constraints registered on a store
 
 }  // namespace frmc

@@ -231,6 +231,9 @@ struct SdHost {
     std::vector<void *> owned;
     int *h_out = nullptr;            // mapped pinned: counts | sums | overflow flag | sequence
     unsigned int seq = 0;
+    int *d_type = nullptr, *d_type_pos = nullptr;   // types by original index / by position (the latter follows the store's layout)
+    int64_t n0 = 0, npad = 0;
+    uint64_t layout_gen = 0;
 };
 
 static std::mutex g_sd_mu;
@@ -293,6 +296,7 @@ extern "C" int frmc_store_distance_add(frmc_store *s, const int32_t *type, int n
     }
     FRMC_CUDA(cudaStreamSynchronize(v.stream));
     h.dev.nT = nT; h.dev.flags = flags; h.dev.type_pos = d_type_pos; h.dev.lim = d_lim;
+    h.d_type = d_type; h.d_type_pos = d_type_pos; h.n0 = v.n0; h.npad = v.npad; h.layout_gen = v.layout_gen;
     FRMC_CUDA(cudaHostAlloc((void **)&h.h_out, sizeof(int) * (16 * cells + 2), cudaHostAllocMapped));
     memset(h.h_out, 0, sizeof(int) * (16 * cells + 2));
     h.dev.out = h.h_out;                         // unified addressing: the mapped host pointer is valid on the device
@@ -307,19 +311,30 @@ extern "C" int frmc_store_distance_move(frmc_store *s, int id, const int32_t *in
 {
     FRMC_REQUIRE(s && indexes && moved && counts_out && sums_out, FRMC_EINVAL, "NULL argument");
     FRMC_REQUIRE(k >= 1 && k <= FRMC_MAX_GROUP, FRMC_ELIMIT, "group size %d outside 1..%d", k, FRMC_MAX_GROUP);
+    int rc = store_flush(s);                     // a deferred accept / reject of the histogram constraints is applied first
+    if (rc) return rc;
+    StoreView v;
+    if ((rc = store_view(s, &v))) return rc;
     SdHost h;
     unsigned int seq;
     {
         std::lock_guard<std::mutex> lock(g_sd_mu);
         auto it = g_sd.find(s);
         FRMC_REQUIRE(it != g_sd.end() && id >= 0 && id < (int)it->second.size(), FRMC_EINVAL, "unknown distance constraint %d", id);
-        seq = ++it->second[(size_t)id].seq;
-        h = it->second[(size_t)id];
+        SdHost &reg = it->second[(size_t)id];
+        FRMC_REQUIRE(reg.n0 == v.n0, FRMC_ESTATE, "the store was re-numbered after atoms were removed: register the constraint again");
+        if (reg.layout_gen != v.layout_gen) {
+            // the store was laid out again (frmc_store_set_coords): the records changed places, the types follow them
+            FRMC_REQUIRE(v.npad <= reg.npad, FRMC_ESTATE, "the store grew since the constraint was registered: register it again");
+            if (v.npad > 0) {
+                sd_type_pos_kernel<<<(unsigned)((v.npad + 255) / 256), 256, 0, v.stream>>>(reg.d_type, v.orig, (int)v.npad, reg.d_type_pos);
+                FRMC_LAUNCH_CHECK();
+            }
+            reg.layout_gen = v.layout_gen;
+        }
+        seq = ++reg.seq;
+        h = reg;
     }
-    int rc = store_flush(s);                     // a deferred accept / reject of the histogram constraints is applied first
-    if (rc) return rc;
-    StoreView v;
-    if ((rc = store_view(s, &v))) return rc;
     SdMove mv;
     memset(&mv, 0, sizeof(mv));
     mv.k = k;

@@ -309,6 +309,51 @@ class DeviceStore(object):
             L.check(rc, "distance_move")
         return counts, sums
 
+    # ------------------------------------------------------------------ coordination-number pre-filter on the store
+    def coordination_add(self, coresIndexes, shellsIndexes, lowerShells, upperShells):
+        """register the definitions of a coordination-number constraint on this store (include/fullrmc_b200.h:
+        frmc_store_coordination_add): per definition the core and shell atom lists and the shell bounds; returns its id"""
+        ndef = len(coresIndexes)
+        if not (len(shellsIndexes) == len(lowerShells) == len(upperShells) == ndef):
+            raise ValueError("every per-definition argument needs one entry per shell definition (%d)" % ndef)
+
+        def flat(lists):
+            arrays = [np.ascontiguousarray(a, dtype=_I32).reshape(-1) for a in lists]
+            off = np.zeros(ndef + 1, np.int64)
+            off[1:] = np.cumsum([a.shape[0] for a in arrays])
+            idx = np.concatenate(arrays) if off[-1] else np.zeros(1, _I32)
+            return off, np.ascontiguousarray(idx, dtype=_I32)
+
+        coff, cidx = flat(coresIndexes)
+        soff, sidx = flat(shellsIndexes)
+        lo = np.array([_F32(x) for x in lowerShells], dtype=_F32)
+        up = np.array([_F32(x) for x in upperShells], dtype=_F32)
+        cid = L.check(self._lib.frmc_store_coordination_add(self._handle, ndef, L.ptr(coff, L.c_i64p), L.ptr(cidx, L.c_i32p),
+                                                            L.ptr(soff, L.c_i64p), L.ptr(sidx, L.c_i32p), L.ptr(lo, L.c_f32p),
+                                                            L.ptr(up, L.c_f32p)), "coordination_add")
+        self._coord = getattr(self, "_coord", {})
+        counts = np.zeros((2, ndef), dtype=_I32)
+        self._coord[cid] = (counts, counts.__array_interface__["data"][0])
+        return cid
+
+    def coordination_move(self, cid, indexes, movedBoxCoordinates):
+        """One launch over the resident atoms for a move of a registered coordination-number constraint: int32 (2, nDef) =
+        what multi_atoms_coord_number_coords adds to coordNumData for the group before and after the move.  A view of a
+        reused buffer."""
+        idx, moved = indexes, movedBoxCoordinates
+        if not (type(idx) is np.ndarray and idx.dtype == _I32 and idx.flags.c_contiguous):
+            idx = np.ascontiguousarray(idx, dtype=_I32)
+        if not (type(moved) is np.ndarray and moved.dtype == _F32 and moved.flags.c_contiguous):
+            moved = np.ascontiguousarray(moved, dtype=_F32)
+        if moved.size != 3 * idx.shape[0]:
+            raise ValueError("movedBoxCoordinates must be (k,3)")
+        counts, pc = self._coord[cid]
+        rc = self._lib.frmc_store_coordination_move(self._handle, cid, idx.__array_interface__["data"][0], idx.shape[0],
+                                                    moved.__array_interface__["data"][0], pc)
+        if rc < 0:
+            L.check(rc, "coordination_move")
+        return counts
+
     def move_atoms(self, indexes, movedBoxCoordinates):
         """apply an accepted move on a store without histogram models (with models, accept() does it)"""
         idx = np.ascontiguousarray(indexes, dtype=_I32)

@@ -328,6 +328,24 @@ int frmc_store_distance_move(frmc_store *s, int id, const int32_t *indexes, int 
                              float *sums_out);
 int frmc_store_move_atoms(frmc_store *s, const int32_t *indexes, int k, const float *moved);
 
+/* ---- the coordination-number pre-filter on the device store -----------------------------
+ * AtomicCoordinationNumberConstraint.compute_before_move / compute_after_move
+ * (Constraints/AtomicCoordinationConstraints.py:519-577) call multi_atoms_coord_number_coords
+ * (Extensions/atomic_coordination.pyx:280-313 through :207-240) for the k atoms of a move, before and after it.
+ * frmc_store_coordination_add registers the definitions once on the store whose atoms the histogram constraints move:
+ * definition d has the core atoms core_indexes[core_offsets[d] .. core_offsets[d+1]) and the shell atoms
+ * shell_indexes[shell_offsets[d] .. shell_offsets[d+1]) (atom indexes of the store's layout, each atom at most once per
+ * list; at most 32 definitions) and the shell lower[d] <= distance <= upper[d] (both ends inclusive, the float32 distance
+ * of pairs_distances_to_point; the atom itself is not skipped).  Returns the constraint's id (>= 0) or an error code.
+ * frmc_store_coordination_move evaluates one move in ONE launch over the resident records -- no coordinate upload, no
+ * list upload: counts_out [2][ndef] = what multi_atoms_coord_number_coords adds to coordNumData for `indexes` on the
+ * stored coordinates (before) and on the coordinates with the group at `moved` (after).  Integer counts: exactly the
+ * reference's float32 values while a cell stays below 2^24.  The whole-system count of compute_data stays with
+ * frmc_coordination_counts. */
+int frmc_store_coordination_add(frmc_store *s, int ndef, const int64_t *core_offsets, const int32_t *core_indexes,
+                                const int64_t *shell_offsets, const int32_t *shell_indexes, const float *lower, const float *upper);
+int frmc_store_coordination_move(frmc_store *s, int id, const int32_t *indexes, int k, const float *moved, int32_t *counts_out);
+
 /* ---- dynamic N and persisted state -------------------------------------------------
  * Atom removal (Engine.__on_runtime_step_try_remove, Engine.py:3231-3276; compute_as_if_amputated / accept_amputation /
  * reject_amputation of the three constraints, PairDistributionConstraints.py:1168-1238,

@@ -73,4 +73,9 @@ with DeviceStore(s2.boxCoords, s2.basis, True, s2.moleculeIndex, s2.elementIndex
     idx = np.arange(8, 12, dtype=np.int32)
     counts, sums = st2.distance_move(cid, idx, (s2.boxCoords[idx] + np.float32(0.01)).astype(np.float32))
     print("store distance pass", int(counts.sum()))
+    by_el = [np.flatnonzero(s2.elementIndex == e).astype(np.int32) for e in range(3)]
+    kid = st2.coordination_add([by_el[0], by_el[1], np.arange(9000, dtype=np.int32)], [by_el[1], by_el[2], by_el[0]], [1.0, 0.0, 0.5], [3.0, 2.5, np.inf])
+    for rep in range(3):
+        cn = st2.coordination_move(kid, idx, (s2.boxCoords[idx] + np.float32(0.01 * (rep + 1))).astype(np.float32))
+    print("store coordination pass", cn.tolist())
 print("done")
