@@ -347,6 +347,8 @@ class DeviceStore(object):
             moved = np.ascontiguousarray(moved, dtype=_F32)
         if moved.size != 3 * idx.shape[0]:
             raise ValueError("movedBoxCoordinates must be (k,3)")
+        if cid not in getattr(self, "_coord", {}):
+            raise ValueError("unknown coordination constraint %r (coordination_add returns the id)" % (cid,))
         counts, pc = self._coord[cid]
         rc = self._lib.frmc_store_coordination_move(self._handle, cid, idx.__array_interface__["data"][0], idx.shape[0],
                                                     moved.__array_interface__["data"][0], pc)
