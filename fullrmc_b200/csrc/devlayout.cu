@@ -290,6 +290,175 @@ __global__ void __launch_bounds__(1024) dl_split_kernel(const DlTask *__restrict
     }
 }
 
+// ---- the same split for LARGE nodes, spread over many CTAs ---------------------------------------------------------
+// One CTA per node leaves the top of the tree (5 nodes of 200 000 points at cfg5, then 10, 20, 40) to a handful of SMs:
+// 1.3 of the 1.5 ms the splits of 10^6 atoms took.  Nodes of at least DL_WIDE_MIN points are cut into chunks of DL_WCHUNK
+// points, one CTA each, in three launches per level:
+//   dl_whist_kernel     the chunk's 2048-bin histogram -> its private copy in global memory + integer atomics into the
+//                       node's histogram
+//   dl_wcut_kernel      one CTA per node: the bin holding record k (as dl_split_kernel), then from the chunks' private
+//                       histograms the records each chunk sends left / into the boundary bin / right, scanned over the
+//                       chunks IN ORDER -- the placement stays the stable partition of the single-CTA kernel, record for
+//                       record -- and the children's boxes
+//   dl_wscatter_kernel  the chunk's records to their places (ballot prefix sums inside the chunk, chunk offsets from the scan)
+static const int DL_WCHUNK = 4096;
+static const int DL_WIDE_MIN = 20000;
+
+struct DlWChunk { int task, first, len; };                 // task of the level's wide list, range inside the node
+struct DlWCut { int qcut, less, eq, r, ax; float lo, scale; };
+
+__device__ __forceinline__ int dl_bin_of(const DlPoint &p, int ax, float lo, float scale)
+{
+    const float v = (ax == 0) ? p.x : (ax == 1) ? p.y : p.z;
+    return max(0, min(DL_BINS - 1, (int)((v - lo) * scale)));
+}
+
+__device__ __forceinline__ void dl_axis_of(const DlBox &B, int &ax, float &lo, float &scale)
+{
+    ax = 0;
+    if (B.hi[1] - B.lo[1] > B.hi[ax] - B.lo[ax]) ax = 1;
+    if (B.hi[2] - B.lo[2] > B.hi[ax] - B.lo[ax]) ax = 2;
+    lo = B.lo[ax];
+    const float ext = B.hi[ax] - B.lo[ax];
+    scale = (ext > 0.f) ? (float)DL_BINS / ext : 0.f;
+}
+
+__global__ void __launch_bounds__(1024) dl_whist_kernel(const DlTask *__restrict__ tasks, const DlWChunk *__restrict__ chunks,
+                                                        const DlPoint *__restrict__ buf0, const DlPoint *__restrict__ buf1,
+                                                        const DlBox *__restrict__ boxes, int *__restrict__ chunk_hist, int *__restrict__ node_hist)
+{
+    __shared__ int hist[DL_BINS];
+    const DlWChunk C = chunks[blockIdx.x];
+    const DlTask T = tasks[C.task];
+    const DlPoint *__restrict__ src = (T.src ? buf1 : buf0) + T.start + C.first;
+    int ax; float lo, scale;
+    dl_axis_of(boxes[T.id], ax, lo, scale);
+    const int tid = threadIdx.x;
+    for (int b = tid; b < DL_BINS; b += 1024) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < C.len; i += 1024) atomicAdd(&hist[dl_bin_of(src[i], ax, lo, scale)], 1);
+    __syncthreads();
+    for (int b = tid; b < DL_BINS; b += 1024) {
+        const int h = hist[b];
+        chunk_hist[(size_t)blockIdx.x * DL_BINS + b] = h;
+        if (h) atomicAdd(&node_hist[(size_t)C.task * DL_BINS + b], h);
+    }
+}
+
+// chunk_first[t] .. chunk_first[t+1]: the chunks of wide task t, in node order; chunk_off[c] = {left, boundary, right}
+// records of the node's earlier chunks
+__global__ void __launch_bounds__(1024) dl_wcut_kernel(const DlTask *__restrict__ tasks, const int *__restrict__ chunk_first,
+                                                       const int *__restrict__ chunk_hist, int *__restrict__ node_hist,
+                                                       DlBox *__restrict__ boxes, DlWCut *__restrict__ cuts, int3 *__restrict__ chunk_off,
+                                                       const DlWChunk *__restrict__ chunks)
+{
+    __shared__ int s_scan[1024];
+    __shared__ int s_qcut, s_less, s_eq;
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DlTask T = tasks[t];
+    const DlBox B = boxes[T.id];
+    int ax; float lo, scale;
+    dl_axis_of(B, ax, lo, scale);
+    int *hist = node_hist + (size_t)t * DL_BINS;
+    {
+        const int a = hist[2 * tid], b = hist[2 * tid + 1];
+        hist[2 * tid] = 0; hist[2 * tid + 1] = 0;                 // re-armed for the next level
+        s_scan[tid] = a + b;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int before = s_scan[tid] - (a + b);
+        if (before < T.k && T.k <= before + a) { s_qcut = 2 * tid; s_less = before; s_eq = a; }
+        else if (before + a < T.k && T.k <= before + a + b) { s_qcut = 2 * tid + 1; s_less = before + a; s_eq = b; }
+        __syncthreads();
+    }
+    const int qcut = s_qcut, less = s_less, eq = s_eq;
+    const int c0 = chunk_first[t], c1 = chunk_first[t + 1];
+    // per chunk: records below the boundary bin and inside it
+    for (int c = c0 + warp; c < c1; c += 32) {
+        const int *h = chunk_hist + (size_t)c * DL_BINS;
+        int below = 0;
+        for (int b = lane; b < qcut; b += 32) below += h[b];
+        below = __reduce_add_sync(0xffffffffu, below);
+        if (lane == 0) chunk_off[c] = make_int3(below, h[qcut], chunks[c].len - below - h[qcut]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan over the node's chunks in order, 32 at a time
+        int runL = 0, runM = 0, runR = 0;
+        for (int base = c0; base < c1; base += 32) {
+            const int c = base + lane;
+            int3 v = (c < c1) ? chunk_off[c] : make_int3(0, 0, 0);
+            int iL = v.x, iM = v.y, iR = v.z;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, iL, o), b = __shfl_up_sync(0xffffffffu, iM, o), d = __shfl_up_sync(0xffffffffu, iR, o);
+                if (lane >= o) { iL += a; iM += b; iR += d; }
+            }
+            if (c < c1) chunk_off[c] = make_int3(runL + iL - v.x, runM + iM - v.y, runR + iR - v.z);
+            runL += __shfl_sync(0xffffffffu, iL, 31); runM += __shfl_sync(0xffffffffu, iM, 31); runR += __shfl_sync(0xffffffffu, iR, 31);
+        }
+    }
+    if (tid == 0) {
+        DlWCut cut;
+        cut.qcut = qcut; cut.less = less; cut.eq = eq; cut.r = T.k - less; cut.ax = ax; cut.lo = lo; cut.scale = scale;
+        cuts[t] = cut;
+        const float at = lo + ((float)qcut + 0.5f) * ((scale > 0.f) ? 1.0f / scale : 0.f);
+        DlBox L = B, R = B;
+        L.hi[ax] = at; R.lo[ax] = at;
+        boxes[T.left] = L; boxes[T.right] = R;
+    }
+}
+
+__global__ void __launch_bounds__(1024) dl_wscatter_kernel(const DlTask *__restrict__ tasks, const DlWChunk *__restrict__ chunks,
+                                                           const DlWCut *__restrict__ cuts, const int3 *__restrict__ chunk_off,
+                                                           DlPoint *__restrict__ buf0, DlPoint *__restrict__ buf1)
+{
+    __shared__ int s_wl[32], s_wm[32], s_wr[32];
+    const DlWChunk C = chunks[blockIdx.x];
+    const DlTask T = tasks[C.task];
+    const DlWCut cut = cuts[C.task];
+    const int3 off = chunk_off[blockIdx.x];
+    const DlPoint *__restrict__ src = (T.src ? buf1 : buf0) + T.start + C.first;
+    DlPoint *__restrict__ dst = (T.src ? buf0 : buf1) + T.start;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int doneL = off.x, doneM = off.y, doneR = off.z;
+    for (int base = 0; base < C.len; base += 1024) {
+        const int i = base + tid;
+        DlPoint p;
+        int cls = 3;
+        if (i < C.len) {
+            p = src[i];
+            const int q = dl_bin_of(p, cut.ax, cut.lo, cut.scale);
+            cls = (q < cut.qcut) ? 0 : (q == cut.qcut) ? 1 : 2;
+        }
+        const unsigned mL = __ballot_sync(0xffffffffu, cls == 0), mM = __ballot_sync(0xffffffffu, cls == 1),
+                       mR = __ballot_sync(0xffffffffu, cls == 2);
+        if (lane == 0) { s_wl[warp] = __popc(mL); s_wm[warp] = __popc(mM); s_wr[warp] = __popc(mR); }
+        __syncthreads();
+        int pl = 0, pm = 0, pr = 0, tl = 0, tm = 0, tr = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int a = s_wl[w], b = s_wm[w], c = s_wr[w];
+            if (w < warp) { pl += a; pm += b; pr += c; }
+            tl += a; tm += b; tr += c;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        if (cls == 0) {
+            dst[doneL + pl + __popc(mL & lt)] = p;
+        } else if (cls == 1) {
+            const int m = doneM + pm + __popc(mM & lt);
+            dst[(m < cut.r) ? (cut.less + m) : (T.k + (m - cut.r))] = p;
+        } else if (cls == 2) {
+            dst[T.k + (cut.eq - cut.r) + doneR + pr + __popc(mR & lt)] = p;
+        }
+        doneL += tl; doneM += tm; doneR += tr;
+        __syncthreads();
+    }
+}
+
 struct DlShift { int shift[FRMC_MAX_ELEMENTS]; };      // padded position - compact position, per element
 
 // one CTA per node of <= DL_LEAF points: the remaining k-d levels in shared memory (a node of len points is split at
@@ -299,7 +468,7 @@ struct DlShift { int shift[FRMC_MAX_ELEMENTS]; };      // padded position - comp
 __global__ void __launch_bounds__(DL_LEAF) dl_leaf_kernel(const DlTask *__restrict__ tasks, const DlPoint *__restrict__ buf0,
                                                           const DlPoint *__restrict__ buf1, const DlBox *__restrict__ boxes,
                                                           const float *__restrict__ coords, const int32_t *__restrict__ molkey,
-                                                          DlShift sh, float4 *__restrict__ atoms, uint32_t *__restrict__ orig)
+                                                          DlShift sh, float4 *__restrict__ atoms, uint32_t *__restrict__ orig, int fast)
 {
     __shared__ DlPoint pa[DL_LEAF], pb[DL_LEAF];
     __shared__ int n_start[64], n_len[64], n_next_start[64], n_next_len[64];
@@ -312,6 +481,66 @@ __global__ void __launch_bounds__(DL_LEAF) dl_leaf_kernel(const DlTask *__restri
     if (tid == 0) { s_nodes = 1; n_start[0] = 0; n_len[0] = T.len; n_box[0] = boxes[T.id]; }
     __syncthreads();
     DlPoint *cur = pa, *nxt = pb;
+    if (T.len == DL_LEAF && fast) {
+        // A full leaf (all but the last leaf of an element): its sub-nodes are aligned runs of 512 / 256 / 128 / 64
+        // points, so every level is a SEGMENTED BITONIC SORT of 64-bit words (order-preserving image of the coordinate
+        // along the node's longest axis, original index) with the point's slot as payload -- 185 compare-exchange
+        // steps for the five levels against 1984 rank-counting iterations per thread, and the same total order, hence
+        // the same records in the same places.  The points stay where they are; only (word, slot) pairs move.
+        unsigned long long *word = reinterpret_cast<unsigned long long *>(pb);
+        int *slot = reinterpret_cast<int *>(pb) + 2 * DL_LEAF;
+        slot[tid] = tid;
+        __syncthreads();
+        for (int level = 0; level < 5; ++level) {
+            const int S = DL_LEAF >> level, v = tid / S;
+            {
+                const DlBox B = n_box[v];
+                int ax = 0;
+                if (B.hi[1] - B.lo[1] > B.hi[ax] - B.lo[ax]) ax = 1;
+                if (B.hi[2] - B.lo[2] > B.hi[ax] - B.lo[ax]) ax = 2;
+                const DlPoint p = pa[slot[tid]];
+                const float c = __fadd_rn((ax == 0) ? p.x : (ax == 1) ? p.y : p.z, 0.0f);      // -0 and +0 compare equal: one image
+                uint32_t u = __float_as_uint(c);
+                u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+                word[tid] = ((unsigned long long)u << 32) | p.idx;
+            }
+            __syncthreads();
+            for (int size = 2; size <= S; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const int j = tid ^ stride;
+                    if (j > tid) {
+                        const bool up = (size == S) || ((tid & size) == 0);
+                        const unsigned long long wi = word[tid], wj = word[j];
+                        if ((wi > wj) == up) {
+                            word[tid] = wj; word[j] = wi;
+                            const int si = slot[tid]; slot[tid] = slot[j]; slot[j] = si;
+                        }
+                    }
+                    __syncthreads();
+                }
+            if (tid < (1 << level)) {
+                const DlBox B = n_box[tid];
+                int ax = 0;
+                if (B.hi[1] - B.lo[1] > B.hi[ax] - B.lo[ax]) ax = 1;
+                if (B.hi[2] - B.lo[2] > B.hi[ax] - B.lo[ax]) ax = 2;
+                const DlPoint c = pa[slot[tid * S + S / 2]];
+                const float cut = (ax == 0) ? c.x : (ax == 1) ? c.y : c.z;
+                DlBox L = B, R = B;
+                L.hi[ax] = cut; R.lo[ax] = cut;
+                n_next_box[2 * tid] = L; n_next_box[2 * tid + 1] = R;
+            }
+            __syncthreads();
+            if (tid < (2 << level)) n_box[tid] = n_next_box[tid];
+            __syncthreads();
+        }
+        const DlPoint p = pa[slot[tid]];
+        const long long i = p.idx;
+        const int pos = T.start + tid + sh.shift[T.elem];
+        const uint32_t meta = ((uint32_t)molkey[i] << 8) | (uint32_t)T.elem;
+        atoms[pos] = make_float4(coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], __uint_as_float(meta));
+        orig[pos] = (uint32_t)i;
+        return;
+    }
     for (int level = 0; level < 8; ++level) {
         // my node: the one whose range holds position tid
         const int nn = s_nodes;
@@ -596,8 +825,38 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
     }
     std::vector<DlBox> h_boxes((size_t)tree.n_boxes);
     for (size_t r = 0; r < roots.size(); ++r) h_boxes[(size_t)root_ids[r]] = roots[r];
+    // large nodes first inside a level: they go through the multi-CTA split (dl_whist / dl_wcut / dl_wscatter)
+    static const bool wide_on = []() { const char *e = getenv("FRMC_WIDE_SPLIT"); return !(e && atoi(e) == 0); }();
+    std::vector<int> level_wide;                   // wide tasks of level d
+    std::vector<DlWChunk> wchunks;                 // all levels, level after level
+    std::vector<int> wchunk_first;                 // per wide task (+1 per level): first chunk, relative to the level's first chunk
+    std::vector<int> level_chunk0, level_first0;   // per level: offsets into wchunks / wchunk_first
+    size_t max_level_wide = 0;
     tree.level_start.push_back(0);
-    for (auto &lv : levels) { tree.split.insert(tree.split.end(), lv.begin(), lv.end()); tree.level_start.push_back((int)tree.split.size()); }
+    for (auto &lv : levels) {
+        std::stable_partition(lv.begin(), lv.end(), [](const DlTask &t) { return wide_on && t.len >= DL_WIDE_MIN; });
+        int nw = 0;
+        while (nw < (int)lv.size() && wide_on && lv[(size_t)nw].len >= DL_WIDE_MIN) ++nw;
+        level_wide.push_back(nw);
+        level_chunk0.push_back((int)wchunks.size());
+        level_first0.push_back((int)wchunk_first.size());
+        const int c_base = (int)wchunks.size();
+        for (int t = 0; t < nw; ++t) {
+            wchunk_first.push_back((int)wchunks.size() - c_base);
+            for (int first = 0; first < lv[(size_t)t].len; first += DL_WCHUNK) {
+                DlWChunk ch;
+                ch.task = t; ch.first = first; ch.len = std::min(DL_WCHUNK, lv[(size_t)t].len - first);
+                wchunks.push_back(ch);
+            }
+        }
+        wchunk_first.push_back((int)wchunks.size() - c_base);
+        max_level_wide = std::max(max_level_wide, (size_t)nw);
+        tree.split.insert(tree.split.end(), lv.begin(), lv.end());
+        tree.level_start.push_back((int)tree.split.size());
+    }
+    size_t max_level_chunks = 0;
+    for (size_t d = 0; d < levels.size(); ++d)
+        max_level_chunks = std::max(max_level_chunks, (size_t)((d + 1 < levels.size() ? level_chunk0[d + 1] : (int)wchunks.size()) - level_chunk0[d]));
     const size_t n_tasks = tree.split.size() + tree.leaf.size();
     DlPoint *d_pts = (DlPoint *)ctx_buffer(c, 10, sizeof(DlPoint) * 2 * (size_t)n);
     unsigned char *d_tb = (unsigned char *)ctx_buffer(c, 11, sizeof(DlTask) * n_tasks + sizeof(DlBox) * (size_t)tree.n_boxes + 64);
@@ -609,18 +868,55 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
     all.insert(all.end(), tree.leaf.begin(), tree.leaf.end());
     FRMC_CUDA(cudaMemcpyAsync(d_tasks, all.data(), sizeof(DlTask) * n_tasks, cudaMemcpyHostToDevice, st));
     FRMC_CUDA(cudaMemcpyAsync(d_boxes, h_boxes.data(), sizeof(DlBox) * h_boxes.size(), cudaMemcpyHostToDevice, st));
+    // scratch of the multi-CTA splits (slot 12): chunk descriptors and first-chunk tables of every level, then per level
+    // (reused) the chunks' histograms, the nodes' histograms, the cuts and the chunk offsets
+    DlWChunk *d_wchunks = nullptr;
+    int *d_wfirst = nullptr, *d_chunk_hist = nullptr, *d_node_hist = nullptr;
+    DlWCut *d_cuts = nullptr;
+    int3 *d_chunk_off = nullptr;
+    if (!wchunks.empty()) {
+        auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
+        const size_t b_chunks = up16(sizeof(DlWChunk) * wchunks.size()), b_first = up16(sizeof(int) * wchunk_first.size()),
+                     b_chist = up16(sizeof(int) * DL_BINS * max_level_chunks), b_nhist = up16(sizeof(int) * DL_BINS * max_level_wide),
+                     b_cuts = up16(sizeof(DlWCut) * max_level_wide), b_off = up16(sizeof(int3) * max_level_chunks);
+        unsigned char *d_w = (unsigned char *)ctx_buffer(c, 12, b_chunks + b_first + b_chist + b_nhist + b_cuts + b_off);
+        if (!d_w) return FRMC_ENOMEM;
+        d_wchunks = reinterpret_cast<DlWChunk *>(d_w);
+        d_wfirst = reinterpret_cast<int *>(d_w + b_chunks);
+        d_chunk_hist = reinterpret_cast<int *>(d_w + b_chunks + b_first);
+        d_node_hist = reinterpret_cast<int *>(d_w + b_chunks + b_first + b_chist);
+        d_cuts = reinterpret_cast<DlWCut *>(d_w + b_chunks + b_first + b_chist + b_nhist);
+        d_chunk_off = reinterpret_cast<int3 *>(d_w + b_chunks + b_first + b_chist + b_nhist + b_cuts);
+        FRMC_CUDA(cudaMemcpyAsync(d_wchunks, wchunks.data(), sizeof(DlWChunk) * wchunks.size(), cudaMemcpyHostToDevice, st));
+        FRMC_CUDA(cudaMemcpyAsync(d_wfirst, wchunk_first.data(), sizeof(int) * wchunk_first.size(), cudaMemcpyHostToDevice, st));
+        FRMC_CUDA(cudaMemsetAsync(d_node_hist, 0, b_nhist, st));          // dl_wcut_kernel re-arms it level after level
+    }
     lap("tree+tasks", false);
     dl_gather_kernel<<<n_chunks, 256, 0, st>>>(d_coords, d_el, (long long)n, nEl, isPBC ? 1 : 0, d_cnt, eb, buf0);
     FRMC_LAUNCH_CHECK();
     for (size_t d = 0; d + 1 < tree.level_start.size(); ++d) {
         const int a = tree.level_start[d], b = tree.level_start[d + 1];
-        if (b > a) {
-            dl_split_kernel<<<b - a, 1024, 0, st>>>(d_tasks + a, buf0, buf1, d_boxes);
+        const int nw = level_wide[d];
+        if (nw > 0) {
+            const int ch0 = level_chunk0[d];
+            const int nch = (d + 1 < level_chunk0.size() ? level_chunk0[d + 1] : (int)wchunks.size()) - ch0;
+            dl_whist_kernel<<<nch, 1024, 0, st>>>(d_tasks + a, d_wchunks + ch0, buf0, buf1, d_boxes, d_chunk_hist, d_node_hist);
+            FRMC_LAUNCH_CHECK();
+            dl_wcut_kernel<<<nw, 1024, 0, st>>>(d_tasks + a, d_wfirst + level_first0[d], d_chunk_hist, d_node_hist, d_boxes, d_cuts, d_chunk_off,
+                                                d_wchunks + ch0);
+            FRMC_LAUNCH_CHECK();
+            dl_wscatter_kernel<<<nch, 1024, 0, st>>>(d_tasks + a, d_wchunks + ch0, d_cuts, d_chunk_off, buf0, buf1);
+            FRMC_LAUNCH_CHECK();
+        }
+        if (b > a + nw) {
+            dl_split_kernel<<<b - a - nw, 1024, 0, st>>>(d_tasks + a + nw, buf0, buf1, d_boxes);
             FRMC_LAUNCH_CHECK();
         }
     }
     lap("gather+splits", true);
-    dl_leaf_kernel<<<(unsigned)tree.leaf.size(), DL_LEAF, 0, st>>>(d_tasks + tree.split.size(), buf0, buf1, d_boxes, d_coords, d_key, sh, d_atoms, d_orig);
+    static const bool leaf_fast_on = []() { const char *e = getenv("FRMC_LEAF_FAST"); return !(e && atoi(e) == 0); }();
+    dl_leaf_kernel<<<(unsigned)tree.leaf.size(), DL_LEAF, 0, st>>>(d_tasks + tree.split.size(), buf0, buf1, d_boxes, d_coords, d_key, sh, d_atoms, d_orig,
+                                                                   (leaf_fast_on && lay.finite) ? 1 : 0);
     FRMC_LAUNCH_CHECK();
     dl_pad_kernel<<<nEl, 256, 0, st>>>(pad, d_atoms, d_orig);
     FRMC_LAUNCH_CHECK();
