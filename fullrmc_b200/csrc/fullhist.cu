@@ -351,14 +351,80 @@ __device__ __forceinline__ float dist2_unit(float xi, float yi, float zi, float 
 //   * intra / inter: atoms of one molecule lie within `mol_span` original indexes of each other (the largest spread
 //     of a molecule, found on the host), so a pair farther apart than that is inter-molecular without looking anything
 //     up; the few candidates go through the exact comparison of the molecule indexes (slow path).
-__global__ void sweep_records_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, long long npad,
-                                     float4 *__restrict__ out)
+// Round 2, later: one warp per 32-record sub-block also RE-ORDERS its records -- the k-d order of the store stops at 32
+// records; here it goes on to 16 and 8 (split along the longest axis of the run's box, full sort on (coordinate, lane),
+// like the leaves of devlayout.cu) -- and writes the bounding boxes of the four 8-record CHUNKS of the sub-block
+// (block_bbox_kernel's conventions).  The sweep tests a warp's I box against the chunk boxes of a J unit and skips
+// the chunks that cannot hold a hit: at cfg5 that removes 30 % of the distance evaluations the unit boxes let through.
+// The order inside a sub-block shows nowhere else: its own box is unchanged, both sides of the sweep read these
+// records, the ordered [a,b] slot comes from the original indexes in the records.
+__global__ void __launch_bounds__(256) sweep_records_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, long long npad,
+                                                            int pbc, float4 *__restrict__ out, float4 *__restrict__ cbox)
 {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npad) return;
+    __shared__ float4 s_rec[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long unit = (long long)blockIdx.x * 8 + w;
+    if (unit * 32 >= npad) return;
+    const long long p = unit * 32 + lane;
     float4 a = atoms[p];
     a.w = __uint_as_float(orig[p]);
+    for (int seg = 32; seg >= 16; seg >>= 1) {
+        const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z);
+        float f[3] = {a.x, a.y, a.z};
+        float lo[3], hi[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (pbc) f[c] = f[c] - floorf(f[c]);
+            lo[c] = fin ? f[c] : INFINITY; hi[c] = fin ? f[c] : -INFINITY;
+        }
+        for (int o = seg >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+        }
+        int ax = 0;
+        if (hi[1] - lo[1] > hi[ax] - lo[ax]) ax = 1;
+        if (hi[2] - lo[2] > hi[ax] - lo[ax]) ax = 2;
+        const float key = fin ? ((ax == 0) ? f[0] : (ax == 1) ? f[1] : f[2]) : INFINITY;     // records without a position go last
+        const int base = lane & ~(seg - 1);
+        int rank = 0;
+        for (int j = 0; j < seg; ++j) {
+            const float kj = __shfl_sync(0xffffffffu, key, base + j);
+            rank += (kj < key || (kj == key && base + j < lane)) ? 1 : 0;
+        }
+        __syncwarp();
+        s_rec[w][base + rank] = a;
+        __syncwarp();
+        a = s_rec[w][lane];
+    }
     out[p] = a;
+    // the chunk boxes: 8 consecutive records
+    {
+        const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z);
+        const float v[3] = {a.x, a.y, a.z};
+        float lo[3], hi[3], amax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float f = pbc ? (v[c] - floorf(v[c])) : v[c];
+            lo[c] = fin ? f : INFINITY; hi[c] = fin ? f : -INFINITY;
+            if (fin) amax = fmaxf(amax, fabsf(v[c]));
+        }
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        if ((lane & 7) == 0) {
+            float4 *b = cbox + (size_t)unit * 8 + (size_t)(lane >> 3) * 2;
+            b[0] = make_float4(lo[0], lo[1], lo[2], 1e-6f * (1.0f + amax));
+            b[1] = make_float4(hi[0], hi[1], hi[2], (lo[0] <= hi[0]) ? 0.f : 1.f);
+        }
+    }
 }
 
 // 32-bit shared-window accesses: the bin pass addresses the queue and the bin-edge table with plain registers
@@ -528,7 +594,7 @@ __device__ __noinline__ uint32_t drain_queue(uint32_t wp, uint32_t wq, uint32_t 
 template <int MODE, bool NOWRAP, bool HASMIN, bool TABLE, bool TRI>
 __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float xi, float yi, float zi, const Lattice &Lc,
                                            float t2min, float t2max, uint32_t &wp, const WarpCtx &W, int hs, float inv_bin,
-                                           float c0)
+                                           float c0, unsigned cmask)
 {
     Lattice L = Lc;               // lattice in plain registers: from the constant bank the compiler re-reads it every iteration
     if (MODE == MODE_ORTHO_FAST || MODE == MODE_ORTHO_GEN) {
@@ -551,6 +617,7 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float
     } else {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+            if (!((cmask >> c) & 1u)) continue;               // the chunk's box is out of reach of the warp's I atoms
             // eight records in flight: loads first, then eight independent distance chains, then the pushes
             float4 a[8];
             float d2[8];
@@ -750,6 +817,7 @@ __global__ void bin_table_kernel(GridParams g, float2 *__restrict__ tab)
 // everything one launch of the sweep needs, by value
 struct SweepArgs {
     const float4 *recs;              // sweep records {x, y, z, original index}
+    const float4 *cbox;              // per 32-record unit: {lo, hi} of its four 8-record chunks (sweep_records_kernel)
     const int32_t *mol;              // molecule index by original atom index (read only when mol_span > 0 ... or for candidates)
     const float4 *bbox;
     uint32_t mol_span;               // largest spread of a molecule in original indexes
@@ -762,7 +830,7 @@ struct SweepArgs {
 };
 
 // counts layout (global, u64): [2][nEl*nEl][hs], index 0 = intra, 1 = inter.
-// stats[0] += edge overflow events, stats[1] += (32 I records x 32 J records) units actually swept.
+// stats[0] += edge overflow events, stats[1] += (32 I records x 8 J records) chunks actually swept.
 template <int MODE, bool HASMIN, bool TABLE>
 __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const SweepArgs A)
 {
@@ -871,11 +939,24 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                                  (__fsub_rn(hiI.z, loJ.z) < T) && (__fsub_rn(hiJ.z, loI.z) < T);
                     }
                 }
+                // which 8-record chunks of ITS unit the warp's I box can reach (sweep_records_kernel wrote their boxes): every
+                // lane tests the four chunks of the unit it stands for; a unit none of whose chunks is in reach is dropped
+                // (the diagonal unit is swept whole)
+                unsigned cm = 0xFu;
+                if (A.cp.enabled && near && !tri) {
+                    const float4 *cb = A.cbox + ((size_t)jb * (SEG_PAD / 32) + (size_t)sb) * 8;
+                    float4 bx[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bx[k] = __ldg(cb + k);
+                    cm = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cm |= blocks_far(loI, hiI, bx[2 * k], bx[2 * k + 1], A.cp) ? 0u : (1u << k);
+                    near = cm != 0u;
+                }
                 unsigned m = __ballot_sync(0xffffffffu, near);
                 const unsigned m_nowrap = __ballot_sync(0xffffffffu, near && nowrap);
                 const unsigned m_tri = __ballot_sync(0xffffffffu, near && tri);
                 if (!m) continue;
-                swept += (unsigned)__popc(m);
                 // stream the surviving sub-blocks: unit n+1 is in flight (TMA) while unit n is swept.  A stage is
                 // free as soon as its sweep has ended: queued hits carry everything the bin pass needs.
                 auto issue = [&](int bit, unsigned sq) {
@@ -906,15 +987,17 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                         } while (!ok);
                     }
                     const float4 *sJu = sJ + st * 32;
+                    const unsigned cmask = __shfl_sync(0xffffffffu, cm, bit);      // the unit's chunks in reach
+                    swept += (unsigned)__popc(cmask);
                     if ((m_tri >> bit) & 1u) {
                         if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u))
-                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
+                            sweep_unit<MODE, true, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, cmask);
                         else
-                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
+                            sweep_unit<MODE, false, HASMIN, TABLE, true>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, cmask);
                     } else if (MODE == MODE_IBC || ((m_nowrap >> bit) & 1u)) {
-                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
+                        sweep_unit<MODE, true, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, cmask);
                     } else {
-                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0);
+                        sweep_unit<MODE, false, HASMIN, TABLE, false>(sJu, ai.x, ai.y, ai.z, A.L, g.t2min, g.t2max, wp, W, g.hs, inv_bin, c0, cmask);
                     }
                     ++seq;
                 }
@@ -1054,7 +1137,7 @@ void pack_rows(const std::vector<WorkItem> &rows, std::vector<unsigned char> &bl
 // Box pass, surviving-pair lists, bin-edge table, then the sweep, on prepared device arrays.  `rows` is the device
 // copy of a pack_rows() blob; mol_by_orig (device, molecule index by original atom index) is read only for pairs
 // within mol_span original indexes of each other (HostLayout::mol_span).  stats[0] accumulates edge-overflow events,
-// stats[1] swept (32 x 32) units.
+// stats[1] swept (32 x 8) chunks.
 int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *atoms, const uint32_t *orig,
                      int64_t npad, float4 *bbox, const WorkItem *rows, int n_rows, int n_pairs, PairLists &lists,
                      const int32_t *mol_by_orig, uint32_t mol_span,
@@ -1086,13 +1169,14 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *
     // sweep records {x, y, z, original index} of the current coordinates
     if (lists.recs_cap < (size_t)npad) {
         if (lists.recs) { FRMC_CUDA(cudaStreamSynchronize(stream)); cudaFree(lists.recs); lists.recs = nullptr; }
-        FRMC_CUDA(cudaMalloc((void **)&lists.recs, sizeof(float4) * (size_t)npad));
+        FRMC_CUDA(cudaMalloc((void **)&lists.recs, sizeof(float4) * ((size_t)npad + (size_t)npad / 4)));    // records + 8 box words per 32
         lists.recs_cap = (size_t)npad;
     }
-    sweep_records_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(atoms, orig, (long long)npad, lists.recs);
+    float4 *cbox = lists.recs + lists.recs_cap;
+    sweep_records_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(atoms, orig, (long long)npad, cp.pbc, lists.recs, cbox);
     FRMC_LAUNCH_CHECK();
     SweepArgs A;
-    A.recs = lists.recs; A.mol = mol_by_orig; A.mol_span = mol_span; A.bbox = bbox;
+    A.recs = lists.recs; A.cbox = cbox; A.mol = mol_by_orig; A.mol_span = mol_span; A.bbox = bbox;
     A.rows = rows; A.pair_first_row = reinterpret_cast<const int *>(rows + n_rows); A.row_item_start = lists.row_ints + 3 * (size_t)n_rows;
     A.entries = lists.entries; A.items = lists.items; A.pair_next = lists.pair_next;
     A.tab = lists.bin_table; A.counts = counts; A.stats = stats;

@@ -4426,7 +4426,7 @@ uint64_t frmc_store_swept_pairs(frmc_store *s)
     cudaSetDevice(s->dev);
     cudaMemcpyAsync(&blocks, s->d_overflow + 1, sizeof(blocks), cudaMemcpyDeviceToHost, s->stream);
     cudaStreamSynchronize(s->stream);
-    return blocks * 1024ull;
+    return blocks * 256ull;               // (32 x 8)-record chunks
 }
 
 }  // extern "C"
