@@ -1275,6 +1275,7 @@ static const int BATCH_MAX_PROPS = 32;
 static const int BATCH_MAX_GROUPS = 16;
 static const int BATCH_MAX_SPEC = 5;
 static const int BATCH_DEFER_MAX_LEAVES = 32;   // longest pairwise schedule a warp sums (n_out up to ~4000)   // accepted-but-uncommitted proposals an evaluation may assume (EpiOut::add2)
+static const int BATCH_PER_LAUNCH = 128;   // batches of host proposals one launch works through (~20 ms)
 static const int BATCH_STAMP_SLOTS = 4 + 5 * 64;   // start, cleared, delta pass done, end; 5 per round
 static const int BATCH_STAMP_TOTAL = BATCH_STAMP_SLOTS + 64 * 128;   // + per round the EPI_STAMP block of CTA 1 (see tools/probe_batch.py)
 
@@ -1611,7 +1612,7 @@ __global__ void generate_batch_kernel(const GenParams gp, BatchRun *__restrict__
 
 template <int MODE, bool GEN, bool FLYT>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
-batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ BatchIn in_host, Lattice L, GridSet gs, int nEl, const ModelSet ms,
+batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn *__restrict__ in_arr, int n_batches, Lattice L, GridSet gs, int nEl, const ModelSet ms,
              const EpiMap em, const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars,
              unsigned long long *__restrict__ overflow, long long *__restrict__ stamps, const BatchIn *__restrict__ in_dev,
              const GenOut *__restrict__ gen, float4 *__restrict__ real)
@@ -1620,16 +1621,17 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     __shared__ __align__(16) EpiShared es;
     __shared__ BatchShared bs;
     const int tid = threadIdx.x;
-    // the launch's proposals: handed over by the host in the kernel parameters, or drawn on the device by
-    // generate_batch_kernel (in_dev; gen / real then carry the real coordinates to commit)
-    // (GEN is a template parameter so that the host-proposal variant keeps reading its proposals from the constant bank)
-    const BatchIn &in = GEN ? *in_dev : in_host;
-    if (GEN && in.n_prop == 0) return;               // nothing generated: the call is finished or must be re-planned (uniform)
-    // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST launch
+    // The proposals: host proposals arrive as an ARRAY of batches in device memory (in_arr[0 .. n_batches)), and ONE launch
+    // works through all of them -- a launch per batch cost 16 us of launch latency, prologue and S(Q)-slab staging around
+    // 148 us of work; generated proposals are drawn batch by batch by generate_batch_kernel (in_dev, one batch per launch;
+    // gen / real then carry the real coordinates to commit).
+    const int nb = GEN ? 1 : n_batches;
+    if (nb <= 0) return;
+    if (GEN && in_dev->n_prop == 0) return;          // nothing generated: the call is finished or must be re-planned (uniform)
+    if (__ldcg(&bd.run->stopped)) return;            // an earlier launch of this call hit a conflict: nothing to do (uniform)
+    // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST batch
 #define BATCH_STAMP(i) do { if (stamps && blockIdx.x == 0 && tid == 0 && (i) < BATCH_STAMP_SLOTS) { \
         unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[(i)] = (long long)gt_; } } while (0)
-    BATCH_STAMP(0);
-    if (__ldcg(&bd.run->stopped)) return;            // an earlier launch of this call hit a conflict: nothing to do (uniform)
     const int G = bd.n_groups;
     const int group = (int)blockIdx.x / em.n, e_idx = (int)blockIdx.x - group * em.n;
     const bool epi = group < G;
@@ -1643,6 +1645,16 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
     }
     __syncthreads();
     unsigned long long bar_target = bs.s_bar;
+  for (int batch = 0; batch < nb; ++batch) {
+    const BatchIn &in = GEN ? *in_dev : in_arr[batch];
+    if (batch > 0) {
+        // the previous batch is behind every CTA (its commits, the run state CTA 0 wrote); a conflict ends the launch
+        grid_arrive(bars);
+        bar_target += gridDim.x;
+        grid_wait(bars, bar_target);
+        if (__ldcg(&bd.run->stopped)) return;        // uniform: written before the barrier
+    }
+    BATCH_STAMP(0);
     const int np = in.n_prop, na = in.n_atoms;
     // every proposal moves one atom: pair corrections between proposals of the launch are applied on the fly (CorrEv)
     // (FLYT is a template parameter: the host leaves the machinery out for large sparse systems, where two proposals of
@@ -2364,16 +2376,18 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const __grid_constant__ Batch
         }
     }
     BATCH_STAMP(3);
-#undef BATCH_STAMP
     if (blockIdx.x == 0 && tid == 0) {
         unsigned long long ov = 0;
         for (int j = 0; j < cur; ++j) ov += __ldcg(bd.bov + j);
         if (ov) atomicAdd(overflow, ov);
         BatchRun *r = bd.run;
-        r->total = total; r->n_rand = ri; r->n_done = in.out_base + cur; r->n_accepted += n_acc; r->rounds += rounds;
+        r->total = total; r->n_rand = ri; r->n_done = in.out_base + cur; r->n_accepted = __ldcg(&r->n_accepted) + n_acc;
+        r->rounds = __ldcg(&r->rounds) + rounds;
         __threadfence();
         r->stopped = stopped ? 1 : 0;
     }
+  }
+#undef BATCH_STAMP
 }
 }  // namespace frmc
 
@@ -2478,6 +2492,9 @@ struct frmc_store {
     int *d_goff = nullptr, *d_gidx = nullptr;        // groups
     int n_groups = 0;
     BatchIn *d_bin = nullptr;        // the generated launch
+    BatchIn *d_bins = nullptr;       // host proposals: all batches of a run (frmc_run_batch)
+    size_t bins_cap = 0;
+    std::vector<BatchIn> h_bins;
     GenOut *d_gen = nullptr;
     int *d_gout = nullptr; size_t gout_cap = 0;      // selected group of every proposal of a call
     bool force_general = false;      // a generated coordinate left the fast-wrap window once: general minimum image from then on
@@ -3183,7 +3200,7 @@ static int batch_prepare(frmc_store *s)
 }
 
 template <int MODE>
-static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
+static int launch_batch_t(frmc_store *s, const BatchIn *in_arr, int n_batches, bool generated)
 {
     GridSet gs = make_gridset(s);
     ModelSet ms;
@@ -3210,7 +3227,7 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
     const BatchIn *in_dev = generated ? s->d_bin : nullptr;
     const GenOut *gen = generated ? s->d_gen : nullptr;
     float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
-    void *args[] = {&s->d_atoms, &npad, (void *)&in, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
+    void *args[] = {&s->d_atoms, &npad, (void *)&in_arr, &n_batches, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
                     &in_dev, &gen, &real};
     // (three variants per geometry mode, not four: generated runs always take the kernel with the on-the-fly corrections)
     const void *kern = generated ? (const void *)batch_kernel<MODE, true, true>
@@ -3225,14 +3242,15 @@ static int launch_batch_t(frmc_store *s, const BatchIn &in, bool generated)
     return FRMC_OK;
 }
 
-static int launch_batch(frmc_store *s, int mode, const BatchIn &in, bool generated = false)
+// in_arr: DEVICE array of n_batches batches of host proposals (NULL / 0 for a generated batch, which sits in s->d_bin)
+static int launch_batch(frmc_store *s, int mode, const BatchIn *in_arr, int n_batches, bool generated = false)
 {
     switch (mode) {
-        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in, generated);
-        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in, generated);
-        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in, generated);
-        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in, generated);
-        default: return launch_batch_t<MODE_TRI_GEN>(s, in, generated);
+        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in_arr, n_batches, generated);
+        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in_arr, n_batches, generated);
+        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in_arr, n_batches, generated);
+        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in_arr, n_batches, generated);
+        default: return launch_batch_t<MODE_TRI_GEN>(s, in_arr, n_batches, generated);
     }
 }
 
@@ -3322,7 +3340,7 @@ void frmc_store_destroy(frmc_store *s)
     cudaFree(s->d_cmd); cudaFree(s->d_pbars);
     for (void *p : s->batch_owned) cudaFree(p);
     cudaFree(s->d_bstamps);
-    cudaFree(s->d_real); cudaFree(s->d_inv); cudaFree(s->d_goff); cudaFree(s->d_gidx); cudaFree(s->d_bin); cudaFree(s->d_gen); cudaFree(s->d_gout);
+    cudaFree(s->d_real); cudaFree(s->d_inv); cudaFree(s->d_goff); cudaFree(s->d_gidx); cudaFree(s->d_bin); cudaFree(s->d_bins); cudaFree(s->d_gen); cudaFree(s->d_gout);
     cudaFree(s->d_bbars); cudaFree(s->d_brand); cudaFree(s->d_bout_chi2); cudaFree(s->d_bout_dec);
     if (s->h_brun) cudaFreeHost(s->h_brun);
     if (s->bev0) cudaEventDestroy(s->bev0);
@@ -4023,6 +4041,8 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
     while (done < n) {
         // cut [done, n) into launches of at most BATCH_MAX_PROPS proposals / FRMC_MAX_GROUP atoms
         int j0 = done;
+        std::vector<BatchIn> &batches = s->h_bins;
+        batches.clear();
         while (j0 < n) {
             BatchIn in;
             memset(&in, 0, sizeof(in));
@@ -4050,8 +4070,21 @@ int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32
                 in.first[np] = na;
             }
             in.n_prop = np; in.n_atoms = na;
-            if ((rc = launch_batch(s, mode, in))) return rc;
+            batches.push_back(in);
             j0 += np;
+        }
+        // all batches of the run go up at once; ONE launch works through up to BATCH_PER_LAUNCH of them (bounded so that a
+        // kernel stays in the tens of milliseconds), later launches continue where it stops
+        if (s->bins_cap < batches.size()) {
+            FRMC_CUDA(cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_bins); s->d_bins = nullptr; s->bins_cap = 0;
+            FRMC_CUDA(cudaMalloc(&s->d_bins, sizeof(BatchIn) * batches.size()));
+            s->bins_cap = batches.size();
+        }
+        FRMC_CUDA(cudaMemcpyAsync(s->d_bins, batches.data(), sizeof(BatchIn) * batches.size(), cudaMemcpyHostToDevice, s->stream));
+        for (size_t b0 = 0; b0 < batches.size(); b0 += BATCH_PER_LAUNCH) {
+            const int nb = (int)std::min<size_t>(BATCH_PER_LAUNCH, batches.size() - b0);
+            if ((rc = launch_batch(s, mode, s->d_bins + b0, nb))) return rc;
         }
         FRMC_CUDA(cudaMemcpyAsync(s->h_brun, bd.run, sizeof(BatchRun), cudaMemcpyDeviceToHost, s->stream));
         FRMC_CUDA(cudaStreamSynchronize(s->stream));
@@ -4243,7 +4276,7 @@ int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_count
         for (int l = 0; l < launches; ++l) {
             generate_batch_kernel<<<1, 32, 0, s->stream>>>(gp, bd.run, s->d_bin, s->d_gen, s->d_atoms);
             FRMC_LAUNCH_CHECK();
-            if ((rc = launch_batch(s, mode, none, true))) return rc;
+            if ((rc = launch_batch(s, mode, nullptr, 0, true))) return rc;
         }
         FRMC_CUDA(cudaMemcpyAsync(s->h_brun, bd.run, sizeof(BatchRun), cudaMemcpyDeviceToHost, s->stream));
         FRMC_CUDA(cudaStreamSynchronize(s->stream));
