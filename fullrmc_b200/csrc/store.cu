@@ -1538,24 +1538,16 @@ __device__ __forceinline__ void zero_ints(int *p, long long n)
 // coordinates are read AFTER every earlier launch has committed (stream order), and a proposal that moves an atom an
 // accepted proposal of its own launch moved ends that launch (batch_kernel), so it is generated again from the
 // new position: the run equals the sequential one.
-struct GenShared {
-    int s_k[BATCH_MAX_PROPS], s_first[BATCH_MAX_PROPS + 1], s_g[BATCH_MAX_PROPS];
-    int s_pos[FRMC_MAX_GROUP];
-    int s_np, s_bad;
-};
-
-// (one warp of the batch kernel, at the head of every batch: the run state, the atoms and the real coordinates were written
-// by other CTAs during the previous batch, hence the .cg loads)
-__device__ __forceinline__ void generate_batch_body(const GenParams &gp, BatchRun *run, BatchIn *din, GenOut *gen,
-                                                    const float4 *atoms, GenShared &gsh)
+__global__ void generate_batch_kernel(const GenParams gp, BatchRun *__restrict__ run, BatchIn *__restrict__ din, GenOut *__restrict__ gen,
+                                      const float4 *__restrict__ atoms)
 {
-    int *s_k = gsh.s_k, *s_first = gsh.s_first, *s_g = gsh.s_g, *s_pos = gsh.s_pos;
-    int &s_np = gsh.s_np, &s_bad = gsh.s_bad;
-    const int j = threadIdx.x & 31;
-    const int base = __ldcg(&run->n_done);
+    __shared__ int s_k[BATCH_MAX_PROPS], s_first[BATCH_MAX_PROPS + 1], s_g[BATCH_MAX_PROPS];
+    __shared__ int s_pos[FRMC_MAX_GROUP];
+    __shared__ int s_np, s_bad;
+    const int j = threadIdx.x;
+    const int base = run->n_done;
     if (j == 0) s_bad = 0;
-    __syncwarp();
-    if (base >= gp.n_total || __ldcg(&run->gen_state) == 3) {
+    if (base >= gp.n_total || run->gen_state == 3) {
         if (j == 0) { din->n_prop = 0; din->n_atoms = 0; din->out_base = base; if (base >= gp.n_total) run->gen_state = 1; }
         return;
     }
@@ -1581,8 +1573,8 @@ __device__ __forceinline__ void generate_batch_body(const GenParams &gp, BatchRu
             const int r = gp.gidx[gp.goff[g] + t];
             const int pos = gp.inv[r];
             float x, y, z;
-            if (gp.pbc) { const float4 rc = __ldcg(gp.real + r); x = rc.x; y = rc.y; z = rc.z; }
-            else { const float4 rc = __ldcg(atoms + pos); x = rc.x; y = rc.y; z = rc.z; }      // non-periodic: box coordinates ARE the real ones
+            if (gp.pbc) { const float4 rc = gp.real[r]; x = rc.x; y = rc.y; z = rc.z; }
+            else { const float4 rc = atoms[pos]; x = rc.x; y = rc.y; z = rc.z; }      // non-periodic: box coordinates ARE the real ones
             const float mx = __fadd_rn(x, sr.vx), my = __fadd_rn(y, sr.vy), mz = __fadd_rn(z, sr.vz);
             float bx = mx, by = my, bz = mz;
             if (gp.pbc) transform_point(gp.rb, mx, my, mz, bx, by, bz);
@@ -1622,22 +1614,21 @@ template <int MODE, bool GEN, bool FLYT>
 __global__ void __launch_bounds__(EPI_THREADS, 1)
 batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn *__restrict__ in_arr, int n_batches, Lattice L, GridSet gs, int nEl, const ModelSet ms,
              const EpiMap em, const BatchDev bd, const CullParams cp, unsigned long long *__restrict__ bars,
-             unsigned long long *__restrict__ overflow, long long *__restrict__ stamps, BatchIn *__restrict__ in_dev,
-             GenOut *__restrict__ gen, float4 *__restrict__ real, const GenParams gp)
+             unsigned long long *__restrict__ overflow, long long *__restrict__ stamps, const BatchIn *__restrict__ in_dev,
+             const GenOut *__restrict__ gen, float4 *__restrict__ real)
 {
     extern __shared__ __align__(128) float epi_smem[];
     __shared__ __align__(16) EpiShared es;
     __shared__ BatchShared bs;
-    __shared__ __align__(16) BatchIn s_in;           // the batch's proposals, staged from device memory
-    __shared__ GenShared gsh;
     const int tid = threadIdx.x;
     // The proposals: host proposals arrive as an ARRAY of batches in device memory (in_arr[0 .. n_batches)), and ONE launch
     // works through all of them -- a launch per batch cost 16 us of launch latency, prologue and S(Q)-slab staging around
-    // 148 us of work.  Generated proposals (GEN) are drawn at the head of every batch by one warp of CTA 0
-    // (generate_batch_body -> in_dev; gen / real then carry the real coordinates to commit), n_batches batches per launch.
-    const int nb = n_batches;
+    // 148 us of work; generated proposals are drawn batch by batch by generate_batch_kernel (in_dev, one batch per launch;
+    // gen / real then carry the real coordinates to commit).
+    const int nb = GEN ? 1 : n_batches;
     if (nb <= 0) return;
-    if (!GEN && __ldcg(&bd.run->stopped)) return;    // an earlier launch of this call hit a conflict: nothing to do (uniform)
+    if (GEN && in_dev->n_prop == 0) return;          // nothing generated: the call is finished or must be re-planned (uniform)
+    if (__ldcg(&bd.run->stopped)) return;            // an earlier launch of this call hit a conflict: nothing to do (uniform)
     // debug timeline (FRMC_BATCH_STAMPS=1): globaltimer ns of CTA 0 at the phase boundaries of the LAST batch
 #define BATCH_STAMP(i) do { if (stamps && blockIdx.x == 0 && tid == 0 && (i) < BATCH_STAMP_SLOTS) { \
         unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); stamps[(i)] = (long long)gt_; } } while (0)
@@ -1655,28 +1646,14 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn *__restrict__ i
     __syncthreads();
     unsigned long long bar_target = bs.s_bar;
   for (int batch = 0; batch < nb; ++batch) {
+    const BatchIn &in = GEN ? *in_dev : in_arr[batch];
     if (batch > 0) {
-        // the previous batch is behind every CTA (its commits, the run state CTA 0 wrote); a conflict ends a launch of host
-        // proposals (the host cuts the batches again), generated steps are simply drawn again from the new positions
+        // the previous batch is behind every CTA (its commits, the run state CTA 0 wrote); a conflict ends the launch
         grid_arrive(bars);
         bar_target += gridDim.x;
         grid_wait(bars, bar_target);
-        if (!GEN && __ldcg(&bd.run->stopped)) return;        // uniform: written before the barrier
+        if (__ldcg(&bd.run->stopped)) return;        // uniform: written before the barrier
     }
-    if (GEN) {
-        if (blockIdx.x == 0 && tid < 32) generate_batch_body(gp, bd.run, in_dev, gen, atoms, gsh);
-        grid_arrive(bars);
-        bar_target += gridDim.x;
-        grid_wait(bars, bar_target);
-    }
-    {
-        const int *src = reinterpret_cast<const int *>(GEN ? in_dev : in_arr + batch);
-        int *dst = reinterpret_cast<int *>(&s_in);
-        for (int i = tid; i < (int)(sizeof(BatchIn) / sizeof(int)); i += blockDim.x) dst[i] = __ldcg(src + i);
-    }
-    __syncthreads();
-    const BatchIn &in = s_in;
-    if (GEN && in.n_prop == 0) return;               // nothing generated: the call is finished or must be re-planned (uniform)
     BATCH_STAMP(0);
     const int np = in.n_prop, na = in.n_atoms;
     // every proposal moves one atom: pair corrections between proposals of the launch are applied on the fly (CorrEv)
@@ -2330,7 +2307,7 @@ batch_kernel(float4 *__restrict__ atoms, int npad, const BatchIn *__restrict__ i
                 for (int x = 0; x < n_aj; ++x)
                     for (int t = bs.in_first[acc_j[x]] + tid; t < bs.in_first[acc_j[x] + 1]; t += blockDim.x) {
                         atoms[bs.sPos[t]] = bs.sNew[t];
-                        if (GEN && real) real[__ldcg(gen->ridx + t)] = make_float4(__ldcg(gen->mreal + 3 * t), __ldcg(gen->mreal + 3 * t + 1), __ldcg(gen->mreal + 3 * t + 2), 0.f);
+                        if (GEN && real) real[gen->ridx[t]] = make_float4(gen->mreal[3 * t], gen->mreal[3 * t + 1], gen->mreal[3 * t + 2], 0.f);
                     }
                 if (tid < ms.n) {
                     bd.run->cchi2[tid] = bs.s_chi[last][tid];
@@ -3223,10 +3200,8 @@ static int batch_prepare(frmc_store *s)
 }
 
 template <int MODE>
-static int launch_batch_t(frmc_store *s, const BatchIn *in_arr, int n_batches, bool generated, const GenParams *gpp)
+static int launch_batch_t(frmc_store *s, const BatchIn *in_arr, int n_batches, bool generated)
 {
-    GenParams gp;
-    if (gpp) gp = *gpp; else memset(&gp, 0, sizeof(gp));
     GridSet gs = make_gridset(s);
     ModelSet ms;
     memset(&ms, 0, sizeof(ms));
@@ -3249,11 +3224,11 @@ static int launch_batch_t(frmc_store *s, const BatchIn *in_arr, int n_batches, b
     gw.t2max = gs.t2hi;
     CullParams cp = make_cull(s->L, MODE, gw);
     if (g_no_cull) cp.enabled = 0;
-    BatchIn *in_dev = generated ? s->d_bin : nullptr;
-    GenOut *gen = generated ? s->d_gen : nullptr;
+    const BatchIn *in_dev = generated ? s->d_bin : nullptr;
+    const GenOut *gen = generated ? s->d_gen : nullptr;
     float4 *real = (generated && s->isPBC) ? s->d_real : nullptr;
     void *args[] = {&s->d_atoms, &npad, (void *)&in_arr, &n_batches, &s->L, &gs, &nEl, &ms, &s->epi_map, &s->bdev, &cp, &s->d_bbars, &ovf, &s->d_bstamps,
-                    &in_dev, &gen, &real, &gp};
+                    &in_dev, &gen, &real};
     // (three variants per geometry mode, not four: generated runs always take the kernel with the on-the-fly corrections)
     const void *kern = generated ? (const void *)batch_kernel<MODE, true, true>
                                  : (s->batch_fly ? (const void *)batch_kernel<MODE, false, true> : (const void *)batch_kernel<MODE, false, false>);
@@ -3268,14 +3243,14 @@ static int launch_batch_t(frmc_store *s, const BatchIn *in_arr, int n_batches, b
 }
 
 // in_arr: DEVICE array of n_batches batches of host proposals (NULL / 0 for a generated batch, which sits in s->d_bin)
-static int launch_batch(frmc_store *s, int mode, const BatchIn *in_arr, int n_batches, bool generated = false, const GenParams *gp = nullptr)
+static int launch_batch(frmc_store *s, int mode, const BatchIn *in_arr, int n_batches, bool generated = false)
 {
     switch (mode) {
-        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in_arr, n_batches, generated, gp);
-        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in_arr, n_batches, generated, gp);
-        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in_arr, n_batches, generated, gp);
-        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in_arr, n_batches, generated, gp);
-        default: return launch_batch_t<MODE_TRI_GEN>(s, in_arr, n_batches, generated, gp);
+        case MODE_IBC: return launch_batch_t<MODE_IBC>(s, in_arr, n_batches, generated);
+        case MODE_ORTHO_FAST: return launch_batch_t<MODE_ORTHO_FAST>(s, in_arr, n_batches, generated);
+        case MODE_TRI_FAST: return launch_batch_t<MODE_TRI_FAST>(s, in_arr, n_batches, generated);
+        case MODE_ORTHO_GEN: return launch_batch_t<MODE_ORTHO_GEN>(s, in_arr, n_batches, generated);
+        default: return launch_batch_t<MODE_TRI_GEN>(s, in_arr, n_batches, generated);
     }
 }
 
@@ -4298,8 +4273,11 @@ int frmc_run_generated(frmc_store *s, int n, uint64_t seed, uint64_t first_count
         }
         const int mode = current_mode(s, nullptr, nullptr);
         const int launches = std::min(64, (n - done + BATCH_MAX_PROPS - 1) / BATCH_MAX_PROPS + 1);
-        // one launch draws and resolves `launches` batches of steps (generate_batch_body at the head of every batch)
-        if ((rc = launch_batch(s, mode, nullptr, launches, true, &gp))) return rc;
+        for (int l = 0; l < launches; ++l) {
+            generate_batch_kernel<<<1, 32, 0, s->stream>>>(gp, bd.run, s->d_bin, s->d_gen, s->d_atoms);
+            FRMC_LAUNCH_CHECK();
+            if ((rc = launch_batch(s, mode, nullptr, 0, true))) return rc;
+        }
         FRMC_CUDA(cudaMemcpyAsync(s->h_brun, bd.run, sizeof(BatchRun), cudaMemcpyDeviceToHost, s->stream));
         FRMC_CUDA(cudaStreamSynchronize(s->stream));
         const BatchRun &r = *s->h_brun;
