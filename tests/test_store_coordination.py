@@ -191,3 +191,44 @@ def test_argument_errors():
         cid = store.coordination_add([np.array([1], np.int32)], [np.array([2], np.int32)], [0.0], [1.0])
         with pytest.raises(ValueError):
             store.coordination_move(cid + 1, np.array([1], np.int32), s.boxCoords[1:2])
+
+
+def test_store_pass_after_atoms_were_removed():
+    """definitions registered on the full system; after removals the engine's relative indexes address the remaining atoms
+    and the removed records take part in nothing: the store pass equals the stateless kernels on the engine's np.delete'd
+    arrays with the lists re-numbered the way the engine's collector re-numbers them"""
+    from fullrmc_b200 import synthetic
+    from fullrmc_b200.model import ModelSpec
+    from fullrmc_b200.store import DeviceStore
+    basis = np.array([[40, 0, 0], [6, 39, 0], [-4, 8, 38]], dtype=F32)
+    s = synthetic.random_system(6000, 3, basis, n_elements=3, molecule_size=2)
+    grid = synthetic.RGrid(0.0, 0.05, 160)
+    rng = np.random.default_rng(13)
+    cores, shells, lower, upper = _definitions(s, rng)
+    common = dict(elements=s.elements, n_per_element=s.numberOfAtomsPerElement, weighting=s.weighting, volume=s.volume,
+                  rho0=s.numberDensity, shell_centers=grid.shellCenters, shell_volumes=grid.shellVolumes)
+    with DeviceStore(s.boxCoords, s.basis, True, s.moleculeIndex, s.elementIndex, 3) as store:
+        gi = store.add_grid(grid.minDistance, grid.maxDistance, grid.bin, grid.hs)
+        store.add_model(gi, ModelSpec("PDF", experimental=np.zeros(grid.hs, F32), **common))
+        store.compute_data()
+        cid = store.coordination_add(cores, shells, lower, upper)
+        box = s.boxCoords.copy()
+        alive = np.arange(6000)                                       # original index of every remaining atom
+        for victim in (4000, 17, 2999, 17):
+            store.propose_amputation(victim); store.accept_amputation()
+            box, alive = np.delete(box, victim, axis=0), np.delete(alive, victim)
+        assert store.numberOfAtoms == box.shape[0]
+        new_index = np.full(6000, -1, np.int64); new_index[alive] = np.arange(alive.shape[0])
+        renum = lambda lists: [np.ascontiguousarray(new_index[a][new_index[a] >= 0], dtype=np.int32) for a in lists]
+        cores2, shells2 = renum(cores), renum(shells)
+
+        class _S(object):
+            basis, numberOfAtoms = s.basis, box.shape[0]
+
+        for step in range(10):
+            idx = np.sort(rng.choice(box.shape[0], 3, replace=False)).astype(np.int32)
+            moved = (box[idx] + rng.normal(0, 0.02, (3, 3))).astype(F32)
+            counts = store.coordination_move(cid, idx, moved).copy()
+            after = box.copy(); after[idx] = moved
+            assert np.array_equal(counts[0].astype(F32), _stateless_counts(idx, box, _S, cores2, shells2, lower, upper)), "before, step %d" % step
+            assert np.array_equal(counts[1].astype(F32), _stateless_counts(idx, after, _S, cores2, shells2, lower, upper)), "after, step %d" % step
