@@ -395,9 +395,10 @@ int frmc_import_data(frmc_store *s, int grid, const float *hintra, const float *
  * totalStandardError before / after.  chi2_out [n][n_models] (the chi2 every proposal was judged on), decisions [n]
  * (0 rejected, 1 accepted, 2 accepted within the tolerance), n_rand_used and device_ms (CUDA-event time of the
  * launches) may be NULL.  The outcome is identical to n frmc_step calls with that rule on the host.  One pass over
- * the store serves up to 32 proposals / 64 moved atoms (16 B/atom of traffic for all of them); see batch_kernel in
- * csrc/store.cu.  Models with a scale-factor refit schedule or an S(Q) slab beyond shared memory run the same
- * rule with one launch per proposal. */
+ * the store serves up to 32 proposals / 64 moved atoms (16 B/atom of traffic for all of them), and ONE launch works
+ * through all such batches of the run (up to 128 per launch); see batch_kernel in csrc/store.cu.  Scale-factor refit
+ * schedules run inside the batch kernel; models with an S(Q) slab beyond shared memory run the same rule with one
+ * launch per proposal. */
 int frmc_run_batch(frmc_store *s, int n, const int32_t *group_sizes, const int32_t *indexes, const float *moved,
                    const float *variance_sq, float tolerance, const float *rand, float *total_io,
                    float *chi2_out, int32_t *decisions, int32_t *n_rand_used, double *device_ms);
