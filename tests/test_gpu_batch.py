@@ -137,6 +137,34 @@ def test_batch_equals_sequential_device_path(name, kinds, n, sigma, tol, repeat,
     seq.close(); bat.close()
 
 
+def test_long_run_spans_several_launches():
+    """4 500 proposals = 141+ batches: more than one launch of the multi-batch kernel (128 batches each), with a repeated
+    atom every 97 proposals (a conflict ends a launch in the middle and the host cuts the rest again); chi^2 of every
+    proposal, every decision and the final state equal the sequential device path"""
+    case = TS.CASES["ortho_atomic"]
+    kinds = ["PDF", "SQ"]
+    seq, _ = TS._build(case, kinds, np.random.default_rng(3))
+    bat, _ = TS._build(case, kinds, np.random.default_rng(3))
+    var2 = np.array([1.0, 0.5], F32)
+    rng = np.random.default_rng(17)
+    total0 = host_total(seq.compute_data(), var2)
+    bat.compute_data()
+    n = 4500
+    props = make_proposals(case, rng, n, 0.02, 97)
+    rand = rng.random(n).astype(F32)
+    chis, decs, total, used = sequential_run(seq, props, total0, rand, 0.2, var2)
+    idx, moved, sizes = flatten(props)
+    l0 = bat.batch_stats()[0]
+    out = bat.run_batch(idx, moved, total0, rand, tolerance=0.2, group_sizes=sizes, variance_squared=var2)
+    assert np.array_equal(out["decisions"], decs) and np.array_equal(out["chi2"], chis)
+    assert F32(out["total"]) == F32(total) and out["rand_used"] == used
+    assert 0 < int((decs > 0).sum()) < n
+    compare_stores(seq, bat, 2)
+    launches = bat.batch_stats()[0] - l0
+    assert 2 <= launches < n // 32, "expected a few multi-batch launches, saw %d" % launches
+    seq.close(); bat.close()
+
+
 @pytest.mark.parametrize("kind", ["ortho", "tri_unwrapped", "non_periodic"])
 def test_batch_on_large_sparse_systems(kind, orc):
     """maxDistance far below the cell size: the delta pass skips most (sub-block, moved atom) pairs, most proposals
