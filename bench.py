@@ -1217,6 +1217,26 @@ def run_b200(args):
         finally:
             _lib.set_block_culling(True)
 
+    # ---- the same histogram with the chunk-level culling switched off (unit-level culling only: what the mid-round
+    #      kernel did): the evaluation count of the previous accounting and the kernel time that goes with it
+    unit_level = None
+    if world == 1 and not args.no_brute:
+        _lib.set_chunk_culling(False)
+        try:
+            with torch.cuda.stream(ext):
+                step()
+                store.set_timing(True)
+                for _ in range(3):
+                    chi2_u = step()
+                torch.cuda.synchronize()
+                ms_u, n_u = store.get_timing("full")
+                store.set_timing(False)
+            unit_level = {"kernel_ms_per_launch": ms_u / max(n_u, 1), "evaluations_per_launch": store.swept_pairs,
+                          "identical_histogram_and_chi2": bool(np.array_equal(counts.cpu().numpy(), counts_host) and np.array_equal(chi2_u, chi2)),
+                          "note": "frmc_set_chunk_culling(0): every (32 x 32) unit whose boxes are within reach is swept whole"}
+        finally:
+            _lib.set_chunk_culling(True)
+
     # ---- e2e: ONE call of the reference-facing function with HOST buffers (raw arrays up, ordering on the device,
     #      sweep, histograms back).  N > 1: rank 0's single process drives all N GPUs through the in-library path
     #      (frmc_full_pairs_histograms_coords_multi: NVLink copy of the store, shards, ncclAllReduce inside the library),
@@ -1317,12 +1337,17 @@ def run_b200(args):
                      "frac": (kernel_gevals / issue_peak) if kernel_gevals else None, "traffic": traffic,
                      "kernel_ms_per_launch": ms_kernel_launch, "evaluations_per_launch": swept_local,
                      "in_range_pairs_per_launch": in_range_pairs,
+                     "unit_level_culling_only": unit_level,
+                     "frac_counting_unit_level_evaluations": (unit_level["evaluations_per_launch"] / (ms_kernel_launch * 1e-3) / 1e9 / issue_peak)
+                                                             if (unit_level and ms_kernel_launch) else None,
                      "hit_fraction_of_evaluations": (in_range_pairs / float(swept_total)) if (in_range_pairs and swept_total) else None,
                      "note": "achieved counts ONLY the distance evaluations the boxes cannot exclude (19 issue slots each); the bin pass -- one "
                              "exact bin and one shared-memory increment per in-range pair, which no culling removes -- is not counted as "
                              "algorithmic work.  The chunk-level culling of this build removes 30 % of the evaluations of the previous "
                              "build (9.97 -> 6.99 G at cfg5) and 9 % of the time (10.2 -> 9.3 ms): the launch is faster while this "
-                             "fraction falls (0.50 -> 0.38), because a quarter of the evaluations are now hits (round 1: 9 %)",
+                             "fraction falls (0.50 -> 0.38), because a quarter of the evaluations are now hits (round 1: 9 %).  "
+                             "unit_level_culling_only = the same kernel with the chunk tests off (measured in this run); "
+                             "frac_counting_unit_level_evaluations = the work of THAT accounting done in THIS kernel's time",
                      "peak_source": "%d SMs x 128 lanes x %.0f MHz (median under load) / 19 fp32 issue slots per evaluation"
                                     % (n_sm, sm_mhz)},
     }

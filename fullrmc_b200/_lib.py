@@ -56,6 +56,7 @@ SIGNATURES = {
     "frmc_device_count": (_I, []),
     "frmc_set_edge_spill": (_I, [_I]),
     "frmc_set_block_culling": (_I, [_I]),
+    "frmc_set_chunk_culling": (_I, [_I]),
     "frmc_ctx_set_timing": (_I, [_I, _I]),
     "frmc_ctx_kernel_ms": (_I, [_I, ctypes.POINTER(ctypes.c_double)]),
     "frmc_set_device_layout": (_I, [_I]),
@@ -200,6 +201,12 @@ def set_edge_spill(on):
 def set_block_culling(on):
     """Full-histogram block culling (default on; results are identical either way).  Returns the previous setting."""
     return bool(load_library().frmc_set_block_culling(int(bool(on))))
+
+
+def set_chunk_culling(on):
+    """Chunk-level culling inside the 32-record units of the full histogram (default on; identical results either way).
+    Returns the previous setting."""
+    return bool(load_library().frmc_set_chunk_culling(int(bool(on))))
 
 
 def kernel_ms_of(call, device=None):

@@ -33,6 +33,7 @@ namespace frmc {
 
 GridParams make_grid(float rmin, float rmax, float bin, int hs);
 int g_no_cull = 0;
+static int g_no_chunk_cull = 0;     // measurement: keep the unit-level culling only (frmc_set_chunk_culling)
 int g_device_layout = 1;      // stateless full histogram: order the caller's atoms on the device (devlayout.cu)
 
 // ------------------------------------------------------------------ host: layout + row list
@@ -826,6 +827,7 @@ struct SweepArgs {
     const float2 *tab;
     unsigned long long *counts; unsigned long long *stats;
     int n_rows, n_pairs, n_items, nblocks, nEl;
+    int chunk_cull;                  // 1: test the 8-record chunks of every unit (default); 0: unit-level culling only
     Lattice L; GridParams g; CullParams cp;
 };
 
@@ -943,7 +945,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
                 // lane tests the four chunks of the unit it stands for; a unit none of whose chunks is in reach is dropped
                 // (the diagonal unit is swept whole)
                 unsigned cm = 0xFu;
-                if (A.cp.enabled && near && !tri) {
+                if (A.cp.enabled && A.chunk_cull && near && !tri) {
                     const float4 *cb = A.cbox + ((size_t)jb * (SEG_PAD / 32) + (size_t)sb) * 8;
                     float4 bx[8];
 #pragma unroll
@@ -1181,7 +1183,7 @@ int full_hist_launch(cudaStream_t stream, int sm_count, int mode, const float4 *
     A.entries = lists.entries; A.items = lists.items; A.pair_next = lists.pair_next;
     A.tab = lists.bin_table; A.counts = counts; A.stats = stats;
     A.n_rows = n_rows; A.n_pairs = n_pairs; A.n_items = lists.n_items; A.nblocks = nblocks; A.nEl = nEl;
-    A.L = L; A.g = g; A.cp = cp;
+    A.L = L; A.g = g; A.cp = cp; A.chunk_cull = g_no_chunk_cull ? 0 : 1;
     const bool hasmin = g.t2min > 0.f;      // rmin <= 0: every non-NaN d2 passes the lower test
 #define FH_CASE(M)                                                                                         \
     case M:                                                                                                \
@@ -1233,6 +1235,13 @@ extern "C" int frmc_set_block_culling(int on)
 {
     int old = !g_no_cull;
     g_no_cull = on ? 0 : 1;
+    return old;
+}
+
+extern "C" int frmc_set_chunk_culling(int on)
+{
+    int old = !g_no_chunk_cull;
+    g_no_chunk_cull = on ? 0 : 1;
     return old;
 }
 

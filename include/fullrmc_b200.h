@@ -60,6 +60,10 @@ int frmc_set_edge_spill(int on);
  * than maxDistance are not swept.  The result is identical either way (tests sweep both); on=0 forces the
  * reference's plain O(N^2) sweep, for measurement.  Returns the previous setting. */
 int frmc_set_block_culling(int on);
+/* The finer level of that culling (default on): inside every 32-record unit the sweep also skips the 8-record chunks whose
+ * own boxes are out of reach of the warp's 32 atoms (csrc/fullhist.cu: sweep_records_kernel).  on=0 keeps the unit-level
+ * culling only, for measurement (frmc_store_swept_pairs then counts whole units).  Identical results either way. */
+int frmc_set_chunk_culling(int on);
 /* Where the stateless full histogram orders the caller's atoms (default on = on the device, csrc/devlayout.cu:
  * raw arrays are uploaded as they are; off = k-d ordering on the host cores before the upload).  The histogram is
  * identical either way.  Returns the previous setting. */

@@ -250,6 +250,35 @@ def test_block_culling_skips_most_of_a_sparse_system():
     assert np.array_equal(intra, intra2) and np.array_equal(inter, inter2)
 
 
+def test_chunk_level_culling_only_removes_evaluations(orc):
+    """the finer level of the culling (8-record chunks inside the 32-record units): fewer distance evaluations, the same
+    histogram -- against the unit-level sweep and against the oracle, in a triclinic and a non-periodic system"""
+    from fullrmc_b200 import _lib, synthetic
+    from fullrmc_b200.store import DeviceStore
+    tri = np.array([[60, 0, 0], [9, 58, 0], [-7, 11, 57]], dtype=np.float32)
+    for s, pbc in ((synthetic.random_system(30000, 5, tri, n_elements=3, molecule_size=3), True),
+                   (synthetic.random_system(20000, 6, np.eye(3, dtype=np.float32), n_elements=2, isPBC=False, spread=40.0), False)):
+        st = DeviceStore(s.boxCoords, s.basis, pbc, s.moleculeIndex, s.elementIndex, s.numberOfElements)
+        g = st.add_grid(0.5, 9.0, 0.05, 170)
+        st.compute_data()
+        swept = st.swept_pairs
+        intra, inter = st.export_data(g)
+        old = _lib.set_chunk_culling(False)
+        try:
+            st.compute_data()
+            swept_units = st.swept_pairs
+            intra2, inter2 = st.export_data(g)
+        finally:
+            _lib.set_chunk_culling(old)
+            st.close()
+        assert 0 < swept < swept_units
+        assert np.array_equal(intra, intra2) and np.array_equal(inter, inter2)
+        wi, we = orc.full_pairs_histograms_coords(boxCoords=s.boxCoords, basis=s.basis, isPBC=pbc, moleculeIndex=s.moleculeIndex,
+                                                  elementIndex=s.elementIndex, numberOfElements=s.numberOfElements,
+                                                  minDistance=np.float32(0.5), maxDistance=np.float32(9.0), bin=np.float32(0.05), histSize=170)
+        assert np.array_equal(intra, wi) and np.array_equal(inter, we)
+
+
 def test_full_histogram_shards_sum_to_whole(ph):
     """the multi-GPU decomposition: per-shard partial histograms add up to the single-call result"""
     from fullrmc_b200 import synthetic
