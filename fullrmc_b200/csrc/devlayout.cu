@@ -691,7 +691,7 @@ static void dl_walk(DlTree &tree, std::vector<std::vector<DlTask>> &levels, int 
 // seg_count, bounds, finiteness, mol_span (rec / orig / inv stay empty); *d_mol_out = the device copy of the molecule
 // keys by original index (what the sweep's exact intra/inter test reads).  One stream synchronisation (element counts).
 int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
-                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out, int32_t **d_mol_out)
+                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out, int32_t **d_mol_out, bool raw_on_device)
 {
     FRMC_REQUIRE(n >= 0 && n < (1ll << 31) - 4096, FRMC_ELIMIT, "atom count %lld outside 0..2^31", (long long)n);
     FRMC_REQUIRE(nEl >= 1 && nEl <= FRMC_MAX_ELEMENTS, FRMC_ELIMIT, "numberOfElements %d outside 1..%d", nEl, FRMC_MAX_ELEMENTS);
@@ -729,8 +729,10 @@ int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *m
         // systems go through the context's page-locked scratch instead, in slices copied by a few host threads, each
         // of which queues the DMA of its own slice as soon as it is staged (20 B/atom: 1.9 -> ~0.8 ms at 10^6 atoms).
         const size_t bytes_c = sizeof(float) * 3 * (size_t)n, bytes_i = sizeof(int32_t) * (size_t)n;
-        unsigned char *pin = (n >= 65536) ? (unsigned char *)ctx_pinned(c, bytes_c + 2 * bytes_i) : nullptr;
-        if (pin) {
+        unsigned char *pin = (n >= 65536 && !raw_on_device) ? (unsigned char *)ctx_pinned(c, bytes_c + 2 * bytes_i) : nullptr;
+        if (raw_on_device) {
+            // nothing to upload: the arrays are already queued on this stream
+        } else if (pin) {
             const int parts = 4;
             std::vector<std::thread> th;
             std::vector<int> errs((size_t)parts, 0);

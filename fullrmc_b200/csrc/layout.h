@@ -52,7 +52,9 @@ int build_layout(const float *coords, int64_t n, const int32_t *mol, const int32
 // the context's scratch slots 0 / 1; `lay` receives the host-side description only (no rec / orig / inv).
 struct DeviceCtx;
 int device_layout(DeviceCtx *c, const float *coords, int64_t n, const int32_t *mol, const int32_t *el, int nEl, int isPBC,
-                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out, int32_t **d_mol_out);
+                  HostLayout &lay, float4 **d_atoms_out, uint32_t **d_orig_out, int32_t **d_mol_out, bool raw_on_device = false);
+// raw_on_device: the caller has already queued the raw arrays into the context's slots 7 (coords [3n] floats) and 8
+// (el [n] | mol [n] ints) on the context's stream (multigpu.cu: every GPU brings its slice over its own PCIe link)
 
 // One ROW of full-histogram work: I-tile [i0, i0 + 256*ni) x the J range [j0, j1) of one element pair
 // (padded positions).  ea/eb are the (segment) elements of the two ranges; when ea == eb the J range starts

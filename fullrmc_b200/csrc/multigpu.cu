@@ -152,8 +152,78 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
     uint32_t *d_orig0 = nullptr;
     int32_t *d_keys0 = nullptr;
     int rc;
+    // direct NVLink copies device 0 -> device k (without peer access cudaMemcpyPeerAsync stages through the host)
+    {
+        static std::mutex mu;
+        static bool enabled[64][64];
+        std::lock_guard<std::mutex> lock(mu);
+        for (int k = 1; k < ndev; ++k) {
+            const int a = c0->dev, b = ctx[(size_t)k]->dev;
+            if (a >= 64 || b >= 64 || enabled[a][b]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                cudaSetDevice(a);
+                if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();      // already enabled by the host program
+                cudaSetDevice(b);
+                if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
+            }
+            enabled[a][b] = true;
+        }
+    }
+    FRMC_CUDA(cudaSetDevice(c0->dev));
     if (g_device_layout) {
-        rc = device_layout(c0, coords, n, mol, el, nEl, isPBC, lay, &d_atoms0, &d_orig0, &d_keys0);
+        // The raw arrays (20 B/atom) reach device 0 over EVERY device's own PCIe link: device k stages slice k in its
+        // page-locked scratch, copies it up on its stream and forwards it to device 0 over NVLink; device 0's stream waits
+        // for the slices and orders the atoms (one link: 1.0 ms of the call at 10^6 atoms, the largest serial piece).
+        bool raw_on_device = false;
+        static const bool sliced_on = []() { const char *e = getenv("FRMC_SLICED_UPLOAD"); return !(e && atoi(e) == 0); }();
+        // (measured at 10^6 atoms: 4.1 -> 3.7 ms per call on 8 GPUs, no gain on 4, 0.5 ms SLOWER on 2 -- one staging thread per
+        //  device and the extra NVLink hop against four pipelined staging threads on one link -- hence from 5 devices on)
+        if (sliced_on && ndev >= 5 && n >= 65536 * (int64_t)ndev) {
+            float *d_c0 = (float *)ctx_buffer(c0, 7, sizeof(float) * 3 * (size_t)n);
+            int32_t *d_e0 = (int32_t *)ctx_buffer(c0, 8, sizeof(int32_t) * 2 * (size_t)n);
+            if (!d_c0 || !d_e0) return FRMC_ENOMEM;
+            int32_t *d_k0 = d_e0 + n;
+            std::vector<cudaEvent_t> up((size_t)ndev, nullptr);
+            std::vector<int> errs((size_t)ndev, 0);
+            std::vector<std::thread> th;
+            for (int k = 0; k < ndev; ++k)
+                th.emplace_back([&, k] {
+                    DeviceCtx *c = ctx[(size_t)k];
+                    if (cudaSetDevice(c->dev) != cudaSuccess) { errs[(size_t)k] = 1; return; }
+                    const int64_t a = n * k / ndev, b = n * (k + 1) / ndev;
+                    const size_t cnt = (size_t)(b - a), bc = sizeof(float) * 3 * cnt, bi = sizeof(int32_t) * cnt;
+                    unsigned char *pin = (unsigned char *)ctx_pinned(c, bc + 2 * bi);
+                    unsigned char *tmp = (k == 0) ? nullptr : (unsigned char *)ctx_buffer(c, 7, bc + 2 * bi);
+                    if (!pin || (k > 0 && !tmp)) { errs[(size_t)k] = 1; return; }
+                    memcpy(pin, coords + 3 * a, bc);
+                    memcpy(pin + bc, el + a, bi);
+                    memcpy(pin + bc + bi, mol + a, bi);
+                    bool ok = true;
+                    if (k == 0) {
+                        ok = ok && cudaMemcpyAsync(d_c0 + 3 * a, pin, bc, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+                        ok = ok && cudaMemcpyAsync(d_e0 + a, pin + bc, bi, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+                        ok = ok && cudaMemcpyAsync(d_k0 + a, pin + bc + bi, bi, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+                    } else {
+                        ok = ok && cudaMemcpyAsync(tmp, pin, bc + 2 * bi, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+                        ok = ok && cudaMemcpyPeerAsync(d_c0 + 3 * a, c0->dev, tmp, c->dev, bc, c->stream) == cudaSuccess;
+                        ok = ok && cudaMemcpyPeerAsync(d_e0 + a, c0->dev, tmp + bc, c->dev, bi, c->stream) == cudaSuccess;
+                        ok = ok && cudaMemcpyPeerAsync(d_k0 + a, c0->dev, tmp + bc + bi, c->dev, bi, c->stream) == cudaSuccess;
+                        ok = ok && cudaEventCreateWithFlags(&up[(size_t)k], cudaEventDisableTiming) == cudaSuccess;
+                        ok = ok && cudaEventRecord(up[(size_t)k], c->stream) == cudaSuccess;
+                    }
+                    if (!ok) errs[(size_t)k] = 1;
+                });
+            for (auto &t : th) t.join();
+            FRMC_CUDA(cudaSetDevice(c0->dev));
+            bool bad = false;
+            for (int k = 0; k < ndev; ++k) bad = bad || errs[(size_t)k];
+            for (int k = 1; k < ndev && !bad; ++k) bad = bad || cudaStreamWaitEvent(c0->stream, up[(size_t)k], 0) != cudaSuccess;
+            for (int k = 1; k < ndev; ++k) if (up[(size_t)k]) cudaEventDestroy(up[(size_t)k]);
+            FRMC_REQUIRE(!bad, FRMC_ECUDA, "sliced upload of the atom arrays failed: %s", cudaGetErrorString(cudaGetLastError()));
+            raw_on_device = true;
+        }
+        rc = device_layout(c0, coords, n, mol, el, nEl, isPBC, lay, &d_atoms0, &d_orig0, &d_keys0, raw_on_device);
         if (rc) return rc;
     } else {
         rc = build_layout(coords, n, mol, el, nEl, isPBC, lay);
@@ -196,24 +266,6 @@ extern "C" int frmc_full_pairs_histograms_coords_multi(int ndev, const int *devs
         if (lay.mol_span > 0) d.mol = (int32_t *)ctx_buffer(c, 6, sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1));
         if (!d.atoms || !d.orig || !d.rows || !d.bbox || !d.counts || (lay.mol_span > 0 && !d.mol)) return FRMC_ENOMEM;
         d.rc = FRMC_OK;
-    }
-    // direct NVLink copies device 0 -> device k (without peer access cudaMemcpyPeerAsync stages through the host)
-    {
-        static std::mutex mu;
-        static bool enabled[64][64];
-        std::lock_guard<std::mutex> lock(mu);
-        for (int k = 1; k < ndev; ++k) {
-            const int a = c0->dev, b = ctx[(size_t)k]->dev;
-            if (a >= 64 || b >= 64 || enabled[a][b]) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
-                cudaSetDevice(a);
-                if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();      // already enabled by the host program
-                cudaSetDevice(b);
-                if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) cudaGetLastError();
-            }
-            enabled[a][b] = true;
-        }
     }
     FRMC_CUDA(cudaSetDevice(c0->dev));
     cudaEvent_t ready;
