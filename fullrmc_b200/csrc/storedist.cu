@@ -14,7 +14,7 @@
 //                     taken at ITS moved position there) -- the exact fp32 distance arithmetic and d^2 window
 //                     thresholds of atomdist.cu; counts by atomics, hits (cell, listed atom, other atom, value)
 //                     appended to a list
-//   sd_finish_kernel  one CTA: the pairs inside the group (F before / after: upper triangle in list order), then a
+//   sd_finish_body    the LAST CTA of the sweep (ticket; one launch per move since the end of round 2): the pairs inside the group (F before / after: upper triangle in list order), then a
 //                     bitonic sort of the whole hit list by (output cell, listed atom, other atom) and one thread per
 //                     cell adding its run in that order -- the reference's float32 `+=` order, so the sums are
 //                     bit-identical to it -- and the list is re-armed for the next call
@@ -53,7 +53,7 @@ struct SdDev {                       // device state of one registered constrain
     const SdLimits *lim;
     int *counts;                     // [4][2][nT*nT]: M before, F before, M after, F after; intra then inter
     float *sums;
-    unsigned int *n_hits;            // [0] hits appended, [1] overflow flag
+    unsigned int *n_hits;            // [0] hits appended, [1] overflow flag, [2] ticket of the sweep's CTAs
     unsigned long long *keys;        // [SD_MAX_HITS] (cell << 40) | (listed atom << 32) | other atom
     float *vals;
     int *out;                        // mapped pinned host memory: [8*nT*nT] counts | [8*nT*nT] sums (bits) | overflow flag | sequence
@@ -92,13 +92,22 @@ __device__ __forceinline__ void sd_pair(float d2, bool same, int ta, int ti, int
 }
 
 template <int MODE>
+__device__ __forceinline__ void sd_finish_body(const SdMove &mv, const Lattice &L, const SdDev &S, unsigned int seq,
+                                               unsigned long long *s_key, float *s_val, const float4 *sOld, const float4 *sNew,
+                                               const int *sType, const float *s_lo, const float *s_up, const float *s_t2lo,
+                                               const float *s_t2up);
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
-sd_sweep_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, int npad, const SdMove mv, Lattice L, const SdDev S)
+sd_sweep_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ orig, int npad, const SdMove mv, Lattice L, const SdDev S, unsigned int seq)
 {
     __shared__ float4 sOld[FRMC_MAX_GROUP], sNew[FRMC_MAX_GROUP];
     __shared__ int sPos[FRMC_MAX_GROUP], sType[FRMC_MAX_GROUP];
     __shared__ float s_lo[SD_MAX_TYPES * SD_MAX_TYPES], s_up[SD_MAX_TYPES * SD_MAX_TYPES];
     __shared__ float s_t2lo[SD_MAX_TYPES * SD_MAX_TYPES], s_t2up[SD_MAX_TYPES * SD_MAX_TYPES];
+    __shared__ unsigned long long s_key[SD_MAX_HITS];      // the last CTA's sort buffers
+    __shared__ float s_val[SD_MAX_HITS];
+    __shared__ bool s_last;
     const int k = mv.k, nT = S.nT;
     for (int t = threadIdx.x; t < nT * nT; t += blockDim.x) {
         s_lo[t] = S.lim->lower[t]; s_up[t] = S.lim->upper[t]; s_t2lo[t] = S.lim->t2lower[t]; s_t2up[t] = S.lim->t2upper[t];
@@ -131,29 +140,25 @@ sd_sweep_kernel(const float4 *__restrict__ atoms, const uint32_t *__restrict__ o
             sd_pair(dist2<MODE>(nw.x, nw.y, nw.z, b.x, b.y, b.z, L), same, ta, ti, 2, t, oa, S, s_lo, s_up, s_t2lo, s_t2up);
         }
     }
+    // the last CTA to get here finishes the call (no second launch): every other CTA's counts and hits are behind its ticket
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(S.n_hits + 2, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sd_finish_body<MODE>(mv, L, S, seq, s_key, s_val, sOld, sNew, sType, s_lo, s_up, s_t2lo, s_t2up);
 }
 
+// the finishing step, run by the LAST CTA of the sweep (ticket): the moved atoms, their types and the windows are still in
+// its shared memory
 template <int MODE>
-__global__ void __launch_bounds__(1024)
-sd_finish_kernel(const float4 *__restrict__ atoms, const SdMove mv, Lattice L, const SdDev S, unsigned int seq)
+__device__ __forceinline__ void sd_finish_body(const SdMove &mv, const Lattice &L, const SdDev &S, unsigned int seq,
+                                               unsigned long long *s_key, float *s_val, const float4 *sOld, const float4 *sNew,
+                                               const int *sType, const float *s_lo, const float *s_up, const float *s_t2lo,
+                                               const float *s_t2up)
 {
-    __shared__ unsigned long long s_key[SD_MAX_HITS];
-    __shared__ float s_val[SD_MAX_HITS];
-    __shared__ float4 sOld[FRMC_MAX_GROUP], sNew[FRMC_MAX_GROUP];
-    __shared__ int sType[FRMC_MAX_GROUP];
-    __shared__ float s_lo[SD_MAX_TYPES * SD_MAX_TYPES], s_up[SD_MAX_TYPES * SD_MAX_TYPES];
-    __shared__ float s_t2lo[SD_MAX_TYPES * SD_MAX_TYPES], s_t2up[SD_MAX_TYPES * SD_MAX_TYPES];
     const int k = mv.k, nT = S.nT, tid = threadIdx.x;
-    for (int t = tid; t < nT * nT; t += blockDim.x) {
-        s_lo[t] = S.lim->lower[t]; s_up[t] = S.lim->upper[t]; s_t2lo[t] = S.lim->t2lower[t]; s_t2up[t] = S.lim->t2upper[t];
-    }
-    for (int t = tid; t < k; t += blockDim.x) {
-        const float4 o = atoms[mv.pos[t]];
-        sOld[t] = o;
-        sNew[t] = make_float4(mv.moved[3 * t], mv.moved[3 * t + 1], mv.moved[3 * t + 2], o.w);
-        sType[t] = S.type_pos[mv.pos[t]];
-    }
-    __syncthreads();
     // F: full_atomic_distances_coords on the group alone (atomic_distances.pyx:500-567): listed atom a, others b > a in
     // list order; the "other atom" of the key is the position in the list
     for (int e = tid; e < k * k; e += blockDim.x) {
@@ -208,7 +213,7 @@ sd_finish_kernel(const float4 *__restrict__ atoms, const SdMove mv, Lattice L, c
     __syncthreads();
     if (tid == 0) {
         S.out[2 * n_cells] = (int)(*reinterpret_cast<volatile unsigned int *>(S.n_hits + 1));
-        S.n_hits[0] = 0u; S.n_hits[1] = 0u;
+        S.n_hits[0] = 0u; S.n_hits[1] = 0u; S.n_hits[2] = 0u;
         __threadfence_system();
         *reinterpret_cast<volatile int *>(S.out + 2 * n_cells + 1) = (int)seq;   // the host spins on this word
     }
@@ -353,9 +358,7 @@ extern "C" int frmc_store_distance_move(frmc_store *s, int id, const int32_t *in
     const int mode = choose_mode_from_bounds(v.L.b, v.isPBC, lo, hi);
     const int cells = h.dev.nT * h.dev.nT;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((v.npad + 255) / 256, (int64_t)v.sm_count * 8));
-#define SD_LAUNCH(M) do { \
-        sd_sweep_kernel<M><<<grid, 256, 0, v.stream>>>(v.atoms, v.orig, (int)v.npad, mv, v.L, h.dev); \
-        sd_finish_kernel<M><<<1, 1024, 0, v.stream>>>(v.atoms, mv, v.L, h.dev, seq); } while (0)
+#define SD_LAUNCH(M) sd_sweep_kernel<M><<<grid, 256, 0, v.stream>>>(v.atoms, v.orig, (int)v.npad, mv, v.L, h.dev, seq)
     switch (mode) {
         case MODE_IBC: SD_LAUNCH(MODE_IBC); break;
         case MODE_ORTHO_FAST: SD_LAUNCH(MODE_ORTHO_FAST); break;
@@ -365,7 +368,7 @@ extern "C" int frmc_store_distance_move(frmc_store *s, int id, const int32_t *in
     }
 #undef SD_LAUNCH
     FRMC_LAUNCH_CHECK();
-    g_launch_count += 2;
+    g_launch_count += 1;
     // the finishing CTA writes the results into mapped pinned memory and then the sequence word: spin on it instead of
     // synchronising the stream (falls back to a stream query so that a failed launch surfaces)
     volatile int *seq_word = h.h_out + 16 * cells + 1;
