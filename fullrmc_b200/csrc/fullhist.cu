@@ -622,8 +622,11 @@ __device__ __forceinline__ void sweep_unit(const float4 *__restrict__ sJu, float
             // eight records in flight: loads first, then eight independent distance chains, then the pushes
             float4 a[8];
             float d2[8];
+            // (32-bit shared-window address in a register: a generic pointer costs a window-base computation per chunk)
+            const uint32_t ja = fh_smem_u32(sJu) + 128u * (uint32_t)c;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = sJu[c * 8 + u];
+            for (int u = 0; u < 8; ++u)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ja + 16u * (uint32_t)u));
 #pragma unroll
             for (int u = 0; u < 8; ++u) d2[u] = dist2_unit<MODE, NOWRAP>(xi, yi, zi, a[u].x, a[u].y, a[u].z, L);
 #pragma unroll
