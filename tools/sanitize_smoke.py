@@ -23,6 +23,12 @@ for n, basis, pbc in ((9000, np.diag([70.0, 66.0, 72.0]).astype(np.float32), Tru
     cn = np.zeros(2, np.float32)
     ac.multi_atoms_coord_number_coords(np.arange(0, n, 7, dtype=np.int32), s.boxCoords, s.basis, pbc, cores, shells, [0.5, 1.0], [3.0, 4.0], as_core, in_shell, cn)
     print("coordination", cn)
+# nodes of more than 20 000 points: the multi-CTA splits of the device-side ordering (dl_whist / dl_wcut / dl_wscatter), full
+# leaves (bitonic sort), the sweep-record pass (order inside the sub-blocks, chunk boxes) and the chunk-level culling
+s = synthetic.random_system(50000, 9, np.diag([120.0, 118.0, 121.0]).astype(np.float32), n_elements=2)
+kw = dict(s.hist_kwargs(), minDistance=np.float32(0.0), maxDistance=np.float32(3.0), bin=np.float32(0.05), histSize=60)
+hi, he = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, **kw)
+print("full hist (wide splits)", 50000, hi.sum() + he.sum())
 if os.environ.get("SAN_SKIP_STORE"):
     print("done (stateless kernels only)"); sys.exit(0)
 s = synthetic.random_system(20000, 5, np.diag([60.0, 60.0, 60.0]).astype(np.float32), n_elements=2)
