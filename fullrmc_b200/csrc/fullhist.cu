@@ -851,6 +851,7 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
     float4 *sJ = reinterpret_cast<float4 *>(wbase + V2_Q_BYTES);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wbase + V2_MBAR_OFF);
     __shared__ int s_tasks, s_again, s_p0;
+    __shared__ int s_skip[2];
     __shared__ SlowCtx s_slow;
 
     for (int c = tid; c < nsh; c += V2_THREADS) sh[c] = 0u;
@@ -905,8 +906,14 @@ __global__ void __launch_bounds__(V2_THREADS, 2) full_hist_warp_kernel(const Swe
         const bool cross = (w0row.ea != w0row.eb);
         slab_ab = w0row.ea * A.nEl + w0row.eb; slab_ba = w0row.eb * A.nEl + w0row.ea;
         W.off_swap = cross ? 4u * (uint32_t)g.hs : 0u;
-        if (tid == 0) { s_slow.slab_ab = slab_ab; s_slow.slab_ba = slab_ba; s_slow.cross = cross ? 1 : 0; }
+        if (tid == 0) {
+            s_slow.slab_ab = slab_ab; s_slow.slab_ba = slab_ba; s_slow.cross = cross ? 1 : 0;
+            // a pair whose tasks have all been handed out is left at once (one barrier instead of three and a global atomic
+            // per warp: a CTA that has run out of work walks through up to 14 such pairs at the end of the launch)
+            s_skip[v & 1] = (*(volatile int *)&A.pair_next[p] >= ntasks) ? 1 : 0;
+        }
         __syncthreads();                          // the slow path's view of the pair; the previous pair's flush is behind us
+        if (s_skip[v & 1]) continue;
         bool again = true;
         while (again) {
             // ---- this warp's tasks of the pair
