@@ -48,6 +48,7 @@ class DeviceBackend(object):
         self.elementsIndex = np.ascontiguousarray(elementsIndex, dtype=np.int32)
         self.accepted = 0            # the engine's accepted-move count (refit and shape-refresh schedules)
         self._move = None            # (indexes, moved) of the proposal being evaluated
+        self._move_src = None        # the argument objects themselves (identity shortcut within one step)
         self._chi2 = None            # chi^2 per model of the staged proposal
         self._resolved = True
         self._dirty = True           # committed data need a compute_data pass
@@ -88,12 +89,20 @@ class DeviceBackend(object):
         # compute_before_move needs no device work of its own: the delta pass forms
         # after-minus-before in one sweep (PairDistributionConstraints.py:1053-1078 + :1095-1120)
         self._compute_data()
+        # every constraint of a step is handed the SAME index object by the engine: seen once, nothing to compare
+        # (the objects themselves are kept in _move_src, so an `is` can only match a live, unchanged argument of this step)
+        if self._move is not None and self._move_src is not None and self._move_src[0] is relativeIndexes:
+            return
         idx = np.ascontiguousarray(relativeIndexes, dtype=np.int32)
         if self._move is None or not np.array_equal(self._move[0], idx):
             self._move = (idx, None)
+            self._move_src = (relativeIndexes, None)
             self._chi2 = None
 
     def _after(self, relativeIndexes, movedBoxCoordinates):
+        if (self._chi2 is not None and self._move_src is not None and self._move_src[0] is relativeIndexes and
+                self._move_src[1] is movedBoxCoordinates):
+            return self._chi2                        # the second, third ... constraint of the step: already evaluated
         idx = np.ascontiguousarray(relativeIndexes, dtype=np.int32)
         moved = np.ascontiguousarray(movedBoxCoordinates, dtype=np.float32)
         same = (self._chi2 is not None and self._move is not None and self._move[1] is not None and
@@ -103,6 +112,7 @@ class DeviceBackend(object):
                 raise RuntimeError("previous move was neither accepted nor rejected")
             self._chi2 = self.store.propose(idx, moved).copy()
             self._move = (idx, moved)
+            self._move_src = (relativeIndexes, movedBoxCoordinates)
             self._resolved = False
         return self._chi2
 
@@ -114,6 +124,7 @@ class DeviceBackend(object):
                 self.accepted += 1
             self._resolved = True
             self._move = None
+            self._move_src = None
             self._chi2 = None
 
     # -------------------------------------------------------------- atom removal (Engine.py:3231-3276, :758-797)
