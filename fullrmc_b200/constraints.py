@@ -110,7 +110,7 @@ class DeviceBackend(object):
         if not same:
             if not self._resolved:
                 raise RuntimeError("previous move was neither accepted nor rejected")
-            self._chi2 = self.store.propose(idx, moved).copy()
+            self._chi2 = self.store.propose(idx, moved)          # (a copy already)
             self._move = (idx, moved)
             self._move_src = (relativeIndexes, movedBoxCoordinates)
             self._resolved = False

@@ -53,6 +53,9 @@ class DeviceStore(object):
         self._chi2 = np.zeros(8, dtype=_F32)
         self._chi2_ptr = L.ptr(self._chi2, L.c_f32p)
         self._step_fn = self._lib.frmc_step
+        # frmc_propose once more with plain addresses for the array arguments (no ctypes cast per call: see step())
+        self._propose_fn = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            L.c_f32p)(("frmc_propose", self._lib))
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -177,13 +180,18 @@ class DeviceStore(object):
     # ------------------------------------------------------------------ per-move path
     def propose(self, indexes, movedBoxCoordinates):
         """compute_before_move + compute_after_move in one pass; returns chi^2-after per model."""
-        idx = np.ascontiguousarray(indexes, dtype=_I32)
-        moved = np.ascontiguousarray(movedBoxCoordinates, dtype=_F32)
+        idx, moved = indexes, movedBoxCoordinates
+        if not (type(idx) is np.ndarray and idx.dtype == _I32 and idx.flags.c_contiguous):
+            idx = np.ascontiguousarray(idx, dtype=_I32)
+        if not (type(moved) is np.ndarray and moved.dtype == _F32 and moved.flags.c_contiguous):
+            moved = np.ascontiguousarray(moved, dtype=_F32)
         if moved.shape != (idx.shape[0], 3):
             raise ValueError("movedBoxCoordinates must be (k,3)")
-        L.check(self._lib.frmc_propose(self._handle, L.ptr(idx, L.c_i32p), idx.shape[0], L.ptr(moved, L.c_f32p),
-                                       L.ptr(self._chi2, L.c_f32p)), "propose")
-        return self._chi2[:self.n_models].copy()
+        rc = self._propose_fn(self._handle, idx.__array_interface__["data"][0], idx.shape[0], moved.__array_interface__["data"][0],
+                              self._chi2_ptr)
+        if rc < 0:
+            L.check(rc, "propose")
+        return self._chi2[:len(self._models)].copy()
 
     def step(self, previous, indexes, movedBoxCoordinates):
         """Resolve the staged proposal (previous: True accept / False reject / None nothing staged)
