@@ -27,6 +27,10 @@ box[:50] = 0.0; box[50:100] = -0.0                    # ties and both zeros
 el = rng.integers(0, 3, n).astype(np.int32)
 mol = (np.arange(n) // 3).astype(np.int32)
 cases = [(s.boxCoords, s.moleculeIndex, s.elementIndex, s.numberOfElements, 1) for s in systems] + [(box, mol, el, 3, 0)]
+# one element, sizes around the thresholds of the multi-CTA split (20 000 points per node, chunks of 4 096) and of the leaves
+for m in (1000, 19999, 20000, 20001, 20481, 24576, 65536, 81921):
+    b1 = rng.random((m, 3)).astype(np.float32)
+    cases.append((b1, np.arange(m, dtype=np.int32), np.zeros(m, np.int32), 1, 1))
 for coords, mol, el, nEl, pbc in cases:
     n = coords.shape[0]
     cap = n + 256 * nEl
@@ -54,7 +58,7 @@ def _layout_digests(**env):
 
 def test_wide_split_and_bitonic_leaves_build_the_same_store():
     base = _layout_digests(FRMC_WIDE_SPLIT="0", FRMC_LEAF_FAST="0")
-    assert len(base) == 3
+    assert len(base) == 11
     assert _layout_digests(FRMC_WIDE_SPLIT="1", FRMC_LEAF_FAST="0") == base
     assert _layout_digests(FRMC_WIDE_SPLIT="0", FRMC_LEAF_FAST="1") == base
     assert _layout_digests() == base
