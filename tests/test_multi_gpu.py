@@ -64,3 +64,20 @@ def test_multi_device_call_at_scale():
     finally:
         del os.environ["FULLRMC_B200_DEVICES"]
     assert np.array_equal(one[0], every[0]) and np.array_equal(one[1], every[1])
+
+
+def test_sliced_upload_on_five_or_more_devices():
+    """from 5 devices on, the raw arrays reach device 0 in slices over every device's own PCIe link (csrc/multigpu.cu); a
+    molecular system of 600 000 atoms (the molecule keys travel the same way): identical to the one-device call"""
+    from fullrmc_b200 import synthetic
+    from fullrmc_b200.Core import pairs_histograms as ph
+    devices = _devices()
+    if len(devices) < 5:
+        pytest.skip("needs at least 5 devices")
+    basis = np.array([[190, 0, 0], [12, 186, 0], [-9, 15, 188]], dtype=np.float32)
+    s = synthetic.random_system(600000, 4, basis, n_elements=3, molecule_size=3)
+    kw = dict(s.hist_kwargs(), minDistance=np.float32(0.0), maxDistance=np.float32(6.0), bin=np.float32(0.05), histSize=120)
+    one = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, **kw)
+    every = ph.full_pairs_histograms_coords(boxCoords=s.boxCoords, _devices=devices, **kw)
+    assert np.array_equal(one[0], every[0]) and np.array_equal(one[1], every[1])
+    assert one[0].sum() > 0 and one[1].sum() > 0
